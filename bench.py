@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the Lisec VoxelNet front end (voxelize + VFE + dense-grid scatter) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload = BASELINE.json configs[1]: a batch of 8 synthetic Lyft-shaped sweeps (100 k points each) per GPU, float32
+grid [8,8,200,400,64] (1.31 GB written per step). A "step" is one pass of the hot path over one batch. Sweeps are
+independent units: ranks shard them with no data-path collective (weak scaling: 8 sweeps per GPU per step).
+
+One JSON line on stdout (rank 0). `value` = sweeps/s with the points already in HBM; `e2e` = the same through the
+host-buffer entry point (H2D of the points and D2H of the per-sweep voxel counts inside the timed region);
+`roofline` = the dominant kernel (dense-grid writer) against the measured HBM copy bandwidth;
+`cpu_baseline` = the reference's CPU formulation (oracle port) timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SWEEPS_PER_GPU = 8
+POINTS_PER_SWEEP = 100_000
+GRID = (8, 200, 400)
+C3 = 64
+N_BATCHES = 14  # distinct input batches rotated through: 14 x 9.6 MB of points > the 126 MB L2
+METRIC = "lidar sweeps/sec (voxelize+VFE+scatter)"
+REF = dict(xSize=0.5, ySize=0.25, zSize=0.25, sampleSize=35, maxVoxelX=100, maxVoxelY=200, maxVoxelZ=8)
+WORKLOAD = ("configs[1]: batch of 8 synthetic Lyft-shaped sweeps x 100k points per GPU, voxelization + VFE + "
+            "dense-grid scatter, f32 grid [8,8,200,400,64]")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- CPU reference formulation (oracle port) ---------------------------------------------------------------
+def cpu_reference_time_per_sweep(points, vox_fraction, slab_cells_x, pack):
+    """Seconds per sweep of the reference's CPU path, from a bounded sample:
+       t_vox  literal-loop VFE_preprocessing (model_training.py:112-152) on the first `vox_fraction` of the points,
+              scaled by 1/vox_fraction (the loops are linear in points and voxels);
+       t_vfe  the VFE stack on a dense [1, slab_cells_x, 400, 35, 6] slab (the reference evaluates all 8*200*400*35
+              slots, model_training.py:229-235 on sparse.to_dense output), scaled to the full 8*200 planes."""
+    from oracle import lisec_oracle as O
+
+    n = max(1, int(len(points) * vox_fraction))
+    t0 = time.perf_counter()
+    st = O.vfe_preprocessing_loops(points[:n], sampler="first_T", **REF)
+    t_vox = (time.perf_counter() - t0) / (n / len(points))
+    ind = np.asarray(st.indices, dtype=np.int64).reshape(-1, 5)
+    val = np.asarray(st.values, dtype=np.float32)
+    t0 = time.perf_counter()
+    dense = np.zeros((1, slab_cells_x, 400, 35, 6), dtype=np.float32)  # densify: sparse.to_dense on the slab
+    m = (ind[:, 0] == 1) & (ind[:, 1] < slab_cells_x) if len(ind) else np.zeros(0, bool)
+    if m.any():
+        dense[0, ind[m, 1], ind[m, 2], ind[m, 3], ind[m, 4]] = val[m]
+    out = O.vfe_forward(dense, pack, np.float32)
+    t_vfe = (time.perf_counter() - t0) * (8 * 200 / slab_cells_x)
+    assert out.shape == (1, slab_cells_x, 400, 64)
+    return t_vox, t_vfe
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    from lisec_b200 import synth
+    from lisec_b200.weights import synthetic_vfe_pack
+
+    pack = synthetic_vfe_pack(0)
+    pts = synth.lyft_like_sweep(POINTS_PER_SWEEP, seed=0)
+    cores = os.cpu_count() or 1
+    frac, slab = 0.1, 50
+    for _ in range(args.warmup):
+        cpu_reference_time_per_sweep(pts, frac / 4, 10, pack)
+    per_sweep = []
+    t_begin = time.perf_counter()
+    for _ in range(args.steps):
+        tv, tf = cpu_reference_time_per_sweep(pts, frac, slab, pack)
+        per_sweep.append(tv + tf)
+    wall = time.perf_counter() - t_begin
+    sec = float(np.mean(per_sweep))
+    value = 1.0 / sec
+    sample = ("per step: literal-loop voxelizer on 10%% of one 100k-point sweep (x10) + dense VFE stack on a "
+              "[1,%d,400,35,6] slab (x%d) -> seconds per sweep; numpy float32, BLAS threads" % (slab, 8 * 200 // slab))
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": "sweeps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sweeps_per_gpu": SWEEPS_PER_GPU, "points_per_sweep": POINTS_PER_SWEEP},
+        "points_per_s": value * POINTS_PER_SWEEP,
+        "cpu_baseline": {"value": value, "unit": "sweeps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- native arm ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    from lisec_b200 import Frontend, synth
+    from lisec_b200.weights import synthetic_vfe_pack
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun with --nproc-per-node %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    pack = synthetic_vfe_pack(0)
+    fe = Frontend(device=local, max_points=SWEEPS_PER_GPU * POINTS_PER_SWEEP, max_sweeps=SWEEPS_PER_GPU)
+    fe.set_weights(pack)
+
+    # synthetic inputs: N_BATCHES distinct batches per rank (seeds disjoint across ranks), pinned on the host and
+    # resident on the device. 8 distinct sweeps per rank, re-ordered per batch: same statistics, different bytes.
+    base = [synth.lyft_like_sweep(POINTS_PER_SWEEP, seed=rank * SWEEPS_PER_GPU + s) for s in range(SWEEPS_PER_GPU)]
+    offsets = np.arange(SWEEPS_PER_GPU + 1, dtype=np.int64) * POINTS_PER_SWEEP
+    host_batches, dev_batches = [], []
+    rng = np.random.default_rng(1234 + rank)
+    for b in range(N_BATCHES):
+        order = np.roll(np.arange(SWEEPS_PER_GPU), b)
+        arr = np.concatenate([base[i][rng.permutation(POINTS_PER_SWEEP)] if b else base[i] for i in order])
+        t = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+        host_batches.append(t)
+        dev_batches.append(t.cuda())
+    grid = fe.new_grid(SWEEPS_PER_GPU)
+    points_bytes = SWEEPS_PER_GPU * POINTS_PER_SWEEP * 12
+    grid_bytes = grid.numel() * grid.element_size()
+
+    def step(i):
+        fe.forward(dev_batches[i % N_BATCHES], offsets, out=grid)
+
+    def step_e2e(i):
+        fe.forward_host(host_batches[i % N_BATCHES], offsets, out=grid)
+        return fe.counts()  # D2H of per-sweep voxel counts + totals; synchronises the stream
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    ev1.record()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = fe.last_launch_count * args.steps
+
+    # dominant kernel, timed alone on the launching stream: the dense-grid writer
+    fe.voxelize(dev_batches[0], offsets)
+    feat = fe.vfe()
+    n_k = max(5, min(args.steps, 20))
+    for _ in range(3):
+        fe.scatter(feat, out=grid)
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(n_k):
+        fe.scatter(feat, out=grid)
+    k1.record()
+    torch.cuda.synchronize()
+    ms_kernel = k0.elapsed_time(k1) / n_k
+    # the other two stages, for the per-stage breakdown
+    stages = {}
+    for name, fn in (("voxelize", lambda: fe.voxelize(dev_batches[0], offsets)), ("vfe", lambda: fe.vfe(out=feat))):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n_k):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        stages[name + "_ms"] = a.elapsed_time(b) / n_k
+    stages["scatter_ms"] = ms_kernel
+    clocks = sampler.stop() if sampler else None
+
+    # end to end through the host-buffer entry point
+    for i in range(min(args.warmup, 3)):
+        step_e2e(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        per, n_vox, n_in, n_oor, n_nf = step_e2e(i)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+
+    if rank == 0:
+        hbm_peak, peak_src = peaks()
+        total_sweeps = SWEEPS_PER_GPU * world * args.steps
+        value = total_sweeps / (ms_total * 1e-3)
+        e2e_value = total_sweeps / (ms_e2e * 1e-3)
+        achieved = grid_bytes / (ms_kernel * 1e-3) / 1e9
+        step_alg_bytes = points_bytes + grid_bytes  # 12*P + nz*nx*ny*C3*4 per sweep, x8 sweeps
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "grid_write_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sweeps_per_gpu": SWEEPS_PER_GPU, "points_per_sweep": POINTS_PER_SWEEP,
+                       "parallelism": "sweeps sharded over %d GPU(s), no data-path collective" % world,
+                       "l2": "1.31 GB grid written per step (10x L2); inputs rotate over %d distinct batches "
+                             "(%d MB > L2)" % (N_BATCHES, N_BATCHES * points_bytes // 2**20)},
+            "points_per_s": value * POINTS_PER_SWEEP,
+            "voxels_per_step": int(n_vox), "points_in_range_per_step": int(n_in),
+            "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": points_bytes,
+                    "d2h_bytes_per_step": 8 * 8 + 4 * (SWEEPS_PER_GPU + 1), "ms_per_step": ms_e2e / args.steps,
+                    "result": "per-sweep voxel counts + totals (the grid stays on the GPU for the Conv3D)"},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "grid_write_f32_c64", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": grid_bytes,
+                         "ms_per_launch": ms_kernel},
+            "roofline_step": {"bound": "hbm", "algorithmic_bytes_per_step": step_alg_bytes,
+                              "achieved": step_alg_bytes / (ms_total / args.steps * 1e-3) / 1e9, "peak": hbm_peak,
+                              "unit": "GB/s",
+                              "frac": step_alg_bytes / (ms_total / args.steps * 1e-3) / 1e9 / hbm_peak},
+            "stages": stages,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            pts0 = base[0]
+            t_vox, t_vfe = cpu_reference_time_per_sweep(pts0, 1.0, 200, pack)
+            line["cpu_baseline"] = {
+                "value": 1.0 / (t_vox + t_vfe), "unit": "sweeps/s", "cores": os.cpu_count() or 1, "kind": "port",
+                "seconds_voxelize": t_vox, "seconds_dense_vfe": t_vfe,
+                "sample": "1 of the 8 sweeps: literal-loop voxelizer on all 100k points (1 core, pure Python as in "
+                          "the reference) + dense VFE stack on z-plane 1 of 8 (x8), numpy float32 with BLAS threads",
+            }
+        print(json.dumps(line), flush=True)
+    fe.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = 3 if args.steps is None else args.steps
+        args.warmup = 1 if args.warmup is None else args.warmup
+        run_reference(args)
+    else:
+        args.steps = 30 if args.steps is None else args.steps
+        args.warmup = max(3, 5 if args.warmup is None else args.warmup)
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,180 @@
+/*
+ * lisec_b200.h — C ABI of liblisec_b200.so: the B200-native VoxelNet front end of bot15498/Lisec.
+ *
+ * One data-parallel hot path, and nothing else:
+ *     points (n,3)  ->  point-to-voxel grouping  ->  stacked VFE  ->  dense [N,nz,nx,ny,C3] voxel grid
+ *
+ * Each entry point names the reference interface it replaces (file:line into the reference checkout).
+ * The reference has no FFI of its own (it is pure Python + Keras); the binding a maintainer would add is a
+ * ctypes stub, shown in INTEGRATION.md and shipped as lisec_b200/_native.py.
+ *
+ * Conventions
+ *   - every function returns LISEC_OK (0) or a negative lisec_status; nothing throws, aborts or prints;
+ *     lisec_last_error(h) returns the text of the last failure on that handle.
+ *   - "device pointer" = CUDA global memory on the handle's device, caller-owned. "host pointer" = ordinary
+ *     (preferably pinned) host memory. The library owns only the workspace it allocates in lisec_create().
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream). All device work is
+ *     enqueued on it; functions marked [async] return before the work has finished.
+ *   - one handle = one CUDA device; calls on one handle are not re-entrant; distinct handles are independent
+ *     (one per GPU is what the multi-GPU sweep sharding uses). No global mutable state.
+ *   - there is no CPU fallback: without a usable CUDA device lisec_create() fails with LISEC_ERR_CUDA.
+ */
+#ifndef LISEC_B200_H_
+#define LISEC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LISEC_ABI_VERSION 1
+#define LISEC_MAX_SWEEPS 64 /* sweeps per call (sweep_offsets travels as a kernel parameter) */
+
+typedef enum lisec_status {
+  LISEC_OK = 0,
+  LISEC_ERR_BAD_ARG = -1,   /* null pointer, negative size, unsorted sweep_offsets ... */
+  LISEC_ERR_BAD_CONFIG = -2,/* unsupported grid / widths / dtype */
+  LISEC_ERR_CAPACITY = -3,  /* more points or sweeps than the handle was created for */
+  LISEC_ERR_CUDA = -4,      /* a CUDA runtime call failed; see lisec_last_error() */
+  LISEC_ERR_STATE = -5,     /* call order violated (e.g. VFE before weights were set) */
+  LISEC_ERR_UNSUPPORTED = -6
+} lisec_status;
+
+typedef enum lisec_dtype {
+  LISEC_F32 = 0,
+  LISEC_F64 = 1,
+  LISEC_BF16 = 2
+} lisec_dtype;
+
+/*
+ * Shapes and caps. The first seven fields are exactly the positional arguments of the reference's
+ *   VFE_preprocessing(points, xSize, ySize, zSize, sampleSize, maxVoxelX, maxVoxelY, maxVoxelZ)
+ * (model_training.py:112; called with Constants.py:7-20 values at Predict.py:21-28, model_training.py:270-277).
+ * The grid is nz = max_voxel_z, nx = 2*max_voxel_x, ny = 2*max_voxel_y (model_training.py:151-152).
+ */
+typedef struct lisec_config {
+  double voxel_x, voxel_y, voxel_z;  /* xSize, ySize, zSize            (Constants.py:7-9: 0.5, 0.25, 0.25) */
+  int32_t sample_size;               /* sampleSize = T                 (Constants.py:20: 35)               */
+  int32_t max_voxel_x;               /* maxVoxelX = nx/2               (100)                               */
+  int32_t max_voxel_y;               /* maxVoxelY = ny/2               (200)                               */
+  int32_t max_voxel_z;               /* maxVoxelZ = nz                 (8)                                 */
+  int32_t c1, c2, c3;                /* VFE-1 / VFE-2 / FCN output widths (model_training.py:231-233: 16, 32, 64) */
+  int32_t grid_dtype;                /* lisec_dtype of the dense grid: LISEC_F32 or LISEC_BF16             */
+  int32_t max_sweeps;                /* capacity: sweeps per call, <= LISEC_MAX_SWEEPS                     */
+  int64_t max_points;                /* capacity: points per call, summed over its sweeps                  */
+  int32_t device;                    /* CUDA device ordinal                                                */
+  int32_t reserved;
+} lisec_config;
+
+/*
+ * VFE parameters in Keras layout and creation order (model_training.py:229-235):
+ *   dense    kernel (6,  c1)   + batch_normalization   {gamma, beta, moving_mean, moving_variance}[c1]
+ *   dense_1  kernel (2*c1, c2) + batch_normalization_1 {...}[c2]       rows 0..c1-1 multiply the POOLED half
+ *   dense_2  kernel (2*c2, c3) + batch_normalization_2 {...}[c3]       rows 0..c2-1 multiply the POOLED half
+ * Kernels are row-major (C_in, C_out), bias-free (model_training.py:184). BatchNormalization uses
+ * bn_epsilon (Keras default 1e-3, model_training.py:171). All pointers are HOST pointers to float32.
+ */
+typedef struct lisec_vfe_weights {
+  const float* dense_kernel[3];
+  const float* bn_gamma[3];
+  const float* bn_beta[3];
+  const float* bn_mean[3];
+  const float* bn_var[3];
+  float bn_epsilon;
+  int32_t reserved;
+} lisec_vfe_weights;
+
+typedef struct lisec_handle lisec_handle;
+
+/* ---- lifetime ---------------------------------------------------------------------------------------- */
+
+int32_t lisec_abi_version(void);
+
+/* Allocates every workspace once (cell tables, point lists, voxel rows). Replaces nothing in the reference
+ * (which re-creates Python dicts per call, model_training.py:113,128); exists so the hot path never allocates. */
+/* On failure *out is still a valid (inert) handle so lisec_last_error(*out) explains why; free it with lisec_destroy(). */
+int32_t lisec_create(const lisec_config* cfg, lisec_handle** out);
+void lisec_destroy(lisec_handle* h);
+const char* lisec_last_error(const lisec_handle* h);
+/* Bytes of device workspace owned by the handle. */
+int64_t lisec_workspace_bytes(const lisec_handle* h);
+
+/* Replaces load_model(...)/createModel(...) for the first 23 Keras layers (Predict.py:51-52,
+ * model_training.py:229-235, 337-338). Folds BN to (scale, shift), uploads, and recomputes c_empty — the C3-vector
+ * the reference's unmasked network produces for a voxel holding only zero rows. Synchronous. */
+int32_t lisec_set_vfe_weights(lisec_handle* h, const lisec_vfe_weights* w, void* stream);
+/* Device-to-host copy of c_empty (c3 floats, always float32). Synchronous. */
+int32_t lisec_get_c_empty(lisec_handle* h, float* c_empty_host);
+
+/* ---- a1-a3: get_voxel + VFE_preprocessing phases 1-2 (model_training.py:103-142) ---------------------- */
+
+/*
+ * [async] Point -> voxel grouping for n_sweeps concatenated sweeps.
+ *   points            device pointer, row-major (n,3) of points_dtype (LISEC_F32 or LISEC_F64), 16-byte aligned
+ *   sweep_offsets     HOST pointer, n_sweeps+1 non-decreasing int64; sweep s owns points [off[s], off[s+1])
+ * Key = (floor(x/voxel_x), floor(y/voxel_y), floor(z/voxel_z)) in float64, strict range test on both sides,
+ * shift by (+max_voxel_x, +max_voxel_y, 0)  (model_training.py:103-107, 117-122). Per voxel the point list is
+ * in ascending point order (:123-126); the kept rows are the first min(count, T) of it — the deterministic
+ * replacement for np.random.choice at :132. Non-finite points are dropped and counted.
+ * Results stay in the handle's workspace; read them back with lisec_voxels_export().
+ */
+int32_t lisec_voxelize(lisec_handle* h, const void* points, int32_t points_dtype,
+                       const int64_t* sweep_offsets, int32_t n_sweeps, void* stream);
+
+/* Voxel / row totals of the last lisec_voxelize() on this handle. Synchronises `stream`.
+ *   n_voxels_per_sweep  host pointer, n_sweeps int32 (may be NULL)
+ *   n_voxels, n_points_in_range (before the T cap), n_dropped_out_of_range, n_dropped_nonfinite
+ *                       host pointers (may be NULL) */
+int32_t lisec_voxel_counts(lisec_handle* h, int32_t* n_voxels_per_sweep, int64_t* n_voxels,
+                           int64_t* n_points_in_range, int64_t* n_dropped_out_of_range,
+                           int64_t* n_dropped_nonfinite, void* stream);
+
+/*
+ * [async] Export the grouping of the last lisec_voxelize(). Voxel order = ascending (sweep, (z*nx + x)*ny + y);
+ * the reference's dict order (first appearance, model_training.py:123-126) is recovered by sorting voxels of a
+ * sweep on point_idx[v][0]. Any output pointer may be NULL. Device pointers, sized for lisec_voxel_counts().n_voxels:
+ *   coords     int32 [V,4]  (sweep, z, x, y)        — the (z,x,y) of model_training.py:148
+ *   counts     int32 [V]    points that fell in the voxel BEFORE the T cap (len(clusteredPoints[voxel]), :131)
+ *   point_idx  int32 [V,T]  kept point indices (index into the sweep's own points, as `idx` at :115), ascending, -1 padded
+ *   features   float32 [V,T,6]  [x, y, z, x-cx, y-cy, z-cz]; centroid = float64 mean of the kept points in
+ *              list order, offsets in float64, one rounding to float32 (model_training.py:134-141 + the Keras
+ *              input cast); pad rows are zeros (:141)
+ */
+int32_t lisec_voxels_export(lisec_handle* h, int32_t* coords, int32_t* counts, int32_t* point_idx,
+                            float* features, void* stream);
+
+/* ---- a4-a5: the reference-shaped dense input (tests / tiny grids only) -------------------------------- */
+
+/* [async] dense float32 [n_sweeps,nz,nx,ny,T,6] exactly as sparse.to_dense(VFE_preprocessing(...)) + tf.stack
+ * build it (model_training.py:143-152, 279, 285; Predict.py:29-30). 537.6 MB per sweep at the real grid —
+ * this is the blow-up the product path exists to avoid; it is here so the drop-in can be checked end to end. */
+int32_t lisec_emit_dense_input(lisec_handle* h, float* dense, void* stream);
+
+/* ---- a6-a11: stacked VFE (model_training.py:155-186, 229-235) ----------------------------------------- */
+
+/* [async] voxel_feat: device float32 [V,c3] — the row MaxPoolingVFELayer(combine=True) (model_training.py:235)
+ * leaves in each occupied voxel; pad rows take part in every max exactly as in the unmasked reference. */
+int32_t lisec_vfe_forward(lisec_handle* h, float* voxel_feat, void* stream);
+
+/* [async] grid: device [n_sweeps,nz,nx,ny,c3] of cfg.grid_dtype — the tensor the first Conv3D consumes
+ * (model_training.py:235-236). Every element is written exactly once: voxel_feat[v] where occupied, c_empty elsewhere. */
+int32_t lisec_scatter_dense(lisec_handle* h, const float* voxel_feat, void* grid, void* stream);
+
+/* [async] lisec_voxelize + lisec_vfe_forward + lisec_scatter_dense without host round trips: what
+ * VFE_preprocessing -> sparse.to_dense -> model.predict's first 23 layers do (Predict.py:21-38). */
+int32_t lisec_frontend_forward(lisec_handle* h, const void* points, int32_t points_dtype,
+                               const int64_t* sweep_offsets, int32_t n_sweeps, void* grid, void* stream);
+
+/* Same, from HOST points (pinned or pageable): copies them to the handle's staging buffer on `stream` first.
+ * This is the call the Python drop-in makes when it is handed a numpy array. [async w.r.t. the kernels] */
+int32_t lisec_frontend_forward_host(lisec_handle* h, const void* points_host, int32_t points_dtype,
+                                    const int64_t* sweep_offsets, int32_t n_sweeps, void* grid, void* stream);
+
+/* Number of kernels the last call on this handle launched (bench.py's gpu_launches). */
+int32_t lisec_last_launch_count(const lisec_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LISEC_B200_H_ */

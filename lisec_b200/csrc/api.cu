@@ -1,0 +1,426 @@
+// C ABI of liblisec_b200.so (see include/lisec_b200.h). Host-side only: argument checks, workspace ownership,
+// BN folding, launch sequencing. No torch types, no exceptions across the boundary, no CPU compute path.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+using namespace lisec;
+
+struct lisec_handle {
+  lisec_config cfg;
+  Geom geom;
+  Workspace ws;
+  VfeParams params;
+  int sm_count = 0;
+  int rows_per_tile = 0;
+  long long max_voxels = 0;
+  long long max_tiles = 0;
+  long long ncells_cap = 0;
+  int scan_blocks_cap = 0;
+  int64_t workspace_bytes = 0;
+  bool weights_set = false;
+  bool voxelized = false;
+  bool count_dirty = true;  // count table must be zero before a point pass; the fill pass leaves it zero
+  // last lisec_voxelize() inputs (export / VFE gather from them)
+  const void* last_points = nullptr;
+  int last_dtype = LISEC_F32;
+  SweepOffsets last_so;
+  int launches = 0;
+  char err[512];
+};
+
+namespace {
+
+int fail(lisec_handle* h, int code, const char* fmt, ...) {
+  if (h) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(h->err, sizeof(h->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+int cuda_fail(lisec_handle* h, cudaError_t e, const char* what) {
+  return fail(h, LISEC_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define LISEC_CUDA(h, call)                                 \
+  do {                                                      \
+    cudaError_t e_ = (call);                                \
+    if (e_ != cudaSuccess) return cuda_fail(h, e_, #call);  \
+  } while (0)
+
+bool is_pow2_double(double s) {
+  int e;
+  return s > 0 && std::frexp(s, &e) == 0.5;
+}
+
+template <typename T>
+cudaError_t dev_alloc(lisec_handle* h, T** p, size_t n) {
+  size_t bytes = n * sizeof(T);
+  bytes = (bytes + 255) & ~size_t(255);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), bytes);
+  if (e == cudaSuccess) h->workspace_bytes += (int64_t)bytes;
+  return e;
+}
+
+void free_workspace(Workspace& w) {
+  void* ptrs[] = {w.count, w.cell_voxel, w.cell_of_point, w.list_unsorted, w.list_sorted, w.entry_voxel,
+                  w.voxel_cell, w.voxel_start, w.row_start, w.tile_first, w.block_sums, w.sweep_voxel_start,
+                  w.totals, w.voxel_feat, w.c_empty, w.staging, w.empty_desc};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  w = Workspace();
+}
+
+int check_offsets(lisec_handle* h, const int64_t* off, int n_sweeps, SweepOffsets* so) {
+  if (!off) return fail(h, LISEC_ERR_BAD_ARG, "sweep_offsets is NULL");
+  if (n_sweeps < 1) return fail(h, LISEC_ERR_BAD_ARG, "n_sweeps = %d, need >= 1", n_sweeps);
+  if (n_sweeps > h->cfg.max_sweeps)
+    return fail(h, LISEC_ERR_CAPACITY, "n_sweeps = %d exceeds the handle's max_sweeps = %d", n_sweeps,
+                h->cfg.max_sweeps);
+  if (off[0] != 0) return fail(h, LISEC_ERR_BAD_ARG, "sweep_offsets[0] = %lld, need 0", (long long)off[0]);
+  for (int s = 0; s < n_sweeps; ++s)
+    if (off[s + 1] < off[s]) return fail(h, LISEC_ERR_BAD_ARG, "sweep_offsets decreases at %d", s + 1);
+  if (off[n_sweeps] > h->cfg.max_points)
+    return fail(h, LISEC_ERR_CAPACITY, "%lld points exceed the handle's max_points = %lld",
+                (long long)off[n_sweeps], (long long)h->cfg.max_points);
+  so->n = n_sweeps;
+  for (int s = 0; s <= n_sweeps; ++s) so->off[s] = off[s];
+  for (int s = n_sweeps + 1; s <= LISEC_MAX_SWEEPS; ++s) so->off[s] = off[n_sweeps];
+  return LISEC_OK;
+}
+
+int do_voxelize(lisec_handle* h, const void* points, int dtype, const SweepOffsets& so, cudaStream_t st) {
+  const long long n_total = so.off[so.n];
+  if (h->count_dirty) {
+    LISEC_CUDA(h, cudaMemsetAsync(h->ws.count, 0, sizeof(int) * (size_t)h->ncells_cap, st));
+    h->count_dirty = false;
+  }
+  h->voxelized = false;
+  h->count_dirty = true;  // until the fill pass has been enqueued
+  LISEC_CUDA(h, launch_point_pass(points, dtype, n_total, so, h->geom, h->ws, st, &h->launches));
+  LISEC_CUDA(h, launch_cell_scan(so, h->geom, h->ws, h->scan_blocks_cap, st, &h->launches));
+  LISEC_CUDA(h, launch_fill_and_order(n_total, h->geom, h->rows_per_tile, h->ws, st, &h->launches));
+  h->count_dirty = false;
+  h->last_points = points;
+  h->last_dtype = dtype;
+  h->last_so = so;
+  h->voxelized = true;
+  return LISEC_OK;
+}
+
+int do_vfe(lisec_handle* h, float* voxel_feat, cudaStream_t st) {
+  LISEC_CUDA(h, launch_vfe(h->last_points, h->last_dtype, h->geom, h->params, h->ws.tile_first,
+                           h->ws.voxel_start, h->ws.row_start, h->ws.list_sorted, h->ws.totals + TOT_TILES,
+                           voxel_feat, h->sm_count, st, &h->launches));
+  return LISEC_OK;
+}
+
+int check_points(lisec_handle* h, const void* points, int dtype, long long n_total, bool device) {
+  if (dtype != LISEC_F32 && dtype != LISEC_F64)
+    return fail(h, LISEC_ERR_BAD_ARG, "points_dtype = %d, need LISEC_F32 or LISEC_F64", dtype);
+  if (n_total > 0 && !points) return fail(h, LISEC_ERR_BAD_ARG, "points is NULL");
+  if (device && (reinterpret_cast<uintptr_t>(points) & 15))
+    return fail(h, LISEC_ERR_BAD_ARG, "points must be 16-byte aligned");
+  return LISEC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t lisec_abi_version(void) { return LISEC_ABI_VERSION; }
+
+int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
+  if (!cfg || !out) return LISEC_ERR_BAD_ARG;
+  *out = nullptr;
+  lisec_handle* h = new (std::nothrow) lisec_handle();
+  if (!h) return LISEC_ERR_CUDA;
+  h->err[0] = 0;
+  h->cfg = *cfg;
+  *out = h;  // returned even on failure so the caller can read lisec_last_error(); lisec_destroy() frees it
+
+  const lisec_config& c = h->cfg;
+  if (!(c.voxel_x > 0 && c.voxel_y > 0 && c.voxel_z > 0) || !std::isfinite(c.voxel_x) ||
+      !std::isfinite(c.voxel_y) || !std::isfinite(c.voxel_z))
+    return fail(h, LISEC_ERR_BAD_CONFIG, "voxel sizes must be finite and > 0");
+  if (c.max_voxel_x < 1 || c.max_voxel_y < 1 || c.max_voxel_z < 1)
+    return fail(h, LISEC_ERR_BAD_CONFIG, "max_voxel_{x,y,z} must be >= 1");
+  if (c.sample_size < 2 || c.sample_size > 64)
+    return fail(h, LISEC_ERR_BAD_CONFIG, "sample_size = %d, supported range is 2..64", c.sample_size);
+  if (c.c1 != 16 || c.c2 != 32 || c.c3 != 64)
+    return fail(h, LISEC_ERR_UNSUPPORTED,
+                "VFE widths (%d,%d,%d): only the current createModel widths (16,32,64) are built", c.c1, c.c2,
+                c.c3);
+  if (c.grid_dtype != LISEC_F32 && c.grid_dtype != LISEC_BF16)
+    return fail(h, LISEC_ERR_BAD_CONFIG, "grid_dtype must be LISEC_F32 or LISEC_BF16");
+  if (c.max_sweeps < 1 || c.max_sweeps > LISEC_MAX_SWEEPS)
+    return fail(h, LISEC_ERR_BAD_CONFIG, "max_sweeps = %d, supported range is 1..%d", c.max_sweeps,
+                LISEC_MAX_SWEEPS);
+  if (c.max_points < 1 || c.max_points > 2000000000LL)
+    return fail(h, LISEC_ERR_BAD_CONFIG, "max_points out of range");
+
+  Geom& g = h->geom;
+  g.size[0] = c.voxel_x; g.size[1] = c.voxel_y; g.size[2] = c.voxel_z;
+  g.exact_inv = is_pow2_double(c.voxel_x) && is_pow2_double(c.voxel_y) && is_pow2_double(c.voxel_z);
+  for (int i = 0; i < 3; ++i) g.inv[i] = g.exact_inv ? 1.0 / g.size[i] : 0.0;
+  g.maxx = c.max_voxel_x; g.maxy = c.max_voxel_y; g.maxz = c.max_voxel_z;
+  g.nx = 2 * c.max_voxel_x; g.ny = 2 * c.max_voxel_y; g.nz = c.max_voxel_z;
+  g.T = c.sample_size;
+  const long long cells = (long long)g.nz * g.nx * g.ny;
+  if (cells * c.max_sweeps > 2000000000LL)
+    return fail(h, LISEC_ERR_BAD_CONFIG, "grid of %lld cells x %d sweeps exceeds int32 indexing", cells,
+                c.max_sweeps);
+  g.cells = (int)cells;
+
+  int ndev = 0;
+  LISEC_CUDA(h, cudaGetDeviceCount(&ndev));
+  if (c.device < 0 || c.device >= ndev)
+    return fail(h, LISEC_ERR_CUDA, "device %d not available (%d CUDA devices)", c.device, ndev);
+  LISEC_CUDA(h, cudaSetDevice(c.device));
+  int major = 0;
+  LISEC_CUDA(h, cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, c.device));
+  if (major != 10)
+    return fail(h, LISEC_ERR_CUDA, "device %d has compute capability %d.x; this library is built for sm_100a only",
+                c.device, major);
+  LISEC_CUDA(h, cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, c.device));
+
+  h->rows_per_tile = vfe_rows_per_tile(g.T);
+  h->ncells_cap = cells * c.max_sweeps;
+  h->max_voxels = c.max_points < h->ncells_cap ? c.max_points : h->ncells_cap;
+  h->max_tiles = (c.max_points + h->max_voxels) / h->rows_per_tile + 2;
+  h->scan_blocks_cap = (int)((h->ncells_cap + kScanTile - 1) / kScanTile);
+
+  Workspace& w = h->ws;
+  const size_t P = (size_t)c.max_points + 4, V = (size_t)h->max_voxels + 1;
+  LISEC_CUDA(h, dev_alloc(h, &w.count, (size_t)h->ncells_cap + kScanItems));
+  LISEC_CUDA(h, dev_alloc(h, &w.cell_voxel, (size_t)h->ncells_cap + kScanItems));
+  LISEC_CUDA(h, dev_alloc(h, &w.cell_of_point, P));
+  LISEC_CUDA(h, dev_alloc(h, &w.list_unsorted, P));
+  LISEC_CUDA(h, dev_alloc(h, &w.list_sorted, P));
+  LISEC_CUDA(h, dev_alloc(h, &w.entry_voxel, P));
+  LISEC_CUDA(h, dev_alloc(h, &w.voxel_cell, V));
+  LISEC_CUDA(h, dev_alloc(h, &w.voxel_start, V + 1));
+  LISEC_CUDA(h, dev_alloc(h, &w.row_start, V + 1));
+  LISEC_CUDA(h, dev_alloc(h, &w.tile_first, (size_t)h->max_tiles + 2));
+  LISEC_CUDA(h, dev_alloc(h, &w.block_sums, (size_t)3 * h->scan_blocks_cap + 4));
+  LISEC_CUDA(h, dev_alloc(h, &w.sweep_voxel_start, (size_t)c.max_sweeps + 2));
+  LISEC_CUDA(h, dev_alloc(h, &w.totals, (size_t)TOT_COUNT));
+  LISEC_CUDA(h, dev_alloc(h, &w.voxel_feat, V * (size_t)c.c3));
+  LISEC_CUDA(h, dev_alloc(h, &w.c_empty, (size_t)c.c3));
+  LISEC_CUDA(h, dev_alloc(h, reinterpret_cast<unsigned char**>(&w.staging), P * 3 * sizeof(double)));
+  LISEC_CUDA(h, dev_alloc(h, &w.empty_desc, (size_t)8));
+  // the one-voxel problem whose VFE output is c_empty: 0 kept points, 1 pad row, 1 tile
+  int desc[8] = {0, 1, 0, 0, 0, 1, 0, 0};
+  const long long one = 1;
+  std::memcpy(&desc[6], &one, sizeof(one));
+  LISEC_CUDA(h, cudaMemcpy(w.empty_desc, desc, sizeof(desc), cudaMemcpyHostToDevice));
+  LISEC_CUDA(h, cudaMemset(w.totals, 0, sizeof(long long) * TOT_COUNT));
+  return LISEC_OK;
+}
+
+void lisec_destroy(lisec_handle* h) {
+  if (!h) return;
+  if (h->sm_count > 0) cudaSetDevice(h->cfg.device);
+  free_workspace(h->ws);
+  delete h;
+}
+
+const char* lisec_last_error(const lisec_handle* h) { return h ? h->err : "null handle"; }
+
+int64_t lisec_workspace_bytes(const lisec_handle* h) { return h ? h->workspace_bytes : 0; }
+
+int32_t lisec_last_launch_count(const lisec_handle* h) { return h ? h->launches : 0; }
+
+int32_t lisec_set_vfe_weights(lisec_handle* h, const lisec_vfe_weights* w, void* stream) {
+  if (!h) return LISEC_ERR_BAD_ARG;
+  if (!w) return fail(h, LISEC_ERR_BAD_ARG, "weights is NULL");
+  for (int l = 0; l < 3; ++l)
+    if (!w->dense_kernel[l] || !w->bn_gamma[l] || !w->bn_beta[l] || !w->bn_mean[l] || !w->bn_var[l])
+      return fail(h, LISEC_ERR_BAD_ARG, "weights for layer %d contain a NULL pointer", l);
+  if (!(w->bn_epsilon >= 0.f)) return fail(h, LISEC_ERR_BAD_ARG, "bn_epsilon must be >= 0");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
+  h->launches = 0;
+  VfeParams& p = h->params;
+  const float* k0 = w->dense_kernel[0];
+  for (int k = 0; k < 6; ++k)
+    for (int j = 0; j < 16; ++j) p.w1[k][j] = k0[k * 16 + j];
+  const float* k1 = w->dense_kernel[1];  // (32,32): rows 0..15 pooled half, 16..31 pointwise half
+  for (int k = 0; k < 16; ++k)
+    for (int j = 0; j < 32; ++j) {
+      p.w2p[k][j] = k1[k * 32 + j];
+      p.w2x[k][j] = k1[(16 + k) * 32 + j];
+    }
+  const float* k2 = w->dense_kernel[2];  // (64,64)
+  for (int k = 0; k < 32; ++k)
+    for (int j = 0; j < 64; ++j) {
+      p.w3p[k][j] = k2[k * 64 + j];
+      p.w3x[k][j] = k2[(32 + k) * 64 + j];
+    }
+  // BatchNormalization at inference (Keras defaults, model_training.py:171): y = x*a + b
+  float* A[3] = {p.a1, p.a2, p.a3};
+  float* B[3] = {p.b1, p.b2, p.b3};
+  const int C[3] = {16, 32, 64};
+  for (int l = 0; l < 3; ++l)
+    for (int j = 0; j < C[l]; ++j) {
+      const float a = (1.0f / std::sqrt(w->bn_var[l][j] + w->bn_epsilon)) * w->bn_gamma[l][j];
+      A[l][j] = a;
+      B[l][j] = w->bn_beta[l][j] - w->bn_mean[l][j] * a;
+    }
+  h->weights_set = true;
+  // c_empty: the same kernel, run on one voxel that holds nothing but the pad row
+  const int* d = h->ws.empty_desc;
+  LISEC_CUDA(h, launch_vfe(nullptr, LISEC_F32, h->geom, p, d, d + 2, d + 4, nullptr,
+                           reinterpret_cast<const long long*>(d + 6), h->ws.c_empty, h->sm_count, st,
+                           &h->launches));
+  LISEC_CUDA(h, cudaStreamSynchronize(st));
+  return LISEC_OK;
+}
+
+int32_t lisec_get_c_empty(lisec_handle* h, float* out) {
+  if (!h) return LISEC_ERR_BAD_ARG;
+  if (!out) return fail(h, LISEC_ERR_BAD_ARG, "c_empty_host is NULL");
+  if (!h->weights_set) return fail(h, LISEC_ERR_STATE, "lisec_set_vfe_weights() has not been called");
+  LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
+  LISEC_CUDA(h, cudaMemcpy(out, h->ws.c_empty, sizeof(float) * h->cfg.c3, cudaMemcpyDeviceToHost));
+  return LISEC_OK;
+}
+
+int32_t lisec_voxelize(lisec_handle* h, const void* points, int32_t dtype, const int64_t* sweep_offsets,
+                       int32_t n_sweeps, void* stream) {
+  if (!h) return LISEC_ERR_BAD_ARG;
+  SweepOffsets so;
+  int rc = check_offsets(h, sweep_offsets, n_sweeps, &so);
+  if (rc) return rc;
+  rc = check_points(h, points, dtype, so.off[so.n], true);
+  if (rc) return rc;
+  LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
+  h->launches = 0;
+  return do_voxelize(h, points, dtype, so, static_cast<cudaStream_t>(stream));
+}
+
+int32_t lisec_voxel_counts(lisec_handle* h, int32_t* per_sweep, int64_t* n_voxels, int64_t* n_in_range,
+                           int64_t* n_oor, int64_t* n_nonfinite, void* stream) {
+  if (!h) return LISEC_ERR_BAD_ARG;
+  if (!h->voxelized) return fail(h, LISEC_ERR_STATE, "no lisec_voxelize() result on this handle");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
+  long long tot[TOT_COUNT];
+  int svs[LISEC_MAX_SWEEPS + 1];
+  LISEC_CUDA(h, cudaMemcpyAsync(tot, h->ws.totals, sizeof(tot), cudaMemcpyDeviceToHost, st));
+  LISEC_CUDA(h, cudaMemcpyAsync(svs, h->ws.sweep_voxel_start, sizeof(int) * (h->last_so.n + 1),
+                                cudaMemcpyDeviceToHost, st));
+  LISEC_CUDA(h, cudaStreamSynchronize(st));
+  if (per_sweep)
+    for (int s = 0; s < h->last_so.n; ++s) per_sweep[s] = svs[s + 1] - svs[s];
+  if (n_voxels) *n_voxels = tot[TOT_VOXELS];
+  if (n_in_range) *n_in_range = tot[TOT_ENTRIES];
+  if (n_oor) *n_oor = tot[TOT_OUT_OF_RANGE];
+  if (n_nonfinite) *n_nonfinite = tot[TOT_NONFINITE];
+  return LISEC_OK;
+}
+
+int32_t lisec_voxels_export(lisec_handle* h, int32_t* coords, int32_t* counts, int32_t* point_idx,
+                            float* features, void* stream) {
+  if (!h) return LISEC_ERR_BAD_ARG;
+  if (!h->voxelized) return fail(h, LISEC_ERR_STATE, "no lisec_voxelize() result on this handle");
+  LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
+  h->launches = 0;
+  LISEC_CUDA(h, launch_export(h->last_points, h->last_dtype, h->last_so, h->geom, h->ws, h->max_voxels, coords,
+                              counts, point_idx, features, nullptr, static_cast<cudaStream_t>(stream),
+                              &h->launches));
+  return LISEC_OK;
+}
+
+int32_t lisec_emit_dense_input(lisec_handle* h, float* dense, void* stream) {
+  if (!h) return LISEC_ERR_BAD_ARG;
+  if (!dense) return fail(h, LISEC_ERR_BAD_ARG, "dense is NULL");
+  if (!h->voxelized) return fail(h, LISEC_ERR_STATE, "no lisec_voxelize() result on this handle");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
+  h->launches = 0;
+  const size_t bytes = sizeof(float) * (size_t)h->last_so.n * h->geom.cells * h->geom.T * 6;
+  LISEC_CUDA(h, cudaMemsetAsync(dense, 0, bytes, st));
+  LISEC_CUDA(h, launch_export(h->last_points, h->last_dtype, h->last_so, h->geom, h->ws, h->max_voxels, nullptr,
+                              nullptr, nullptr, nullptr, dense, st, &h->launches));
+  return LISEC_OK;
+}
+
+int32_t lisec_vfe_forward(lisec_handle* h, float* voxel_feat, void* stream) {
+  if (!h) return LISEC_ERR_BAD_ARG;
+  if (!voxel_feat) return fail(h, LISEC_ERR_BAD_ARG, "voxel_feat is NULL");
+  if (!h->weights_set) return fail(h, LISEC_ERR_STATE, "lisec_set_vfe_weights() has not been called");
+  if (!h->voxelized) return fail(h, LISEC_ERR_STATE, "no lisec_voxelize() result on this handle");
+  LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
+  h->launches = 0;
+  return do_vfe(h, voxel_feat, static_cast<cudaStream_t>(stream));
+}
+
+int32_t lisec_scatter_dense(lisec_handle* h, const float* voxel_feat, void* grid, void* stream) {
+  if (!h) return LISEC_ERR_BAD_ARG;
+  if (!voxel_feat || !grid) return fail(h, LISEC_ERR_BAD_ARG, "voxel_feat / grid is NULL");
+  if (!h->weights_set) return fail(h, LISEC_ERR_STATE, "lisec_set_vfe_weights() has not been called");
+  if (!h->voxelized) return fail(h, LISEC_ERR_STATE, "no lisec_voxelize() result on this handle");
+  if (reinterpret_cast<uintptr_t>(grid) & 15) return fail(h, LISEC_ERR_BAD_ARG, "grid must be 16-byte aligned");
+  LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
+  h->launches = 0;
+  LISEC_CUDA(h, launch_grid_write(h->geom, h->last_so.n, h->cfg.c3, h->cfg.grid_dtype, h->ws.cell_voxel,
+                                  voxel_feat, h->ws.c_empty, grid, h->sm_count,
+                                  static_cast<cudaStream_t>(stream), &h->launches));
+  return LISEC_OK;
+}
+
+static int frontend(lisec_handle* h, const void* dev_points, int dtype, const SweepOffsets& so, void* grid,
+                    cudaStream_t st) {
+  int rc = do_voxelize(h, dev_points, dtype, so, st);
+  if (rc) return rc;
+  rc = do_vfe(h, h->ws.voxel_feat, st);
+  if (rc) return rc;
+  LISEC_CUDA(h, launch_grid_write(h->geom, so.n, h->cfg.c3, h->cfg.grid_dtype, h->ws.cell_voxel,
+                                  h->ws.voxel_feat, h->ws.c_empty, grid, h->sm_count, st, &h->launches));
+  return LISEC_OK;
+}
+
+int32_t lisec_frontend_forward(lisec_handle* h, const void* points, int32_t dtype, const int64_t* sweep_offsets,
+                               int32_t n_sweeps, void* grid, void* stream) {
+  if (!h) return LISEC_ERR_BAD_ARG;
+  if (!grid) return fail(h, LISEC_ERR_BAD_ARG, "grid is NULL");
+  if (reinterpret_cast<uintptr_t>(grid) & 15) return fail(h, LISEC_ERR_BAD_ARG, "grid must be 16-byte aligned");
+  if (!h->weights_set) return fail(h, LISEC_ERR_STATE, "lisec_set_vfe_weights() has not been called");
+  SweepOffsets so;
+  int rc = check_offsets(h, sweep_offsets, n_sweeps, &so);
+  if (rc) return rc;
+  rc = check_points(h, points, dtype, so.off[so.n], true);
+  if (rc) return rc;
+  LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
+  h->launches = 0;
+  return frontend(h, points, dtype, so, grid, static_cast<cudaStream_t>(stream));
+}
+
+int32_t lisec_frontend_forward_host(lisec_handle* h, const void* points_host, int32_t dtype,
+                                    const int64_t* sweep_offsets, int32_t n_sweeps, void* grid, void* stream) {
+  if (!h) return LISEC_ERR_BAD_ARG;
+  if (!grid) return fail(h, LISEC_ERR_BAD_ARG, "grid is NULL");
+  if (reinterpret_cast<uintptr_t>(grid) & 15) return fail(h, LISEC_ERR_BAD_ARG, "grid must be 16-byte aligned");
+  if (!h->weights_set) return fail(h, LISEC_ERR_STATE, "lisec_set_vfe_weights() has not been called");
+  SweepOffsets so;
+  int rc = check_offsets(h, sweep_offsets, n_sweeps, &so);
+  if (rc) return rc;
+  rc = check_points(h, points_host, dtype, so.off[so.n], false);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
+  h->launches = 0;
+  const size_t bytes = (size_t)so.off[so.n] * 3 * (dtype == LISEC_F64 ? sizeof(double) : sizeof(float));
+  if (bytes) LISEC_CUDA(h, cudaMemcpyAsync(h->ws.staging, points_host, bytes, cudaMemcpyHostToDevice, st));
+  return frontend(h, h->ws.staging, dtype, so, grid, st);
+}
+
+}  // extern "C"

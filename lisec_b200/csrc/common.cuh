@@ -1,0 +1,101 @@
+// Internal declarations shared by the kernels and the C ABI of liblisec_b200.so. Not installed.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lisec_b200.h"
+
+namespace lisec {
+
+// ---- geometry: the positional arguments of VFE_preprocessing (reference model_training.py:112) ----------
+struct Geom {
+  double size[3];  // xSize, ySize, zSize
+  double inv[3];   // 1/size when that is exact (size is a power of two), else 0
+  int exact_inv;   // 1: key = floor(p * inv) is bit-identical to floor(p / size)
+  int maxx, maxy, maxz;  // maxVoxelX, maxVoxelY, maxVoxelZ
+  int nx, ny, nz;        // 2*maxx, 2*maxy, maxz
+  int T;                 // sampleSize
+  int cells;             // nz*nx*ny cells per sweep
+};
+
+// sweep_offsets travels by value so the point pass needs no extra device read.
+struct SweepOffsets {
+  long long off[LISEC_MAX_SWEEPS + 1];
+  int n;
+};
+
+// Folded VFE parameters, primary architecture (model_training.py:231-233): 6->16 | 32->32 | 64->64.
+// Passed as a __grid_constant__ kernel parameter: ptxas then feeds the weights to FFMA from uniform
+// registers / the constant bank, with no per-thread load in the inner product loops.
+struct VfeParams {
+  float w1[6][16];    // dense    (6,16)
+  float w2p[16][32];  // dense_1 rows 0..15  : multiply the pooled half   (Concatenate([pooling, layer]), :164-165)
+  float w2x[16][32];  // dense_1 rows 16..31 : multiply the pointwise half
+  float w3p[32][64];  // dense_2 rows 0..31  : pooled half
+  float w3x[32][64];  // dense_2 rows 32..63 : pointwise half
+  float a1[16], b1[16];  // BN folded: y = x*a + b, a = gamma*rsqrt(var+eps), b = beta - mean*a
+  float a2[32], b2[32];
+  float a3[64], b3[64];
+};
+
+// totals[] slots (device, long long)
+enum {
+  TOT_VOXELS = 0,
+  TOT_ENTRIES = 1,  // in-range points
+  TOT_ROWS = 2,     // kept rows + one pad row per non-full voxel
+  TOT_TILES = 3,
+  TOT_NONFINITE = 4,
+  TOT_OUT_OF_RANGE = 5,
+  TOT_COUNT = 8
+};
+
+constexpr int kVfeThreads = 256;  // rows per VFE tile
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;     // cells per thread in the cell-table scans
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+struct Workspace {
+  // cell tables, [max_sweeps * cells]
+  int* count = nullptr;       // points per cell; built by the point pass, drained back to 0 by the fill pass
+  int* cell_voxel = nullptr;  // occupancy map: voxel row of the cell, or -1
+  // per point, [max_points]
+  int* cell_of_point = nullptr;
+  int* list_unsorted = nullptr;  // CSR payload in arrival order
+  int* list_sorted = nullptr;    // CSR payload, first min(count,T) of each segment ascending
+  int* entry_voxel = nullptr;    // voxel row of each CSR entry
+  // per voxel, [max_voxels + 1]
+  int* voxel_cell = nullptr;
+  int* voxel_start = nullptr;  // CSR offsets into list_*
+  int* row_start = nullptr;    // offsets in VFE rows (kept + pad)
+  int* tile_first = nullptr;   // first voxel of each VFE tile, [max_tiles + 2]
+  int* block_sums = nullptr;   // [3][scan_blocks] reduce -> exclusive prefix
+  int* sweep_voxel_start = nullptr;  // [max_sweeps + 1]
+  long long* totals = nullptr;       // [TOT_COUNT]
+  float* voxel_feat = nullptr;       // [max_voxels, c3] for the fused entry point
+  float* c_empty = nullptr;          // [c3]
+  void* staging = nullptr;           // host->device landing buffer for *_host entry points
+  int* empty_desc = nullptr;         // 8 ints describing the one-voxel problem that yields c_empty
+};
+
+// ---- launchers (each returns the cudaError_t of its launches) --------------------------------------------
+cudaError_t launch_point_pass(const void* pts, int pts_dtype, long long n_total, const SweepOffsets& so,
+                              const Geom& g, Workspace& w, cudaStream_t st, int* launches);
+cudaError_t launch_cell_scan(const SweepOffsets& so, const Geom& g, Workspace& w, int scan_blocks_cap,
+                             cudaStream_t st, int* launches);
+cudaError_t launch_fill_and_order(long long n_total, const Geom& g, int rows_per_tile, Workspace& w,
+                                  cudaStream_t st, int* launches);
+cudaError_t launch_export(const void* pts, int pts_dtype, const SweepOffsets& so, const Geom& g,
+                          const Workspace& w, long long max_voxels, int32_t* coords, int32_t* counts,
+                          int32_t* point_idx, float* features, float* dense, cudaStream_t st, int* launches);
+cudaError_t launch_vfe(const void* pts, int pts_dtype, const Geom& g, const VfeParams& p, const int* tile_first,
+                       const int* voxel_start, const int* row_start, const int* list_sorted,
+                       const long long* n_tiles, float* voxel_feat, int sm_count, cudaStream_t st,
+                       int* launches);
+cudaError_t launch_grid_write(const Geom& g, int n_sweeps, int c3, int grid_dtype, const int* cell_voxel,
+                              const float* voxel_feat, const float* c_empty, void* grid, int sm_count,
+                              cudaStream_t st, int* launches);
+
+int vfe_rows_per_tile(int T);
+
+}  // namespace lisec

@@ -1,0 +1,116 @@
+// Dense voxel-grid writer on sm_100a: the tensor MaxPoolingVFELayer(combine=True) hands to the first Conv3D
+// (reference model_training.py:235-236), shape [N, nz, nx, ny, C3].
+//
+// The reference reaches it by densifying the INPUT (sparse.to_dense, model_training.py:279 / Predict.py:29-30) and
+// running the VFE on all nz*nx*ny*T slots. Here the VFE ran on occupied voxels only, and this kernel writes every
+// grid element exactly once: the voxel's feature row where the occupancy map says so, c_empty elsewhere (the
+// unmasked network's output for an all-zero voxel is a non-zero constant). No memset + scatter:
+// that would write the occupied rows twice.
+//
+// HBM-bound: 256 B (f32) / 128 B (bf16) stored per cell against 4 B of occupancy map read. A warp takes 32
+// consecutive cells: one coalesced 128 B map load, then 16-byte streaming stores, 512 contiguous bytes per
+// store instruction.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace lisec {
+
+namespace {
+
+__device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(uint4* p, uint4 v) { __stcs(p, v); }
+
+// f32 grid, C3 = 64: 16 lanes x float4 cover one cell; a warp stores 2 cells per instruction.
+__global__ void __launch_bounds__(256) grid_write_f32_c64(const int* __restrict__ cell_voxel,
+                                                          const float* __restrict__ voxel_feat,
+                                                          const float* __restrict__ c_empty,
+                                                          float* __restrict__ grid, long long ncells) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane >> 4;   // which of the 2 cells of a store
+  const int chunk = lane & 15; // which float4 of the 64-channel row
+  const float4 bg = reinterpret_cast<const float4*>(c_empty)[chunk];
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long ngroups = (ncells + 31) >> 5;
+  for (long long grp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < ngroups; grp += warps) {
+    const long long base = grp << 5;
+    const int my = (base + lane < ncells) ? __ldg(cell_voxel + base + lane) : -1;
+    float4 val[16];
+    int vox[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      vox[i] = __shfl_sync(0xffffffffu, my, 2 * i + sub);
+      val[i] = bg;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (vox[i] >= 0) val[i] = __ldg(reinterpret_cast<const float4*>(voxel_feat + (size_t)vox[i] * 64) + chunk);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const long long cell = base + 2 * i + sub;
+      if (cell < ncells) st_stream(reinterpret_cast<float4*>(grid + cell * 64) + chunk, val[i]);
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<unsigned*>(&h);
+}
+
+// bf16 grid, C3 = 64: 8 lanes x 16 B cover one cell; a warp stores 4 cells per instruction. Values are rounded
+// once from the float32 result (c_empty included).
+__global__ void __launch_bounds__(256) grid_write_bf16_c64(const int* __restrict__ cell_voxel,
+                                                           const float* __restrict__ voxel_feat,
+                                                           const float* __restrict__ c_empty,
+                                                           __nv_bfloat16* __restrict__ grid, long long ncells) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane >> 3;
+  const int chunk = lane & 7;  // 8 channels
+  const float4 b0 = reinterpret_cast<const float4*>(c_empty)[2 * chunk];
+  const float4 b1 = reinterpret_cast<const float4*>(c_empty)[2 * chunk + 1];
+  const uint4 bg = make_uint4(pack_bf16x2(b0.x, b0.y), pack_bf16x2(b0.z, b0.w), pack_bf16x2(b1.x, b1.y),
+                              pack_bf16x2(b1.z, b1.w));
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long ngroups = (ncells + 31) >> 5;
+  for (long long grp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < ngroups; grp += warps) {
+    const long long base = grp << 5;
+    const int my = (base + lane < ncells) ? __ldg(cell_voxel + base + lane) : -1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int vox = __shfl_sync(0xffffffffu, my, 4 * i + sub);
+      uint4 val = bg;
+      if (vox >= 0) {
+        const float4* src = reinterpret_cast<const float4*>(voxel_feat + (size_t)vox * 64) + 2 * chunk;
+        const float4 f0 = __ldg(src), f1 = __ldg(src + 1);
+        val = make_uint4(pack_bf16x2(f0.x, f0.y), pack_bf16x2(f0.z, f0.w), pack_bf16x2(f1.x, f1.y),
+                         pack_bf16x2(f1.z, f1.w));
+      }
+      const long long cell = base + 4 * i + sub;
+      if (cell < ncells) st_stream(reinterpret_cast<uint4*>(grid + cell * 64) + chunk, val);
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_grid_write(const Geom& g, int n_sweeps, int c3, int grid_dtype, const int* cell_voxel,
+                              const float* voxel_feat, const float* c_empty, void* grid, int sm_count,
+                              cudaStream_t st, int* launches) {
+  if (c3 != 64) return cudaErrorInvalidValue;
+  const long long ncells = (long long)n_sweeps * g.cells;
+  if (ncells == 0) return cudaSuccess;
+  long long blocks = ((ncells + 31) / 32 + 7) / 8;  // 8 warps per block, one 32-cell group per warp
+  const long long cap = (long long)sm_count * 8 * 4; // grid-stride beyond 4 waves of 8 resident CTAs per SM
+  if (blocks > cap) blocks = cap;
+  if (grid_dtype == LISEC_F32)
+    grid_write_f32_c64<<<(unsigned)blocks, 256, 0, st>>>(cell_voxel, voxel_feat, c_empty,
+                                                         static_cast<float*>(grid), ncells);
+  else
+    grid_write_bf16_c64<<<(unsigned)blocks, 256, 0, st>>>(cell_voxel, voxel_feat, c_empty,
+                                                          static_cast<__nv_bfloat16*>(grid), ncells);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+}  // namespace lisec

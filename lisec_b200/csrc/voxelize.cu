@@ -1,0 +1,429 @@
+// Point -> voxel grouping on sm_100a.
+//
+// Replaces reference model_training.py:103-126 (get_voxel + the dict-building loop of VFE_preprocessing) and the
+// sampling rule at :131-132 with its deterministic contract (first T indices in point order).
+//
+// Pipeline (all launches on the caller's stream, no host round trip):
+//   point_pass   12 B/point read, float4-vectorised; voxel key in float64; strict range test; warp-aggregated
+//                atomicAdd histogram into the per-cell count table; writes cell_of_point.
+//   cell_scan    three fused exclusive scans over the cell table (occupied -> voxel row, count -> CSR offset,
+//                kept+pad -> VFE row offset); writes the occupancy map cell_voxel. Voxel rows therefore come out
+//                in ascending (sweep, z, x, y) cell order, independent of thread scheduling.
+//   fill_pass    warp-aggregated atomicSub slot claim drains the count table back to zero (so the next call
+//                needs no memset) and writes the CSR payload in arrival order.
+//   order_pass   rank-by-counting inside each voxel segment, early exit at T: entry p lands at position
+//                #{q in voxel : q < p}. This is what makes the slot assignment deterministic in point order
+//                whatever order the atomics resolved in. Also marks the VFE tile boundaries.
+#include "common.cuh"
+
+namespace lisec {
+
+namespace {
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// ---- voxel key (model_training.py:103-107, 117-122) ------------------------------------------------------
+// status: 0 kept, 1 out of range, 2 non-finite (the reference would raise in math.floor; we drop and count).
+__device__ __forceinline__ int cell_of(double x, double y, double z, const Geom& g, int& status) {
+  if (!(isfinite(x) && isfinite(y) && isfinite(z))) {
+    status = 2;
+    return -1;
+  }
+  double kx, ky, kz;
+  if (g.exact_inv) {  // power-of-two voxel sizes: the product is exact, so it equals the quotient bit for bit
+    kx = floor(x * g.inv[0]);
+    ky = floor(y * g.inv[1]);
+    kz = floor(z * g.inv[2]);
+  } else {
+    kx = floor(x / g.size[0]);
+    ky = floor(y / g.size[1]);
+    kz = floor(z / g.size[2]);
+  }
+  // strict on both sides (:118-120); comparisons stay in float64 so huge coordinates cannot wrap an int
+  const bool keep = (kx > -(double)g.maxx) && (kx < (double)g.maxx) && (ky > -(double)g.maxy) &&
+                    (ky < (double)g.maxy) && (kz > 0.0) && (kz < (double)g.maxz);
+  if (!keep) {
+    status = 1;
+    return -1;
+  }
+  status = 0;
+  // fixedKey = (kx + maxVoxelX, ky + maxVoxelY, kz) (:122); dense layout is (z, x, y) (:148, :151-152)
+  return ((int)kz * g.nx + ((int)kx + g.maxx)) * g.ny + ((int)ky + g.maxy);
+}
+
+template <typename PT>
+struct Vec4Load;
+template <>
+struct Vec4Load<float> {
+  // 4 points = 12 floats = three 16-byte loads
+  static __device__ __forceinline__ void load(const float* base, long long g, float (&v)[12]) {
+    const float4* p = reinterpret_cast<const float4*>(base) + 3 * g;
+    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
+  }
+};
+template <>
+struct Vec4Load<double> {
+  static __device__ __forceinline__ void load(const double* base, long long g, double (&v)[12]) {
+    const double2* p = reinterpret_cast<const double2*>(base) + 6 * g;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double2 a = __ldg(p + i);
+      v[2 * i] = a.x;
+      v[2 * i + 1] = a.y;
+    }
+  }
+};
+
+// ---- K1: point pass ---------------------------------------------------------------------------------------
+template <typename PT>
+__global__ void __launch_bounds__(256) point_pass_kernel(const PT* __restrict__ pts, long long n_total,
+                                                         const __grid_constant__ SweepOffsets so,
+                                                         const __grid_constant__ Geom g,
+                                                         int* __restrict__ cell_of_point, int* __restrict__ count,
+                                                         unsigned long long* __restrict__ totals) {
+  const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long p0 = grp * 4;
+  PT v[12];
+  const bool full = p0 + 3 < n_total;
+  if (full) {
+    Vec4Load<PT>::load(pts, grp, v);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      long long idx = p0 * 3 + i;
+      v[i] = (idx < n_total * 3) ? pts[idx] : PT(0);
+    }
+  }
+  // sweep of the first point; later points of the group advance it (groups may straddle sweeps)
+  int s = 0;
+  if (p0 < n_total) {
+    while (s + 1 < so.n && p0 >= so.off[s + 1]) ++s;
+  }
+  int cell[4];
+  int n_oor = 0, n_nonf = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long long p = p0 + j;
+    cell[j] = -1;
+    if (p < n_total) {
+      while (s + 1 < so.n && p >= so.off[s + 1]) ++s;
+      int status;
+      int c = cell_of((double)v[3 * j], (double)v[3 * j + 1], (double)v[3 * j + 2], g, status);
+      n_oor += (status == 1);
+      n_nonf += (status == 2);
+      cell[j] = (c >= 0) ? s * g.cells + c : -1;
+    }
+  }
+  if (full) {
+    reinterpret_cast<int4*>(cell_of_point)[grp] = make_int4(cell[0], cell[1], cell[2], cell[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (p0 + j < n_total) cell_of_point[p0 + j] = cell[j];
+  }
+  // warp-aggregated histogram: lanes that hit the same cell elect one leader that adds the group size
+  const int lane = lane_id();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const unsigned active = __ballot_sync(0xffffffffu, cell[j] >= 0);
+    if (cell[j] >= 0) {
+      const unsigned peers = __match_any_sync(active, cell[j]);
+      if (lane == __ffs(peers) - 1) atomicAdd(&count[cell[j]], __popc(peers));
+    }
+  }
+  // dropped-point statistics: one atomic per warp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    n_oor += __shfl_xor_sync(0xffffffffu, n_oor, o);
+    n_nonf += __shfl_xor_sync(0xffffffffu, n_nonf, o);
+  }
+  if (lane == 0) {
+    if (n_oor) atomicAdd(&totals[TOT_OUT_OF_RANGE], (unsigned long long)n_oor);
+    if (n_nonf) atomicAdd(&totals[TOT_NONFINITE], (unsigned long long)n_nonf);
+  }
+}
+
+// ---- K2: cell-table scans ---------------------------------------------------------------------------------
+struct Tri {
+  int v, e, r;  // voxels, CSR entries, VFE rows
+};
+__device__ __forceinline__ Tri tri_add(Tri a, Tri b) { return Tri{a.v + b.v, a.e + b.e, a.r + b.r}; }
+__device__ __forceinline__ Tri tri_of_count(int c, int T) {
+  // rows = kept points + one pad row when the voxel is not full (all pad rows of a voxel are identical, so one
+  // virtual zero row reproduces the unmasked reference exactly)
+  return c > 0 ? Tri{1, c, (c < T ? c + 1 : T)} : Tri{0, 0, 0};
+}
+__device__ __forceinline__ Tri tri_shfl_up(Tri a, int d) {
+  return Tri{__shfl_up_sync(0xffffffffu, a.v, d), __shfl_up_sync(0xffffffffu, a.e, d),
+             __shfl_up_sync(0xffffffffu, a.r, d)};
+}
+
+// exclusive scan of one Tri per thread over a 256-thread block; *total = block sum
+__device__ __forceinline__ Tri block_exclusive(Tri x, Tri* total, Tri* smem /*[8+1]*/) {
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  Tri inc = x;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    Tri y = tri_shfl_up(inc, d);
+    if (lane >= d) inc = tri_add(inc, y);
+  }
+  if (lane == 31) smem[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    Tri w = lane < (kScanThreads / 32) ? smem[lane] : Tri{0, 0, 0};
+    Tri winc = w;
+#pragma unroll
+    for (int d = 1; d < kScanThreads / 32; d <<= 1) {
+      Tri y = tri_shfl_up(winc, d);
+      if (lane >= d) winc = tri_add(winc, y);
+    }
+    if (lane < kScanThreads / 32) smem[lane] = Tri{winc.v - w.v, winc.e - w.e, winc.r - w.r};
+    if (lane == kScanThreads / 32 - 1) smem[kScanThreads / 32] = winc;
+  }
+  __syncthreads();
+  const Tri base = smem[warp];
+  *total = smem[kScanThreads / 32];
+  return Tri{base.v + inc.v - x.v, base.e + inc.e - x.e, base.r + inc.r - x.r};
+}
+
+__device__ __forceinline__ void load_counts(const int* __restrict__ count, long long base, long long ncells,
+                                            int (&c)[kScanItems]) {
+  if (base + kScanItems <= ncells) {
+    const int4* p = reinterpret_cast<const int4*>(count + base);
+    int4 a = p[0], b = p[1];
+    c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w;
+    c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) c[i] = (base + i < ncells) ? count[base + i] : 0;
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const int* __restrict__ count, long long ncells,
+                                                                   int T, int nblocks,
+                                                                   int* __restrict__ block_sums) {
+  __shared__ Tri smem[kScanThreads / 32 + 1];
+  const long long base = ((long long)blockIdx.x * kScanThreads + threadIdx.x) * kScanItems;
+  int c[kScanItems];
+  load_counts(count, base, ncells, c);
+  Tri t{0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) t = tri_add(t, tri_of_count(c[i], T));
+  Tri total;
+  block_exclusive(t, &total, smem);
+  if (threadIdx.x == 0) {
+    block_sums[blockIdx.x] = total.v;
+    block_sums[nblocks + blockIdx.x] = total.e;
+    block_sums[2 * nblocks + blockIdx.x] = total.r;
+  }
+}
+
+// one block: exclusive scan of the per-block sums in place, totals and sentinels
+__global__ void __launch_bounds__(kScanThreads) scan_spine_kernel(int* __restrict__ block_sums, int nblocks,
+                                                                  int n_sweeps, long long* __restrict__ totals,
+                                                                  int* __restrict__ voxel_start,
+                                                                  int* __restrict__ row_start,
+                                                                  int* __restrict__ sweep_voxel_start) {
+  __shared__ Tri smem[kScanThreads / 32 + 1];
+  Tri carry{0, 0, 0};
+  for (int b0 = 0; b0 < nblocks; b0 += kScanThreads) {
+    const int b = b0 + threadIdx.x;
+    Tri x{0, 0, 0};
+    if (b < nblocks) x = Tri{block_sums[b], block_sums[nblocks + b], block_sums[2 * nblocks + b]};
+    Tri total;
+    Tri ex = block_exclusive(x, &total, smem);
+    if (b < nblocks) {
+      block_sums[b] = carry.v + ex.v;
+      block_sums[nblocks + b] = carry.e + ex.e;
+      block_sums[2 * nblocks + b] = carry.r + ex.r;
+    }
+    carry = tri_add(carry, total);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    totals[TOT_VOXELS] = carry.v;
+    totals[TOT_ENTRIES] = carry.e;
+    totals[TOT_ROWS] = carry.r;
+    totals[TOT_TILES] = 0;  // set by order_pass when there is at least one voxel
+    voxel_start[carry.v] = carry.e;
+    row_start[carry.v] = carry.r;
+    sweep_voxel_start[n_sweeps] = carry.v;
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_down_kernel(const int* __restrict__ count, long long ncells,
+                                                                 int T, int cells_per_sweep, int nblocks,
+                                                                 const int* __restrict__ block_sums,
+                                                                 int* __restrict__ cell_voxel,
+                                                                 int* __restrict__ voxel_cell,
+                                                                 int* __restrict__ voxel_start,
+                                                                 int* __restrict__ row_start,
+                                                                 int* __restrict__ sweep_voxel_start) {
+  __shared__ Tri smem[kScanThreads / 32 + 1];
+  const long long base = ((long long)blockIdx.x * kScanThreads + threadIdx.x) * kScanItems;
+  int c[kScanItems];
+  load_counts(count, base, ncells, c);
+  Tri t{0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) t = tri_add(t, tri_of_count(c[i], T));
+  Tri total;
+  Tri ex = block_exclusive(t, &total, smem);
+  Tri run{block_sums[blockIdx.x] + ex.v, block_sums[nblocks + blockIdx.x] + ex.e,
+          block_sums[2 * nblocks + blockIdx.x] + ex.r};
+  int cv[kScanItems];
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    const long long cell = base + i;
+    cv[i] = -1;
+    if (cell < ncells) {
+      if (cell % cells_per_sweep == 0) sweep_voxel_start[cell / cells_per_sweep] = run.v;
+      if (c[i] > 0) {
+        cv[i] = run.v;
+        voxel_cell[run.v] = (int)cell;
+        voxel_start[run.v] = run.e;
+        row_start[run.v] = run.r;
+        run = tri_add(run, tri_of_count(c[i], T));
+      }
+    }
+  }
+  if (base + kScanItems <= ncells) {
+    int4* p = reinterpret_cast<int4*>(cell_voxel + base);
+    p[0] = make_int4(cv[0], cv[1], cv[2], cv[3]);
+    p[1] = make_int4(cv[4], cv[5], cv[6], cv[7]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i)
+      if (base + i < ncells) cell_voxel[base + i] = cv[i];
+  }
+}
+
+// ---- K3: fill pass ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fill_pass_kernel(const int* __restrict__ cell_of_point, long long n_total,
+                                                        const int* __restrict__ cell_voxel,
+                                                        const int* __restrict__ voxel_start,
+                                                        int* __restrict__ count, int* __restrict__ list_unsorted,
+                                                        int* __restrict__ entry_voxel) {
+  const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long p0 = grp * 4;
+  int cell[4] = {-1, -1, -1, -1};
+  if (p0 + 3 < n_total) {
+    int4 c = reinterpret_cast<const int4*>(cell_of_point)[grp];
+    cell[0] = c.x; cell[1] = c.y; cell[2] = c.z; cell[3] = c.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (p0 + j < n_total) cell[j] = cell_of_point[p0 + j];
+  }
+  const int lane = lane_id();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const unsigned active = __ballot_sync(0xffffffffu, cell[j] >= 0);
+    if (cell[j] >= 0) {
+      const int v = cell_voxel[cell[j]];
+      const int start = voxel_start[v];
+      const unsigned peers = __match_any_sync(active, cell[j]);
+      const int leader = __ffs(peers) - 1;
+      const int npeers = __popc(peers);
+      int old = 0;
+      if (lane == leader) old = atomicSub(&count[cell[j]], npeers);  // drains the table back to zero
+      old = __shfl_sync(peers, old, leader);
+      const int rank = __popc(peers & ((1u << lane) - 1u));
+      const int slot = old - npeers + rank;
+      list_unsorted[start + slot] = (int)(p0 + j);
+      entry_voxel[start + slot] = v;
+    }
+  }
+}
+
+// ---- K4: order pass (+ VFE tile boundaries) ---------------------------------------------------------------
+__global__ void __launch_bounds__(256) order_pass_kernel(const int* __restrict__ list_unsorted,
+                                                         const int* __restrict__ entry_voxel,
+                                                         const int* __restrict__ voxel_start,
+                                                         const int* __restrict__ row_start, int T,
+                                                         int rows_per_tile, long long* __restrict__ totals,
+                                                         int* __restrict__ list_sorted,
+                                                         int* __restrict__ tile_first) {
+  const long long n_entries = totals[TOT_ENTRIES];
+  const long long n_voxels = totals[TOT_VOXELS];
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n_voxels) {
+    // tile(v) = row_start[v] / rows_per_tile; a voxel has at most T rows < rows_per_tile, so consecutive voxels
+    // differ by at most one tile and every tile index up to the last one has a first voxel.
+    const int t = row_start[e] / rows_per_tile;
+    const int tprev = e > 0 ? row_start[e - 1] / rows_per_tile : -1;
+    if (t != tprev) tile_first[t] = (int)e;
+    if (e == n_voxels - 1) {
+      tile_first[t + 1] = (int)n_voxels;
+      totals[TOT_TILES] = t + 1;
+    }
+  }
+  if (e >= n_entries) return;
+  const int v = entry_voxel[e];
+  const int s = voxel_start[v];
+  const int n = voxel_start[v + 1] - s;
+  const int p = list_unsorted[e];
+  int rank = 0;
+  if (n > 1) {
+    for (int i = 0; i < n; ++i) {
+      rank += (list_unsorted[s + i] < p);
+      if (rank >= T) break;  // not among the first T in point order: dropped (the cap at :131)
+    }
+  }
+  if (rank < T) list_sorted[s + rank] = p;
+}
+
+}  // namespace
+
+// ---- launchers --------------------------------------------------------------------------------------------
+cudaError_t launch_point_pass(const void* pts, int pts_dtype, long long n_total, const SweepOffsets& so,
+                              const Geom& g, Workspace& w, cudaStream_t st, int* launches) {
+  cudaError_t err = cudaMemsetAsync(w.totals, 0, sizeof(long long) * TOT_COUNT, st);
+  if (err != cudaSuccess) return err;
+  if (n_total == 0) return cudaSuccess;
+  const long long groups = (n_total + 3) / 4;
+  const unsigned blocks = (unsigned)((groups + 255) / 256);
+  auto* tot = reinterpret_cast<unsigned long long*>(w.totals);
+  if (pts_dtype == LISEC_F32)
+    point_pass_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(pts), n_total, so, g,
+                                                     w.cell_of_point, w.count, tot);
+  else
+    point_pass_kernel<double><<<blocks, 256, 0, st>>>(static_cast<const double*>(pts), n_total, so, g,
+                                                      w.cell_of_point, w.count, tot);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cell_scan(const SweepOffsets& so, const Geom& g, Workspace& w, int scan_blocks_cap,
+                             cudaStream_t st, int* launches) {
+  const long long ncells = (long long)so.n * g.cells;
+  const int nblocks = (int)((ncells + kScanTile - 1) / kScanTile);
+  if (nblocks > scan_blocks_cap) return cudaErrorInvalidValue;
+  scan_reduce_kernel<<<nblocks, kScanThreads, 0, st>>>(w.count, ncells, g.T, nblocks, w.block_sums);
+  scan_spine_kernel<<<1, kScanThreads, 0, st>>>(w.block_sums, nblocks, so.n, w.totals, w.voxel_start,
+                                                w.row_start, w.sweep_voxel_start);
+  scan_down_kernel<<<nblocks, kScanThreads, 0, st>>>(w.count, ncells, g.T, g.cells, nblocks, w.block_sums,
+                                                     w.cell_voxel, w.voxel_cell, w.voxel_start, w.row_start,
+                                                     w.sweep_voxel_start);
+  *launches += 3;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill_and_order(long long n_total, const Geom& g, int rows_per_tile, Workspace& w,
+                                  cudaStream_t st, int* launches) {
+  if (n_total == 0) return cudaSuccess;
+  const long long groups = (n_total + 3) / 4;
+  fill_pass_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(w.cell_of_point, n_total, w.cell_voxel,
+                                                                     w.voxel_start, w.count, w.list_unsorted,
+                                                                     w.entry_voxel);
+  // entries <= points; threads beyond the device-side totals exit
+  order_pass_kernel<<<(unsigned)((n_total + 255) / 256), 256, 0, st>>>(
+      w.list_unsorted, w.entry_voxel, w.voxel_start, w.row_start, g.T, rows_per_tile, w.totals, w.list_sorted,
+      w.tile_first);
+  *launches += 2;
+  return cudaGetLastError();
+}
+
+}  // namespace lisec
