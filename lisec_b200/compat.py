@@ -1,0 +1,213 @@
+"""Drop-in for the reference's call sites on the front-end path — same names, argument meaning and shapes.
+
+    reference (bot15498/Lisec)                                         here
+    ------------------------------------------------------------------ --------------------------------------------
+    VFE_preprocessing(points, xSize, ySize, zSize, sampleSize,         VFE_preprocessing(...)  -> SparseVoxelTensor
+                      maxVoxelX, maxVoxelY, maxVoxelZ)                     .indices [nnz,5] (z,x,y,i,j)  .values
+        model_training.py:112, callers Predict.py:21-28,                   .dense_shape  .shape
+        model_training.py:270-277, 314-321
+    sparse.reshape(t, (1,) + t.shape)          Predict.py:29           sparse.reshape(t, shape)
+    sparse.to_dense(t, default_value=0.,       Predict.py:30,          sparse.to_dense(t, ...)  -> DenseVoxelInput
+                    validate_indices=False)    model_training.py:279
+    tf.stack(points, axis=0)                   model_training.py:285   stack(list, axis=0)
+    createModel(nx, ny, nz, maxPoints)         model_training.py:222   createModel(nx, ny, nz, maxPoints, weights=)
+    load_model(path, custom_objects={...})     Predict.py:51-52        load_model(path, custom_objects=None)
+    model.predict(x)                           Predict.py:38           model.predict_voxel_grid(x)  (first 23 layers)
+
+What is different underneath: nothing is densified. SparseVoxelTensor and DenseVoxelInput are lazy handles on the
+sweep's points; the 537.6 MB-per-sweep dense input (README.md:58-64 of the reference) only exists if somebody asks
+for it (`.numpy()` on a tiny grid). `predict_voxel_grid` sends all stacked sweeps through ONE
+lisec_frontend_forward call and returns the [N, nz, nx, ny, 64] tensor the reference's first Conv3D consumes
+(model_training.py:235-236), resident on the GPU.
+
+Sampling: the reference subsamples over-full voxels with the unseeded global RNG (np.random.choice,
+model_training.py:132); here the kept rows are the first `sampleSize` in point order.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import constants as K
+from .frontend import Frontend
+from .weights import load_npz, synthetic_vfe_pack
+
+_FRONTENDS: dict = {}
+
+
+def _frontend(cfg_key, n_points: int, n_sweeps: int, device: int = 0) -> Frontend:
+    """One Frontend per (geometry, device); re-created with doubled capacity when a call outgrows it."""
+    key = (cfg_key, device)
+    fe = _FRONTENDS.get(key)
+    need_pts, need_sw = max(n_points, 1), max(n_sweeps, 1)
+    if fe is None or fe.cfg.max_points < need_pts or fe.cfg.max_sweeps < need_sw:
+        xs, ys, zs, T, mx, my, mz = cfg_key
+        cap_pts = max(need_pts, 2 * (fe.cfg.max_points if fe else 0), 262_144)
+        cap_sw = min(64, max(need_sw, 2 * (fe.cfg.max_sweeps if fe else 0), 8))
+        weights = getattr(fe, "_pack", None)
+        if fe is not None:
+            fe.close()
+        fe = Frontend(device=device, max_points=cap_pts, max_sweeps=cap_sw, voxel_size=(xs, ys, zs),
+                      sample_size=T, max_voxel=(mx, my, mz))
+        if weights is not None:
+            fe.set_weights(weights)
+            fe._pack = weights
+        _FRONTENDS[key] = fe
+    return fe
+
+
+class SparseVoxelTensor:
+    """Stands where tf.SparseTensor stood (model_training.py:151-152). Lazy: holds the sweep's points."""
+
+    def __init__(self, points, cfg_key):
+        self._points = np.ascontiguousarray(points)
+        if self._points.dtype not in (np.float32, np.float64):
+            self._points = self._points.astype(np.float64)
+        self._cfg = cfg_key
+        xs, ys, zs, T, mx, my, mz = cfg_key
+        self.dense_shape = [mz, mx * 2, my * 2, T, 6]
+        self.shape = tuple(self.dense_shape)
+        self._coo = None
+
+    def _materialise(self):
+        if self._coo is None:
+            fe = _frontend(self._cfg, len(self._points), 1)
+            fe.voxelize(self._points, [0, len(self._points)])
+            vs = fe.export()
+            T = self._cfg[3]
+            first = vs.point_idx[:, 0].cpu().numpy()
+            order = np.argsort(first, kind="stable")  # the reference's dict order: first appearance (:123-126)
+            coords = vs.coords.cpu().numpy()[order][:, 1:]
+            feats = vs.features.cpu().numpy()[order]
+            V = len(order)
+            ii, jj = np.meshgrid(np.arange(T), np.arange(6), indexing="ij")
+            ind = np.empty((V, T, 6, 5), dtype=np.int64)
+            for k in range(3):
+                ind[..., k] = coords[:, k, None, None]
+            ind[..., 3], ind[..., 4] = ii[None], jj[None]
+            self._coo = (ind.reshape(-1, 5), feats.reshape(-1))
+        return self._coo
+
+    @property
+    def indices(self):
+        """[nnz,5] (z,x,y,i,j): 6*T entries per occupied voxel, zero pad rows included (model_training.py:143-149)."""
+        return self._materialise()[0]
+
+    @property
+    def values(self):
+        """float32: the reference's float64 values after the Keras input cast."""
+        return self._materialise()[1]
+
+
+def VFE_preprocessing(points, xSize, ySize, zSize, sampleSize, maxVoxelX, maxVoxelY, maxVoxelZ) -> SparseVoxelTensor:
+    return SparseVoxelTensor(points, (float(xSize), float(ySize), float(zSize), int(sampleSize), int(maxVoxelX),
+                                      int(maxVoxelY), int(maxVoxelZ)))
+
+
+class DenseVoxelInput:
+    """Stands where the dense [N, nz, nx, ny, T, 6] tensor stood. Lazy: a list of sweeps."""
+
+    def __init__(self, sweeps: List[SparseVoxelTensor], batched: bool):
+        self.sweeps = sweeps
+        self.batched = batched
+        s = tuple(sweeps[0].shape)
+        self.shape = ((len(sweeps),) + s) if batched else s
+
+    def numpy(self) -> np.ndarray:
+        """The dense tensor itself (float32) — only sensible on small grids."""
+        cfg = self.sweeps[0]._cfg
+        pts = np.concatenate([s._points.astype(np.float64) for s in self.sweeps])
+        off = np.cumsum([0] + [len(s._points) for s in self.sweeps])
+        fe = _frontend(cfg, len(pts), len(self.sweeps))
+        fe.voxelize(pts, off)
+        d = fe.emit_dense_input().cpu().numpy()
+        return d if self.batched else d[0]
+
+
+class sparse:  # noqa: N801 - mirrors `from tensorflow import sparse`
+    @staticmethod
+    def reshape(t: SparseVoxelTensor, shape: Sequence[int]) -> "DenseVoxelInput | SparseVoxelTensor":
+        if tuple(shape) == tuple(t.shape):
+            return t
+        if tuple(shape) == (1,) + tuple(t.shape):  # Predict.py:29
+            b = _BatchedSparse([t])
+            return b
+        raise ValueError("only the (1,)+shape reshape of Predict.py:29 is supported, got %s" % (tuple(shape),))
+
+    @staticmethod
+    def to_dense(t, default_value=0.0, validate_indices=False) -> DenseVoxelInput:
+        if default_value != 0.0:
+            raise ValueError("the reference only densifies with default_value=0. (model_training.py:279)")
+        if isinstance(t, _BatchedSparse):
+            return DenseVoxelInput(t.sweeps, batched=True)
+        return DenseVoxelInput([t], batched=False)
+
+
+class _BatchedSparse:
+    def __init__(self, sweeps):
+        self.sweeps = sweeps
+        self.shape = (len(sweeps),) + tuple(sweeps[0].shape)
+        self.dense_shape = list(self.shape)
+
+
+def stack(values: Sequence[DenseVoxelInput], axis: int = 0) -> DenseVoxelInput:
+    """tf.stack(points, axis=0) of per-sample dense tensors (model_training.py:285)."""
+    if axis != 0:
+        raise ValueError("the reference stacks on axis 0 only")
+    sweeps = []
+    for v in values:
+        if v.batched:
+            raise ValueError("stack() takes un-batched per-sample tensors")
+        sweeps.extend(v.sweeps)
+    return DenseVoxelInput(sweeps, batched=True)
+
+
+class RepeatLayer:  # model_training.py:32-40 — implicit in the fused kernel; kept so custom_objects={...} resolves
+    pass
+
+
+class MaxPoolingVFELayer:  # model_training.py:44-61
+    def __init__(self, combine=False, **kwargs):
+        self.combineDim = combine
+
+
+class VoxelNetFrontEnd:
+    """The first 23 Keras layers of createModel (model_training.py:229-235) with their weights."""
+
+    def __init__(self, nx, ny, nz, maxPoints, pack: dict):
+        self.grid = (nz, nx, ny)
+        self.maxPoints = maxPoints
+        self.pack = pack
+
+    def predict_voxel_grid(self, x: DenseVoxelInput, device: int = 0) -> torch.Tensor:
+        if not isinstance(x, DenseVoxelInput):
+            raise TypeError("expected the output of sparse.to_dense()/stack(); a materialised dense array would be "
+                            "the 500 GB path this library exists to avoid")
+        cfg = x.sweeps[0]._cfg
+        nz, nx, ny = self.grid
+        if (cfg[6], 2 * cfg[4], 2 * cfg[5]) != (nz, nx, ny) or cfg[3] != self.maxPoints:
+            raise ValueError("input shape %s does not match the model's InputVoxel (%d,%d,%d,%d,6)"
+                             % (x.shape, nz, nx, ny, self.maxPoints))
+        dts = {s._points.dtype for s in x.sweeps}
+        dt = np.float32 if dts == {np.dtype("float32")} else np.float64
+        pts = np.concatenate([s._points.astype(dt, copy=False) for s in x.sweeps])
+        off = np.cumsum([0] + [len(s._points) for s in x.sweeps]).astype(np.int64)
+        fe = _frontend(cfg, len(pts), len(x.sweeps), device)
+        if getattr(fe, "_pack", None) is not self.pack:
+            fe.set_weights(self.pack)
+            fe._pack = self.pack
+        return fe.forward_host(pts, off)
+
+
+def createModel(nx=K.nx, ny=K.ny, nz=K.nz, maxPoints=K.maxPoints, weights: Optional[dict] = None, seed: int = 0):
+    """model_training.py:222. Keras would random-initialise; `weights` (Keras-named arrays) or a seeded synthetic
+    pack stands in."""
+    return VoxelNetFrontEnd(nx, ny, nz, maxPoints, weights if weights is not None else synthetic_vfe_pack(seed))
+
+
+def load_model(path: str, custom_objects: Optional[dict] = None, nx=K.nx, ny=K.ny, nz=K.nz, maxPoints=K.maxPoints):
+    """Predict.py:51-52 / model_training.py:337-338. Reads a .npz weight pack with Keras layer names (h5py is not
+    available in this image; see lisec_b200/weights.py)."""
+    return VoxelNetFrontEnd(nx, ny, nz, maxPoints, load_npz(path))

@@ -255,8 +255,8 @@ int32_t lisec_set_vfe_weights(lisec_handle* h, const lisec_vfe_weights* w, void*
   const float* k1 = w->dense_kernel[1];  // (32,32): rows 0..15 pooled half, 16..31 pointwise half
   for (int k = 0; k < 16; ++k)
     for (int j = 0; j < 32; ++j) {
-      p.w2p[k][j] = k1[k * 32 + j];
-      p.w2x[k][j] = k1[(16 + k) * 32 + j];
+      p.w2p[k][j] = (double)k1[k * 32 + j];
+      p.w2x[k][j] = (double)k1[(16 + k) * 32 + j];
     }
   const float* k2 = w->dense_kernel[2];  // (64,64)
   for (int k = 0; k < 32; ++k)

@@ -30,8 +30,10 @@ struct SweepOffsets {
 // registers / the constant bank, with no per-thread load in the inner product loops.
 struct VfeParams {
   float w1[6][16];    // dense    (6,16)
-  float w2p[16][32];  // dense_1 rows 0..15  : multiply the pooled half   (Concatenate([pooling, layer]), :164-165)
-  float w2x[16][32];  // dense_1 rows 16..31 : multiply the pointwise half
+  // dense_1 is held in float64: its product is accumulated in float64 and rounded once. Its inputs (BN'd raw
+  // coordinates) are large and its two halves cancel, so this is where a float32 chain loses the 1e-5 budget.
+  double w2p[16][32];  // dense_1 rows 0..15  : multiply the pooled half   (Concatenate([pooling, layer]), :164-165)
+  double w2x[16][32];  // dense_1 rows 16..31 : multiply the pointwise half
   float w3p[32][64];  // dense_2 rows 0..31  : pooled half
   float w3x[32][64];  // dense_2 rows 32..63 : pointwise half
   float a1[16], b1[16];  // BN folded: y = x*a + b, a = gamma*rsqrt(var+eps), b = beta - mean*a

@@ -16,7 +16,8 @@ int vfe_rows_per_tile(int T) { return kVfeThreads - T + 1; }
 
 namespace {
 
-constexpr int kHS = 65;                     // float stride of a row in sH / sP (odd: conflict-free both ways)
+constexpr int kHS = 65;                     // float stride of a row in sH (odd: conflict-free both ways)
+constexpr int kPS = 66;                     // float stride of a row in sP (even: a row can also hold 32 doubles)
 constexpr int kMaxVox = kVfeThreads / 2;    // every voxel has >= 2 rows unless it is full (then T rows)
 
 template <typename PT>
@@ -61,7 +62,7 @@ struct VfeSmem {
 
 template <typename PT>
 constexpr size_t vfe_smem_bytes() {
-  return sizeof(float) * (kVfeThreads * kHS + kMaxVox * kHS) + sizeof(double) * kMaxVox * 3 +
+  return sizeof(float) * (kVfeThreads * kHS + kMaxVox * kPS) + sizeof(double) * kMaxVox * 3 +
          sizeof(PT) * kVfeThreads * 3 + sizeof(int) * (3 * kMaxVox + 4);
 }
 
@@ -75,8 +76,11 @@ __global__ void __launch_bounds__(kVfeThreads, 2)
   double* sCen = reinterpret_cast<double*>(smem_raw);
   PT* sPt = reinterpret_cast<PT*>(sCen + kMaxVox * 3);
   float* sH = reinterpret_cast<float*>(sPt + kVfeThreads * 3);
-  float* sP = sH + kVfeThreads * kHS;
-  int* sRowOff = reinterpret_cast<int*>(sP + kMaxVox * kHS);
+  float* sP = sH + kVfeThreads * kHS;  // 8-byte aligned: kVfeThreads * kHS is even
+  // pooled half of dense_1 in float64: row lv of sP viewed as doubles, floats [2, 66) (the voxel's own thread has
+  // read its pooled vector out of floats [0,16) before it writes these)
+  auto sQ2 = [sP](int lv) { return reinterpret_cast<double*>(sP + lv * kPS + 2); };
+  int* sRowOff = reinterpret_cast<int*>(sP + kMaxVox * kPS);
   int* sKept = sRowOff + kMaxVox + 1;
   int* sEstart = sKept + kMaxVox;
 
@@ -137,69 +141,86 @@ __global__ void __launch_bounds__(kVfeThreads, 2)
       float f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // pad row: six zeros (:141)
       if (real) point_features((double)px, (double)py, (double)pz, sCen[lv * 3], sCen[lv * 3 + 1], sCen[lv * 3 + 2], f);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float acc = 0.f;
+      for (int j = 0; j < 16; ++j) h1[j] = 0.f;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) acc = fmaf(f[k], P.w1[k][j], acc);
-        h1[j] = fmaxf(fmaf(acc, P.a1[j], P.b1[j]), 0.f);
+      for (int k = 0; k < 6; ++k)  // k outer, j inner: the weights of one k are contiguous -> 128-bit constant loads
+#pragma unroll
+        for (int j = 0; j < 16; ++j) h1[j] = fmaf(f[k], P.w1[k][j], h1[j]);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        h1[j] = fmaxf(fmaf(h1[j], P.a1[j], P.b1[j]), 0.f);
         sH[tid * kHS + j] = h1[j];
       }
     }
     __syncthreads();
-    pool_rows<16>(sH, sRowOff, nv, sP, kHS);  // MaxPoolingVFELayer over T (:160); RepeatLayer is implicit
+    pool_rows<16>(sH, sRowOff, nv, sP, kPS);  // MaxPoolingVFELayer over T (:160); RepeatLayer is implicit
     __syncthreads();
     if (tid < nv) {  // pooled half of dense_1, once per voxel
       float pool[16];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) pool[k] = sP[tid * kHS + k];
+      for (int k = 0; k < 16; ++k) pool[k] = sP[tid * kPS + k];
+      double acc[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float acc = 0.f;
+      for (int j = 0; j < 32; ++j) acc[j] = 0.0;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) acc = fmaf(pool[k], P.w2p[k][j], acc);
-        sP[tid * kHS + j] = acc;
-      }
+      for (int k = 0; k < 16; ++k)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = fma((double)pool[k], P.w2p[k][j], acc[j]);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sQ2(tid)[j] = acc[j];
     }
     __syncthreads();
 
     // ---- VFE-2: Dense(32->32) + BN + ReLU on concat[pooled, pointwise] (addVFELayer(., 32, 64), :232) ----
     float h2[32];
     if (has_row) {
+      // float64 accumulation of the whole 32-term product (pooled half first), one rounding to float32
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float acc = sP[lv * kHS + j];
+      for (int jc = 0; jc < 32; jc += 16) {
+        double acc[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) acc = fmaf(h1[k], P.w2x[k][j], acc);
-        h2[j] = fmaxf(fmaf(acc, P.a2[j], P.b2[j]), 0.f);
-        sH[tid * kHS + j] = h2[j];
+        for (int j = 0; j < 16; ++j) acc[j] = sQ2(lv)[jc + j];
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = fma((double)h1[k], P.w2x[k][jc + j], acc[j]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          h2[jc + j] = fmaxf(fmaf(__double2float_rn(acc[j]), P.a2[jc + j], P.b2[jc + j]), 0.f);
+          sH[tid * kHS + jc + j] = h2[jc + j];
+        }
       }
     }
     __syncthreads();
-    pool_rows<32>(sH, sRowOff, nv, sP, kHS);
+    pool_rows<32>(sH, sRowOff, nv, sP, kPS);
     __syncthreads();
     if (tid < nv) {  // pooled half of dense_2
       float pool[32];
 #pragma unroll
-      for (int k = 0; k < 32; ++k) pool[k] = sP[tid * kHS + k];
+      for (int k = 0; k < 32; ++k) pool[k] = sP[tid * kPS + k];
+float acc[64];
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        float acc = 0.f;
+      for (int j = 0; j < 64; ++j) acc[j] = 0.f;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) acc = fmaf(pool[k], P.w3p[k][j], acc);
-        sP[tid * kHS + j] = acc;
-      }
+      for (int k = 0; k < 32; ++k)
+#pragma unroll
+        for (int j = 0; j < 64; ++j) acc[j] = fmaf(pool[k], P.w3p[k][j], acc[j]);
+#pragma unroll
+      for (int j = 0; j < 64; ++j) sP[tid * kPS + j] = acc[j];
     }
     __syncthreads();
 
     // ---- FCN: Dense(64->64) + BN + ReLU (addFCN(., 64, 64), :233) ----
     if (has_row) {
+float acc[64];
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        float acc = sP[lv * kHS + j];
+      for (int j = 0; j < 64; ++j) acc[j] = sP[lv * kPS + j];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) acc = fmaf(h2[k], P.w3x[k][j], acc);
-        sH[tid * kHS + j] = fmaxf(fmaf(acc, P.a3[j], P.b3[j]), 0.f);
-      }
+      for (int k = 0; k < 32; ++k)
+#pragma unroll
+        for (int j = 0; j < 64; ++j) acc[j] = fmaf(h2[k], P.w3x[k][j], acc[j]);
+#pragma unroll
+      for (int j = 0; j < 64; ++j) sH[tid * kHS + j] = fmaxf(fmaf(acc[j], P.a3[j], P.b3[j]), 0.f);
     }
     __syncthreads();
     // MaxPoolingVFELayer(combine=True) (:235): one C3 row per voxel, written coalesced

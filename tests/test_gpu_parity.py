@@ -22,9 +22,10 @@ REL_TOL = 1e-5
 REF = dict(xSize=0.5, ySize=0.25, zSize=0.25, sampleSize=35, maxVoxelX=100, maxVoxelY=200, maxVoxelZ=8)
 
 
-def within(gpu, ref, tol=REL_TOL):
+def within(gpu, ref, tol=REL_TOL, floor=None):
     ref = np.asarray(ref, dtype=np.float64)
-    floor = np.sqrt(np.mean(ref * ref)) if ref.size else 1.0
+    if floor is None:
+        floor = np.sqrt(np.mean(ref * ref)) if ref.size else 1.0
     err = np.abs(np.asarray(gpu, dtype=np.float64) - ref) / np.maximum(np.abs(ref), floor)
     return float(err.max()) if err.size else 0.0
 
@@ -237,7 +238,8 @@ def test_grid_against_dense_reference_forward_small_grid():
         want = O.to_dense(ind, val, [4, 12, 20, 35, 6]).astype(np.float32)
         assert dense[s].tobytes() == want.tobytes()  # the reference's model input, bit for bit
         ref = O.vfe_forward(dense[s], pack, np.float64)  # the reference's dense formulation
-        assert within(grid[s], ref) <= REL_TOL
+        occ = ref[tuple(vox["coords"].T)]  # floor = RMS over the occupied voxels, as in the sparse tests
+        assert within(grid[s], ref, floor=np.sqrt(np.mean(occ * occ))) <= REL_TOL
     f.close()
 
 
