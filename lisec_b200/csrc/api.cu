@@ -14,7 +14,8 @@ struct lisec_handle {
   lisec_config cfg;
   Geom geom;
   Workspace ws;
-  VfeParams params;
+  VfeSmall params;
+  float wblob[kVfeBlobFloats];
   int sm_count = 0;
   int rows_per_tile = 0;
   long long max_voxels = 0;
@@ -72,7 +73,7 @@ cudaError_t dev_alloc(lisec_handle* h, T** p, size_t n) {
 void free_workspace(Workspace& w) {
   void* ptrs[] = {w.count, w.cell_voxel, w.cell_of_point, w.list_unsorted, w.list_sorted, w.entry_voxel,
                   w.voxel_cell, w.voxel_start, w.row_start, w.tile_first, w.block_sums, w.sweep_voxel_start,
-                  w.totals, w.voxel_feat, w.c_empty, w.staging, w.empty_desc};
+                  w.totals, w.voxel_feat, w.c_empty, w.vfe_w, w.staging, w.empty_desc};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   w = Workspace();
@@ -116,7 +117,7 @@ int do_voxelize(lisec_handle* h, const void* points, int dtype, const SweepOffse
 }
 
 int do_vfe(lisec_handle* h, float* voxel_feat, cudaStream_t st) {
-  LISEC_CUDA(h, launch_vfe(h->last_points, h->last_dtype, h->geom, h->params, h->ws.tile_first,
+  LISEC_CUDA(h, launch_vfe(h->last_points, h->last_dtype, h->geom, h->params, h->ws.vfe_w, h->ws.tile_first,
                            h->ws.voxel_start, h->ws.row_start, h->ws.list_sorted, h->ws.totals + TOT_TILES,
                            voxel_feat, h->sm_count, st, &h->launches));
   return LISEC_OK;
@@ -214,6 +215,7 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
   LISEC_CUDA(h, dev_alloc(h, &w.totals, (size_t)TOT_COUNT));
   LISEC_CUDA(h, dev_alloc(h, &w.voxel_feat, V * (size_t)c.c3));
   LISEC_CUDA(h, dev_alloc(h, &w.c_empty, (size_t)c.c3));
+  LISEC_CUDA(h, dev_alloc(h, &w.vfe_w, (size_t)kVfeBlobFloats));
   LISEC_CUDA(h, dev_alloc(h, reinterpret_cast<unsigned char**>(&w.staging), P * 3 * sizeof(double)));
   LISEC_CUDA(h, dev_alloc(h, &w.empty_desc, (size_t)8));
   // the one-voxel problem whose VFE output is c_empty: 0 kept points, 1 pad row, 1 tile
@@ -248,22 +250,14 @@ int32_t lisec_set_vfe_weights(lisec_handle* h, const lisec_vfe_weights* w, void*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
   h->launches = 0;
-  VfeParams& p = h->params;
+  VfeSmall& p = h->params;
   const float* k0 = w->dense_kernel[0];
   for (int k = 0; k < 6; ++k)
-    for (int j = 0; j < 16; ++j) p.w1[k][j] = k0[k * 16 + j];
-  const float* k1 = w->dense_kernel[1];  // (32,32): rows 0..15 pooled half, 16..31 pointwise half
-  for (int k = 0; k < 16; ++k)
-    for (int j = 0; j < 32; ++j) {
-      p.w2p[k][j] = (double)k1[k * 32 + j];
-      p.w2x[k][j] = (double)k1[(16 + k) * 32 + j];
-    }
-  const float* k2 = w->dense_kernel[2];  // (64,64)
-  for (int k = 0; k < 32; ++k)
-    for (int j = 0; j < 64; ++j) {
-      p.w3p[k][j] = k2[k * 64 + j];
-      p.w3x[k][j] = k2[(32 + k) * 64 + j];
-    }
+    for (int j = 0; j < 16; ++j) p.w1[k][j] = (double)k0[k * 16 + j];
+  // blob = [W2P | W2X | W3P | W3X]; a Keras kernel is (C_in, C_out) row-major with the pooled half's rows first
+  float* blob = h->wblob;
+  std::memcpy(blob, w->dense_kernel[1], sizeof(float) * 32 * 32);             // rows 0..15 = W2P, 16..31 = W2X
+  std::memcpy(blob + 32 * 32, w->dense_kernel[2], sizeof(float) * 64 * 64);   // rows 0..31 = W3P, 32..63 = W3X
   // BatchNormalization at inference (Keras defaults, model_training.py:171): y = x*a + b
   float* A[3] = {p.a1, p.a2, p.a3};
   float* B[3] = {p.b1, p.b2, p.b3};
@@ -276,8 +270,9 @@ int32_t lisec_set_vfe_weights(lisec_handle* h, const lisec_vfe_weights* w, void*
     }
   h->weights_set = true;
   // c_empty: the same kernel, run on one voxel that holds nothing but the pad row
+  LISEC_CUDA(h, cudaMemcpyAsync(h->ws.vfe_w, blob, sizeof(float) * kVfeBlobFloats, cudaMemcpyHostToDevice, st));
   const int* d = h->ws.empty_desc;
-  LISEC_CUDA(h, launch_vfe(nullptr, LISEC_F32, h->geom, p, d, d + 2, d + 4, nullptr,
+  LISEC_CUDA(h, launch_vfe(nullptr, LISEC_F32, h->geom, p, h->ws.vfe_w, d, d + 2, d + 4, nullptr,
                            reinterpret_cast<const long long*>(d + 6), h->ws.c_empty, h->sm_count, st,
                            &h->launches));
   LISEC_CUDA(h, cudaStreamSynchronize(st));

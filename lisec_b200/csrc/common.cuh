@@ -26,20 +26,18 @@ struct SweepOffsets {
 };
 
 // Folded VFE parameters, primary architecture (model_training.py:231-233): 6->16 | 32->32 | 64->64.
-// Passed as a __grid_constant__ kernel parameter: ptxas then feeds the weights to FFMA from uniform
-// registers / the constant bank, with no per-thread load in the inner product loops.
-struct VfeParams {
-  float w1[6][16];    // dense    (6,16)
-  // dense_1 is held in float64: its product is accumulated in float64 and rounded once. Its inputs (BN'd raw
-  // coordinates) are large and its two halves cancel, so this is where a float32 chain loses the 1e-5 budget.
-  double w2p[16][32];  // dense_1 rows 0..15  : multiply the pooled half   (Concatenate([pooling, layer]), :164-165)
-  double w2x[16][32];  // dense_1 rows 16..31 : multiply the pointwise half
-  float w3p[32][64];  // dense_2 rows 0..31  : pooled half
-  float w3x[32][64];  // dense_2 rows 32..63 : pointwise half
+// VfeSmall travels as a __grid_constant__ kernel parameter (uniform-register operands for the one-row-per-thread
+// first layer and the BN epilogues); the four larger matrices travel as one device blob that every CTA stages into
+// shared memory once: [W2P 16x32 | W2X 16x32 | W3P 32x64 | W3X 32x64] floats, row-major (C_in, C_out).
+//   W2P / W3P = kernel rows that multiply the POOLED half  (Concatenate([pooling, layer]), :164-165)
+//   W2X / W3X = kernel rows that multiply the pointwise half
+struct VfeSmall {
+  double w1[6][16];      // dense (6,16), held in float64: this product is accumulated in float64
   float a1[16], b1[16];  // BN folded: y = x*a + b, a = gamma*rsqrt(var+eps), b = beta - mean*a
   float a2[32], b2[32];
   float a3[64], b3[64];
 };
+constexpr int kVfeBlobFloats = 2 * 16 * 32 + 2 * 32 * 64;
 
 // totals[] slots (device, long long)
 enum {
@@ -76,6 +74,7 @@ struct Workspace {
   long long* totals = nullptr;       // [TOT_COUNT]
   float* voxel_feat = nullptr;       // [max_voxels, c3] for the fused entry point
   float* c_empty = nullptr;          // [c3]
+  float* vfe_w = nullptr;            // [kVfeBlobFloats] weight blob (see VfeSmall)
   void* staging = nullptr;           // host->device landing buffer for *_host entry points
   int* empty_desc = nullptr;         // 8 ints describing the one-voxel problem that yields c_empty
 };
@@ -90,10 +89,9 @@ cudaError_t launch_fill_and_order(long long n_total, const Geom& g, int rows_per
 cudaError_t launch_export(const void* pts, int pts_dtype, const SweepOffsets& so, const Geom& g,
                           const Workspace& w, long long max_voxels, int32_t* coords, int32_t* counts,
                           int32_t* point_idx, float* features, float* dense, cudaStream_t st, int* launches);
-cudaError_t launch_vfe(const void* pts, int pts_dtype, const Geom& g, const VfeParams& p, const int* tile_first,
-                       const int* voxel_start, const int* row_start, const int* list_sorted,
-                       const long long* n_tiles, float* voxel_feat, int sm_count, cudaStream_t st,
-                       int* launches);
+cudaError_t launch_vfe(const void* pts, int pts_dtype, const Geom& g, const VfeSmall& p, const float* wblob,
+                       const int* tile_first, const int* voxel_start, const int* row_start, const int* list_sorted,
+                       const long long* n_tiles, float* voxel_feat, int sm_count, cudaStream_t st, int* launches);
 cudaError_t launch_grid_write(const Geom& g, int n_sweeps, int c3, int grid_dtype, const int* cell_voxel,
                               const float* voxel_feat, const float* c_empty, void* grid, int sm_count,
                               cudaStream_t st, int* launches);

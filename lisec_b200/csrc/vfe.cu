@@ -1,14 +1,29 @@
 // Stacked VFE on sm_100a: centroid augmentation, three pointwise linears (+BN+ReLU), two per-voxel max-pools with
 // concat, and the final max over T — reference model_training.py:134-141 (features) and :155-186, 229-235 (layers).
 //
-// One thread owns one VFE row (a kept point, or the single virtual zero row that stands for all identical pad rows
-// of a non-full voxel). A tile is a run of whole voxels holding at most kVfeThreads rows. The
-// pointwise products run entirely in registers with the weights arriving as uniform-register / constant-bank
-// operands (VfeParams is a __grid_constant__ parameter), so the inner loops are pure FFMA. Because
-// Concatenate([pooled, pointwise]) feeds a bias-free Dense, the pooled half of the next layer's product is the
-// same for every row of a voxel: it is computed once per voxel and added as the accumulator's initial value.
-// Per-voxel max-pools go through shared memory (row-major, odd stride, conflict-free), not atomics.
+// Work unit: a tile = a run of whole voxels holding at most 256 VFE rows (a row is a kept point, or the single
+// virtual zero row that stands for all identical pad rows of a non-full voxel). One 256-thread CTA
+// per tile, persistent over tiles. Inside a tile every Dense is a small GEMM on on-chip data:
+//
+//     rows    H_next[256 x N] = H[256 x K] * Wx[K x N]  (+ Q[voxel(row)])       8x8 / 8x4 register tile per thread
+//     voxels  Q[128 x N]      = Pool[128 x K] * Wp[K x N]                        4x8 / 4x4 register tile per thread
+//
+// with the activations k-major in shared memory (A operand: 16-byte loads of 4 consecutive rows) and the weights in
+// shared memory ([K][N], 16-byte loads of 4 consecutive columns). This is the classic SIMT SGEMM inner loop:
+// 4 LDS.128 feed 64 FFMA, measured at 54 TFLOP/s on B200 against a 58.7 TFLOP/s FP32-pipe peak
+// (tools/ffma_probe.cu, tools/fp32_peak.cu); the earlier thread-per-row form topped out at 39.
+// Because Concatenate([pooled, pointwise]) feeds a bias-free Dense (model_training.py:164-165, 184), the pooled half
+// of the next product is the same for every row of a voxel: it is computed once per voxel (Q) and used as the
+// accumulators' initial value. Thread mapping: lane = 8 consecutive tile rows, warp = column group, so a voxel's rows
+// all sit in one warp and every max-pool is an in-register segmented max plus a 4-step segmented shuffle scan — no
+// shared-memory pooling passes, no atomics (ncu on the previous version: 48 % of the time in smem pooling loops).
+//
+// Precision (parity bar 1e-5 against the float64 oracle): dense (6->16) acts on raw coordinates up to +-50 m and is
+// accumulated in float64 (96 DFMA per row); dense_1's two halves cancel, so its 32-term sum is accumulated in
+// float32 blocks of 4 (a fresh accumulator per block, then added) — measured worst case 4.7e-6 over seeds and clouds,
+// the level of a CPU float32 forward; dense_2 is a plain float32 FMA chain.
 #include "common.cuh"
+#include "vfe_math.cuh"
 
 namespace lisec {
 
@@ -16,76 +31,219 @@ int vfe_rows_per_tile(int T) { return kVfeThreads - T + 1; }
 
 namespace {
 
-constexpr int kHS = 65;                     // float stride of a row in sH (odd: conflict-free both ways)
-constexpr int kPS = 66;                     // float stride of a row in sP (even: a row can also hold 32 doubles)
-constexpr int kMaxVox = kVfeThreads / 2;    // every voxel has >= 2 rows unless it is full (then T rows)
+constexpr int kRows = kVfeThreads;   // 256 rows per tile
+constexpr int kVox = kVfeThreads / 2;  // 128 voxels per tile: a non-full voxel has >= 2 rows, a full one T >= 2
+constexpr int PR = kRows + 4;        // float pitch of row-indexed k-major tiles (16-byte aligned rows, 4-bank skew)
+constexpr int PV = kVox + 4;         // float pitch of voxel-indexed k-major tiles
+constexpr int QS = 68;               // float stride of a voxel's row in sQ
 
-template <typename PT>
-__device__ __forceinline__ void load_point(const PT* __restrict__ pts, long long p, PT& x, PT& y, PT& z) {
-  x = __ldg(pts + 3 * p);
-  y = __ldg(pts + 3 * p + 1);
-  z = __ldg(pts + 3 * p + 2);
-}
+// shared-memory map (bytes)
+constexpr int OFF_W2P = 0;                         // [16][32]
+constexpr int OFF_W2X = OFF_W2P + 16 * 32 * 4;     // [16][32]
+constexpr int OFF_W3P = OFF_W2X + 16 * 32 * 4;     // [32][64]
+constexpr int OFF_W3X = OFF_W3P + 32 * 64 * 4;     // [32][64]
+constexpr int OFF_H1T = OFF_W3X + 32 * 64 * 4;     // [16][PR]   dense outputs of VFE-1, k-major
+constexpr int OFF_P1T = OFF_H1T + 16 * PR * 4;     // [16][PV]   pooled VFE-1
+constexpr int OFF_P2T = OFF_H1T;                   // [32][PV]   pooled VFE-2, reuses H1T+P1T (dead by then)
+constexpr int OFF_H2T = OFF_P1T + 16 * PV * 4;     // [32][PR]   VFE-2 outputs; later one 32-channel half of FCN outputs
+constexpr int OFF_Q = OFF_H2T + 32 * PR * 4;       // [kVox][QS] pooled-half products; later the pooled FCN rows
+constexpr int OFF_CEN = OFF_Q;                     // double[kVox][3], dead before Q is first written
+constexpr int OFF_PT = OFF_CEN + kVox * 3 * 8;     // PT[kRows][3]
+constexpr int OFF_ROWOFF = OFF_Q + kVox * QS * 4;  // int[kVox + 4]
+constexpr int OFF_ROWVOX = OFF_ROWOFF + (kVox + 4) * 4;  // uint8[kRows]
+constexpr int kSmemBytes = OFF_ROWVOX + kRows;
+constexpr int OFF_KEPT = OFF_H2T;                  // int[kVox], setup only
+constexpr int OFF_ESTART = OFF_KEPT + kVox * 4;    // int[kVox], setup only
+static_assert(32 * PV * 4 <= 16 * PR * 4 + 16 * PV * 4, "P2T must fit in H1T+P1T");
+static_assert(OFF_PT + kRows * 3 * 8 <= OFF_ROWOFF, "centroid/point staging must fit in the Q region");
+static_assert(2 * (kSmemBytes + 1024) <= 233472, "two CTAs per SM");
 
-// [x, y, z, x-cx, y-cy, z-cz]: subtraction in float64, one rounding to float32 (model_training.py:137-140 and the
-// float32 cast at the Keras model input)
-__device__ __forceinline__ void point_features(double x, double y, double z, double cx, double cy, double cz,
-                                               float (&f)[6]) {
-  f[0] = __double2float_rn(x);
-  f[1] = __double2float_rn(y);
-  f[2] = __double2float_rn(z);
-  f[3] = __double2float_rn(x - cx);
-  f[4] = __double2float_rn(y - cy);
-  f[5] = __double2float_rn(z - cz);
-}
-
-template <int C>
-__device__ __forceinline__ void pool_rows(const float* __restrict__ sH, const int* __restrict__ sRowOff, int nv,
-                                          float* __restrict__ dst, int dst_stride) {
-  for (int idx = threadIdx.x; idx < nv * C; idx += kVfeThreads) {
-    const int lv = idx / C, ch = idx % C;
-    const int rb = sRowOff[lv], re = sRowOff[lv + 1];
-    float m = sH[rb * kHS + ch];
-    for (int r = rb + 1; r < re; ++r) m = fmaxf(m, sH[r * kHS + ch]);
-    dst[lv * dst_stride + ch] = m;
+// ---- register-tile GEMM: acc[R][C] += A[k][row(r)] * W[k][col(c)], k = 0..K-1 -------------------------------
+// The lane's rows come as R/4 float4 chunks at row0 + i*chunk_stride (consecutive lanes -> consecutive 16 bytes);
+// the warp's columns come in groups of 4 at offsets coff[g] (same address for every lane: a broadcast load).
+// BLOCK4: float32 accumulation in blocks of 4 k-steps (see the precision note above).
+template <int R, int CG, int K, bool BLOCK4>
+__device__ __forceinline__ void tile_gemm(const float* __restrict__ sA, int pitch, int chunk_stride, int row0,
+                                          const float* __restrict__ sW, int ldw, const int (&coff)[CG],
+                                          float (&acc)[R][CG * 4]) {
+  static_assert(R % 4 == 0 && K % 4 == 0, "tile shape");
+  if (BLOCK4) {
+#pragma unroll 1
+    for (int kb = 0; kb < K; kb += 4) {
+      float blk[R][CG * 4];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < CG * 4; ++c) blk[r][c] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int k = kb + kk;
+        float a[R], b[CG * 4];
+#pragma unroll
+        for (int i = 0; i < R / 4; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(sA + k * pitch + row0 + chunk_stride * i);
+          a[4 * i] = v.x; a[4 * i + 1] = v.y; a[4 * i + 2] = v.z; a[4 * i + 3] = v.w;
+        }
+#pragma unroll
+        for (int g = 0; g < CG; ++g) {
+          const float4 v = *reinterpret_cast<const float4*>(sW + k * ldw + coff[g]);
+          b[4 * g] = v.x; b[4 * g + 1] = v.y; b[4 * g + 2] = v.z; b[4 * g + 3] = v.w;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int c = 0; c < CG * 4; ++c) blk[r][c] = fmaf(a[r], b[c], blk[r][c]);
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < CG * 4; ++c) acc[r][c] += blk[r][c];
+    }
+  } else {
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+      float a[R], b[CG * 4];
+#pragma unroll
+      for (int i = 0; i < R / 4; ++i) {
+        const float4 v = *reinterpret_cast<const float4*>(sA + k * pitch + row0 + chunk_stride * i);
+        a[4 * i] = v.x; a[4 * i + 1] = v.y; a[4 * i + 2] = v.z; a[4 * i + 3] = v.w;
+      }
+#pragma unroll
+      for (int g = 0; g < CG; ++g) {
+        const float4 v = *reinterpret_cast<const float4*>(sW + k * ldw + coff[g]);
+        b[4 * g] = v.x; b[4 * g + 1] = v.y; b[4 * g + 2] = v.z; b[4 * g + 3] = v.w;
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < CG * 4; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
+    }
   }
 }
 
-struct VfeSmem {
-  float* sH;      // [kVfeThreads][kHS]  layer outputs, one row per thread
-  float* sP;      // [kMaxVox][kHS]      pooled vector, then (in place) its product with the pooled-half weights
-  double* sCen;   // [kMaxVox][3]
-  int* sRowOff;   // [kMaxVox + 1]
-  int* sKept;     // [kMaxVox]
-  int* sEstart;   // [kMaxVox]
+// position of tile row r inside a k-major row tile: lane l = r/8 owns rows 8l..8l+7 and loads them as two float4 at
+// 4l and 128+4l, so both 16-byte loads of a warp cover 512 contiguous bytes (no bank conflicts)
+__device__ __forceinline__ int row_pos(int r) { return ((r >> 3) << 2) + (r & 3) + ((r & 4) << 5); }
+
+// ---- per-voxel max in registers ----------------------------------------------------------------------------
+// A lane holds 8 consecutive tile rows, a warp all 256 of them, so every voxel (a run of consecutive rows) lives in
+// one warp. Column-independent bookkeeping, computed once per tile:
+struct PoolMeta {
+  int v[8];          // local voxel of each of the lane's rows (255 = padding row past the tile's last row)
+  unsigned bnd;      // bit r (1..7): row r starts a new voxel inside this lane
+  int kh, kt;        // voxel of the first / last row
+  bool cont;         // the first row's voxel continues from the previous lane
+  bool emit_head;    // the first row's voxel ends inside this lane
+  bool emit_tail;    // the last row's voxel starts and ends inside this lane (and is not the first row's voxel)
+  bool take[4];      // segmented-scan schedule over lanes, distances 1,2,4,8 (a voxel spans at most 9 lanes for T<=64)
 };
 
-template <typename PT>
-constexpr size_t vfe_smem_bytes() {
-  return sizeof(float) * (kVfeThreads * kHS + kMaxVox * kPS) + sizeof(double) * kMaxVox * 3 +
-         sizeof(PT) * kVfeThreads * 3 + sizeof(int) * (3 * kMaxVox + 4);
+__device__ __forceinline__ PoolMeta make_pool_meta(const unsigned char* __restrict__ sRowVox, int lane) {
+  PoolMeta m;
+  const uint2 rv = *reinterpret_cast<const uint2*>(sRowVox + lane * 8);
+  m.bnd = 0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    m.v[r] = ((r < 4 ? rv.x : rv.y) >> (8 * (r & 3))) & 0xff;
+    if (r > 0 && m.v[r] != m.v[r - 1]) m.bnd |= 1u << r;
+  }
+  m.kh = m.v[0];
+  m.kt = m.v[7];
+  const bool whole = m.bnd == 0;
+  const int prev_kt = __shfl_up_sync(0xffffffffu, m.kt, 1);
+  const int next_kh = __shfl_down_sync(0xffffffffu, m.kh, 1);
+  m.cont = lane > 0 && prev_kt == m.kh;
+  const bool tail_cont = lane < 31 && next_kh == m.kt;
+  m.emit_head = whole ? !tail_cont : true;
+  m.emit_tail = !whole && !tail_cont;
+  // inclusive segmented max-scan over lanes of the "last voxel of the lane" values; a lane extends the run of its
+  // predecessor iff it is one whole voxel that continues from it
+  bool flag = !(whole && m.cont);
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const bool up = __shfl_up_sync(0xffffffffu, flag, 1 << s);
+    m.take[s] = lane >= (1 << s) && !flag;
+    if (m.take[s]) flag = up;
+  }
+  return m;
+}
+
+// val[r][c]: the lane's 8 rows x NC columns. emit(voxel, values[NC]) is called exactly once per voxel, by the lane
+// in which the voxel ends, with the max over all of the voxel's rows for the lane's NC columns.
+template <int NC, typename Emit>
+__device__ __forceinline__ void pool_lane_rows(const float (&val)[8][NC], const PoolMeta& m, Emit emit) {
+  float run[NC], head[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) run[c] = val[0][c];
+  bool first = true;
+#pragma unroll
+  for (int r = 1; r < 8; ++r) {
+    if (m.bnd & (1u << r)) {
+      if (first) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) head[c] = run[c];
+        first = false;
+      } else {  // a voxel that starts and ends inside the lane
+        emit(m.v[r - 1], run);
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) run[c] = val[r][c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) run[c] = fmaxf(run[c], val[r][c]);
+    }
+  }
+  if (first) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) head[c] = run[c];
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    float x = run[c];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const float y = __shfl_up_sync(0xffffffffu, x, 1 << s);
+      if (m.take[s]) x = fmaxf(x, y);
+    }
+    const float in = __shfl_up_sync(0xffffffffu, x, 1);
+    if (m.cont) head[c] = fmaxf(in, head[c]);
+  }
+  if (m.emit_head) emit(m.kh, head);
+  if (m.emit_tail) emit(m.kt, run);
 }
 
 template <typename PT>
 __global__ void __launch_bounds__(kVfeThreads, 2)
-    vfe_kernel(const PT* __restrict__ pts, const __grid_constant__ VfeParams P, int T,
+    vfe_kernel(const PT* __restrict__ pts, const __grid_constant__ VfeSmall P, const float* __restrict__ wblob, int T,
                const int* __restrict__ tile_first, const int* __restrict__ voxel_start,
                const int* __restrict__ row_start, const int* __restrict__ list_sorted,
                const long long* __restrict__ n_tiles_ptr, float* __restrict__ voxel_feat) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* sCen = reinterpret_cast<double*>(smem_raw);
-  PT* sPt = reinterpret_cast<PT*>(sCen + kMaxVox * 3);
-  float* sH = reinterpret_cast<float*>(sPt + kVfeThreads * 3);
-  float* sP = sH + kVfeThreads * kHS;  // 8-byte aligned: kVfeThreads * kHS is even
-  // pooled half of dense_1 in float64: row lv of sP viewed as doubles, floats [2, 66) (the voxel's own thread has
-  // read its pooled vector out of floats [0,16) before it writes these)
-  auto sQ2 = [sP](int lv) { return reinterpret_cast<double*>(sP + lv * kPS + 2); };
-  int* sRowOff = reinterpret_cast<int*>(sP + kMaxVox * kPS);
-  int* sKept = sRowOff + kMaxVox + 1;
-  int* sEstart = sKept + kMaxVox;
+  extern __shared__ __align__(16) unsigned char smem[];
+  float* sW2P = reinterpret_cast<float*>(smem + OFF_W2P);
+  float* sW2X = reinterpret_cast<float*>(smem + OFF_W2X);
+  float* sW3P = reinterpret_cast<float*>(smem + OFF_W3P);
+  float* sW3X = reinterpret_cast<float*>(smem + OFF_W3X);
+  float* sH1T = reinterpret_cast<float*>(smem + OFF_H1T);
+  float* sP1T = reinterpret_cast<float*>(smem + OFF_P1T);
+  float* sP2T = reinterpret_cast<float*>(smem + OFF_P2T);
+  float* sH2T = reinterpret_cast<float*>(smem + OFF_H2T);
+  float* sQ = reinterpret_cast<float*>(smem + OFF_Q);
+  double* sCen = reinterpret_cast<double*>(smem + OFF_CEN);
+  PT* sPt = reinterpret_cast<PT*>(smem + OFF_PT);
+  int* sRowOff = reinterpret_cast<int*>(smem + OFF_ROWOFF);
+  unsigned char* sRowVox = smem + OFF_ROWVOX;
+  int* sKept = reinterpret_cast<int*>(smem + OFF_KEPT);
+  int* sEstart = reinterpret_cast<int*>(smem + OFF_ESTART);
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // register tiles: lane = row group (8 tile rows / 4 voxel rows), warp = column group
   const int n_tiles = (int)*n_tiles_ptr;
+  if ((int)blockIdx.x >= n_tiles) return;
+
+  // weights: [W2P | W2X | W3P | W3X] as laid out by the host, straight into the first 20 KB
+  for (int i = tid; i < (OFF_H1T / 16); i += kVfeThreads)
+    reinterpret_cast<float4*>(smem)[i] = __ldg(reinterpret_cast<const float4*>(wblob) + i);
+
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int v0 = tile_first[t];
     const int nv = tile_first[t + 1] - v0;
@@ -100,7 +258,7 @@ __global__ void __launch_bounds__(kVfeThreads, 2)
     __syncthreads();
     const int nrows = sRowOff[nv];
     const bool has_row = tid < nrows;
-    int lv = 0;
+    int lv = 255;  // padding row
     bool real = false;
     PT px = PT(0), py = PT(0), pz = PT(0);
     if (has_row) {
@@ -117,6 +275,7 @@ __global__ void __launch_bounds__(kVfeThreads, 2)
       sPt[tid * 3 + 1] = py;
       sPt[tid * 3 + 2] = pz;
     }
+    sRowVox[tid] = (unsigned char)lv;
     __syncthreads();
     // centroid = np.mean(currPoints, axis=0) (model_training.py:135): float64, rows added in list order, one divide
     if (tid < nv) {
@@ -128,215 +287,162 @@ __global__ void __launch_bounds__(kVfeThreads, 2)
         sy += (double)q[3 * i + 1];
         sz += (double)q[3 * i + 2];
       }
-      const double inv_n = (double)(kept > 0 ? kept : 1);
-      sCen[tid * 3] = sx / inv_n;
-      sCen[tid * 3 + 1] = sy / inv_n;
-      sCen[tid * 3 + 2] = sz / inv_n;
+      const double n = (double)(kept > 0 ? kept : 1);
+      sCen[tid * 3] = sx / n;
+      sCen[tid * 3 + 1] = sy / n;
+      sCen[tid * 3 + 2] = sz / n;
     }
     __syncthreads();
 
-    // ---- VFE-1: Dense(6->16, no bias) + BN + ReLU (addVFELayer(in, 6, 32), :231 -> :155-166) ----
-    float h1[16];
-    if (has_row) {
+    // ---- VFE-1: Dense(6->16, no bias) + BN + ReLU (addVFELayer(in, 6, 32), :231 -> :155-166); one row per thread ----
+    {
       float f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // pad row: six zeros (:141)
       if (real) point_features((double)px, (double)py, (double)pz, sCen[lv * 3], sCen[lv * 3 + 1], sCen[lv * 3 + 2], f);
+      double d[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) h1[j] = 0.f;
+      for (int j = 0; j < 16; ++j) d[j] = 0.0;
 #pragma unroll
-      for (int k = 0; k < 6; ++k)  // k outer, j inner: the weights of one k are contiguous -> 128-bit constant loads
+      for (int k = 0; k < 6; ++k) {
+        const double fk = (double)f[k];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) h1[j] = fmaf(f[k], P.w1[k][j], h1[j]);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        h1[j] = fmaxf(fmaf(h1[j], P.a1[j], P.b1[j]), 0.f);
-        sH[tid * kHS + j] = h1[j];
+        for (int j = 0; j < 16; ++j) d[j] = fma(fk, P.w1[k][j], d[j]);
       }
+      const int pos = row_pos(tid);
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        sH1T[j * PR + pos] = has_row ? fmaxf(fmaf(__double2float_rn(d[j]), P.a1[j], P.b1[j]), 0.f) : 0.f;
     }
     __syncthreads();
-    pool_rows<16>(sH, sRowOff, nv, sP, kPS);  // MaxPoolingVFELayer over T (:160); RepeatLayer is implicit
-    __syncthreads();
-    if (tid < nv) {  // pooled half of dense_1, once per voxel
-      float pool[16];
+    const PoolMeta meta = make_pool_meta(sRowVox, lane);
+    {  // MaxPoolingVFELayer over T (:160); RepeatLayer is implicit. Warp w pools channels 2w, 2w+1.
+      float val[8][2];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) pool[k] = sP[tid * kPS + k];
-      double acc[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = 0.0;
-#pragma unroll
-      for (int k = 0; k < 16; ++k)
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = fma((double)pool[k], P.w2p[k][j], acc[j]);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) sQ2(tid)[j] = acc[j];
+      for (int c = 0; c < 2; ++c) {
+        const float* src = sH1T + (2 * warp + c) * PR;
+        const float4 lo = *reinterpret_cast<const float4*>(src + 4 * lane);
+        const float4 hi = *reinterpret_cast<const float4*>(src + 128 + 4 * lane);
+        val[0][c] = lo.x; val[1][c] = lo.y; val[2][c] = lo.z; val[3][c] = lo.w;
+        val[4][c] = hi.x; val[5][c] = hi.y; val[6][c] = hi.z; val[7][c] = hi.w;
+      }
+      pool_lane_rows<2>(val, meta, [&](int v, const float(&x)[2]) {
+        if (v < nv) {
+          sP1T[(2 * warp) * PV + v] = x[0];
+          sP1T[(2 * warp + 1) * PV + v] = x[1];
+        }
+      });
     }
     __syncthreads();
 
     // ---- VFE-2: Dense(32->32) + BN + ReLU on concat[pooled, pointwise] (addVFELayer(., 32, 64), :232) ----
-    float h2[32];
-    if (has_row) {
-      // float64 accumulation of the whole 32-term product (pooled half first), one rounding to float32
+    const int coff4[1] = {warp * 4};
+    {  // pooled half, once per voxel: Q2[128 x 32] = P1[128 x 16] * W2p; 4x4 tile per thread
+      float acc[4][4];
 #pragma unroll
-      for (int jc = 0; jc < 32; jc += 16) {
-        double acc[16];
+      for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = sQ2(lv)[jc + j];
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+      tile_gemm<4, 1, 16, true>(sP1T, PV, 0, lane * 4, sW2P, 32, coff4, acc);
 #pragma unroll
-        for (int k = 0; k < 16; ++k)
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = fma((double)h1[k], P.w2x[k][jc + j], acc[j]);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          h2[jc + j] = fmaxf(fmaf(__double2float_rn(acc[j]), P.a2[jc + j], P.b2[jc + j]), 0.f);
-          sH[tid * kHS + jc + j] = h2[jc + j];
-        }
-      }
+      for (int r = 0; r < 4; ++r)
+        *reinterpret_cast<float4*>(sQ + (lane * 4 + r) * QS + warp * 4) =
+            make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
     }
     __syncthreads();
-    pool_rows<32>(sH, sRowOff, nv, sP, kPS);
-    __syncthreads();
-    if (tid < nv) {  // pooled half of dense_2
-      float pool[32];
+    {  // rows: 8x4 tile per thread, accumulators start at the voxel's pooled-half product
+      float acc[8][4];
 #pragma unroll
-      for (int k = 0; k < 32; ++k) pool[k] = sP[tid * kPS + k];
-float acc[64];
+      for (int r = 0; r < 8; ++r) {
+        const float4 q = *reinterpret_cast<const float4*>(sQ + (meta.v[r] & (kVox - 1)) * QS + warp * 4);
+        acc[r][0] = q.x; acc[r][1] = q.y; acc[r][2] = q.z; acc[r][3] = q.w;
+      }
+      tile_gemm<8, 1, 16, true>(sH1T, PR, 128, lane * 4, sW2X, 32, coff4, acc);
 #pragma unroll
-      for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+      for (int c = 0; c < 4; ++c) {
+        const float a = P.a2[warp * 4 + c], b = P.b2[warp * 4 + c];
 #pragma unroll
-      for (int k = 0; k < 32; ++k)
+        for (int r = 0; r < 8; ++r) acc[r][c] = fmaxf(fmaf(acc[r][c], a, b), 0.f);
+        float* dst = sH2T + (warp * 4 + c) * PR + 4 * lane;
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+        *reinterpret_cast<float4*>(dst + 128) = make_float4(acc[4][c], acc[5][c], acc[6][c], acc[7][c]);
+      }
+      __syncthreads();  // every warp is done with sH1T (A operand) and sQ: sP2T may now overwrite sH1T/sP1T
+      pool_lane_rows<4>(acc, meta, [&](int v, const float(&x)[4]) {
+        if (v < nv) {
 #pragma unroll
-        for (int j = 0; j < 64; ++j) acc[j] = fmaf(pool[k], P.w3p[k][j], acc[j]);
-#pragma unroll
-      for (int j = 0; j < 64; ++j) sP[tid * kPS + j] = acc[j];
+          for (int c = 0; c < 4; ++c) sP2T[(warp * 4 + c) * PV + v] = x[c];
+        }
+      });
     }
     __syncthreads();
 
-    // ---- FCN: Dense(64->64) + BN + ReLU (addFCN(., 64, 64), :233) ----
-    if (has_row) {
-float acc[64];
+    // ---- FCN: Dense(64->64) + BN + ReLU (addFCN(., 64, 64), :233), then MaxPoolingVFELayer(combine=True) (:235) ----
+    const int coff8[2] = {warp * 4, 32 + warp * 4};  // this warp's 8 output channels
+    {  // pooled half: Q3[128 x 64] = P2[128 x 32] * W3p; 4x8 tile per thread
+      float acc[4][8];
 #pragma unroll
-      for (int j = 0; j < 64; ++j) acc[j] = sP[lv * kPS + j];
+      for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int k = 0; k < 32; ++k)
+        for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+      tile_gemm<4, 2, 32, false>(sP2T, PV, 0, lane * 4, sW3P, 64, coff8, acc);
 #pragma unroll
-        for (int j = 0; j < 64; ++j) acc[j] = fmaf(h2[k], P.w3x[k][j], acc[j]);
-#pragma unroll
-      for (int j = 0; j < 64; ++j) sH[tid * kHS + j] = fmaxf(fmaf(acc[j], P.a3[j], P.b3[j]), 0.f);
+      for (int r = 0; r < 4; ++r) {
+        float* dst = sQ + (lane * 4 + r) * QS;
+        *reinterpret_cast<float4*>(dst + coff8[0]) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        *reinterpret_cast<float4*>(dst + coff8[1]) = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+      }
     }
     __syncthreads();
-    // MaxPoolingVFELayer(combine=True) (:235): one C3 row per voxel, written coalesced
-    pool_rows<64>(sH, sRowOff, nv, voxel_feat + (size_t)v0 * 64, 64);
-    __syncthreads();
-  }
-}
-
-// ---- export of the grouping in the reference's terms (tests, drop-in COO/dense emission) ------------------
-template <typename PT>
-__global__ void __launch_bounds__(256) export_kernel(const PT* __restrict__ pts, const __grid_constant__ SweepOffsets so,
-                                                     const __grid_constant__ Geom g,
-                                                     const int* __restrict__ voxel_cell,
-                                                     const int* __restrict__ voxel_start,
-                                                     const int* __restrict__ list_sorted,
-                                                     const long long* __restrict__ totals, int32_t* __restrict__ coords,
-                                                     int32_t* __restrict__ counts, int32_t* __restrict__ point_idx,
-                                                     float* __restrict__ features, float* __restrict__ dense) {
-  const int lane = threadIdx.x & 31;
-  const long long n_voxels = totals[TOT_VOXELS];
-  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long v = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < n_voxels; v += warps) {
-    const int cell = voxel_cell[v];
-    const int sweep = cell / g.cells;
-    const int rem = cell - sweep * g.cells;
-    const int s = voxel_start[v];
-    const int c = voxel_start[v + 1] - s;
-    const int kept = c < g.T ? c : g.T;
-    if (lane == 0) {
-      if (coords) {
-        coords[4 * v] = sweep;
-        coords[4 * v + 1] = rem / (g.nx * g.ny);
-        coords[4 * v + 2] = (rem / g.ny) % g.nx;
-        coords[4 * v + 3] = rem % g.ny;
-      }
-      if (counts) counts[v] = c;
-    }
-    double cx = 0.0, cy = 0.0, cz = 0.0;
-    if (features || dense) {
-      for (int i = 0; i < kept; ++i) {  // same operation order as the VFE kernel: sequential float64 adds
-        PT x, y, z;
-        load_point(pts, (long long)list_sorted[s + i], x, y, z);
-        cx += (double)x;
-        cy += (double)y;
-        cz += (double)z;
-      }
-      const double n = (double)(kept > 0 ? kept : 1);
-      cx /= n;
-      cy /= n;
-      cz /= n;
-    }
-    for (int i = lane; i < g.T; i += 32) {
-      const bool real = i < kept;
-      const int p = real ? list_sorted[s + i] : -1;
-      if (point_idx) point_idx[v * g.T + i] = real ? (int)(p - so.off[sweep]) : -1;
-      if (features || dense) {
-        float f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (real) {
-          PT x, y, z;
-          load_point(pts, (long long)p, x, y, z);
-          point_features((double)x, (double)y, (double)z, cx, cy, cz, f);
-        }
-        if (features) {
+    {  // rows: 8x8 tile per thread; the per-voxel max goes straight from registers to the output row
+      float out[8][8];
 #pragma unroll
-          for (int j = 0; j < 6; ++j) features[(v * g.T + i) * 6 + j] = f[j];
-        }
-        if (dense && real) {  // dense was zero-filled: sparse.to_dense(default_value=0.) (model_training.py:279)
-#pragma unroll
-          for (int j = 0; j < 6; ++j) dense[((long long)cell * g.T + i) * 6 + j] = f[j];
-        }
+      for (int r = 0; r < 8; ++r) {
+        const float* q = sQ + (meta.v[r] & (kVox - 1)) * QS;
+        const float4 q0 = *reinterpret_cast<const float4*>(q + coff8[0]);
+        const float4 q1 = *reinterpret_cast<const float4*>(q + coff8[1]);
+        out[r][0] = q0.x; out[r][1] = q0.y; out[r][2] = q0.z; out[r][3] = q0.w;
+        out[r][4] = q1.x; out[r][5] = q1.y; out[r][6] = q1.z; out[r][7] = q1.w;
       }
+      tile_gemm<8, 2, 32, false>(sH2T, PR, 128, lane * 4, sW3X, 64, coff8, out);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int col = coff8[c >> 2] + (c & 3);
+        const float a = P.a3[col], b = P.b3[col];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) out[r][c] = fmaxf(fmaf(out[r][c], a, b), 0.f);
+      }
+      float* dst_base = voxel_feat + (size_t)v0 * 64;
+      pool_lane_rows<8>(out, meta, [&](int v, const float(&x)[8]) {
+        if (v < nv) {  // two 16-byte stores per voxel and warp; the 8 warps complete the 256-byte row
+          float* dst = dst_base + (size_t)v * 64;
+          *reinterpret_cast<float4*>(dst + coff8[0]) = make_float4(x[0], x[1], x[2], x[3]);
+          *reinterpret_cast<float4*>(dst + coff8[1]) = make_float4(x[4], x[5], x[6], x[7]);
+        }
+      });
     }
+    __syncthreads();  // the next tile's setup reuses sRowOff / sH2T / sQ
   }
 }
 
 }  // namespace
 
-cudaError_t launch_vfe(const void* pts, int pts_dtype, const Geom& g, const VfeParams& p, const int* tile_first,
-                       const int* voxel_start, const int* row_start, const int* list_sorted,
-                       const long long* n_tiles, float* voxel_feat, int sm_count, cudaStream_t st,
-                       int* launches) {
+cudaError_t launch_vfe(const void* pts, int pts_dtype, const Geom& g, const VfeSmall& p, const float* wblob,
+                       const int* tile_first, const int* voxel_start, const int* row_start, const int* list_sorted,
+                       const long long* n_tiles, float* voxel_feat, int sm_count, cudaStream_t st, int* launches) {
   cudaError_t err;
   const int grid = 2 * sm_count;  // persistent: two resident CTAs per SM, tiles strided over them
   if (pts_dtype == LISEC_F32) {
-    err = cudaFuncSetAttribute(vfe_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)vfe_smem_bytes<float>());
+    err = cudaFuncSetAttribute(vfe_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (err != cudaSuccess) return err;
-    vfe_kernel<float><<<grid, kVfeThreads, vfe_smem_bytes<float>(), st>>>(
-        static_cast<const float*>(pts), p, g.T, tile_first, voxel_start, row_start, list_sorted, n_tiles,
-        voxel_feat);
+    vfe_kernel<float><<<grid, kVfeThreads, kSmemBytes, st>>>(static_cast<const float*>(pts), p, wblob, g.T,
+                                                            tile_first, voxel_start, row_start, list_sorted,
+                                                            n_tiles, voxel_feat);
   } else {
-    err = cudaFuncSetAttribute(vfe_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)vfe_smem_bytes<double>());
+    err = cudaFuncSetAttribute(vfe_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (err != cudaSuccess) return err;
-    vfe_kernel<double><<<grid, kVfeThreads, vfe_smem_bytes<double>(), st>>>(
-        static_cast<const double*>(pts), p, g.T, tile_first, voxel_start, row_start, list_sorted, n_tiles,
-        voxel_feat);
+    vfe_kernel<double><<<grid, kVfeThreads, kSmemBytes, st>>>(static_cast<const double*>(pts), p, wblob, g.T,
+                                                             tile_first, voxel_start, row_start, list_sorted,
+                                                             n_tiles, voxel_feat);
   }
-  ++*launches;
-  return cudaGetLastError();
-}
-
-cudaError_t launch_export(const void* pts, int pts_dtype, const SweepOffsets& so, const Geom& g,
-                          const Workspace& w, long long max_voxels, int32_t* coords, int32_t* counts,
-                          int32_t* point_idx, float* features, float* dense, cudaStream_t st, int* launches) {
-  long long blocks = (max_voxels * 32 + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  if (blocks < 1) blocks = 1;
-  if (pts_dtype == LISEC_F32)
-    export_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(pts), so, g, w.voxel_cell,
-                                                           w.voxel_start, w.list_sorted, w.totals, coords, counts,
-                                                           point_idx, features, dense);
-  else
-    export_kernel<double><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const double*>(pts), so, g, w.voxel_cell,
-                                                            w.voxel_start, w.list_sorted, w.totals, coords, counts,
-                                                            point_idx, features, dense);
   ++*launches;
   return cudaGetLastError();
 }

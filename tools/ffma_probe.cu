@@ -9,6 +9,9 @@
 #include <vector>
 
 struct W { float w[32][64]; };
+#ifndef REP
+#define REP 1
+#endif
 
 __global__ void __launch_bounds__(256, 2) k_uniform(const __grid_constant__ W w, const float* __restrict__ H,
                                                     float* __restrict__ D, int M) {
@@ -22,10 +25,15 @@ __global__ void __launch_bounds__(256, 2) k_uniform(const __grid_constant__ W w,
     float acc[64];
 #pragma unroll
     for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+#pragma unroll 1
+    for (int rep = 0; rep < REP; ++rep) {
 #pragma unroll
     for (int k = 0; k < 32; ++k)
 #pragma unroll
       for (int j = 0; j < 64; ++j) acc[j] = fmaf(h[k], w.w[k][j], acc[j]);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) h[k] *= 0.5f;
+    }
     float m = 0.f;
 #pragma unroll
     for (int j = 0; j < 64; ++j) m += fmaxf(acc[j], 0.f);
@@ -68,6 +76,8 @@ __global__ void __launch_bounds__(256, 2) k_smem(const float* __restrict__ Wg, c
       for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < COLS_PER_THREAD; ++j) acc[i][j] = 0.f;
+#pragma unroll 1
+      for (int rep = 0; rep < REP; ++rep)
 #pragma unroll 8
       for (int k = 0; k < 32; ++k) {
         float a[8], b[COLS_PER_THREAD];
@@ -222,6 +232,121 @@ __global__ void __launch_bounds__(256, 2) k_smem2c(const float* __restrict__ Wg,
   }
 }
 
+// H: warp w owns output columns [8w, 8w+8) with those weights in uniform registers (all lanes use the same
+// weights); lane owns rows {lane + 32 i} (VEC=false, 8 conflict-free LDS.32 per k) or rows [8 lane, 8 lane + 8)
+// (VEC=true, 2 LDS.128 per k). Every warp streams the whole A tile from shared memory.
+template <bool VEC>
+__global__ void __launch_bounds__(256, 2) k_hybrid(const __grid_constant__ W w, const float* __restrict__ H,
+                                                   float* __restrict__ D, int M) {
+  extern __shared__ __align__(16) float smem[];
+  float* sA = smem;  // [32][PITCH]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int tile = blockIdx.x; tile * TM < M; tile += gridDim.x) {
+    __syncthreads();
+    {
+      const float* src = H + ((size_t)tile * TM + tid) * 32;
+#pragma unroll
+      for (int k = 0; k < 32; k += 4) {
+        float4 v = *reinterpret_cast<const float4*>(src + k);
+        sA[(k + 0) * PITCH + tid] = v.x; sA[(k + 1) * PITCH + tid] = v.y;
+        sA[(k + 2) * PITCH + tid] = v.z; sA[(k + 3) * PITCH + tid] = v.w;
+      }
+    }
+    __syncthreads();
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    // the column block is warp-uniform: switch so that each case indexes the constant bank statically
+#define HYB_BODY(CW)                                                                                   \
+    _Pragma("unroll 4") for (int k = 0; k < 32; ++k) {                                                 \
+      float a[8];                                                                                      \
+      if (VEC) {                                                                                       \
+        const float4 a0 = *reinterpret_cast<const float4*>(sA + k * PITCH + lane * 8);                 \
+        const float4 a1 = *reinterpret_cast<const float4*>(sA + k * PITCH + lane * 8 + 4);             \
+        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w; \
+      } else {                                                                                         \
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) a[i] = sA[k * PITCH + lane + 32 * i];            \
+      }                                                                                                \
+      _Pragma("unroll") for (int i = 0; i < 8; ++i)                                                    \
+        _Pragma("unroll") for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], w.w[k][(CW) * 8 + j], acc[i][j]); \
+    }
+    switch (warp) {
+      case 0: HYB_BODY(0) break;
+      case 1: HYB_BODY(1) break;
+      case 2: HYB_BODY(2) break;
+      case 3: HYB_BODY(3) break;
+      case 4: HYB_BODY(4) break;
+      case 5: HYB_BODY(5) break;
+      case 6: HYB_BODY(6) break;
+      default: HYB_BODY(7) break;
+    }
+    float out = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) out += fmaxf(acc[i][j], 0.f);
+    D[(size_t)tile * TM + tid] = out;
+  }
+}
+
+// Hc / Hs: the hybrid data flow with ONE loop body for all warps. MODE 0: weights by dynamically indexed constant
+// load (w.w[k][8*warp + j]); MODE 1: weights from shared memory, warp-uniform address (broadcast LDS.128).
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) k_hybrid1(const __grid_constant__ W w, const float* __restrict__ Wg,
+                                                    const float* __restrict__ H, float* __restrict__ D, int M) {
+  extern __shared__ __align__(16) float smem[];
+  float* sA = smem;               // [32][PITCH]
+  float* sW = smem + 32 * PITCH;  // [32][64]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 32 * 64; i += 256) sW[i] = Wg[i];
+  for (int tile = blockIdx.x; tile * TM < M; tile += gridDim.x) {
+    __syncthreads();
+    {
+      const float* src = H + ((size_t)tile * TM + tid) * 32;
+#pragma unroll
+      for (int k = 0; k < 32; k += 4) {
+        float4 v = *reinterpret_cast<const float4*>(src + k);
+        sA[(k + 0) * PITCH + tid] = v.x; sA[(k + 1) * PITCH + tid] = v.y;
+        sA[(k + 2) * PITCH + tid] = v.z; sA[(k + 3) * PITCH + tid] = v.w;
+      }
+    }
+    __syncthreads();
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 1
+    for (int rep = 0; rep < REP; ++rep)
+#pragma unroll 4
+    for (int k = 0; k < 32; ++k) {
+      float a[8], b[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = sA[k * PITCH + lane + 32 * i];
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] = w.w[k][warp * 8 + j];
+      } else {
+        const float4 b0 = *reinterpret_cast<const float4*>(sW + k * 64 + warp * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(sW + k * 64 + warp * 8 + 4);
+        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    float out = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) out += fmaxf(acc[i][j], 0.f);
+    D[(size_t)tile * TM + tid] = out;
+  }
+}
+
 int main() {
   const int M = 1 << 20;  // about the row count of an 8-sweep batch
   std::vector<float> hH((size_t)M * 32), hW(32 * 64);
@@ -237,12 +362,14 @@ int main() {
   cudaFuncSetAttribute(k_smem<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(k_smem<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  const double flop = 2.0 * M * 32 * 64;
+  const double flop = 2.0 * M * 32 * 64 * REP;
   std::vector<float> r0(M), r1(M);
   const size_t smem2 = (2 * 32 * 64 + 32 * PITCH) * sizeof(float);
   cudaFuncSetAttribute(k_smem2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
   cudaFuncSetAttribute(k_smem2c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-  for (int variant = 0; variant < 6; ++variant) {
+  const size_t smemh = (32 * PITCH) * sizeof(float);
+  const size_t smemh1 = (32 * PITCH + 32 * 64) * sizeof(float);
+  for (int variant = 0; variant < 10; ++variant) {
     float best = 1e9f;
     for (int it = 0; it < 6; ++it) {
       cudaEventRecord(e0);
@@ -252,13 +379,17 @@ int main() {
       if (variant == 3) k_uniform2<<<2 * sms, 256>>>(w, dH, dD, M);
       if (variant == 4) k_smem2<<<2 * sms, 256, smem2>>>(dW, dH, dD, M);
       if (variant == 5) k_smem2c<<<2 * sms, 256, smem2>>>(dW, dH, dD, M);
+      if (variant == 6) k_hybrid<false><<<2 * sms, 256, smemh>>>(w, dH, dD, M);
+      if (variant == 7) k_hybrid<true><<<2 * sms, 256, smemh>>>(w, dH, dD, M);
+      if (variant == 8) k_hybrid1<0><<<2 * sms, 256, smemh1>>>(w, dW, dH, dD, M);
+      if (variant == 9) k_hybrid1<1><<<2 * sms, 256, smemh1>>>(w, dW, dH, dD, M);
       cudaEventRecord(e1); cudaEventSynchronize(e1);
       float ms; cudaEventElapsedTime(&ms, e0, e1); if (it > 0 && ms < best) best = ms;
     }
     cudaError_t err = cudaGetLastError();
     cudaMemcpy(variant == 0 ? r0.data() : r1.data(), dD, (size_t)M * 4, cudaMemcpyDeviceToHost);
     double maxdiff = 0; if (variant) for (int i = 0; i < M; ++i) { double d = fabs((double)r0[i] - r1[i]); if (d > maxdiff) maxdiff = d; }
-    const char* names[6] = {"U  thread-per-row, uniform-register weights", "S  smem 8x8 register tile", "S4 smem 8x4 register tile x2", "U2 thread-per-row, uniform weights, FFMA2", "S2 smem 8x8, FFMA2 row pairs, dup W", "S2c smem 8x8, FFMA2 col pairs"};
+    const char* names[10] = {"U  thread-per-row, uniform-register weights", "S  smem 8x8 register tile", "S4 smem 8x4 register tile x2", "U2 thread-per-row, uniform weights, FFMA2", "S2 smem 8x8, FFMA2 row pairs, dup W", "S2c smem 8x8, FFMA2 col pairs", "H  warp-uniform weights (UR), rows on lanes, LDS.32", "Hv warp-uniform weights (UR), rows on lanes, LDS.128", "Hc one body, weights by indexed constant load", "Hs one body, weights by smem broadcast LDS.128"};
     printf("%-46s %8.3f ms  %7.2f TFLOP/s  (H read %.0f GB/s)  maxdiff_vs_U %.3g  %s\n", names[variant], best,
            flop / best / 1e9, (double)M * 128 / best / 1e6, maxdiff, cudaGetErrorString(err));
   }
