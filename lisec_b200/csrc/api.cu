@@ -72,7 +72,8 @@ cudaError_t dev_alloc(lisec_handle* h, T** p, size_t n) {
 
 void free_workspace(Workspace& w) {
   void* ptrs[] = {w.count, w.cell_voxel, w.cell_of_point, w.list_unsorted, w.list_sorted, w.entry_voxel,
-                  w.voxel_cell, w.voxel_start, w.row_start, w.tile_first, w.block_sums, w.sweep_voxel_start,
+                  w.voxel_cell, w.voxel_start, w.row_start, w.tile_first, w.row_point, w.row_voxel, w.centroid,
+                  w.block_sums, w.sweep_voxel_start,
                   w.totals, w.voxel_feat, w.c_empty, w.vfe_w, w.staging, w.empty_desc};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -117,9 +118,11 @@ int do_voxelize(lisec_handle* h, const void* points, int dtype, const SweepOffse
 }
 
 int do_vfe(lisec_handle* h, float* voxel_feat, cudaStream_t st) {
-  LISEC_CUDA(h, launch_vfe(h->last_points, h->last_dtype, h->geom, h->params, h->ws.vfe_w, h->ws.tile_first,
-                           h->ws.voxel_start, h->ws.row_start, h->ws.list_sorted, h->ws.totals + TOT_TILES,
-                           voxel_feat, h->sm_count, st, &h->launches));
+  LISEC_CUDA(h, launch_centroids(h->last_points, h->last_dtype, h->geom, h->ws, h->max_voxels, st, &h->launches));
+  const VfeProblem prob{h->ws.tile_first, h->ws.row_start, h->ws.row_point, h->ws.row_voxel, h->ws.centroid,
+                        h->ws.totals + TOT_TILES};
+  LISEC_CUDA(h, launch_vfe(h->last_points, h->last_dtype, h->params, h->ws.vfe_w, prob, voxel_feat, h->sm_count, st,
+                           &h->launches));
   return LISEC_OK;
 }
 
@@ -210,6 +213,9 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
   LISEC_CUDA(h, dev_alloc(h, &w.voxel_start, V + 1));
   LISEC_CUDA(h, dev_alloc(h, &w.row_start, V + 1));
   LISEC_CUDA(h, dev_alloc(h, &w.tile_first, (size_t)h->max_tiles + 2));
+  LISEC_CUDA(h, dev_alloc(h, &w.row_point, P + V));
+  LISEC_CUDA(h, dev_alloc(h, &w.row_voxel, P + V));
+  LISEC_CUDA(h, dev_alloc(h, &w.centroid, 3 * V));
   LISEC_CUDA(h, dev_alloc(h, &w.block_sums, (size_t)3 * h->scan_blocks_cap + 4));
   LISEC_CUDA(h, dev_alloc(h, &w.sweep_voxel_start, (size_t)c.max_sweeps + 2));
   LISEC_CUDA(h, dev_alloc(h, &w.totals, (size_t)TOT_COUNT));
@@ -217,11 +223,12 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
   LISEC_CUDA(h, dev_alloc(h, &w.c_empty, (size_t)c.c3));
   LISEC_CUDA(h, dev_alloc(h, &w.vfe_w, (size_t)kVfeBlobFloats));
   LISEC_CUDA(h, dev_alloc(h, reinterpret_cast<unsigned char**>(&w.staging), P * 3 * sizeof(double)));
-  LISEC_CUDA(h, dev_alloc(h, &w.empty_desc, (size_t)8));
+  LISEC_CUDA(h, dev_alloc(h, &w.empty_desc, (size_t)16));
   // the one-voxel problem whose VFE output is c_empty: 0 kept points, 1 pad row, 1 tile
-  int desc[8] = {0, 1, 0, 0, 0, 1, 0, 0};
+  // layout: tile_first {0,1} | row_start {0,1} | n_tiles (int64) 1 | row_point {-1} | row_voxel {0}
+  int desc[16] = {0, 1, 0, 1, 0, 0, -1, 0};
   const long long one = 1;
-  std::memcpy(&desc[6], &one, sizeof(one));
+  std::memcpy(&desc[4], &one, sizeof(one));
   LISEC_CUDA(h, cudaMemcpy(w.empty_desc, desc, sizeof(desc), cudaMemcpyHostToDevice));
   LISEC_CUDA(h, cudaMemset(w.totals, 0, sizeof(long long) * TOT_COUNT));
   return LISEC_OK;
@@ -272,9 +279,8 @@ int32_t lisec_set_vfe_weights(lisec_handle* h, const lisec_vfe_weights* w, void*
   // c_empty: the same kernel, run on one voxel that holds nothing but the pad row
   LISEC_CUDA(h, cudaMemcpyAsync(h->ws.vfe_w, blob, sizeof(float) * kVfeBlobFloats, cudaMemcpyHostToDevice, st));
   const int* d = h->ws.empty_desc;
-  LISEC_CUDA(h, launch_vfe(nullptr, LISEC_F32, h->geom, p, h->ws.vfe_w, d, d + 2, d + 4, nullptr,
-                           reinterpret_cast<const long long*>(d + 6), h->ws.c_empty, h->sm_count, st,
-                           &h->launches));
+  const VfeProblem empty{d, d + 2, d + 6, d + 7, nullptr, reinterpret_cast<const long long*>(d + 4)};
+  LISEC_CUDA(h, launch_vfe(nullptr, LISEC_F32, p, h->ws.vfe_w, empty, h->ws.c_empty, h->sm_count, st, &h->launches));
   LISEC_CUDA(h, cudaStreamSynchronize(st));
   return LISEC_OK;
 }
@@ -376,10 +382,12 @@ static int frontend(lisec_handle* h, const void* dev_points, int dtype, const Sw
                     cudaStream_t st) {
   int rc = do_voxelize(h, dev_points, dtype, so, st);
   if (rc) return rc;
-  rc = do_vfe(h, h->ws.voxel_feat, st);
-  if (rc) return rc;
-  LISEC_CUDA(h, launch_grid_write(h->geom, so.n, h->cfg.c3, h->cfg.grid_dtype, h->ws.cell_voxel,
-                                  h->ws.voxel_feat, h->ws.c_empty, grid, h->sm_count, st, &h->launches));
+  LISEC_CUDA(h, launch_centroids(dev_points, dtype, h->geom, h->ws, h->max_voxels, st, &h->launches));
+  const VfeProblem prob{h->ws.tile_first, h->ws.row_start, h->ws.row_point, h->ws.row_voxel, h->ws.centroid,
+                        h->ws.totals + TOT_TILES};
+  // one kernel: VFE on the FP32 pipe, voxel rows and the c_empty background written to the grid concurrently
+  LISEC_CUDA(h, launch_vfe_to_grid(dev_points, dtype, h->params, h->ws.vfe_w, prob, h->ws, h->geom, so.n,
+                                   h->cfg.grid_dtype, grid, h->sm_count, st, &h->launches));
   return LISEC_OK;
 }
 

@@ -69,6 +69,10 @@ struct Workspace {
   int* voxel_start = nullptr;  // CSR offsets into list_*
   int* row_start = nullptr;    // offsets in VFE rows (kept + pad)
   int* tile_first = nullptr;   // first voxel of each VFE tile, [max_tiles + 2]
+  // per VFE row, [max_points + max_voxels]: what the VFE kernel needs to start a tile with one coalesced read
+  int* row_point = nullptr;    // global point index of the row, or -1 for the voxel's virtual pad row
+  int* row_voxel = nullptr;    // voxel row the VFE row belongs to
+  double* centroid = nullptr;  // [max_voxels][3] float64 mean of the kept points (np.mean order)
   int* block_sums = nullptr;   // [3][scan_blocks] reduce -> exclusive prefix
   int* sweep_voxel_start = nullptr;  // [max_sweeps + 1]
   long long* totals = nullptr;       // [TOT_COUNT]
@@ -89,9 +93,23 @@ cudaError_t launch_fill_and_order(long long n_total, const Geom& g, int rows_per
 cudaError_t launch_export(const void* pts, int pts_dtype, const SweepOffsets& so, const Geom& g,
                           const Workspace& w, long long max_voxels, int32_t* coords, int32_t* counts,
                           int32_t* point_idx, float* features, float* dense, cudaStream_t st, int* launches);
-cudaError_t launch_vfe(const void* pts, int pts_dtype, const Geom& g, const VfeSmall& p, const float* wblob,
-                       const int* tile_first, const int* voxel_start, const int* row_start, const int* list_sorted,
-                       const long long* n_tiles, float* voxel_feat, int sm_count, cudaStream_t st, int* launches);
+// The VFE problem description (device pointers): tiles -> rows -> (point, voxel); see Workspace.
+struct VfeProblem {
+  const int* tile_first;
+  const int* row_start;
+  const int* row_point;
+  const int* row_voxel;
+  const double* centroid;
+  const long long* n_tiles;
+};
+cudaError_t launch_centroids(const void* pts, int pts_dtype, const Geom& g, const Workspace& w, long long max_voxels,
+                             cudaStream_t st, int* launches);
+cudaError_t launch_vfe(const void* pts, int pts_dtype, const VfeSmall& p, const float* wblob, const VfeProblem& prob,
+                       float* voxel_feat, int sm_count, cudaStream_t st, int* launches);
+// Fused VFE + dense grid: voxel rows go straight to their cells, a 9th warp per CTA streams c_empty into empty cells.
+cudaError_t launch_vfe_to_grid(const void* pts, int pts_dtype, const VfeSmall& p, const float* wblob,
+                               const VfeProblem& prob, const Workspace& w, const Geom& g, int n_sweeps, int grid_dtype,
+                               void* grid, int sm_count, cudaStream_t st, int* launches);
 cudaError_t launch_grid_write(const Geom& g, int n_sweeps, int c3, int grid_dtype, const int* cell_voxel,
                               const float* voxel_feat, const float* c_empty, void* grid, int sm_count,
                               cudaStream_t st, int* launches);

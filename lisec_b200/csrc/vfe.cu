@@ -22,6 +22,8 @@
 // accumulated in float64 (96 DFMA per row); dense_1's two halves cancel, so its 32-term sum is accumulated in
 // float32 blocks of 4 (a fresh accumulator per block, then added) — measured worst case 4.7e-6 over seeds and clouds,
 // the level of a CPU float32 forward; dense_2 is a plain float32 FMA chain.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "vfe_math.cuh"
 
@@ -30,6 +32,11 @@ namespace lisec {
 int vfe_rows_per_tile(int T) { return kVfeThreads - T + 1; }
 
 namespace {
+
+__device__ __forceinline__ unsigned pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<unsigned*>(&h);
+}
 
 constexpr int kRows = kVfeThreads;   // 256 rows per tile
 constexpr int kVox = kVfeThreads / 2;  // 128 voxels per tile: a non-full voxel has >= 2 rows, a full one T >= 2
@@ -46,16 +53,11 @@ constexpr int OFF_H1T = OFF_W3X + 32 * 64 * 4;     // [16][PR]   dense outputs o
 constexpr int OFF_P1T = OFF_H1T + 16 * PR * 4;     // [16][PV]   pooled VFE-1
 constexpr int OFF_P2T = OFF_H1T;                   // [32][PV]   pooled VFE-2, reuses H1T+P1T (dead by then)
 constexpr int OFF_H2T = OFF_P1T + 16 * PV * 4;     // [32][PR]   VFE-2 outputs; later one 32-channel half of FCN outputs
-constexpr int OFF_Q = OFF_H2T + 32 * PR * 4;       // [kVox][QS] pooled-half products; later the pooled FCN rows
-constexpr int OFF_CEN = OFF_Q;                     // double[kVox][3], dead before Q is first written
-constexpr int OFF_PT = OFF_CEN + kVox * 3 * 8;     // PT[kRows][3]
-constexpr int OFF_ROWOFF = OFF_Q + kVox * QS * 4;  // int[kVox + 4]
-constexpr int OFF_ROWVOX = OFF_ROWOFF + (kVox + 4) * 4;  // uint8[kRows]
-constexpr int kSmemBytes = OFF_ROWVOX + kRows;
-constexpr int OFF_KEPT = OFF_H2T;                  // int[kVox], setup only
-constexpr int OFF_ESTART = OFF_KEPT + kVox * 4;    // int[kVox], setup only
+constexpr int OFF_Q = OFF_H2T + 32 * PR * 4;       // [kVox][QS] pooled-half products of the current layer
+constexpr int OFF_ROWVOX = OFF_Q + kVox * QS * 4;  // uint8[kRows] local voxel of each tile row
+constexpr int OFF_VOXCELL = OFF_ROWVOX + kRows;      // int[kVox] cell of each tile voxel (grid output modes)
+constexpr int kSmemBytes = OFF_VOXCELL + kVox * 4;
 static_assert(32 * PV * 4 <= 16 * PR * 4 + 16 * PV * 4, "P2T must fit in H1T+P1T");
-static_assert(OFF_PT + kRows * 3 * 8 <= OFF_ROWOFF, "centroid/point staging must fit in the Q region");
 static_assert(2 * (kSmemBytes + 1024) <= 233472, "two CTAs per SM");
 
 // ---- register-tile GEMM: acc[R][C] += A[k][row(r)] * W[k][col(c)], k = 0..K-1 -------------------------------
@@ -120,6 +122,9 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ sA, int pitc
     }
   }
 }
+
+// barrier among the 8 compute warps only (the 9th warp of the fused kernel streams the grid background and never joins)
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kVfeThreads) : "memory"); }
 
 // position of tile row r inside a k-major row tile: lane l = r/8 owns rows 8l..8l+7 and loads them as two float4 at
 // 4l and 128+4l, so both 16-byte loads of a warp cover 512 contiguous bytes (no bank conflicts)
@@ -212,13 +217,93 @@ __device__ __forceinline__ void pool_lane_rows(const float (&val)[8][NC], const 
   if (m.emit_tail) emit(m.kt, run);
 }
 
+// float64 mean of each voxel's kept points, added in list order with one divide — np.mean(currPoints, axis=0)
+// (model_training.py:135) bit for bit. One thread per voxel; a pre-pass so that VFE tiles start without a barrier.
 template <typename PT>
-__global__ void __launch_bounds__(kVfeThreads, 2)
-    vfe_kernel(const PT* __restrict__ pts, const __grid_constant__ VfeSmall P, const float* __restrict__ wblob, int T,
-               const int* __restrict__ tile_first, const int* __restrict__ voxel_start,
-               const int* __restrict__ row_start, const int* __restrict__ list_sorted,
-               const long long* __restrict__ n_tiles_ptr, float* __restrict__ voxel_feat) {
+__global__ void __launch_bounds__(256) centroid_kernel(const PT* __restrict__ pts, int T,
+                                                       const int* __restrict__ voxel_start,
+                                                       const int* __restrict__ list_sorted,
+                                                       const long long* __restrict__ totals,
+                                                       double* __restrict__ centroid) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= totals[TOT_VOXELS]) return;
+  const int s = voxel_start[v];
+  const int c = voxel_start[v + 1] - s;
+  const int kept = c < T ? c : T;
+  double sx = 0.0, sy = 0.0, sz = 0.0;
+  for (int i = 0; i < kept; ++i) {
+    PT x, y, z;
+    load_point(pts, (long long)list_sorted[s + i], x, y, z);
+    sx += (double)x;
+    sy += (double)y;
+    sz += (double)z;
+  }
+  const double n = (double)(kept > 0 ? kept : 1);
+  centroid[3 * v] = sx / n;
+  centroid[3 * v + 1] = sy / n;
+  centroid[3 * v + 2] = sz / n;
+}
+
+// ---- background writer (fused kernel, warp 8 of every CTA) --------------------------------------------------
+// Streams c_empty into every EMPTY cell of the grid while the compute warps are busy on the FP32 pipe; occupied cells
+// are written by the compute warps (their voxel rows), so every grid element is still written exactly once.
+// 32 cells per step: one coalesced 128-byte read of the occupancy map, then 16-byte streaming stores.
+template <typename GT>
+__device__ __forceinline__ void background_writer(const int* __restrict__ cell_voxel, const float* __restrict__ c_empty,
+                                                  GT* __restrict__ grid, long long ncells, int lane) {
+  constexpr int LPC = sizeof(GT) == 4 ? 16 : 8;  // lanes per cell: 64 channels x sizeof(GT) / 16 bytes
+  constexpr int CPS = 32 / LPC;                  // cells per store instruction
+  const int sub = lane / LPC, chunk = lane % LPC;
+  uint4 bg;
+  if (sizeof(GT) == 4) {
+    bg = reinterpret_cast<const uint4*>(c_empty)[chunk];
+  } else {
+    const float4 b0 = reinterpret_cast<const float4*>(c_empty)[2 * chunk];
+    const float4 b1 = reinterpret_cast<const float4*>(c_empty)[2 * chunk + 1];
+    bg = make_uint4(pack_bf16x2(b0.x, b0.y), pack_bf16x2(b0.z, b0.w), pack_bf16x2(b1.x, b1.y), pack_bf16x2(b1.z, b1.w));
+  }
+  const long long ngroups = (ncells + 31) >> 5;
+  constexpr int U = 4;  // occupancy-map loads kept in flight
+  for (long long g0 = blockIdx.x; g0 < ngroups; g0 += (long long)gridDim.x * U) {
+    int occ[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long cell = ((g0 + (long long)u * gridDim.x) << 5) + lane;
+      occ[u] = (g0 + (long long)u * gridDim.x < ngroups && cell < ncells) ? __ldg(cell_voxel + cell) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long base = (g0 + (long long)u * gridDim.x) << 5;
+#pragma unroll
+      for (int i = 0; i < 32 / CPS; ++i) {
+        const int vox = __shfl_sync(0xffffffffu, occ[u], CPS * i + sub);
+        if (vox < 0) __stcs(reinterpret_cast<uint4*>(grid + (base + CPS * i + sub) * 64) + chunk, bg);
+      }
+    }
+  }
+}
+
+// MODE 0: voxel rows to voxel_feat[V][64] (float32), no background.  MODE 1 / 2: rows straight into the float32 /
+// bf16 dense grid at their cell, background by the 9th warp.
+struct VfeOutput {
+  float* voxel_feat;
+  void* grid;
+  const int* voxel_cell;  // voxel row -> cell (sweep * cells + (z*nx + x)*ny + y)
+  const int* cell_voxel;  // occupancy map
+  const float* c_empty;
+  long long ncells;
+};
+
+template <typename PT, int MODE>
+__global__ void __launch_bounds__(kVfeThreads + 32, 2)
+    vfe_kernel(const PT* __restrict__ pts, const __grid_constant__ VfeSmall P, const float* __restrict__ wblob,
+               const __grid_constant__ VfeProblem prob, const __grid_constant__ VfeOutput out) {
   extern __shared__ __align__(16) unsigned char smem[];
+  if (threadIdx.x >= kVfeThreads) {  // warp 8
+    if (MODE == 1) background_writer(out.cell_voxel, out.c_empty, static_cast<float*>(out.grid), out.ncells, threadIdx.x & 31);
+    if (MODE == 2) background_writer(out.cell_voxel, out.c_empty, static_cast<__nv_bfloat16*>(out.grid), out.ncells, threadIdx.x & 31);
+    return;
+  }
   float* sW2P = reinterpret_cast<float*>(smem + OFF_W2P);
   float* sW2X = reinterpret_cast<float*>(smem + OFF_W2X);
   float* sW3P = reinterpret_cast<float*>(smem + OFF_W3P);
@@ -228,16 +313,12 @@ __global__ void __launch_bounds__(kVfeThreads, 2)
   float* sP2T = reinterpret_cast<float*>(smem + OFF_P2T);
   float* sH2T = reinterpret_cast<float*>(smem + OFF_H2T);
   float* sQ = reinterpret_cast<float*>(smem + OFF_Q);
-  double* sCen = reinterpret_cast<double*>(smem + OFF_CEN);
-  PT* sPt = reinterpret_cast<PT*>(smem + OFF_PT);
-  int* sRowOff = reinterpret_cast<int*>(smem + OFF_ROWOFF);
   unsigned char* sRowVox = smem + OFF_ROWVOX;
-  int* sKept = reinterpret_cast<int*>(smem + OFF_KEPT);
-  int* sEstart = reinterpret_cast<int*>(smem + OFF_ESTART);
+  int* sVoxCell = reinterpret_cast<int*>(smem + OFF_VOXCELL);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // register tiles: lane = row group (8 tile rows / 4 voxel rows), warp = column group
-  const int n_tiles = (int)*n_tiles_ptr;
+  const int n_tiles = (int)*prob.n_tiles;
   if ((int)blockIdx.x >= n_tiles) return;
 
   // weights: [W2P | W2X | W3P | W3X] as laid out by the host, straight into the first 20 KB
@@ -245,59 +326,26 @@ __global__ void __launch_bounds__(kVfeThreads, 2)
     reinterpret_cast<float4*>(smem)[i] = __ldg(reinterpret_cast<const float4*>(wblob) + i);
 
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const int v0 = tile_first[t];
-    const int nv = tile_first[t + 1] - v0;
-    const int r0 = row_start[v0];
-    if (tid <= nv) sRowOff[tid] = row_start[v0 + tid] - r0;
-    if (tid < nv) {
-      const int s = voxel_start[v0 + tid];
-      const int c = voxel_start[v0 + tid + 1] - s;
-      sKept[tid] = c < T ? c : T;
-      sEstart[tid] = s;
-    }
-    __syncthreads();
-    const int nrows = sRowOff[nv];
+    const int v0 = prob.tile_first[t], v1 = prob.tile_first[t + 1];
+    const int nv = v1 - v0;
+    const int r0 = prob.row_start[v0];
+    const int nrows = prob.row_start[v1] - r0;
     const bool has_row = tid < nrows;
-    int lv = 255;  // padding row
-    bool real = false;
-    PT px = PT(0), py = PT(0), pz = PT(0);
-    if (has_row) {
-      int lo = 0, hi = nv;  // largest lv with sRowOff[lv] <= tid
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (sRowOff[mid] <= tid) lo = mid; else hi = mid;
-      }
-      lv = lo;
-      const int i = tid - sRowOff[lv];
-      real = i < sKept[lv];
-      if (real) load_point(pts, (long long)list_sorted[sEstart[lv] + i], px, py, pz);
-      sPt[tid * 3] = px;
-      sPt[tid * 3 + 1] = py;
-      sPt[tid * 3 + 2] = pz;
-    }
-    sRowVox[tid] = (unsigned char)lv;
-    __syncthreads();
-    // centroid = np.mean(currPoints, axis=0) (model_training.py:135): float64, rows added in list order, one divide
-    if (tid < nv) {
-      const int kept = sKept[tid];
-      double sx = 0.0, sy = 0.0, sz = 0.0;
-      const PT* q = sPt + sRowOff[tid] * 3;
-      for (int i = 0; i < kept; ++i) {
-        sx += (double)q[3 * i];
-        sy += (double)q[3 * i + 1];
-        sz += (double)q[3 * i + 2];
-      }
-      const double n = (double)(kept > 0 ? kept : 1);
-      sCen[tid * 3] = sx / n;
-      sCen[tid * 3 + 1] = sy / n;
-      sCen[tid * 3 + 2] = sz / n;
-    }
-    __syncthreads();
 
     // ---- VFE-1: Dense(6->16, no bias) + BN + ReLU (addVFELayer(in, 6, 32), :231 -> :155-166); one row per thread ----
     {
+      int p = -1, lv = 255;  // 255 = padding row past the tile's last row
+      if (has_row) {
+        p = prob.row_point[r0 + tid];
+        lv = prob.row_voxel[r0 + tid] - v0;
+      }
       float f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // pad row: six zeros (:141)
-      if (real) point_features((double)px, (double)py, (double)pz, sCen[lv * 3], sCen[lv * 3 + 1], sCen[lv * 3 + 2], f);
+      if (p >= 0) {
+        PT px, py, pz;
+        load_point(pts, (long long)p, px, py, pz);
+        const double* c = prob.centroid + 3 * (size_t)(v0 + lv);
+        point_features((double)px, (double)py, (double)pz, c[0], c[1], c[2], f);
+      }
       double d[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) d[j] = 0.0;
@@ -311,8 +359,10 @@ __global__ void __launch_bounds__(kVfeThreads, 2)
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         sH1T[j * PR + pos] = has_row ? fmaxf(fmaf(__double2float_rn(d[j]), P.a1[j], P.b1[j]), 0.f) : 0.f;
+      sRowVox[tid] = (unsigned char)lv;
+      if (MODE != 0 && tid < nv) sVoxCell[tid] = out.voxel_cell[v0 + tid];
     }
-    __syncthreads();
+    compute_sync();
     const PoolMeta meta = make_pool_meta(sRowVox, lane);
     {  // MaxPoolingVFELayer over T (:160); RepeatLayer is implicit. Warp w pools channels 2w, 2w+1.
       float val[8][2];
@@ -331,7 +381,7 @@ __global__ void __launch_bounds__(kVfeThreads, 2)
         }
       });
     }
-    __syncthreads();
+    compute_sync();
 
     // ---- VFE-2: Dense(32->32) + BN + ReLU on concat[pooled, pointwise] (addVFELayer(., 32, 64), :232) ----
     const int coff4[1] = {warp * 4};
@@ -347,7 +397,7 @@ __global__ void __launch_bounds__(kVfeThreads, 2)
         *reinterpret_cast<float4*>(sQ + (lane * 4 + r) * QS + warp * 4) =
             make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
     }
-    __syncthreads();
+    compute_sync();
     {  // rows: 8x4 tile per thread, accumulators start at the voxel's pooled-half product
       float acc[8][4];
 #pragma unroll
@@ -365,7 +415,7 @@ __global__ void __launch_bounds__(kVfeThreads, 2)
         *reinterpret_cast<float4*>(dst) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
         *reinterpret_cast<float4*>(dst + 128) = make_float4(acc[4][c], acc[5][c], acc[6][c], acc[7][c]);
       }
-      __syncthreads();  // every warp is done with sH1T (A operand) and sQ: sP2T may now overwrite sH1T/sP1T
+      compute_sync();  // every warp is done with sH1T (A operand) and sQ: sP2T may now overwrite sH1T/sP1T
       pool_lane_rows<4>(acc, meta, [&](int v, const float(&x)[4]) {
         if (v < nv) {
 #pragma unroll
@@ -373,7 +423,7 @@ __global__ void __launch_bounds__(kVfeThreads, 2)
         }
       });
     }
-    __syncthreads();
+    compute_sync();
 
     // ---- FCN: Dense(64->64) + BN + ReLU (addFCN(., 64, 64), :233), then MaxPoolingVFELayer(combine=True) (:235) ----
     const int coff8[2] = {warp * 4, 32 + warp * 4};  // this warp's 8 output channels
@@ -391,60 +441,94 @@ __global__ void __launch_bounds__(kVfeThreads, 2)
         *reinterpret_cast<float4*>(dst + coff8[1]) = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
       }
     }
-    __syncthreads();
+    compute_sync();
     {  // rows: 8x8 tile per thread; the per-voxel max goes straight from registers to the output row
-      float out[8][8];
+      float out8[8][8];
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         const float* q = sQ + (meta.v[r] & (kVox - 1)) * QS;
         const float4 q0 = *reinterpret_cast<const float4*>(q + coff8[0]);
         const float4 q1 = *reinterpret_cast<const float4*>(q + coff8[1]);
-        out[r][0] = q0.x; out[r][1] = q0.y; out[r][2] = q0.z; out[r][3] = q0.w;
-        out[r][4] = q1.x; out[r][5] = q1.y; out[r][6] = q1.z; out[r][7] = q1.w;
+        out8[r][0] = q0.x; out8[r][1] = q0.y; out8[r][2] = q0.z; out8[r][3] = q0.w;
+        out8[r][4] = q1.x; out8[r][5] = q1.y; out8[r][6] = q1.z; out8[r][7] = q1.w;
       }
-      tile_gemm<8, 2, 32, false>(sH2T, PR, 128, lane * 4, sW3X, 64, coff8, out);
+      tile_gemm<8, 2, 32, false>(sH2T, PR, 128, lane * 4, sW3X, 64, coff8, out8);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const int col = coff8[c >> 2] + (c & 3);
         const float a = P.a3[col], b = P.b3[col];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) out[r][c] = fmaxf(fmaf(out[r][c], a, b), 0.f);
+        for (int r = 0; r < 8; ++r) out8[r][c] = fmaxf(fmaf(out8[r][c], a, b), 0.f);
       }
-      float* dst_base = voxel_feat + (size_t)v0 * 64;
-      pool_lane_rows<8>(out, meta, [&](int v, const float(&x)[8]) {
-        if (v < nv) {  // two 16-byte stores per voxel and warp; the 8 warps complete the 256-byte row
-          float* dst = dst_base + (size_t)v * 64;
-          *reinterpret_cast<float4*>(dst + coff8[0]) = make_float4(x[0], x[1], x[2], x[3]);
-          *reinterpret_cast<float4*>(dst + coff8[1]) = make_float4(x[4], x[5], x[6], x[7]);
+      pool_lane_rows<8>(out8, meta, [&](int v, const float(&x)[8]) {
+        if (v < nv) {  // two 16-byte (bf16: 8-byte) stores per voxel and warp; the 8 warps complete the row
+          if (MODE == 0) {
+            float* dst = out.voxel_feat + (size_t)(v0 + v) * 64;
+            *reinterpret_cast<float4*>(dst + coff8[0]) = make_float4(x[0], x[1], x[2], x[3]);
+            *reinterpret_cast<float4*>(dst + coff8[1]) = make_float4(x[4], x[5], x[6], x[7]);
+          } else if (MODE == 1) {
+            float* dst = static_cast<float*>(out.grid) + (size_t)sVoxCell[v] * 64;
+            __stcs(reinterpret_cast<float4*>(dst + coff8[0]), make_float4(x[0], x[1], x[2], x[3]));
+            __stcs(reinterpret_cast<float4*>(dst + coff8[1]), make_float4(x[4], x[5], x[6], x[7]));
+          } else {
+            __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(out.grid) + (size_t)sVoxCell[v] * 64;
+            *reinterpret_cast<uint2*>(dst + coff8[0]) = make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
+            *reinterpret_cast<uint2*>(dst + coff8[1]) = make_uint2(pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+          }
         }
       });
     }
-    __syncthreads();  // the next tile's setup reuses sRowOff / sH2T / sQ
+    compute_sync();  // the next tile's setup overwrites sH1T and sRowVox
   }
 }
 
 }  // namespace
 
-cudaError_t launch_vfe(const void* pts, int pts_dtype, const Geom& g, const VfeSmall& p, const float* wblob,
-                       const int* tile_first, const int* voxel_start, const int* row_start, const int* list_sorted,
-                       const long long* n_tiles, float* voxel_feat, int sm_count, cudaStream_t st, int* launches) {
-  cudaError_t err;
-  const int grid = 2 * sm_count;  // persistent: two resident CTAs per SM, tiles strided over them
-  if (pts_dtype == LISEC_F32) {
-    err = cudaFuncSetAttribute(vfe_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (err != cudaSuccess) return err;
-    vfe_kernel<float><<<grid, kVfeThreads, kSmemBytes, st>>>(static_cast<const float*>(pts), p, wblob, g.T,
-                                                            tile_first, voxel_start, row_start, list_sorted,
-                                                            n_tiles, voxel_feat);
-  } else {
-    err = cudaFuncSetAttribute(vfe_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (err != cudaSuccess) return err;
-    vfe_kernel<double><<<grid, kVfeThreads, kSmemBytes, st>>>(static_cast<const double*>(pts), p, wblob, g.T,
-                                                             tile_first, voxel_start, row_start, list_sorted,
-                                                             n_tiles, voxel_feat);
-  }
+cudaError_t launch_centroids(const void* pts, int pts_dtype, const Geom& g, const Workspace& w, long long max_voxels,
+                             cudaStream_t st, int* launches) {
+  const unsigned blocks = (unsigned)((max_voxels + 255) / 256);  // threads past the device-side voxel count exit
+  if (pts_dtype == LISEC_F32)
+    centroid_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(pts), g.T, w.voxel_start, w.list_sorted,
+                                                   w.totals, w.centroid);
+  else
+    centroid_kernel<double><<<blocks, 256, 0, st>>>(static_cast<const double*>(pts), g.T, w.voxel_start,
+                                                    w.list_sorted, w.totals, w.centroid);
   ++*launches;
   return cudaGetLastError();
+}
+
+template <typename PT, int MODE>
+static cudaError_t launch_vfe_mode(const PT* pts, const VfeSmall& p, const float* wblob, const VfeProblem& prob,
+                                   const VfeOutput& out, int sm_count, cudaStream_t st) {
+  cudaError_t err = cudaFuncSetAttribute(vfe_kernel<PT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (err != cudaSuccess) return err;
+  // persistent: two resident CTAs per SM (8 compute warps + 1 background-writer warp each), tiles strided over them
+  vfe_kernel<PT, MODE><<<2 * sm_count, kVfeThreads + 32, kSmemBytes, st>>>(pts, p, wblob, prob, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_vfe(const void* pts, int pts_dtype, const VfeSmall& p, const float* wblob, const VfeProblem& prob,
+                       float* voxel_feat, int sm_count, cudaStream_t st, int* launches) {
+  const VfeOutput out{voxel_feat, nullptr, nullptr, nullptr, nullptr, 0};
+  ++*launches;
+  if (pts_dtype == LISEC_F32)
+    return launch_vfe_mode<float, 0>(static_cast<const float*>(pts), p, wblob, prob, out, sm_count, st);
+  return launch_vfe_mode<double, 0>(static_cast<const double*>(pts), p, wblob, prob, out, sm_count, st);
+}
+
+cudaError_t launch_vfe_to_grid(const void* pts, int pts_dtype, const VfeSmall& p, const float* wblob,
+                               const VfeProblem& prob, const Workspace& w, const Geom& g, int n_sweeps, int grid_dtype,
+                               void* grid, int sm_count, cudaStream_t st, int* launches) {
+  const VfeOutput out{nullptr, grid, w.voxel_cell, w.cell_voxel, w.c_empty, (long long)n_sweeps * g.cells};
+  ++*launches;
+  if (pts_dtype == LISEC_F32) {
+    const float* q = static_cast<const float*>(pts);
+    return grid_dtype == LISEC_F32 ? launch_vfe_mode<float, 1>(q, p, wblob, prob, out, sm_count, st)
+                                   : launch_vfe_mode<float, 2>(q, p, wblob, prob, out, sm_count, st);
+  }
+  const double* q = static_cast<const double*>(pts);
+  return grid_dtype == LISEC_F32 ? launch_vfe_mode<double, 1>(q, p, wblob, prob, out, sm_count, st)
+                                 : launch_vfe_mode<double, 2>(q, p, wblob, prob, out, sm_count, st);
 }
 
 }  // namespace lisec

@@ -13,7 +13,8 @@
 //                needs no memset) and writes the CSR payload in arrival order.
 //   order_pass   rank-by-counting inside each voxel segment, early exit at T: entry p lands at position
 //                #{q in voxel : q < p}. This is what makes the slot assignment deterministic in point order
-//                whatever order the atomics resolved in. Also marks the VFE tile boundaries.
+//                whatever order the atomics resolved in. Also marks the VFE tile boundaries and writes the per-row
+//                tables (row -> point, row -> voxel) the VFE kernel starts its tiles from.
 #include "common.cuh"
 
 namespace lisec {
@@ -345,7 +346,8 @@ __global__ void __launch_bounds__(256) order_pass_kernel(const int* __restrict__
                                                          const int* __restrict__ row_start, int T,
                                                          int rows_per_tile, long long* __restrict__ totals,
                                                          int* __restrict__ list_sorted,
-                                                         int* __restrict__ tile_first) {
+                                                         int* __restrict__ tile_first, int* __restrict__ row_point,
+                                                         int* __restrict__ row_voxel) {
   const long long n_entries = totals[TOT_ENTRIES];
   const long long n_voxels = totals[TOT_VOXELS];
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -372,7 +374,17 @@ __global__ void __launch_bounds__(256) order_pass_kernel(const int* __restrict__
       if (rank >= T) break;  // not among the first T in point order: dropped (the cap at :131)
     }
   }
-  if (rank < T) list_sorted[s + rank] = p;
+  if (rank < T) {
+    list_sorted[s + rank] = p;
+    // VFE row tables: row_start[v] + rank is this point's row; a non-full voxel gets one virtual pad row after its points
+    const int row = row_start[v] + rank;
+    row_point[row] = p;
+    row_voxel[row] = v;
+    if (rank == 0 && n < T) {
+      row_point[row + n] = -1;
+      row_voxel[row + n] = v;
+    }
+  }
 }
 
 }  // namespace
@@ -421,7 +433,7 @@ cudaError_t launch_fill_and_order(long long n_total, const Geom& g, int rows_per
   // entries <= points; threads beyond the device-side totals exit
   order_pass_kernel<<<(unsigned)((n_total + 255) / 256), 256, 0, st>>>(
       w.list_unsorted, w.entry_voxel, w.voxel_start, w.row_start, g.T, rows_per_tile, w.totals, w.list_sorted,
-      w.tile_first);
+      w.tile_first, w.row_point, w.row_voxel);
   *launches += 2;
   return cudaGetLastError();
 }

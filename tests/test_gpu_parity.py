@@ -214,7 +214,7 @@ def test_fused_forward_equals_modular_and_host_entry(fe):
     host = fe.forward_host(pinned, off)
     torch.cuda.synchronize()
     assert torch.equal(host, modular)
-    assert fe.last_launch_count == 8
+    assert fe.last_launch_count == 8  # point, 3 scans, fill, order, centroids, fused VFE + grid
 
 
 def test_grid_against_dense_reference_forward_small_grid():
