@@ -166,10 +166,17 @@ int32_t lisec_scatter_dense(lisec_handle* h, const float* voxel_feat, void* grid
 int32_t lisec_frontend_forward(lisec_handle* h, const void* points, int32_t points_dtype,
                                const int64_t* sweep_offsets, int32_t n_sweeps, void* grid, void* stream);
 
-/* Same, from HOST points (pinned or pageable): copies them to the handle's staging buffer on `stream` first.
- * This is the call the Python drop-in makes when it is handed a numpy array. [async w.r.t. the kernels] */
+/* Same, from HOST points (pinned for a truly asynchronous copy). The copy runs on the handle's own copy stream into one
+ * of two staging buffers, so the H2D copy of call i+1 overlaps the kernels of call i; the kernels run on `stream`.
+ * The host buffer must stay valid until the copy has completed (e.g. until `stream` has been synchronised).
+ * This is the call the Python drop-in makes when it is handed a numpy array. [async] */
 int32_t lisec_frontend_forward_host(lisec_handle* h, const void* points_host, int32_t points_dtype,
                                     const int64_t* sweep_offsets, int32_t n_sweeps, void* grid, void* stream);
+
+/* [async] lisec_voxel_counts() without the synchronisation: enqueues the device-to-host copy of the totals on `stream`
+ * into caller-owned pinned memory. Layout: int64[8] = {n_voxels, n_points_in_range, n_vfe_rows, n_vfe_tiles,
+ * n_dropped_nonfinite, n_dropped_out_of_range, 0, 0}, then int32[n_sweeps+1] = exclusive prefix of voxels per sweep. */
+int32_t lisec_voxel_counts_async(lisec_handle* h, void* pinned_out, int64_t pinned_bytes, void* stream);
 
 /* Number of kernels the last call on this handle launched (bench.py's gpu_launches). */
 int32_t lisec_last_launch_count(const lisec_handle* h);

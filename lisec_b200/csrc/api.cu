@@ -31,6 +31,13 @@ struct lisec_handle {
   int last_dtype = LISEC_F32;
   SweepOffsets last_so;
   int launches = 0;
+  // host-input pipeline: copies go on their own stream into alternating staging buffers, so the H2D copy of call i+1
+  // overlaps the kernels of call i
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr};  // staging[b] holds the new points
+  cudaEvent_t ev_free[2] = {nullptr, nullptr};    // the kernels that read staging[b] have been enqueued and finished
+  void* staging2 = nullptr;                       // second staging buffer (the first is ws.staging)
+  int staging_idx = 0;
   char err[512];
 };
 
@@ -72,7 +79,7 @@ cudaError_t dev_alloc(lisec_handle* h, T** p, size_t n) {
 
 void free_workspace(Workspace& w) {
   void* ptrs[] = {w.count, w.cell_voxel, w.cell_of_point, w.list_unsorted, w.list_sorted, w.entry_voxel,
-                  w.voxel_cell, w.voxel_start, w.row_start, w.tile_first, w.row_point, w.row_voxel, w.centroid,
+                  w.voxel_cell, w.voxel_start, w.row_start, w.tile_first, w.tile_row0, w.row_voxel, w.row_feat,
                   w.block_sums, w.sweep_voxel_start,
                   w.totals, w.voxel_feat, w.c_empty, w.vfe_w, w.staging, w.empty_desc};
   for (void* p : ptrs)
@@ -118,11 +125,9 @@ int do_voxelize(lisec_handle* h, const void* points, int dtype, const SweepOffse
 }
 
 int do_vfe(lisec_handle* h, float* voxel_feat, cudaStream_t st) {
-  LISEC_CUDA(h, launch_centroids(h->last_points, h->last_dtype, h->geom, h->ws, h->max_voxels, st, &h->launches));
-  const VfeProblem prob{h->ws.tile_first, h->ws.row_start, h->ws.row_point, h->ws.row_voxel, h->ws.centroid,
-                        h->ws.totals + TOT_TILES};
-  LISEC_CUDA(h, launch_vfe(h->last_points, h->last_dtype, h->params, h->ws.vfe_w, prob, voxel_feat, h->sm_count, st,
-                           &h->launches));
+  LISEC_CUDA(h, launch_row_features(h->last_points, h->last_dtype, h->geom, h->ws, h->max_voxels, st, &h->launches));
+  const VfeProblem prob{h->ws.tile_first, h->ws.tile_row0, h->ws.row_voxel, h->ws.row_feat, h->ws.totals + TOT_TILES};
+  LISEC_CUDA(h, launch_vfe(h->params, h->ws.vfe_w, prob, voxel_feat, h->sm_count, st, &h->launches));
   return LISEC_OK;
 }
 
@@ -213,9 +218,9 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
   LISEC_CUDA(h, dev_alloc(h, &w.voxel_start, V + 1));
   LISEC_CUDA(h, dev_alloc(h, &w.row_start, V + 1));
   LISEC_CUDA(h, dev_alloc(h, &w.tile_first, (size_t)h->max_tiles + 2));
-  LISEC_CUDA(h, dev_alloc(h, &w.row_point, P + V));
+  LISEC_CUDA(h, dev_alloc(h, &w.tile_row0, (size_t)h->max_tiles + 2));
   LISEC_CUDA(h, dev_alloc(h, &w.row_voxel, P + V));
-  LISEC_CUDA(h, dev_alloc(h, &w.centroid, 3 * V));
+  LISEC_CUDA(h, dev_alloc(h, &w.row_feat, 6 * (P + V)));
   LISEC_CUDA(h, dev_alloc(h, &w.block_sums, (size_t)3 * h->scan_blocks_cap + 4));
   LISEC_CUDA(h, dev_alloc(h, &w.sweep_voxel_start, (size_t)c.max_sweeps + 2));
   LISEC_CUDA(h, dev_alloc(h, &w.totals, (size_t)TOT_COUNT));
@@ -223,10 +228,16 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
   LISEC_CUDA(h, dev_alloc(h, &w.c_empty, (size_t)c.c3));
   LISEC_CUDA(h, dev_alloc(h, &w.vfe_w, (size_t)kVfeBlobFloats));
   LISEC_CUDA(h, dev_alloc(h, reinterpret_cast<unsigned char**>(&w.staging), P * 3 * sizeof(double)));
+  LISEC_CUDA(h, dev_alloc(h, reinterpret_cast<unsigned char**>(&h->staging2), P * 3 * sizeof(double)));
+  LISEC_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    LISEC_CUDA(h, cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming));
+    LISEC_CUDA(h, cudaEventCreateWithFlags(&h->ev_free[b], cudaEventDisableTiming));
+  }
   LISEC_CUDA(h, dev_alloc(h, &w.empty_desc, (size_t)16));
   // the one-voxel problem whose VFE output is c_empty: 0 kept points, 1 pad row, 1 tile
-  // layout: tile_first {0,1} | row_start {0,1} | n_tiles (int64) 1 | row_point {-1} | row_voxel {0}
-  int desc[16] = {0, 1, 0, 1, 0, 0, -1, 0};
+  // layout: tile_first {0,1} | tile_row0 {0,1} | n_tiles (int64) 1 | row_voxel {0} | pad | row_feat 6 x 0.f
+  int desc[16] = {0, 1, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const long long one = 1;
   std::memcpy(&desc[4], &one, sizeof(one));
   LISEC_CUDA(h, cudaMemcpy(w.empty_desc, desc, sizeof(desc), cudaMemcpyHostToDevice));
@@ -238,6 +249,12 @@ void lisec_destroy(lisec_handle* h) {
   if (!h) return;
   if (h->sm_count > 0) cudaSetDevice(h->cfg.device);
   free_workspace(h->ws);
+  if (h->staging2) cudaFree(h->staging2);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (int b = 0; b < 2; ++b) {
+    if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
+    if (h->ev_free[b]) cudaEventDestroy(h->ev_free[b]);
+  }
   delete h;
 }
 
@@ -279,8 +296,9 @@ int32_t lisec_set_vfe_weights(lisec_handle* h, const lisec_vfe_weights* w, void*
   // c_empty: the same kernel, run on one voxel that holds nothing but the pad row
   LISEC_CUDA(h, cudaMemcpyAsync(h->ws.vfe_w, blob, sizeof(float) * kVfeBlobFloats, cudaMemcpyHostToDevice, st));
   const int* d = h->ws.empty_desc;
-  const VfeProblem empty{d, d + 2, d + 6, d + 7, nullptr, reinterpret_cast<const long long*>(d + 4)};
-  LISEC_CUDA(h, launch_vfe(nullptr, LISEC_F32, p, h->ws.vfe_w, empty, h->ws.c_empty, h->sm_count, st, &h->launches));
+  const VfeProblem empty{d, d + 2, d + 6, reinterpret_cast<const float*>(d + 8),
+                         reinterpret_cast<const long long*>(d + 4)};
+  LISEC_CUDA(h, launch_vfe(p, h->ws.vfe_w, empty, h->ws.c_empty, h->sm_count, st, &h->launches));
   LISEC_CUDA(h, cudaStreamSynchronize(st));
   return LISEC_OK;
 }
@@ -382,11 +400,10 @@ static int frontend(lisec_handle* h, const void* dev_points, int dtype, const Sw
                     cudaStream_t st) {
   int rc = do_voxelize(h, dev_points, dtype, so, st);
   if (rc) return rc;
-  LISEC_CUDA(h, launch_centroids(dev_points, dtype, h->geom, h->ws, h->max_voxels, st, &h->launches));
-  const VfeProblem prob{h->ws.tile_first, h->ws.row_start, h->ws.row_point, h->ws.row_voxel, h->ws.centroid,
-                        h->ws.totals + TOT_TILES};
+  LISEC_CUDA(h, launch_row_features(dev_points, dtype, h->geom, h->ws, h->max_voxels, st, &h->launches));
+  const VfeProblem prob{h->ws.tile_first, h->ws.tile_row0, h->ws.row_voxel, h->ws.row_feat, h->ws.totals + TOT_TILES};
   // one kernel: VFE on the FP32 pipe, voxel rows and the c_empty background written to the grid concurrently
-  LISEC_CUDA(h, launch_vfe_to_grid(dev_points, dtype, h->params, h->ws.vfe_w, prob, h->ws, h->geom, so.n,
+  LISEC_CUDA(h, launch_vfe_to_grid(h->params, h->ws.vfe_w, prob, h->ws, h->geom, so.n,
                                    h->cfg.grid_dtype, grid, h->sm_count, st, &h->launches));
   return LISEC_OK;
 }
@@ -422,8 +439,34 @@ int32_t lisec_frontend_forward_host(lisec_handle* h, const void* points_host, in
   LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
   h->launches = 0;
   const size_t bytes = (size_t)so.off[so.n] * 3 * (dtype == LISEC_F64 ? sizeof(double) : sizeof(float));
-  if (bytes) LISEC_CUDA(h, cudaMemcpyAsync(h->ws.staging, points_host, bytes, cudaMemcpyHostToDevice, st));
-  return frontend(h, h->ws.staging, dtype, so, grid, st);
+  const int b = h->staging_idx;
+  h->staging_idx ^= 1;
+  void* staging = b ? h->staging2 : h->ws.staging;
+  // copy stream: wait until the kernels of two calls ago are done with this buffer, then copy
+  LISEC_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_free[b], 0));
+  if (bytes) LISEC_CUDA(h, cudaMemcpyAsync(staging, points_host, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+  LISEC_CUDA(h, cudaEventRecord(h->ev_copied[b], h->copy_stream));
+  // compute stream: wait for the copy, run the path, release the buffer
+  LISEC_CUDA(h, cudaStreamWaitEvent(st, h->ev_copied[b], 0));
+  rc = frontend(h, staging, dtype, so, grid, st);
+  if (rc) return rc;
+  LISEC_CUDA(h, cudaEventRecord(h->ev_free[b], st));
+  return LISEC_OK;
+}
+
+int32_t lisec_voxel_counts_async(lisec_handle* h, void* pinned_out, int64_t pinned_bytes, void* stream) {
+  if (!h) return LISEC_ERR_BAD_ARG;
+  if (!pinned_out) return fail(h, LISEC_ERR_BAD_ARG, "pinned_out is NULL");
+  if (!h->voxelized) return fail(h, LISEC_ERR_STATE, "no lisec_voxelize() result on this handle");
+  const int64_t need = (int64_t)sizeof(long long) * TOT_COUNT + (int64_t)sizeof(int) * (h->last_so.n + 1);
+  if (pinned_bytes < need) return fail(h, LISEC_ERR_BAD_ARG, "pinned_out holds %lld bytes, need %lld", (long long)pinned_bytes, (long long)need);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
+  unsigned char* out = static_cast<unsigned char*>(pinned_out);
+  LISEC_CUDA(h, cudaMemcpyAsync(out, h->ws.totals, sizeof(long long) * TOT_COUNT, cudaMemcpyDeviceToHost, st));
+  LISEC_CUDA(h, cudaMemcpyAsync(out + sizeof(long long) * TOT_COUNT, h->ws.sweep_voxel_start,
+                                sizeof(int) * (h->last_so.n + 1), cudaMemcpyDeviceToHost, st));
+  return LISEC_OK;
 }
 
 }  // extern "C"

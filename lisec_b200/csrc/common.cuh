@@ -70,9 +70,9 @@ struct Workspace {
   int* row_start = nullptr;    // offsets in VFE rows (kept + pad)
   int* tile_first = nullptr;   // first voxel of each VFE tile, [max_tiles + 2]
   // per VFE row, [max_points + max_voxels]: what the VFE kernel needs to start a tile with one coalesced read
-  int* row_point = nullptr;    // global point index of the row, or -1 for the voxel's virtual pad row
   int* row_voxel = nullptr;    // voxel row the VFE row belongs to
-  double* centroid = nullptr;  // [max_voxels][3] float64 mean of the kept points (np.mean order)
+  float* row_feat = nullptr;   // [rows][6] float32 features [x,y,z,x-cx,y-cy,z-cz] (zeros for a pad row)
+  int* tile_row0 = nullptr;    // first VFE row of each tile, [max_tiles + 2]
   int* block_sums = nullptr;   // [3][scan_blocks] reduce -> exclusive prefix
   int* sweep_voxel_start = nullptr;  // [max_sweeps + 1]
   long long* totals = nullptr;       // [TOT_COUNT]
@@ -95,19 +95,19 @@ cudaError_t launch_export(const void* pts, int pts_dtype, const SweepOffsets& so
                           int32_t* point_idx, float* features, float* dense, cudaStream_t st, int* launches);
 // The VFE problem description (device pointers): tiles -> rows -> (point, voxel); see Workspace.
 struct VfeProblem {
-  const int* tile_first;
-  const int* row_start;
-  const int* row_point;
-  const int* row_voxel;
-  const double* centroid;
+  const int* tile_first;   // [n_tiles + 1] first voxel of each tile
+  const int* tile_row0;    // [n_tiles + 1] first VFE row of each tile
+  const int* row_voxel;    // [rows]
+  const float* row_feat;   // [rows][6]
   const long long* n_tiles;
 };
-cudaError_t launch_centroids(const void* pts, int pts_dtype, const Geom& g, const Workspace& w, long long max_voxels,
-                             cudaStream_t st, int* launches);
-cudaError_t launch_vfe(const void* pts, int pts_dtype, const VfeSmall& p, const float* wblob, const VfeProblem& prob,
+// float64 centroid + float32 feature rows for every VFE row (model_training.py:134-141), contiguous in row order
+cudaError_t launch_row_features(const void* pts, int pts_dtype, const Geom& g, const Workspace& w, long long max_voxels,
+                                cudaStream_t st, int* launches);
+cudaError_t launch_vfe(const VfeSmall& p, const float* wblob, const VfeProblem& prob,
                        float* voxel_feat, int sm_count, cudaStream_t st, int* launches);
 // Fused VFE + dense grid: voxel rows go straight to their cells, a 9th warp per CTA streams c_empty into empty cells.
-cudaError_t launch_vfe_to_grid(const void* pts, int pts_dtype, const VfeSmall& p, const float* wblob,
+cudaError_t launch_vfe_to_grid(const VfeSmall& p, const float* wblob,
                                const VfeProblem& prob, const Workspace& w, const Geom& g, int n_sweeps, int grid_dtype,
                                void* grid, int sm_count, cudaStream_t st, int* launches);
 cudaError_t launch_grid_write(const Geom& g, int n_sweeps, int c3, int grid_dtype, const int* cell_voxel,

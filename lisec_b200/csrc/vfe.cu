@@ -24,6 +24,8 @@
 // the level of a CPU float32 forward; dense_2 is a plain float32 FMA chain.
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "vfe_math.cuh"
 
@@ -38,6 +40,13 @@ __device__ __forceinline__ unsigned pack_bf16x2(float a, float b) {
   return *reinterpret_cast<unsigned*>(&h);
 }
 
+constexpr int kGroups = 2;  // tile groups per CTA
+constexpr int kWriterThreads = 128;  // one warpgroup of background writers (register-trimmed with setmaxnreg)
+#ifndef LISEC_WRITER_WARPS
+#define LISEC_WRITER_WARPS 4
+#endif
+constexpr int kWriterWarps = LISEC_WRITER_WARPS;  // how many of its 4 warps actually write
+constexpr int kCtaThreads = kGroups * kVfeThreads + kWriterThreads;
 constexpr int kRows = kVfeThreads;   // 256 rows per tile
 constexpr int kVox = kVfeThreads / 2;  // 128 voxels per tile: a non-full voxel has >= 2 rows, a full one T >= 2
 constexpr int PR = kRows + 4;        // float pitch of row-indexed k-major tiles (16-byte aligned rows, 4-bank skew)
@@ -56,9 +65,14 @@ constexpr int OFF_H2T = OFF_P1T + 16 * PV * 4;     // [32][PR]   VFE-2 outputs; 
 constexpr int OFF_Q = OFF_H2T + 32 * PR * 4;       // [kVox][QS] pooled-half products of the current layer
 constexpr int OFF_ROWVOX = OFF_Q + kVox * QS * 4;  // uint8[kRows] local voxel of each tile row
 constexpr int OFF_VOXCELL = OFF_ROWVOX + kRows;      // int[kVox] cell of each tile voxel (grid output modes)
-constexpr int kSmemBytes = OFF_VOXCELL + kVox * 4;
+constexpr int OFF_FSTAGE = OFF_VOXCELL + kVox * 4;   // float[kRows][6] the NEXT tile's feature rows (cp.async prefetch)
+constexpr int OFF_VSTAGE = OFF_FSTAGE + kRows * 6 * 4;  // int[kRows] the NEXT tile's row -> voxel
+constexpr int kGroupBytes = OFF_VSTAGE + kRows * 4 - OFF_H1T;  // per tile group; the weights (first 20 KB) are shared
+constexpr int OFF_BG = OFF_H1T + kGroups * kGroupBytes;  // 32 cells x 64 channels of c_empty: the TMA source tile
+constexpr int kSmemBytes = OFF_BG + 32 * 64 * 4;
 static_assert(32 * PV * 4 <= 16 * PR * 4 + 16 * PV * 4, "P2T must fit in H1T+P1T");
-static_assert(2 * (kSmemBytes + 1024) <= 233472, "two CTAs per SM");
+static_assert(kSmemBytes <= 232448, "one CTA per SM, 227 KB opt-in limit");
+static_assert(kGroupBytes % 16 == 0, "group regions stay 16-byte aligned");
 
 // ---- register-tile GEMM: acc[R][C] += A[k][row(r)] * W[k][col(c)], k = 0..K-1 -------------------------------
 // The lane's rows come as R/4 float4 chunks at row0 + i*chunk_stride (consecutive lanes -> consecutive 16 bytes);
@@ -123,8 +137,16 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ sA, int pitc
   }
 }
 
-// barrier among the 8 compute warps only (the 9th warp of the fused kernel streams the grid background and never joins)
-__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kVfeThreads) : "memory"); }
+// One CTA per SM = two tile groups of 8 warps (each works on its own tile with its own named barrier) plus one
+// warpgroup of background writers. 20 warps put 5 on every SM sub-partition, i.e. 96 registers each at launch; the
+// writers then give theirs back (setmaxnreg.dec 32) and the four compute warpgroups grow to 112 (setmaxnreg.inc;
+// the pool is per CTA, so the compute side can only take what the writers released: 4 x (112-96) = 96-32).
+__device__ __forceinline__ void group_sync(int group) {
+  asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kVfeThreads) : "memory");
+}
+__device__ __forceinline__ void all_compute_sync() {
+  asm volatile("bar.sync 3, %0;" ::"n"(kGroups * kVfeThreads) : "memory");
+}
 
 // position of tile row r inside a k-major row tile: lane l = r/8 owns rows 8l..8l+7 and loads them as two float4 at
 // 4l and 128+4l, so both 16-byte loads of a warp cover 512 contiguous bytes (no bank conflicts)
@@ -217,14 +239,90 @@ __device__ __forceinline__ void pool_lane_rows(const float (&val)[8][NC], const 
   if (m.emit_tail) emit(m.kt, run);
 }
 
-// float64 mean of each voxel's kept points, added in list order with one divide — np.mean(currPoints, axis=0)
-// (model_training.py:135) bit for bit. One thread per voxel; a pre-pass so that VFE tiles start without a barrier.
+// MODE 0: voxel rows to voxel_feat[V][64] (float32), no background.  MODE 1 / 2: rows straight into the float32 /
+// bf16 dense grid at their cell, background by the writer warpgroup.
+struct VfeOutput {
+  float* voxel_feat;
+  void* grid;
+  const int* voxel_cell;  // voxel row -> cell (sweep * cells + (z*nx + x)*ny + y)
+  const int* cell_voxel;  // occupancy map
+  const float* c_empty;
+  long long ncells;
+};
+
+// ---- background writer (fused kernel, the CTA's last warpgroup) ----------------------------------------------
+// c_empty goes into every EMPTY cell of the grid while the compute warps keep the FP32 pipe busy; occupied cells are
+// written by the tiles' own voxel rows, so every grid element is still written exactly once.
+// The data never touches the LSU: a 32-cell tile of replicated c_empty sits in shared memory and every run of
+// consecutive empty cells is ONE TMA bulk store (cp.async.bulk shared -> global, SASS UBLKCP) issued by the lane of
+// the run's first cell.
+__device__ __forceinline__ void bulk_store(void* gdst, unsigned ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <typename GT>
+__device__ __forceinline__ void background_writer(const int* __restrict__ cell_voxel, const float* __restrict__ c_empty,
+                                                  GT* __restrict__ grid, long long ncells, unsigned char* sBg,
+                                                  int wtid) {
+  const int lane = wtid & 31, wwarp = wtid >> 5;
+  // fill the tile: 32 cells x 64 channels of GT, every cell = c_empty (rounded once for bf16)
+  for (int i = wtid; i < 32 * 64; i += kWriterThreads) {
+    if (sizeof(GT) == 4) reinterpret_cast<float*>(sBg)[i] = c_empty[i & 63];
+    else reinterpret_cast<__nv_bfloat16*>(sBg)[i] = __float2bfloat16_rn(c_empty[i & 63]);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA
+  asm volatile("bar.sync 4, %0;" ::"n"(kWriterThreads) : "memory");
+  if (wwarp >= kWriterWarps) return;
+  const unsigned src = (unsigned)__cvta_generic_to_shared(sBg);
+  const int ngroups = (int)((ncells + 31) >> 5);
+  const int stride = gridDim.x * kWriterWarps;
+  constexpr int U = 4;  // 32-cell groups per step; the next step's occupancy words are already in flight
+  auto load_occ = [&](int g0, int (&occ)[U]) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int g = g0 + u * stride;
+      const long long cell = ((long long)g << 5) + lane;
+      occ[u] = (g < ngroups && cell < ncells) ? __ldg(cell_voxel + cell) : 0;  // 0 = "not empty": nothing to write
+    }
+  };
+  int occ[U], nxt[U];
+  int g0 = blockIdx.x * kWriterWarps + wwarp;
+  load_occ(g0, occ);
+  for (; g0 < ngroups; g0 += U * stride) {
+    load_occ(g0 + U * stride, nxt);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned empty = __ballot_sync(0xffffffffu, occ[u] < 0);
+      const bool starts = ((empty >> lane) & 1u) && !(lane > 0 && ((empty >> (lane - 1)) & 1u));
+      if (starts) {
+        const unsigned rest = ~(empty >> lane);  // zeros shift in on top, so rest == 0 only for lane 0 of a full group
+        const int len = rest ? __ffs(rest) - 1 : 32;  // consecutive empty cells from this lane on
+        GT* dst = grid + (((long long)(g0 + u * stride) << 5) + lane) * 64;
+        bulk_store(dst, src, (unsigned)(len * 64 * sizeof(GT)));
+      }
+    }
+    bulk_commit();
+#pragma unroll
+    for (int u = 0; u < U; ++u) occ[u] = nxt[u];
+  }
+  bulk_wait_all();  // the tile must outlive every read of it; also makes the writes complete before the warp retires
+}
+
+// Pre-pass, one thread per voxel: float64 mean of the voxel's kept points, added in list order with one divide —
+// np.mean(currPoints, axis=0) (model_training.py:135) bit for bit — then the float32 feature rows
+// [x,y,z,x-cx,y-cy,z-cz] (:137-140 + the Keras input cast) of its VFE rows, contiguous in row order, and six zeros for
+// the virtual pad row (:141). The VFE kernel then starts every tile from one contiguous, prefetchable 24 B/row read
+// instead of a chain of dependent gathers.
 template <typename PT>
-__global__ void __launch_bounds__(256) centroid_kernel(const PT* __restrict__ pts, int T,
-                                                       const int* __restrict__ voxel_start,
-                                                       const int* __restrict__ list_sorted,
-                                                       const long long* __restrict__ totals,
-                                                       double* __restrict__ centroid) {
+__global__ void __launch_bounds__(256) row_features_kernel(const PT* __restrict__ pts, int T,
+                                                           const int* __restrict__ voxel_start,
+                                                           const int* __restrict__ row_start,
+                                                           const int* __restrict__ list_sorted,
+                                                           const long long* __restrict__ totals,
+                                                           float* __restrict__ row_feat) {
   const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= totals[TOT_VOXELS]) return;
   const int s = voxel_start[v];
@@ -239,112 +337,119 @@ __global__ void __launch_bounds__(256) centroid_kernel(const PT* __restrict__ pt
     sz += (double)z;
   }
   const double n = (double)(kept > 0 ? kept : 1);
-  centroid[3 * v] = sx / n;
-  centroid[3 * v + 1] = sy / n;
-  centroid[3 * v + 2] = sz / n;
-}
-
-// ---- background writer (fused kernel, warp 8 of every CTA) --------------------------------------------------
-// Streams c_empty into every EMPTY cell of the grid while the compute warps are busy on the FP32 pipe; occupied cells
-// are written by the compute warps (their voxel rows), so every grid element is still written exactly once.
-// 32 cells per step: one coalesced 128-byte read of the occupancy map, then 16-byte streaming stores.
-template <typename GT>
-__device__ __forceinline__ void background_writer(const int* __restrict__ cell_voxel, const float* __restrict__ c_empty,
-                                                  GT* __restrict__ grid, long long ncells, int lane) {
-  constexpr int LPC = sizeof(GT) == 4 ? 16 : 8;  // lanes per cell: 64 channels x sizeof(GT) / 16 bytes
-  constexpr int CPS = 32 / LPC;                  // cells per store instruction
-  const int sub = lane / LPC, chunk = lane % LPC;
-  uint4 bg;
-  if (sizeof(GT) == 4) {
-    bg = reinterpret_cast<const uint4*>(c_empty)[chunk];
-  } else {
-    const float4 b0 = reinterpret_cast<const float4*>(c_empty)[2 * chunk];
-    const float4 b1 = reinterpret_cast<const float4*>(c_empty)[2 * chunk + 1];
-    bg = make_uint4(pack_bf16x2(b0.x, b0.y), pack_bf16x2(b0.z, b0.w), pack_bf16x2(b1.x, b1.y), pack_bf16x2(b1.z, b1.w));
+  const double cx = sx / n, cy = sy / n, cz = sz / n;
+  float2* dst = reinterpret_cast<float2*>(row_feat + (size_t)row_start[v] * 6);
+  for (int i = 0; i < kept; ++i) {
+    PT x, y, z;
+    load_point(pts, (long long)list_sorted[s + i], x, y, z);
+    float f[6];
+    point_features((double)x, (double)y, (double)z, cx, cy, cz, f);
+    dst[3 * i] = make_float2(f[0], f[1]);
+    dst[3 * i + 1] = make_float2(f[2], f[3]);
+    dst[3 * i + 2] = make_float2(f[4], f[5]);
   }
-  const long long ngroups = (ncells + 31) >> 5;
-  constexpr int U = 4;  // occupancy-map loads kept in flight
-  for (long long g0 = blockIdx.x; g0 < ngroups; g0 += (long long)gridDim.x * U) {
-    int occ[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long cell = ((g0 + (long long)u * gridDim.x) << 5) + lane;
-      occ[u] = (g0 + (long long)u * gridDim.x < ngroups && cell < ncells) ? __ldg(cell_voxel + cell) : 0;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long base = (g0 + (long long)u * gridDim.x) << 5;
-#pragma unroll
-      for (int i = 0; i < 32 / CPS; ++i) {
-        const int vox = __shfl_sync(0xffffffffu, occ[u], CPS * i + sub);
-        if (vox < 0) __stcs(reinterpret_cast<uint4*>(grid + (base + CPS * i + sub) * 64) + chunk, bg);
-      }
-    }
+  if (kept < T) {
+    dst[3 * kept] = make_float2(0.f, 0.f);
+    dst[3 * kept + 1] = make_float2(0.f, 0.f);
+    dst[3 * kept + 2] = make_float2(0.f, 0.f);
   }
 }
 
-// MODE 0: voxel rows to voxel_feat[V][64] (float32), no background.  MODE 1 / 2: rows straight into the float32 /
-// bf16 dense grid at their cell, background by the 9th warp.
-struct VfeOutput {
-  float* voxel_feat;
-  void* grid;
-  const int* voxel_cell;  // voxel row -> cell (sweep * cells + (z*nx + x)*ny + y)
-  const int* cell_voxel;  // occupancy map
-  const float* c_empty;
-  long long ncells;
-};
+__device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <typename PT, int MODE>
-__global__ void __launch_bounds__(kVfeThreads + 32, 2)
-    vfe_kernel(const PT* __restrict__ pts, const __grid_constant__ VfeSmall P, const float* __restrict__ wblob,
+template <int MODE>
+__global__ void __launch_bounds__(kCtaThreads, 1)
+    vfe_kernel(const __grid_constant__ VfeSmall P, const float* __restrict__ wblob,
                const __grid_constant__ VfeProblem prob, const __grid_constant__ VfeOutput out) {
   extern __shared__ __align__(16) unsigned char smem[];
-  if (threadIdx.x >= kVfeThreads) {  // warp 8
-    if (MODE == 1) background_writer(out.cell_voxel, out.c_empty, static_cast<float*>(out.grid), out.ncells, threadIdx.x & 31);
-    if (MODE == 2) background_writer(out.cell_voxel, out.c_empty, static_cast<__nv_bfloat16*>(out.grid), out.ncells, threadIdx.x & 31);
+  if (threadIdx.x >= kGroups * kVfeThreads) {  // the writer warpgroup
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    const int wtid = threadIdx.x - kGroups * kVfeThreads;
+    if (MODE == 1)
+      background_writer(out.cell_voxel, out.c_empty, static_cast<float*>(out.grid), out.ncells, smem + OFF_BG, wtid);
+    if (MODE == 2)
+      background_writer(out.cell_voxel, out.c_empty, static_cast<__nv_bfloat16*>(out.grid), out.ncells, smem + OFF_BG,
+                        wtid);
     return;
   }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");  // 4 x (112 - 96) = 96 - 32: exactly what the writers released
+  const int group = threadIdx.x / kVfeThreads;
+  const int tid = threadIdx.x % kVfeThreads, lane = tid & 31, warp = tid >> 5;
+  // register tiles: lane = row group (8 tile rows / 4 voxel rows), warp = column group
+  unsigned char* gsm = smem + group * kGroupBytes;  // this group's activations; offsets below are group-relative
   float* sW2P = reinterpret_cast<float*>(smem + OFF_W2P);
   float* sW2X = reinterpret_cast<float*>(smem + OFF_W2X);
   float* sW3P = reinterpret_cast<float*>(smem + OFF_W3P);
   float* sW3X = reinterpret_cast<float*>(smem + OFF_W3X);
-  float* sH1T = reinterpret_cast<float*>(smem + OFF_H1T);
-  float* sP1T = reinterpret_cast<float*>(smem + OFF_P1T);
-  float* sP2T = reinterpret_cast<float*>(smem + OFF_P2T);
-  float* sH2T = reinterpret_cast<float*>(smem + OFF_H2T);
-  float* sQ = reinterpret_cast<float*>(smem + OFF_Q);
-  unsigned char* sRowVox = smem + OFF_ROWVOX;
-  int* sVoxCell = reinterpret_cast<int*>(smem + OFF_VOXCELL);
+  float* sH1T = reinterpret_cast<float*>(gsm + OFF_H1T);
+  float* sP1T = reinterpret_cast<float*>(gsm + OFF_P1T);
+  float* sP2T = reinterpret_cast<float*>(gsm + OFF_P2T);
+  float* sH2T = reinterpret_cast<float*>(gsm + OFF_H2T);
+  float* sQ = reinterpret_cast<float*>(gsm + OFF_Q);
+  unsigned char* sRowVox = gsm + OFF_ROWVOX;
+  int* sVoxCell = reinterpret_cast<int*>(gsm + OFF_VOXCELL);
+  float* sFeatStage = reinterpret_cast<float*>(gsm + OFF_FSTAGE);
+  int* sVoxStage = reinterpret_cast<int*>(gsm + OFF_VSTAGE);
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // register tiles: lane = row group (8 tile rows / 4 voxel rows), warp = column group
   const int n_tiles = (int)*prob.n_tiles;
-  if ((int)blockIdx.x >= n_tiles) return;
-
-  // weights: [W2P | W2X | W3P | W3X] as laid out by the host, straight into the first 20 KB
-  for (int i = tid; i < (OFF_H1T / 16); i += kVfeThreads)
+  // weights: [W2P | W2X | W3P | W3X] as laid out by the host, straight into the first 20 KB (all compute threads)
+  for (int i = threadIdx.x; i < (OFF_H1T / 16); i += kGroups * kVfeThreads)  // (writer threads left above)
     reinterpret_cast<float4*>(smem)[i] = __ldg(reinterpret_cast<const float4*>(wblob) + i);
+  all_compute_sync();
 
-  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const int v0 = prob.tile_first[t], v1 = prob.tile_first[t + 1];
-    const int nv = v1 - v0;
-    const int r0 = prob.row_start[v0];
-    const int nrows = prob.row_start[v1] - r0;
+  // tile header = (first voxel, first row) of the tile and of its successor; rows and voxels are contiguous
+  struct Header { int v0, v1, r0, r1; };
+  auto load_header = [&](int t) {
+    Header h{0, 0, 0, 0};
+    if (t < n_tiles) {
+      h.v0 = __ldg(prob.tile_first + t);
+      h.v1 = __ldg(prob.tile_first + t + 1);
+      h.r0 = __ldg(prob.tile_row0 + t);
+      h.r1 = __ldg(prob.tile_row0 + t + 1);
+    }
+    return h;
+  };
+  // asynchronous copy of a tile's feature rows (24 B each, contiguous) and row -> voxel words into the staging buffers
+  auto prefetch_rows = [&](const Header& h) {
+    const int nrows = h.r1 - h.r0;
+    const float* src = prob.row_feat + (size_t)h.r0 * 6;
+#pragma unroll
+    for (int c = tid; c < kRows * 3; c += kVfeThreads)
+      if (c < nrows * 3) cp_async8(sFeatStage + 2 * c, src + 2 * c);
+    if (tid < nrows) cp_async4(sVoxStage + tid, prob.row_voxel + h.r0 + tid);
+  };
+  const int tstride = gridDim.x * kGroups;
+  int t = blockIdx.x * kGroups + group;
+  Header cur = load_header(t);
+  if (t < n_tiles) prefetch_rows(cur);
+  cp_async_commit();
+  cp_async_wait_all();
+  group_sync(group);
+
+  for (; t < n_tiles; t += tstride) {
+    const int v0 = cur.v0, nv = cur.v1 - cur.v0, nrows = cur.r1 - cur.r0;
     const bool has_row = tid < nrows;
+    const Header nxt = load_header(t + tstride);  // consumed after the first barrier: its latency hides behind VFE-1
 
     // ---- VFE-1: Dense(6->16, no bias) + BN + ReLU (addVFELayer(in, 6, 32), :231 -> :155-166); one row per thread ----
     {
-      int p = -1, lv = 255;  // 255 = padding row past the tile's last row
+      float f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      int lv = 255;  // 255 = padding row past the tile's last row
       if (has_row) {
-        p = prob.row_point[r0 + tid];
-        lv = prob.row_voxel[r0 + tid] - v0;
-      }
-      float f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // pad row: six zeros (:141)
-      if (p >= 0) {
-        PT px, py, pz;
-        load_point(pts, (long long)p, px, py, pz);
-        const double* c = prob.centroid + 3 * (size_t)(v0 + lv);
-        point_features((double)px, (double)py, (double)pz, c[0], c[1], c[2], f);
+        const float2 f01 = *reinterpret_cast<const float2*>(sFeatStage + 6 * tid);
+        const float2 f23 = *reinterpret_cast<const float2*>(sFeatStage + 6 * tid + 2);
+        const float2 f45 = *reinterpret_cast<const float2*>(sFeatStage + 6 * tid + 4);
+        f[0] = f01.x; f[1] = f01.y; f[2] = f23.x; f[3] = f23.y; f[4] = f45.x; f[5] = f45.y;
+        lv = sVoxStage[tid] - v0;
       }
       double d[16];
 #pragma unroll
@@ -360,9 +465,13 @@ __global__ void __launch_bounds__(kVfeThreads + 32, 2)
       for (int j = 0; j < 16; ++j)
         sH1T[j * PR + pos] = has_row ? fmaxf(fmaf(__double2float_rn(d[j]), P.a1[j], P.b1[j]), 0.f) : 0.f;
       sRowVox[tid] = (unsigned char)lv;
-      if (MODE != 0 && tid < nv) sVoxCell[tid] = out.voxel_cell[v0 + tid];
     }
-    compute_sync();
+    group_sync(group);
+    // the staging buffers are free again: start the next tile's rows (and this tile's voxel -> cell words, needed only
+    // by the final store) on their way; they land while the GEMMs run
+    if (t + tstride < n_tiles) prefetch_rows(nxt);
+    if (MODE != 0 && tid < nv) cp_async4(sVoxCell + tid, out.voxel_cell + v0 + tid);
+    cp_async_commit();
     const PoolMeta meta = make_pool_meta(sRowVox, lane);
     {  // MaxPoolingVFELayer over T (:160); RepeatLayer is implicit. Warp w pools channels 2w, 2w+1.
       float val[8][2];
@@ -381,7 +490,7 @@ __global__ void __launch_bounds__(kVfeThreads + 32, 2)
         }
       });
     }
-    compute_sync();
+    group_sync(group);
 
     // ---- VFE-2: Dense(32->32) + BN + ReLU on concat[pooled, pointwise] (addVFELayer(., 32, 64), :232) ----
     const int coff4[1] = {warp * 4};
@@ -397,7 +506,7 @@ __global__ void __launch_bounds__(kVfeThreads + 32, 2)
         *reinterpret_cast<float4*>(sQ + (lane * 4 + r) * QS + warp * 4) =
             make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
     }
-    compute_sync();
+    group_sync(group);
     {  // rows: 8x4 tile per thread, accumulators start at the voxel's pooled-half product
       float acc[8][4];
 #pragma unroll
@@ -415,7 +524,7 @@ __global__ void __launch_bounds__(kVfeThreads + 32, 2)
         *reinterpret_cast<float4*>(dst) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
         *reinterpret_cast<float4*>(dst + 128) = make_float4(acc[4][c], acc[5][c], acc[6][c], acc[7][c]);
       }
-      compute_sync();  // every warp is done with sH1T (A operand) and sQ: sP2T may now overwrite sH1T/sP1T
+      group_sync(group);  // every warp is done with sH1T (A operand) and sQ: sP2T may now overwrite sH1T/sP1T
       pool_lane_rows<4>(acc, meta, [&](int v, const float(&x)[4]) {
         if (v < nv) {
 #pragma unroll
@@ -423,7 +532,7 @@ __global__ void __launch_bounds__(kVfeThreads + 32, 2)
         }
       });
     }
-    compute_sync();
+    group_sync(group);
 
     // ---- FCN: Dense(64->64) + BN + ReLU (addFCN(., 64, 64), :233), then MaxPoolingVFELayer(combine=True) (:235) ----
     const int coff8[2] = {warp * 4, 32 + warp * 4};  // this warp's 8 output channels
@@ -441,7 +550,8 @@ __global__ void __launch_bounds__(kVfeThreads + 32, 2)
         *reinterpret_cast<float4*>(dst + coff8[1]) = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
       }
     }
-    compute_sync();
+    cp_async_wait_all();  // issued a whole tile ago; the barrier below publishes the staged rows and sVoxCell
+    group_sync(group);
     {  // rows: 8x8 tile per thread; the per-voxel max goes straight from registers to the output row
       float out8[8][8];
 #pragma unroll
@@ -478,57 +588,50 @@ __global__ void __launch_bounds__(kVfeThreads + 32, 2)
         }
       });
     }
-    compute_sync();  // the next tile's setup overwrites sH1T and sRowVox
+    group_sync(group);  // the next tile's setup overwrites sH1T and sRowVox
+    cur = nxt;
   }
 }
 
 }  // namespace
 
-cudaError_t launch_centroids(const void* pts, int pts_dtype, const Geom& g, const Workspace& w, long long max_voxels,
-                             cudaStream_t st, int* launches) {
+cudaError_t launch_row_features(const void* pts, int pts_dtype, const Geom& g, const Workspace& w, long long max_voxels,
+                                cudaStream_t st, int* launches) {
   const unsigned blocks = (unsigned)((max_voxels + 255) / 256);  // threads past the device-side voxel count exit
   if (pts_dtype == LISEC_F32)
-    centroid_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(pts), g.T, w.voxel_start, w.list_sorted,
-                                                   w.totals, w.centroid);
+    row_features_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(pts), g.T, w.voxel_start, w.row_start,
+                                                       w.list_sorted, w.totals, w.row_feat);
   else
-    centroid_kernel<double><<<blocks, 256, 0, st>>>(static_cast<const double*>(pts), g.T, w.voxel_start,
-                                                    w.list_sorted, w.totals, w.centroid);
+    row_features_kernel<double><<<blocks, 256, 0, st>>>(static_cast<const double*>(pts), g.T, w.voxel_start,
+                                                        w.row_start, w.list_sorted, w.totals, w.row_feat);
   ++*launches;
   return cudaGetLastError();
 }
 
-template <typename PT, int MODE>
-static cudaError_t launch_vfe_mode(const PT* pts, const VfeSmall& p, const float* wblob, const VfeProblem& prob,
-                                   const VfeOutput& out, int sm_count, cudaStream_t st) {
-  cudaError_t err = cudaFuncSetAttribute(vfe_kernel<PT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+template <int MODE>
+static cudaError_t launch_vfe_mode(const VfeSmall& p, const float* wblob, const VfeProblem& prob, const VfeOutput& out,
+                                   int sm_count, cudaStream_t st) {
+  cudaError_t err = cudaFuncSetAttribute(vfe_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (err != cudaSuccess) return err;
-  // persistent: two resident CTAs per SM (8 compute warps + 1 background-writer warp each), tiles strided over them
-  vfe_kernel<PT, MODE><<<2 * sm_count, kVfeThreads + 32, kSmemBytes, st>>>(pts, p, wblob, prob, out);
+  // persistent: one CTA per SM (2 tile groups x 8 warps + 1 writer warpgroup), tiles strided over the tile groups
+  vfe_kernel<MODE><<<sm_count, kCtaThreads, kSmemBytes, st>>>(p, wblob, prob, out);
   return cudaGetLastError();
 }
 
-cudaError_t launch_vfe(const void* pts, int pts_dtype, const VfeSmall& p, const float* wblob, const VfeProblem& prob,
-                       float* voxel_feat, int sm_count, cudaStream_t st, int* launches) {
+cudaError_t launch_vfe(const VfeSmall& p, const float* wblob, const VfeProblem& prob, float* voxel_feat, int sm_count,
+                       cudaStream_t st, int* launches) {
   const VfeOutput out{voxel_feat, nullptr, nullptr, nullptr, nullptr, 0};
   ++*launches;
-  if (pts_dtype == LISEC_F32)
-    return launch_vfe_mode<float, 0>(static_cast<const float*>(pts), p, wblob, prob, out, sm_count, st);
-  return launch_vfe_mode<double, 0>(static_cast<const double*>(pts), p, wblob, prob, out, sm_count, st);
+  return launch_vfe_mode<0>(p, wblob, prob, out, sm_count, st);
 }
 
-cudaError_t launch_vfe_to_grid(const void* pts, int pts_dtype, const VfeSmall& p, const float* wblob,
-                               const VfeProblem& prob, const Workspace& w, const Geom& g, int n_sweeps, int grid_dtype,
-                               void* grid, int sm_count, cudaStream_t st, int* launches) {
+cudaError_t launch_vfe_to_grid(const VfeSmall& p, const float* wblob, const VfeProblem& prob, const Workspace& w,
+                               const Geom& g, int n_sweeps, int grid_dtype, void* grid, int sm_count, cudaStream_t st,
+                               int* launches) {
   const VfeOutput out{nullptr, grid, w.voxel_cell, w.cell_voxel, w.c_empty, (long long)n_sweeps * g.cells};
   ++*launches;
-  if (pts_dtype == LISEC_F32) {
-    const float* q = static_cast<const float*>(pts);
-    return grid_dtype == LISEC_F32 ? launch_vfe_mode<float, 1>(q, p, wblob, prob, out, sm_count, st)
-                                   : launch_vfe_mode<float, 2>(q, p, wblob, prob, out, sm_count, st);
-  }
-  const double* q = static_cast<const double*>(pts);
-  return grid_dtype == LISEC_F32 ? launch_vfe_mode<double, 1>(q, p, wblob, prob, out, sm_count, st)
-                                 : launch_vfe_mode<double, 2>(q, p, wblob, prob, out, sm_count, st);
+  return grid_dtype == LISEC_F32 ? launch_vfe_mode<1>(p, wblob, prob, out, sm_count, st)
+                                 : launch_vfe_mode<2>(p, wblob, prob, out, sm_count, st);
 }
 
 }  // namespace lisec

@@ -13,8 +13,7 @@
 //                needs no memset) and writes the CSR payload in arrival order.
 //   order_pass   rank-by-counting inside each voxel segment, early exit at T: entry p lands at position
 //                #{q in voxel : q < p}. This is what makes the slot assignment deterministic in point order
-//                whatever order the atomics resolved in. Also marks the VFE tile boundaries and writes the per-row
-//                tables (row -> point, row -> voxel) the VFE kernel starts its tiles from.
+//                whatever order the atomics resolved in. Also marks the VFE tile boundaries and the row -> voxel table.
 #include "common.cuh"
 
 namespace lisec {
@@ -346,7 +345,7 @@ __global__ void __launch_bounds__(256) order_pass_kernel(const int* __restrict__
                                                          const int* __restrict__ row_start, int T,
                                                          int rows_per_tile, long long* __restrict__ totals,
                                                          int* __restrict__ list_sorted,
-                                                         int* __restrict__ tile_first, int* __restrict__ row_point,
+                                                         int* __restrict__ tile_first, int* __restrict__ tile_row0,
                                                          int* __restrict__ row_voxel) {
   const long long n_entries = totals[TOT_ENTRIES];
   const long long n_voxels = totals[TOT_VOXELS];
@@ -356,9 +355,13 @@ __global__ void __launch_bounds__(256) order_pass_kernel(const int* __restrict__
     // differ by at most one tile and every tile index up to the last one has a first voxel.
     const int t = row_start[e] / rows_per_tile;
     const int tprev = e > 0 ? row_start[e - 1] / rows_per_tile : -1;
-    if (t != tprev) tile_first[t] = (int)e;
+    if (t != tprev) {
+      tile_first[t] = (int)e;
+      tile_row0[t] = row_start[e];
+    }
     if (e == n_voxels - 1) {
       tile_first[t + 1] = (int)n_voxels;
+      tile_row0[t + 1] = row_start[n_voxels];
       totals[TOT_TILES] = t + 1;
     }
   }
@@ -378,12 +381,8 @@ __global__ void __launch_bounds__(256) order_pass_kernel(const int* __restrict__
     list_sorted[s + rank] = p;
     // VFE row tables: row_start[v] + rank is this point's row; a non-full voxel gets one virtual pad row after its points
     const int row = row_start[v] + rank;
-    row_point[row] = p;
     row_voxel[row] = v;
-    if (rank == 0 && n < T) {
-      row_point[row + n] = -1;
-      row_voxel[row + n] = v;
-    }
+    if (rank == 0 && n < T) row_voxel[row + n] = v;
   }
 }
 
@@ -433,7 +432,7 @@ cudaError_t launch_fill_and_order(long long n_total, const Geom& g, int rows_per
   // entries <= points; threads beyond the device-side totals exit
   order_pass_kernel<<<(unsigned)((n_total + 255) / 256), 256, 0, st>>>(
       w.list_unsorted, w.entry_voxel, w.voxel_start, w.row_start, g.T, rows_per_tile, w.totals, w.list_sorted,
-      w.tile_first, w.row_point, w.row_voxel);
+      w.tile_first, w.tile_row0, w.row_voxel);
   *launches += 2;
   return cudaGetLastError();
 }

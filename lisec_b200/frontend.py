@@ -179,6 +179,24 @@ class Frontend:
             )
         return per, nv.value, nin.value, noor.value, nnf.value
 
+    COUNTS_BYTES = 8 * 8 + 4 * (N.LISEC_MAX_SWEEPS + 1)
+
+    def counts_async(self, pinned: torch.Tensor) -> None:
+        """Enqueue the totals read-back into a pinned uint8 tensor (>= COUNTS_BYTES); decode with decode_counts()
+        once the stream (or an event recorded after this call) has completed."""
+        if not pinned.is_pinned() or pinned.dtype != torch.uint8 or pinned.numel() < self.COUNTS_BYTES:
+            raise ValueError("counts_async() wants a pinned uint8 tensor of at least %d bytes" % self.COUNTS_BYTES)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.lisec_voxel_counts_async(self._h, C.c_void_p(pinned.data_ptr()), pinned.numel(),
+                                                           self._stream()))
+
+    def decode_counts(self, pinned: torch.Tensor, n_sweeps: Optional[int] = None):
+        n = self._n_sweeps if n_sweeps is None else n_sweeps
+        raw = pinned.numpy()
+        tot = raw[:64].view(np.int64)
+        svs = raw[64:64 + 4 * (n + 1)].view(np.int32)
+        return np.diff(svs), int(tot[0]), int(tot[1]), int(tot[5]), int(tot[4])
+
     def export(self, features: bool = True) -> VoxelSet:
         per, V, nin, noor, nnf = self.counts()
         dev = self.device
