@@ -161,7 +161,12 @@ int32_t lisec_vfe_forward(lisec_handle* h, float* voxel_feat, void* stream);
  * (model_training.py:235-236). Every element is written exactly once: voxel_feat[v] where occupied, c_empty elsewhere. */
 int32_t lisec_scatter_dense(lisec_handle* h, const float* voxel_feat, void* grid, void* stream);
 
-/* [async] lisec_voxelize + lisec_vfe_forward + lisec_scatter_dense without host round trips: what
+/* [async] lisec_vfe_forward + lisec_scatter_dense as ONE kernel on the grouping of the last lisec_voxelize(): the voxel
+ * rows go straight from registers to their cells while a writer warpgroup streams c_empty into the empty cells by TMA
+ * bulk stores; no voxel_feat round trip, every grid element written exactly once. */
+int32_t lisec_vfe_scatter_fused(lisec_handle* h, void* grid, void* stream);
+
+/* [async] lisec_voxelize + lisec_vfe_scatter_fused without host round trips: what
  * VFE_preprocessing -> sparse.to_dense -> model.predict's first 23 layers do (Predict.py:21-38). */
 int32_t lisec_frontend_forward(lisec_handle* h, const void* points, int32_t points_dtype,
                                const int64_t* sweep_offsets, int32_t n_sweeps, void* grid, void* stream);

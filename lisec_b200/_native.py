@@ -88,6 +88,7 @@ SIGNATURES = {
     "lisec_emit_dense_input": (C.c_int32, [_H, _VP, _VP]),
     "lisec_vfe_forward": (C.c_int32, [_H, _VP, _VP]),
     "lisec_scatter_dense": (C.c_int32, [_H, _VP, _VP, _VP]),
+    "lisec_vfe_scatter_fused": (C.c_int32, [_H, _VP, _VP]),
     "lisec_frontend_forward": (C.c_int32, [_H, _VP, C.c_int32, _I64P, C.c_int32, _VP, _VP]),
     "lisec_frontend_forward_host": (C.c_int32, [_H, _VP, C.c_int32, _I64P, C.c_int32, _VP, _VP]),
     "lisec_voxel_counts_async": (C.c_int32, [_H, _VP, C.c_int64, _VP]),

@@ -396,16 +396,31 @@ int32_t lisec_scatter_dense(lisec_handle* h, const float* voxel_feat, void* grid
   return LISEC_OK;
 }
 
+static int fused_stage(lisec_handle* h, void* grid, cudaStream_t st) {
+  LISEC_CUDA(h, launch_row_features(h->last_points, h->last_dtype, h->geom, h->ws, h->max_voxels, st, &h->launches));
+  const VfeProblem prob{h->ws.tile_first, h->ws.tile_row0, h->ws.row_voxel, h->ws.row_feat, h->ws.totals + TOT_TILES};
+  // one kernel: VFE on the FP32 pipe, voxel rows and the c_empty background written to the grid concurrently
+  LISEC_CUDA(h, launch_vfe_to_grid(h->params, h->ws.vfe_w, prob, h->ws, h->geom, h->last_so.n, h->cfg.grid_dtype, grid,
+                                   h->sm_count, st, &h->launches));
+  return LISEC_OK;
+}
+
 static int frontend(lisec_handle* h, const void* dev_points, int dtype, const SweepOffsets& so, void* grid,
                     cudaStream_t st) {
   int rc = do_voxelize(h, dev_points, dtype, so, st);
   if (rc) return rc;
-  LISEC_CUDA(h, launch_row_features(dev_points, dtype, h->geom, h->ws, h->max_voxels, st, &h->launches));
-  const VfeProblem prob{h->ws.tile_first, h->ws.tile_row0, h->ws.row_voxel, h->ws.row_feat, h->ws.totals + TOT_TILES};
-  // one kernel: VFE on the FP32 pipe, voxel rows and the c_empty background written to the grid concurrently
-  LISEC_CUDA(h, launch_vfe_to_grid(h->params, h->ws.vfe_w, prob, h->ws, h->geom, so.n,
-                                   h->cfg.grid_dtype, grid, h->sm_count, st, &h->launches));
-  return LISEC_OK;
+  return fused_stage(h, grid, st);
+}
+
+int32_t lisec_vfe_scatter_fused(lisec_handle* h, void* grid, void* stream) {
+  if (!h) return LISEC_ERR_BAD_ARG;
+  if (!grid) return fail(h, LISEC_ERR_BAD_ARG, "grid is NULL");
+  if (reinterpret_cast<uintptr_t>(grid) & 15) return fail(h, LISEC_ERR_BAD_ARG, "grid must be 16-byte aligned");
+  if (!h->weights_set) return fail(h, LISEC_ERR_STATE, "lisec_set_vfe_weights() has not been called");
+  if (!h->voxelized) return fail(h, LISEC_ERR_STATE, "no lisec_voxelize() result on this handle");
+  LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
+  h->launches = 0;
+  return fused_stage(h, grid, static_cast<cudaStream_t>(stream));
 }
 
 int32_t lisec_frontend_forward(lisec_handle* h, const void* points, int32_t dtype, const int64_t* sweep_offsets,

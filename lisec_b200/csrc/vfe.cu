@@ -472,7 +472,6 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
     if (t + tstride < n_tiles) prefetch_rows(nxt);
     if (MODE != 0 && tid < nv) cp_async4(sVoxCell + tid, out.voxel_cell + v0 + tid);
     cp_async_commit();
-    const PoolMeta meta = make_pool_meta(sRowVox, lane);
     {  // MaxPoolingVFELayer over T (:160); RepeatLayer is implicit. Warp w pools channels 2w, 2w+1.
       float val[8][2];
 #pragma unroll
@@ -483,7 +482,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
         val[0][c] = lo.x; val[1][c] = lo.y; val[2][c] = lo.z; val[3][c] = lo.w;
         val[4][c] = hi.x; val[5][c] = hi.y; val[6][c] = hi.z; val[7][c] = hi.w;
       }
-      pool_lane_rows<2>(val, meta, [&](int v, const float(&x)[2]) {
+      pool_lane_rows<2>(val, make_pool_meta(sRowVox, lane), [&](int v, const float(&x)[2]) {
         if (v < nv) {
           sP1T[(2 * warp) * PV + v] = x[0];
           sP1T[(2 * warp + 1) * PV + v] = x[1];
@@ -509,10 +508,14 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
     group_sync(group);
     {  // rows: 8x4 tile per thread, accumulators start at the voxel's pooled-half product
       float acc[8][4];
+      {
+        const uint2 rv = *reinterpret_cast<const uint2*>(sRowVox + lane * 8);  // local voxel of each of the 8 rows
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const float4 q = *reinterpret_cast<const float4*>(sQ + (meta.v[r] & (kVox - 1)) * QS + warp * 4);
-        acc[r][0] = q.x; acc[r][1] = q.y; acc[r][2] = q.z; acc[r][3] = q.w;
+        for (int r = 0; r < 8; ++r) {
+          const int v = ((r < 4 ? rv.x : rv.y) >> (8 * (r & 3))) & (kVox - 1);  // (padding rows read some valid row)
+          const float4 q = *reinterpret_cast<const float4*>(sQ + v * QS + warp * 4);
+          acc[r][0] = q.x; acc[r][1] = q.y; acc[r][2] = q.z; acc[r][3] = q.w;
+        }
       }
       tile_gemm<8, 1, 16, true>(sH1T, PR, 128, lane * 4, sW2X, 32, coff4, acc);
 #pragma unroll
@@ -525,7 +528,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
         *reinterpret_cast<float4*>(dst + 128) = make_float4(acc[4][c], acc[5][c], acc[6][c], acc[7][c]);
       }
       group_sync(group);  // every warp is done with sH1T (A operand) and sQ: sP2T may now overwrite sH1T/sP1T
-      pool_lane_rows<4>(acc, meta, [&](int v, const float(&x)[4]) {
+      pool_lane_rows<4>(acc, make_pool_meta(sRowVox, lane), [&](int v, const float(&x)[4]) {
         if (v < nv) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) sP2T[(warp * 4 + c) * PV + v] = x[c];
@@ -554,13 +557,16 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
     group_sync(group);
     {  // rows: 8x8 tile per thread; the per-voxel max goes straight from registers to the output row
       float out8[8][8];
+      {
+        const uint2 rv = *reinterpret_cast<const uint2*>(sRowVox + lane * 8);
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const float* q = sQ + (meta.v[r] & (kVox - 1)) * QS;
-        const float4 q0 = *reinterpret_cast<const float4*>(q + coff8[0]);
-        const float4 q1 = *reinterpret_cast<const float4*>(q + coff8[1]);
-        out8[r][0] = q0.x; out8[r][1] = q0.y; out8[r][2] = q0.z; out8[r][3] = q0.w;
-        out8[r][4] = q1.x; out8[r][5] = q1.y; out8[r][6] = q1.z; out8[r][7] = q1.w;
+        for (int r = 0; r < 8; ++r) {
+          const float* q = sQ + (((r < 4 ? rv.x : rv.y) >> (8 * (r & 3))) & (kVox - 1)) * QS;
+          const float4 q0 = *reinterpret_cast<const float4*>(q + coff8[0]);
+          const float4 q1 = *reinterpret_cast<const float4*>(q + coff8[1]);
+          out8[r][0] = q0.x; out8[r][1] = q0.y; out8[r][2] = q0.z; out8[r][3] = q0.w;
+          out8[r][4] = q1.x; out8[r][5] = q1.y; out8[r][6] = q1.z; out8[r][7] = q1.w;
+        }
       }
       tile_gemm<8, 2, 32, false>(sH2T, PR, 128, lane * 4, sW3X, 64, coff8, out8);
 #pragma unroll
@@ -570,7 +576,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
 #pragma unroll
         for (int r = 0; r < 8; ++r) out8[r][c] = fmaxf(fmaf(out8[r][c], a, b), 0.f);
       }
-      pool_lane_rows<8>(out8, meta, [&](int v, const float(&x)[8]) {
+      pool_lane_rows<8>(out8, make_pool_meta(sRowVox, lane), [&](int v, const float(&x)[8]) {
         if (v < nv) {  // two 16-byte (bf16: 8-byte) stores per voxel and warp; the 8 warps complete the row
           if (MODE == 0) {
             float* dst = out.voxel_feat + (size_t)(v0 + v) * 64;

@@ -240,6 +240,14 @@ class Frontend:
             self._check(self._lib.lisec_scatter_dense(self._h, _ptr(voxel_feat), _ptr(out), self._stream()))
         return out
 
+    def vfe_scatter_fused(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """VFE + dense grid in one kernel, on the grouping of the last voxelize()."""
+        if out is None:
+            out = self.new_grid(self._n_sweeps)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.lisec_vfe_scatter_fused(self._h, _ptr(out), self._stream()))
+        return out
+
     def forward(self, points: ArrayLike, sweep_offsets: Optional[Sequence[int]] = None,
                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """points already on the device -> dense grid [n_sweeps,nz,nx,ny,c3]; no host round trip."""

@@ -210,11 +210,13 @@ def test_fused_forward_equals_modular_and_host_entry(fe):
     modular = fe.scatter(fe.vfe())
     fused = fe.forward(torch.from_numpy(pts).cuda(), off)
     assert torch.equal(fused, modular)
+    fe.voxelize(pts, off)
+    assert torch.equal(fe.vfe_scatter_fused(), modular)  # the fused stage alone, on an existing grouping
     pinned = torch.from_numpy(pts).pin_memory()
     host = fe.forward_host(pinned, off)
     torch.cuda.synchronize()
     assert torch.equal(host, modular)
-    assert fe.last_launch_count == 8  # point, 3 scans, fill, order, centroids, fused VFE + grid
+    assert fe.last_launch_count == 8  # point, 3 scans, fill, order, row features, fused VFE + grid
 
 
 def test_grid_against_dense_reference_forward_small_grid():
