@@ -7,6 +7,7 @@
 #include <new>
 
 #include "common.cuh"
+#include "umma.cuh"
 
 using namespace lisec;
 
@@ -278,10 +279,32 @@ int32_t lisec_set_vfe_weights(lisec_handle* h, const lisec_vfe_weights* w, void*
   const float* k0 = w->dense_kernel[0];
   for (int k = 0; k < 6; ++k)
     for (int j = 0; j < 16; ++j) p.w1[k][j] = (double)k0[k * 16 + j];
-  // blob = [W2P | W2X | W3P | W3X]; a Keras kernel is (C_in, C_out) row-major with the pooled half's rows first
+  // blob = [W2P | W2X | W3^T hi image | W3^T lo image]; a Keras kernel is (C_in, C_out) row-major with the pooled
+  // half's rows first. dense_2 runs on the tensor core as 3xTF32: each weight is split into hi = rn_tf32(w) and
+  // lo = rn_tf32(w - hi) and laid out as the A operand W3^T[c_out][c_in] (K-major, 128-byte swizzle, umma.cuh).
   float* blob = h->wblob;
   std::memcpy(blob, w->dense_kernel[1], sizeof(float) * 32 * 32);             // rows 0..15 = W2P, 16..31 = W2X
-  std::memcpy(blob + 32 * 32, w->dense_kernel[2], sizeof(float) * 64 * 64);   // rows 0..31 = W3P, 32..63 = W3X
+  {
+    auto tf32_rn = [](float x) {  // cvt.rna.tf32.f32: round to nearest, ties away, 10 explicit mantissa bits
+      uint32_t u;
+      std::memcpy(&u, &x, 4);
+      if ((u & 0x7f800000u) != 0x7f800000u) u = (u + 0x1000u) & 0xffffe000u;
+      float r;
+      std::memcpy(&r, &u, 4);
+      return r;
+    };
+    unsigned char* hi = reinterpret_cast<unsigned char*>(blob + 32 * 32);
+    unsigned char* lo = hi + 64 * 64 * sizeof(float);
+    const float* k2 = w->dense_kernel[2];
+    for (int k = 0; k < 64; ++k)
+      for (int m = 0; m < 64; ++m) {
+        const float v = k2[k * 64 + m];
+        const float vh = tf32_rn(v), vl = tf32_rn(v - vh);
+        const uint32_t off = umma::kmajor_offset(m, k, 64 * 128);
+        std::memcpy(hi + off, &vh, 4);
+        std::memcpy(lo + off, &vl, 4);
+      }
+  }
   // BatchNormalization at inference (Keras defaults, model_training.py:171): y = x*a + b
   float* A[3] = {p.a1, p.a2, p.a3};
   float* B[3] = {p.b1, p.b2, p.b3};

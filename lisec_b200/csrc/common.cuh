@@ -27,17 +27,18 @@ struct SweepOffsets {
 
 // Folded VFE parameters, primary architecture (model_training.py:231-233): 6->16 | 32->32 | 64->64.
 // VfeSmall travels as a __grid_constant__ kernel parameter (uniform-register operands for the one-row-per-thread
-// first layer and the BN epilogues); the four larger matrices travel as one device blob that every CTA stages into
-// shared memory once: [W2P 16x32 | W2X 16x32 | W3P 32x64 | W3X 32x64] floats, row-major (C_in, C_out).
-//   W2P / W3P = kernel rows that multiply the POOLED half  (Concatenate([pooling, layer]), :164-165)
-//   W2X / W3X = kernel rows that multiply the pointwise half
+// first layer and the BN epilogues); the larger matrices travel as one device blob that every CTA stages into shared
+// memory once: [W2P 16x32 | W2X 16x32] floats, row-major (C_in, C_out), then dense_2 as two tensor-core operand images
+// (tf32 hi part, tf32 lo part) of W3^T[c_out][c_in] in the K-major 128-byte-swizzled layout of umma.cuh, 2 slabs each.
+//   W2P / slab 0 = kernel rows that multiply the POOLED half  (Concatenate([pooling, layer]), :164-165)
+//   W2X / slab 1 = kernel rows that multiply the pointwise half
 struct VfeSmall {
   double w1[6][16];      // dense (6,16), held in float64: this product is accumulated in float64
   float a1[16], b1[16];  // BN folded: y = x*a + b, a = gamma*rsqrt(var+eps), b = beta - mean*a
   float a2[32], b2[32];
   float a3[64], b3[64];
 };
-constexpr int kVfeBlobFloats = 2 * 16 * 32 + 2 * 32 * 64;
+constexpr int kVfeBlobFloats = 2 * 16 * 32 + 2 * 64 * 64;
 
 // totals[] slots (device, long long)
 enum {

@@ -2,31 +2,37 @@
 // concat, and the final max over T — reference model_training.py:134-141 (features) and :155-186, 229-235 (layers).
 //
 // Work unit: a tile = a run of whole voxels holding at most 256 VFE rows (a row is a kept point, or the single
-// virtual zero row that stands for all identical pad rows of a non-full voxel). One 256-thread CTA
-// per tile, persistent over tiles. Inside a tile every Dense is a small GEMM on on-chip data:
+// virtual zero row that stands for all identical pad rows of a non-full voxel). One persistent CTA per
+// SM, warp-specialised into a three-stage pipeline over tiles:
 //
-//     rows    H_next[256 x N] = H[256 x K] * Wx[K x N]  (+ Q[voxel(row)])       8x8 / 8x4 register tile per thread
-//     voxels  Q[128 x N]      = Pool[128 x K] * Wp[K x N]                        4x8 / 4x4 register tile per thread
+//   FRONT  (warps 0-7, FP32 pipe)   VFE-1 (6->16, float64), max-pool, VFE-2 (32->32) as register-tiled SIMT GEMMs with
+//                                   in-register max-pools; leaves the FCN input X = [pooled | pointwise] (256 x 64),
+//                                   split into tf32 hi/lo parts, in shared memory in the tensor core's operand layout
+//   TENSOR (one elected thread)     FCN Dense(64->64): D^T[64 ch x 256 rows] = W3^T * X^T as 24 tcgen05.mma (kind::tf32,
+//                                   M=64, N=256, K=8; 3xTF32: Wh*Xl + Wl*Xh + Wh*Xh), accumulators in TMEM, double
+//                                   buffered, completion signalled to an mbarrier by tcgen05.commit
+//   BACK   (warps 8-11)             tcgen05.ld: a thread owns one output CHANNEL and walks the tile's rows in order, so
+//                                   the final per-voxel max is a sequential in-register scan with warp-uniform voxel
+//                                   boundaries; BN + ReLU are applied once per voxel (they are monotonic, so they
+//                                   commute with the max), and the row goes straight to voxel_feat or to its grid cell
+//   WRITER (warps 12-15, fused modes) streams c_empty into the empty cells with TMA bulk stores
 //
-// with the activations k-major in shared memory (A operand: 16-byte loads of 4 consecutive rows) and the weights in
-// shared memory ([K][N], 16-byte loads of 4 consecutive columns). This is the classic SIMT SGEMM inner loop:
-// 4 LDS.128 feed 64 FFMA, measured at 54 TFLOP/s on B200 against a 58.7 TFLOP/s FP32-pipe peak
-// (tools/ffma_probe.cu, tools/fp32_peak.cu); the earlier thread-per-row form topped out at 39.
-// Because Concatenate([pooled, pointwise]) feeds a bias-free Dense (model_training.py:164-165, 184), the pooled half
-// of the next product is the same for every row of a voxel: it is computed once per voxel (Q) and used as the
-// accumulators' initial value. Thread mapping: lane = 8 consecutive tile rows, warp = column group, so a voxel's rows
-// all sit in one warp and every max-pool is an in-register segmented max plus a 4-step segmented shuffle scan — no
-// shared-memory pooling passes, no atomics (ncu on the previous version: 48 % of the time in smem pooling loops).
+// Why the FCN alone goes to the tensor core: it is 75 % of the path's FLOPs, it follows the last ReLU (no cancellation
+// in its sums), and 3xTF32 reproduces a float32 FMA chain (tools/umma_probe.cu: 1.1e-6 vs 1.0e-6 of rms). dense_1's
+// two halves cancel, so it stays on the FP32 pipe with blocked accumulation, and dense (6->16) acts on raw coordinates
+// up to +-50 m and is accumulated in float64. Parity bar 1e-5 against the float64 oracle.
 //
-// Precision (parity bar 1e-5 against the float64 oracle): dense (6->16) acts on raw coordinates up to +-50 m and is
-// accumulated in float64 (96 DFMA per row); dense_1's two halves cancel, so its 32-term sum is accumulated in
-// float32 blocks of 4 (a fresh accumulator per block, then added) — measured worst case 4.7e-6 over seeds and clouds,
-// the level of a CPU float32 forward; dense_2 is a plain float32 FMA chain.
+// Because Concatenate([pooled, pointwise]) feeds a bias-free Dense (model_training.py:164-165, 184), the pooled half of
+// dense_1's product is the same for every row of a voxel: it is computed once per voxel (Q) and used as the
+// accumulators' initial value. For the FCN the pooled half is simply broadcast into X's first 32 channels.
+// SIMT thread mapping: lane = 8 consecutive tile rows, warp = column group, so a voxel's rows all sit in one warp and
+// the max-pools are an in-register segmented max plus a 4-step segmented shuffle scan.
 #include <cuda_bf16.h>
 
 #include <type_traits>
 
 #include "common.cuh"
+#include "umma.cuh"
 #include "vfe_math.cuh"
 
 namespace lisec {
@@ -40,84 +46,73 @@ __device__ __forceinline__ unsigned pack_bf16x2(float a, float b) {
   return *reinterpret_cast<unsigned*>(&h);
 }
 
-constexpr int kGroups = 2;  // tile groups per CTA
-constexpr int kWriterThreads = 128;  // one warpgroup of background writers (register-trimmed with setmaxnreg)
-#ifndef LISEC_WRITER_WARPS
-#define LISEC_WRITER_WARPS 4
-#endif
-constexpr int kWriterWarps = LISEC_WRITER_WARPS;  // how many of its 4 warps actually write
-constexpr int kCtaThreads = kGroups * kVfeThreads + kWriterThreads;
-constexpr int kRows = kVfeThreads;   // 256 rows per tile
+constexpr int kFrontThreads = kVfeThreads;  // 8 warps, one tile at a time
+constexpr int kBackThreads = 128;           // 4 warps = the 4 TMEM lane quadrants
+constexpr int kWriterThreads = 128;         // background writers (fused modes)
+constexpr int kCtaThreads = kFrontThreads + kBackThreads + kWriterThreads;
+constexpr int kBackWarp0 = kFrontThreads / 32;
+constexpr int kRows = kVfeThreads;     // 256 rows per tile
 constexpr int kVox = kVfeThreads / 2;  // 128 voxels per tile: a non-full voxel has >= 2 rows, a full one T >= 2
-constexpr int PR = kRows + 4;        // float pitch of row-indexed k-major tiles (16-byte aligned rows, 4-bank skew)
-constexpr int PV = kVox + 4;         // float pitch of voxel-indexed k-major tiles
-constexpr int QS = 68;               // float stride of a voxel's row in sQ
+constexpr int PR = kRows + 4;          // float pitch of row-indexed k-major tiles (16-byte aligned rows, 4-bank skew)
+constexpr int PV = kVox + 4;           // float pitch of voxel-indexed k-major tiles
+constexpr int QS = 36;                 // float stride of a voxel's 32-channel row in sQ / sP2
+constexpr int kBgCells = 32;           // cells in the writers' TMA source tile
 
-// shared-memory map (bytes)
-constexpr int OFF_W2P = 0;                         // [16][32]
-constexpr int OFF_W2X = OFF_W2P + 16 * 32 * 4;     // [16][32]
-constexpr int OFF_W3P = OFF_W2X + 16 * 32 * 4;     // [32][64]
-constexpr int OFF_W3X = OFF_W3P + 32 * 64 * 4;     // [32][64]
-constexpr int OFF_H1T = OFF_W3X + 32 * 64 * 4;     // [16][PR]   dense outputs of VFE-1, k-major
-constexpr int OFF_P1T = OFF_H1T + 16 * PR * 4;     // [16][PV]   pooled VFE-1
-constexpr int OFF_P2T = OFF_H1T;                   // [32][PV]   pooled VFE-2, reuses H1T+P1T (dead by then)
-constexpr int OFF_H2T = OFF_P1T + 16 * PV * 4;     // [32][PR]   VFE-2 outputs; later one 32-channel half of FCN outputs
-constexpr int OFF_Q = OFF_H2T + 32 * PR * 4;       // [kVox][QS] pooled-half products of the current layer
-constexpr int OFF_ROWVOX = OFF_Q + kVox * QS * 4;  // uint8[kRows] local voxel of each tile row
-constexpr int OFF_VOXCELL = OFF_ROWVOX + kRows;      // int[kVox] cell of each tile voxel (grid output modes)
-constexpr int OFF_FSTAGE = OFF_VOXCELL + kVox * 4;   // float[kRows][6] the NEXT tile's feature rows (cp.async prefetch)
+// tensor-core operands (K-major, 128-byte swizzle; see umma.cuh)
+constexpr uint32_t kXSlab = kRows * 128;  // one 32-channel half of X: 256 rows x 128 B
+constexpr uint32_t kWSlab = 64 * 128;     // one 32-channel half of W3^T: 64 rows x 128 B
+constexpr int kTmemCols = 512;            // two accumulator buffers of 256 columns (one column per tile row)
+
+// per accumulator buffer: what the back stage needs to know about the tile
+struct TileInfo {
+  unsigned last_mask[8];  // bit r: tile row r is the last row of its voxel
+  int nrows, nv, v0, pad;
+  int voxcell[kVox];      // cell of each tile voxel (grid output modes)
+};
+
+// shared-memory map (bytes; the base is 1 KB-aligned)
+constexpr int OFF_XH = 0;                           // X hi: 2 slabs
+constexpr int OFF_XL = OFF_XH + 2 * kXSlab;         // X lo
+constexpr int OFF_W3H = OFF_XL + 2 * kXSlab;        // W3^T hi: 2 slabs (pooled half, pointwise half)
+constexpr int OFF_W3L = OFF_W3H + 2 * kWSlab;       // W3^T lo
+constexpr int OFF_W2P = OFF_W3L + 2 * kWSlab;       // [16][32]
+constexpr int OFF_W2X = OFF_W2P + 16 * 32 * 4;      // [16][32]
+constexpr int OFF_H1T = OFF_W2X + 16 * 32 * 4;      // [16][PR]   dense outputs of VFE-1, k-major
+constexpr int OFF_P1T = OFF_H1T + 16 * PR * 4;      // [16][PV]   pooled VFE-1
+constexpr int OFF_P2 = OFF_H1T;                     // [kVox][QS] pooled VFE-2, reuses H1T+P1T (dead by then)
+constexpr int OFF_Q = OFF_P1T + 16 * PV * 4;        // [kVox][QS] pooled-half products of dense_1
+constexpr int OFF_ROWVOX = OFF_Q + kVox * QS * 4;   // uint8[kRows] local voxel of each tile row
+constexpr int OFF_VOXCELL = OFF_ROWVOX + kRows;     // int[kVox] cell of each tile voxel, front stage's own copy
+constexpr int OFF_FSTAGE = OFF_VOXCELL + kVox * 4;  // float[kRows][6] the NEXT tile's feature rows (cp.async prefetch)
 constexpr int OFF_VSTAGE = OFF_FSTAGE + kRows * 6 * 4;  // int[kRows] the NEXT tile's row -> voxel
-constexpr int kGroupBytes = OFF_VSTAGE + kRows * 4 - OFF_H1T;  // per tile group; the weights (first 20 KB) are shared
-constexpr int OFF_BG = OFF_H1T + kGroups * kGroupBytes;  // 32 cells x 64 channels of c_empty: the TMA source tile
-constexpr int kSmemBytes = OFF_BG + 32 * 64 * 4;
-static_assert(32 * PV * 4 <= 16 * PR * 4 + 16 * PV * 4, "P2T must fit in H1T+P1T");
+constexpr int OFF_INFO = OFF_VSTAGE + kRows * 4;    // TileInfo[2]
+constexpr int OFF_BAR = OFF_INFO + 2 * (int)sizeof(TileInfo);  // mbarriers: full[2], empty[2]; then the TMEM base slot
+constexpr int OFF_BG = (OFF_BAR + 64 + 127) & ~127;            // kBgCells x 64 channels of c_empty: the TMA source tile
+constexpr int kSmemBytes = OFF_BG + kBgCells * 64 * 4 + 1024;  // + slack to align the base to 1 KB
+static_assert(kVox * QS * 4 <= 16 * PR * 4 + 16 * PV * 4, "P2 must fit in H1T+P1T");
 static_assert(kSmemBytes <= 232448, "one CTA per SM, 227 KB opt-in limit");
-static_assert(kGroupBytes % 16 == 0, "group regions stay 16-byte aligned");
+static_assert(OFF_W3H % 1024 == 0 && OFF_XL % 1024 == 0, "operand slabs are 1 KB-aligned");
+static_assert(sizeof(TileInfo) % 16 == 0 && OFF_INFO % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
 
 // ---- register-tile GEMM: acc[R][C] += A[k][row(r)] * W[k][col(c)], k = 0..K-1 -------------------------------
 // The lane's rows come as R/4 float4 chunks at row0 + i*chunk_stride (consecutive lanes -> consecutive 16 bytes);
 // the warp's columns come in groups of 4 at offsets coff[g] (same address for every lane: a broadcast load).
-// BLOCK4: float32 accumulation in blocks of 4 k-steps (see the precision note above).
-template <int R, int CG, int K, bool BLOCK4>
-__device__ __forceinline__ void tile_gemm(const float* __restrict__ sA, int pitch, int chunk_stride, int row0,
-                                          const float* __restrict__ sW, int ldw, const int (&coff)[CG],
-                                          float (&acc)[R][CG * 4]) {
+// float32 accumulation in blocks of 4 k-steps (a fresh accumulator per block, then added): dense_1's two halves cancel.
+template <int R, int CG, int K>
+__device__ __forceinline__ void tile_gemm_blocked(const float* __restrict__ sA, int pitch, int chunk_stride, int row0,
+                                                  const float* __restrict__ sW, int ldw, const int (&coff)[CG],
+                                                  float (&acc)[R][CG * 4]) {
   static_assert(R % 4 == 0 && K % 4 == 0, "tile shape");
-  if (BLOCK4) {
 #pragma unroll 1
-    for (int kb = 0; kb < K; kb += 4) {
-      float blk[R][CG * 4];
+  for (int kb = 0; kb < K; kb += 4) {
+    float blk[R][CG * 4];
 #pragma unroll
-      for (int r = 0; r < R; ++r)
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int c = 0; c < CG * 4; ++c) blk[r][c] = 0.f;
+      for (int c = 0; c < CG * 4; ++c) blk[r][c] = 0.f;
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const int k = kb + kk;
-        float a[R], b[CG * 4];
-#pragma unroll
-        for (int i = 0; i < R / 4; ++i) {
-          const float4 v = *reinterpret_cast<const float4*>(sA + k * pitch + row0 + chunk_stride * i);
-          a[4 * i] = v.x; a[4 * i + 1] = v.y; a[4 * i + 2] = v.z; a[4 * i + 3] = v.w;
-        }
-#pragma unroll
-        for (int g = 0; g < CG; ++g) {
-          const float4 v = *reinterpret_cast<const float4*>(sW + k * ldw + coff[g]);
-          b[4 * g] = v.x; b[4 * g + 1] = v.y; b[4 * g + 2] = v.z; b[4 * g + 3] = v.w;
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-          for (int c = 0; c < CG * 4; ++c) blk[r][c] = fmaf(a[r], b[c], blk[r][c]);
-      }
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int c = 0; c < CG * 4; ++c) acc[r][c] += blk[r][c];
-    }
-  } else {
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
+    for (int kk = 0; kk < 4; ++kk) {
+      const int k = kb + kk;
       float a[R], b[CG * 4];
 #pragma unroll
       for (int i = 0; i < R / 4; ++i) {
@@ -132,25 +127,31 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ sA, int pitc
 #pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int c = 0; c < CG * 4; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
+        for (int c = 0; c < CG * 4; ++c) blk[r][c] = fmaf(a[r], b[c], blk[r][c]);
     }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < CG * 4; ++c) acc[r][c] += blk[r][c];
   }
 }
 
-// One CTA per SM = two tile groups of 8 warps (each works on its own tile with its own named barrier) plus one
-// warpgroup of background writers. 20 warps put 5 on every SM sub-partition, i.e. 96 registers each at launch; the
-// writers then give theirs back (setmaxnreg.dec 32) and the four compute warpgroups grow to 112 (setmaxnreg.inc;
-// the pool is per CTA, so the compute side can only take what the writers released: 4 x (112-96) = 96-32).
-__device__ __forceinline__ void group_sync(int group) {
-  asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kVfeThreads) : "memory");
-}
-__device__ __forceinline__ void all_compute_sync() {
-  asm volatile("bar.sync 3, %0;" ::"n"(kGroups * kVfeThreads) : "memory");
+__device__ __forceinline__ void front_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kFrontThreads) : "memory");
 }
 
 // position of tile row r inside a k-major row tile: lane l = r/8 owns rows 8l..8l+7 and loads them as two float4 at
 // 4l and 128+4l, so both 16-byte loads of a warp cover 512 contiguous bytes (no bank conflicts)
 __device__ __forceinline__ int row_pos(int r) { return ((r >> 3) << 2) + (r & 3) + ((r & 4) << 5); }
+
+// Row r of the tile is row n(r) of the tensor-core operand X (and column n(r) of the accumulator): the 8 rows of lane
+// l are rotated by l inside their group of 8, so that for a fixed register index the lanes of a quarter-warp hit eight
+// different 16-byte chunks of the swizzled 128-byte lines (conflict-free STS.128). The back stage undoes the rotation
+// with compile-time register indices.
+__device__ __forceinline__ int x_row(int l, int i) { return 8 * l + ((i + l) & 7); }
+__device__ __forceinline__ uint32_t x_offset(int slab, int n, int chunk) {
+  return (uint32_t)slab * kXSlab + (uint32_t)n * 128u + (uint32_t)((chunk ^ (n & 7)) << 4);
+}
 
 // ---- per-voxel max in registers ----------------------------------------------------------------------------
 // A lane holds 8 consecutive tile rows, a warp all 256 of them, so every voxel (a run of consecutive rows) lives in
@@ -240,7 +241,7 @@ __device__ __forceinline__ void pool_lane_rows(const float (&val)[8][NC], const 
 }
 
 // MODE 0: voxel rows to voxel_feat[V][64] (float32), no background.  MODE 1 / 2: rows straight into the float32 /
-// bf16 dense grid at their cell, background by the writer warpgroup.
+// bf16 dense grid at their cell, background by the writer warps.
 struct VfeOutput {
   float* voxel_feat;
   void* grid;
@@ -250,12 +251,11 @@ struct VfeOutput {
   long long ncells;
 };
 
-// ---- background writer (fused kernel, the CTA's last warpgroup) ----------------------------------------------
-// c_empty goes into every EMPTY cell of the grid while the compute warps keep the FP32 pipe busy; occupied cells are
-// written by the tiles' own voxel rows, so every grid element is still written exactly once.
-// The data never touches the LSU: a 32-cell tile of replicated c_empty sits in shared memory and every run of
-// consecutive empty cells is ONE TMA bulk store (cp.async.bulk shared -> global, SASS UBLKCP) issued by the lane of
-// the run's first cell.
+// ---- background writer (fused modes, warps 12-15) ------------------------------------------------------------
+// c_empty goes into every EMPTY cell of the grid while the other warps compute; occupied cells are written by the
+// back stage, so every grid element is still written exactly once. The data never touches the LSU: a 32-cell tile of
+// replicated c_empty sits in shared memory and every run of consecutive empty cells is ONE TMA bulk store
+// (cp.async.bulk shared -> global, SASS UBLKCP) issued by the lane of the run's first cell.
 __device__ __forceinline__ void bulk_store(void* gdst, unsigned ssrc, unsigned bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes)
                : "memory");
@@ -267,18 +267,18 @@ template <typename GT>
 __device__ __forceinline__ void background_writer(const int* __restrict__ cell_voxel, const float* __restrict__ c_empty,
                                                   GT* __restrict__ grid, long long ncells, unsigned char* sBg,
                                                   int wtid) {
+  constexpr int kWarps = kWriterThreads / 32;
   const int lane = wtid & 31, wwarp = wtid >> 5;
   // fill the tile: 32 cells x 64 channels of GT, every cell = c_empty (rounded once for bf16)
-  for (int i = wtid; i < 32 * 64; i += kWriterThreads) {
+  for (int i = wtid; i < kBgCells * 64; i += kWriterThreads) {
     if (sizeof(GT) == 4) reinterpret_cast<float*>(sBg)[i] = c_empty[i & 63];
     else reinterpret_cast<__nv_bfloat16*>(sBg)[i] = __float2bfloat16_rn(c_empty[i & 63]);
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA
-  asm volatile("bar.sync 4, %0;" ::"n"(kWriterThreads) : "memory");
-  if (wwarp >= kWriterWarps) return;
+  umma::fence_async_smem();  // generic-proxy writes -> visible to the TMA
+  asm volatile("bar.sync 2, %0;" ::"n"(kWriterThreads) : "memory");
   const unsigned src = (unsigned)__cvta_generic_to_shared(sBg);
   const int ngroups = (int)((ncells + 31) >> 5);
-  const int stride = gridDim.x * kWriterWarps;
+  const int stride = gridDim.x * kWarps;
   constexpr int U = 4;  // 32-cell groups per step; the next step's occupancy words are already in flight
   auto load_occ = [&](int g0, int (&occ)[U]) {
 #pragma unroll
@@ -289,7 +289,7 @@ __device__ __forceinline__ void background_writer(const int* __restrict__ cell_v
     }
   };
   int occ[U], nxt[U];
-  int g0 = blockIdx.x * kWriterWarps + wwarp;
+  int g0 = blockIdx.x * kWarps + wwarp;
   load_occ(g0, occ);
   for (; g0 < ngroups; g0 += U * stride) {
     load_occ(g0 + U * stride, nxt);
@@ -366,14 +366,126 @@ __device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// ---- TENSOR stage: the FCN's Dense(64->64) for one tile, issued by one thread --------------------------------
+// D^T[ch][n] (+)= sum_k W3^T[ch][k] * X[n][k], k over [pooled 32 | pointwise 32]. 3xTF32, small terms first so that
+// their sum is not rounded against the large one: Wh*Xl, Wl*Xh, then Wh*Xh.
+__device__ __forceinline__ void issue_fcn_mma(uint32_t smem_base, uint32_t d_tmem) {
+  constexpr uint32_t idesc = umma::make_idesc_tf32_k(64, kRows);
+  const uint32_t w[3] = {smem_base + OFF_W3H, smem_base + OFF_W3L, smem_base + OFF_W3H};
+  const uint32_t x[3] = {smem_base + OFF_XL, smem_base + OFF_XH, smem_base + OFF_XH};
+  uint32_t acc = 0;
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {  // k-step kb: slab kb/4, 32 bytes per step inside the swizzled 128-byte rows
+      const uint64_t a = umma::make_desc_k_sw128(w[s] + (kb >> 2) * kWSlab + (kb & 3) * 32);
+      const uint64_t b = umma::make_desc_k_sw128(x[s] + (kb >> 2) * kXSlab + (kb & 3) * 32);
+      umma::mma_tf32_ss(d_tmem, a, b, idesc, acc);
+      acc = 1;
+    }
+}
+
+// ---- BACK stage: accumulators -> per-voxel max -> BN + ReLU -> output row ------------------------------------
+// Warp q of the stage reads TMEM lanes 32q..32q+31; an M=64 accumulator keeps channel c in lane (c % 16) + 32 (c / 16),
+// so lanes 0..15 of the warp own channels 16q..16q+15 and lanes 16..31 idle (they take part in the loads only).
+// Columns are tile rows (rotated inside groups of 8, see x_row). y = relu(a*z + b) is monotonic in z, so
+// max_rows relu(a*z_r + b) = relu(a*z* + b) with z* = max z_r (a >= 0) or min z_r (a < 0): both are tracked.
+template <int MODE>
+__device__ __forceinline__ void back_stage(const VfeSmall& P, const VfeOutput& out, unsigned char* smem, int n_tiles,
+                                           uint32_t tmem_base, int bwarp, int lane) {
+  const uint32_t bar_full = umma::smem_u32(smem + OFF_BAR), bar_empty = bar_full + 16;
+  const int ch = 16 * bwarp + (lane & 15);
+  const bool active = lane < 16;
+  const float a = P.a3[ch], b = P.b3[ch];
+  const uint32_t tlane = tmem_base + ((uint32_t)(32 * bwarp) << 16);
+  int it = 0;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+    const int buf = it & 1;
+    umma::mbar_wait(bar_full + 8 * buf, (it >> 1) & 1);
+    umma::fence_after_sync();
+    const TileInfo* info = reinterpret_cast<const TileInfo*>(smem + OFF_INFO) + buf;
+    const int nrows = info->nrows, v0 = info->v0;
+    float mx = -INFINITY, mn = INFINITY;
+    int v = 0;
+    auto emit = [&]() {
+      const float z = a >= 0.f ? mx : mn;
+      const float y = fmaxf(fmaf(z, a, b), 0.f);
+      if (active) {
+        if (MODE == 0) out.voxel_feat[(size_t)(v0 + v) * 64 + ch] = y;
+        else if (MODE == 1) __stcs(static_cast<float*>(out.grid) + (size_t)info->voxcell[v] * 64 + ch, y);
+        else static_cast<__nv_bfloat16*>(out.grid)[(size_t)info->voxcell[v] * 64 + ch] = __float2bfloat16_rn(y);
+      }
+      ++v;
+      mx = -INFINITY;
+      mn = INFINITY;
+    };
+#pragma unroll 1
+    for (int c0 = 0; c0 < nrows; c0 += 64) {  // two 32-column loads per step: the rotation pattern repeats every 64
+      const uint2 mask = *reinterpret_cast<const uint2*>(&info->last_mask[c0 >> 5]);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float x[32];
+        umma::tmem_ld_32x32(tlane + buf * kRows + c0 + 32 * half, x);
+        const unsigned m = half ? mask.y : mask.x;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {  // tile row c0 + 32 half + 8 g + i sits in column 8 g + ((i + G) & 7), G = 4 half + g
+            const float val = x[8 * g + ((i + 4 * half + g) & 7)];
+            mx = fmaxf(mx, val);
+            mn = fminf(mn, val);
+            if (m & (1u << (8 * g + i))) emit();
+          }
+      }
+    }
+    umma::fence_before_sync();
+    __syncwarp();
+    if (lane == 0) umma::mbar_arrive(bar_empty + 8 * buf);
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kCtaThreads, 1)
     vfe_kernel(const __grid_constant__ VfeSmall P, const float* __restrict__ wblob,
                const __grid_constant__ VfeProblem prob, const __grid_constant__ VfeOutput out) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  if (threadIdx.x >= kGroups * kVfeThreads) {  // the writer warpgroup
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-    const int wtid = threadIdx.x - kGroups * kVfeThreads;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem =
+      reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp_in_cta = threadIdx.x >> 5;
+  const uint32_t smem_base = umma::smem_u32(smem);
+  const uint32_t bar_full = smem_base + OFF_BAR, bar_empty = bar_full + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 32);
+  const int n_tiles = (int)*prob.n_tiles;
+
+  // ---- one-time setup: weights, barriers, TMEM ----
+  if (threadIdx.x < kFrontThreads + kBackThreads) {
+    // blob = [W2P | W2X] float32 row-major, then the W3^T hi and lo operand images (built by the host, api.cu)
+    const float4* src = reinterpret_cast<const float4*>(wblob);
+    float4* w2 = reinterpret_cast<float4*>(smem + OFF_W2P);
+    float4* w3 = reinterpret_cast<float4*>(smem + OFF_W3H);
+    constexpr int n2 = 2 * 16 * 32 / 4, n3 = 4 * (int)kWSlab / 16;
+    for (int i = threadIdx.x; i < n2 + n3; i += kFrontThreads + kBackThreads) {
+      const float4 v = __ldg(src + i);
+      if (i < n2) w2[i] = v;
+      else w3[i - n2] = v;
+    }
+    umma::fence_async_smem();  // W3 is read by the tensor core
+  }
+  if (threadIdx.x == 0) {
+    for (int bfr = 0; bfr < 2; ++bfr) {
+      umma::mbar_init(bar_full + 8 * bfr, 2);   // tcgen05.commit + the issuing thread's own (release) arrive
+      umma::mbar_init(bar_empty + 8 * bfr, kBackThreads / 32);
+    }
+    umma::mbar_init_fence();
+  }
+  if (warp_in_cta == kBackWarp0) umma::tmem_alloc<kTmemCols>(tmem_slot);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x >= kFrontThreads + kBackThreads) {  // ---- WRITER ----
+    const int wtid = threadIdx.x - kFrontThreads - kBackThreads;
     if (MODE == 1)
       background_writer(out.cell_voxel, out.c_empty, static_cast<float*>(out.grid), out.ncells, smem + OFF_BG, wtid);
     if (MODE == 2)
@@ -381,30 +493,25 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
                         wtid);
     return;
   }
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");  // 4 x (112 - 96) = 96 - 32: exactly what the writers released
-  const int group = threadIdx.x / kVfeThreads;
-  const int tid = threadIdx.x % kVfeThreads, lane = tid & 31, warp = tid >> 5;
-  // register tiles: lane = row group (8 tile rows / 4 voxel rows), warp = column group
-  unsigned char* gsm = smem + group * kGroupBytes;  // this group's activations; offsets below are group-relative
+  if (threadIdx.x >= kFrontThreads) {  // ---- BACK ----
+    back_stage<MODE>(P, out, smem, n_tiles, tmem_base, warp_in_cta - kBackWarp0, threadIdx.x & 31);
+    asm volatile("bar.sync 3, %0;" ::"n"(kFrontThreads + kBackThreads) : "memory");
+    if (warp_in_cta == kBackWarp0) umma::tmem_dealloc<kTmemCols>(tmem_base);
+    return;
+  }
+
+  // ---- FRONT ----
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* sW2P = reinterpret_cast<float*>(smem + OFF_W2P);
   float* sW2X = reinterpret_cast<float*>(smem + OFF_W2X);
-  float* sW3P = reinterpret_cast<float*>(smem + OFF_W3P);
-  float* sW3X = reinterpret_cast<float*>(smem + OFF_W3X);
-  float* sH1T = reinterpret_cast<float*>(gsm + OFF_H1T);
-  float* sP1T = reinterpret_cast<float*>(gsm + OFF_P1T);
-  float* sP2T = reinterpret_cast<float*>(gsm + OFF_P2T);
-  float* sH2T = reinterpret_cast<float*>(gsm + OFF_H2T);
-  float* sQ = reinterpret_cast<float*>(gsm + OFF_Q);
-  unsigned char* sRowVox = gsm + OFF_ROWVOX;
-  int* sVoxCell = reinterpret_cast<int*>(gsm + OFF_VOXCELL);
-  float* sFeatStage = reinterpret_cast<float*>(gsm + OFF_FSTAGE);
-  int* sVoxStage = reinterpret_cast<int*>(gsm + OFF_VSTAGE);
-
-  const int n_tiles = (int)*prob.n_tiles;
-  // weights: [W2P | W2X | W3P | W3X] as laid out by the host, straight into the first 20 KB (all compute threads)
-  for (int i = threadIdx.x; i < (OFF_H1T / 16); i += kGroups * kVfeThreads)  // (writer threads left above)
-    reinterpret_cast<float4*>(smem)[i] = __ldg(reinterpret_cast<const float4*>(wblob) + i);
-  all_compute_sync();
+  float* sH1T = reinterpret_cast<float*>(smem + OFF_H1T);
+  float* sP1T = reinterpret_cast<float*>(smem + OFF_P1T);
+  float* sP2 = reinterpret_cast<float*>(smem + OFF_P2);
+  float* sQ = reinterpret_cast<float*>(smem + OFF_Q);
+  unsigned char* sRowVox = smem + OFF_ROWVOX;
+  int* sVoxCell = reinterpret_cast<int*>(smem + OFF_VOXCELL);
+  float* sFeatStage = reinterpret_cast<float*>(smem + OFF_FSTAGE);
+  int* sVoxStage = reinterpret_cast<int*>(smem + OFF_VSTAGE);
 
   // tile header = (first voxel, first row) of the tile and of its successor; rows and voxels are contiguous
   struct Header { int v0, v1, r0, r1; };
@@ -423,19 +530,21 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
     const int nrows = h.r1 - h.r0;
     const float* src = prob.row_feat + (size_t)h.r0 * 6;
 #pragma unroll
-    for (int c = tid; c < kRows * 3; c += kVfeThreads)
+    for (int c = tid; c < kRows * 3; c += kFrontThreads)
       if (c < nrows * 3) cp_async8(sFeatStage + 2 * c, src + 2 * c);
     if (tid < nrows) cp_async4(sVoxStage + tid, prob.row_voxel + h.r0 + tid);
   };
-  const int tstride = gridDim.x * kGroups;
-  int t = blockIdx.x * kGroups + group;
+  const int tstride = gridDim.x;
+  int t = blockIdx.x;
   Header cur = load_header(t);
   if (t < n_tiles) prefetch_rows(cur);
   cp_async_commit();
   cp_async_wait_all();
-  group_sync(group);
+  front_sync();
 
-  for (; t < n_tiles; t += tstride) {
+  int it = 0;
+  for (; t < n_tiles; t += tstride, ++it) {
+    const int buf = it & 1;
     const int v0 = cur.v0, nv = cur.v1 - cur.v0, nrows = cur.r1 - cur.r0;
     const bool has_row = tid < nrows;
     const Header nxt = load_header(t + tstride);  // consumed after the first barrier: its latency hides behind VFE-1
@@ -466,12 +575,13 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
         sH1T[j * PR + pos] = has_row ? fmaxf(fmaf(__double2float_rn(d[j]), P.a1[j], P.b1[j]), 0.f) : 0.f;
       sRowVox[tid] = (unsigned char)lv;
     }
-    group_sync(group);
+    front_sync();
     // the staging buffers are free again: start the next tile's rows (and this tile's voxel -> cell words, needed only
-    // by the final store) on their way; they land while the GEMMs run
+    // by the back stage) on their way; they land while the GEMMs run
     if (t + tstride < n_tiles) prefetch_rows(nxt);
     if (MODE != 0 && tid < nv) cp_async4(sVoxCell + tid, out.voxel_cell + v0 + tid);
     cp_async_commit();
+    const PoolMeta meta = make_pool_meta(sRowVox, lane);
     {  // MaxPoolingVFELayer over T (:160); RepeatLayer is implicit. Warp w pools channels 2w, 2w+1.
       float val[8][2];
 #pragma unroll
@@ -482,14 +592,14 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
         val[0][c] = lo.x; val[1][c] = lo.y; val[2][c] = lo.z; val[3][c] = lo.w;
         val[4][c] = hi.x; val[5][c] = hi.y; val[6][c] = hi.z; val[7][c] = hi.w;
       }
-      pool_lane_rows<2>(val, make_pool_meta(sRowVox, lane), [&](int v, const float(&x)[2]) {
+      pool_lane_rows<2>(val, meta, [&](int v, const float(&x)[2]) {
         if (v < nv) {
           sP1T[(2 * warp) * PV + v] = x[0];
           sP1T[(2 * warp + 1) * PV + v] = x[1];
         }
       });
     }
-    group_sync(group);
+    front_sync();
 
     // ---- VFE-2: Dense(32->32) + BN + ReLU on concat[pooled, pointwise] (addVFELayer(., 32, 64), :232) ----
     const int coff4[1] = {warp * 4};
@@ -499,104 +609,88 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-      tile_gemm<4, 1, 16, true>(sP1T, PV, 0, lane * 4, sW2P, 32, coff4, acc);
+      tile_gemm_blocked<4, 1, 16>(sP1T, PV, 0, lane * 4, sW2P, 32, coff4, acc);
 #pragma unroll
       for (int r = 0; r < 4; ++r)
         *reinterpret_cast<float4*>(sQ + (lane * 4 + r) * QS + warp * 4) =
             make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
     }
-    group_sync(group);
+    front_sync();
+    float h2[8][4];  // rows 8 lane .. 8 lane + 7, channels 4 warp .. 4 warp + 3 of the VFE-2 pointwise output
     {  // rows: 8x4 tile per thread, accumulators start at the voxel's pooled-half product
-      float acc[8][4];
-      {
-        const uint2 rv = *reinterpret_cast<const uint2*>(sRowVox + lane * 8);  // local voxel of each of the 8 rows
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const int v = ((r < 4 ? rv.x : rv.y) >> (8 * (r & 3))) & (kVox - 1);  // (padding rows read some valid row)
-          const float4 q = *reinterpret_cast<const float4*>(sQ + v * QS + warp * 4);
-          acc[r][0] = q.x; acc[r][1] = q.y; acc[r][2] = q.z; acc[r][3] = q.w;
-        }
+      for (int r = 0; r < 8; ++r) {
+        const int v = meta.v[r] & (kVox - 1);  // (padding rows read some valid row)
+        const float4 q = *reinterpret_cast<const float4*>(sQ + v * QS + warp * 4);
+        h2[r][0] = q.x; h2[r][1] = q.y; h2[r][2] = q.z; h2[r][3] = q.w;
       }
-      tile_gemm<8, 1, 16, true>(sH1T, PR, 128, lane * 4, sW2X, 32, coff4, acc);
+      tile_gemm_blocked<8, 1, 16>(sH1T, PR, 128, lane * 4, sW2X, 32, coff4, h2);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const float a = P.a2[warp * 4 + c], b = P.b2[warp * 4 + c];
+        const float sa = P.a2[warp * 4 + c], sb = P.b2[warp * 4 + c];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) acc[r][c] = fmaxf(fmaf(acc[r][c], a, b), 0.f);
-        float* dst = sH2T + (warp * 4 + c) * PR + 4 * lane;
-        *reinterpret_cast<float4*>(dst) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
-        *reinterpret_cast<float4*>(dst + 128) = make_float4(acc[4][c], acc[5][c], acc[6][c], acc[7][c]);
-      }
-      group_sync(group);  // every warp is done with sH1T (A operand) and sQ: sP2T may now overwrite sH1T/sP1T
-      pool_lane_rows<4>(acc, make_pool_meta(sRowVox, lane), [&](int v, const float(&x)[4]) {
-        if (v < nv) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) sP2T[(warp * 4 + c) * PV + v] = x[c];
-        }
-      });
-    }
-    group_sync(group);
-
-    // ---- FCN: Dense(64->64) + BN + ReLU (addFCN(., 64, 64), :233), then MaxPoolingVFELayer(combine=True) (:235) ----
-    const int coff8[2] = {warp * 4, 32 + warp * 4};  // this warp's 8 output channels
-    {  // pooled half: Q3[128 x 64] = P2[128 x 32] * W3p; 4x8 tile per thread
-      float acc[4][8];
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
-      tile_gemm<4, 2, 32, false>(sP2T, PV, 0, lane * 4, sW3P, 64, coff8, acc);
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        float* dst = sQ + (lane * 4 + r) * QS;
-        *reinterpret_cast<float4*>(dst + coff8[0]) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-        *reinterpret_cast<float4*>(dst + coff8[1]) = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+        for (int r = 0; r < 8; ++r) h2[r][c] = fmaxf(fmaf(h2[r][c], sa, sb), 0.f);
       }
     }
+    // X is single-buffered: the previous tile's MMAs must have finished reading it
+    if (it > 0) umma::mbar_wait(bar_full + 8 * (buf ^ 1), ((it - 1) >> 1) & 1);
+    // pointwise half of the FCN input: X[n][32 + 4 warp ..] = h2, split into tf32 hi / lo
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      float4 hi, lo;
+      umma::tf32_split(h2[r][0], hi.x, lo.x);
+      umma::tf32_split(h2[r][1], hi.y, lo.y);
+      umma::tf32_split(h2[r][2], hi.z, lo.z);
+      umma::tf32_split(h2[r][3], hi.w, lo.w);
+      const uint32_t off = x_offset(1, x_row(lane, r), warp);
+      *reinterpret_cast<float4*>(smem + OFF_XH + off) = hi;
+      *reinterpret_cast<float4*>(smem + OFF_XL + off) = lo;
+    }
+    front_sync();  // every warp is done with sH1T (A operand) and sQ: sP2 may now overwrite sH1T/sP1T
+    pool_lane_rows<4>(h2, meta, [&](int v, const float(&x)[4]) {
+      if (v < nv) *reinterpret_cast<float4*>(sP2 + v * QS + warp * 4) = make_float4(x[0], x[1], x[2], x[3]);
+    });
     cp_async_wait_all();  // issued a whole tile ago; the barrier below publishes the staged rows and sVoxCell
-    group_sync(group);
-    {  // rows: 8x8 tile per thread; the per-voxel max goes straight from registers to the output row
-      float out8[8][8];
-      {
-        const uint2 rv = *reinterpret_cast<const uint2*>(sRowVox + lane * 8);
+    front_sync();
+
+    // ---- FCN input, pooled half: Concatenate([pooled, pointwise]) (:164-165) = the voxel's pooled row, repeated ----
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const float* q = sQ + (((r < 4 ? rv.x : rv.y) >> (8 * (r & 3))) & (kVox - 1)) * QS;
-          const float4 q0 = *reinterpret_cast<const float4*>(q + coff8[0]);
-          const float4 q1 = *reinterpret_cast<const float4*>(q + coff8[1]);
-          out8[r][0] = q0.x; out8[r][1] = q0.y; out8[r][2] = q0.z; out8[r][3] = q0.w;
-          out8[r][4] = q1.x; out8[r][5] = q1.y; out8[r][6] = q1.z; out8[r][7] = q1.w;
-        }
-      }
-      tile_gemm<8, 2, 32, false>(sH2T, PR, 128, lane * 4, sW3X, 64, coff8, out8);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int col = coff8[c >> 2] + (c & 3);
-        const float a = P.a3[col], b = P.b3[col];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) out8[r][c] = fmaxf(fmaf(out8[r][c], a, b), 0.f);
-      }
-      pool_lane_rows<8>(out8, make_pool_meta(sRowVox, lane), [&](int v, const float(&x)[8]) {
-        if (v < nv) {  // two 16-byte (bf16: 8-byte) stores per voxel and warp; the 8 warps complete the row
-          if (MODE == 0) {
-            float* dst = out.voxel_feat + (size_t)(v0 + v) * 64;
-            *reinterpret_cast<float4*>(dst + coff8[0]) = make_float4(x[0], x[1], x[2], x[3]);
-            *reinterpret_cast<float4*>(dst + coff8[1]) = make_float4(x[4], x[5], x[6], x[7]);
-          } else if (MODE == 1) {
-            float* dst = static_cast<float*>(out.grid) + (size_t)sVoxCell[v] * 64;
-            __stcs(reinterpret_cast<float4*>(dst + coff8[0]), make_float4(x[0], x[1], x[2], x[3]));
-            __stcs(reinterpret_cast<float4*>(dst + coff8[1]), make_float4(x[4], x[5], x[6], x[7]));
-          } else {
-            __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(out.grid) + (size_t)sVoxCell[v] * 64;
-            *reinterpret_cast<uint2*>(dst + coff8[0]) = make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
-            *reinterpret_cast<uint2*>(dst + coff8[1]) = make_uint2(pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
-          }
-        }
-      });
+    for (int r = 0; r < 8; ++r) {
+      const float4 p = *reinterpret_cast<const float4*>(sP2 + (meta.v[r] & (kVox - 1)) * QS + warp * 4);
+      float4 hi, lo;
+      umma::tf32_split(p.x, hi.x, lo.x);
+      umma::tf32_split(p.y, hi.y, lo.y);
+      umma::tf32_split(p.z, hi.z, lo.z);
+      umma::tf32_split(p.w, hi.w, lo.w);
+      const uint32_t off = x_offset(0, x_row(lane, r), warp);
+      *reinterpret_cast<float4*>(smem + OFF_XH + off) = hi;
+      *reinterpret_cast<float4*>(smem + OFF_XL + off) = lo;
     }
-    group_sync(group);  // the next tile's setup overwrites sH1T and sRowVox
+    // the accumulator buffer and its TileInfo are free once the back stage has drained their previous use
+    if (it >= 2) umma::mbar_wait(bar_empty + 8 * buf, ((it >> 1) - 1) & 1);
+    {
+      TileInfo* info = reinterpret_cast<TileInfo*>(smem + OFF_INFO) + buf;
+      const int my = sRowVox[tid], next = tid + 1 < kRows ? sRowVox[tid + 1] : 255;
+      const unsigned last = __ballot_sync(0xffffffffu, has_row && (tid + 1 == nrows || my != next));
+      if (lane == 0) info->last_mask[warp] = last;
+      if (MODE != 0 && tid < nv) info->voxcell[tid] = sVoxCell[tid];
+      if (tid == 0) {
+        info->nrows = nrows;
+        info->nv = nv;
+        info->v0 = v0;
+      }
+    }
+    umma::fence_async_smem();  // X (generic-proxy writes) -> visible to the tensor core
+    front_sync();              // also: the next tile's VFE-1 overwrites sH1T (= sP2) and sRowVox
+    if (tid == 0) {  // ---- TENSOR ----
+      umma::fence_after_sync();
+      issue_fcn_mma(smem_base, tmem_base + buf * kRows);
+      umma::mma_commit(bar_full + 8 * buf);
+      umma::mbar_arrive(bar_full + 8 * buf);  // release: publishes TileInfo to the back stage
+    }
     cur = nxt;
   }
+  asm volatile("bar.sync 3, %0;" ::"n"(kFrontThreads + kBackThreads) : "memory");
 }
 
 }  // namespace
@@ -619,7 +713,7 @@ static cudaError_t launch_vfe_mode(const VfeSmall& p, const float* wblob, const 
                                    int sm_count, cudaStream_t st) {
   cudaError_t err = cudaFuncSetAttribute(vfe_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (err != cudaSuccess) return err;
-  // persistent: one CTA per SM (2 tile groups x 8 warps + 1 writer warpgroup), tiles strided over the tile groups
+  // persistent: one CTA per SM (front 8 warps, back 4 warps, writers 4 warps), tiles strided over the CTAs
   vfe_kernel<MODE><<<sm_count, kCtaThreads, kSmemBytes, st>>>(p, wblob, prob, out);
   return cudaGetLastError();
 }
