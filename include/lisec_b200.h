@@ -183,6 +183,10 @@ int32_t lisec_frontend_forward_host(lisec_handle* h, const void* points_host, in
  * n_dropped_nonfinite, n_dropped_out_of_range, 0, 0}, then int32[n_sweeps+1] = exclusive prefix of voxels per sweep. */
 int32_t lisec_voxel_counts_async(lisec_handle* h, void* pinned_out, int64_t pinned_bytes, void* stream);
 
+/* Debug aid, inert unless the environment had LISEC_TRACE=1 at lisec_create(): cycle counters of the VFE kernel's pipeline
+ * stages in the last VFE launch, int64 [256 CTAs][16 slots] (slot meaning: lisec_b200/csrc/vfe.cu). Synchronous. */
+int32_t lisec_debug_trace(lisec_handle* h, int64_t* out, int64_t n);
+
 /* Number of kernels the last call on this handle launched (bench.py's gpu_launches). */
 int32_t lisec_last_launch_count(const lisec_handle* h);
 

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -82,7 +83,7 @@ void free_workspace(Workspace& w) {
   void* ptrs[] = {w.count, w.cell_voxel, w.cell_of_point, w.list_unsorted, w.list_sorted, w.entry_voxel,
                   w.voxel_cell, w.voxel_start, w.row_start, w.tile_first, w.tile_row0, w.row_voxel, w.row_feat,
                   w.block_sums, w.sweep_voxel_start,
-                  w.totals, w.voxel_feat, w.c_empty, w.vfe_w, w.staging, w.empty_desc};
+                  w.totals, w.voxel_feat, w.c_empty, w.vfe_w, w.staging, w.empty_desc, w.trace};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   w = Workspace();
@@ -128,7 +129,8 @@ int do_voxelize(lisec_handle* h, const void* points, int dtype, const SweepOffse
 int do_vfe(lisec_handle* h, float* voxel_feat, cudaStream_t st) {
   LISEC_CUDA(h, launch_row_features(h->last_points, h->last_dtype, h->geom, h->ws, h->max_voxels, st, &h->launches));
   const VfeProblem prob{h->ws.tile_first, h->ws.tile_row0, h->ws.row_voxel, h->ws.row_feat, h->ws.totals + TOT_TILES};
-  LISEC_CUDA(h, launch_vfe(h->params, h->ws.vfe_w, prob, voxel_feat, h->sm_count, st, &h->launches));
+  LISEC_CUDA(h, launch_vfe(h->params, h->ws.vfe_w, prob, voxel_feat, h->sm_count, st, &h->launches,
+                           reinterpret_cast<long long*>(h->ws.trace)));
   return LISEC_OK;
 }
 
@@ -235,6 +237,10 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
     LISEC_CUDA(h, cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming));
     LISEC_CUDA(h, cudaEventCreateWithFlags(&h->ev_free[b], cudaEventDisableTiming));
   }
+  if (const char* t = std::getenv("LISEC_TRACE"); t && t[0] == '1') {
+    LISEC_CUDA(h, dev_alloc(h, &w.trace, (size_t)kTraceCtas * kTraceSlots));
+    LISEC_CUDA(h, cudaMemset(w.trace, 0, sizeof(unsigned long long) * kTraceCtas * kTraceSlots));
+  }
   LISEC_CUDA(h, dev_alloc(h, &w.empty_desc, (size_t)16));
   // the one-voxel problem whose VFE output is c_empty: 0 kept points, 1 pad row, 1 tile
   // layout: tile_first {0,1} | tile_row0 {0,1} | n_tiles (int64) 1 | row_voxel {0} | pad | row_feat 6 x 0.f
@@ -278,7 +284,7 @@ int32_t lisec_set_vfe_weights(lisec_handle* h, const lisec_vfe_weights* w, void*
   VfeSmall& p = h->params;
   const float* k0 = w->dense_kernel[0];
   for (int k = 0; k < 6; ++k)
-    for (int j = 0; j < 16; ++j) p.w1[k][j] = (double)k0[k * 16 + j];
+    for (int j = 0; j < 16; ++j) p.w1f[k][j] = k0[k * 16 + j];
   // blob = [W2P | W2X | W3^T hi image | W3^T lo image]; a Keras kernel is (C_in, C_out) row-major with the pooled
   // half's rows first. dense_2 runs on the tensor core as 3xTF32: each weight is split into hi = rn_tf32(w) and
   // lo = rn_tf32(w - hi) and laid out as the A operand W3^T[c_out][c_in] (K-major, 128-byte swizzle, umma.cuh).
@@ -489,6 +495,16 @@ int32_t lisec_frontend_forward_host(lisec_handle* h, const void* points_host, in
   rc = frontend(h, staging, dtype, so, grid, st);
   if (rc) return rc;
   LISEC_CUDA(h, cudaEventRecord(h->ev_free[b], st));
+  return LISEC_OK;
+}
+
+int32_t lisec_debug_trace(lisec_handle* h, int64_t* out, int64_t n) {
+  if (!h) return LISEC_ERR_BAD_ARG;
+  if (!h->ws.trace) return fail(h, LISEC_ERR_STATE, "tracing is off: set LISEC_TRACE=1 before lisec_create()");
+  if (!out || n < (int64_t)kTraceCtas * kTraceSlots) return fail(h, LISEC_ERR_BAD_ARG, "out too small");
+  LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
+  LISEC_CUDA(h, cudaDeviceSynchronize());
+  LISEC_CUDA(h, cudaMemcpy(out, h->ws.trace, sizeof(int64_t) * kTraceCtas * kTraceSlots, cudaMemcpyDeviceToHost));
   return LISEC_OK;
 }
 

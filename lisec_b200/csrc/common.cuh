@@ -33,7 +33,7 @@ struct SweepOffsets {
 //   W2P / slab 0 = kernel rows that multiply the POOLED half  (Concatenate([pooling, layer]), :164-165)
 //   W2X / slab 1 = kernel rows that multiply the pointwise half
 struct VfeSmall {
-  double w1[6][16];      // dense (6,16), held in float64: this product is accumulated in float64
+  float w1f[6][16];      // dense (6,16); its product is evaluated in compensated float32 (vfe.cu, VFE-1)
   float a1[16], b1[16];  // BN folded: y = x*a + b, a = gamma*rsqrt(var+eps), b = beta - mean*a
   float a2[32], b2[32];
   float a3[64], b3[64];
@@ -82,7 +82,11 @@ struct Workspace {
   float* vfe_w = nullptr;            // [kVfeBlobFloats] weight blob (see VfeSmall)
   void* staging = nullptr;           // host->device landing buffer for *_host entry points
   int* empty_desc = nullptr;         // 8 ints describing the one-voxel problem that yields c_empty
+  // Debug only (LISEC_TRACE=1 at lisec_create, else nullptr): per-CTA cycle counters of the VFE kernel's pipeline
+  // stages, long long [kTraceCtas][16] (slots listed in vfe.cu); read back with lisec_debug_trace().
+  unsigned long long* trace = nullptr;
 };
+constexpr int kTraceCtas = 256, kTraceSlots = 16;
 
 // ---- launchers (each returns the cudaError_t of its launches) --------------------------------------------
 cudaError_t launch_point_pass(const void* pts, int pts_dtype, long long n_total, const SweepOffsets& so,
@@ -106,7 +110,7 @@ struct VfeProblem {
 cudaError_t launch_row_features(const void* pts, int pts_dtype, const Geom& g, const Workspace& w, long long max_voxels,
                                 cudaStream_t st, int* launches);
 cudaError_t launch_vfe(const VfeSmall& p, const float* wblob, const VfeProblem& prob,
-                       float* voxel_feat, int sm_count, cudaStream_t st, int* launches);
+                       float* voxel_feat, int sm_count, cudaStream_t st, int* launches, long long* prof = nullptr);
 // Fused VFE + dense grid: voxel rows go straight to their cells, a 9th warp per CTA streams c_empty into empty cells.
 cudaError_t launch_vfe_to_grid(const VfeSmall& p, const float* wblob,
                                const VfeProblem& prob, const Workspace& w, const Geom& g, int n_sweeps, int grid_dtype,

@@ -46,11 +46,16 @@ __device__ __forceinline__ unsigned pack_bf16x2(float a, float b) {
   return *reinterpret_cast<unsigned*>(&h);
 }
 
-constexpr int kFrontThreads = kVfeThreads;  // 8 warps, one tile at a time
-constexpr int kBackThreads = 128;           // 4 warps = the 4 TMEM lane quadrants
-constexpr int kWriterThreads = 128;         // background writers (fused modes)
-constexpr int kCtaThreads = kFrontThreads + kBackThreads + kWriterThreads;
-constexpr int kBackWarp0 = kFrontThreads / 32;
+// Warp roles. The SM's arbiter favours high warp ids, so the stage that sets the pace (FRONT) sits on top.
+constexpr int kWriterWarps = 3;             // warps 0-2: background writers (fused modes)
+constexpr int kTensorWarp = 3;              // warp 3: lane 0 issues the MMAs
+constexpr int kBackWarp0 = 4;               // warps 4-7: back stage, warp id % 4 = its TMEM lane quadrant
+constexpr int kBackThreads = 128;
+constexpr int kFrontWarp0 = 8;              // warps 8-23: front stage (16 warps on one 256-row tile: the stage is
+constexpr int kFrontWarps = 16;             // latency-bound, so it gets the warps; each warp owns 2 of 32 channels)
+constexpr int kFrontThreads = 32 * kFrontWarps;
+constexpr int kCtaThreads = 32 * kFrontWarp0 + kFrontThreads;
+constexpr int kSlots = 4;                   // accumulator buffers in flight (and TileInfo slots)
 constexpr int kRows = kVfeThreads;     // 256 rows per tile
 constexpr int kVox = kVfeThreads / 2;  // 128 voxels per tile: a non-full voxel has >= 2 rows, a full one T >= 2
 constexpr int PR = kRows + 4;          // float pitch of row-indexed k-major tiles (16-byte aligned rows, 4-bank skew)
@@ -61,7 +66,7 @@ constexpr int kBgCells = 32;           // cells in the writers' TMA source tile
 // tensor-core operands (K-major, 128-byte swizzle; see umma.cuh)
 constexpr uint32_t kXSlab = kRows * 128;  // one 32-channel half of X: 256 rows x 128 B
 constexpr uint32_t kWSlab = 64 * 128;     // one 32-channel half of W3^T: 64 rows x 128 B
-constexpr int kTmemCols = 512;            // two accumulator buffers of 256 columns (one column per tile row)
+constexpr int kTmemCols = 512;            // 4 accumulators: 2 column ranges of 256 (one column per tile row) x 2 lane halves
 
 // per accumulator buffer: what the back stage needs to know about the tile
 struct TileInfo {
@@ -85,10 +90,11 @@ constexpr int OFF_ROWVOX = OFF_Q + kVox * QS * 4;   // uint8[kRows] local voxel 
 constexpr int OFF_VOXCELL = OFF_ROWVOX + kRows;     // int[kVox] cell of each tile voxel, front stage's own copy
 constexpr int OFF_FSTAGE = OFF_VOXCELL + kVox * 4;  // float[kRows][6] the NEXT tile's feature rows (cp.async prefetch)
 constexpr int OFF_VSTAGE = OFF_FSTAGE + kRows * 6 * 4;  // int[kRows] the NEXT tile's row -> voxel
-constexpr int OFF_INFO = OFF_VSTAGE + kRows * 4;    // TileInfo[2]
-constexpr int OFF_BAR = OFF_INFO + 2 * (int)sizeof(TileInfo);  // mbarriers: full[2], empty[2]; then the TMEM base slot
-constexpr int OFF_BG = (OFF_BAR + 64 + 127) & ~127;            // kBgCells x 64 channels of c_empty: the TMA source tile
-constexpr int kSmemBytes = OFF_BG + kBgCells * 64 * 4 + 1024;  // + slack to align the base to 1 KB
+constexpr int OFF_INFO = OFF_VSTAGE + kRows * 4;    // TileInfo[kSlots]
+constexpr int OFF_BAR = OFF_INFO + kSlots * (int)sizeof(TileInfo);  // mbarriers acc_full[4], acc_empty[4], x_full
+constexpr int OFF_TMEM_SLOT = OFF_BAR + 8 * (2 * kSlots + 1);       // TMEM base address (written by tcgen05.alloc)
+constexpr int OFF_BG = (OFF_TMEM_SLOT + 8 + 127) & ~127;            // kBgCells x 64 channels of c_empty: the TMA source tile
+constexpr int kSmemBytes = OFF_BG + kBgCells * 64 * 4;  // dynamic shared memory starts 1 KB-aligned (no static smem)
 static_assert(kVox * QS * 4 <= 16 * PR * 4 + 16 * PV * 4, "P2 must fit in H1T+P1T");
 static_assert(kSmemBytes <= 232448, "one CTA per SM, 227 KB opt-in limit");
 static_assert(OFF_W3H % 1024 == 0 && OFF_XL % 1024 == 0, "operand slabs are 1 KB-aligned");
@@ -96,43 +102,46 @@ static_assert(sizeof(TileInfo) % 16 == 0 && OFF_INFO % 16 == 0 && OFF_BAR % 8 ==
 
 // ---- register-tile GEMM: acc[R][C] += A[k][row(r)] * W[k][col(c)], k = 0..K-1 -------------------------------
 // The lane's rows come as R/4 float4 chunks at row0 + i*chunk_stride (consecutive lanes -> consecutive 16 bytes);
-// the warp's columns come in groups of 4 at offsets coff[g] (same address for every lane: a broadcast load).
+// the warp's columns are NC consecutive ones at col0 (same address for every lane: a broadcast load).
 // float32 accumulation in blocks of 4 k-steps (a fresh accumulator per block, then added): dense_1's two halves cancel.
-template <int R, int CG, int K>
+// NC = 2 or 4 columns per thread at column offset col0 (one 8- or 16-byte broadcast load per k).
+template <int R, int NC, int K>
 __device__ __forceinline__ void tile_gemm_blocked(const float* __restrict__ sA, int pitch, int chunk_stride, int row0,
-                                                  const float* __restrict__ sW, int ldw, const int (&coff)[CG],
-                                                  float (&acc)[R][CG * 4]) {
-  static_assert(R % 4 == 0 && K % 4 == 0, "tile shape");
+                                                  const float* __restrict__ sW, int ldw, int col0,
+                                                  float (&acc)[R][NC]) {
+  static_assert(R % 4 == 0 && K % 4 == 0 && (NC == 2 || NC == 4), "tile shape");
 #pragma unroll 1
   for (int kb = 0; kb < K; kb += 4) {
-    float blk[R][CG * 4];
+    float blk[R][NC];
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int c = 0; c < CG * 4; ++c) blk[r][c] = 0.f;
+      for (int c = 0; c < NC; ++c) blk[r][c] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       const int k = kb + kk;
-      float a[R], b[CG * 4];
+      float a[R], b[NC];
 #pragma unroll
       for (int i = 0; i < R / 4; ++i) {
         const float4 v = *reinterpret_cast<const float4*>(sA + k * pitch + row0 + chunk_stride * i);
         a[4 * i] = v.x; a[4 * i + 1] = v.y; a[4 * i + 2] = v.z; a[4 * i + 3] = v.w;
       }
-#pragma unroll
-      for (int g = 0; g < CG; ++g) {
-        const float4 v = *reinterpret_cast<const float4*>(sW + k * ldw + coff[g]);
-        b[4 * g] = v.x; b[4 * g + 1] = v.y; b[4 * g + 2] = v.z; b[4 * g + 3] = v.w;
+      if (NC == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(sW + k * ldw + col0);
+        b[0] = v.x; b[1] = v.y; b[2] = v.z; b[NC - 1] = v.w;
+      } else {
+        const float2 v = *reinterpret_cast<const float2*>(sW + k * ldw + col0);
+        b[0] = v.x; b[1] = v.y;
       }
 #pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int c = 0; c < CG * 4; ++c) blk[r][c] = fmaf(a[r], b[c], blk[r][c]);
+        for (int c = 0; c < NC; ++c) blk[r][c] = fmaf(a[r], b[c], blk[r][c]);
     }
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int c = 0; c < CG * 4; ++c) acc[r][c] += blk[r][c];
+      for (int c = 0; c < NC; ++c) acc[r][c] += blk[r][c];
   }
 }
 
@@ -249,15 +258,63 @@ struct VfeOutput {
   const int* cell_voxel;  // occupancy map
   const float* c_empty;
   long long ncells;
+  long long* prof;  // debug (LISEC_TRACE=1): per-CTA cycle counters [kProfSlots], see Workspace::trace
 };
+constexpr int kProfSlots = 16;
+// slots: 0 front total, 1 VFE-1, 2 pool1, 3 Q2, 4 dense_1, 5 wait X free, 6 X pointwise, 7 pool2, 8 X pooled,
+//        9 wait accumulator free, 10 info + MMA issue, 11 back total, 12 back wait full, 13 back scan, 14 tiles
+#ifndef LISEC_PROF
+#define LISEC_PROF 0  // 1: compile the per-stage cycle counters in (make PROF=1); they cost registers in the hot loops
+#endif
+#if !LISEC_PROF
+struct Prof {
+  long long* dst;
+  long long acc[kProfSlots];
+  __device__ __forceinline__ void begin(long long*) { dst = nullptr; }
+  __device__ __forceinline__ void lap(int) {}
+  __device__ __forceinline__ void flush(int, int) {}
+};
+#else
+struct Prof {
+  long long* dst;
+  long long t0, acc[kProfSlots];
+  __device__ __forceinline__ void begin(long long* d) {
+    dst = d;
+    if (dst) {
+#pragma unroll
+      for (int i = 0; i < kProfSlots; ++i) acc[i] = 0;
+      t0 = clock64();
+    }
+  }
+  __device__ __forceinline__ void lap(int slot) {
+    if (dst) {
+      const long long t1 = clock64();
+      acc[slot] += t1 - t0;
+      t0 = t1;
+    }
+  }
+  __device__ __forceinline__ void flush(int first, int last) {
+    if (dst)
+      for (int i = first; i <= last; ++i) dst[(size_t)blockIdx.x * kProfSlots + i] = acc[i];
+  }
+};
+#endif
 
 // ---- background writer (fused modes, warps 12-15) ------------------------------------------------------------
 // c_empty goes into every EMPTY cell of the grid while the other warps compute; occupied cells are written by the
 // back stage, so every grid element is still written exactly once. The data never touches the LSU: a 32-cell tile of
 // replicated c_empty sits in shared memory and every run of consecutive empty cells is ONE TMA bulk store
 // (cp.async.bulk shared -> global, SASS UBLKCP) issued by the lane of the run's first cell.
-__device__ __forceinline__ void bulk_store(void* gdst, unsigned ssrc, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes)
+// The 1.2 GB background stream is written once and not read again by this path: evict-first in L2, so that it does
+// not push out the row features, tile tables and cell maps the other warps are prefetching.
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_store(void* gdst, unsigned ssrc, unsigned bytes, unsigned long long policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(ssrc),
+               "r"(bytes), "l"(policy)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -267,16 +324,17 @@ template <typename GT>
 __device__ __forceinline__ void background_writer(const int* __restrict__ cell_voxel, const float* __restrict__ c_empty,
                                                   GT* __restrict__ grid, long long ncells, unsigned char* sBg,
                                                   int wtid) {
-  constexpr int kWarps = kWriterThreads / 32;
+  constexpr int kWarps = kWriterWarps;
   const int lane = wtid & 31, wwarp = wtid >> 5;
   // fill the tile: 32 cells x 64 channels of GT, every cell = c_empty (rounded once for bf16)
-  for (int i = wtid; i < kBgCells * 64; i += kWriterThreads) {
+  for (int i = wtid; i < kBgCells * 64; i += 32 * kWriterWarps) {
     if (sizeof(GT) == 4) reinterpret_cast<float*>(sBg)[i] = c_empty[i & 63];
     else reinterpret_cast<__nv_bfloat16*>(sBg)[i] = __float2bfloat16_rn(c_empty[i & 63]);
   }
   umma::fence_async_smem();  // generic-proxy writes -> visible to the TMA
-  asm volatile("bar.sync 2, %0;" ::"n"(kWriterThreads) : "memory");
+  asm volatile("bar.sync 2, %0;" ::"n"(32 * kWriterWarps) : "memory");
   const unsigned src = (unsigned)__cvta_generic_to_shared(sBg);
+  const unsigned long long policy = l2_evict_first_policy();
   const int ngroups = (int)((ncells + 31) >> 5);
   const int stride = gridDim.x * kWarps;
   constexpr int U = 4;  // 32-cell groups per step; the next step's occupancy words are already in flight
@@ -301,7 +359,7 @@ __device__ __forceinline__ void background_writer(const int* __restrict__ cell_v
         const unsigned rest = ~(empty >> lane);  // zeros shift in on top, so rest == 0 only for lane 0 of a full group
         const int len = rest ? __ffs(rest) - 1 : 32;  // consecutive empty cells from this lane on
         GT* dst = grid + (((long long)(g0 + u * stride) << 5) + lane) * 64;
-        bulk_store(dst, src, (unsigned)(len * 64 * sizeof(GT)));
+        bulk_store(dst, src, (unsigned)(len * 64 * sizeof(GT)), policy);
       }
     }
     bulk_commit();
@@ -365,8 +423,9 @@ __device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all_but_last() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
-// ---- TENSOR stage: the FCN's Dense(64->64) for one tile, issued by one thread --------------------------------
+// ---- TENSOR stage: the FCN's Dense(64->64) for one tile, issued by one thread (lane 0 of the tensor warp) ----
 // D^T[ch][n] (+)= sum_k W3^T[ch][k] * X[n][k], k over [pooled 32 | pointwise 32]. 3xTF32, small terms first so that
 // their sum is not rounded against the large one: Wh*Xl, Wl*Xh, then Wh*Xh.
 __device__ __forceinline__ void issue_fcn_mma(uint32_t smem_base, uint32_t d_tmem) {
@@ -385,47 +444,73 @@ __device__ __forceinline__ void issue_fcn_mma(uint32_t smem_base, uint32_t d_tme
     }
 }
 
-// ---- BACK stage: accumulators -> per-voxel max -> BN + ReLU -> output row ------------------------------------
-// Warp q of the stage reads TMEM lanes 32q..32q+31; an M=64 accumulator keeps channel c in lane (c % 16) + 32 (c / 16),
-// so lanes 0..15 of the warp own channels 16q..16q+15 and lanes 16..31 idle (they take part in the loads only).
-// Columns are tile rows (rotated inside groups of 8, see x_row). y = relu(a*z + b) is monotonic in z, so
-// max_rows relu(a*z_r + b) = relu(a*z* + b) with z* = max z_r (a >= 0) or min z_r (a < 0): both are tracked.
-template <int MODE>
-__device__ __forceinline__ void back_stage(const VfeSmall& P, const VfeOutput& out, unsigned char* smem, int n_tiles,
-                                           uint32_t tmem_base, int bwarp, int lane) {
-  const uint32_t bar_full = umma::smem_u32(smem + OFF_BAR), bar_empty = bar_full + 16;
-  const int ch = 16 * bwarp + (lane & 15);
-  const bool active = lane < 16;
-  const float a = P.a3[ch], b = P.b3[ch];
-  const uint32_t tlane = tmem_base + ((uint32_t)(32 * bwarp) << 16);
-  int it = 0;
-  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-    const int buf = it & 1;
-    umma::mbar_wait(bar_full + 8 * buf, (it >> 1) & 1);
+// mbarrier addresses and the accumulator of pipeline slot s = (tile ordinal) & 3: even ordinals use TMEM lanes 0..15
+// of every quadrant, odd ones lanes 16..31 (the two interleaved placements of an M=64 accumulator); the column range
+// alternates every second tile.
+__device__ __forceinline__ uint32_t bar_acc_full(uint32_t smem_base, int s) { return smem_base + OFF_BAR + 8 * s; }
+__device__ __forceinline__ uint32_t bar_acc_empty(uint32_t smem_base, int s) {
+  return smem_base + OFF_BAR + 8 * (kSlots + s);
+}
+__device__ __forceinline__ uint32_t bar_x_full(uint32_t smem_base) { return smem_base + OFF_BAR + 8 * (2 * kSlots); }
+__device__ __forceinline__ uint32_t acc_addr(uint32_t tmem_base, int s) {
+  return tmem_base + ((uint32_t)(16 * (s & 1)) << 16) + (uint32_t)(s >> 1) * kRows;
+}
+
+// The tensor warp's loop: X complete -> accumulator free -> 24 MMAs -> commit.
+__device__ __forceinline__ void tensor_stage(uint32_t smem_base, uint32_t tmem_base, int my_tiles) {
+  for (int it = 0; it < my_tiles; ++it) {
+    const int s = it & (kSlots - 1);
+    umma::mbar_wait(bar_x_full(smem_base), it & 1);
+    if (it >= kSlots) umma::mbar_wait(bar_acc_empty(smem_base, s), ((it / kSlots) - 1) & 1);
     umma::fence_after_sync();
-    const TileInfo* info = reinterpret_cast<const TileInfo*>(smem + OFF_INFO) + buf;
-    const int nrows = info->nrows, v0 = info->v0;
+    issue_fcn_mma(smem_base, acc_addr(tmem_base, s));
+    umma::mma_commit(bar_acc_full(smem_base, s));
+    umma::mbar_arrive(bar_acc_full(smem_base, s));  // release: publishes the front stage's TileInfo to the back stage
+  }
+}
+
+// ---- BACK stage: accumulators -> per-voxel max -> BN + ReLU -> output row ------------------------------------
+// Warp q of the stage reads TMEM lanes 32q..32q+31; an M=64 accumulator keeps channel c in lane (c % 16) + 32 (c / 16)
+// (+16 for the interleaved placement), so lanes 0..15 of the warp own channels 16q..16q+15 of an EVEN tile and lanes
+// 16..31 the same channels of the following ODD tile: the warp scans a pair of tiles per pass, every lane busy.
+// Columns are tile rows (rotated inside groups of 8, see x_row): a thread walks its tile's rows in order, so the per-
+// voxel max is a sequential scan; voxel ends come from the tile's last-row bit mask (per lane: the two halves of the
+// warp work on different tiles, so everything below is predicated, not branched). y = relu(a*z + b) is monotonic in z,
+// so max_rows relu(a*z_r + b) = relu(a*z* + b) with z* = max z_r (a >= 0) or min z_r (a < 0): both are tracked and
+// BN + ReLU are applied once per voxel.
+template <int MODE>
+__device__ __forceinline__ void back_stage(const VfeSmall& P, const VfeOutput& out, unsigned char* smem,
+                                           uint32_t smem_base, int my_tiles, uint32_t tmem_base, int bwarp, int lane) {
+  const int ch = 16 * bwarp + (lane & 15), hh = lane >> 4;
+  const float a = P.a3[ch], b = P.b3[ch];
+  const bool pos = a >= 0.f;
+  const uint32_t tlane = tmem_base + ((uint32_t)(32 * bwarp) << 16);
+  Prof prof;
+  prof.begin(bwarp == 0 && lane == 0 ? out.prof : nullptr);
+  for (int p = 0; 2 * p < my_tiles; ++p) {
+    const int it = 2 * p + hh;           // this lane's tile
+    const bool valid = it < my_tiles;
+    const int s_even = (2 * p) & (kSlots - 1), s = valid ? (it & (kSlots - 1)) : s_even;
+    umma::mbar_wait(bar_acc_full(smem_base, s_even), ((2 * p) / kSlots) & 1);
+    if (2 * p + 1 < my_tiles) umma::mbar_wait(bar_acc_full(smem_base, s_even + 1), ((2 * p + 1) / kSlots) & 1);
+    umma::fence_after_sync();
+    prof.lap(12);
+    const TileInfo* info = reinterpret_cast<const TileInfo*>(smem + OFF_INFO) + s;
+    const int nrows = valid ? info->nrows : 0;
+    const int nrows_max = max(nrows, __shfl_xor_sync(0xffffffffu, nrows, 16));
     float mx = -INFINITY, mn = INFINITY;
     int v = 0;
-    auto emit = [&]() {
-      const float z = a >= 0.f ? mx : mn;
-      const float y = fmaxf(fmaf(z, a, b), 0.f);
-      if (active) {
-        if (MODE == 0) out.voxel_feat[(size_t)(v0 + v) * 64 + ch] = y;
-        else if (MODE == 1) __stcs(static_cast<float*>(out.grid) + (size_t)info->voxcell[v] * 64 + ch, y);
-        else static_cast<__nv_bfloat16*>(out.grid)[(size_t)info->voxcell[v] * 64 + ch] = __float2bfloat16_rn(y);
-      }
-      ++v;
-      mx = -INFINITY;
-      mn = INFINITY;
-    };
+    int cell = MODE != 0 ? info->voxcell[0] : 0;
+    float* row0 = MODE == 0 ? out.voxel_feat + (size_t)info->v0 * 64 + ch : nullptr;
+    const uint32_t tcol = tlane + (uint32_t)((2 * p / 2) & 1) * kRows;
 #pragma unroll 1
-    for (int c0 = 0; c0 < nrows; c0 += 64) {  // two 32-column loads per step: the rotation pattern repeats every 64
-      const uint2 mask = *reinterpret_cast<const uint2*>(&info->last_mask[c0 >> 5]);
+    for (int c0 = 0; c0 < nrows_max; c0 += 64) {  // two 32-column loads per step: the rotation pattern repeats every 64
+      uint2 mask = *reinterpret_cast<const uint2*>(&info->last_mask[c0 >> 5]);
+      if (!valid) mask = make_uint2(0u, 0u);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         float x[32];
-        umma::tmem_ld_32x32(tlane + buf * kRows + c0 + 32 * half, x);
+        umma::tmem_ld_32x32(tcol + c0 + 32 * half, x);
         const unsigned m = half ? mask.y : mask.x;
 #pragma unroll
         for (int g = 0; g < 4; ++g)
@@ -434,37 +519,53 @@ __device__ __forceinline__ void back_stage(const VfeSmall& P, const VfeOutput& o
             const float val = x[8 * g + ((i + 4 * half + g) & 7)];
             mx = fmaxf(mx, val);
             mn = fminf(mn, val);
-            if (m & (1u << (8 * g + i))) emit();
+            const bool last = (m >> (8 * g + i)) & 1u;
+            const float y = fmaxf(fmaf(pos ? mx : mn, a, b), 0.f);
+            if (last) {
+              if (MODE == 0) row0[(size_t)v * 64] = y;
+              else if (MODE == 1) __stcs(static_cast<float*>(out.grid) + (size_t)cell * 64 + ch, y);
+              else static_cast<__nv_bfloat16*>(out.grid)[(size_t)cell * 64 + ch] = __float2bfloat16_rn(y);
+              ++v;
+              if (MODE != 0) cell = info->voxcell[v & (kVox - 1)];  // the next voxel's cell: in flight while its rows are scanned
+            }
+            mx = last ? -INFINITY : mx;
+            mn = last ? INFINITY : mn;
           }
       }
     }
     umma::fence_before_sync();
     __syncwarp();
-    if (lane == 0) umma::mbar_arrive(bar_empty + 8 * buf);
+    if (lane == 0) {
+      umma::mbar_arrive(bar_acc_empty(smem_base, s_even));
+      if (2 * p + 1 < my_tiles) umma::mbar_arrive(bar_acc_empty(smem_base, s_even + 1));
+    }
+    prof.lap(13);
   }
+  if (prof.dst) prof.acc[11] = prof.acc[12] + prof.acc[13];
+  prof.flush(11, 13);
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(kCtaThreads, 1)
     vfe_kernel(const __grid_constant__ VfeSmall P, const float* __restrict__ wblob,
                const __grid_constant__ VfeProblem prob, const __grid_constant__ VfeOutput out) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem =
-      reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) unsigned char smem[];  // the operand slabs need 1 KB alignment (128-byte swizzle)
   const int warp_in_cta = threadIdx.x >> 5;
   const uint32_t smem_base = umma::smem_u32(smem);
-  const uint32_t bar_full = smem_base + OFF_BAR, bar_empty = bar_full + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 32);
+  if (smem_base & 1023u) __trap();
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM_SLOT);
   const int n_tiles = (int)*prob.n_tiles;
+  // tiles are strided over the CTAs: this one owns ordinals it = 0 .. my_tiles-1, tile blockIdx.x + it * gridDim.x
+  const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   // ---- one-time setup: weights, barriers, TMEM ----
-  if (threadIdx.x < kFrontThreads + kBackThreads) {
+  {
     // blob = [W2P | W2X] float32 row-major, then the W3^T hi and lo operand images (built by the host, api.cu)
     const float4* src = reinterpret_cast<const float4*>(wblob);
     float4* w2 = reinterpret_cast<float4*>(smem + OFF_W2P);
     float4* w3 = reinterpret_cast<float4*>(smem + OFF_W3H);
     constexpr int n2 = 2 * 16 * 32 / 4, n3 = 4 * (int)kWSlab / 16;
-    for (int i = threadIdx.x; i < n2 + n3; i += kFrontThreads + kBackThreads) {
+    for (int i = threadIdx.x; i < n2 + n3; i += kCtaThreads) {
       const float4 v = __ldg(src + i);
       if (i < n2) w2[i] = v;
       else w3[i - n2] = v;
@@ -472,10 +573,11 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
     umma::fence_async_smem();  // W3 is read by the tensor core
   }
   if (threadIdx.x == 0) {
-    for (int bfr = 0; bfr < 2; ++bfr) {
-      umma::mbar_init(bar_full + 8 * bfr, 2);   // tcgen05.commit + the issuing thread's own (release) arrive
-      umma::mbar_init(bar_empty + 8 * bfr, kBackThreads / 32);
+    for (int s = 0; s < kSlots; ++s) {
+      umma::mbar_init(bar_acc_full(smem_base, s), 2);  // tcgen05.commit + the issuing thread's own (release) arrive
+      umma::mbar_init(bar_acc_empty(smem_base, s), kBackThreads / 32);
     }
+    umma::mbar_init(bar_x_full(smem_base), kFrontThreads / 32);
     umma::mbar_init_fence();
   }
   if (warp_in_cta == kBackWarp0) umma::tmem_alloc<kTmemCols>(tmem_slot);
@@ -484,24 +586,31 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
   umma::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (threadIdx.x >= kFrontThreads + kBackThreads) {  // ---- WRITER ----
-    const int wtid = threadIdx.x - kFrontThreads - kBackThreads;
+  if (warp_in_cta < kWriterWarps) {  // ---- WRITER ----
     if (MODE == 1)
-      background_writer(out.cell_voxel, out.c_empty, static_cast<float*>(out.grid), out.ncells, smem + OFF_BG, wtid);
+      background_writer(out.cell_voxel, out.c_empty, static_cast<float*>(out.grid), out.ncells, smem + OFF_BG,
+                        (int)threadIdx.x);
     if (MODE == 2)
       background_writer(out.cell_voxel, out.c_empty, static_cast<__nv_bfloat16*>(out.grid), out.ncells, smem + OFF_BG,
-                        wtid);
+                        (int)threadIdx.x);
     return;
   }
-  if (threadIdx.x >= kFrontThreads) {  // ---- BACK ----
-    back_stage<MODE>(P, out, smem, n_tiles, tmem_base, warp_in_cta - kBackWarp0, threadIdx.x & 31);
+  if (warp_in_cta == kTensorWarp) {  // ---- TENSOR ----
+    if ((threadIdx.x & 31) == 0) tensor_stage(smem_base, tmem_base, my_tiles);
+    return;
+  }
+  if (warp_in_cta < kFrontWarp0) {  // ---- BACK ----
+    back_stage<MODE>(P, out, smem, smem_base, my_tiles, tmem_base, warp_in_cta - kBackWarp0, threadIdx.x & 31);
     asm volatile("bar.sync 3, %0;" ::"n"(kFrontThreads + kBackThreads) : "memory");
     if (warp_in_cta == kBackWarp0) umma::tmem_dealloc<kTmemCols>(tmem_base);
     return;
   }
 
   // ---- FRONT ----
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // 512 threads on one 256-row tile. GEMM / pooling mapping: lane = 8 consecutive tile rows (4 voxels for the
+  // per-voxel product), warp w = channels 2w, 2w+1 of 32 (pool1: channel w of 16). VFE-1: thread = (row, half of the
+  // 16 outputs).
+  const int tid = threadIdx.x - 32 * kFrontWarp0, lane = tid & 31, warp = tid >> 5;
   float* sW2P = reinterpret_cast<float*>(smem + OFF_W2P);
   float* sW2X = reinterpret_cast<float*>(smem + OFF_W2X);
   float* sH1T = reinterpret_cast<float*>(smem + OFF_H1T);
@@ -537,141 +646,150 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
   const int tstride = gridDim.x;
   int t = blockIdx.x;
   Header cur = load_header(t);
+  Header nxt = load_header(t + tstride);
   if (t < n_tiles) prefetch_rows(cur);
   cp_async_commit();
   cp_async_wait_all();
   front_sync();
 
+  Prof prof;
+  prof.begin(tid == 0 ? out.prof : nullptr);
   int it = 0;
   for (; t < n_tiles; t += tstride, ++it) {
-    const int buf = it & 1;
+    const int slot = it & (kSlots - 1);
     const int v0 = cur.v0, nv = cur.v1 - cur.v0, nrows = cur.r1 - cur.r0;
-    const bool has_row = tid < nrows;
-    const Header nxt = load_header(t + tstride);  // consumed after the first barrier: its latency hides behind VFE-1
+    const Header nxt2 = load_header(t + 2 * tstride);  // two tiles ahead: a whole tile to land
 
-    // ---- VFE-1: Dense(6->16, no bias) + BN + ReLU (addVFELayer(in, 6, 32), :231 -> :155-166); one row per thread ----
+    // ---- VFE-1: Dense(6->16, no bias) + BN + ReLU (addVFELayer(in, 6, 32), :231 -> :155-166) ----
+    // thread = (row, 8 of the 16 outputs). The sum runs over raw coordinates up to +-50 m and must come out as the
+    // correctly rounded float64 result; float64 FMAs share their pipe with the tensor core (they stall for the whole
+    // FCN of the previous tile), so it is done in float32 with exact error terms (Ogita-Rump-Oishi Dot2): TwoProduct
+    // by FMA and TwoSum for the three large terms, a plain FMA chain for the three centroid offsets (|.| < 1 voxel).
     {
+      const int row = tid & (kRows - 1), jh = tid >> 8;
+      const bool has_row = row < nrows;
       float f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       int lv = 255;  // 255 = padding row past the tile's last row
       if (has_row) {
-        const float2 f01 = *reinterpret_cast<const float2*>(sFeatStage + 6 * tid);
-        const float2 f23 = *reinterpret_cast<const float2*>(sFeatStage + 6 * tid + 2);
-        const float2 f45 = *reinterpret_cast<const float2*>(sFeatStage + 6 * tid + 4);
+        const float2 f01 = *reinterpret_cast<const float2*>(sFeatStage + 6 * row);
+        const float2 f23 = *reinterpret_cast<const float2*>(sFeatStage + 6 * row + 2);
+        const float2 f45 = *reinterpret_cast<const float2*>(sFeatStage + 6 * row + 4);
         f[0] = f01.x; f[1] = f01.y; f[2] = f23.x; f[3] = f23.y; f[4] = f45.x; f[5] = f45.y;
-        lv = sVoxStage[tid] - v0;
+        lv = sVoxStage[row] - v0;
       }
-      double d[16];
+      const int pos = row_pos(row);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) d[j] = 0.0;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        const double fk = (double)f[k];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) d[j] = fma(fk, P.w1[k][j], d[j]);
+      for (int jj = 0; jj < 8; ++jj) {
+        const int j = 8 * jh + jj;
+        const float w0 = P.w1f[0][j], w1 = P.w1f[1][j], w2 = P.w1f[2][j];
+        const float p0 = __fmul_rn(f[0], w0), e0 = __fmaf_rn(f[0], w0, -p0);
+        const float p1 = __fmul_rn(f[1], w1), e1 = __fmaf_rn(f[1], w1, -p1);
+        const float p2 = __fmul_rn(f[2], w2), e2 = __fmaf_rn(f[2], w2, -p2);
+        const float s1 = __fadd_rn(p0, p1), b1 = __fsub_rn(s1, p0);
+        const float r1 = __fadd_rn(__fsub_rn(p0, __fsub_rn(s1, b1)), __fsub_rn(p1, b1));
+        const float s2 = __fadd_rn(s1, p2), b2 = __fsub_rn(s2, s1);
+        const float r2 = __fadd_rn(__fsub_rn(s1, __fsub_rn(s2, b2)), __fsub_rn(p2, b2));
+        const float small = __fmaf_rn(f[3], P.w1f[3][j], __fmaf_rn(f[4], P.w1f[4][j], __fmul_rn(f[5], P.w1f[5][j])));
+        const float corr = __fadd_rn(__fadd_rn(__fadd_rn(e0, e1), __fadd_rn(e2, r1)), __fadd_rn(r2, small));
+        const float d = __fadd_rn(s2, corr);
+        sH1T[j * PR + pos] = has_row ? fmaxf(fmaf(d, P.a1[j], P.b1[j]), 0.f) : 0.f;
       }
-      const int pos = row_pos(tid);
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        sH1T[j * PR + pos] = has_row ? fmaxf(fmaf(__double2float_rn(d[j]), P.a1[j], P.b1[j]), 0.f) : 0.f;
-      sRowVox[tid] = (unsigned char)lv;
+      if (jh == 0) sRowVox[row] = (unsigned char)lv;
     }
     front_sync();
-    // the staging buffers are free again: start the next tile's rows (and this tile's voxel -> cell words, needed only
-    // by the back stage) on their way; they land while the GEMMs run
-    if (t + tstride < n_tiles) prefetch_rows(nxt);
+    prof.lap(1);
+    // the staging buffers are free again: start this tile's voxel -> cell words (needed by the back stage, group 1) and
+    // the next tile's rows (needed when this tile is done, group 2) on their way; they land while the GEMMs run
     if (MODE != 0 && tid < nv) cp_async4(sVoxCell + tid, out.voxel_cell + v0 + tid);
     cp_async_commit();
+    if (t + tstride < n_tiles) prefetch_rows(nxt);
+    cp_async_commit();
     const PoolMeta meta = make_pool_meta(sRowVox, lane);
-    {  // MaxPoolingVFELayer over T (:160); RepeatLayer is implicit. Warp w pools channels 2w, 2w+1.
-      float val[8][2];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const float* src = sH1T + (2 * warp + c) * PR;
-        const float4 lo = *reinterpret_cast<const float4*>(src + 4 * lane);
-        const float4 hi = *reinterpret_cast<const float4*>(src + 128 + 4 * lane);
-        val[0][c] = lo.x; val[1][c] = lo.y; val[2][c] = lo.z; val[3][c] = lo.w;
-        val[4][c] = hi.x; val[5][c] = hi.y; val[6][c] = hi.z; val[7][c] = hi.w;
-      }
-      pool_lane_rows<2>(val, meta, [&](int v, const float(&x)[2]) {
-        if (v < nv) {
-          sP1T[(2 * warp) * PV + v] = x[0];
-          sP1T[(2 * warp + 1) * PV + v] = x[1];
-        }
+    {  // MaxPoolingVFELayer over T (:160); RepeatLayer is implicit. Warp w pools channel w.
+      float val[8][1];
+      const float* src = sH1T + warp * PR;
+      const float4 lo = *reinterpret_cast<const float4*>(src + 4 * lane);
+      const float4 hi = *reinterpret_cast<const float4*>(src + 128 + 4 * lane);
+      val[0][0] = lo.x; val[1][0] = lo.y; val[2][0] = lo.z; val[3][0] = lo.w;
+      val[4][0] = hi.x; val[5][0] = hi.y; val[6][0] = hi.z; val[7][0] = hi.w;
+      pool_lane_rows<1>(val, meta, [&](int v, const float(&x)[1]) {
+        if (v < nv) sP1T[warp * PV + v] = x[0];
       });
     }
     front_sync();
+    prof.lap(2);
 
     // ---- VFE-2: Dense(32->32) + BN + ReLU on concat[pooled, pointwise] (addVFELayer(., 32, 64), :232) ----
-    const int coff4[1] = {warp * 4};
-    {  // pooled half, once per voxel: Q2[128 x 32] = P1[128 x 16] * W2p; 4x4 tile per thread
-      float acc[4][4];
+    {  // pooled half, once per voxel: Q2[128 x 32] = P1[128 x 16] * W2p; 4 voxels x 2 channels per thread
+      float acc[4][2];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r][0] = acc[r][1] = 0.f;
+      tile_gemm_blocked<4, 2, 16>(sP1T, PV, 0, lane * 4, sW2P, 32, 2 * warp, acc);
 #pragma unroll
       for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-      tile_gemm_blocked<4, 1, 16>(sP1T, PV, 0, lane * 4, sW2P, 32, coff4, acc);
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-        *reinterpret_cast<float4*>(sQ + (lane * 4 + r) * QS + warp * 4) =
-            make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        *reinterpret_cast<float2*>(sQ + (lane * 4 + r) * QS + 2 * warp) = make_float2(acc[r][0], acc[r][1]);
     }
     front_sync();
-    float h2[8][4];  // rows 8 lane .. 8 lane + 7, channels 4 warp .. 4 warp + 3 of the VFE-2 pointwise output
-    {  // rows: 8x4 tile per thread, accumulators start at the voxel's pooled-half product
+    prof.lap(3);
+    float h2[8][2];  // rows 8 lane .. 8 lane + 7, channels 2 warp, 2 warp + 1 of the VFE-2 pointwise output
+    {  // rows: 8x2 tile per thread, accumulators start at the voxel's pooled-half product
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         const int v = meta.v[r] & (kVox - 1);  // (padding rows read some valid row)
-        const float4 q = *reinterpret_cast<const float4*>(sQ + v * QS + warp * 4);
-        h2[r][0] = q.x; h2[r][1] = q.y; h2[r][2] = q.z; h2[r][3] = q.w;
+        const float2 q = *reinterpret_cast<const float2*>(sQ + v * QS + 2 * warp);
+        h2[r][0] = q.x; h2[r][1] = q.y;
       }
-      tile_gemm_blocked<8, 1, 16>(sH1T, PR, 128, lane * 4, sW2X, 32, coff4, h2);
+      tile_gemm_blocked<8, 2, 16>(sH1T, PR, 128, lane * 4, sW2X, 32, 2 * warp, h2);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float sa = P.a2[warp * 4 + c], sb = P.b2[warp * 4 + c];
+      for (int c = 0; c < 2; ++c) {
+        const float sa = P.a2[2 * warp + c], sb = P.b2[2 * warp + c];
 #pragma unroll
         for (int r = 0; r < 8; ++r) h2[r][c] = fmaxf(fmaf(h2[r][c], sa, sb), 0.f);
       }
     }
+    prof.lap(4);
     // X is single-buffered: the previous tile's MMAs must have finished reading it
-    if (it > 0) umma::mbar_wait(bar_full + 8 * (buf ^ 1), ((it - 1) >> 1) & 1);
-    // pointwise half of the FCN input: X[n][32 + 4 warp ..] = h2, split into tf32 hi / lo
+    if (it > 0) umma::mbar_wait(bar_acc_full(smem_base, (it - 1) & (kSlots - 1)), ((it - 1) / kSlots) & 1);
+    prof.lap(5);
+    // pointwise half of the FCN input: X[n][32 + 2 warp ..] = h2, split into tf32 hi / lo
+    const uint32_t xsub = (uint32_t)(warp & 1) * 8;  // which half of the 16-byte chunk warp / 2
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      float4 hi, lo;
+      float2 hi, lo;
       umma::tf32_split(h2[r][0], hi.x, lo.x);
       umma::tf32_split(h2[r][1], hi.y, lo.y);
-      umma::tf32_split(h2[r][2], hi.z, lo.z);
-      umma::tf32_split(h2[r][3], hi.w, lo.w);
-      const uint32_t off = x_offset(1, x_row(lane, r), warp);
-      *reinterpret_cast<float4*>(smem + OFF_XH + off) = hi;
-      *reinterpret_cast<float4*>(smem + OFF_XL + off) = lo;
+      const uint32_t off = x_offset(1, x_row(lane, r), warp >> 1) + xsub;
+      *reinterpret_cast<float2*>(smem + OFF_XH + off) = hi;
+      *reinterpret_cast<float2*>(smem + OFF_XL + off) = lo;
     }
     front_sync();  // every warp is done with sH1T (A operand) and sQ: sP2 may now overwrite sH1T/sP1T
-    pool_lane_rows<4>(h2, meta, [&](int v, const float(&x)[4]) {
-      if (v < nv) *reinterpret_cast<float4*>(sP2 + v * QS + warp * 4) = make_float4(x[0], x[1], x[2], x[3]);
+    prof.lap(6);
+    pool_lane_rows<2>(h2, meta, [&](int v, const float(&x)[2]) {
+      if (v < nv) *reinterpret_cast<float2*>(sP2 + v * QS + 2 * warp) = make_float2(x[0], x[1]);
     });
-    cp_async_wait_all();  // issued a whole tile ago; the barrier below publishes the staged rows and sVoxCell
+    cp_async_wait_all_but_last();  // this thread's sVoxCell word (group 1); the rows may still be in flight
     front_sync();
+    prof.lap(7);
 
     // ---- FCN input, pooled half: Concatenate([pooled, pointwise]) (:164-165) = the voxel's pooled row, repeated ----
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      const float4 p = *reinterpret_cast<const float4*>(sP2 + (meta.v[r] & (kVox - 1)) * QS + warp * 4);
-      float4 hi, lo;
+      const float2 p = *reinterpret_cast<const float2*>(sP2 + (meta.v[r] & (kVox - 1)) * QS + 2 * warp);
+      float2 hi, lo;
       umma::tf32_split(p.x, hi.x, lo.x);
       umma::tf32_split(p.y, hi.y, lo.y);
-      umma::tf32_split(p.z, hi.z, lo.z);
-      umma::tf32_split(p.w, hi.w, lo.w);
-      const uint32_t off = x_offset(0, x_row(lane, r), warp);
-      *reinterpret_cast<float4*>(smem + OFF_XH + off) = hi;
-      *reinterpret_cast<float4*>(smem + OFF_XL + off) = lo;
+      const uint32_t off = x_offset(0, x_row(lane, r), warp >> 1) + xsub;
+      *reinterpret_cast<float2*>(smem + OFF_XH + off) = hi;
+      *reinterpret_cast<float2*>(smem + OFF_XL + off) = lo;
     }
-    // the accumulator buffer and its TileInfo are free once the back stage has drained their previous use
-    if (it >= 2) umma::mbar_wait(bar_empty + 8 * buf, ((it >> 1) - 1) & 1);
-    {
-      TileInfo* info = reinterpret_cast<TileInfo*>(smem + OFF_INFO) + buf;
+    prof.lap(8);
+    // the slot's TileInfo is free once the back stage has drained the slot's previous use
+    if (it >= kSlots) umma::mbar_wait(bar_acc_empty(smem_base, slot), ((it / kSlots) - 1) & 1);
+    prof.lap(9);
+    if (tid < kRows) {
+      TileInfo* info = reinterpret_cast<TileInfo*>(smem + OFF_INFO) + slot;
       const int my = sRowVox[tid], next = tid + 1 < kRows ? sRowVox[tid + 1] : 255;
-      const unsigned last = __ballot_sync(0xffffffffu, has_row && (tid + 1 == nrows || my != next));
+      const unsigned last = __ballot_sync(0xffffffffu, tid < nrows && (tid + 1 == nrows || my != next));
       if (lane == 0) info->last_mask[warp] = last;
       if (MODE != 0 && tid < nv) info->voxcell[tid] = sVoxCell[tid];
       if (tid == 0) {
@@ -681,14 +799,20 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
       }
     }
     umma::fence_async_smem();  // X (generic-proxy writes) -> visible to the tensor core
-    front_sync();              // also: the next tile's VFE-1 overwrites sH1T (= sP2) and sRowVox
-    if (tid == 0) {  // ---- TENSOR ----
-      umma::fence_after_sync();
-      issue_fcn_mma(smem_base, tmem_base + buf * kRows);
-      umma::mma_commit(bar_full + 8 * buf);
-      umma::mbar_arrive(bar_full + 8 * buf);  // release: publishes TileInfo to the back stage
-    }
+    __syncwarp();
+    if (lane == 0) umma::mbar_arrive(bar_x_full(smem_base));  // 16 warps -> the tensor warp issues this tile's MMAs
+    cp_async_wait_all();  // the next tile's rows (group 2), issued a whole tile ago
+    front_sync();  // publishes them; also: the next tile's VFE-1 overwrites sH1T (= sP2) and sRowVox
+    prof.lap(10);
     cur = nxt;
+    nxt = nxt2;
+  }
+  if (prof.dst) {
+    prof.acc[0] = 0;
+    for (int i = 1; i <= 10; ++i) prof.acc[0] += prof.acc[i];
+    prof.acc[14] = it;
+    prof.flush(0, 10);
+    prof.flush(14, 14);
   }
   asm volatile("bar.sync 3, %0;" ::"n"(kFrontThreads + kBackThreads) : "memory");
 }
@@ -713,14 +837,14 @@ static cudaError_t launch_vfe_mode(const VfeSmall& p, const float* wblob, const 
                                    int sm_count, cudaStream_t st) {
   cudaError_t err = cudaFuncSetAttribute(vfe_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (err != cudaSuccess) return err;
-  // persistent: one CTA per SM (front 8 warps, back 4 warps, writers 4 warps), tiles strided over the CTAs
+  // persistent: one CTA per SM (3 writer warps, 1 tensor warp, 4 back warps, 8 front warps), tiles strided over the CTAs
   vfe_kernel<MODE><<<sm_count, kCtaThreads, kSmemBytes, st>>>(p, wblob, prob, out);
   return cudaGetLastError();
 }
 
 cudaError_t launch_vfe(const VfeSmall& p, const float* wblob, const VfeProblem& prob, float* voxel_feat, int sm_count,
-                       cudaStream_t st, int* launches) {
-  const VfeOutput out{voxel_feat, nullptr, nullptr, nullptr, nullptr, 0};
+                       cudaStream_t st, int* launches, long long* prof) {
+  const VfeOutput out{voxel_feat, nullptr, nullptr, nullptr, nullptr, 0, prof};
   ++*launches;
   return launch_vfe_mode<0>(p, wblob, prob, out, sm_count, st);
 }
@@ -728,7 +852,8 @@ cudaError_t launch_vfe(const VfeSmall& p, const float* wblob, const VfeProblem& 
 cudaError_t launch_vfe_to_grid(const VfeSmall& p, const float* wblob, const VfeProblem& prob, const Workspace& w,
                                const Geom& g, int n_sweeps, int grid_dtype, void* grid, int sm_count, cudaStream_t st,
                                int* launches) {
-  const VfeOutput out{nullptr, grid, w.voxel_cell, w.cell_voxel, w.c_empty, (long long)n_sweeps * g.cells};
+  const VfeOutput out{nullptr, grid, w.voxel_cell, w.cell_voxel, w.c_empty, (long long)n_sweeps * g.cells,
+                      reinterpret_cast<long long*>(w.trace)};
   ++*launches;
   return grid_dtype == LISEC_F32 ? launch_vfe_mode<1>(p, wblob, prob, out, sm_count, st)
                                  : launch_vfe_mode<2>(p, wblob, prob, out, sm_count, st);
