@@ -60,7 +60,8 @@ constexpr int kRows = kVfeThreads;     // 256 rows per tile
 constexpr int kVox = kVfeThreads / 2;  // 128 voxels per tile: a non-full voxel has >= 2 rows, a full one T >= 2
 constexpr int PR = kRows + 4;          // float pitch of row-indexed k-major tiles (16-byte aligned rows, 4-bank skew)
 constexpr int PV = kVox + 4;           // float pitch of voxel-indexed k-major tiles
-constexpr int QS = 36;                 // float stride of a voxel's 32-channel row in sQ / sP2
+constexpr int QS = 34;                 // float stride of a voxel's 32-channel row in sQ / sP2: 8-byte accesses at
+                                       // v * QS + 2 * warp fall on bank pair (v + warp) % 16 -> consecutive voxels spread
 constexpr int kBgCells = 32;           // cells in the writers' TMA source tile
 
 // tensor-core operands (K-major, 128-byte swizzle; see umma.cuh)
@@ -84,8 +85,9 @@ constexpr int OFF_W2P = OFF_W3L + 2 * kWSlab;       // [16][32]
 constexpr int OFF_W2X = OFF_W2P + 16 * 32 * 4;      // [16][32]
 constexpr int OFF_H1T = OFF_W2X + 16 * 32 * 4;      // [16][PR]   dense outputs of VFE-1, k-major
 constexpr int OFF_P1T = OFF_H1T + 16 * PR * 4;      // [16][PV]   pooled VFE-1
-constexpr int OFF_P2 = OFF_H1T;                     // [kVox][QS] pooled VFE-2, reuses H1T+P1T (dead by then)
 constexpr int OFF_Q = OFF_P1T + 16 * PV * 4;        // [kVox][QS] pooled-half products of dense_1
+constexpr int OFF_P2 = OFF_Q;                       // [kVox][QS] pooled VFE-2: same place — warp w alone reads and
+                                                    // writes columns 2w, 2w+1 of both, so a __syncwarp orders them
 constexpr int OFF_ROWVOX = OFF_Q + kVox * QS * 4;   // uint8[kRows] local voxel of each tile row
 constexpr int OFF_VOXCELL = OFF_ROWVOX + kRows;     // int[kVox] cell of each tile voxel, front stage's own copy
 constexpr int OFF_FSTAGE = OFF_VOXCELL + kVox * 4;  // float[kRows][6] the NEXT tile's feature rows (cp.async prefetch)
@@ -95,7 +97,6 @@ constexpr int OFF_BAR = OFF_INFO + kSlots * (int)sizeof(TileInfo);  // mbarriers
 constexpr int OFF_TMEM_SLOT = OFF_BAR + 8 * (2 * kSlots + 1);       // TMEM base address (written by tcgen05.alloc)
 constexpr int OFF_BG = (OFF_TMEM_SLOT + 8 + 127) & ~127;            // kBgCells x 64 channels of c_empty: the TMA source tile
 constexpr int kSmemBytes = OFF_BG + kBgCells * 64 * 4;  // dynamic shared memory starts 1 KB-aligned (no static smem)
-static_assert(kVox * QS * 4 <= 16 * PR * 4 + 16 * PV * 4, "P2 must fit in H1T+P1T");
 static_assert(kSmemBytes <= 232448, "one CTA per SM, 227 KB opt-in limit");
 static_assert(OFF_W3H % 1024 == 0 && OFF_XL % 1024 == 0, "operand slabs are 1 KB-aligned");
 static_assert(sizeof(TileInfo) % 16 == 0 && OFF_INFO % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
@@ -720,16 +721,38 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
     prof.lap(2);
 
     // ---- VFE-2: Dense(32->32) + BN + ReLU on concat[pooled, pointwise] (addVFELayer(., 32, 64), :232) ----
-    {  // pooled half, once per voxel: Q2[128 x 32] = P1[128 x 16] * W2p; 4 voxels x 2 channels per thread
+    {  // pooled half, once per voxel: Q2[128 x 32] = P1[128 x 16] * W2p. A thread takes voxels lane, lane + 32, lane + 64,
+       // lane + 96 (not 4 consecutive ones: its float2 stores into sQ are then conflict-free) x 2 channels.
       float acc[4][2];
 #pragma unroll
       for (int r = 0; r < 4; ++r) acc[r][0] = acc[r][1] = 0.f;
-      tile_gemm_blocked<4, 2, 16>(sP1T, PV, 0, lane * 4, sW2P, 32, 2 * warp, acc);
+#pragma unroll 1
+      for (int kb = 0; kb < 16; kb += 4) {
+        float blk[4][2];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) blk[r][0] = blk[r][1] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const float* a = sP1T + (kb + kk) * PV + lane;
+          const float2 b = *reinterpret_cast<const float2*>(sW2P + (kb + kk) * 32 + 2 * warp);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const float av = a[32 * r];
+            blk[r][0] = fmaf(av, b.x, blk[r][0]);
+            blk[r][1] = fmaf(av, b.y, blk[r][1]);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          acc[r][0] += blk[r][0];
+          acc[r][1] += blk[r][1];
+        }
+      }
 #pragma unroll
       for (int r = 0; r < 4; ++r)
-        *reinterpret_cast<float2*>(sQ + (lane * 4 + r) * QS + 2 * warp) = make_float2(acc[r][0], acc[r][1]);
+        *reinterpret_cast<float2*>(sQ + (lane + 32 * r) * QS + 2 * warp) = make_float2(acc[r][0], acc[r][1]);
     }
-    front_sync();
+    __syncwarp();  // columns 2 warp, 2 warp + 1 of sQ are this warp's own: no block barrier
     prof.lap(3);
     float h2[8][2];  // rows 8 lane .. 8 lane + 7, channels 2 warp, 2 warp + 1 of the VFE-2 pointwise output
     {  // rows: 8x2 tile per thread, accumulators start at the voxel's pooled-half product
@@ -762,13 +785,12 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
       *reinterpret_cast<float2*>(smem + OFF_XH + off) = hi;
       *reinterpret_cast<float2*>(smem + OFF_XL + off) = lo;
     }
-    front_sync();  // every warp is done with sH1T (A operand) and sQ: sP2 may now overwrite sH1T/sP1T
+    __syncwarp();  // every lane has taken its accumulator seeds out of sQ: sP2 (same columns) may overwrite them
     prof.lap(6);
     pool_lane_rows<2>(h2, meta, [&](int v, const float(&x)[2]) {
       if (v < nv) *reinterpret_cast<float2*>(sP2 + v * QS + 2 * warp) = make_float2(x[0], x[1]);
     });
-    cp_async_wait_all_but_last();  // this thread's sVoxCell word (group 1); the rows may still be in flight
-    front_sync();
+    __syncwarp();
     prof.lap(7);
 
     // ---- FCN input, pooled half: Concatenate([pooled, pointwise]) (:164-165) = the voxel's pooled row, repeated ----
@@ -786,6 +808,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
     // the slot's TileInfo is free once the back stage has drained the slot's previous use
     if (it >= kSlots) umma::mbar_wait(bar_acc_empty(smem_base, slot), ((it / kSlots) - 1) & 1);
     prof.lap(9);
+    cp_async_wait_all_but_last();  // this thread's own sVoxCell word (group 1); the rows may still be in flight
     if (tid < kRows) {
       TileInfo* info = reinterpret_cast<TileInfo*>(smem + OFF_INFO) + slot;
       const int my = sRowVox[tid], next = tid + 1 < kRows ? sRowVox[tid + 1] : 255;
@@ -802,7 +825,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
     __syncwarp();
     if (lane == 0) umma::mbar_arrive(bar_x_full(smem_base));  // 16 warps -> the tensor warp issues this tile's MMAs
     cp_async_wait_all();  // the next tile's rows (group 2), issued a whole tile ago
-    front_sync();  // publishes them; also: the next tile's VFE-1 overwrites sH1T (= sP2) and sRowVox
+    front_sync();  // publishes them; also: the next tile's VFE-1 overwrites sH1T and sRowVox, its Q2 overwrites sQ
     prof.lap(10);
     cur = nxt;
     nxt = nxt2;
