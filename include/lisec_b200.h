@@ -162,8 +162,8 @@ int32_t lisec_vfe_forward(lisec_handle* h, float* voxel_feat, void* stream);
 int32_t lisec_scatter_dense(lisec_handle* h, const float* voxel_feat, void* grid, void* stream);
 
 /* [async] lisec_vfe_forward + lisec_scatter_dense as ONE kernel on the grouping of the last lisec_voxelize(): the voxel
- * rows go straight from registers to their cells while a writer warpgroup streams c_empty into the empty cells by TMA
- * bulk stores; no voxel_feat round trip, every grid element written exactly once. */
+ * rows go straight from the tensor-core accumulators to their cells while writer warps stream c_empty into the empty
+ * cells by TMA bulk stores; no voxel_feat round trip, every grid element written exactly once. */
 int32_t lisec_vfe_scatter_fused(lisec_handle* h, void* grid, void* stream);
 
 /* [async] lisec_voxelize + lisec_vfe_scatter_fused without host round trips: what
@@ -182,6 +182,10 @@ int32_t lisec_frontend_forward_host(lisec_handle* h, const void* points_host, in
  * into caller-owned pinned memory. Layout: int64[8] = {n_voxels, n_points_in_range, n_vfe_rows, n_vfe_tiles,
  * n_dropped_nonfinite, n_dropped_out_of_range, 0, 0}, then int32[n_sweeps+1] = exclusive prefix of voxels per sweep. */
 int32_t lisec_voxel_counts_async(lisec_handle* h, void* pinned_out, int64_t pinned_bytes, void* stream);
+
+/* Device time (ms, CUDA events on the call's stream) of the fused VFE + grid kernel inside the last
+ * lisec_frontend_forward* / lisec_vfe_scatter_fused call. Synchronises on that kernel's end. */
+int32_t lisec_last_fused_kernel_ms(lisec_handle* h, float* ms);
 
 /* Debug aid, inert unless the environment had LISEC_TRACE=1 at lisec_create(): cycle counters of the VFE kernel's pipeline
  * stages in the last VFE launch, int64 [256 CTAs][16 slots] (slot meaning: lisec_b200/csrc/vfe.cu). Synchronous. */

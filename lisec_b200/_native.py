@@ -92,6 +92,7 @@ SIGNATURES = {
     "lisec_frontend_forward": (C.c_int32, [_H, _VP, C.c_int32, _I64P, C.c_int32, _VP, _VP]),
     "lisec_frontend_forward_host": (C.c_int32, [_H, _VP, C.c_int32, _I64P, C.c_int32, _VP, _VP]),
     "lisec_voxel_counts_async": (C.c_int32, [_H, _VP, C.c_int64, _VP]),
+    "lisec_last_fused_kernel_ms": (C.c_int32, [_H, _FP]),
     "lisec_debug_trace": (C.c_int32, [_H, _I64P, C.c_int64]),
     "lisec_last_launch_count": (C.c_int32, [_H]),
 }

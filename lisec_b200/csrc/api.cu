@@ -40,6 +40,9 @@ struct lisec_handle {
   cudaEvent_t ev_free[2] = {nullptr, nullptr};    // the kernels that read staging[b] have been enqueued and finished
   void* staging2 = nullptr;                       // second staging buffer (the first is ws.staging)
   int staging_idx = 0;
+  // CUDA events around the fused VFE + grid kernel of the last fused call (bench.py's live roofline figure)
+  cudaEvent_t ev_kernel[2] = {nullptr, nullptr};
+  bool kernel_timed = false;
   char err[512];
 };
 
@@ -241,6 +244,7 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
     LISEC_CUDA(h, dev_alloc(h, &w.trace, (size_t)kTraceCtas * kTraceSlots));
     LISEC_CUDA(h, cudaMemset(w.trace, 0, sizeof(unsigned long long) * kTraceCtas * kTraceSlots));
   }
+  for (int b = 0; b < 2; ++b) LISEC_CUDA(h, cudaEventCreate(&h->ev_kernel[b]));
   LISEC_CUDA(h, dev_alloc(h, &w.empty_desc, (size_t)16));
   // the one-voxel problem whose VFE output is c_empty: 0 kept points, 1 pad row, 1 tile
   // layout: tile_first {0,1} | tile_row0 {0,1} | n_tiles (int64) 1 | row_voxel {0} | pad | row_feat 6 x 0.f
@@ -258,6 +262,8 @@ void lisec_destroy(lisec_handle* h) {
   free_workspace(h->ws);
   if (h->staging2) cudaFree(h->staging2);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (int b = 0; b < 2; ++b)
+    if (h->ev_kernel[b]) cudaEventDestroy(h->ev_kernel[b]);
   for (int b = 0; b < 2; ++b) {
     if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
     if (h->ev_free[b]) cudaEventDestroy(h->ev_free[b]);
@@ -428,9 +434,12 @@ int32_t lisec_scatter_dense(lisec_handle* h, const float* voxel_feat, void* grid
 static int fused_stage(lisec_handle* h, void* grid, cudaStream_t st) {
   LISEC_CUDA(h, launch_row_features(h->last_points, h->last_dtype, h->geom, h->ws, h->max_voxels, st, &h->launches));
   const VfeProblem prob{h->ws.tile_first, h->ws.tile_row0, h->ws.row_voxel, h->ws.row_feat, h->ws.totals + TOT_TILES};
-  // one kernel: VFE on the FP32 pipe, voxel rows and the c_empty background written to the grid concurrently
+  // one kernel: VFE (FP32 pipe + tensor core), voxel rows and the c_empty background written to the grid concurrently
+  LISEC_CUDA(h, cudaEventRecord(h->ev_kernel[0], st));
   LISEC_CUDA(h, launch_vfe_to_grid(h->params, h->ws.vfe_w, prob, h->ws, h->geom, h->last_so.n, h->cfg.grid_dtype, grid,
                                    h->sm_count, st, &h->launches));
+  LISEC_CUDA(h, cudaEventRecord(h->ev_kernel[1], st));
+  h->kernel_timed = true;
   return LISEC_OK;
 }
 
@@ -495,6 +504,16 @@ int32_t lisec_frontend_forward_host(lisec_handle* h, const void* points_host, in
   rc = frontend(h, staging, dtype, so, grid, st);
   if (rc) return rc;
   LISEC_CUDA(h, cudaEventRecord(h->ev_free[b], st));
+  return LISEC_OK;
+}
+
+int32_t lisec_last_fused_kernel_ms(lisec_handle* h, float* ms) {
+  if (!h) return LISEC_ERR_BAD_ARG;
+  if (!ms) return fail(h, LISEC_ERR_BAD_ARG, "ms is NULL");
+  if (!h->kernel_timed) return fail(h, LISEC_ERR_STATE, "no fused call has run on this handle");
+  LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
+  LISEC_CUDA(h, cudaEventSynchronize(h->ev_kernel[1]));
+  LISEC_CUDA(h, cudaEventElapsedTime(ms, h->ev_kernel[0], h->ev_kernel[1]));
   return LISEC_OK;
 }
 

@@ -240,6 +240,14 @@ class Frontend:
             self._check(self._lib.lisec_scatter_dense(self._h, _ptr(voxel_feat), _ptr(out), self._stream()))
         return out
 
+    @property
+    def last_fused_kernel_ms(self) -> float:
+        """Device time of the fused VFE + grid kernel inside the last fused call (CUDA events on its stream)."""
+        ms = C.c_float(0.0)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.lisec_last_fused_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
     def vfe_scatter_fused(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """VFE + dense grid in one kernel, on the grouping of the last voxelize()."""
         if out is None:

@@ -208,14 +208,16 @@ def test_fused_forward_equals_modular_and_host_entry(fe):
     pts, off = synth.sweep_batch(3, 40_000, seed0=9)
     fe.voxelize(pts, off)
     modular = fe.scatter(fe.vfe())
-    fused = fe.forward(torch.from_numpy(pts).cuda(), off)
+    poison = lambda: torch.full_like(modular, float("nan"))  # a cell nobody writes stays NaN and fails the compare
+    fused = fe.forward(torch.from_numpy(pts).cuda(), off, out=poison())
     assert torch.equal(fused, modular)
     fe.voxelize(pts, off)
-    assert torch.equal(fe.vfe_scatter_fused(), modular)  # the fused stage alone, on an existing grouping
+    assert torch.equal(fe.vfe_scatter_fused(out=poison()), modular)  # the fused stage alone, on an existing grouping
     pinned = torch.from_numpy(pts).pin_memory()
-    host = fe.forward_host(pinned, off)
+    host = fe.forward_host(pinned, off, out=poison())
     torch.cuda.synchronize()
     assert torch.equal(host, modular)
+    assert fe.last_fused_kernel_ms > 0.0
     assert fe.last_launch_count == 8  # point, 3 scans, fill, order, row features, fused VFE + grid
 
 
