@@ -121,4 +121,29 @@ cudaError_t launch_grid_write(const Geom& g, int n_sweeps, int c3, int grid_dtyp
 
 int vfe_rows_per_tile(int T);
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------------
+// The path is a chain of short kernels on one stream. Each is launched with programmatic stream serialization: its
+// CTAs may be scheduled as soon as every CTA of its predecessor has executed pdl_launch_dependents() (first statement
+// of every kernel), and pdl_wait() then blocks until the predecessor has completed and its writes are visible. The
+// launch latency and any set-up a kernel does before pdl_wait() overlap the predecessor's tail.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 }  // namespace lisec

@@ -382,6 +382,8 @@ __global__ void __launch_bounds__(256) row_features_kernel(const PT* __restrict_
                                                            const int* __restrict__ list_sorted,
                                                            const long long* __restrict__ totals,
                                                            float* __restrict__ row_feat) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= totals[TOT_VOXELS]) return;
   const int s = voxel_start[v];
@@ -551,13 +553,11 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
     vfe_kernel(const __grid_constant__ VfeSmall P, const float* __restrict__ wblob,
                const __grid_constant__ VfeProblem prob, const __grid_constant__ VfeOutput out) {
   extern __shared__ __align__(1024) unsigned char smem[];  // the operand slabs need 1 KB alignment (128-byte swizzle)
+  pdl_launch_dependents();  // (the set-up below touches nothing its predecessors write; pdl_wait() follows it)
   const int warp_in_cta = threadIdx.x >> 5;
   const uint32_t smem_base = umma::smem_u32(smem);
   if (smem_base & 1023u) __trap();
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM_SLOT);
-  const int n_tiles = (int)*prob.n_tiles;
-  // tiles are strided over the CTAs: this one owns ordinals it = 0 .. my_tiles-1, tile blockIdx.x + it * gridDim.x
-  const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   // ---- one-time setup: weights, barriers, TMEM ----
   {
@@ -586,6 +586,10 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // from here on: the grouping, the row features and the occupancy map of this call
+  const int n_tiles = (int)*prob.n_tiles;
+  // tiles are strided over the CTAs: this one owns ordinals it = 0 .. my_tiles-1, tile blockIdx.x + it * gridDim.x
+  const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (warp_in_cta < kWriterWarps) {  // ---- WRITER ----
     if (MODE == 1)
@@ -845,14 +849,17 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
 cudaError_t launch_row_features(const void* pts, int pts_dtype, const Geom& g, const Workspace& w, long long max_voxels,
                                 cudaStream_t st, int* launches) {
   const unsigned blocks = (unsigned)((max_voxels + 255) / 256);  // threads past the device-side voxel count exit
+  cudaError_t err;
   if (pts_dtype == LISEC_F32)
-    row_features_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(pts), g.T, w.voxel_start, w.row_start,
-                                                       w.list_sorted, w.totals, w.row_feat);
+    err = launch_pdl(row_features_kernel<float>, blocks, 256, 0, st, static_cast<const float*>(pts), g.T,
+                     (const int*)w.voxel_start, (const int*)w.row_start, (const int*)w.list_sorted,
+                     (const long long*)w.totals, w.row_feat);
   else
-    row_features_kernel<double><<<blocks, 256, 0, st>>>(static_cast<const double*>(pts), g.T, w.voxel_start,
-                                                        w.row_start, w.list_sorted, w.totals, w.row_feat);
+    err = launch_pdl(row_features_kernel<double>, blocks, 256, 0, st, static_cast<const double*>(pts), g.T,
+                     (const int*)w.voxel_start, (const int*)w.row_start, (const int*)w.list_sorted,
+                     (const long long*)w.totals, w.row_feat);
   ++*launches;
-  return cudaGetLastError();
+  return err;
 }
 
 template <int MODE>
@@ -861,8 +868,7 @@ static cudaError_t launch_vfe_mode(const VfeSmall& p, const float* wblob, const 
   cudaError_t err = cudaFuncSetAttribute(vfe_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (err != cudaSuccess) return err;
   // persistent: one CTA per SM (3 writer warps, 1 tensor warp, 4 back warps, 8 front warps), tiles strided over the CTAs
-  vfe_kernel<MODE><<<sm_count, kCtaThreads, kSmemBytes, st>>>(p, wblob, prob, out);
-  return cudaGetLastError();
+  return launch_pdl(vfe_kernel<MODE>, sm_count, kCtaThreads, kSmemBytes, st, p, wblob, prob, out);
 }
 
 cudaError_t launch_vfe(const VfeSmall& p, const float* wblob, const VfeProblem& prob, float* voxel_feat, int sm_count,

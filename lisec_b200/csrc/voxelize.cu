@@ -84,6 +84,8 @@ __global__ void __launch_bounds__(256) point_pass_kernel(const PT* __restrict__ 
                                                          const __grid_constant__ Geom g,
                                                          int* __restrict__ cell_of_point, int* __restrict__ count,
                                                          unsigned long long* __restrict__ totals) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long p0 = grp * 4;
   PT v[12];
@@ -206,6 +208,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const int* __
                                                                    int T, int nblocks,
                                                                    int* __restrict__ block_sums) {
   __shared__ Tri smem[kScanThreads / 32 + 1];
+  pdl_launch_dependents();
+  pdl_wait();
   const long long base = ((long long)blockIdx.x * kScanThreads + threadIdx.x) * kScanItems;
   int c[kScanItems];
   load_counts(count, base, ncells, c);
@@ -228,6 +232,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_spine_kernel(int* __restric
                                                                   int* __restrict__ row_start,
                                                                   int* __restrict__ sweep_voxel_start) {
   __shared__ Tri smem[kScanThreads / 32 + 1];
+  pdl_launch_dependents();
+  pdl_wait();
   Tri carry{0, 0, 0};
   for (int b0 = 0; b0 < nblocks; b0 += kScanThreads) {
     const int b = b0 + threadIdx.x;
@@ -263,6 +269,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_down_kernel(const int* __re
                                                                  int* __restrict__ row_start,
                                                                  int* __restrict__ sweep_voxel_start) {
   __shared__ Tri smem[kScanThreads / 32 + 1];
+  pdl_launch_dependents();
+  pdl_wait();
   const long long base = ((long long)blockIdx.x * kScanThreads + threadIdx.x) * kScanItems;
   int c[kScanItems];
   load_counts(count, base, ncells, c);
@@ -306,6 +314,8 @@ __global__ void __launch_bounds__(256) fill_pass_kernel(const int* __restrict__ 
                                                         const int* __restrict__ voxel_start,
                                                         int* __restrict__ count, int* __restrict__ list_unsorted,
                                                         int* __restrict__ entry_voxel) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long p0 = grp * 4;
   int cell[4] = {-1, -1, -1, -1};
@@ -347,6 +357,8 @@ __global__ void __launch_bounds__(256) order_pass_kernel(const int* __restrict__
                                                          int* __restrict__ list_sorted,
                                                          int* __restrict__ tile_first, int* __restrict__ tile_row0,
                                                          int* __restrict__ row_voxel) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long n_entries = totals[TOT_ENTRIES];
   const long long n_voxels = totals[TOT_VOXELS];
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -398,13 +410,13 @@ cudaError_t launch_point_pass(const void* pts, int pts_dtype, long long n_total,
   const unsigned blocks = (unsigned)((groups + 255) / 256);
   auto* tot = reinterpret_cast<unsigned long long*>(w.totals);
   if (pts_dtype == LISEC_F32)
-    point_pass_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(pts), n_total, so, g,
-                                                     w.cell_of_point, w.count, tot);
+    err = launch_pdl(point_pass_kernel<float>, blocks, 256, 0, st, static_cast<const float*>(pts), n_total, so, g,
+                     w.cell_of_point, w.count, tot);
   else
-    point_pass_kernel<double><<<blocks, 256, 0, st>>>(static_cast<const double*>(pts), n_total, so, g,
-                                                      w.cell_of_point, w.count, tot);
+    err = launch_pdl(point_pass_kernel<double>, blocks, 256, 0, st, static_cast<const double*>(pts), n_total, so, g,
+                     w.cell_of_point, w.count, tot);
   ++*launches;
-  return cudaGetLastError();
+  return err;
 }
 
 cudaError_t launch_cell_scan(const SweepOffsets& so, const Geom& g, Workspace& w, int scan_blocks_cap,
@@ -412,29 +424,33 @@ cudaError_t launch_cell_scan(const SweepOffsets& so, const Geom& g, Workspace& w
   const long long ncells = (long long)so.n * g.cells;
   const int nblocks = (int)((ncells + kScanTile - 1) / kScanTile);
   if (nblocks > scan_blocks_cap) return cudaErrorInvalidValue;
-  scan_reduce_kernel<<<nblocks, kScanThreads, 0, st>>>(w.count, ncells, g.T, nblocks, w.block_sums);
-  scan_spine_kernel<<<1, kScanThreads, 0, st>>>(w.block_sums, nblocks, so.n, w.totals, w.voxel_start,
-                                                w.row_start, w.sweep_voxel_start);
-  scan_down_kernel<<<nblocks, kScanThreads, 0, st>>>(w.count, ncells, g.T, g.cells, nblocks, w.block_sums,
-                                                     w.cell_voxel, w.voxel_cell, w.voxel_start, w.row_start,
-                                                     w.sweep_voxel_start);
+  cudaError_t err = launch_pdl(scan_reduce_kernel, nblocks, kScanThreads, 0, st, (const int*)w.count, ncells, g.T,
+                               nblocks, w.block_sums);
+  if (err == cudaSuccess)
+    err = launch_pdl(scan_spine_kernel, 1, kScanThreads, 0, st, w.block_sums, nblocks, so.n, w.totals, w.voxel_start,
+                     w.row_start, w.sweep_voxel_start);
+  if (err == cudaSuccess)
+    err = launch_pdl(scan_down_kernel, nblocks, kScanThreads, 0, st, (const int*)w.count, ncells, g.T, g.cells, nblocks,
+                     (const int*)w.block_sums, w.cell_voxel, w.voxel_cell, w.voxel_start, w.row_start,
+                     w.sweep_voxel_start);
   *launches += 3;
-  return cudaGetLastError();
+  return err;
 }
 
 cudaError_t launch_fill_and_order(long long n_total, const Geom& g, int rows_per_tile, Workspace& w,
                                   cudaStream_t st, int* launches) {
   if (n_total == 0) return cudaSuccess;
   const long long groups = (n_total + 3) / 4;
-  fill_pass_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(w.cell_of_point, n_total, w.cell_voxel,
-                                                                     w.voxel_start, w.count, w.list_unsorted,
-                                                                     w.entry_voxel);
+  cudaError_t err = launch_pdl(fill_pass_kernel, (unsigned)((groups + 255) / 256), 256, 0, st,
+                               (const int*)w.cell_of_point, n_total, (const int*)w.cell_voxel,
+                               (const int*)w.voxel_start, w.count, w.list_unsorted, w.entry_voxel);
   // entries <= points; threads beyond the device-side totals exit
-  order_pass_kernel<<<(unsigned)((n_total + 255) / 256), 256, 0, st>>>(
-      w.list_unsorted, w.entry_voxel, w.voxel_start, w.row_start, g.T, rows_per_tile, w.totals, w.list_sorted,
-      w.tile_first, w.tile_row0, w.row_voxel);
+  if (err == cudaSuccess)
+    err = launch_pdl(order_pass_kernel, (unsigned)((n_total + 255) / 256), 256, 0, st, (const int*)w.list_unsorted,
+                     (const int*)w.entry_voxel, (const int*)w.voxel_start, (const int*)w.row_start, g.T, rows_per_tile,
+                     w.totals, w.list_sorted, w.tile_first, w.tile_row0, w.row_voxel);
   *launches += 2;
-  return cudaGetLastError();
+  return err;
 }
 
 }  // namespace lisec
