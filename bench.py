@@ -82,6 +82,12 @@ def run_reference(args):
     pack = synthetic_vfe_pack(0)
     pts = synth.lyft_like_sweep(POINTS_PER_SWEEP, seed=0)
     cores = os.cpu_count() or 1
+    try:  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host thread it can
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
     frac, slab = 0.1, 50
     for _ in range(args.warmup):
         cpu_reference_time_per_sweep(pts, frac / 4, 10, pack)

@@ -8,7 +8,7 @@
 // address; slabs are 1 KB-aligned). One MMA has K = 8: k-step j inside a slab is the same descriptor advanced by 32
 // bytes. Measured with tools/umma_probe.cu (M=64, N=256, K=64): exact placement, 3xTF32 error 1.1e-6 of rms.
 // An MN-major tf32 operand needs the separate SWIZZLE_128B_BASE32B layout (plain SWIZZLE_128B MN-major yields zeros for
-// 32-bit types; probe variants 0/1) — not used here.
+// 32-bit types; probe variants 0/1, whose helpers live in the probe) — not used here.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -18,12 +18,6 @@ namespace lisec {
 namespace umma {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// byte offset of element (mn, k) inside an operand whose k-atoms are k_atom_stride bytes apart
-__device__ __host__ __forceinline__ uint32_t op_offset(int mn, int k, uint32_t k_atom_stride) {
-  return (uint32_t)(k >> 3) * k_atom_stride + (uint32_t)(mn >> 5) * 1024u + (uint32_t)(k & 7) * 128u +
-         (uint32_t)((((mn & 31) >> 2) ^ (k & 7)) << 4) + (uint32_t)(mn & 3) * 4u;
-}
 
 // byte offset of element (mn, k) of a K-major SW128 operand whose 32-channel slabs are slab_bytes apart
 __device__ __host__ __forceinline__ uint32_t kmajor_offset(int mn, int k, uint32_t slab_bytes) {
@@ -43,29 +37,6 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
 // Instruction descriptor for kind::tf32, float32 accumulation, both operands K-major.
 __device__ __host__ constexpr uint32_t make_idesc_tf32_k(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// Shared-memory matrix descriptor (64 bit): start address, leading / stride byte offsets (all >> 4), version 1
-// (Blackwell), layout type 2 = SWIZZLE_128B. For an MN-major swizzled operand the "leading" offset is the distance
-// between mn-atoms (1 KB here) and the "stride" offset the distance between k-atoms.
-__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t mn_atom_stride,
-                                                       uint32_t k_atom_stride) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
-  d |= (uint64_t)((mn_atom_stride >> 4) & 0x3fff) << 16;
-  d |= (uint64_t)((k_atom_stride >> 4) & 0x3fff) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
-  return d;
-}
-
-// Instruction descriptor for kind::tf32, float32 accumulation, both operands MN-major.
-__device__ __host__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {
-  return (1u << 4)                      // D format: F32
-         | (2u << 7) | (2u << 10)       // A, B format: TF32
-         | (1u << 15) | (1u << 16)      // A, B major: MN
-         | ((uint32_t)(N >> 3) << 17)   // N / 8
-         | ((uint32_t)(M >> 4) << 24);  // M / 16
 }
 
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.

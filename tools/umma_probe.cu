@@ -13,6 +13,37 @@
 
 using namespace lisec::umma;
 
+// ---- MN-major / plain SWIZZLE_128B variants (hypotheses 0 and 1: they yield zeros for tf32) ----
+// byte offset of element (mn, k) inside an operand whose k-atoms are k_atom_stride bytes apart
+__device__ __host__ __forceinline__ uint32_t op_offset(int mn, int k, uint32_t k_atom_stride) {
+  return (uint32_t)(k >> 3) * k_atom_stride + (uint32_t)(mn >> 5) * 1024u + (uint32_t)(k & 7) * 128u +
+         (uint32_t)((((mn & 31) >> 2) ^ (k & 7)) << 4) + (uint32_t)(mn & 3) * 4u;
+}
+
+// Shared-memory matrix descriptor (64 bit): start address, leading / stride byte offsets (all >> 4), version 1
+// (Blackwell), layout type 2 = SWIZZLE_128B. For an MN-major swizzled operand the "leading" offset is the distance
+// between mn-atoms (1 KB here) and the "stride" offset the distance between k-atoms.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t mn_atom_stride,
+                                                       uint32_t k_atom_stride) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)((mn_atom_stride >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((k_atom_stride >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
+// Instruction descriptor for kind::tf32, float32 accumulation, both operands MN-major.
+__device__ __host__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {
+  return (1u << 4)                      // D format: F32
+         | (2u << 7) | (2u << 10)       // A, B format: TF32
+         | (1u << 15) | (1u << 16)      // A, B major: MN
+         | ((uint32_t)(N >> 3) << 17)   // N / 8
+         | ((uint32_t)(M >> 4) << 24);  // M / 16
+}
+
+
 constexpr int N = 256, K = 64, M = 64;
 constexpr uint32_t X_KSTRIDE = (N / 32) * 1024;  // 8 KB between k-atoms of X
 constexpr uint32_t W_KSTRIDE = (M / 32) * 1024;  // 2 KB between k-atoms of W^T
@@ -26,7 +57,7 @@ __device__ __host__ inline uint32_t kmaj_offset(int mn, int k, uint32_t slab) {
   return (uint32_t)(k >> 5) * slab + (uint32_t)mn * 128u + (uint32_t)((((k & 31) >> 2) ^ (mn & 7)) << 4) +
          (uint32_t)(k & 3) * 4u;
 }
-__device__ inline uint64_t make_desc_k_sw128(uint32_t smem_addr) {
+__device__ inline uint64_t probe_desc_k_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
   d |= (uint64_t)1 << 16;             // LBO (unused for swizzled K-major)
@@ -101,7 +132,7 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ X, const 
     const uint32_t idesc = swap == 2 ? (make_idesc_tf32_mn(M, N) & ~((1u << 15) | (1u << 16))) : make_idesc_tf32_mn(M, N);
     auto desc = [&](unsigned char* base, int kb, uint32_t kstride) {
       if (swap == 2)  // K-major: k-block kb/4 is a slab of (kstride/1024*32) rows x 128 B, k-step inside it = +32 B
-        return make_desc_k_sw128(smem_u32(base) + (kb >> 2) * (kstride / 1024 * 32 * 128) + (kb & 3) * 32);
+        return probe_desc_k_sw128(smem_u32(base) + (kb >> 2) * (kstride / 1024 * 32 * 128) + (kb & 3) * 32);
       const uint32_t addr = smem_u32(base) + kb * kstride;
       return swap ? make_desc_mn_sw128(addr, kstride, 1024) : make_desc_mn_sw128(addr, 1024, kstride);
     };
