@@ -309,3 +309,80 @@ def test_error_behaviour(fe):
         f.forward(np.zeros((10, 3), np.float32), [0, 10])  # weights not set
     assert e.value.status == -5
     f.close()
+
+
+def test_config4_million_point_cloud(fe):
+    """BASELINE config 4: one aggregated ~1 M-point cloud, a large share of voxels at the T cap (no pad row, the
+    first-35 rule decides which points count)."""
+    pack = synthetic_vfe_pack(0)
+    pts = synth.saturated_cloud(1_000_000, n_sweeps=10, theta=3.5)
+    vs, ref = check_grouping(fe, pts, [0, len(pts)])
+    assert int((ref["counts"] >= 35).sum()) > 1000  # the cap really is exercised
+    got = fe.vfe().cpu().numpy()
+    want = O.vfe_forward(ref["features"].astype(np.float32), pack, np.float64)
+    assert within(got, want) <= REL_TOL
+
+
+def test_full_voxels_and_tile_boundaries(fe):
+    """Voxels with exactly T, T-1 and T+1 points back to back (with / without the virtual pad row), enough of them
+    that many 256-row tiles end on a full voxel; plus single-point voxels so that tiles also end on 2-row voxels."""
+    rng = np.random.default_rng(11)
+    pts = []
+    k = 0
+    for ix in range(-60, 60):
+        for iy in range(-40, 40, 2):
+            n = (34, 35, 36, 1, 70)[k % 5]
+            k += 1
+            base = np.array([ix * 0.5 + 0.05, iy * 0.25 + 0.02, 0.55], np.float32)
+            pts.append(base + rng.uniform(0, [0.4, 0.2, 0.15], size=(n, 3)).astype(np.float32))
+    pts = np.concatenate(pts).astype(np.float32)
+    pts = pts[rng.permutation(len(pts))]
+    pack = synthetic_vfe_pack(2)
+    fe.set_weights(pack)
+    vs, ref = check_grouping(fe, pts, [0, len(pts)])
+    assert set(np.unique(ref["counts"])) >= {1, 34, 35, 36, 70}
+    got = fe.vfe().cpu().numpy()
+    want = O.vfe_forward(ref["features"].astype(np.float32), pack, np.float64)
+    assert within(got, want) <= REL_TOL
+    grid = fe.forward(pts, [0, len(pts)], out=torch.full((1, 8, 200, 400, 64), float("nan"), device="cuda"))
+    c = vs.coords.long()
+    assert torch.equal(grid[c[:, 0], c[:, 1], c[:, 2], c[:, 3]], torch.from_numpy(got).cuda())
+    assert not bool(torch.isnan(grid).any())
+    fe.set_weights(synthetic_vfe_pack(0))
+
+
+@pytest.mark.parametrize("T", [2, 8, 64])
+def test_other_sample_sizes_small_grid(T):
+    """sampleSize is a parameter of VFE_preprocessing (model_training.py:112): the tile packing (rows per tile =
+    256 - T + 1), the T cap and the pad-row rule must hold for any supported T."""
+    from lisec_b200 import Frontend
+
+    args = dict(xSize=0.5, ySize=0.25, zSize=0.25, sampleSize=T, maxVoxelX=8, maxVoxelY=12, maxVoxelZ=4)
+    f = Frontend(max_points=40_000, max_sweeps=2, max_voxel=(8, 12, 4), sample_size=T)
+    pack = synthetic_vfe_pack(4)
+    f.set_weights(pack)
+    rng = np.random.default_rng(T)
+    pts = rng.normal([0, 0, 0.5], [0.9, 0.7, 0.3], size=(30_000, 3)).astype(np.float32)  # dense core, sparse rim
+    off = [0, 12_000, 30_000]
+    grid = f.forward(pts, off, out=torch.full((2, 4, 16, 24, 64), float("nan"), device="cuda")).cpu().numpy()
+    ce = O.c_empty(pack, T)
+    for s in range(2):
+        vox = O.voxelize_np(pts[off[s]:off[s + 1]], **args)
+        assert vox["counts"].max() > T  # the cap is exercised
+        feat = O.vfe_forward(vox["features"].astype(np.float32), pack, np.float64)
+        want = O.scatter_dense(vox["coords"], feat, ce, (4, 16, 24), dtype=np.float64)
+        assert within(grid[s], want, floor=np.sqrt(np.mean(feat * feat))) <= REL_TOL
+    f.close()
+
+
+def test_bf16_fused_grid_every_cell_written():
+    from lisec_b200 import Frontend
+
+    f = Frontend(max_points=250_000, max_sweeps=2, grid_dtype="bf16")
+    f.set_weights(synthetic_vfe_pack(1))
+    pts, off = synth.sweep_batch(2, 100_000, seed0=40)
+    grid = f.forward(pts, off, out=torch.full((2, 8, 200, 400, 64), float("nan"), dtype=torch.bfloat16, device="cuda"))
+    assert not bool(torch.isnan(grid).any())
+    modular = f.scatter(f.vfe())
+    assert torch.equal(grid, modular)
+    f.close()
