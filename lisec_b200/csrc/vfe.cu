@@ -259,6 +259,7 @@ struct VfeOutput {
   const int* cell_voxel;  // occupancy map
   const float* c_empty;
   long long ncells;
+  const int* warm;       // the per-cell count table: pulled back into L2 for the NEXT call's point pass (see the writer)
   long long* prof;  // debug (LISEC_TRACE=1): per-CTA cycle counters [kProfSlots], see Workspace::trace
 };
 constexpr int kProfSlots = 16;
@@ -368,6 +369,18 @@ __device__ __forceinline__ void background_writer(const int* __restrict__ cell_v
     for (int u = 0; u < U; ++u) occ[u] = nxt[u];
   }
   bulk_wait_all();  // the tile must outlive every read of it; also makes the writes complete before the warp retires
+}
+
+// The grid stream has just pushed everything else out of L2, and the next call's point pass starts with ~0.5 M
+// scattered atomics into the per-cell count table (ncu: it was bound by those read-modify-writes going to DRAM). The
+// writers are done well before the other stages, so they pull the table (4 B per cell, all zeros at this point) back
+// into L2, marked evict-last.
+__device__ __forceinline__ void warm_count_table(const int* __restrict__ count, long long ncells, int wtid) {
+  const long long lines = (ncells * 4 + 127) >> 7;
+  const char* base = reinterpret_cast<const char*>(count);
+  for (long long i = (long long)blockIdx.x * (32 * kWriterWarps) + wtid; i < lines;
+       i += (long long)gridDim.x * (32 * kWriterWarps))
+    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base + (i << 7)));
 }
 
 // Pre-pass, one thread per voxel: float64 mean of the voxel's kept points, added in list order with one divide —
@@ -598,6 +611,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
     if (MODE == 2)
       background_writer(out.cell_voxel, out.c_empty, static_cast<__nv_bfloat16*>(out.grid), out.ncells, smem + OFF_BG,
                         (int)threadIdx.x);
+    if (MODE != 0 && out.warm) warm_count_table(out.warm, out.ncells, (int)threadIdx.x);
     return;
   }
   if (warp_in_cta == kTensorWarp) {  // ---- TENSOR ----
@@ -873,7 +887,7 @@ static cudaError_t launch_vfe_mode(const VfeSmall& p, const float* wblob, const 
 
 cudaError_t launch_vfe(const VfeSmall& p, const float* wblob, const VfeProblem& prob, float* voxel_feat, int sm_count,
                        cudaStream_t st, int* launches, long long* prof) {
-  const VfeOutput out{voxel_feat, nullptr, nullptr, nullptr, nullptr, 0, prof};
+  const VfeOutput out{voxel_feat, nullptr, nullptr, nullptr, nullptr, 0, nullptr, prof};
   ++*launches;
   return launch_vfe_mode<0>(p, wblob, prob, out, sm_count, st);
 }
@@ -881,7 +895,7 @@ cudaError_t launch_vfe(const VfeSmall& p, const float* wblob, const VfeProblem& 
 cudaError_t launch_vfe_to_grid(const VfeSmall& p, const float* wblob, const VfeProblem& prob, const Workspace& w,
                                const Geom& g, int n_sweeps, int grid_dtype, void* grid, int sm_count, cudaStream_t st,
                                int* launches) {
-  const VfeOutput out{nullptr, grid, w.voxel_cell, w.cell_voxel, w.c_empty, (long long)n_sweeps * g.cells,
+  const VfeOutput out{nullptr, grid, w.voxel_cell, w.cell_voxel, w.c_empty, (long long)n_sweeps * g.cells, w.count,
                       reinterpret_cast<long long*>(w.trace)};
   ++*launches;
   return grid_dtype == LISEC_F32 ? launch_vfe_mode<1>(p, wblob, prob, out, sm_count, st)

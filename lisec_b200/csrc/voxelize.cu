@@ -6,7 +6,7 @@
 // Pipeline (all launches on the caller's stream, no host round trip):
 //   point_pass   12 B/point read, float4-vectorised; voxel key in float64; strict range test; warp-aggregated
 //                atomicAdd histogram into the per-cell count table; writes cell_of_point.
-//   cell_scan    three fused exclusive scans over the cell table (occupied -> voxel row, count -> CSR offset,
+//   cell_scan    two kernels (block totals; prefix of earlier blocks + scan): three fused exclusive scans over the cell table (occupied -> voxel row, count -> CSR offset,
 //                kept+pad -> VFE row offset); writes the occupancy map cell_voxel. Voxel rows therefore come out
 //                in ascending (sweep, z, x, y) cell order, independent of thread scheduling.
 //   fill_pass    warp-aggregated atomicSub slot claim drains the count table back to zero (so the next call
@@ -225,44 +225,13 @@ __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const int* __
   }
 }
 
-// one block: exclusive scan of the per-block sums in place, totals and sentinels
-__global__ void __launch_bounds__(kScanThreads) scan_spine_kernel(int* __restrict__ block_sums, int nblocks,
-                                                                  int n_sweeps, long long* __restrict__ totals,
-                                                                  int* __restrict__ voxel_start,
-                                                                  int* __restrict__ row_start,
-                                                                  int* __restrict__ sweep_voxel_start) {
-  __shared__ Tri smem[kScanThreads / 32 + 1];
-  pdl_launch_dependents();
-  pdl_wait();
-  Tri carry{0, 0, 0};
-  for (int b0 = 0; b0 < nblocks; b0 += kScanThreads) {
-    const int b = b0 + threadIdx.x;
-    Tri x{0, 0, 0};
-    if (b < nblocks) x = Tri{block_sums[b], block_sums[nblocks + b], block_sums[2 * nblocks + b]};
-    Tri total;
-    Tri ex = block_exclusive(x, &total, smem);
-    if (b < nblocks) {
-      block_sums[b] = carry.v + ex.v;
-      block_sums[nblocks + b] = carry.e + ex.e;
-      block_sums[2 * nblocks + b] = carry.r + ex.r;
-    }
-    carry = tri_add(carry, total);
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    totals[TOT_VOXELS] = carry.v;
-    totals[TOT_ENTRIES] = carry.e;
-    totals[TOT_ROWS] = carry.r;
-    totals[TOT_TILES] = 0;  // set by order_pass when there is at least one voxel
-    voxel_start[carry.v] = carry.e;
-    row_start[carry.v] = carry.r;
-    sweep_voxel_start[n_sweeps] = carry.v;
-  }
-}
-
+// Second pass. There is no separate "spine" kernel: a block gets its exclusive prefix by summing the totals of the
+// blocks before it (at most nblocks/256 coalesced L2 loads per thread), and the last block, which thereby holds the
+// grand totals, writes them and the sentinels.
 __global__ void __launch_bounds__(kScanThreads) scan_down_kernel(const int* __restrict__ count, long long ncells,
-                                                                 int T, int cells_per_sweep, int nblocks,
+                                                                 int T, int cells_per_sweep, int nblocks, int n_sweeps,
                                                                  const int* __restrict__ block_sums,
+                                                                 long long* __restrict__ totals,
                                                                  int* __restrict__ cell_voxel,
                                                                  int* __restrict__ voxel_cell,
                                                                  int* __restrict__ voxel_start,
@@ -274,13 +243,28 @@ __global__ void __launch_bounds__(kScanThreads) scan_down_kernel(const int* __re
   const long long base = ((long long)blockIdx.x * kScanThreads + threadIdx.x) * kScanItems;
   int c[kScanItems];
   load_counts(count, base, ncells, c);
+  Tri before{0, 0, 0};
+  for (int j = threadIdx.x; j < (int)blockIdx.x; j += kScanThreads)
+    before = tri_add(before, Tri{block_sums[j], block_sums[nblocks + j], block_sums[2 * nblocks + j]});
+  Tri prefix;
+  block_exclusive(before, &prefix, smem);  // only its block total is wanted: the sum over all earlier blocks
+  __syncthreads();                         // smem is reused below
   Tri t{0, 0, 0};
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) t = tri_add(t, tri_of_count(c[i], T));
   Tri total;
   Tri ex = block_exclusive(t, &total, smem);
-  Tri run{block_sums[blockIdx.x] + ex.v, block_sums[nblocks + blockIdx.x] + ex.e,
-          block_sums[2 * nblocks + blockIdx.x] + ex.r};
+  Tri run = tri_add(prefix, ex);
+  if (blockIdx.x == nblocks - 1 && threadIdx.x == 0) {
+    const Tri carry = tri_add(prefix, total);
+    totals[TOT_VOXELS] = carry.v;
+    totals[TOT_ENTRIES] = carry.e;
+    totals[TOT_ROWS] = carry.r;
+    totals[TOT_TILES] = 0;  // set by order_pass when there is at least one voxel
+    voxel_start[carry.v] = carry.e;
+    row_start[carry.v] = carry.r;
+    sweep_voxel_start[n_sweeps] = carry.v;
+  }
   int cv[kScanItems];
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) {
@@ -427,13 +411,10 @@ cudaError_t launch_cell_scan(const SweepOffsets& so, const Geom& g, Workspace& w
   cudaError_t err = launch_pdl(scan_reduce_kernel, nblocks, kScanThreads, 0, st, (const int*)w.count, ncells, g.T,
                                nblocks, w.block_sums);
   if (err == cudaSuccess)
-    err = launch_pdl(scan_spine_kernel, 1, kScanThreads, 0, st, w.block_sums, nblocks, so.n, w.totals, w.voxel_start,
-                     w.row_start, w.sweep_voxel_start);
-  if (err == cudaSuccess)
     err = launch_pdl(scan_down_kernel, nblocks, kScanThreads, 0, st, (const int*)w.count, ncells, g.T, g.cells, nblocks,
-                     (const int*)w.block_sums, w.cell_voxel, w.voxel_cell, w.voxel_start, w.row_start,
+                     so.n, (const int*)w.block_sums, w.totals, w.cell_voxel, w.voxel_cell, w.voxel_start, w.row_start,
                      w.sweep_voxel_start);
-  *launches += 3;
+  *launches += 2;
   return err;
 }
 
