@@ -266,19 +266,27 @@ __global__ void __launch_bounds__(kScanThreads) scan_down_kernel(const int* __re
     sweep_voxel_start[n_sweeps] = carry.v;
   }
   int cv[kScanItems];
+  // cell ids fit 32 bits (checked in lisec_create); one division per thread finds the position inside the sweep
+  const int cell0 = (int)base;
+  int in_sweep = base < ncells ? cell0 % cells_per_sweep : 1;
+  int sweep = base < ncells ? cell0 / cells_per_sweep : 0;
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) {
-    const long long cell = base + i;
+    const int cell = cell0 + i;
     cv[i] = -1;
-    if (cell < ncells) {
-      if (cell % cells_per_sweep == 0) sweep_voxel_start[cell / cells_per_sweep] = run.v;
+    if (base + i < ncells) {
+      if (in_sweep == 0) sweep_voxel_start[sweep] = run.v;
       if (c[i] > 0) {
         cv[i] = run.v;
-        voxel_cell[run.v] = (int)cell;
+        voxel_cell[run.v] = cell;
         voxel_start[run.v] = run.e;
         row_start[run.v] = run.r;
         run = tri_add(run, tri_of_count(c[i], T));
       }
+    }
+    if (++in_sweep == cells_per_sweep) {
+      in_sweep = 0;
+      ++sweep;
     }
   }
   if (base + kScanItems <= ncells) {
@@ -312,22 +320,35 @@ __global__ void __launch_bounds__(256) fill_pass_kernel(const int* __restrict__ 
       if (p0 + j < n_total) cell[j] = cell_of_point[p0 + j];
   }
   const int lane = lane_id();
+  // the chain cell -> voxel -> segment start -> slot is three dependent L2 round trips: run the four points of the
+  // thread through each stage together so the round trips overlap
+  int v[4], start[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = cell[j] >= 0 ? __ldg(cell_voxel + cell[j]) : -1;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) start[j] = cell[j] >= 0 ? __ldg(voxel_start + v[j]) : 0;
+  unsigned peers[4];
+  int old[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const unsigned active = __ballot_sync(0xffffffffu, cell[j] >= 0);
+    peers[j] = 0;
+    old[j] = 0;
     if (cell[j] >= 0) {
-      const int v = cell_voxel[cell[j]];
-      const int start = voxel_start[v];
-      const unsigned peers = __match_any_sync(active, cell[j]);
-      const int leader = __ffs(peers) - 1;
-      const int npeers = __popc(peers);
-      int old = 0;
-      if (lane == leader) old = atomicSub(&count[cell[j]], npeers);  // drains the table back to zero
-      old = __shfl_sync(peers, old, leader);
-      const int rank = __popc(peers & ((1u << lane) - 1u));
-      const int slot = old - npeers + rank;
-      list_unsorted[start + slot] = (int)(p0 + j);
-      entry_voxel[start + slot] = v;
+      peers[j] = __match_any_sync(active, cell[j]);
+      if (lane == __ffs(peers[j]) - 1) old[j] = atomicSub(&count[cell[j]], __popc(peers[j]));  // drains the table to zero
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (cell[j] >= 0) {
+      const int leader = __ffs(peers[j]) - 1;
+      const int npeers = __popc(peers[j]);
+      const int o = __shfl_sync(peers[j], old[j], leader);
+      const int rank = __popc(peers[j] & ((1u << lane) - 1u));
+      const int slot = o - npeers + rank;
+      list_unsorted[start[j] + slot] = (int)(p0 + j);
+      entry_voxel[start[j] + slot] = v[j];
     }
   }
 }
