@@ -243,6 +243,11 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
   if (const char* t = std::getenv("LISEC_TRACE"); t && t[0] == '1') {
     LISEC_CUDA(h, dev_alloc(h, &w.trace, (size_t)kTraceCtas * kTraceSlots));
     LISEC_CUDA(h, cudaMemset(w.trace, 0, sizeof(unsigned long long) * kTraceCtas * kTraceSlots));
+    LISEC_CUDA(h, cudaMemset(w.trace + (size_t)kTimelineRow0 * kTraceSlots, 0xff, sizeof(unsigned long long)));
+    for (int k = 0; k < TL_COUNT; ++k)  // [0] = min stamp starts at ~0, [1] = max stamp starts at 0
+      LISEC_CUDA(h, cudaMemset(w.trace + (size_t)(kTimelineRow0 + k) * kTraceSlots, 0xff, sizeof(unsigned long long)));
+    LISEC_CUDA(h, set_trace_voxelize(w.trace));
+    LISEC_CUDA(h, set_trace_vfe(w.trace));
   }
   for (int b = 0; b < 2; ++b) LISEC_CUDA(h, cudaEventCreate(&h->ev_kernel[b]));
   LISEC_CUDA(h, dev_alloc(h, &w.empty_desc, (size_t)16));
@@ -524,6 +529,11 @@ int32_t lisec_debug_trace(lisec_handle* h, int64_t* out, int64_t n) {
   LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
   LISEC_CUDA(h, cudaDeviceSynchronize());
   LISEC_CUDA(h, cudaMemcpy(out, h->ws.trace, sizeof(int64_t) * kTraceCtas * kTraceSlots, cudaMemcpyDeviceToHost));
+  for (int k = 0; k < TL_COUNT; ++k) {  // re-arm the timeline rows: min stamp = ~0, max stamp = 0
+    unsigned long long* row = h->ws.trace + (size_t)(kTimelineRow0 + k) * kTraceSlots;
+    LISEC_CUDA(h, cudaMemset(row, 0xff, sizeof(unsigned long long)));
+    LISEC_CUDA(h, cudaMemset(row + 1, 0, sizeof(unsigned long long)));
+  }
   return LISEC_OK;
 }
 

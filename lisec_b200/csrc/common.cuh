@@ -120,6 +120,8 @@ cudaError_t launch_grid_write(const Geom& g, int n_sweeps, int c3, int grid_dtyp
                               cudaStream_t st, int* launches);
 
 int vfe_rows_per_tile(int T);
+cudaError_t set_trace_voxelize(unsigned long long* trace);
+cudaError_t set_trace_vfe(unsigned long long* trace);
 
 // ---- programmatic dependent launch ------------------------------------------------------------------------------
 // The path is a chain of short kernels on one stream. Each is launched with programmatic stream serialization: its
@@ -129,6 +131,19 @@ int vfe_rows_per_tile(int T);
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Debug timeline (LISEC_TRACE=1): every kernel stamps the moment its pdl_wait() returned — i.e. the moment its
+// predecessor completed — into rows 200+k of the trace buffer ([0] = earliest CTA, [1] = latest stamp). Kernel ids:
+enum { TL_POINT = 0, TL_SCAN_REDUCE, TL_SCAN_DOWN, TL_FILL, TL_ORDER, TL_ROWFEAT, TL_VFE, TL_VFE_END, TL_COUNT };
+constexpr int kTimelineRow0 = 200;
+__device__ __forceinline__ void timeline_stamp(unsigned long long* trace, int k) {
+  if (trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    atomicMin(trace + (size_t)(kTimelineRow0 + k) * kTraceSlots, t);
+    atomicMax(trace + (size_t)(kTimelineRow0 + k) * kTraceSlots + 1, t);
+  }
+}
 
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

@@ -41,6 +41,8 @@ int vfe_rows_per_tile(int T) { return kVfeThreads - T + 1; }
 
 namespace {
 
+__device__ unsigned long long* g_trace = nullptr;  // debug timeline (set_trace_vfe), normally null
+
 __device__ __forceinline__ unsigned pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<unsigned*>(&h);
@@ -397,6 +399,7 @@ __global__ void __launch_bounds__(256) row_features_kernel(const PT* __restrict_
                                                            float* __restrict__ row_feat) {
   pdl_launch_dependents();
   pdl_wait();
+  timeline_stamp(g_trace, TL_ROWFEAT);
   const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= totals[TOT_VOXELS]) return;
   const int s = voxel_start[v];
@@ -600,6 +603,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
   umma::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // from here on: the grouping, the row features and the occupancy map of this call
+  if (MODE != 0) timeline_stamp(g_trace, TL_VFE);
   const int n_tiles = (int)*prob.n_tiles;
   // tiles are strided over the CTAs: this one owns ordinals it = 0 .. my_tiles-1, tile blockIdx.x + it * gridDim.x
   const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -856,9 +860,20 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
     prof.flush(14, 14);
   }
   asm volatile("bar.sync 3, %0;" ::"n"(kFrontThreads + kBackThreads) : "memory");
+  if (MODE != 0 && tid == 0) {  // (threadIdx.x != 0 here: stamp by hand)
+    unsigned long long* tr = g_trace;
+    if (tr) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+      atomicMax(tr + (size_t)(kTimelineRow0 + TL_VFE_END) * kTraceSlots + 1, now);
+    }
+  }
 }
 
 }  // namespace
+
+cudaError_t set_trace_vfe(unsigned long long* trace) { return cudaMemcpyToSymbol(g_trace, &trace, sizeof(trace)); }
+
 
 cudaError_t launch_row_features(const void* pts, int pts_dtype, const Geom& g, const Workspace& w, long long max_voxels,
                                 cudaStream_t st, int* launches) {

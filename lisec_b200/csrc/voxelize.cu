@@ -20,6 +20,8 @@ namespace lisec {
 
 namespace {
 
+__device__ unsigned long long* g_trace = nullptr;  // debug timeline (set_trace_voxelize), normally null
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 // ---- voxel key (model_training.py:103-107, 117-122) ------------------------------------------------------
@@ -86,6 +88,7 @@ __global__ void __launch_bounds__(256) point_pass_kernel(const PT* __restrict__ 
                                                          unsigned long long* __restrict__ totals) {
   pdl_launch_dependents();
   pdl_wait();
+  timeline_stamp(g_trace, TL_POINT);
   const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long p0 = grp * 4;
   PT v[12];
@@ -210,6 +213,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const int* __
   __shared__ Tri smem[kScanThreads / 32 + 1];
   pdl_launch_dependents();
   pdl_wait();
+  timeline_stamp(g_trace, TL_SCAN_REDUCE);
   const long long base = ((long long)blockIdx.x * kScanThreads + threadIdx.x) * kScanItems;
   int c[kScanItems];
   load_counts(count, base, ncells, c);
@@ -240,6 +244,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_down_kernel(const int* __re
   __shared__ Tri smem[kScanThreads / 32 + 1];
   pdl_launch_dependents();
   pdl_wait();
+  timeline_stamp(g_trace, TL_SCAN_DOWN);
   const long long base = ((long long)blockIdx.x * kScanThreads + threadIdx.x) * kScanItems;
   int c[kScanItems];
   load_counts(count, base, ncells, c);
@@ -308,6 +313,7 @@ __global__ void __launch_bounds__(256) fill_pass_kernel(const int* __restrict__ 
                                                         int* __restrict__ entry_voxel) {
   pdl_launch_dependents();
   pdl_wait();
+  timeline_stamp(g_trace, TL_FILL);
   const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long p0 = grp * 4;
   int cell[4] = {-1, -1, -1, -1};
@@ -364,6 +370,7 @@ __global__ void __launch_bounds__(256) order_pass_kernel(const int* __restrict__
                                                          int* __restrict__ row_voxel) {
   pdl_launch_dependents();
   pdl_wait();
+  timeline_stamp(g_trace, TL_ORDER);
   const long long n_entries = totals[TOT_ENTRIES];
   const long long n_voxels = totals[TOT_VOXELS];
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -406,6 +413,10 @@ __global__ void __launch_bounds__(256) order_pass_kernel(const int* __restrict__
 }  // namespace
 
 // ---- launchers --------------------------------------------------------------------------------------------
+cudaError_t set_trace_voxelize(unsigned long long* trace) {
+  return cudaMemcpyToSymbol(g_trace, &trace, sizeof(trace));
+}
+
 cudaError_t launch_point_pass(const void* pts, int pts_dtype, long long n_total, const SweepOffsets& so,
                               const Geom& g, Workspace& w, cudaStream_t st, int* launches) {
   cudaError_t err = cudaMemsetAsync(w.totals, 0, sizeof(long long) * TOT_COUNT, st);
