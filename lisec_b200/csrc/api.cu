@@ -130,7 +130,7 @@ int do_voxelize(lisec_handle* h, const void* points, int dtype, const SweepOffse
 }
 
 int do_vfe(lisec_handle* h, float* voxel_feat, cudaStream_t st) {
-  LISEC_CUDA(h, launch_row_features(h->last_points, h->last_dtype, h->geom, h->ws, h->max_voxels, st, &h->launches));
+  LISEC_CUDA(h, launch_row_features(h->last_points, h->last_dtype, h->geom, h->ws, 2 * h->last_so.off[h->last_so.n], st, &h->launches));
   const VfeProblem prob{h->ws.tile_first, h->ws.tile_row0, h->ws.row_voxel, h->ws.row_feat, h->ws.totals + TOT_TILES};
   LISEC_CUDA(h, launch_vfe(h->params, h->ws.vfe_w, prob, voxel_feat, h->sm_count, st, &h->launches,
                            reinterpret_cast<long long*>(h->ws.trace)));
@@ -437,7 +437,7 @@ int32_t lisec_scatter_dense(lisec_handle* h, const float* voxel_feat, void* grid
 }
 
 static int fused_stage(lisec_handle* h, void* grid, cudaStream_t st) {
-  LISEC_CUDA(h, launch_row_features(h->last_points, h->last_dtype, h->geom, h->ws, h->max_voxels, st, &h->launches));
+  LISEC_CUDA(h, launch_row_features(h->last_points, h->last_dtype, h->geom, h->ws, 2 * h->last_so.off[h->last_so.n], st, &h->launches));
   const VfeProblem prob{h->ws.tile_first, h->ws.tile_row0, h->ws.row_voxel, h->ws.row_feat, h->ws.totals + TOT_TILES};
   // one kernel: VFE (FP32 pipe + tensor core), voxel rows and the c_empty background written to the grid concurrently
   LISEC_CUDA(h, cudaEventRecord(h->ev_kernel[0], st));

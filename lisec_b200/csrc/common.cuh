@@ -107,7 +107,7 @@ struct VfeProblem {
   const long long* n_tiles;
 };
 // float64 centroid + float32 feature rows for every VFE row (model_training.py:134-141), contiguous in row order
-cudaError_t launch_row_features(const void* pts, int pts_dtype, const Geom& g, const Workspace& w, long long max_voxels,
+cudaError_t launch_row_features(const void* pts, int pts_dtype, const Geom& g, const Workspace& w, long long max_rows,
                                 cudaStream_t st, int* launches);
 cudaError_t launch_vfe(const VfeSmall& p, const float* wblob, const VfeProblem& prob,
                        float* voxel_feat, int sm_count, cudaStream_t st, int* launches, long long* prof = nullptr);

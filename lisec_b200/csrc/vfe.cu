@@ -385,51 +385,67 @@ __device__ __forceinline__ void warm_count_table(const int* __restrict__ count, 
     asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base + (i << 7)));
 }
 
-// Pre-pass, one thread per voxel: float64 mean of the voxel's kept points, added in list order with one divide —
-// np.mean(currPoints, axis=0) (model_training.py:135) bit for bit — then the float32 feature rows
-// [x,y,z,x-cx,y-cy,z-cz] (:137-140 + the Keras input cast) of its VFE rows, contiguous in row order, and six zeros for
-// the virtual pad row (:141). The VFE kernel then starts every tile from one contiguous, prefetchable 24 B/row read
-// instead of a chain of dependent gathers.
+// Pre-pass, one thread per VFE row: float64 mean of the row's voxel's kept points, added in list order with one
+// divide — np.mean(currPoints, axis=0) (model_training.py:135) bit for bit — then the float32 feature row
+// [x,y,z,x-cx,y-cy,z-cz] (:137-140 + the Keras input cast), or six zeros for the virtual pad row (:141). Rows are
+// contiguous in row order, so the VFE kernel starts every tile from one prefetchable 24 B/row read instead of a chain
+// of dependent gathers. The rows of a voxel each redo its (<= T term) sum: those re-reads hit L1, the stores are
+// coalesced, and no thread carries a whole saturated voxel alone.
 template <typename PT>
 __global__ void __launch_bounds__(256) row_features_kernel(const PT* __restrict__ pts, int T,
                                                            const int* __restrict__ voxel_start,
                                                            const int* __restrict__ row_start,
+                                                           const int* __restrict__ row_voxel,
                                                            const int* __restrict__ list_sorted,
                                                            const long long* __restrict__ totals,
                                                            float* __restrict__ row_feat) {
   pdl_launch_dependents();
   pdl_wait();
   timeline_stamp(g_trace, TL_ROWFEAT);
-  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= totals[TOT_VOXELS]) return;
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= totals[TOT_ROWS]) return;
+  const int v = row_voxel[r];
   const int s = voxel_start[v];
   const int c = voxel_start[v + 1] - s;
   const int kept = c < T ? c : T;
-  double sx = 0.0, sy = 0.0, sz = 0.0;
-  for (int i = 0; i < kept; ++i) {
-    PT x, y, z;
-    load_point(pts, (long long)list_sorted[s + i], x, y, z);
-    sx += (double)x;
-    sy += (double)y;
-    sz += (double)z;
+  const int mine = (int)(r - row_start[v]);  // == kept: the virtual pad row
+  float2* dst = reinterpret_cast<float2*>(row_feat + (size_t)r * 6);
+  if (mine >= kept) {
+    dst[0] = make_float2(0.f, 0.f);
+    dst[1] = make_float2(0.f, 0.f);
+    dst[2] = make_float2(0.f, 0.f);
+    return;
   }
-  const double n = (double)(kept > 0 ? kept : 1);
-  const double cx = sx / n, cy = sy / n, cz = sz / n;
-  float2* dst = reinterpret_cast<float2*>(row_feat + (size_t)row_start[v] * 6);
-  for (int i = 0; i < kept; ++i) {
-    PT x, y, z;
-    load_point(pts, (long long)list_sorted[s + i], x, y, z);
-    float f[6];
-    point_features((double)x, (double)y, (double)z, cx, cy, cz, f);
-    dst[3 * i] = make_float2(f[0], f[1]);
-    dst[3 * i + 1] = make_float2(f[2], f[3]);
-    dst[3 * i + 2] = make_float2(f[4], f[5]);
+  // The loads of a chunk are issued together; the additions stay in list order, one at a time.
+  constexpr int CH = 6;
+  double sx = 0.0, sy = 0.0, sz = 0.0, px = 0.0, py = 0.0, pz = 0.0;
+  for (int i0 = 0; i0 < kept; i0 += CH) {
+    int id[CH];
+    PT x[CH], y[CH], z[CH];
+#pragma unroll
+    for (int u = 0; u < CH; ++u) id[u] = i0 + u < kept ? list_sorted[s + i0 + u] : -1;
+#pragma unroll
+    for (int u = 0; u < CH; ++u)
+      if (id[u] >= 0) load_point(pts, (long long)id[u], x[u], y[u], z[u]);
+#pragma unroll
+    for (int u = 0; u < CH; ++u)
+      if (id[u] >= 0) {
+        sx += (double)x[u];
+        sy += (double)y[u];
+        sz += (double)z[u];
+        if (i0 + u == mine) {
+          px = (double)x[u];
+          py = (double)y[u];
+          pz = (double)z[u];
+        }
+      }
   }
-  if (kept < T) {
-    dst[3 * kept] = make_float2(0.f, 0.f);
-    dst[3 * kept + 1] = make_float2(0.f, 0.f);
-    dst[3 * kept + 2] = make_float2(0.f, 0.f);
-  }
+  const double n = (double)kept;
+  float f[6];
+  point_features(px, py, pz, sx / n, sy / n, sz / n, f);
+  dst[0] = make_float2(f[0], f[1]);
+  dst[1] = make_float2(f[2], f[3]);
+  dst[2] = make_float2(f[4], f[5]);
 }
 
 __device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
@@ -875,18 +891,18 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
 cudaError_t set_trace_vfe(unsigned long long* trace) { return cudaMemcpyToSymbol(g_trace, &trace, sizeof(trace)); }
 
 
-cudaError_t launch_row_features(const void* pts, int pts_dtype, const Geom& g, const Workspace& w, long long max_voxels,
+cudaError_t launch_row_features(const void* pts, int pts_dtype, const Geom& g, const Workspace& w, long long max_rows,
                                 cudaStream_t st, int* launches) {
-  const unsigned blocks = (unsigned)((max_voxels + 255) / 256);  // threads past the device-side voxel count exit
+  const unsigned blocks = (unsigned)((max_rows + 255) / 256) + 1;  // threads past the device-side row count exit
   cudaError_t err;
   if (pts_dtype == LISEC_F32)
     err = launch_pdl(row_features_kernel<float>, blocks, 256, 0, st, static_cast<const float*>(pts), g.T,
-                     (const int*)w.voxel_start, (const int*)w.row_start, (const int*)w.list_sorted,
-                     (const long long*)w.totals, w.row_feat);
+                     (const int*)w.voxel_start, (const int*)w.row_start, (const int*)w.row_voxel,
+                     (const int*)w.list_sorted, (const long long*)w.totals, w.row_feat);
   else
     err = launch_pdl(row_features_kernel<double>, blocks, 256, 0, st, static_cast<const double*>(pts), g.T,
-                     (const int*)w.voxel_start, (const int*)w.row_start, (const int*)w.list_sorted,
-                     (const long long*)w.totals, w.row_feat);
+                     (const int*)w.voxel_start, (const int*)w.row_start, (const int*)w.row_voxel,
+                     (const int*)w.list_sorted, (const long long*)w.totals, w.row_feat);
   ++*launches;
   return err;
 }

@@ -396,9 +396,13 @@ __global__ void __launch_bounds__(256) order_pass_kernel(const int* __restrict__
   const int p = list_unsorted[e];
   int rank = 0;
   if (n > 1) {
-    for (int i = 0; i < n; ++i) {
-      rank += (list_unsorted[s + i] < p);
-      if (rank >= T) break;  // not among the first T in point order: dropped (the cap at :131)
+    // chunks of 8 independent loads, then the early exit: not among the first T in point order = dropped (:131)
+    for (int i0 = 0; i0 < n && rank < T; i0 += 8) {
+      int q[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) q[u] = i0 + u < n ? list_unsorted[s + i0 + u] : 0x7fffffff;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) rank += (q[u] < p);
     }
   }
   if (rank < T) {
