@@ -194,6 +194,47 @@ int32_t lisec_debug_trace(lisec_handle* h, int64_t* out, int64_t n);
 /* Number of kernels the last call on this handle launched (bench.py's gpu_launches). */
 int32_t lisec_last_launch_count(const lisec_handle* h);
 
+/* ---- dense layers behind the voxel grid: middle Conv3D stack and RPN --------------------------
+ *
+ * One plan = one Keras layer group of the reference's createModel (model_training.py:236-256), run as an implicit GEMM
+ * on the tensor cores (lisec_b200/csrc/conv.cu). A plan binds caller-owned DEVICE buffers:
+ *   in       bf16 [batch, in_d, in_h, in_w, in_c]                 channels-last (Conv2D layers: in_d = 1)
+ *   weights  bf16 [kd*kh*kw][n_tiles*out_c][in_c]                 tap-major, K (= in_c) contiguous
+ *   scale, shift  float32 [out_c] (or [n_tiles*out_c] without shuffle)
+ *   out      bf16 or float32 [batch, out_d, out_h, out_w, out_pitch], written at channel offset out_ch_off
+ * and computes  out = act((in (*) weights) * scale + shift)  with zero padding (pad_d, pad_h, pad_w) — the reference's
+ * ZeroPadding3D/2D + 'valid' convolution (:192-193, :202-203) — and strides (stride_d, stride_hw, stride_hw).
+ * BatchNormalization, the convolution bias and, for the Conv3D blocks, the bias-free Dense that follows the BN (:194-195)
+ * are affine and are folded into (weights, scale, shift) by the host (lisec_b200/network.py).
+ * shuffle = s > 1: a Conv2DTranspose whose kernel equals its stride s (:248, :251): a 1x1 GEMM with n_tiles = s*s
+ * groups of out_c columns; group (i, j) lands at output position (s*h + i, s*w + j). out_h/out_w are then s x larger.
+ * tile_w x tile_h = 128 output positions per CTA tile (tile_w a power of two). */
+typedef struct lisec_conv_desc {
+  int32_t batch, in_d, in_h, in_w, in_c;
+  int32_t kd, kh, kw;
+  int32_t stride_d, stride_hw;
+  int32_t pad_d, pad_h, pad_w;
+  int32_t out_c, n_tiles, shuffle;
+  int32_t out_pitch, out_ch_off;
+  int32_t relu;      /* 1: ReLU after the affine */
+  int32_t out_dtype; /* LISEC_BF16 or LISEC_F32 */
+  int32_t tile_w, tile_h;
+  int32_t reserved;
+} lisec_conv_desc;
+
+typedef struct lisec_conv_plan lisec_conv_plan;
+
+/* Validates the description, encodes the TMA tensor maps of `in` and `weights`. The current CUDA device is the plan's. */
+int32_t lisec_conv_plan_create(const lisec_conv_desc* desc, const void* in, const void* weights, const float* scale,
+                               const float* shift, void* out, lisec_conv_plan** plan);
+/* [async] One kernel launch on `stream`. */
+int32_t lisec_conv_plan_run(lisec_conv_plan* plan, void* stream);
+/* out_dhw[3] = output depth, height, width (after the pixel shuffle). */
+int32_t lisec_conv_plan_output_shape(const lisec_conv_plan* plan, int32_t* out_dhw);
+void lisec_conv_plan_destroy(lisec_conv_plan* plan);
+/* Text of the last lisec_conv_* failure on the calling thread. */
+const char* lisec_conv_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

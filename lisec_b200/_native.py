@@ -68,6 +68,12 @@ class lisec_vfe_weights(C.Structure):
     ]
 
 
+class lisec_conv_desc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "batch", "in_d", "in_h", "in_w", "in_c", "kd", "kh", "kw", "stride_d", "stride_hw", "pad_d", "pad_h", "pad_w",
+        "out_c", "n_tiles", "shuffle", "out_pitch", "out_ch_off", "relu", "out_dtype", "tile_w", "tile_h", "reserved")]
+
+
 _H = C.c_void_p
 _VP = C.c_void_p
 _I32P = C.POINTER(C.c_int32)
@@ -95,6 +101,11 @@ SIGNATURES = {
     "lisec_last_fused_kernel_ms": (C.c_int32, [_H, _FP]),
     "lisec_debug_trace": (C.c_int32, [_H, _I64P, C.c_int64]),
     "lisec_last_launch_count": (C.c_int32, [_H]),
+    "lisec_conv_plan_create": (C.c_int32, [C.POINTER(lisec_conv_desc), _VP, _VP, _VP, _VP, _VP, C.POINTER(_H)]),
+    "lisec_conv_plan_run": (C.c_int32, [_H, _VP]),
+    "lisec_conv_plan_output_shape": (C.c_int32, [_H, _I32P]),
+    "lisec_conv_plan_destroy": (None, [_H]),
+    "lisec_conv_last_error": (C.c_char_p, []),
 }
 
 _lib = None

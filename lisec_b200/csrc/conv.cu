@@ -1,0 +1,479 @@
+// Dense convolutions of the VoxelNet middle layers and RPN on the sm_100a tensor cores: one implicit-GEMM kernel
+// (TMA -> shared memory -> tcgen05.mma -> TMEM -> epilogue) behind lisec_conv_plan_*.
+//
+// Replaces, one plan per layer, the Keras layers of reference model_training.py:
+//   addConv3DLayer  :191-196  ZeroPadding3D + Conv3D(64, k3, valid) + BatchNormalization + Dense(64, relu, no bias)
+//   addConv2DLayer  :201-208  ZeroPadding2D + Conv2D(k3, stride) + BatchNormalization + ReLU
+//   Conv2DTranspose :245,248,251 (k3 s1 / k2 s2 / k4 s4, padding='same'), Concatenate :252, the two 1x1 heads :253-254
+// The host side (lisec_b200/network.py) folds each layer's affine tail into (weights, scale, shift); see there.
+//
+// Formulation. Activations are channels-last bf16 [B, D, H, W, C]. An output tile is 128 output positions: a
+// tile_w x tile_h box in (W, H) at one (b, d). For every filter tap and every 64-channel block of C the A operand
+// [128 positions x 64 ch] is ONE TMA box load whose start coordinate is the tile origin shifted by the tap — the
+// zero padding of ZeroPadding3D/2D is the TMA's out-of-bounds fill, nothing is materialised — and the B operand
+// [N x 64 ch] is one box of the [taps][N][C] weight tensor. Both land K-major with the 128-byte swizzle the tensor
+// core reads (umma.cuh). Stride-2 layers read a space-to-depth VIEW of the same memory: [H/2][2][W/2][2C], where a
+// tap picks a parity plane and a 64-channel window of the 2C pair, so a strided tap is again a plain box.
+// Transposed convolutions with kernel == stride do not overlap: they are 1x1 GEMMs with N = k*k*C_out, run as k*k
+// N-tiles whose epilogue writes the pixel-shuffled position. The k3 s1 one is a 3x3 convolution with the kernel
+// flipped (host side).
+//
+// One persistent CTA per SM, 6 warps: warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane; owns TMEM),
+// warps 2-5 = epilogue (TMEM lane quadrant = warp id % 4). Three pipelines: shared-memory stages (full/empty
+// mbarriers), two TMEM accumulators (acc_full/acc_empty) so a tile's epilogue overlaps the next tile's MMAs, and
+// the static tile schedule (tile = blockIdx.x + i * gridDim.x, N-tile fastest so neighbours share A in L2).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace lisec {
+namespace {
+
+constexpr int kConvThreads = 192;
+constexpr int kMaxTaps = 27;
+constexpr int kMaxStages = 8;
+constexpr uint32_t kABytes = 128 * 128;  // 128 positions x 64 bf16 channels
+
+struct ConvParams {
+  // tile schedule
+  int tiles_w, tiles_h, out_d, batch, n_tiles;
+  long long total_tiles;
+  int bw, bw_log2, bh;
+  // K loop
+  int n_taps, c_blocks, N, stages;
+  // TMA coordinates of a tap: (c_off[t] + 64 cb, b1 + t1[t], b2 + t2[t], b3 + t3[t], b)
+  int s2d, stride_d;
+  short c_off[kMaxTaps];
+  signed char t1[kMaxTaps], t2[kMaxTaps], t3[kMaxTaps];
+  // epilogue: y = acc * scale[n] + shift[n], optional ReLU, to out[(b, d, h*shuffle + i, w*shuffle + j)][ch_off + n]
+  int out_h, out_w, shuffle, relu, out_f32, out_ch_off;
+  long long out_pitch;
+  const float* scale;
+  const float* shift;
+  void* out;
+};
+
+// ---- PTX helpers not in umma.cuh ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t mbar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t mbar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(mbar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// kind::f16 with bf16 operands, float32 accumulation, both operands K-major
+__device__ __host__ constexpr uint32_t make_idesc_bf16_k(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct TileCoord {
+  int nt, ow0, oh0, od, b;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& P, long long tile) {
+  TileCoord t;
+  t.nt = (int)(tile % P.n_tiles);
+  long long r = tile / P.n_tiles;
+  t.ow0 = (int)(r % P.tiles_w) * P.bw;
+  r /= P.tiles_w;
+  t.oh0 = (int)(r % P.tiles_h) * P.bh;
+  r /= P.tiles_h;
+  t.od = (int)(r % P.out_d);
+  t.b = (int)(r / P.out_d);
+  return t;
+}
+
+__device__ __forceinline__ unsigned pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<unsigned*>(&h);
+}
+
+// one chunk of NV consecutive channels of one output position: affine + ReLU + store
+template <int NV>
+__device__ __forceinline__ void store_chunk(const ConvParams& P, const float (&x)[NV], int sidx0, size_t elem0,
+                                            bool valid) {
+  float y[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    y[i] = fmaf(x[i], __ldg(P.scale + sidx0 + i), __ldg(P.shift + sidx0 + i));
+    if (P.relu) y[i] = fmaxf(y[i], 0.f);
+  }
+  if (!valid) return;
+  if (P.out_f32) {
+    float4* dst = reinterpret_cast<float4*>(static_cast<float*>(P.out) + elem0);
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i) dst[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+  } else {
+    uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(P.out) + elem0);
+#pragma unroll
+    for (int i = 0; i < NV / 8; ++i)
+      dst[i] = make_uint4(pack2(y[8 * i], y[8 * i + 1]), pack2(y[8 * i + 2], y[8 * i + 3]),
+                          pack2(y[8 * i + 4], y[8 * i + 5]), pack2(y[8 * i + 6], y[8 * i + 7]));
+  }
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+    conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const __grid_constant__ ConvParams P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = umma::smem_u32(smem);
+  if (base & 1023u) __trap();
+  const uint32_t b_bytes = (uint32_t)P.N * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t bar0 = base + (uint32_t)P.stages * stage_bytes;
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
+  auto bar_acc_full = [&](int a) { return bar0 + 8u * (2 * kMaxStages + a); };
+  auto bar_acc_empty = [&](int a) { return bar0 + 8u * (2 * kMaxStages + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (size_t)P.stages * stage_bytes + 8 * (2 * kMaxStages + 4));
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
+    for (int s = 0; s < P.stages; ++s) {
+      umma::mbar_init(bar_full(s), 1);
+      umma::mbar_init(bar_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      umma::mbar_init(bar_acc_full(a), 1);
+      umma::mbar_init(bar_acc_empty(a), 4);
+    }
+    umma::mbar_init_fence();
+  }
+  if (warp == 1) umma::tmem_alloc<512>(tmem_slot);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // the previous layer's output is complete and visible from here on
+
+  const int k_blocks = P.n_taps * P.c_blocks;
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(P, tile);
+        const int b1 = t.ow0, b2 = P.s2d ? 0 : t.oh0, b3 = P.s2d ? t.oh0 : t.od * P.stride_d;
+        for (int tap = 0; tap < P.n_taps; ++tap) {
+          const int c1 = b1 + P.t1[tap], c2 = b2 + P.t2[tap], c3 = b3 + P.t3[tap];
+          for (int cb = 0; cb < P.c_blocks; ++cb) {
+            umma::mbar_wait(bar_empty(s), ph ^ 1u);
+            mbar_arrive_expect_tx(bar_full(s), stage_bytes);
+            const uint32_t dst = base + (uint32_t)s * stage_bytes;
+            tma_load_5d(dst, &map_a, bar_full(s), P.c_off[tap] + 64 * cb, c1, c2, c3, t.b);
+            tma_load_3d(dst + kABytes, &map_b, bar_full(s), 64 * cb, t.nt * P.N, tap);
+            if (++s == P.stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16_k(128, P.N);
+      int s = 0, acc = 0;
+      uint32_t ph = 0, acc_ph = 0;
+      for (long long tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        umma::mbar_wait(bar_acc_empty(acc), acc_ph ^ 1u);
+        umma::fence_after_sync();
+        const uint32_t d = tmem_base + (uint32_t)(acc * P.N);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          umma::mbar_wait(bar_full(s), ph);
+          umma::fence_after_sync();
+          const uint32_t a0 = base + (uint32_t)s * stage_bytes, b0 = a0 + kABytes;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            mma_bf16_ss(d, umma::make_desc_k_sw128(a0 + 32 * j), umma::make_desc_k_sw128(b0 + 32 * j), idesc,
+                        (kb | j) != 0);
+          umma::mma_commit(bar_empty(s));  // the stage is free again once these MMAs have read it
+          if (++s == P.stages) { s = 0; ph ^= 1u; }
+        }
+        umma::mma_commit(bar_acc_full(acc));
+        if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> affine (+ReLU) -> global =====
+    const int q = warp & 3, row = 32 * q + lane;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    const int sh = P.shuffle;
+    for (long long tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(P, tile);
+      const int oh = t.oh0 + (row >> P.bw_log2), ow = t.ow0 + (row & (P.bw - 1));
+      const bool valid = oh < P.out_h && ow < P.out_w;
+      const int si = sh > 1 ? t.nt / sh : 0, sj = sh > 1 ? t.nt % sh : 0;
+      const size_t pix = (((size_t)t.b * P.out_d + t.od) * ((size_t)P.out_h * sh) + (size_t)oh * sh + si) *
+                             ((size_t)P.out_w * sh) + (size_t)ow * sh + sj;
+      const int n0 = sh > 1 ? 0 : t.nt * P.N;  // scale/shift index and output channel of the tile's first column
+      const size_t elem = pix * (size_t)P.out_pitch + P.out_ch_off + n0;
+      umma::mbar_wait(bar_acc_full(acc), acc_ph);
+      umma::fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * P.N);
+      if (P.N == 16) {
+        float x[16];
+        tmem_ld_32x16(taddr, x);
+        store_chunk<16>(P, x, n0, elem, valid);
+      } else {
+        for (int c0 = 0; c0 < P.N; c0 += 32) {
+          float x[32];
+          umma::tmem_ld_32x32(taddr + c0, x);
+          store_chunk<32>(P, x, n0 + c0, elem + c0, valid);
+        }
+      }
+      umma::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(bar_acc_empty(acc));
+      if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) umma::tmem_dealloc<512>(tmem_base);
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+thread_local char g_conv_error[512] = "";
+
+int conv_fail(int status, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_conv_error, sizeof(g_conv_error), fmt, ap);
+  va_end(ap);
+  return status;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+}  // namespace
+}  // namespace lisec
+
+using namespace lisec;
+
+struct lisec_conv_plan {
+  CUtensorMap map_a, map_b;
+  ConvParams p;
+  int grid, smem, device;
+};
+
+extern "C" {
+
+const char* lisec_conv_last_error(void) { return g_conv_error; }
+
+int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const void* weights, const float* scale,
+                               const float* shift, void* out, lisec_conv_plan** plan_out) {
+  if (!d || !in || !weights || !scale || !shift || !out || !plan_out)
+    return conv_fail(LISEC_ERR_BAD_ARG, "null argument");
+  *plan_out = nullptr;
+  const int C = d->in_c, N = d->out_c;
+  if (C < 64 || C % 64) return conv_fail(LISEC_ERR_BAD_CONFIG, "in_c = %d: need a multiple of 64", C);
+  if (N < 16 || N > 256 || N % 16) return conv_fail(LISEC_ERR_BAD_CONFIG, "out_c = %d: need 16..256, multiple of 16", N);
+  if (N != 16 && N % 32) return conv_fail(LISEC_ERR_BAD_CONFIG, "out_c = %d: need 16 or a multiple of 32", N);
+  const int taps = d->kd * d->kh * d->kw;
+  if (taps < 1 || taps > kMaxTaps) return conv_fail(LISEC_ERR_BAD_CONFIG, "%d taps: at most %d", taps, kMaxTaps);
+  const int s = d->stride_hw;
+  if (s != 1 && s != 2) return conv_fail(LISEC_ERR_BAD_CONFIG, "stride_hw = %d: 1 or 2", s);
+  if (s == 2 && (d->in_d != 1 || d->kd != 1 || d->in_h % 2 || d->in_w % 2 || 2 * C > 32767))
+    return conv_fail(LISEC_ERR_BAD_CONFIG, "stride-2 layers are 2-D with even H and W");
+  if (d->tile_w * d->tile_h != 128 || (d->tile_w & (d->tile_w - 1)) || d->tile_w > 128)
+    return conv_fail(LISEC_ERR_BAD_CONFIG, "tile %d x %d: need a power-of-two width and 128 positions", d->tile_w,
+                     d->tile_h);
+  const int n_tiles = d->n_tiles < 1 ? 1 : d->n_tiles;
+  const int shuffle = d->shuffle < 1 ? 1 : d->shuffle;
+  if (shuffle > 1 && (n_tiles != shuffle * shuffle || taps != 1))
+    return conv_fail(LISEC_ERR_BAD_CONFIG, "pixel shuffle %d needs %d N-tiles and a 1x1 kernel", shuffle,
+                     shuffle * shuffle);
+  if (d->batch < 1 || d->in_d < 1 || d->in_h < 1 || d->in_w < 1 || d->stride_d < 1)
+    return conv_fail(LISEC_ERR_BAD_ARG, "bad input shape");
+  const int OD = (d->in_d + 2 * d->pad_d - d->kd) / d->stride_d + 1;
+  const int OH = (d->in_h + 2 * d->pad_h - d->kh) / s + 1;
+  const int OW = (d->in_w + 2 * d->pad_w - d->kw) / s + 1;
+  if (OD < 1 || OH < 1 || OW < 1) return conv_fail(LISEC_ERR_BAD_CONFIG, "empty output");
+  const int align = d->out_dtype == LISEC_F32 ? 4 : 8;
+  if (d->out_pitch % align || d->out_ch_off % align || d->out_pitch < d->out_ch_off + (shuffle > 1 ? N : n_tiles * N))
+    return conv_fail(LISEC_ERR_BAD_CONFIG, "out_pitch %d / out_ch_off %d: need multiples of %d and room for %d channels",
+                     d->out_pitch, d->out_ch_off, align, N);
+  if (d->out_dtype != LISEC_F32 && d->out_dtype != LISEC_BF16) return conv_fail(LISEC_ERR_BAD_CONFIG, "out_dtype");
+  EncodeTiledFn encode = encode_tiled_fn();
+  if (!encode) return conv_fail(LISEC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+
+  lisec_conv_plan* pl = new lisec_conv_plan();
+  memset(pl, 0, sizeof(*pl));
+  ConvParams& p = pl->p;
+  p.bw = d->tile_w;
+  p.bh = d->tile_h;
+  p.bw_log2 = 0;
+  while ((1 << p.bw_log2) < p.bw) ++p.bw_log2;
+  p.tiles_w = (OW + p.bw - 1) / p.bw;
+  p.tiles_h = (OH + p.bh - 1) / p.bh;
+  p.out_d = OD;
+  p.batch = d->batch;
+  p.n_tiles = n_tiles;
+  p.total_tiles = (long long)n_tiles * p.tiles_w * p.tiles_h * OD * d->batch;
+  p.n_taps = taps;
+  p.c_blocks = C / 64;
+  p.N = N;
+  p.s2d = s == 2;
+  p.stride_d = d->stride_d;
+  int t = 0;
+  for (int kd = 0; kd < d->kd; ++kd)
+    for (int kh = 0; kh < d->kh; ++kh)
+      for (int kw = 0; kw < d->kw; ++kw, ++t) {
+        if (s == 1) {
+          p.c_off[t] = 0;
+          p.t1[t] = (signed char)(kw - d->pad_w);
+          p.t2[t] = (signed char)(kh - d->pad_h);
+          p.t3[t] = (signed char)(kd - d->pad_d);
+        } else {  // input position 2*o + (k - pad) = 2*(o + q) + parity
+          const int uw = kw - d->pad_w, uh = kh - d->pad_h;
+          const int qw = floor_div(uw, 2), qh = floor_div(uh, 2);
+          p.c_off[t] = (short)((uw - 2 * qw) * C);
+          p.t1[t] = (signed char)qw;
+          p.t2[t] = (signed char)(uh - 2 * qh);
+          p.t3[t] = (signed char)qh;
+        }
+      }
+  p.out_h = OH;
+  p.out_w = OW;
+  p.shuffle = shuffle;
+  p.relu = d->relu != 0;
+  p.out_f32 = d->out_dtype == LISEC_F32;
+  p.out_ch_off = d->out_ch_off;
+  p.out_pitch = d->out_pitch;
+  p.scale = scale;
+  p.shift = shift;
+  p.out = out;
+  const uint32_t stage_bytes = kABytes + (uint32_t)N * 128u;
+  int stages = (int)((200u * 1024u) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  p.stages = stages;
+  pl->smem = stages * (int)stage_bytes + 8 * (2 * kMaxStages + 4) + 16;
+
+  // tensor maps (bf16, 128-byte swizzle, zero fill out of bounds)
+  const cuuint64_t eb = 2;
+  cuuint64_t dims[5], strides[4];
+  cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+  const cuuint64_t W = d->in_w, H = d->in_h, D = d->in_d, B = d->batch;
+  if (s == 1) {
+    dims[0] = C; dims[1] = W; dims[2] = H; dims[3] = D; dims[4] = B;
+    strides[0] = C * eb; strides[1] = W * C * eb; strides[2] = H * W * C * eb; strides[3] = D * H * W * C * eb;
+    box[0] = 64; box[1] = p.bw; box[2] = p.bh; box[3] = 1; box[4] = 1;
+  } else {
+    dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = B;
+    strides[0] = 2 * C * eb; strides[1] = W * C * eb; strides[2] = 2 * W * C * eb; strides[3] = H * W * C * eb;
+    box[0] = 64; box[1] = p.bw; box[2] = 1; box[3] = p.bh; box[4] = 1;
+  }
+  CUresult r = encode(&pl->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    delete pl;
+    return conv_fail(LISEC_ERR_CUDA, "cuTensorMapEncodeTiled(input) failed: CUresult %d", (int)r);
+  }
+  const cuuint64_t NT = (cuuint64_t)n_tiles * N;
+  cuuint64_t wdims[3] = {(cuuint64_t)C, NT, (cuuint64_t)taps};
+  cuuint64_t wstr[2] = {C * eb, NT * C * eb};
+  cuuint32_t wbox[3] = {64, (cuuint32_t)N, 1}, westr[3] = {1, 1, 1};
+  r = encode(&pl->map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(weights), wdims, wstr, wbox, westr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    delete pl;
+    return conv_fail(LISEC_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: CUresult %d", (int)r);
+  }
+  int dev = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);  // per function, not per plan: the opt-in maximum
+  if (e != cudaSuccess) {
+    delete pl;
+    return conv_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
+  }
+  pl->device = dev;
+  pl->grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
+  *plan_out = pl;
+  return LISEC_OK;
+}
+
+int32_t lisec_conv_plan_run(lisec_conv_plan* pl, void* stream) {
+  if (!pl) return conv_fail(LISEC_ERR_BAD_ARG, "null plan");
+  cudaError_t e = launch_pdl(conv_igemm_kernel, pl->grid, kConvThreads, (size_t)pl->smem,
+                             static_cast<cudaStream_t>(stream), pl->map_a, pl->map_b, pl->p);
+  if (e != cudaSuccess) return conv_fail(LISEC_ERR_CUDA, "conv launch: %s", cudaGetErrorString(e));
+  return LISEC_OK;
+}
+
+int32_t lisec_conv_plan_output_shape(const lisec_conv_plan* pl, int32_t* odhw) {
+  if (!pl || !odhw) return conv_fail(LISEC_ERR_BAD_ARG, "null argument");
+  odhw[0] = pl->p.out_d;
+  odhw[1] = pl->p.out_h * pl->p.shuffle;
+  odhw[2] = pl->p.out_w * pl->p.shuffle;
+  return LISEC_OK;
+}
+
+void lisec_conv_plan_destroy(lisec_conv_plan* pl) { delete pl; }
+
+}  // extern "C"

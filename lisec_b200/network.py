@@ -1,0 +1,197 @@
+"""The dense network behind the voxel grid — middle Conv3D stack, RPN, heads (reference model_training.py:236-256) —
+as a list of tensor-core convolution plans (lisec_conv_plan_*, lisec_b200/csrc/conv.cu).
+
+Host side of SURVEY §8 row a12. What Keras builds layer by layer in createModel, this module builds plan by plan; the
+affine tails are folded on the host in float64 before anything is rounded to the bf16 operands:
+
+  addConv3DLayer (:191-196)  ZeroPadding3D + Conv3D(bias) + BatchNormalization + Dense(64, relu, no bias)
+      conv -> BN -> Dense is linear up to the ReLU:   W'[tap,ci,n] = sum_c K[tap,ci,c] g[c] Wd[c,n],
+      shift'[n] = sum_c ((bias[c] - mean[c]) g[c] + beta[c]) Wd[c,n],  g = gamma / sqrt(var + 1e-3)  -> one plan, ReLU
+  addConv2DLayer (:201-208)  Conv2D(bias) + BatchNormalization + ReLU -> scale = g, shift = (bias - mean) g + beta
+  Conv2DTranspose (:245,248,251, padding='same')  k3 s1 = 3x3 convolution with the kernel flipped; k2 s2 / k4 s4 do not
+      overlap = 1x1 GEMMs with k*k groups of 256 columns, pixel-shuffled by the epilogue. Each writes its 256-channel
+      slice of the Concatenate (:252) buffer directly.
+  ClassificationLayer + RegressionLayer (:253-254)  one 1x1 plan with N = 2 + 14 = 16 columns, float32 out.
+
+Activations are channels-last bf16 [B, D, H=x, W=y, C]; accumulation is float32 in TMEM. There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native
+from .weights import conv3d_blocks, rpn_blocks, validate_network_pack
+
+BN_EPS = 1e-3
+
+
+def best_tile(out_h: int, out_w: int) -> Tuple[int, int]:
+    """tile_w x tile_h = 128 output positions, tile_w a power of two: the shape that wastes the fewest positions."""
+    best = None
+    for lg in range(0, 8):
+        tw, th = 1 << lg, 128 >> lg
+        cover = -(-out_w // tw) * tw * -(-out_h // th) * th
+        key = (cover, abs(lg - 4))
+        if best is None or key < best[0]:
+            best = (key, (tw, th))
+    return best[1]
+
+
+def _bn_fold(pack, bn):
+    g = pack[bn + "/gamma"].astype(np.float64) / np.sqrt(pack[bn + "/moving_variance"].astype(np.float64) + BN_EPS)
+    return g, pack[bn + "/beta"].astype(np.float64) - pack[bn + "/moving_mean"].astype(np.float64) * g
+
+
+class _Layer:
+    def __init__(self, name, desc, w, scale, shift, src, dst):
+        self.name, self.desc, self.w, self.scale, self.shift, self.src, self.dst = name, desc, w, scale, shift, src, dst
+        self.plan = C.c_void_p()
+
+
+class DenseNetwork:
+    """Plans and activation buffers for one batch size and grid. `grid` is the input buffer the front end writes."""
+
+    def __init__(self, pack: dict, batch: int, nx: int = 200, ny: int = 400, nz: int = 8, device: int = 0):
+        if nz != 8 or nx % 8 or ny % 8:
+            raise ValueError("the Conv3D stack collapses nz = 8 to 1 and the RPN halves x, y three times: need nz = 8 "
+                             "and nx, ny multiples of 8 (got %d, %d, %d)" % (nz, nx, ny))
+        if not torch.cuda.is_available():
+            raise RuntimeError("lisec_b200 has no CPU fallback: a CUDA device is required")
+        self._lib = _native.load()
+        self.device = torch.device("cuda", device)
+        self.batch, self.nx, self.ny, self.nz = batch, nx, ny, nz
+        pack = validate_network_pack(pack)
+        bf = torch.bfloat16
+        dev = self.device
+
+        def buf(*shape, dtype=bf):
+            return torch.zeros(shape, dtype=dtype, device=dev)
+
+        B = batch
+        self.grid = buf(B, nz, nx, ny, 64)
+        self.layers: List[_Layer] = []
+        # ---- middle: three Conv3D blocks (:236-238) ----
+        src, d = self.grid, nz
+        for conv, bn, dense, stride, pad in conv3d_blocks():
+            K = pack[conv + "/kernel"].astype(np.float64).reshape(27, 64, 64)  # [tap (kd,kh,kw)][ci][c]
+            g, b0 = _bn_fold(pack, bn)
+            Wd = pack[dense + "/kernel"].astype(np.float64)
+            W = np.einsum("tic,c,cn->tni", K, g, Wd)
+            shift = (pack[conv + "/bias"].astype(np.float64) * g + b0) @ Wd
+            od = (d + 2 * pad[0] - 3) // stride[0] + 1
+            dst = buf(B, od, nx, ny, 64)
+            self._add(conv, src, dst, W, np.ones(64), shift, in_d=d, in_h=nx, in_w=ny, in_c=64, k=(3, 3, 3),
+                      stride_d=stride[0], stride_hw=1, pad=pad, out_c=64, relu=1)
+            src, d = dst, od
+        assert d == 1
+        # ---- RPN (:245-251) ----
+        h, w = nx, ny
+        self.concat = buf(B, 1, nx // 2, ny // 2, 768)
+        for bi, (convs, (tname, k, s, tc_in)) in enumerate(rpn_blocks()):
+            pp = None
+            for conv, bn, cin, cout, stride in convs:
+                K = pack[conv + "/kernel"].astype(np.float64).reshape(9, cin, cout)
+                g, b0 = _bn_fold(pack, bn)
+                W = K.transpose(0, 2, 1)
+                shift = pack[conv + "/bias"].astype(np.float64) * g + b0
+                oh, ow = h // stride, w // stride
+                if pp is None:
+                    pp = [buf(B, 1, oh, ow, cout), buf(B, 1, oh, ow, cout)]
+                dst = pp[0] if src is not pp[0] else pp[1]
+                self._add(conv, src, dst, W, g, shift, in_d=1, in_h=h, in_w=w, in_c=cin, k=(1, 3, 3), stride_d=1,
+                          stride_hw=stride, pad=(0, 1, 1), out_c=cout, relu=1)
+                src, h, w = dst, oh, ow
+            F = pack[tname + "/kernel"].astype(np.float64)  # (k, k, 256, cin)
+            bias = pack[tname + "/bias"].astype(np.float64)
+            if s == 1:  # 'same' k3 s1: out[y] = sum_ky in[y + 1 - ky] F[ky] = a 3x3 convolution with the flipped kernel
+                W = F[::-1, ::-1].reshape(9, 256, tc_in)
+                self._add(tname, src, self.concat, W, np.ones(256), bias, in_d=1, in_h=h, in_w=w, in_c=tc_in,
+                          k=(1, 3, 3), stride_d=1, stride_hw=1, pad=(0, 1, 1), out_c=256, relu=0, out_pitch=768,
+                          out_ch_off=256 * bi)
+            else:  # kernel == stride: out[s y + i] = in[y] F[i]
+                W = F.reshape(1, k * k * 256, tc_in)
+                self._add(tname, src, self.concat, W, np.ones(256), bias, in_d=1, in_h=h, in_w=w, in_c=tc_in,
+                          k=(1, 1, 1), stride_d=1, stride_hw=1, pad=(0, 0, 0), out_c=256, relu=0, out_pitch=768,
+                          out_ch_off=256 * bi, n_tiles=k * k, shuffle=s)
+        # ---- heads (:253-254): 2 + 14 columns of one 1x1 GEMM ----
+        Kh = np.concatenate([pack["ClassificationLayer/kernel"][0, 0], pack["RegressionLayer/kernel"][0, 0]], axis=1)
+        bh = np.concatenate([pack["ClassificationLayer/bias"], pack["RegressionLayer/bias"]]).astype(np.float64)
+        self.heads = buf(B, 1, nx // 2, ny // 2, 16, dtype=torch.float32)
+        self._add("heads", self.concat, self.heads, Kh.astype(np.float64).T.reshape(1, 16, 768), np.ones(16), bh, in_d=1,
+                  in_h=nx // 2, in_w=ny // 2, in_c=768, k=(1, 1, 1), stride_d=1, stride_hw=1, pad=(0, 0, 0), out_c=16,
+                  relu=0, out_dtype=_native.LISEC_F32)
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+
+    def _add(self, name, src, dst, W, scale, shift, *, in_d, in_h, in_w, in_c, k, stride_d, stride_hw, pad, out_c, relu,
+             out_pitch=None, out_ch_off=0, n_tiles=1, shuffle=1, out_dtype=_native.LISEC_BF16):
+        od = (in_d + 2 * pad[0] - k[0]) // stride_d + 1
+        oh = (in_h + 2 * pad[1] - k[1]) // stride_hw + 1
+        ow = (in_w + 2 * pad[2] - k[2]) // stride_hw + 1
+        tw, th = best_tile(oh, ow)
+        desc = _native.lisec_conv_desc(
+            batch=self.batch, in_d=in_d, in_h=in_h, in_w=in_w, in_c=in_c, kd=k[0], kh=k[1], kw=k[2], stride_d=stride_d,
+            stride_hw=stride_hw, pad_d=pad[0], pad_h=pad[1], pad_w=pad[2], out_c=out_c, n_tiles=n_tiles, shuffle=shuffle,
+            out_pitch=out_pitch if out_pitch is not None else n_tiles * out_c if shuffle == 1 else out_c,
+            out_ch_off=out_ch_off, relu=relu, out_dtype=out_dtype, tile_w=tw, tile_h=th, reserved=0)
+        dev = self.device
+        w = torch.from_numpy(np.ascontiguousarray(W, dtype=np.float32)).to(dev).to(torch.bfloat16).contiguous()
+        sc = torch.from_numpy(np.ascontiguousarray(scale, dtype=np.float32)).to(dev)
+        sh = torch.from_numpy(np.ascontiguousarray(shift, dtype=np.float32)).to(dev)
+        layer = _Layer(name, desc, w, sc, sh, src, dst)
+        with torch.cuda.device(dev):
+            st = self._lib.lisec_conv_plan_create(C.byref(desc), C.c_void_p(src.data_ptr()), C.c_void_p(w.data_ptr()),
+                                                  C.c_void_p(sc.data_ptr()), C.c_void_p(sh.data_ptr()),
+                                                  C.c_void_p(dst.data_ptr()), C.byref(layer.plan))
+        if st != _native.LISEC_OK:
+            raise _native.LisecError(st, "%s: %s" % (name, self._lib.lisec_conv_last_error().decode()))
+        shape = (C.c_int32 * 3)()
+        self._lib.lisec_conv_plan_output_shape(layer.plan, shape)
+        want = tuple(dst.shape[1:4])
+        if tuple(shape) != want:
+            raise RuntimeError("%s: plan output %s does not match its buffer %s" % (name, tuple(shape), want))
+        self.layers.append(layer)
+
+    @property
+    def flops(self) -> float:
+        """Multiply-add count x 2 of one forward pass over the batch (algorithmic, un-padded)."""
+        total = 0.0
+        for L in self.layers:
+            d = L.desc
+            od = (d.in_d + 2 * d.pad_d - d.kd) // d.stride_d + 1
+            oh = (d.in_h + 2 * d.pad_h - d.kh) // d.stride_hw + 1
+            ow = (d.in_w + 2 * d.pad_w - d.kw) // d.stride_hw + 1
+            total += 2.0 * d.batch * od * oh * ow * d.kd * d.kh * d.kw * d.in_c * d.out_c * d.n_tiles
+        return total
+
+    def run_layers(self, first: int = 0, last: Optional[int] = None) -> None:
+        """Enqueue the plans [first, last) on the current torch stream."""
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        with torch.cuda.device(self.device):
+            for L in self.layers[first:last]:
+                st = self._lib.lisec_conv_plan_run(L.plan, stream)
+                if st != _native.LISEC_OK:
+                    raise _native.LisecError(st, "%s: %s" % (L.name, self._lib.lisec_conv_last_error().decode()))
+
+    def forward(self, grid: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """prob [B, nx/2, ny/2, 2], regress [B, nx/2, ny/2, 14] (float32 views of one buffer) from self.grid."""
+        if grid is not None and grid.data_ptr() != self.grid.data_ptr():
+            self.grid.copy_(grid)
+        self.run_layers()
+        return self.heads[:, 0, :, :, :2], self.heads[:, 0, :, :, 2:]
+
+    def close(self) -> None:
+        for L in self.layers:
+            if L.plan:
+                self._lib.lisec_conv_plan_destroy(L.plan)
+                L.plan = C.c_void_p()
+        self.layers = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

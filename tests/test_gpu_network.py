@@ -1,0 +1,111 @@
+"""Parity of the tensor-core convolution plans (middle Conv3D stack, RPN, heads) on the GPU.
+
+Two levels. (1) Every plan against a float32 torch-CPU convolution of the SAME operands (the GPU's own bf16 input
+buffer, the folded bf16 weights, scale, shift): this isolates the kernel — TMA boxes, padding, strides, the
+space-to-depth view, the pixel shuffle, channel offsets — from the folding; the only differences are summation order
+and the final bf16 rounding (2^-9). (2) The whole network against the float64 oracle that restates the Keras layers
+(oracle/network_oracle.py) from the un-folded weight pack: bf16 bar of north_star, 2e-2.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def layer_reference(L, src: torch.Tensor) -> torch.Tensor:
+    """float32 CPU result of one plan from its own operands: [B, OD, OH*s, OW*s, N] (N = out_c, or n_tiles*out_c)."""
+    d = L.desc
+    x = src.float().cpu().permute(0, 4, 1, 2, 3)
+    NT = d.n_tiles * d.out_c
+    w = L.w.float().cpu().reshape(d.kd, d.kh, d.kw, NT, d.in_c).permute(3, 4, 0, 1, 2)
+    y = F.conv3d(x, w, None, stride=(d.stride_d, d.stride_hw, d.stride_hw), padding=(d.pad_d, d.pad_h, d.pad_w))
+    sc, sh = L.scale.cpu(), L.shift.cpu()
+    if d.shuffle > 1:
+        s = d.shuffle
+        B, _, OD, OH, OW = y.shape
+        y = y.reshape(B, s, s, d.out_c, OD, OH, OW).permute(0, 3, 4, 5, 1, 6, 2).reshape(B, d.out_c, OD, OH * s, OW * s)
+    y = y * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1)
+    if d.relu:
+        y = torch.relu(y)
+    return y.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def rel_err(got, want):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    floor = np.sqrt(np.mean(want * want)) + 1e-30
+    return float((np.abs(got - want) / np.maximum(np.abs(want), floor)).max())
+
+
+@pytest.mark.parametrize("nx,ny,batch", [(24, 40, 2), (16, 8, 1), (40, 136, 1)])
+def test_every_plan_matches_a_float32_convolution_of_its_own_operands(nx, ny, batch):
+    from lisec_b200.network import DenseNetwork
+    from lisec_b200.weights import synthetic_network_pack
+
+    net = DenseNetwork(synthetic_network_pack(1), batch=batch, nx=nx, ny=ny)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    net.grid.copy_(torch.randn(net.grid.shape, generator=g).clamp_(min=-0.5).to(torch.bfloat16))
+    for i, L in enumerate(net.layers):
+        # poison the destination slice so an unwritten element cannot pass
+        if L.desc.out_ch_off == 0 and L.dst.shape[-1] == L.desc.out_c * (L.desc.n_tiles if L.desc.shuffle == 1 else 1):
+            L.dst.fill_(float("nan"))
+        net.run_layers(i, i + 1)
+        torch.cuda.synchronize()
+        want = layer_reference(L, L.src)
+        n = want.shape[-1]
+        got = L.dst[..., L.desc.out_ch_off:L.desc.out_ch_off + n].float().cpu()
+        assert got.shape == want.shape, (L.name, got.shape, want.shape)
+        assert torch.isfinite(got).all(), L.name
+        err = rel_err(got.numpy(), want.numpy())
+        assert err <= (1e-4 if L.desc.out_dtype == 0 else 6e-3), (L.name, err)
+    net.close()
+
+
+def test_network_matches_the_keras_oracle_bf16():
+    from lisec_b200.network import DenseNetwork
+    from lisec_b200.weights import synthetic_network_pack
+    from oracle import network_oracle as NO
+
+    pack = synthetic_network_pack(0)
+    nx, ny, batch = 24, 40, 2
+    net = DenseNetwork(pack, batch=batch, nx=nx, ny=ny)
+    g = torch.Generator(device="cpu").manual_seed(11)
+    grid = torch.rand((batch, 8, nx, ny, 64), generator=g).to(torch.bfloat16)
+    net.grid.copy_(grid)
+    prob, reg = net.forward()
+    torch.cuda.synchronize()
+    want_p, want_r = NO.network_forward(grid.float().numpy(), pack)
+    assert prob.shape == want_p.shape and reg.shape == want_r.shape
+    # bf16 operands, float32 accumulation: north_star's bf16 bar
+    assert rel_err(prob.cpu().numpy(), want_p) <= 2e-2
+    assert rel_err(reg.cpu().numpy(), want_r) <= 2e-2
+    net.close()
+
+
+def test_bad_descriptions_are_rejected():
+    from lisec_b200 import _native
+    import ctypes as C
+
+    lib = _native.load()
+    x = torch.zeros(1, 1, 8, 8, 64, dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros(9, 64, 64, dtype=torch.bfloat16, device="cuda")
+    s = torch.ones(64, device="cuda")
+    plan = C.c_void_p()
+
+    def create(**kw):
+        base = dict(batch=1, in_d=1, in_h=8, in_w=8, in_c=64, kd=1, kh=3, kw=3, stride_d=1, stride_hw=1, pad_d=0,
+                    pad_h=1, pad_w=1, out_c=64, n_tiles=1, shuffle=1, out_pitch=64, out_ch_off=0, relu=1, out_dtype=2,
+                    tile_w=16, tile_h=8, reserved=0)
+        base.update(kw)
+        d = _native.lisec_conv_desc(**base)
+        return lib.lisec_conv_plan_create(C.byref(d), x.data_ptr(), w.data_ptr(), s.data_ptr(), s.data_ptr(),
+                                          x.data_ptr(), C.byref(plan))
+
+    assert create(in_c=48) == -2 and b"in_c" in lib.lisec_conv_last_error()
+    assert create(out_c=24) == -2
+    assert create(tile_w=16, tile_h=4) == -2
+    assert create(stride_hw=3) == -2
+    assert create(out_pitch=32) == -2
+    assert create() == 0
+    lib.lisec_conv_plan_destroy(plan)
