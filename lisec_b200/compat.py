@@ -12,7 +12,9 @@
     tf.stack(points, axis=0)                   model_training.py:285   stack(list, axis=0)
     createModel(nx, ny, nz, maxPoints)         model_training.py:222   createModel(nx, ny, nz, maxPoints, weights=)
     load_model(path, custom_objects={...})     Predict.py:51-52        load_model(path, custom_objects=None)
-    model.predict(x)                           Predict.py:38           model.predict_voxel_grid(x)  (first 23 layers)
+    model.predict(x)                           Predict.py:38           model.predict(x) -> [prob, regress]  (bf16 tensor-core
+                                                                           middle + RPN, lisec_b200/network.py), and
+                                                                       model.predict_voxel_grid(x)  (first 23 layers only)
 
 What is different underneath: nothing is densified. SparseVoxelTensor and DenseVoxelInput are lazy handles on the
 sweep's points; the 537.6 MB-per-sweep dense input (README.md:58-64 of the reference) only exists if somebody asks
@@ -32,14 +34,14 @@ import torch
 
 from . import constants as K
 from .frontend import Frontend
-from .weights import load_npz, synthetic_vfe_pack
+from .weights import load_npz, synthetic_model_pack
 
 _FRONTENDS: dict = {}
 
 
-def _frontend(cfg_key, n_points: int, n_sweeps: int, device: int = 0) -> Frontend:
-    """One Frontend per (geometry, device); re-created with doubled capacity when a call outgrows it."""
-    key = (cfg_key, device)
+def _frontend(cfg_key, n_points: int, n_sweeps: int, device: int = 0, grid_dtype: str = "f32") -> Frontend:
+    """One Frontend per (geometry, device, grid dtype); re-created with doubled capacity when a call outgrows it."""
+    key = (cfg_key, device, grid_dtype)
     fe = _FRONTENDS.get(key)
     need_pts, need_sw = max(n_points, 1), max(n_sweeps, 1)
     if fe is None or fe.cfg.max_points < need_pts or fe.cfg.max_sweeps < need_sw:
@@ -50,7 +52,7 @@ def _frontend(cfg_key, n_points: int, n_sweeps: int, device: int = 0) -> Fronten
         if fe is not None:
             fe.close()
         fe = Frontend(device=device, max_points=cap_pts, max_sweeps=cap_sw, voxel_size=(xs, ys, zs),
-                      sample_size=T, max_voxel=(mx, my, mz))
+                      sample_size=T, max_voxel=(mx, my, mz), grid_dtype=grid_dtype)
         if weights is not None:
             fe.set_weights(weights)
             fe._pack = weights
@@ -174,14 +176,16 @@ class MaxPoolingVFELayer:  # model_training.py:44-61
 
 
 class VoxelNetFrontEnd:
-    """The first 23 Keras layers of createModel (model_training.py:229-235) with their weights."""
+    """createModel (model_training.py:222-257) with its weights: the first 23 Keras layers (VFE stack, :229-235) as the
+    fused front-end kernels, the rest (:236-256) as tensor-core convolution plans."""
 
     def __init__(self, nx, ny, nz, maxPoints, pack: dict):
         self.grid = (nz, nx, ny)
         self.maxPoints = maxPoints
         self.pack = pack
+        self._nets: dict = {}
 
-    def predict_voxel_grid(self, x: DenseVoxelInput, device: int = 0) -> torch.Tensor:
+    def _run_frontend(self, x: DenseVoxelInput, device: int, grid_dtype: str, out=None) -> torch.Tensor:
         if not isinstance(x, DenseVoxelInput):
             raise TypeError("expected the output of sparse.to_dense()/stack(); a materialised dense array would be "
                             "the 500 GB path this library exists to avoid")
@@ -194,17 +198,37 @@ class VoxelNetFrontEnd:
         dt = np.float32 if dts == {np.dtype("float32")} else np.float64
         pts = np.concatenate([s._points.astype(dt, copy=False) for s in x.sweeps])
         off = np.cumsum([0] + [len(s._points) for s in x.sweeps]).astype(np.int64)
-        fe = _frontend(cfg, len(pts), len(x.sweeps), device)
+        fe = _frontend(cfg, len(pts), len(x.sweeps), device, grid_dtype)
         if getattr(fe, "_pack", None) is not self.pack:
             fe.set_weights(self.pack)
             fe._pack = self.pack
-        return fe.forward_host(pts, off)
+        return fe.forward_host(pts, off, out=out)
+
+    def predict_voxel_grid(self, x: DenseVoxelInput, device: int = 0) -> torch.Tensor:
+        """The float32 [N, nz, nx, ny, 64] tensor the reference's first Conv3D consumes (:235-236), on the GPU."""
+        return self._run_frontend(x, device, "f32")
+
+    def predict(self, x: DenseVoxelInput, device: int = 0) -> list:
+        """model.predict(x) (Predict.py:38): [prob (N, nx/2, ny/2, 2), regress (N, nx/2, ny/2, 14)] float32 numpy arrays.
+        The front end writes a bf16 grid straight into the dense network's input buffer; the middle Conv3D stack, RPN
+        and heads run as bf16 tensor-core plans with float32 accumulation (lisec_b200/network.py)."""
+        from .network import DenseNetwork
+
+        n = len(x.sweeps) if isinstance(x, DenseVoxelInput) else 0
+        key = (n, device)
+        net = self._nets.get(key)
+        if net is None:
+            nz, nx, ny = self.grid
+            net = self._nets[key] = DenseNetwork(self.pack, batch=n, nx=nx, ny=ny, nz=nz, device=device)
+        self._run_frontend(x, device, "bf16", out=net.grid)
+        prob, reg = net.forward()
+        return [prob.contiguous().cpu().numpy(), reg.contiguous().cpu().numpy()]
 
 
 def createModel(nx=K.nx, ny=K.ny, nz=K.nz, maxPoints=K.maxPoints, weights: Optional[dict] = None, seed: int = 0):
     """model_training.py:222. Keras would random-initialise; `weights` (Keras-named arrays) or a seeded synthetic
     pack stands in."""
-    return VoxelNetFrontEnd(nx, ny, nz, maxPoints, weights if weights is not None else synthetic_vfe_pack(seed))
+    return VoxelNetFrontEnd(nx, ny, nz, maxPoints, weights if weights is not None else synthetic_model_pack(seed))
 
 
 def load_model(path: str, custom_objects: Optional[dict] = None, nx=K.nx, ny=K.ny, nz=K.nz, maxPoints=K.maxPoints):
