@@ -46,6 +46,17 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def tensor_peak():
+    """Dense bf16 TFLOP/s: the sustained figure (a kernel timed inside a long step)."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        if "bf16_tflops_sustained" in d:
+            return float(d["bf16_tflops_sustained"]), "measured sustained (MEASURED_PEAKS.json)"
+    return 1500.0, "fallback (B200_PROFILING.md)"
+
+
 # ---- CPU reference formulation (oracle port) ---------------------------------------------------------------
 def cpu_reference_time_per_sweep(points, vox_fraction, slab_cells_x, pack):
     """Seconds per sweep of the reference's CPU path, from a bounded sample:
@@ -209,11 +220,10 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from lisec_b200.sharding import max_over_ranks as _max_over_ranks
+
     def max_over_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return _max_over_ranks(x, device="cuda")
 
     pack = synthetic_vfe_pack(0)
     fe = Frontend(device=local, max_points=SWEEPS_PER_GPU * POINTS_PER_SWEEP, max_sweeps=SWEEPS_PER_GPU)
@@ -311,6 +321,38 @@ def run_native(args):
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     per, n_vox, n_in, n_oor, n_nf = last["counts"]
+
+    # configs[2] beside the headline: the whole inference forward (front end with a bf16 grid written straight into the
+    # dense network's input, then middle Conv3D + RPN + heads as bf16 tensor-core plans), same batches, same timing rules
+    full = None
+    if not args.no_full_inference:
+        from lisec_b200.network import DenseNetwork
+        from lisec_b200.weights import synthetic_network_pack
+
+        fe16 = Frontend(device=local, max_points=SWEEPS_PER_GPU * POINTS_PER_SWEEP, max_sweeps=SWEEPS_PER_GPU,
+                        grid_dtype="bf16")
+        fe16.set_weights(pack)
+        net = DenseNetwork(synthetic_network_pack(0), batch=SWEEPS_PER_GPU, device=local)
+
+        def step_full(i):
+            fe16.forward(dev_batches[i % N_BATCHES], offsets, out=net.grid)
+            net.forward()
+
+        for i in range(args.warmup):
+            step_full(i)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(args.steps):
+            step_full(i)
+        f1.record()
+        barrier()
+        ms_full = max_over_ranks(f0.elapsed_time(f1)) / args.steps
+        ms_net = timed(lambda: net.forward(), n_k)
+        full = {"ms_per_step": ms_full, "network_ms": ms_net, "flops_per_step": net.flops,
+                "launches_per_step": fe16.last_launch_count + len(net.layers)}
+        net.close()
+        fe16.close()
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
@@ -358,6 +400,20 @@ def run_native(args):
             "stages": stages,
             "clocks": clocks,
         }
+        if full is not None:
+            tpk, tsrc = tensor_peak()
+            tfl = full["flops_per_step"] / (full["network_ms"] * 1e-3) / 1e12
+            line["full_inference"] = {
+                "metric": "lidar sweeps/sec (voxelize+VFE+Conv3D+RPN+heads, full fwd)", "dtype": "bf16",
+                "workload": "configs[2] shape at the bench batch: 8 sweeps per GPU per step, outputs (8,100,200,2) + "
+                            "(8,100,200,14) float32",
+                "value": SWEEPS_PER_GPU * world / (full["ms_per_step"] * 1e-3), "unit": "sweeps/s",
+                "ms_per_step": full["ms_per_step"], "gpu_launches_per_step": full["launches_per_step"],
+                "roofline": {"kernel": "conv_igemm_kernel x %d (middle Conv3D + RPN + heads), timed alone"
+                                       % (full["launches_per_step"] - fe.last_launch_count),
+                             "bound": "tensor", "achieved": tfl, "peak": tpk, "unit": "TFLOP/s", "frac": tfl / tpk,
+                             "peak_source": tsrc, "algorithmic_flops_per_step": full["flops_per_step"],
+                             "ms_per_step": full["network_ms"], "traffic": None}}
         if world == 1 and not args.no_cpu_baseline:
             pts0 = base[0]
             t_vox, t_vfe = cpu_reference_time_per_sweep(pts0, 1.0, 200, pack)
@@ -380,6 +436,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-inference", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 3 if args.steps is None else args.steps
