@@ -208,7 +208,7 @@ int32_t lisec_last_launch_count(const lisec_handle* h);
  * are affine and are folded into (weights, scale, shift) by the host (lisec_b200/network.py).
  * shuffle = s > 1: a Conv2DTranspose whose kernel equals its stride s (:248, :251): a 1x1 GEMM with n_tiles = s*s
  * groups of out_c columns; group (i, j) lands at output position (s*h + i, s*w + j). out_h/out_w are then s x larger.
- * tile_w x tile_h = 128 output positions per CTA tile (tile_w a power of two). */
+ * tile_w x tile_h = 128 output positions per M-tile (tile_w a power of two). */
 typedef struct lisec_conv_desc {
   int32_t batch, in_d, in_h, in_w, in_c;
   int32_t kd, kh, kw;
@@ -219,6 +219,9 @@ typedef struct lisec_conv_desc {
   int32_t relu;      /* 1: ReLU after the affine */
   int32_t out_dtype; /* LISEC_BF16 or LISEC_F32 */
   int32_t tile_w, tile_h;
+  int32_t m_tiles;   /* 1 or 2 M-tiles stacked along H per CTA tile: they share every weight box (needs tile_w >= 8) */
+  int32_t group_kh;  /* 1: the kh taps of one (kd, kw) come from ONE input box with a kh-1 row halo; the weights are then
+                        ordered [kd][kw][kh][n_tiles*out_c][in_c] (stride_hw = 1 only) */
   int32_t reserved;
 } lisec_conv_desc;
 

@@ -12,6 +12,7 @@ import os
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblisec_b200.so")
 
 LISEC_OK = 0
+LISEC_ERR_BAD_CONFIG = -2
 LISEC_F32, LISEC_F64, LISEC_BF16 = 0, 1, 2
 LISEC_MAX_SWEEPS = 64
 ABI_VERSION = 1
@@ -71,7 +72,8 @@ class lisec_vfe_weights(C.Structure):
 class lisec_conv_desc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "batch", "in_d", "in_h", "in_w", "in_c", "kd", "kh", "kw", "stride_d", "stride_hw", "pad_d", "pad_h", "pad_w",
-        "out_c", "n_tiles", "shuffle", "out_pitch", "out_ch_off", "relu", "out_dtype", "tile_w", "tile_h", "reserved")]
+        "out_c", "n_tiles", "shuffle", "out_pitch", "out_ch_off", "relu", "out_dtype", "tile_w", "tile_h", "m_tiles",
+        "group_kh", "reserved")]
 
 
 _H = C.c_void_p

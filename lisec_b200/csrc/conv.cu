@@ -46,9 +46,11 @@ struct ConvParams {
   int tiles_w, tiles_h, out_d, batch, n_tiles;
   long long total_tiles;
   int bw, bw_log2, bh;
-  // K loop
-  int n_taps, c_blocks, N, stages;
-  // TMA coordinates of a tap: (c_off[t] + 64 cb, b1 + t1[t], b2 + t2[t], b3 + t3[t], b)
+  // K loop: n_taps shared-memory stages per 64-channel block; a stage carries `group` filter taps (the kh taps of one
+  // (kd, kw), built from row offsets of ONE input box with a kh-1 row halo) for `mt` M-tiles stacked along H
+  int n_taps, c_blocks, N, stages, group, mt;
+  uint32_t a_bytes, stage_bytes;
+  // TMA coordinates of a stage: (c_off[t] + 64 cb, b1 + t1[t], b2 + t2[t], b3 + t3[t], b)
   int s2d, stride_d;
   short c_off[kMaxTaps];
   signed char t1[kMaxTaps], t2[kMaxTaps], t3[kMaxTaps];
@@ -95,6 +97,43 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with the descriptors given as (low word, shared high word): the operand address lives in the low 14 bits of the
+// low word, so stepping through a stage is a 32-bit add per operand. The single issuing thread's instruction stream is
+// what paces the tensor pipe when the MMAs are small (N = 64), so every instruction per MMA counts.
+__device__ __forceinline__ void mma_bf16_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// the MMAs of one shared-memory stage: GROUP taps x MT M-tiles x 4 k-steps of 16 channels
+template <int GROUP, int MT>
+__device__ __forceinline__ void issue_stage(uint32_t a0, uint32_t b0, uint32_t d0, uint32_t N, uint32_t h_row16,
+                                            uint32_t bh, uint32_t idesc, uint32_t first) {
+  const uint64_t proto = umma::make_desc_k_sw128(0);
+  const uint32_t hi = (uint32_t)(proto >> 32), lo0 = (uint32_t)proto;
+  const uint32_t a_lo0 = lo0 + (a0 >> 4), b_lo0 = lo0 + (b0 >> 4), b_tap16 = N * 8u;  // N * 128 bytes / 16
+#pragma unroll
+  for (int g = 0; g < GROUP; ++g)
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      const uint32_t a_lo = a_lo0 + (uint32_t)(g + m * bh) * h_row16, b_lo = b_lo0 + (uint32_t)g * b_tap16;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        mma_bf16_ss_lo(d0 + (uint32_t)m * N, a_lo + 2 * j, b_lo + 2 * j, hi, idesc,
+                       (g == 0 && j == 0) ? first : 1u);
+    }
+}
+
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   asm volatile(
@@ -118,7 +157,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& P, long long 
   long long r = tile / P.n_tiles;
   t.ow0 = (int)(r % P.tiles_w) * P.bw;
   r /= P.tiles_w;
-  t.oh0 = (int)(r % P.tiles_h) * P.bh;
+  t.oh0 = (int)(r % P.tiles_h) * P.bh * P.mt;
   r /= P.tiles_h;
   t.od = (int)(r % P.out_d);
   t.b = (int)(r / P.out_d);
@@ -135,10 +174,19 @@ template <int NV>
 __device__ __forceinline__ void store_chunk(const ConvParams& P, const float (&x)[NV], int sidx0, size_t elem0,
                                             bool valid) {
   float y[NV];
+  const float4* sc = reinterpret_cast<const float4*>(P.scale + sidx0);  // sidx0 is a multiple of 16: 16-byte loads
+  const float4* sf = reinterpret_cast<const float4*>(P.shift + sidx0);
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    y[i] = fmaf(x[i], __ldg(P.scale + sidx0 + i), __ldg(P.shift + sidx0 + i));
-    if (P.relu) y[i] = fmaxf(y[i], 0.f);
+  for (int i = 0; i < NV / 4; ++i) {
+    const float4 a = __ldg(sc + i), b = __ldg(sf + i);
+    y[4 * i] = fmaf(x[4 * i], a.x, b.x);
+    y[4 * i + 1] = fmaf(x[4 * i + 1], a.y, b.y);
+    y[4 * i + 2] = fmaf(x[4 * i + 2], a.z, b.z);
+    y[4 * i + 3] = fmaf(x[4 * i + 3], a.w, b.w);
+  }
+  if (P.relu) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) y[i] = fmaxf(y[i], 0.f);
   }
   if (!valid) return;
   if (P.out_f32) {
@@ -162,8 +210,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = umma::smem_u32(smem);
   if (base & 1023u) __trap();
-  const uint32_t b_bytes = (uint32_t)P.N * 128u;
-  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t b_tap_bytes = (uint32_t)P.N * 128u;
+  const uint32_t stage_bytes = P.stage_bytes;
   const uint32_t bar0 = base + (uint32_t)P.stages * stage_bytes;
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
   auto bar_empty = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
@@ -207,7 +255,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
             mbar_arrive_expect_tx(bar_full(s), stage_bytes);
             const uint32_t dst = base + (uint32_t)s * stage_bytes;
             tma_load_5d(dst, &map_a, bar_full(s), P.c_off[tap] + 64 * cb, c1, c2, c3, t.b);
-            tma_load_3d(dst + kABytes, &map_b, bar_full(s), 64 * cb, t.nt * P.N, tap);
+            tma_load_3d(dst + P.a_bytes, &map_b, bar_full(s), 64 * cb, t.nt * P.N, tap * P.group);
             if (++s == P.stages) { s = 0; ph ^= 1u; }
           }
         }
@@ -222,15 +270,20 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       for (long long tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         umma::mbar_wait(bar_acc_empty(acc), acc_ph ^ 1u);
         umma::fence_after_sync();
-        const uint32_t d = tmem_base + (uint32_t)(acc * P.N);
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * P.mt * P.N);
+        const uint32_t h_row16 = (uint32_t)P.bw * 8u;  // one H row of the A box in 16-byte units (a multiple of 1 KB when used)
+        const int variant = (P.group == 3 ? 2 : 0) + (P.mt == 2 ? 1 : 0);
         for (int kb = 0; kb < k_blocks; ++kb) {
           umma::mbar_wait(bar_full(s), ph);
           umma::fence_after_sync();
-          const uint32_t a0 = base + (uint32_t)s * stage_bytes, b0 = a0 + kABytes;
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            mma_bf16_ss(d, umma::make_desc_k_sw128(a0 + 32 * j), umma::make_desc_k_sw128(b0 + 32 * j), idesc,
-                        (kb | j) != 0);
+          const uint32_t a0 = base + (uint32_t)s * stage_bytes, b0 = a0 + P.a_bytes;
+          const uint32_t first = kb != 0;
+          switch (variant) {
+            case 0: issue_stage<1, 1>(a0, b0, d0, (uint32_t)P.N, h_row16, (uint32_t)P.bh, idesc, first); break;
+            case 1: issue_stage<1, 2>(a0, b0, d0, (uint32_t)P.N, h_row16, (uint32_t)P.bh, idesc, first); break;
+            case 2: issue_stage<3, 1>(a0, b0, d0, (uint32_t)P.N, h_row16, (uint32_t)P.bh, idesc, first); break;
+            default: issue_stage<3, 2>(a0, b0, d0, (uint32_t)P.N, h_row16, (uint32_t)P.bh, idesc, first); break;
+          }
           umma::mma_commit(bar_empty(s));  // the stage is free again once these MMAs have read it
           if (++s == P.stages) { s = 0; ph ^= 1u; }
         }
@@ -246,25 +299,27 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     const int sh = P.shuffle;
     for (long long tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(P, tile);
-      const int oh = t.oh0 + (row >> P.bw_log2), ow = t.ow0 + (row & (P.bw - 1));
-      const bool valid = oh < P.out_h && ow < P.out_w;
       const int si = sh > 1 ? t.nt / sh : 0, sj = sh > 1 ? t.nt % sh : 0;
-      const size_t pix = (((size_t)t.b * P.out_d + t.od) * ((size_t)P.out_h * sh) + (size_t)oh * sh + si) *
-                             ((size_t)P.out_w * sh) + (size_t)ow * sh + sj;
       const int n0 = sh > 1 ? 0 : t.nt * P.N;  // scale/shift index and output channel of the tile's first column
-      const size_t elem = pix * (size_t)P.out_pitch + P.out_ch_off + n0;
       umma::mbar_wait(bar_acc_full(acc), acc_ph);
       umma::fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * P.N);
-      if (P.N == 16) {
-        float x[16];
-        tmem_ld_32x16(taddr, x);
-        store_chunk<16>(P, x, n0, elem, valid);
-      } else {
-        for (int c0 = 0; c0 < P.N; c0 += 32) {
-          float x[32];
-          umma::tmem_ld_32x32(taddr + c0, x);
-          store_chunk<32>(P, x, n0 + c0, elem + c0, valid);
+      for (int m = 0; m < P.mt; ++m) {
+        const int oh = t.oh0 + m * P.bh + (row >> P.bw_log2), ow = t.ow0 + (row & (P.bw - 1));
+        const bool valid = oh < P.out_h && ow < P.out_w;
+        const size_t pix = (((size_t)t.b * P.out_d + t.od) * ((size_t)P.out_h * sh) + (size_t)oh * sh + si) *
+                               ((size_t)P.out_w * sh) + (size_t)ow * sh + sj;
+        const size_t elem = pix * (size_t)P.out_pitch + P.out_ch_off + n0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((acc * P.mt + m) * P.N);
+        if (P.N == 16) {
+          float x[16];
+          tmem_ld_32x16(taddr, x);
+          store_chunk<16>(P, x, n0, elem, valid);
+        } else {
+          for (int c0 = 0; c0 < P.N; c0 += 32) {
+            float x[32];
+            umma::tmem_ld_32x32(taddr + c0, x);
+            store_chunk<32>(P, x, n0 + c0, elem + c0, valid);
+          }
         }
       }
       umma::fence_before_sync();
@@ -342,6 +397,14 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
                      d->tile_h);
   const int n_tiles = d->n_tiles < 1 ? 1 : d->n_tiles;
   const int shuffle = d->shuffle < 1 ? 1 : d->shuffle;
+  const int mt = d->m_tiles < 1 ? 1 : d->m_tiles;
+  const int group = d->group_kh ? d->kh : 1;
+  if (group != 1 && group != 3) return conv_fail(LISEC_ERR_BAD_CONFIG, "group_kh needs kh = 3");
+  if (mt > 2 || 2 * mt * N > 512) return conv_fail(LISEC_ERR_BAD_CONFIG, "m_tiles = %d with out_c = %d: 2 * m_tiles * out_c accumulator columns must fit 512", mt, N);
+  if ((mt > 1 || group > 1) && d->tile_w < 8)
+    return conv_fail(LISEC_ERR_BAD_CONFIG, "m_tiles / group_kh need tile_w >= 8 (1 KB-aligned H rows)");
+  if (group > 1 && (s != 1 || d->kh < 2)) return conv_fail(LISEC_ERR_BAD_CONFIG, "group_kh needs stride_hw = 1 and kh > 1");
+  if (d->tile_h * mt + group - 1 > 256) return conv_fail(LISEC_ERR_BAD_CONFIG, "input box taller than 256 rows");
   if (shuffle > 1 && (n_tiles != shuffle * shuffle || taps != 1))
     return conv_fail(LISEC_ERR_BAD_CONFIG, "pixel shuffle %d needs %d N-tiles and a 1x1 kernel", shuffle,
                      shuffle * shuffle);
@@ -367,34 +430,46 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
   p.bw_log2 = 0;
   while ((1 << p.bw_log2) < p.bw) ++p.bw_log2;
   p.tiles_w = (OW + p.bw - 1) / p.bw;
-  p.tiles_h = (OH + p.bh - 1) / p.bh;
+  p.tiles_h = (OH + p.bh * mt - 1) / (p.bh * mt);
+  p.mt = mt;
+  p.group = group;
   p.out_d = OD;
   p.batch = d->batch;
   p.n_tiles = n_tiles;
   p.total_tiles = (long long)n_tiles * p.tiles_w * p.tiles_h * OD * d->batch;
-  p.n_taps = taps;
+  p.n_taps = taps / group;
   p.c_blocks = C / 64;
   p.N = N;
   p.s2d = s == 2;
   p.stride_d = d->stride_d;
   int t = 0;
-  for (int kd = 0; kd < d->kd; ++kd)
-    for (int kh = 0; kh < d->kh; ++kh)
+  if (group > 1) {  // stages in (kd, kw) order; the box starts at the kh = 0 row and carries the kh-1 halo rows
+    for (int kd = 0; kd < d->kd; ++kd)
       for (int kw = 0; kw < d->kw; ++kw, ++t) {
-        if (s == 1) {
-          p.c_off[t] = 0;
-          p.t1[t] = (signed char)(kw - d->pad_w);
-          p.t2[t] = (signed char)(kh - d->pad_h);
-          p.t3[t] = (signed char)(kd - d->pad_d);
-        } else {  // input position 2*o + (k - pad) = 2*(o + q) + parity
-          const int uw = kw - d->pad_w, uh = kh - d->pad_h;
-          const int qw = floor_div(uw, 2), qh = floor_div(uh, 2);
-          p.c_off[t] = (short)((uw - 2 * qw) * C);
-          p.t1[t] = (signed char)qw;
-          p.t2[t] = (signed char)(uh - 2 * qh);
-          p.t3[t] = (signed char)qh;
-        }
+        p.c_off[t] = 0;
+        p.t1[t] = (signed char)(kw - d->pad_w);
+        p.t2[t] = (signed char)(-d->pad_h);
+        p.t3[t] = (signed char)(kd - d->pad_d);
       }
+  } else {
+    for (int kd = 0; kd < d->kd; ++kd)
+      for (int kh = 0; kh < d->kh; ++kh)
+        for (int kw = 0; kw < d->kw; ++kw, ++t) {
+          if (s == 1) {
+            p.c_off[t] = 0;
+            p.t1[t] = (signed char)(kw - d->pad_w);
+            p.t2[t] = (signed char)(kh - d->pad_h);
+            p.t3[t] = (signed char)(kd - d->pad_d);
+          } else {  // input position 2*o + (k - pad) = 2*(o + q) + parity
+            const int uw = kw - d->pad_w, uh = kh - d->pad_h;
+            const int qw = floor_div(uw, 2), qh = floor_div(uh, 2);
+            p.c_off[t] = (short)((uw - 2 * qw) * C);
+            p.t1[t] = (signed char)qw;
+            p.t2[t] = (signed char)(uh - 2 * qh);
+            p.t3[t] = (signed char)qh;
+          }
+        }
+  }
   p.out_h = OH;
   p.out_w = OW;
   p.shuffle = shuffle;
@@ -405,9 +480,20 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
   p.scale = scale;
   p.shift = shift;
   p.out = out;
-  const uint32_t stage_bytes = kABytes + (uint32_t)N * 128u;
-  int stages = (int)((200u * 1024u) / stage_bytes);
+  const int box_h = p.bh * mt + group - 1;
+  p.a_bytes = (uint32_t)(p.bw * box_h) * 128u;
+  p.stage_bytes = p.a_bytes + (uint32_t)(group * N) * 128u;
+  const uint32_t stage_bytes = p.stage_bytes;
+  if (stage_bytes % 1024u) {
+    delete pl;
+    return conv_fail(LISEC_ERR_BAD_CONFIG, "stage of %u bytes is not 1 KB-aligned", stage_bytes);
+  }
+  int stages = (int)((220u * 1024u) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) {
+    delete pl;
+    return conv_fail(LISEC_ERR_BAD_CONFIG, "a stage of %u bytes leaves room for fewer than 2 stages", stage_bytes);
+  }
   p.stages = stages;
   pl->smem = stages * (int)stage_bytes + 8 * (2 * kMaxStages + 4) + 16;
 
@@ -419,11 +505,11 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
   if (s == 1) {
     dims[0] = C; dims[1] = W; dims[2] = H; dims[3] = D; dims[4] = B;
     strides[0] = C * eb; strides[1] = W * C * eb; strides[2] = H * W * C * eb; strides[3] = D * H * W * C * eb;
-    box[0] = 64; box[1] = p.bw; box[2] = p.bh; box[3] = 1; box[4] = 1;
+    box[0] = 64; box[1] = p.bw; box[2] = box_h; box[3] = 1; box[4] = 1;
   } else {
     dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = B;
     strides[0] = 2 * C * eb; strides[1] = W * C * eb; strides[2] = 2 * W * C * eb; strides[3] = H * W * C * eb;
-    box[0] = 64; box[1] = p.bw; box[2] = 1; box[3] = p.bh; box[4] = 1;
+    box[0] = 64; box[1] = p.bw; box[2] = 1; box[3] = box_h; box[4] = 1;
   }
   CUresult r = encode(&pl->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -435,7 +521,7 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
   const cuuint64_t NT = (cuuint64_t)n_tiles * N;
   cuuint64_t wdims[3] = {(cuuint64_t)C, NT, (cuuint64_t)taps};
   cuuint64_t wstr[2] = {C * eb, NT * C * eb};
-  cuuint32_t wbox[3] = {64, (cuuint32_t)N, 1}, westr[3] = {1, 1, 1};
+  cuuint32_t wbox[3] = {64, (cuuint32_t)N, (cuuint32_t)group}, westr[3] = {1, 1, 1};
   r = encode(&pl->map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(weights), wdims, wstr, wbox, westr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

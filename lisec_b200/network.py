@@ -29,12 +29,15 @@ from .weights import conv3d_blocks, rpn_blocks, validate_network_pack
 BN_EPS = 1e-3
 
 
-def best_tile(out_h: int, out_w: int) -> Tuple[int, int]:
-    """tile_w x tile_h = 128 output positions, tile_w a power of two: the shape that wastes the fewest positions."""
+def best_tile(out_h: int, out_w: int, m_tiles: int = 1, min_w: int = 1) -> Tuple[int, int]:
+    """tile_w x tile_h = 128 output positions per M-tile, tile_w a power of two: the shape whose CTA tiles
+    (tile_w x m_tiles*tile_h) waste the fewest positions."""
     best = None
     for lg in range(0, 8):
         tw, th = 1 << lg, 128 >> lg
-        cover = -(-out_w // tw) * tw * -(-out_h // th) * th
+        if tw < min_w:
+            continue
+        cover = -(-out_w // tw) * tw * -(-out_h // (th * m_tiles)) * th * m_tiles
         key = (cover, abs(lg - 4))
         if best is None or key < best[0]:
             best = (key, (tw, th))
@@ -52,10 +55,21 @@ class _Layer:
         self.plan = C.c_void_p()
 
 
+def default_schedule(k, stride_hw: int, in_c: int, out_c: int, n_tiles: int) -> List[Tuple[int, int]]:
+    """Candidate (m_tiles, group_kh) settings of a layer, best first; the first one the library accepts is used.
+    The kernel is bound by L2 -> shared-memory delivery (profiles/conv_r1j_summary.txt): fetching the kh taps from one
+    halo box cuts the input traffic, two M-tiles per weight box halve the weight traffic. Both need room — 2 * m_tiles *
+    out_c accumulator columns <= 512 and at least two pipeline stages of shared memory — which the library checks."""
+    mts = (2, 1) if out_c <= 128 else (1,)
+    groups = (1, 0) if (stride_hw == 1 and k[1] == 3) else (0,)
+    return [(mt, g) for g in groups for mt in mts]
+
+
 class DenseNetwork:
     """Plans and activation buffers for one batch size and grid. `grid` is the input buffer the front end writes."""
 
-    def __init__(self, pack: dict, batch: int, nx: int = 200, ny: int = 400, nz: int = 8, device: int = 0):
+    def __init__(self, pack: dict, batch: int, nx: int = 200, ny: int = 400, nz: int = 8, device: int = 0,
+                 schedule=default_schedule):
         if nz != 8 or nx % 8 or ny % 8:
             raise ValueError("the Conv3D stack collapses nz = 8 to 1 and the RPN halves x, y three times: need nz = 8 "
                              "and nx, ny multiples of 8 (got %d, %d, %d)" % (nz, nx, ny))
@@ -64,6 +78,7 @@ class DenseNetwork:
         self._lib = _native.load()
         self.device = torch.device("cuda", device)
         self.batch, self.nx, self.ny, self.nz = batch, nx, ny, nz
+        self._schedule = schedule
         pack = validate_network_pack(pack)
         bf = torch.bfloat16
         dev = self.device
@@ -131,21 +146,34 @@ class DenseNetwork:
         od = (in_d + 2 * pad[0] - k[0]) // stride_d + 1
         oh = (in_h + 2 * pad[1] - k[1]) // stride_hw + 1
         ow = (in_w + 2 * pad[2] - k[2]) // stride_hw + 1
-        tw, th = best_tile(oh, ow)
-        desc = _native.lisec_conv_desc(
-            batch=self.batch, in_d=in_d, in_h=in_h, in_w=in_w, in_c=in_c, kd=k[0], kh=k[1], kw=k[2], stride_d=stride_d,
-            stride_hw=stride_hw, pad_d=pad[0], pad_h=pad[1], pad_w=pad[2], out_c=out_c, n_tiles=n_tiles, shuffle=shuffle,
-            out_pitch=out_pitch if out_pitch is not None else n_tiles * out_c if shuffle == 1 else out_c,
-            out_ch_off=out_ch_off, relu=relu, out_dtype=out_dtype, tile_w=tw, tile_h=th, reserved=0)
         dev = self.device
-        w = torch.from_numpy(np.ascontiguousarray(W, dtype=np.float32)).to(dev).to(torch.bfloat16).contiguous()
         sc = torch.from_numpy(np.ascontiguousarray(scale, dtype=np.float32)).to(dev)
         sh = torch.from_numpy(np.ascontiguousarray(shift, dtype=np.float32)).to(dev)
-        layer = _Layer(name, desc, w, sc, sh, src, dst)
-        with torch.cuda.device(dev):
-            st = self._lib.lisec_conv_plan_create(C.byref(desc), C.c_void_p(src.data_ptr()), C.c_void_p(w.data_ptr()),
-                                                  C.c_void_p(sc.data_ptr()), C.c_void_p(sh.data_ptr()),
-                                                  C.c_void_p(dst.data_ptr()), C.byref(layer.plan))
+        cands = self._schedule(k, stride_hw, in_c, out_c, n_tiles)
+        if isinstance(cands, tuple):
+            cands = [cands]
+        layer, st = None, _native.LISEC_OK
+        for m_tiles, group_kh in cands:
+            tw, th = best_tile(oh, ow, m_tiles, 8 if (m_tiles > 1 or group_kh) else 1)
+            Wk = np.asarray(W)
+            if group_kh:  # the kernel wants the kh taps of one (kd, kw) adjacent: [kd][kw][kh][N][C]
+                Wk = Wk.reshape(k[0], k[1], k[2], -1, in_c).transpose(0, 2, 1, 3, 4).reshape(k[0] * k[1] * k[2], -1, in_c)
+            desc = _native.lisec_conv_desc(
+                batch=self.batch, in_d=in_d, in_h=in_h, in_w=in_w, in_c=in_c, kd=k[0], kh=k[1], kw=k[2],
+                stride_d=stride_d, stride_hw=stride_hw, pad_d=pad[0], pad_h=pad[1], pad_w=pad[2], out_c=out_c,
+                n_tiles=n_tiles, shuffle=shuffle,
+                out_pitch=out_pitch if out_pitch is not None else n_tiles * out_c if shuffle == 1 else out_c,
+                out_ch_off=out_ch_off, relu=relu, out_dtype=out_dtype, tile_w=tw, tile_h=th, m_tiles=m_tiles,
+                group_kh=group_kh, reserved=0)
+            w = torch.from_numpy(np.ascontiguousarray(Wk, dtype=np.float32)).to(dev).to(torch.bfloat16).contiguous()
+            layer = _Layer(name, desc, w, sc, sh, src, dst)
+            with torch.cuda.device(dev):
+                st = self._lib.lisec_conv_plan_create(C.byref(desc), C.c_void_p(src.data_ptr()),
+                                                      C.c_void_p(w.data_ptr()), C.c_void_p(sc.data_ptr()),
+                                                      C.c_void_p(sh.data_ptr()), C.c_void_p(dst.data_ptr()),
+                                                      C.byref(layer.plan))
+            if st != _native.LISEC_ERR_BAD_CONFIG:
+                break
         if st != _native.LISEC_OK:
             raise _native.LisecError(st, "%s: %s" % (name, self._lib.lisec_conv_last_error().decode()))
         shape = (C.c_int32 * 3)()

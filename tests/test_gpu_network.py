@@ -19,7 +19,10 @@ def layer_reference(L, src: torch.Tensor) -> torch.Tensor:
     d = L.desc
     x = src.float().cpu().permute(0, 4, 1, 2, 3)
     NT = d.n_tiles * d.out_c
-    w = L.w.float().cpu().reshape(d.kd, d.kh, d.kw, NT, d.in_c).permute(3, 4, 0, 1, 2)
+    if d.group_kh:  # stored [kd][kw][kh][NT][C]
+        w = L.w.float().cpu().reshape(d.kd, d.kw, d.kh, NT, d.in_c).permute(3, 4, 0, 2, 1)
+    else:
+        w = L.w.float().cpu().reshape(d.kd, d.kh, d.kw, NT, d.in_c).permute(3, 4, 0, 1, 2)
     y = F.conv3d(x, w, None, stride=(d.stride_d, d.stride_hw, d.stride_hw), padding=(d.pad_d, d.pad_h, d.pad_w))
     sc, sh = L.scale.cpu(), L.shift.cpu()
     if d.shuffle > 1:
@@ -47,12 +50,25 @@ def rel_err(got, want):
     return float((np.abs(got - want) / np.maximum(np.abs(want), floor)).max())
 
 
+def _plain(k, stride_hw, in_c, out_c, n_tiles):
+    return [(1, 0)]
+
+
+def _two_tiles(k, stride_hw, in_c, out_c, n_tiles):
+    return [(2, 0), (1, 0)]
+
+
+def _halo_one_tile(k, stride_hw, in_c, out_c, n_tiles):
+    return [(1, 1), (1, 0)]
+
+
+@pytest.mark.parametrize("schedule", [None, _plain, _two_tiles, _halo_one_tile])
 @pytest.mark.parametrize("nx,ny,batch", [(24, 40, 2), (16, 8, 1), (40, 136, 1)])
-def test_every_plan_matches_a_float32_convolution_of_its_own_operands(nx, ny, batch):
-    from lisec_b200.network import DenseNetwork
+def test_every_plan_matches_a_float32_convolution_of_its_own_operands(nx, ny, batch, schedule):
+    from lisec_b200.network import DenseNetwork, default_schedule
     from lisec_b200.weights import synthetic_network_pack
 
-    net = DenseNetwork(synthetic_network_pack(1), batch=batch, nx=nx, ny=ny)
+    net = DenseNetwork(synthetic_network_pack(1), batch=batch, nx=nx, ny=ny, schedule=schedule or default_schedule)
     g = torch.Generator(device="cpu").manual_seed(5)
     net.grid.copy_(torch.randn(net.grid.shape, generator=g).clamp_(min=-0.5).to(torch.bfloat16))
     for i, L in enumerate(net.layers):

@@ -14,7 +14,14 @@ from lisec_b200.weights import synthetic_network_pack  # noqa: E402
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 check = len(sys.argv) > 2 and sys.argv[2] == "check"
 pack = synthetic_network_pack(0)
-net = DenseNetwork(pack, batch=batch)
+sched = os.environ.get("NET_SCHED")  # e.g. "1,1" = (m_tiles, group_kh) for every layer that accepts it
+if sched:
+    from lisec_b200.network import default_schedule
+
+    want = tuple(int(x) for x in sched.split(","))
+    net = DenseNetwork(pack, batch=batch, schedule=lambda *a: [want] + default_schedule(*a) + [(1, 0)])
+else:
+    net = DenseNetwork(pack, batch=batch)
 g = torch.Generator(device="cpu").manual_seed(3)
 grid = torch.rand((1, 8, 200, 400, 64), generator=g).to(torch.bfloat16)
 for b in range(batch):
@@ -41,7 +48,8 @@ for L, ms in zip(net.layers, acc):
     ow = (d.in_w + 2 * d.pad_w - d.kw) // d.stride_hw + 1
     fl = 2.0 * d.batch * od * oh * ow * d.kd * d.kh * d.kw * d.in_c * d.out_c * d.n_tiles
     tot += ms
-    print("%-20s %8.3f ms  %7.1f TFLOP/s  tile %dx%d" % (L.name, ms, fl / ms / 1e9, d.tile_w, d.tile_h))
+    print("%-20s %8.3f ms  %7.1f TFLOP/s  tile %dx%d x%d%s" % (L.name, ms, fl / ms / 1e9, d.tile_w, d.tile_h, d.m_tiles,
+                                                               " kh-halo" if d.group_kh else ""))
 t0 = torch.cuda.Event(enable_timing=True)
 t1 = torch.cuda.Event(enable_timing=True)
 t0.record()
