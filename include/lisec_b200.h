@@ -206,9 +206,15 @@ int32_t lisec_last_launch_count(const lisec_handle* h);
  * ZeroPadding3D/2D + 'valid' convolution (:192-193, :202-203) — and strides (stride_d, stride_hw, stride_hw).
  * BatchNormalization, the convolution bias and, for the Conv3D blocks, the bias-free Dense that follows the BN (:194-195)
  * are affine and are folded into (weights, scale, shift) by the host (lisec_b200/network.py).
- * shuffle = s > 1: a Conv2DTranspose whose kernel equals its stride s (:248, :251): a 1x1 GEMM with n_tiles = s*s
- * groups of out_c columns; group (i, j) lands at output position (s*h + i, s*w + j). out_h/out_w are then s x larger.
- * tile_w x tile_h = 128 output positions per M-tile (tile_w a power of two). */
+ * shuffle = s > 1: a Conv2DTranspose whose kernel equals its stride s (:248, :251): a 1x1 GEMM with s*s groups of
+ * columns; group (i, j) lands at output position (s*h + i, s*w + j). out_h/out_w are then s x larger. A group is
+ * n_tiles / (s*s) consecutive N-tiles of out_c columns each (usually 1).
+ * tile_w x tile_h = 128 output positions per M-tile (tile_w a power of two).
+ * in_dtype = LISEC_F32: every operand is a PAIR of float32 planes (hi = x rounded to tf32, lo = x - hi):
+ *   in [2][batch, in_d, in_h, in_w, in_c], weights [2][taps][n_tiles*out_c][in_c], out [2][...] when out_split = 1;
+ * each product is evaluated as Ah*Bl + Al*Bh + Ah*Bh on the tf32 tensor-core path with float32 accumulation, which
+ * reproduces a float32 FMA chain (tools/umma_probe.cu); the partial sums leave the tensor core every 64 channels and are
+ * added in float32 registers. m_tiles = 1, group_kh = 0, out_dtype = LISEC_F32, out_c <= 128 (wider layers: n_tiles). */
 typedef struct lisec_conv_desc {
   int32_t batch, in_d, in_h, in_w, in_c;
   int32_t kd, kh, kw;
@@ -220,6 +226,8 @@ typedef struct lisec_conv_desc {
   int32_t out_dtype; /* LISEC_BF16 or LISEC_F32 */
   int32_t tile_w, tile_h;
   int32_t m_tiles;   /* 1 or 2 M-tiles stacked along H per CTA tile: they share every weight box (needs tile_w >= 8) */
+  int32_t in_dtype;  /* LISEC_BF16, or LISEC_F32 = 3xTF32 (float32-grade products, see below) */
+  int32_t out_split; /* float32 plans: 1 = write hi / lo planes for the next float32 plan, 0 = plain float32 */
   int32_t group_kh;  /* 1: the kh taps of one (kd, kw) come from ONE input box with a kh-1 row halo; the weights are then
                         ordered [kd][kw][kh][n_tiles*out_c][in_c] (stride_hw = 1 only) */
   int32_t reserved;
@@ -232,6 +240,8 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* desc, const void* in, cons
                                const float* shift, void* out, lisec_conv_plan** plan);
 /* [async] One kernel launch on `stream`. */
 int32_t lisec_conv_plan_run(lisec_conv_plan* plan, void* stream);
+/* [async] x[n] float32 -> hi[n], lo[n]: the operand planes a float32 plan reads (n a multiple of 4). */
+int32_t lisec_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
 /* out_dhw[3] = output depth, height, width (after the pixel shuffle). */
 int32_t lisec_conv_plan_output_shape(const lisec_conv_plan* plan, int32_t* out_dhw);
 void lisec_conv_plan_destroy(lisec_conv_plan* plan);

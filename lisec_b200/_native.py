@@ -73,7 +73,7 @@ class lisec_conv_desc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "batch", "in_d", "in_h", "in_w", "in_c", "kd", "kh", "kw", "stride_d", "stride_hw", "pad_d", "pad_h", "pad_w",
         "out_c", "n_tiles", "shuffle", "out_pitch", "out_ch_off", "relu", "out_dtype", "tile_w", "tile_h", "m_tiles",
-        "group_kh", "reserved")]
+        "in_dtype", "out_split", "group_kh", "reserved")]
 
 
 _H = C.c_void_p
@@ -106,6 +106,7 @@ SIGNATURES = {
     "lisec_conv_plan_create": (C.c_int32, [C.POINTER(lisec_conv_desc), _VP, _VP, _VP, _VP, _VP, C.POINTER(_H)]),
     "lisec_conv_plan_run": (C.c_int32, [_H, _VP]),
     "lisec_conv_plan_output_shape": (C.c_int32, [_H, _I32P]),
+    "lisec_split_tf32": (C.c_int32, [_VP, _VP, _VP, C.c_int64, _VP]),
     "lisec_conv_plan_destroy": (None, [_H]),
     "lisec_conv_last_error": (C.c_char_p, []),
 }

@@ -49,7 +49,12 @@ struct ConvParams {
   // K loop: n_taps shared-memory stages per 64-channel block; a stage carries `group` filter taps (the kh taps of one
   // (kd, kw), built from row offsets of ONE input box with a kh-1 row halo) for `mt` M-tiles stacked along H
   int n_taps, c_blocks, N, stages, group, mt;
-  uint32_t a_bytes, stage_bytes;
+  uint32_t a_bytes, stage_bytes;  // a_bytes: ONE A operand image; f32 mode stages are [A hi][A lo][B hi][B lo]
+  // float32 mode (3xTF32): 32 channels per 128-byte row; the lo planes are the same tensor maps at batch + lo_batch /
+  // tap + lo_tap; the epilogue splits its float32 result into hi / lo planes out_lo_off elements apart (0: no split)
+  int f32, cpb, lo_batch, lo_tap;
+  int nsub;  // N-tiles per pixel-shuffle group (1 without shuffle)
+  long long out_lo_off;
   // TMA coordinates of a stage: (c_off[t] + 64 cb, b1 + t1[t], b2 + t2[t], b3 + t3[t], b)
   int s2d, stride_d;
   short c_off[kMaxTaps];
@@ -134,6 +139,36 @@ __device__ __forceinline__ void issue_stage(uint32_t a0, uint32_t b0, uint32_t d
     }
 }
 
+__device__ __forceinline__ void mma_tf32_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// float32 mode: one stage = 32 channels = 4 k-steps of 8; per k-step the 3xTF32 triple, small terms first so that their
+// sum is not rounded against the large one (as in the VFE kernel's FCN): Ah*Bl, Al*Bh, Ah*Bh.
+__device__ __forceinline__ void issue_stage_tf32(uint32_t a0, uint32_t a_bytes, uint32_t b0, uint32_t b_bytes, uint32_t d0,
+                                                 uint32_t idesc, uint32_t first) {
+  const uint64_t proto = umma::make_desc_k_sw128(0);
+  const uint32_t hi = (uint32_t)(proto >> 32), lo0 = (uint32_t)proto;
+  const uint32_t ah = lo0 + (a0 >> 4), al = ah + (a_bytes >> 4), bh = lo0 + (b0 >> 4), bl = bh + (b_bytes >> 4);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    mma_tf32_ss_lo(d0, ah + 2 * j, bl + 2 * j, hi, idesc, j == 0 ? first : 1u);
+    mma_tf32_ss_lo(d0, al + 2 * j, bh + 2 * j, hi, idesc, 1u);
+    mma_tf32_ss_lo(d0, ah + 2 * j, bh + 2 * j, hi, idesc, 1u);
+  }
+}
+
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   asm volatile(
@@ -191,14 +226,59 @@ __device__ __forceinline__ void store_chunk(const ConvParams& P, const float (&x
   if (!valid) return;
   if (P.out_f32) {
     float4* dst = reinterpret_cast<float4*>(static_cast<float*>(P.out) + elem0);
+    if (P.out_lo_off) {  // the next layer's 3xTF32 operands: hi = rn_tf32(y), lo = rn_tf32(y - hi)
+      float4* dlo = reinterpret_cast<float4*>(static_cast<float*>(P.out) + elem0 + P.out_lo_off);
 #pragma unroll
-    for (int i = 0; i < NV / 4; ++i) dst[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+      for (int i = 0; i < NV / 4; ++i) {
+        float h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma::tf32_split(y[4 * i + k], h[k], l[k]);
+        dst[i] = make_float4(h[0], h[1], h[2], h[3]);
+        dlo[i] = make_float4(l[0], l[1], l[2], l[3]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV / 4; ++i) dst[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+    }
   } else {
     uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(P.out) + elem0);
 #pragma unroll
     for (int i = 0; i < NV / 8; ++i)
       dst[i] = make_uint4(pack2(y[8 * i], y[8 * i + 1]), pack2(y[8 * i + 2], y[8 * i + 3]),
                           pack2(y[8 * i + 4], y[8 * i + 5]), pack2(y[8 * i + 6], y[8 * i + 7]));
+  }
+}
+
+// ===== TMA producer (one thread): every stage of every tile of this CTA, in order =====
+__device__ __forceinline__ void producer_loop(const ConvParams& P, const CUtensorMap& map_a, const CUtensorMap& map_b,
+                                              uint32_t base, uint32_t bar0) {
+  const uint32_t b_tap_bytes = (uint32_t)P.N * 128u, stage_bytes = P.stage_bytes;
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
+  int s = 0;
+  uint32_t ph = 0;
+  for (long long tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+    const TileCoord t = decode_tile(P, tile);
+    const int b1 = t.ow0, b2 = P.s2d ? 0 : t.oh0, b3 = P.s2d ? t.oh0 : t.od * P.stride_d;
+    for (int tap = 0; tap < P.n_taps; ++tap) {
+      const int c1 = b1 + P.t1[tap], c2 = b2 + P.t2[tap], c3 = b3 + P.t3[tap];
+      for (int cb = 0; cb < P.c_blocks; ++cb) {
+        umma::mbar_wait(bar_empty(s), ph ^ 1u);
+        mbar_arrive_expect_tx(bar_full(s), stage_bytes);
+        const uint32_t dst = base + (uint32_t)s * stage_bytes;
+        const int c0 = P.c_off[tap] + P.cpb * cb;
+        if (!P.f32) {
+          tma_load_5d(dst, &map_a, bar_full(s), c0, c1, c2, c3, t.b);
+          tma_load_3d(dst + P.a_bytes, &map_b, bar_full(s), P.cpb * cb, t.nt * P.N, tap * P.group);
+        } else {
+          tma_load_5d(dst, &map_a, bar_full(s), c0, c1, c2, c3, t.b);
+          tma_load_5d(dst + P.a_bytes, &map_a, bar_full(s), c0, c1, c2, c3, t.b + P.lo_batch);
+          tma_load_3d(dst + 2 * P.a_bytes, &map_b, bar_full(s), P.cpb * cb, t.nt * P.N, tap);
+          tma_load_3d(dst + 2 * P.a_bytes + b_tap_bytes, &map_b, bar_full(s), P.cpb * cb, t.nt * P.N, tap + P.lo_tap);
+        }
+        if (++s == P.stages) { s = 0; ph ^= 1u; }
+      }
+    }
   }
 }
 
@@ -242,25 +322,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   const int k_blocks = P.n_taps * P.c_blocks;
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (long long tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(P, tile);
-        const int b1 = t.ow0, b2 = P.s2d ? 0 : t.oh0, b3 = P.s2d ? t.oh0 : t.od * P.stride_d;
-        for (int tap = 0; tap < P.n_taps; ++tap) {
-          const int c1 = b1 + P.t1[tap], c2 = b2 + P.t2[tap], c3 = b3 + P.t3[tap];
-          for (int cb = 0; cb < P.c_blocks; ++cb) {
-            umma::mbar_wait(bar_empty(s), ph ^ 1u);
-            mbar_arrive_expect_tx(bar_full(s), stage_bytes);
-            const uint32_t dst = base + (uint32_t)s * stage_bytes;
-            tma_load_5d(dst, &map_a, bar_full(s), P.c_off[tap] + 64 * cb, c1, c2, c3, t.b);
-            tma_load_3d(dst + P.a_bytes, &map_b, bar_full(s), 64 * cb, t.nt * P.N, tap * P.group);
-            if (++s == P.stages) { s = 0; ph ^= 1u; }
-          }
-        }
-      }
-    }
+    if (lane == 0) producer_loop(P, map_a, map_b, base, bar0);
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
@@ -299,8 +361,9 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     const int sh = P.shuffle;
     for (long long tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(P, tile);
-      const int si = sh > 1 ? t.nt / sh : 0, sj = sh > 1 ? t.nt % sh : 0;
-      const int n0 = sh > 1 ? 0 : t.nt * P.N;  // scale/shift index and output channel of the tile's first column
+      const int grp = t.nt / P.nsub;  // pixel-shuffle group (i, j); its out_c channels may span nsub N-tiles
+      const int si = sh > 1 ? grp / sh : 0, sj = sh > 1 ? grp % sh : 0;
+      const int n0 = sh > 1 ? (t.nt % P.nsub) * P.N : t.nt * P.N;  // scale/shift index and output channel of column 0
       umma::mbar_wait(bar_acc_full(acc), acc_ph);
       umma::fence_after_sync();
       for (int m = 0; m < P.mt; ++m) {
@@ -331,6 +394,137 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 1) umma::tmem_dealloc<512>(tmem_base);
+}
+
+// ---- float32 plans: 3xTF32 with the partial sums promoted to the FP32 pipe every 64 channels --------------------
+// The tensor core's float32 accumulator does not round to nearest: a sum of several hundred MMAs into one accumulator
+// drifts by ~1e-5..1e-4 of its magnitude (measured 6e-5 on the K = 1728 Conv3D), past north_star's 1e-5. So an
+// accumulator only ever takes ONE 64-channel chunk (2 stages, 24 MMAs, as in the VFE kernel's FCN: 1e-6); the
+// epilogue warps add the chunks in registers (round-to-nearest FADD) while the next chunk's MMAs run into the other
+// accumulator. A thread keeps its row's N running sums in registers, so float32 plans take out_c <= 128; wider layers
+// run as several N-tiles (n_tiles, also inside a pixel-shuffle group).
+constexpr int kConvF32Threads = 192;
+
+__global__ void __launch_bounds__(kConvF32Threads, 1)
+    conv_igemm_f32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                          const __grid_constant__ ConvParams P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = umma::smem_u32(smem);
+  if (base & 1023u) __trap();
+  const uint32_t b_tap_bytes = (uint32_t)P.N * 128u;
+  const uint32_t stage_bytes = P.stage_bytes;
+  const uint32_t bar0 = base + (uint32_t)P.stages * stage_bytes;
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
+  auto bar_acc_full = [&](int a) { return bar0 + 8u * (2 * kMaxStages + a); };
+  auto bar_acc_empty = [&](int a) { return bar0 + 8u * (2 * kMaxStages + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (size_t)P.stages * stage_bytes + 8 * (2 * kMaxStages + 4));
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
+    for (int s = 0; s < P.stages; ++s) {
+      umma::mbar_init(bar_full(s), 1);
+      umma::mbar_init(bar_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      umma::mbar_init(bar_acc_full(a), 1);
+      umma::mbar_init(bar_acc_empty(a), 4);
+    }
+    umma::mbar_init_fence();
+  }
+  if (warp == 1) umma::tmem_alloc<512>(tmem_slot);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  const int chunks = P.n_taps * P.c_blocks / 2;  // 64 channels = 2 stages of 32 per chunk (in_c is a multiple of 64)
+  if (warp == 0) {
+    if (lane == 0) producer_loop(P, map_a, map_b, base, bar0);
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma::make_idesc_tf32_k(128, P.N);
+      int s = 0, acc = 0;
+      uint32_t ph = 0, acc_ph = 0;
+      for (long long tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x)
+        for (int c = 0; c < chunks; ++c) {
+          umma::mbar_wait(bar_acc_empty(acc), acc_ph ^ 1u);
+          umma::fence_after_sync();
+          const uint32_t d0 = tmem_base + (uint32_t)(acc * P.N);
+          for (int h = 0; h < 2; ++h) {
+            umma::mbar_wait(bar_full(s), ph);
+            umma::fence_after_sync();
+            const uint32_t a0 = base + (uint32_t)s * stage_bytes;
+            issue_stage_tf32(a0, P.a_bytes, a0 + 2 * P.a_bytes, b_tap_bytes, d0, idesc, (uint32_t)h);
+            umma::mma_commit(bar_empty(s));
+            if (++s == P.stages) { s = 0; ph ^= 1u; }
+          }
+          umma::mma_commit(bar_acc_full(acc));
+          if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+        }
+    }
+  } else {
+    const int q = warp & 3, row = 32 * q + lane;
+    const int ncols = P.N, col0 = 0;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    const int sh = P.shuffle;
+    for (long long tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      float sum[8][16];
+      for (int c = 0; c < chunks; ++c) {
+        umma::mbar_wait(bar_acc_full(acc), acc_ph);
+        umma::fence_after_sync();
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * P.N + col0);
+#pragma unroll
+        for (int g = 0; g < 8; ++g)  // 16 columns at a time: 128 running sums + 16 fresh values stay in registers
+          if (16 * g < ncols) {
+            float x[16];
+            tmem_ld_32x16(taddr + 16 * g, x);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sum[g][i] = c ? __fadd_rn(sum[g][i], x[i]) : x[i];
+          }
+        umma::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(bar_acc_empty(acc));
+        if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+      }
+      const TileCoord t = decode_tile(P, tile);
+      const int grp = t.nt / P.nsub;
+      const int si = sh > 1 ? grp / sh : 0, sj = sh > 1 ? grp % sh : 0;
+      const int n0 = (sh > 1 ? (t.nt % P.nsub) * P.N : t.nt * P.N) + col0;
+      const int oh = t.oh0 + (row >> P.bw_log2), ow = t.ow0 + (row & (P.bw - 1));
+      const bool valid = oh < P.out_h && ow < P.out_w;
+      const size_t pix = (((size_t)t.b * P.out_d + t.od) * ((size_t)P.out_h * sh) + (size_t)oh * sh + si) *
+                             ((size_t)P.out_w * sh) + (size_t)ow * sh + sj;
+      const size_t elem = pix * (size_t)P.out_pitch + P.out_ch_off + n0;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        if (16 * g < ncols) store_chunk<16>(P, sum[g], n0 + 16 * g, elem + 16 * g, valid);
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) umma::tmem_dealloc<512>(tmem_base);
+}
+
+// x -> (hi, lo) tf32 operand planes of the float32 plans (the front end's float32 grid feeds the first Conv3D)
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi,
+                                                         float4* __restrict__ lo, long long n4) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldcs(x + i);
+    float4 h, l;
+    umma::tf32_split(v.x, h.x, l.x);
+    umma::tf32_split(v.y, h.y, l.y);
+    umma::tf32_split(v.z, h.z, l.z);
+    umma::tf32_split(v.w, h.w, l.w);
+    hi[i] = h;
+    lo[i] = l;
+  }
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
@@ -383,6 +577,12 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
     return conv_fail(LISEC_ERR_BAD_ARG, "null argument");
   *plan_out = nullptr;
   const int C = d->in_c, N = d->out_c;
+  const bool f32 = d->in_dtype == LISEC_F32;
+  if (!f32 && d->in_dtype != LISEC_BF16) return conv_fail(LISEC_ERR_BAD_CONFIG, "in_dtype: LISEC_BF16 or LISEC_F32");
+  if (f32 && (d->m_tiles > 1 || d->group_kh || d->out_dtype != LISEC_F32))
+    return conv_fail(LISEC_ERR_BAD_CONFIG, "float32 plans: m_tiles = 1, group_kh = 0, float32 output");
+  if (!f32 && d->out_split) return conv_fail(LISEC_ERR_BAD_CONFIG, "out_split is the float32 plans' hi/lo output");
+  const int cpb = f32 ? 32 : 64;
   if (C < 64 || C % 64) return conv_fail(LISEC_ERR_BAD_CONFIG, "in_c = %d: need a multiple of 64", C);
   if (N < 16 || N > 256 || N % 16) return conv_fail(LISEC_ERR_BAD_CONFIG, "out_c = %d: need 16..256, multiple of 16", N);
   if (N != 16 && N % 32) return conv_fail(LISEC_ERR_BAD_CONFIG, "out_c = %d: need 16 or a multiple of 32", N);
@@ -405,9 +605,11 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
     return conv_fail(LISEC_ERR_BAD_CONFIG, "m_tiles / group_kh need tile_w >= 8 (1 KB-aligned H rows)");
   if (group > 1 && (s != 1 || d->kh < 2)) return conv_fail(LISEC_ERR_BAD_CONFIG, "group_kh needs stride_hw = 1 and kh > 1");
   if (d->tile_h * mt + group - 1 > 256) return conv_fail(LISEC_ERR_BAD_CONFIG, "input box taller than 256 rows");
-  if (shuffle > 1 && (n_tiles != shuffle * shuffle || taps != 1))
-    return conv_fail(LISEC_ERR_BAD_CONFIG, "pixel shuffle %d needs %d N-tiles and a 1x1 kernel", shuffle,
+  if (shuffle > 1 && (n_tiles % (shuffle * shuffle) || taps != 1))
+    return conv_fail(LISEC_ERR_BAD_CONFIG, "pixel shuffle %d needs a multiple of %d N-tiles and a 1x1 kernel", shuffle,
                      shuffle * shuffle);
+  const int nsub = shuffle > 1 ? n_tiles / (shuffle * shuffle) : 1;
+  if (f32 && N > 128) return conv_fail(LISEC_ERR_BAD_CONFIG, "float32 plans take out_c <= 128 per N-tile (got %d)", N);
   if (d->batch < 1 || d->in_d < 1 || d->in_h < 1 || d->in_w < 1 || d->stride_d < 1)
     return conv_fail(LISEC_ERR_BAD_ARG, "bad input shape");
   const int OD = (d->in_d + 2 * d->pad_d - d->kd) / d->stride_d + 1;
@@ -415,7 +617,7 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
   const int OW = (d->in_w + 2 * d->pad_w - d->kw) / s + 1;
   if (OD < 1 || OH < 1 || OW < 1) return conv_fail(LISEC_ERR_BAD_CONFIG, "empty output");
   const int align = d->out_dtype == LISEC_F32 ? 4 : 8;
-  if (d->out_pitch % align || d->out_ch_off % align || d->out_pitch < d->out_ch_off + (shuffle > 1 ? N : n_tiles * N))
+  if (d->out_pitch % align || d->out_ch_off % align || d->out_pitch < d->out_ch_off + (shuffle > 1 ? nsub * N : n_tiles * N))
     return conv_fail(LISEC_ERR_BAD_CONFIG, "out_pitch %d / out_ch_off %d: need multiples of %d and room for %d channels",
                      d->out_pitch, d->out_ch_off, align, N);
   if (d->out_dtype != LISEC_F32 && d->out_dtype != LISEC_BF16) return conv_fail(LISEC_ERR_BAD_CONFIG, "out_dtype");
@@ -438,7 +640,12 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
   p.n_tiles = n_tiles;
   p.total_tiles = (long long)n_tiles * p.tiles_w * p.tiles_h * OD * d->batch;
   p.n_taps = taps / group;
-  p.c_blocks = C / 64;
+  p.c_blocks = C / cpb;
+  p.f32 = f32;
+  p.cpb = cpb;
+  p.lo_batch = d->batch;
+  p.lo_tap = taps;
+  p.nsub = nsub;
   p.N = N;
   p.s2d = s == 2;
   p.stride_d = d->stride_d;
@@ -480,9 +687,11 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
   p.scale = scale;
   p.shift = shift;
   p.out = out;
+  // hi / lo output planes: [2][batch, out_d, out_h*shuffle, out_w*shuffle, out_pitch]
+  p.out_lo_off = d->out_split ? (long long)d->batch * OD * ((long long)OH * shuffle) * ((long long)OW * shuffle) * d->out_pitch : 0;
   const int box_h = p.bh * mt + group - 1;
   p.a_bytes = (uint32_t)(p.bw * box_h) * 128u;
-  p.stage_bytes = p.a_bytes + (uint32_t)(group * N) * 128u;
+  p.stage_bytes = (p.a_bytes + (uint32_t)(group * N) * 128u) * (f32 ? 2u : 1u);
   const uint32_t stage_bytes = p.stage_bytes;
   if (stage_bytes % 1024u) {
     delete pl;
@@ -498,20 +707,22 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
   pl->smem = stages * (int)stage_bytes + 8 * (2 * kMaxStages + 4) + 16;
 
   // tensor maps (bf16, 128-byte swizzle, zero fill out of bounds)
-  const cuuint64_t eb = 2;
+  const cuuint64_t eb = f32 ? 4 : 2;
+  const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const cuuint64_t planes = f32 ? 2 : 1;  // hi / lo operand planes ride on the outermost dimension
   cuuint64_t dims[5], strides[4];
   cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
   const cuuint64_t W = d->in_w, H = d->in_h, D = d->in_d, B = d->batch;
   if (s == 1) {
-    dims[0] = C; dims[1] = W; dims[2] = H; dims[3] = D; dims[4] = B;
+    dims[0] = C; dims[1] = W; dims[2] = H; dims[3] = D; dims[4] = B * planes;
     strides[0] = C * eb; strides[1] = W * C * eb; strides[2] = H * W * C * eb; strides[3] = D * H * W * C * eb;
-    box[0] = 64; box[1] = p.bw; box[2] = box_h; box[3] = 1; box[4] = 1;
+    box[0] = cpb; box[1] = p.bw; box[2] = box_h; box[3] = 1; box[4] = 1;
   } else {
-    dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = B;
+    dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = B * planes;
     strides[0] = 2 * C * eb; strides[1] = W * C * eb; strides[2] = 2 * W * C * eb; strides[3] = H * W * C * eb;
-    box[0] = 64; box[1] = p.bw; box[2] = 1; box[3] = box_h; box[4] = 1;
+    box[0] = cpb; box[1] = p.bw; box[2] = 1; box[3] = box_h; box[4] = 1;
   }
-  CUresult r = encode(&pl->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), dims, strides, box, estr,
+  CUresult r = encode(&pl->map_a, dt, 5, const_cast<void*>(in), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -519,10 +730,10 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
     return conv_fail(LISEC_ERR_CUDA, "cuTensorMapEncodeTiled(input) failed: CUresult %d", (int)r);
   }
   const cuuint64_t NT = (cuuint64_t)n_tiles * N;
-  cuuint64_t wdims[3] = {(cuuint64_t)C, NT, (cuuint64_t)taps};
+  cuuint64_t wdims[3] = {(cuuint64_t)C, NT, (cuuint64_t)taps * planes};
   cuuint64_t wstr[2] = {C * eb, NT * C * eb};
-  cuuint32_t wbox[3] = {64, (cuuint32_t)N, (cuuint32_t)group}, westr[3] = {1, 1, 1};
-  r = encode(&pl->map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(weights), wdims, wstr, wbox, westr,
+  cuuint32_t wbox[3] = {(cuuint32_t)cpb, (cuuint32_t)N, (cuuint32_t)group}, westr[3] = {1, 1, 1};
+  r = encode(&pl->map_b, dt, 3, const_cast<void*>(weights), wdims, wstr, wbox, westr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -534,6 +745,8 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);  // per function, not per plan: the opt-in maximum
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_igemm_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   if (e != cudaSuccess) {
     delete pl;
     return conv_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
@@ -546,9 +759,25 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
 
 int32_t lisec_conv_plan_run(lisec_conv_plan* pl, void* stream) {
   if (!pl) return conv_fail(LISEC_ERR_BAD_ARG, "null plan");
-  cudaError_t e = launch_pdl(conv_igemm_kernel, pl->grid, kConvThreads, (size_t)pl->smem,
-                             static_cast<cudaStream_t>(stream), pl->map_a, pl->map_b, pl->p);
+  cudaError_t e = pl->p.f32 ? launch_pdl(conv_igemm_f32_kernel, pl->grid, kConvF32Threads, (size_t)pl->smem,
+                                         static_cast<cudaStream_t>(stream), pl->map_a, pl->map_b, pl->p)
+                            : launch_pdl(conv_igemm_kernel, pl->grid, kConvThreads, (size_t)pl->smem,
+                                         static_cast<cudaStream_t>(stream), pl->map_a, pl->map_b, pl->p);
   if (e != cudaSuccess) return conv_fail(LISEC_ERR_CUDA, "conv launch: %s", cudaGetErrorString(e));
+  return LISEC_OK;
+}
+
+int32_t lisec_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
+  if (!x || !hi || !lo || n < 0 || n % 4) return conv_fail(LISEC_ERR_BAD_ARG, "split: null pointer or n not a multiple of 4");
+  if (n == 0) return LISEC_OK;
+  int dev = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e == cudaSuccess)
+    e = launch_pdl(split_tf32_kernel, sms * 8, 256, 0, static_cast<cudaStream_t>(stream),
+                   reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo),
+                   (long long)(n / 4));
+  if (e != cudaSuccess) return conv_fail(LISEC_ERR_CUDA, "split launch: %s", cudaGetErrorString(e));
   return LISEC_OK;
 }
 

@@ -13,7 +13,12 @@ affine tails are folded on the host in float64 before anything is rounded to the
       slice of the Concatenate (:252) buffer directly.
   ClassificationLayer + RegressionLayer (:253-254)  one 1x1 plan with N = 2 + 14 = 16 columns, float32 out.
 
-Activations are channels-last bf16 [B, D, H=x, W=y, C]; accumulation is float32 in TMEM. There is no CPU fallback.
+Activations are channels-last [B, D, H=x, W=y, C]; accumulation is float32 in TMEM. Two arithmetic modes:
+  dtype="bf16"  bf16 operands and activations (north_star's 2e-2 bar), the fast path;
+  dtype="f32"   every operand is a pair of float32 planes (hi = tf32-rounded, lo = remainder) and every product runs as
+                3xTF32 (Ah*Bl + Al*Bh + Ah*Bh), which reproduces float32 products (north_star's 1e-5 bar); activations
+                are stored as [2][B, D, H, W, C] hi/lo planes by each plan's epilogue.
+There is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -44,6 +49,12 @@ def best_tile(out_h: int, out_w: int, m_tiles: int = 1, min_w: int = 1) -> Tuple
     return best[1]
 
 
+def tf32_round(x: np.ndarray) -> np.ndarray:
+    """float32 -> nearest tf32 (10 mantissa bits), ties away from zero: what cvt.rna.tf32.f32 does on the device."""
+    b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
 def _bn_fold(pack, bn):
     g = pack[bn + "/gamma"].astype(np.float64) / np.sqrt(pack[bn + "/moving_variance"].astype(np.float64) + BN_EPS)
     return g, pack[bn + "/beta"].astype(np.float64) - pack[bn + "/moving_mean"].astype(np.float64) * g
@@ -69,7 +80,7 @@ class DenseNetwork:
     """Plans and activation buffers for one batch size and grid. `grid` is the input buffer the front end writes."""
 
     def __init__(self, pack: dict, batch: int, nx: int = 200, ny: int = 400, nz: int = 8, device: int = 0,
-                 schedule=default_schedule):
+                 schedule=default_schedule, dtype: str = "bf16"):
         if nz != 8 or nx % 8 or ny % 8:
             raise ValueError("the Conv3D stack collapses nz = 8 to 1 and the RPN halves x, y three times: need nz = 8 "
                              "and nx, ny multiples of 8 (got %d, %d, %d)" % (nz, nx, ny))
@@ -78,19 +89,25 @@ class DenseNetwork:
         self._lib = _native.load()
         self.device = torch.device("cuda", device)
         self.batch, self.nx, self.ny, self.nz = batch, nx, ny, nz
-        self._schedule = schedule
+        if dtype not in ("bf16", "f32"):
+            raise ValueError("dtype must be 'bf16' or 'f32', got %r" % (dtype,))
+        self.f32 = dtype == "f32"
+        self._schedule = (lambda *a: [(1, 0)]) if self.f32 else schedule
         pack = validate_network_pack(pack)
-        bf = torch.bfloat16
         dev = self.device
+        f32 = self.f32
 
-        def buf(*shape, dtype=bf):
-            return torch.zeros(shape, dtype=dtype, device=dev)
+        def buf(*shape, dtype=None, planes=True):
+            if f32:  # hi / lo planes in front
+                return torch.zeros(((2,) if planes else ()) + shape, dtype=torch.float32, device=dev)
+            return torch.zeros(shape, dtype=dtype or torch.bfloat16, device=dev)
 
         B = batch
-        self.grid = buf(B, nz, nx, ny, 64)
+        self.grid = buf(B, nz, nx, ny, 64, planes=False)  # what the front end writes: bf16, or plain float32
+        self.grid_planes = buf(B, nz, nx, ny, 64) if f32 else self.grid
         self.layers: List[_Layer] = []
         # ---- middle: three Conv3D blocks (:236-238) ----
-        src, d = self.grid, nz
+        src, d = self.grid_planes, nz
         for conv, bn, dense, stride, pad in conv3d_blocks():
             K = pack[conv + "/kernel"].astype(np.float64).reshape(27, 64, 64)  # [tap (kd,kh,kw)][ci][c]
             g, b0 = _bn_fold(pack, bn)
@@ -135,14 +152,22 @@ class DenseNetwork:
         # ---- heads (:253-254): 2 + 14 columns of one 1x1 GEMM ----
         Kh = np.concatenate([pack["ClassificationLayer/kernel"][0, 0], pack["RegressionLayer/kernel"][0, 0]], axis=1)
         bh = np.concatenate([pack["ClassificationLayer/bias"], pack["RegressionLayer/bias"]]).astype(np.float64)
-        self.heads = buf(B, 1, nx // 2, ny // 2, 16, dtype=torch.float32)
+        self.heads = buf(B, 1, nx // 2, ny // 2, 16, dtype=torch.float32, planes=False)
         self._add("heads", self.concat, self.heads, Kh.astype(np.float64).T.reshape(1, 16, 768), np.ones(16), bh, in_d=1,
                   in_h=nx // 2, in_w=ny // 2, in_c=768, k=(1, 1, 1), stride_d=1, stride_hw=1, pad=(0, 0, 0), out_c=16,
-                  relu=0, out_dtype=_native.LISEC_F32)
+                  relu=0, out_dtype=_native.LISEC_F32, out_split=0)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
 
     def _add(self, name, src, dst, W, scale, shift, *, in_d, in_h, in_w, in_c, k, stride_d, stride_hw, pad, out_c, relu,
-             out_pitch=None, out_ch_off=0, n_tiles=1, shuffle=1, out_dtype=_native.LISEC_BF16):
+             out_pitch=None, out_ch_off=0, n_tiles=1, shuffle=1, out_dtype=None, out_split=None):
+        if out_dtype is None:
+            out_dtype = _native.LISEC_F32 if self.f32 else _native.LISEC_BF16
+        if out_split is None:
+            out_split = 1 if self.f32 else 0
+        if out_pitch is None:
+            out_pitch = n_tiles * out_c if shuffle == 1 else out_c
+        if self.f32 and out_c > 128:  # float32 plans keep a row's running sums in registers: N-tiles of 128 columns
+            n_tiles, out_c = n_tiles * (out_c // 128), 128
         od = (in_d + 2 * pad[0] - k[0]) // stride_d + 1
         oh = (in_h + 2 * pad[1] - k[1]) // stride_hw + 1
         ow = (in_w + 2 * pad[2] - k[2]) // stride_hw + 1
@@ -162,10 +187,16 @@ class DenseNetwork:
                 batch=self.batch, in_d=in_d, in_h=in_h, in_w=in_w, in_c=in_c, kd=k[0], kh=k[1], kw=k[2],
                 stride_d=stride_d, stride_hw=stride_hw, pad_d=pad[0], pad_h=pad[1], pad_w=pad[2], out_c=out_c,
                 n_tiles=n_tiles, shuffle=shuffle,
-                out_pitch=out_pitch if out_pitch is not None else n_tiles * out_c if shuffle == 1 else out_c,
+                out_pitch=out_pitch,
                 out_ch_off=out_ch_off, relu=relu, out_dtype=out_dtype, tile_w=tw, tile_h=th, m_tiles=m_tiles,
+                in_dtype=_native.LISEC_F32 if self.f32 else _native.LISEC_BF16, out_split=out_split,
                 group_kh=group_kh, reserved=0)
-            w = torch.from_numpy(np.ascontiguousarray(Wk, dtype=np.float32)).to(dev).to(torch.bfloat16).contiguous()
+            if self.f32:  # hi / lo planes of the float64-folded weights
+                hi = tf32_round(Wk.astype(np.float32))
+                lo = (Wk.astype(np.float64) - hi.astype(np.float64)).astype(np.float32)
+                w = torch.from_numpy(np.stack([hi, lo])).to(dev).contiguous()
+            else:
+                w = torch.from_numpy(np.ascontiguousarray(Wk, dtype=np.float32)).to(dev).to(torch.bfloat16).contiguous()
             layer = _Layer(name, desc, w, sc, sh, src, dst)
             with torch.cuda.device(dev):
                 st = self._lib.lisec_conv_plan_create(C.byref(desc), C.c_void_p(src.data_ptr()),
@@ -178,7 +209,7 @@ class DenseNetwork:
             raise _native.LisecError(st, "%s: %s" % (name, self._lib.lisec_conv_last_error().decode()))
         shape = (C.c_int32 * 3)()
         self._lib.lisec_conv_plan_output_shape(layer.plan, shape)
-        want = tuple(dst.shape[1:4])
+        want = tuple(dst.shape[-4:-1])
         if tuple(shape) != want:
             raise RuntimeError("%s: plan output %s does not match its buffer %s" % (name, tuple(shape), want))
         self.layers.append(layer)
@@ -208,6 +239,13 @@ class DenseNetwork:
         """prob [B, nx/2, ny/2, 2], regress [B, nx/2, ny/2, 14] (float32 views of one buffer) from self.grid."""
         if grid is not None and grid.data_ptr() != self.grid.data_ptr():
             self.grid.copy_(grid)
+        if self.f32:  # the front end's float32 grid -> the first plan's hi / lo operand planes
+            with torch.cuda.device(self.device):
+                st = self._lib.lisec_split_tf32(C.c_void_p(self.grid.data_ptr()), C.c_void_p(self.grid_planes[0].data_ptr()),
+                                                C.c_void_p(self.grid_planes[1].data_ptr()), self.grid.numel(),
+                                                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+            if st != _native.LISEC_OK:
+                raise _native.LisecError(st, self._lib.lisec_conv_last_error().decode())
         self.run_layers()
         return self.heads[:, 0, :, :, :2], self.heads[:, 0, :, :, 2:]
 

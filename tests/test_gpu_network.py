@@ -87,6 +87,63 @@ def test_every_plan_matches_a_float32_convolution_of_its_own_operands(nx, ny, ba
     net.close()
 
 
+def test_float32_plans_match_a_float64_convolution_of_their_own_operands():
+    """3xTF32: hi + lo operand planes in, hi + lo out. Against float64 of the same operands the result carries only
+    float32-grade rounding (products to ~2^-22, float32 accumulation, the final hi/lo split to 2^-21)."""
+    from lisec_b200.network import DenseNetwork
+    from lisec_b200.weights import synthetic_network_pack
+
+    net = DenseNetwork(synthetic_network_pack(1), batch=1, nx=24, ny=40, dtype="f32")
+    g = torch.Generator(device="cpu").manual_seed(7)
+    net.grid.copy_(torch.randn(net.grid.shape, generator=g).clamp_(min=-0.5))
+    net.forward()
+    torch.cuda.synchronize()
+    x, planes = net.grid.double().cpu(), net.grid_planes.double().sum(0).cpu()
+    assert float(((planes - x).abs() / x.abs().clamp_min(1e-30)).max()) <= 2.0 ** -21  # hi + lo = x to 2 x 11 bits
+    for i, L in enumerate(net.layers):  # one plan at a time: the ping-pong buffers are reused down the network
+        net.run_layers(i, i + 1)
+        torch.cuda.synchronize()
+        d = L.desc
+        x = L.src.double().sum(0).cpu().permute(0, 4, 1, 2, 3)
+        NT = d.n_tiles * d.out_c
+        w = L.w.double().sum(0).cpu().reshape(d.kd, d.kh, d.kw, NT, d.in_c).permute(3, 4, 0, 1, 2)
+        y = F.conv3d(x, w, None, stride=(d.stride_d, d.stride_hw, d.stride_hw), padding=(d.pad_d, d.pad_h, d.pad_w))
+        if d.shuffle > 1:
+            s = d.shuffle
+            B, _, OD, OH, OW = y.shape
+            co = NT // (s * s)
+            y = y.reshape(B, s, s, co, OD, OH, OW).permute(0, 3, 4, 5, 1, 6, 2).reshape(B, co, OD, OH * s, OW * s)
+        y = y * L.scale.double().cpu().view(1, -1, 1, 1, 1) + L.shift.double().cpu().view(1, -1, 1, 1, 1)
+        if d.relu:
+            y = torch.relu(y)
+        want = y.permute(0, 2, 3, 4, 1)
+        dst = L.dst.double().sum(0) if d.out_split else L.dst.double()
+        got = dst[..., d.out_ch_off:d.out_ch_off + want.shape[-1]].cpu()
+        assert got.shape == want.shape, (L.name, got.shape, want.shape)
+        err = rel_err(got.numpy(), want.numpy())
+        assert err <= 3e-6, (L.name, err)
+    net.close()
+
+
+def test_network_matches_the_keras_oracle_float32():
+    """north_star's float32 bar for the RPN outputs: 1e-5, element-wise, against the float64 Keras restatement."""
+    from lisec_b200.network import DenseNetwork
+    from lisec_b200.weights import synthetic_network_pack
+    from oracle import network_oracle as NO
+
+    for seed, (nx, ny, batch) in enumerate([(24, 40, 2), (40, 136, 1)]):
+        pack = synthetic_network_pack(seed)
+        net = DenseNetwork(pack, batch=batch, nx=nx, ny=ny, dtype="f32")
+        g = torch.Generator(device="cpu").manual_seed(11 + seed)
+        grid = torch.rand((batch, 8, nx, ny, 64), generator=g)
+        prob, reg = net.forward(grid.cuda())
+        torch.cuda.synchronize()
+        want_p, want_r = NO.network_forward(grid.numpy(), pack)
+        for got, want in ((prob, want_p), (reg, want_r)):
+            assert rel_err(got.cpu().numpy(), want) <= 1e-5
+        net.close()
+
+
 def test_network_matches_the_keras_oracle_bf16():
     from lisec_b200.network import DenseNetwork
     from lisec_b200.weights import synthetic_network_pack
@@ -158,7 +215,7 @@ def test_bad_descriptions_are_rejected():
     def create(**kw):
         base = dict(batch=1, in_d=1, in_h=8, in_w=8, in_c=64, kd=1, kh=3, kw=3, stride_d=1, stride_hw=1, pad_d=0,
                     pad_h=1, pad_w=1, out_c=64, n_tiles=1, shuffle=1, out_pitch=64, out_ch_off=0, relu=1, out_dtype=2,
-                    tile_w=16, tile_h=8, reserved=0)
+                    tile_w=16, tile_h=8, m_tiles=1, in_dtype=2, out_split=0, group_kh=0, reserved=0)
         base.update(kw)
         d = _native.lisec_conv_desc(**base)
         return lib.lisec_conv_plan_create(C.byref(d), x.data_ptr(), w.data_ptr(), s.data_ptr(), s.data_ptr(),
@@ -169,5 +226,7 @@ def test_bad_descriptions_are_rejected():
     assert create(tile_w=16, tile_h=4) == -2
     assert create(stride_hw=3) == -2
     assert create(out_pitch=32) == -2
+    assert create(in_dtype=0) == -2  # float32 plans need float32 output
+    assert create(m_tiles=2, out_c=256) == -2
     assert create() == 0
     lib.lisec_conv_plan_destroy(plan)
