@@ -208,19 +208,20 @@ class VoxelNetFrontEnd:
         """The float32 [N, nz, nx, ny, 64] tensor the reference's first Conv3D consumes (:235-236), on the GPU."""
         return self._run_frontend(x, device, "f32")
 
-    def predict(self, x: DenseVoxelInput, device: int = 0) -> list:
+    def predict(self, x: DenseVoxelInput, device: int = 0, dtype: str = "bf16") -> list:
         """model.predict(x) (Predict.py:38): [prob (N, nx/2, ny/2, 2), regress (N, nx/2, ny/2, 14)] float32 numpy arrays.
-        The front end writes a bf16 grid straight into the dense network's input buffer; the middle Conv3D stack, RPN
-        and heads run as bf16 tensor-core plans with float32 accumulation (lisec_b200/network.py)."""
+        The front end writes its grid straight into the dense network's input buffer; the middle Conv3D stack, RPN and
+        heads run as tensor-core plans (lisec_b200/network.py): dtype="bf16" (bf16 operands, float32 accumulation; 2e-2
+        of the reference) or dtype="f32" (3xTF32 on float32 hi/lo planes; 1e-5 of the reference, ~7x slower)."""
         from .network import DenseNetwork
 
         n = len(x.sweeps) if isinstance(x, DenseVoxelInput) else 0
-        key = (n, device)
+        key = (n, device, dtype)
         net = self._nets.get(key)
         if net is None:
             nz, nx, ny = self.grid
-            net = self._nets[key] = DenseNetwork(self.pack, batch=n, nx=nx, ny=ny, nz=nz, device=device)
-        self._run_frontend(x, device, "bf16", out=net.grid)
+            net = self._nets[key] = DenseNetwork(self.pack, batch=n, nx=nx, ny=ny, nz=nz, device=device, dtype=dtype)
+        self._run_frontend(x, device, "f32" if dtype == "f32" else "bf16", out=net.grid)
         prob, reg = net.forward()
         return [prob.contiguous().cpu().numpy(), reg.contiguous().cpu().numpy()]
 

@@ -399,8 +399,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 // ---- float32 plans: 3xTF32 with the partial sums promoted to the FP32 pipe every 64 channels --------------------
 // The tensor core's float32 accumulator does not round to nearest: a sum of several hundred MMAs into one accumulator
 // drifts by ~1e-5..1e-4 of its magnitude (measured 6e-5 on the K = 1728 Conv3D), past north_star's 1e-5. So an
-// accumulator only ever takes ONE 64-channel chunk (2 stages, 24 MMAs, as in the VFE kernel's FCN: 1e-6); the
-// epilogue warps add the chunks in registers (round-to-nearest FADD) while the next chunk's MMAs run into the other
+// accumulator only ever takes ONE 32-channel stage (12 MMAs; 24 per accumulator left the whole network at 1.0e-5, on
+// the bar); the epilogue warps add the chunks in registers (round-to-nearest FADD) while the next chunk's MMAs run into the other
 // accumulator. A thread keeps its row's N running sums in registers, so float32 plans take out_c <= 128; wider layers
 // run as several N-tiles (n_tiles, also inside a pixel-shuffle group).
 constexpr int kConvF32Threads = 192;
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(kConvF32Threads, 1)
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
 
-  const int chunks = P.n_taps * P.c_blocks / 2;  // 64 channels = 2 stages of 32 per chunk (in_c is a multiple of 64)
+  const int chunks = P.n_taps * P.c_blocks;  // one 32-channel stage per chunk
   if (warp == 0) {
     if (lane == 0) producer_loop(P, map_a, map_b, base, bar0);
   } else if (warp == 1) {
@@ -454,14 +454,12 @@ __global__ void __launch_bounds__(kConvF32Threads, 1)
           umma::mbar_wait(bar_acc_empty(acc), acc_ph ^ 1u);
           umma::fence_after_sync();
           const uint32_t d0 = tmem_base + (uint32_t)(acc * P.N);
-          for (int h = 0; h < 2; ++h) {
-            umma::mbar_wait(bar_full(s), ph);
-            umma::fence_after_sync();
-            const uint32_t a0 = base + (uint32_t)s * stage_bytes;
-            issue_stage_tf32(a0, P.a_bytes, a0 + 2 * P.a_bytes, b_tap_bytes, d0, idesc, (uint32_t)h);
-            umma::mma_commit(bar_empty(s));
-            if (++s == P.stages) { s = 0; ph ^= 1u; }
-          }
+          umma::mbar_wait(bar_full(s), ph);
+          umma::fence_after_sync();
+          const uint32_t a0 = base + (uint32_t)s * stage_bytes;
+          issue_stage_tf32(a0, P.a_bytes, a0 + 2 * P.a_bytes, b_tap_bytes, d0, idesc, 0u);
+          umma::mma_commit(bar_empty(s));
+          if (++s == P.stages) { s = 0; ph ^= 1u; }
           umma::mma_commit(bar_acc_full(acc));
           if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
         }
@@ -478,14 +476,21 @@ __global__ void __launch_bounds__(kConvF32Threads, 1)
         umma::mbar_wait(bar_acc_full(acc), acc_ph);
         umma::fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * P.N + col0);
+        if (ncols == 16) {
+          float x[16];
+          tmem_ld_32x16(taddr, x);
 #pragma unroll
-        for (int g = 0; g < 8; ++g)  // 16 columns at a time: 128 running sums + 16 fresh values stay in registers
-          if (16 * g < ncols) {
-            float x[16];
-            tmem_ld_32x16(taddr + 16 * g, x);
+          for (int i = 0; i < 16; ++i) sum[0][i] = c ? __fadd_rn(sum[0][i], x[i]) : x[i];
+        } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) sum[g][i] = c ? __fadd_rn(sum[g][i], x[i]) : x[i];
-          }
+          for (int g = 0; g < 4; ++g)  // 32 columns per TMEM load (128 running sums + 32 fresh values in registers)
+            if (32 * g < ncols) {
+              float x[32];
+              umma::tmem_ld_32x32(taddr + 32 * g, x);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) sum[2 * g + (i >> 4)][i & 15] = c ? __fadd_rn(sum[2 * g + (i >> 4)][i & 15], x[i]) : x[i];
+            }
+        }
         umma::fence_before_sync();
         __syncwarp();
         if (lane == 0) umma::mbar_arrive(bar_acc_empty(acc));
@@ -609,7 +614,8 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
     return conv_fail(LISEC_ERR_BAD_CONFIG, "pixel shuffle %d needs a multiple of %d N-tiles and a 1x1 kernel", shuffle,
                      shuffle * shuffle);
   const int nsub = shuffle > 1 ? n_tiles / (shuffle * shuffle) : 1;
-  if (f32 && N > 128) return conv_fail(LISEC_ERR_BAD_CONFIG, "float32 plans take out_c <= 128 per N-tile (got %d)", N);
+  if (f32 && (N > 128 || (N != 16 && N % 64)))
+    return conv_fail(LISEC_ERR_BAD_CONFIG, "float32 plans take out_c = 16, 64 or 128 per N-tile (got %d)", N);
   if (d->batch < 1 || d->in_d < 1 || d->in_h < 1 || d->in_w < 1 || d->stride_d < 1)
     return conv_fail(LISEC_ERR_BAD_ARG, "bad input shape");
   const int OD = (d->in_d + 2 * d->pad_d - d->kd) / d->stride_d + 1;

@@ -230,3 +230,33 @@ def test_bad_descriptions_are_rejected():
     assert create(m_tiles=2, out_c=256) == -2
     assert create() == 0
     lib.lisec_conv_plan_destroy(plan)
+
+
+def test_config3_full_grid_inference_float32_and_bf16():
+    """BASELINE configs[2] at the reference's own geometry (8 x 200 x 400, T = 35): synthetic Lyft-shaped sweeps through
+    voxelize + VFE + middle Conv3D + RPN + heads, float32 and bf16, against the CPU oracle (VFE on the occupied voxels
+    in float64, the dense network in float64 torch)."""
+    from lisec_b200 import compat, synth
+    from lisec_b200.weights import synthetic_model_pack
+    from oracle import lisec_oracle as O
+    from oracle import network_oracle as NO
+
+    pack = synthetic_model_pack(4)
+    sweeps = [synth.lyft_like_sweep(60_000, seed=40 + i) for i in range(2)]
+    model = compat.createModel(200, 400, 8, 35, weights=pack)
+    dense = [compat.sparse.to_dense(compat.VFE_preprocessing(p, 0.5, 0.25, 0.25, 35, 100, 200, 8)) for p in sweeps]
+    x = compat.stack(dense, axis=0)
+    ref = dict(xSize=0.5, ySize=0.25, zSize=0.25, sampleSize=35, maxVoxelX=100, maxVoxelY=200, maxVoxelZ=8)
+    grids = []
+    for p in sweeps:
+        vox = O.voxelize_np(p, **ref)
+        feat = O.vfe_forward(vox["features"].astype(np.float32), pack)
+        grids.append(O.scatter_dense(vox["coords"], feat, O.c_empty(pack, 35), (8, 200, 400), dtype=np.float64))
+    want_p, want_r = NO.network_forward(np.stack(grids), pack)
+    prob, reg = model.predict(x, dtype="f32")
+    assert prob.shape == (2, 100, 200, 2) and reg.shape == (2, 100, 200, 14)
+    assert rel_err(prob, want_p) <= 1e-5 and rel_err(reg, want_r) <= 1e-5  # north_star: 1e-5 (fp32)
+    prob, reg = model.predict(x, dtype="bf16")
+    for got, want in ((prob, want_p), (reg, want_r)):
+        emax, el2 = scale_err(got, want)
+        assert emax <= 2e-2 and el2 <= 1e-2, (emax, el2)  # north_star: 2e-2 (bf16)
