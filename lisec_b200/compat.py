@@ -226,6 +226,48 @@ class VoxelNetFrontEnd:
         return [prob.contiguous().cpu().numpy(), reg.contiguous().cpu().numpy()]
 
 
+def predictMain(samples, outPath, level5Data, model, combine_lidar_data=None, dtype: str = "bf16", batch: int = 8):
+    """Predict.predictMain(samples, outPath, level5Data, model) (Predict.py:9-40): for every sample write
+    `sample{i}_label.npy` (prob, (1, nx/2, ny/2, 2)) and `sample{i}_regress.npy` ((1, nx/2, ny/2, 14)) into outPath.
+
+    The reference handles one sample per model.predict call; here up to `batch` samples share one pass (sweeps are
+    independent, the files are the same). Dataset I/O stays the reference's: `combine_lidar_data(sample, dataDir,
+    level5Data)` (model_training.py:73-98, needs lyft_dataset_sdk + pyquaternion) is passed in by the caller; it must
+    return the (n, 3) float array the reference's returns. dataDir is the caller's business (the reference hard-codes a
+    Windows path at Predict.py:12): a loader that needs it closes over it."""
+    import os
+
+    if combine_lidar_data is None:
+        raise ValueError("pass the reference's combine_lidar_data (model_training.py:73) or an equivalent loader: "
+                         "dataset I/O is outside this library")
+    cfg = (K.voxelx, K.voxely, K.voxelz, K.maxPoints, K.nx // 2, K.ny // 2, K.nz)
+    for i0 in range(0, len(samples), batch):
+        dense = []
+        for sample in samples[i0:i0 + batch]:
+            pts = combine_lidar_data(sample, None, level5Data)
+            t = VFE_preprocessing(pts, *cfg)                        # Predict.py:21-28
+            t = sparse.reshape(t, (1,) + tuple(t.shape))            # Predict.py:29
+            dense.append(sparse.to_dense(t, default_value=0., validate_indices=False))  # Predict.py:30
+        x = DenseVoxelInput([s for d in dense for s in d.sweeps], batched=True)
+        prob, regress = model.predict(x, dtype=dtype)               # Predict.py:38
+        for j in range(len(dense)):
+            np.save(os.path.join(outPath, "sample%d_label.npy" % (i0 + j)), prob[j:j + 1])      # Predict.py:39
+            np.save(os.path.join(outPath, "sample%d_regress.npy" % (i0 + j)), regress[j:j + 1])  # Predict.py:40
+
+
+def train(samples, level5Data, save_path):
+    """model_training.train (model_training.py:260-302). NOT BUILT: the training step (backward through the VFE stack
+    and the dense network, training-mode BatchNormalization, SGD-Nesterov, NCCL gradient all-reduce; BASELINE
+    configs[4]) is the next row of this library; inference is complete."""
+    raise NotImplementedError("lisec_b200 implements the inference path (Predict.predictMain); train() is not built yet")
+
+
+def train_with_model(samples, level5Data, model_path, save_path):
+    """model_training.train_with_model (model_training.py:305-346). NOT BUILT, see train()."""
+    raise NotImplementedError("lisec_b200 implements the inference path (Predict.predictMain); train_with_model() is "
+                              "not built yet")
+
+
 def createModel(nx=K.nx, ny=K.ny, nz=K.nz, maxPoints=K.maxPoints, weights: Optional[dict] = None, seed: int = 0):
     """model_training.py:222. Keras would random-initialise; `weights` (Keras-named arrays) or a seeded synthetic
     pack stands in."""

@@ -260,3 +260,28 @@ def test_config3_full_grid_inference_float32_and_bf16():
     for got, want in ((prob, want_p), (reg, want_r)):
         emax, el2 = scale_err(got, want)
         assert emax <= 2e-2 and el2 <= 1e-2, (emax, el2)  # north_star: 2e-2 (bf16)
+
+
+def test_predictMain_writes_the_reference_files(tmp_path):
+    """Predict.predictMain's contract (Predict.py:9-40): two .npy per sample, shapes (1,100,200,2) / (1,100,200,14);
+    batching samples must not change a sample's result."""
+    from lisec_b200 import compat, synth
+    from lisec_b200.weights import synthetic_model_pack
+
+    model = compat.createModel(weights=synthetic_model_pack(1))
+    clouds = {k: synth.lyft_like_sweep(30_000, seed=70 + k).astype(np.float64) for k in range(3)}
+    loader = lambda sample, dataDir, level5Data: clouds[sample["token"]]  # noqa: E731
+    samples = [{"token": k} for k in range(3)]
+    compat.predictMain(samples, str(tmp_path), None, model, combine_lidar_data=loader, batch=2)
+    one = tmp_path / "single"
+    one.mkdir()
+    compat.predictMain(samples[2:], str(one), None, model, combine_lidar_data=loader, batch=1)
+    for i in range(3):
+        p = np.load(tmp_path / ("sample%d_label.npy" % i))
+        r = np.load(tmp_path / ("sample%d_regress.npy" % i))
+        assert p.shape == (1, 100, 200, 2) and r.shape == (1, 100, 200, 14) and p.dtype == np.float32
+        assert np.isfinite(p).all() and np.isfinite(r).all()
+    assert np.array_equal(np.load(tmp_path / "sample2_label.npy"), np.load(one / "sample0_label.npy"))
+    assert np.array_equal(np.load(tmp_path / "sample2_regress.npy"), np.load(one / "sample0_regress.npy"))
+    with pytest.raises(NotImplementedError):
+        compat.train(samples, None, "x.h5")
