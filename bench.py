@@ -349,8 +349,38 @@ def run_native(args):
         barrier()
         ms_full = max_over_ranks(f0.elapsed_time(f1)) / args.steps
         ms_net = timed(lambda: net.forward(), n_k)
+
+        # the same through host buffers: pinned points in, prob / regress (float32) back to pinned host memory
+        out_host = torch.empty((SWEEPS_PER_GPU, 1, GRID[1] // 2, GRID[2] // 2, 16), dtype=torch.float32).pin_memory()
+
+        def step_full_e2e(i):
+            fe16.forward_host(host_batches[i % N_BATCHES], offsets, out=net.grid)
+            net.forward()
+            out_host.copy_(net.heads, non_blocking=True)
+
+        for i in range(min(args.warmup, 3)):
+            step_full_e2e(i)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(args.steps):
+            step_full_e2e(i)
+        g1.record()
+        barrier()
+        ms_full_e2e = max_over_ranks(g0.elapsed_time(g1)) / args.steps
         full = {"ms_per_step": ms_full, "network_ms": ms_net, "flops_per_step": net.flops,
+                "ms_e2e": ms_full_e2e, "d2h": out_host.numel() * 4,
                 "launches_per_step": fe16.last_launch_count + len(net.layers)}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            # CPU side of the dense network: the oracle's torch-CPU float32 forward on one sweep's grid, all host threads
+            from oracle import network_oracle as NO
+
+            fe16.forward(dev_batches[0], offsets, out=net.grid)
+            g1cpu = net.grid[:1].float().cpu().numpy()
+            torch.set_num_threads(os.cpu_count() or 1)
+            t0 = time.perf_counter()
+            NO.network_forward(g1cpu, synthetic_network_pack(0), dtype=torch.float32)
+            full["cpu_network_s"] = time.perf_counter() - t0
         net.close()
         fe16.close()
     clocks = sampler.stop() if sampler else None
@@ -409,6 +439,9 @@ def run_native(args):
                             "(8,100,200,14) float32",
                 "value": SWEEPS_PER_GPU * world / (full["ms_per_step"] * 1e-3), "unit": "sweeps/s",
                 "ms_per_step": full["ms_per_step"], "gpu_launches_per_step": full["launches_per_step"],
+                "e2e": {"value": SWEEPS_PER_GPU * world / (full["ms_e2e"] * 1e-3), "unit": "sweeps/s",
+                        "ms_per_step": full["ms_e2e"], "h2d_bytes_per_step": points_bytes,
+                        "d2h_bytes_per_step": full["d2h"]},
                 "roofline": {"kernel": "conv_igemm_kernel x %d (middle Conv3D + RPN + heads), timed alone"
                                        % (full["launches_per_step"] - fe.last_launch_count),
                              "bound": "tensor", "achieved": tfl, "peak": tpk, "unit": "TFLOP/s", "frac": tfl / tpk,
@@ -417,6 +450,12 @@ def run_native(args):
         if world == 1 and not args.no_cpu_baseline:
             pts0 = base[0]
             t_vox, t_vfe = cpu_reference_time_per_sweep(pts0, 1.0, 200, pack)
+            if full is not None and "cpu_network_s" in full:
+                line["full_inference"]["cpu_baseline"] = {
+                    "value": 1.0 / (t_vox + t_vfe + full["cpu_network_s"]), "unit": "sweeps/s",
+                    "cores": os.cpu_count() or 1, "kind": "port", "seconds_network": full["cpu_network_s"],
+                    "sample": "the front-end sample below + the oracle's torch-CPU float32 forward of the dense "
+                              "network (Conv3D stack, RPN, heads) on one sweep's grid"}
             line["cpu_baseline"] = {
                 "value": 1.0 / (t_vox + t_vfe), "unit": "sweeps/s", "cores": os.cpu_count() or 1, "kind": "port",
                 "seconds_voxelize": t_vox, "seconds_dense_vfe": t_vfe,
