@@ -123,7 +123,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---- native arm ---------------------------------------------------------------------------------------------
@@ -462,13 +462,31 @@ def run_native(args):
                 "sample": "1 of the 8 sweeps: literal-loop voxelizer on all 100k points (1 core, pure Python as in "
                           "the reference) + dense VFE stack on z-plane 1 of 8 (x8), numpy float32 with BLAS threads",
             }
-        print(json.dumps(line), flush=True)
+        emit(line)
     fe.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the process's real stdout; everything else any library prints to fd 1 during the run
+    (NCCL's version banner, for one) has been pointed at stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
