@@ -296,6 +296,24 @@ int32_t lisec_set_vfe_weights(lisec_handle* h, const lisec_vfe_weights* w, void*
   const float* k0 = w->dense_kernel[0];
   for (int k = 0; k < 6; ++k)
     for (int j = 0; j < 16; ++j) p.w1f[k][j] = k0[k * 16 + j];
+  // BatchNormalization at inference (Keras defaults, model_training.py:171): y = x*a + b
+  float* A[3] = {p.a1, p.a2, p.a3};
+  float* B[3] = {p.b1, p.b2, p.b3};
+  const int C[3] = {16, 32, 64};
+  for (int l = 0; l < 3; ++l)
+    for (int j = 0; j < C[l]; ++j) {
+      const float a = (1.0f / std::sqrt(w->bn_var[l][j] + w->bn_epsilon)) * w->bn_gamma[l][j];
+      A[l][j] = a;
+      B[l][j] = w->bn_beta[l][j] - w->bn_mean[l][j] * a;
+    }
+  // The back stage takes the per-voxel max of the FCN's raw sums and applies BN + ReLU once: relu(a*z + b) is monotonic
+  // in z, increasing for a >= 0 and decreasing for a < 0. Folding sign(a) into dense_2's output column makes it
+  // increasing for every channel: relu(|a| * max(s*z) + b). The kernel then tracks one running max per channel.
+  float sgn3[64];
+  for (int m = 0; m < 64; ++m) {
+    sgn3[m] = p.a3[m] < 0.f ? -1.f : 1.f;
+    p.a3[m] = std::fabs(p.a3[m]);
+  }
   // blob = [W2P | W2X | W3^T hi image | W3^T lo image]; a Keras kernel is (C_in, C_out) row-major with the pooled
   // half's rows first. dense_2 runs on the tensor core as 3xTF32: each weight is split into hi = rn_tf32(w) and
   // lo = rn_tf32(w - hi) and laid out as the A operand W3^T[c_out][c_in] (K-major, 128-byte swizzle, umma.cuh).
@@ -315,23 +333,13 @@ int32_t lisec_set_vfe_weights(lisec_handle* h, const lisec_vfe_weights* w, void*
     const float* k2 = w->dense_kernel[2];
     for (int k = 0; k < 64; ++k)
       for (int m = 0; m < 64; ++m) {
-        const float v = k2[k * 64 + m];
+        const float v = k2[k * 64 + m] * sgn3[m];  // exact sign flip
         const float vh = tf32_rn(v), vl = tf32_rn(v - vh);
         const uint32_t off = umma::kmajor_offset(m, k, 64 * 128);
         std::memcpy(hi + off, &vh, 4);
         std::memcpy(lo + off, &vl, 4);
       }
   }
-  // BatchNormalization at inference (Keras defaults, model_training.py:171): y = x*a + b
-  float* A[3] = {p.a1, p.a2, p.a3};
-  float* B[3] = {p.b1, p.b2, p.b3};
-  const int C[3] = {16, 32, 64};
-  for (int l = 0; l < 3; ++l)
-    for (int j = 0; j < C[l]; ++j) {
-      const float a = (1.0f / std::sqrt(w->bn_var[l][j] + w->bn_epsilon)) * w->bn_gamma[l][j];
-      A[l][j] = a;
-      B[l][j] = w->bn_beta[l][j] - w->bn_mean[l][j] * a;
-    }
   h->weights_set = true;
   // c_empty: the same kernel, run on one voxel that holds nothing but the pad row
   LISEC_CUDA(h, cudaMemcpyAsync(h->ws.vfe_w, blob, sizeof(float) * kVfeBlobFloats, cudaMemcpyHostToDevice, st));

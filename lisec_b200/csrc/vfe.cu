@@ -5,22 +5,23 @@
 // virtual zero row that stands for all identical pad rows of a non-full voxel). One persistent CTA per
 // SM, warp-specialised into a three-stage pipeline over tiles:
 //
-//   FRONT  (warps 0-7, FP32 pipe)   VFE-1 (6->16, float64), max-pool, VFE-2 (32->32) as register-tiled SIMT GEMMs with
-//                                   in-register max-pools; leaves the FCN input X = [pooled | pointwise] (256 x 64),
-//                                   split into tf32 hi/lo parts, in shared memory in the tensor core's operand layout
-//   TENSOR (one elected thread)     FCN Dense(64->64): D^T[64 ch x 256 rows] = W3^T * X^T as 24 tcgen05.mma (kind::tf32,
-//                                   M=64, N=256, K=8; 3xTF32: Wh*Xl + Wl*Xh + Wh*Xh), accumulators in TMEM, double
-//                                   buffered, completion signalled to an mbarrier by tcgen05.commit
-//   BACK   (warps 8-11)             tcgen05.ld: a thread owns one output CHANNEL and walks the tile's rows in order, so
-//                                   the final per-voxel max is a sequential in-register scan with warp-uniform voxel
-//                                   boundaries; BN + ReLU are applied once per voxel (they are monotonic, so they
-//                                   commute with the max), and the row goes straight to voxel_feat or to its grid cell
-//   WRITER (warps 12-15, fused modes) streams c_empty into the empty cells with TMA bulk stores
+//   WRITER (warps 0-2, fused modes)  streams c_empty into the empty cells with TMA bulk stores (cp.async.bulk, evict-first)
+//   TENSOR (warp 3, one lane)        FCN Dense(64->64): D^T[64 ch x 256 rows] = W3^T * X^T as 24 tcgen05.mma (kind::tf32,
+//                                    M=64, N=256, K=8; 3xTF32: Wh*Xl + Wl*Xh + Wh*Xh), 4 accumulators in TMEM,
+//                                    completion signalled to an mbarrier by tcgen05.commit
+//   BACK   (warps 4-7)               tcgen05.ld: a thread owns one output CHANNEL and walks the tile's rows in order, so
+//                                    the final per-voxel max is a sequential in-register scan; BN + ReLU are applied once
+//                                    per voxel (they are monotonic, so they commute with the max), and the row goes
+//                                    straight to voxel_feat or to its grid cell
+//   FRONT  (warps 8-23, FP32 pipe)   VFE-1 (6->16, compensated float32), max-pool, VFE-2 (32->32) as register-tiled SIMT
+//                                    GEMMs with in-register max-pools; leaves the FCN input X = [pooled | pointwise]
+//                                    (256 x 64), split into tf32 hi/lo parts, in shared memory in the tensor core's
+//                                    operand layout
 //
 // Why the FCN alone goes to the tensor core: it is 75 % of the path's FLOPs, it follows the last ReLU (no cancellation
 // in its sums), and 3xTF32 reproduces a float32 FMA chain (tools/umma_probe.cu: 1.1e-6 vs 1.0e-6 of rms). dense_1's
 // two halves cancel, so it stays on the FP32 pipe with blocked accumulation, and dense (6->16) acts on raw coordinates
-// up to +-50 m and is accumulated in float64. Parity bar 1e-5 against the float64 oracle.
+// up to +-50 m and is evaluated in compensated float32 (Dot2; see VFE-1 below). Parity bar 1e-5 against the float64 oracle.
 //
 // Because Concatenate([pooled, pointwise]) feeds a bias-free Dense (model_training.py:164-165, 184), the pooled half of
 // dense_1's product is the same for every row of a voxel: it is computed once per voxel (Q) and used as the
@@ -392,7 +393,7 @@ __device__ __forceinline__ void warm_count_table(const int* __restrict__ count, 
 // of dependent gathers. The rows of a voxel each redo its (<= T term) sum: those re-reads hit L1, the stores are
 // coalesced, and no thread carries a whole saturated voxel alone.
 template <typename PT>
-__global__ void __launch_bounds__(256) row_features_kernel(const PT* __restrict__ pts, int T,
+__global__ void __launch_bounds__(256, 6) row_features_kernel(const PT* __restrict__ pts, int T,
                                                            const int* __restrict__ voxel_start,
                                                            const int* __restrict__ row_start,
                                                            const int* __restrict__ row_voxel,
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(256) row_features_kernel(const PT* __restrict_
     return;
   }
   // The loads of a chunk are issued together; the additions stay in list order, one at a time.
-  constexpr int CH = 6;
+  constexpr int CH = 4;
   double sx = 0.0, sy = 0.0, sz = 0.0, px = 0.0, py = 0.0, pz = 0.0;
   for (int i0 = 0; i0 < kept; i0 += CH) {
     int id[CH];
@@ -510,15 +511,14 @@ __device__ __forceinline__ void tensor_stage(uint32_t smem_base, uint32_t tmem_b
 // 16..31 the same channels of the following ODD tile: the warp scans a pair of tiles per pass, every lane busy.
 // Columns are tile rows (rotated inside groups of 8, see x_row): a thread walks its tile's rows in order, so the per-
 // voxel max is a sequential scan; voxel ends come from the tile's last-row bit mask (per lane: the two halves of the
-// warp work on different tiles, so everything below is predicated, not branched). y = relu(a*z + b) is monotonic in z,
-// so max_rows relu(a*z_r + b) = relu(a*z* + b) with z* = max z_r (a >= 0) or min z_r (a < 0): both are tracked and
-// BN + ReLU are applied once per voxel.
+// warp work on different tiles). y = relu(a*z + b) is monotonic in z; the host folds sign(a) into dense_2's output
+// column (api.cu), so a >= 0 here for every channel and max_rows relu(a*z_r + b) = relu(a*max_r z_r + b): one running
+// max per thread, BN + ReLU applied once per voxel.
 template <int MODE>
 __device__ __forceinline__ void back_stage(const VfeSmall& P, const VfeOutput& out, unsigned char* smem,
                                            uint32_t smem_base, int my_tiles, uint32_t tmem_base, int bwarp, int lane) {
   const int ch = 16 * bwarp + (lane & 15), hh = lane >> 4;
-  const float a = P.a3[ch], b = P.b3[ch];
-  const bool pos = a >= 0.f;
+  const float a = P.a3[ch], b = P.b3[ch];  // a = |BN scale|, see above
   const uint32_t tlane = tmem_base + ((uint32_t)(32 * bwarp) << 16);
   Prof prof;
   prof.begin(bwarp == 0 && lane == 0 ? out.prof : nullptr);
@@ -533,7 +533,7 @@ __device__ __forceinline__ void back_stage(const VfeSmall& P, const VfeOutput& o
     const TileInfo* info = reinterpret_cast<const TileInfo*>(smem + OFF_INFO) + s;
     const int nrows = valid ? info->nrows : 0;
     const int nrows_max = max(nrows, __shfl_xor_sync(0xffffffffu, nrows, 16));
-    float mx = -INFINITY, mn = INFINITY;
+    float mx = -INFINITY;
     int v = 0;
     int cell = MODE != 0 ? info->voxcell[0] : 0;
     float* row0 = MODE == 0 ? out.voxel_feat + (size_t)info->v0 * 64 + ch : nullptr;
@@ -551,20 +551,16 @@ __device__ __forceinline__ void back_stage(const VfeSmall& P, const VfeOutput& o
         for (int g = 0; g < 4; ++g)
 #pragma unroll
           for (int i = 0; i < 8; ++i) {  // tile row c0 + 32 half + 8 g + i sits in column 8 g + ((i + G) & 7), G = 4 half + g
-            const float val = x[8 * g + ((i + 4 * half + g) & 7)];
-            mx = fmaxf(mx, val);
-            mn = fminf(mn, val);
-            const bool last = (m >> (8 * g + i)) & 1u;
-            const float y = fmaxf(fmaf(pos ? mx : mn, a, b), 0.f);
-            if (last) {
+            mx = fmaxf(mx, x[8 * g + ((i + 4 * half + g) & 7)]);
+            if ((m >> (8 * g + i)) & 1u) {  // the voxel's last row (uniform over the 16 lanes that share the tile)
+              const float y = fmaxf(fmaf(mx, a, b), 0.f);
               if (MODE == 0) row0[(size_t)v * 64] = y;
               else if (MODE == 1) __stcs(static_cast<float*>(out.grid) + (size_t)cell * 64 + ch, y);
               else static_cast<__nv_bfloat16*>(out.grid)[(size_t)cell * 64 + ch] = __float2bfloat16_rn(y);
               ++v;
               if (MODE != 0) cell = info->voxcell[v & (kVox - 1)];  // the next voxel's cell: in flight while its rows are scanned
+              mx = -INFINITY;
             }
-            mx = last ? -INFINITY : mx;
-            mn = last ? INFINITY : mn;
           }
       }
     }
@@ -912,7 +908,7 @@ static cudaError_t launch_vfe_mode(const VfeSmall& p, const float* wblob, const 
                                    int sm_count, cudaStream_t st) {
   cudaError_t err = cudaFuncSetAttribute(vfe_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (err != cudaSuccess) return err;
-  // persistent: one CTA per SM (3 writer warps, 1 tensor warp, 4 back warps, 8 front warps), tiles strided over the CTAs
+  // persistent: one CTA per SM (3 writer warps, 1 tensor warp, 4 back warps, 16 front warps), tiles strided over the CTAs
   return launch_pdl(vfe_kernel<MODE>, sm_count, kCtaThreads, kSmemBytes, st, p, wblob, prob, out);
 }
 
