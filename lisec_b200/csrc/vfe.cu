@@ -118,10 +118,6 @@ __device__ __forceinline__ void tile_gemm_blocked(const float* __restrict__ sA, 
   for (int kb = 0; kb < K; kb += 4) {
     float blk[R][NC];
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int c = 0; c < NC; ++c) blk[r][c] = 0.f;
-#pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       const int k = kb + kk;
       float a[R], b[NC];
@@ -140,7 +136,8 @@ __device__ __forceinline__ void tile_gemm_blocked(const float* __restrict__ sA, 
 #pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int c = 0; c < NC; ++c) blk[r][c] = fmaf(a[r], b[c], blk[r][c]);
+        for (int c = 0; c < NC; ++c)  // the block's first term is a plain product (no zeroing pass; only the sign of a zero differs)
+          blk[r][c] = kk == 0 ? __fmul_rn(a[r], b[c]) : fmaf(a[r], b[c], blk[r][c]);
     }
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -764,16 +761,14 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
       for (int kb = 0; kb < 16; kb += 4) {
         float blk[4][2];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) blk[r][0] = blk[r][1] = 0.f;
-#pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const float* a = sP1T + (kb + kk) * PV + lane;
           const float2 b = *reinterpret_cast<const float2*>(sW2P + (kb + kk) * 32 + 2 * warp);
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             const float av = a[32 * r];
-            blk[r][0] = fmaf(av, b.x, blk[r][0]);
-            blk[r][1] = fmaf(av, b.y, blk[r][1]);
+            blk[r][0] = kk == 0 ? __fmul_rn(av, b.x) : fmaf(av, b.x, blk[r][0]);
+            blk[r][1] = kk == 0 ? __fmul_rn(av, b.y) : fmaf(av, b.y, blk[r][1]);
           }
         }
 #pragma unroll
