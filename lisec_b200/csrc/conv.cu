@@ -18,8 +18,8 @@
 // N-tiles whose epilogue writes the pixel-shuffled position. The k3 s1 one is a 3x3 convolution with the kernel
 // flipped (host side).
 //
-// One persistent CTA per SM, 6 warps: warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane; owns TMEM),
-// warps 2-5 = epilogue (TMEM lane quadrant = warp id % 4). Three pipelines: shared-memory stages (full/empty
+// One persistent CTA per SM, 10 warps: warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane; owns TMEM),
+// warps 2-9 = epilogue (TMEM lane quadrant = warp id % 4, two warps per quadrant split the columns). Three pipelines: shared-memory stages (full/empty
 // mbarriers), two TMEM accumulators (acc_full/acc_empty) so a tile's epilogue overlaps the next tile's MMAs, and
 // the static tile schedule (tile = blockIdx.x + i * gridDim.x, N-tile fastest so neighbours share A in L2).
 #include <cuda.h>
@@ -36,7 +36,7 @@
 namespace lisec {
 namespace {
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
 constexpr int kMaxTaps = 27;
 constexpr int kMaxStages = 8;
 constexpr uint32_t kABytes = 128 * 128;  // 128 positions x 64 bf16 channels
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     }
     for (int a = 0; a < 2; ++a) {
       umma::mbar_init(bar_acc_full(a), 1);
-      umma::mbar_init(bar_acc_empty(a), 4);
+      umma::mbar_init(bar_acc_empty(a), 8);
     }
     umma::mbar_init_fence();
   }
@@ -355,7 +355,11 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     }
   } else {
     // ===== epilogue: TMEM -> registers -> affine (+ReLU) -> global =====
-    const int q = warp & 3, row = 32 * q + lane;
+    // 8 warps: warp w reads TMEM lanes 32 (w % 4) .. +31 (= tile rows) and owns half of the N columns. One warp per
+    // scheduler could not hide its own dependency latencies: with N = 256 and a short K loop (the transposed
+    // convolutions) the epilogue, not the tensor pipe, set the pace (ncu: 12 cycles per issued instruction).
+    const int q = warp & 3, row = 32 * q + lane, half = (warp - 2) >> 2;
+    const int ncols = P.N >= 64 ? P.N / 2 : (half == 0 ? P.N : 0), col0 = P.N >= 64 ? half * (P.N / 2) : 0;
     int acc = 0;
     uint32_t acc_ph = 0;
     const int sh = P.shuffle;
@@ -371,17 +375,17 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         const bool valid = oh < P.out_h && ow < P.out_w;
         const size_t pix = (((size_t)t.b * P.out_d + t.od) * ((size_t)P.out_h * sh) + (size_t)oh * sh + si) *
                                ((size_t)P.out_w * sh) + (size_t)ow * sh + sj;
-        const size_t elem = pix * (size_t)P.out_pitch + P.out_ch_off + n0;
-        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((acc * P.mt + m) * P.N);
-        if (P.N == 16) {
+        const size_t elem = pix * (size_t)P.out_pitch + P.out_ch_off + n0 + col0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((acc * P.mt + m) * P.N + col0);
+        if (ncols == 16) {
           float x[16];
           tmem_ld_32x16(taddr, x);
-          store_chunk<16>(P, x, n0, elem, valid);
+          store_chunk<16>(P, x, n0 + col0, elem, valid);
         } else {
-          for (int c0 = 0; c0 < P.N; c0 += 32) {
+          for (int c0 = 0; c0 < ncols; c0 += 32) {
             float x[32];
             umma::tmem_ld_32x32(taddr + c0, x);
-            store_chunk<32>(P, x, n0 + c0, elem + c0, valid);
+            store_chunk<32>(P, x, n0 + col0 + c0, elem + c0, valid);
           }
         }
       }
