@@ -229,7 +229,10 @@ typedef struct lisec_conv_desc {
   int32_t in_dtype;  /* LISEC_BF16, or LISEC_F32 = 3xTF32 (float32-grade products, see below) */
   int32_t out_split; /* float32 plans: 1 = write hi / lo planes for the next float32 plan, 0 = plain float32 */
   int32_t group_kh;  /* 1: the kh taps of one (kd, kw) come from ONE input box with a kh-1 row halo; the weights are then
-                        ordered [kd][kw][kh][n_tiles*out_c][in_c] (stride_hw = 1 only) */
+                        ordered [kd][kw][kh][n_tiles*out_c][in_c] (stride_hw = 1 only).
+                        2: "halo" plan for 3x3 taps, stride_hw = 1, out_c <= 128, tile 8 x 16: ONE box with a 1-position
+                        halo per (kd, 64 channels) serves all nine (kh, kw) taps; m_tiles stack along W; weights in
+                        the plain [kd][kh][kw] order */
   int32_t reserved;
 } lisec_conv_desc;
 

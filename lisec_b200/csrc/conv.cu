@@ -54,6 +54,11 @@ struct ConvParams {
   // tap + lo_tap; the epilogue splits its float32 result into hi / lo planes out_lo_off elements apart (0: no split)
   int f32, cpb, lo_batch, lo_tap;
   int nsub;  // N-tiles per pixel-shuffle group (1 without shuffle)
+  // halo mode (group_kh = 2): one input box with a 1-position halo per (kd, 64-channel block) serves all kh x kw taps;
+  // the weights stream through their own ring, three kw taps per slot
+  int halo, a_slots, b_slots, box_w, kd_n;
+  int step_w, step_h;  // CTA tile pitch in output positions (M-tiles stack along H, or along W in halo mode)
+  uint32_t a_slot_bytes, a_box_bytes;
   long long out_lo_off;
   // TMA coordinates of a stage: (c_off[t] + 64 cb, b1 + t1[t], b2 + t2[t], b3 + t3[t], b)
   int s2d, stride_d;
@@ -190,9 +195,9 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& P, long long 
   TileCoord t;
   t.nt = (int)(tile % P.n_tiles);
   long long r = tile / P.n_tiles;
-  t.ow0 = (int)(r % P.tiles_w) * P.bw;
+  t.ow0 = (int)(r % P.tiles_w) * P.step_w;
   r /= P.tiles_w;
-  t.oh0 = (int)(r % P.tiles_h) * P.bh * P.mt;
+  t.oh0 = (int)(r % P.tiles_h) * P.step_h;
   r /= P.tiles_h;
   t.od = (int)(r % P.out_d);
   t.b = (int)(r / P.out_d);
@@ -246,6 +251,27 @@ __device__ __forceinline__ void store_chunk(const ConvParams& P, const float (&x
     for (int i = 0; i < NV / 8; ++i)
       dst[i] = make_uint4(pack2(y[8 * i], y[8 * i + 1]), pack2(y[8 * i + 2], y[8 * i + 3]),
                           pack2(y[8 * i + 4], y[8 * i + 5]), pack2(y[8 * i + 6], y[8 * i + 7]));
+  }
+}
+
+// one output position (oh, ow) of tile t: ncols accumulator columns from taddr on -> affine (+ReLU) -> global
+__device__ __forceinline__ void epilogue_rows(const ConvParams& P, const TileCoord& t, int oh, int ow, int si, int sj,
+                                              int n0, int col0, int ncols, uint32_t taddr) {
+  const int sh = P.shuffle;
+  const bool valid = oh < P.out_h && ow < P.out_w;
+  const size_t pix = (((size_t)t.b * P.out_d + t.od) * ((size_t)P.out_h * sh) + (size_t)oh * sh + si) *
+                         ((size_t)P.out_w * sh) + (size_t)ow * sh + sj;
+  const size_t elem = pix * (size_t)P.out_pitch + P.out_ch_off + n0 + col0;
+  if (ncols == 16) {
+    float x[16];
+    tmem_ld_32x16(taddr, x);
+    store_chunk<16>(P, x, n0 + col0, elem, valid);
+  } else {
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
+      float x[32];
+      umma::tmem_ld_32x32(taddr + c0, x);
+      store_chunk<32>(P, x, n0 + col0 + c0, elem + c0, valid);
+    }
   }
 }
 
@@ -372,23 +398,160 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       umma::fence_after_sync();
       for (int m = 0; m < P.mt; ++m) {
         const int oh = t.oh0 + m * P.bh + (row >> P.bw_log2), ow = t.ow0 + (row & (P.bw - 1));
-        const bool valid = oh < P.out_h && ow < P.out_w;
-        const size_t pix = (((size_t)t.b * P.out_d + t.od) * ((size_t)P.out_h * sh) + (size_t)oh * sh + si) *
-                               ((size_t)P.out_w * sh) + (size_t)ow * sh + sj;
-        const size_t elem = pix * (size_t)P.out_pitch + P.out_ch_off + n0 + col0;
-        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((acc * P.mt + m) * P.N + col0);
-        if (ncols == 16) {
-          float x[16];
-          tmem_ld_32x16(taddr, x);
-          store_chunk<16>(P, x, n0 + col0, elem, valid);
-        } else {
-          for (int c0 = 0; c0 < ncols; c0 += 32) {
-            float x[32];
-            umma::tmem_ld_32x32(taddr + c0, x);
-            store_chunk<32>(P, x, n0 + col0 + c0, elem + c0, valid);
-          }
-        }
+        epilogue_rows(P, t, oh, ow, si, sj, n0, col0, ncols,
+                      tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((acc * P.mt + m) * P.N + col0));
       }
+      umma::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(bar_acc_empty(acc));
+      if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) umma::tmem_dealloc<512>(tmem_base);
+}
+
+// ---- halo plans (group_kh = 2): stride-1 3x3(x3) convolutions with every kh x kw tap read from ONE input box ---------
+// tcgen05.mma applies the 128-byte swizzle to the ABSOLUTE shared-memory address (tools/umma_shift_probe.cu: a K-major
+// SWIZZLE_128B operand may start at any 128-byte row, with its 8-row groups any multiple of 16 bytes apart, base offset
+// 0). So a tap is just a descriptor: the box [18 x 18 positions x 64 ch] (a 16 x 16 tile plus a 1-position halo) is
+// loaded once per (kd, 64-channel block); M-tile m (8 wide, 16 high, two side by side) under tap (kh, kw) starts at box
+// row kh * 18 + kw + 8 m and its 8-row groups are one box line (18 rows = 2304 bytes) apart. Input traffic per output
+// drops 2.7x against the kh-halo plans; the weights stream through their own ring, three kw taps per slot.
+__global__ void __launch_bounds__(kConvThreads, 1)
+    conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const __grid_constant__ ConvParams P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = umma::smem_u32(smem);
+  if (base & 1023u) __trap();
+  const uint32_t b_slot_bytes = 3u * (uint32_t)P.N * 128u;
+  const uint32_t b_base = base + (uint32_t)P.a_slots * P.a_slot_bytes;
+  const uint32_t bar0 = b_base + (uint32_t)P.b_slots * b_slot_bytes;
+  auto bar_a_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_a_empty = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto bar_b_full = [&](int s) { return bar0 + 8u * (8 + s); };
+  auto bar_b_empty = [&](int s) { return bar0 + 8u * (16 + s); };
+  auto bar_acc_full = [&](int a) { return bar0 + 8u * (24 + a); };
+  auto bar_acc_empty = [&](int a) { return bar0 + 8u * (26 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bar0 - base) + 8 * 28);
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
+    for (int s = 0; s < P.a_slots; ++s) {
+      umma::mbar_init(bar_a_full(s), 1);
+      umma::mbar_init(bar_a_empty(s), 1);
+    }
+    for (int s = 0; s < P.b_slots; ++s) {
+      umma::mbar_init(bar_b_full(s), 1);
+      umma::mbar_init(bar_b_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      umma::mbar_init(bar_acc_full(a), 1);
+      umma::mbar_init(bar_acc_empty(a), 8);
+    }
+    umma::mbar_init_fence();
+  }
+  if (warp == 1) umma::tmem_alloc<512>(tmem_slot);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  const int a_steps = P.kd_n * P.c_blocks;  // input boxes per tile; each is followed by 3 weight slots (kh = 0, 1, 2)
+  if (warp == 0) {
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (long long tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(P, tile);
+        for (int kd = 0; kd < P.kd_n; ++kd)
+          for (int cb = 0; cb < P.c_blocks; ++cb) {
+            umma::mbar_wait(bar_a_empty(as), aph ^ 1u);
+            mbar_arrive_expect_tx(bar_a_full(as), P.a_box_bytes);
+            tma_load_5d(base + (uint32_t)as * P.a_slot_bytes, &map_a, bar_a_full(as), 64 * cb, t.ow0 + P.t1[0],
+                        t.oh0 + P.t2[0], t.od * P.stride_d + kd + P.t3[0], t.b);
+            if (++as == P.a_slots) { as = 0; aph ^= 1u; }
+            for (int kh = 0; kh < 3; ++kh) {
+              umma::mbar_wait(bar_b_empty(bs), bph ^ 1u);
+              mbar_arrive_expect_tx(bar_b_full(bs), b_slot_bytes);
+              tma_load_3d(b_base + (uint32_t)bs * b_slot_bytes, &map_b, bar_b_full(bs), 64 * cb, t.nt * P.N,
+                          (kd * 3 + kh) * 3);
+              if (++bs == P.b_slots) { bs = 0; bph ^= 1u; }
+            }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16_k(128, P.N);
+      const uint64_t proto = umma::make_desc_k_sw128(0);
+      const uint32_t lo0 = (uint32_t)proto, hi_b = (uint32_t)(proto >> 32);
+      // A: 8-row groups one box line apart (stride byte offset = box_w * 128, in 16-byte units in bits 0..13 of the high word)
+      const uint32_t hi_a = (hi_b & ~0x3fffu) | (((uint32_t)P.box_w * 128u) >> 4);
+      const uint32_t line16 = (uint32_t)P.box_w * 8u, b_tap16 = (uint32_t)P.N * 8u;
+      int as = 0, bs = 0, acc = 0;
+      uint32_t aph = 0, bph = 0, acc_ph = 0;
+      for (long long tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        umma::mbar_wait(bar_acc_empty(acc), acc_ph ^ 1u);
+        umma::fence_after_sync();
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * P.mt * P.N);
+        for (int st = 0; st < a_steps; ++st) {
+          umma::mbar_wait(bar_a_full(as), aph);
+          const uint32_t a_lo0 = lo0 + ((base + (uint32_t)as * P.a_slot_bytes) >> 4);
+          for (int kh = 0; kh < 3; ++kh) {
+            umma::mbar_wait(bar_b_full(bs), bph);
+            umma::fence_after_sync();
+            const uint32_t b_lo0 = lo0 + ((b_base + (uint32_t)bs * b_slot_bytes) >> 4);
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+              for (int m = 0; m < 2; ++m) {
+                if (m < P.mt) {
+                  const uint32_t a_lo = a_lo0 + (uint32_t)kh * line16 + (uint32_t)(kw + 8 * m) * 8u;
+                  const uint32_t b_lo = b_lo0 + (uint32_t)kw * b_tap16;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const uint32_t accum = (st | kh | kw | j) != 0;
+                    asm volatile(
+                        "{\n\t"
+                        ".reg .pred p;\n\t"
+                        ".reg .b64 da, db;\n\t"
+                        "mov.b64 da, {%1, %3};\n\t"
+                        "mov.b64 db, {%2, %4};\n\t"
+                        "setp.ne.b32 p, %6, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+                        "}\n" ::"r"(d0 + (uint32_t)(m * P.N)),
+                        "r"(a_lo + 2 * j), "r"(b_lo + 2 * j), "r"(hi_a), "r"(hi_b), "r"(idesc), "r"(accum)
+                        : "memory");
+                  }
+                }
+              }
+            umma::mma_commit(bar_b_empty(bs));
+            if (++bs == P.b_slots) { bs = 0; bph ^= 1u; }
+          }
+          umma::mma_commit(bar_a_empty(as));
+          if (++as == P.a_slots) { as = 0; aph ^= 1u; }
+        }
+        umma::mma_commit(bar_acc_full(acc));
+        if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+      }
+    }
+  } else {
+    const int q = warp & 3, row = 32 * q + lane, half = (warp - 2) >> 2;
+    const int ncols = P.N >= 64 ? P.N / 2 : (half == 0 ? P.N : 0), col0 = P.N >= 64 ? half * (P.N / 2) : 0;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (long long tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(P, tile);
+      umma::mbar_wait(bar_acc_full(acc), acc_ph);
+      umma::fence_after_sync();
+      for (int m = 0; m < P.mt; ++m)  // M-tile m: 8 positions wide, 16 high, at w offset 8 m
+        epilogue_rows(P, t, t.oh0 + (row >> 3), t.ow0 + 8 * m + (row & 7), 0, 0, t.nt * P.N, col0, ncols,
+                      tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((acc * P.mt + m) * P.N + col0));
       umma::fence_before_sync();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(bar_acc_empty(acc));
@@ -607,8 +770,12 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
   const int n_tiles = d->n_tiles < 1 ? 1 : d->n_tiles;
   const int shuffle = d->shuffle < 1 ? 1 : d->shuffle;
   const int mt = d->m_tiles < 1 ? 1 : d->m_tiles;
-  const int group = d->group_kh ? d->kh : 1;
+  const bool halo = d->group_kh == 2;
+  const int group = (d->group_kh == 1) ? d->kh : 1;
   if (group != 1 && group != 3) return conv_fail(LISEC_ERR_BAD_CONFIG, "group_kh needs kh = 3");
+  if (halo && (f32 || s != 1 || d->kh != 3 || d->kw != 3 || d->kd > 3 || N > 128 || shuffle != 1 || d->tile_w != 8 ||
+               d->tile_h != 16))
+    return conv_fail(LISEC_ERR_BAD_CONFIG, "halo plans: bf16, stride_hw = 1, 3x3 taps, out_c <= 128, tile 8 x 16");
   if (mt > 2 || 2 * mt * N > 512) return conv_fail(LISEC_ERR_BAD_CONFIG, "m_tiles = %d with out_c = %d: 2 * m_tiles * out_c accumulator columns must fit 512", mt, N);
   if ((mt > 1 || group > 1) && d->tile_w < 8)
     return conv_fail(LISEC_ERR_BAD_CONFIG, "m_tiles / group_kh need tile_w >= 8 (1 KB-aligned H rows)");
@@ -643,6 +810,15 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
   while ((1 << p.bw_log2) < p.bw) ++p.bw_log2;
   p.tiles_w = (OW + p.bw - 1) / p.bw;
   p.tiles_h = (OH + p.bh * mt - 1) / (p.bh * mt);
+  p.step_w = p.bw;
+  p.step_h = p.bh * mt;
+  if (halo) {  // M-tiles side by side along W
+    p.step_w = p.bw * mt;
+    p.step_h = p.bh;
+    p.tiles_w = (OW + p.step_w - 1) / p.step_w;
+    p.tiles_h = (OH + p.step_h - 1) / p.step_h;
+  }
+  p.halo = halo;
   p.mt = mt;
   p.group = group;
   p.out_d = OD;
@@ -660,7 +836,14 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
   p.s2d = s == 2;
   p.stride_d = d->stride_d;
   int t = 0;
-  if (group > 1) {  // stages in (kd, kw) order; the box starts at the kh = 0 row and carries the kh-1 halo rows
+  if (halo) {  // one box per kd: its origin is the tile origin minus the padding
+    p.c_off[0] = 0;
+    p.t1[0] = (signed char)(-d->pad_w);
+    p.t2[0] = (signed char)(-d->pad_h);
+    p.t3[0] = (signed char)(-d->pad_d);
+    p.kd_n = d->kd;
+    p.box_w = p.bw * mt + 2;
+  } else if (group > 1) {  // stages in (kd, kw) order; the box starts at the kh = 0 row and carries the kh-1 halo rows
     for (int kd = 0; kd < d->kd; ++kd)
       for (int kw = 0; kw < d->kw; ++kw, ++t) {
         p.c_off[t] = 0;
@@ -699,22 +882,43 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
   p.out = out;
   // hi / lo output planes: [2][batch, out_d, out_h*shuffle, out_w*shuffle, out_pitch]
   p.out_lo_off = d->out_split ? (long long)d->batch * OD * ((long long)OH * shuffle) * ((long long)OW * shuffle) * d->out_pitch : 0;
-  const int box_h = p.bh * mt + group - 1;
-  p.a_bytes = (uint32_t)(p.bw * box_h) * 128u;
-  p.stage_bytes = (p.a_bytes + (uint32_t)(group * N) * 128u) * (f32 ? 2u : 1u);
-  const uint32_t stage_bytes = p.stage_bytes;
-  if (stage_bytes % 1024u) {
-    delete pl;
-    return conv_fail(LISEC_ERR_BAD_CONFIG, "stage of %u bytes is not 1 KB-aligned", stage_bytes);
+  int box_h = p.bh * mt + group - 1, box_w = p.bw;
+  if (halo) {
+    box_h = p.bh + 2;
+    box_w = p.box_w;
+    p.a_box_bytes = (uint32_t)(box_w * box_h) * 128u;
+    p.a_slot_bytes = (p.a_box_bytes + 1023u) & ~1023u;
+    p.a_slots = 2;
+    const uint32_t b_slot = 3u * (uint32_t)N * 128u;
+    const uint32_t room = 220u * 1024u - 2u * p.a_slot_bytes;
+    int b_slots = (int)(room / b_slot);
+    if (b_slots > 8) b_slots = 8;
+    if (b_slots < 2) {
+      delete pl;
+      return conv_fail(LISEC_ERR_BAD_CONFIG, "halo plan: no room for two weight slots of %u bytes", b_slot);
+    }
+    p.b_slots = b_slots;
+    p.a_bytes = p.a_box_bytes;
+    p.stage_bytes = 0;
+    p.stages = 0;
+    pl->smem = (int)(2u * p.a_slot_bytes + (uint32_t)b_slots * b_slot) + 8 * 28 + 16;
+  } else {
+    p.a_bytes = (uint32_t)(p.bw * box_h) * 128u;
+    p.stage_bytes = (p.a_bytes + (uint32_t)(group * N) * 128u) * (f32 ? 2u : 1u);
+    const uint32_t stage_bytes = p.stage_bytes;
+    if (stage_bytes % 1024u) {
+      delete pl;
+      return conv_fail(LISEC_ERR_BAD_CONFIG, "stage of %u bytes is not 1 KB-aligned", stage_bytes);
+    }
+    int stages = (int)((220u * 1024u) / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) {
+      delete pl;
+      return conv_fail(LISEC_ERR_BAD_CONFIG, "a stage of %u bytes leaves room for fewer than 2 stages", stage_bytes);
+    }
+    p.stages = stages;
+    pl->smem = stages * (int)stage_bytes + 8 * (2 * kMaxStages + 4) + 16;
   }
-  int stages = (int)((220u * 1024u) / stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) {
-    delete pl;
-    return conv_fail(LISEC_ERR_BAD_CONFIG, "a stage of %u bytes leaves room for fewer than 2 stages", stage_bytes);
-  }
-  p.stages = stages;
-  pl->smem = stages * (int)stage_bytes + 8 * (2 * kMaxStages + 4) + 16;
 
   // tensor maps (bf16, 128-byte swizzle, zero fill out of bounds)
   const cuuint64_t eb = f32 ? 4 : 2;
@@ -726,7 +930,7 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
   if (s == 1) {
     dims[0] = C; dims[1] = W; dims[2] = H; dims[3] = D; dims[4] = B * planes;
     strides[0] = C * eb; strides[1] = W * C * eb; strides[2] = H * W * C * eb; strides[3] = D * H * W * C * eb;
-    box[0] = cpb; box[1] = p.bw; box[2] = box_h; box[3] = 1; box[4] = 1;
+    box[0] = cpb; box[1] = box_w; box[2] = box_h; box[3] = 1; box[4] = 1;
   } else {
     dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = B * planes;
     strides[0] = 2 * C * eb; strides[1] = W * C * eb; strides[2] = 2 * W * C * eb; strides[3] = H * W * C * eb;
@@ -742,7 +946,7 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
   const cuuint64_t NT = (cuuint64_t)n_tiles * N;
   cuuint64_t wdims[3] = {(cuuint64_t)C, NT, (cuuint64_t)taps * planes};
   cuuint64_t wstr[2] = {C * eb, NT * C * eb};
-  cuuint32_t wbox[3] = {(cuuint32_t)cpb, (cuuint32_t)N, (cuuint32_t)group}, westr[3] = {1, 1, 1};
+  cuuint32_t wbox[3] = {(cuuint32_t)cpb, (cuuint32_t)N, (cuuint32_t)(halo ? 3 : group)}, westr[3] = {1, 1, 1};
   r = encode(&pl->map_b, dt, 3, const_cast<void*>(weights), wdims, wstr, wbox, westr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -757,6 +961,8 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
     e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);  // per function, not per plan: the opt-in maximum
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_igemm_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   if (e != cudaSuccess) {
     delete pl;
     return conv_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
@@ -769,7 +975,9 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
 
 int32_t lisec_conv_plan_run(lisec_conv_plan* pl, void* stream) {
   if (!pl) return conv_fail(LISEC_ERR_BAD_ARG, "null plan");
-  cudaError_t e = pl->p.f32 ? launch_pdl(conv_igemm_f32_kernel, pl->grid, kConvF32Threads, (size_t)pl->smem,
+  cudaError_t e = pl->p.halo ? launch_pdl(conv_halo_kernel, pl->grid, kConvThreads, (size_t)pl->smem,
+                                          static_cast<cudaStream_t>(stream), pl->map_a, pl->map_b, pl->p)
+                  : pl->p.f32 ? launch_pdl(conv_igemm_f32_kernel, pl->grid, kConvF32Threads, (size_t)pl->smem,
                                          static_cast<cudaStream_t>(stream), pl->map_a, pl->map_b, pl->p)
                             : launch_pdl(conv_igemm_kernel, pl->grid, kConvThreads, (size_t)pl->smem,
                                          static_cast<cudaStream_t>(stream), pl->map_a, pl->map_b, pl->p);

@@ -76,6 +76,18 @@ def default_schedule(k, stride_hw: int, in_c: int, out_c: int, n_tiles: int) -> 
     return [(mt, g) for g in groups for mt in mts]
 
 
+def halo_schedule(k, stride_hw: int, in_c: int, out_c: int, n_tiles: int) -> List[Tuple[int, int]]:
+    """default_schedule with the "halo" plans (group_kh = 2) first where they apply: one 18 x 18 input box per (kd, 64
+    channels) serves all nine (kh, kw) taps — every tap is a descriptor into the same box (tools/umma_shift_probe.cu).
+    Measured on B200: L2 -> SM bytes of the Conv3D blocks drop another 1.6x, the time does not (955 TFLOP/s either
+    way): at N = 64 the kernel is then bound by the MMAs' own shared-memory operand reads (6 KB per 128x64x16 MMA) and
+    the issuing thread. Kept as an option for when the L2 is shared with something else."""
+    cands = default_schedule(k, stride_hw, in_c, out_c, n_tiles)
+    if stride_hw == 1 and k[1] == 3 and k[2] == 3 and out_c <= 128:
+        cands = [(2, 2)] + cands
+    return cands
+
+
 class DenseNetwork:
     """Plans and activation buffers for one batch size and grid. `grid` is the input buffer the front end writes."""
 
@@ -179,9 +191,9 @@ class DenseNetwork:
             cands = [cands]
         layer, st = None, _native.LISEC_OK
         for m_tiles, group_kh in cands:
-            tw, th = best_tile(oh, ow, m_tiles, 8 if (m_tiles > 1 or group_kh) else 1)
+            tw, th = (8, 16) if group_kh == 2 else best_tile(oh, ow, m_tiles, 8 if (m_tiles > 1 or group_kh) else 1)
             Wk = np.asarray(W)
-            if group_kh:  # the kernel wants the kh taps of one (kd, kw) adjacent: [kd][kw][kh][N][C]
+            if group_kh == 1:  # the kernel wants the kh taps of one (kd, kw) adjacent: [kd][kw][kh][N][C]
                 Wk = Wk.reshape(k[0], k[1], k[2], -1, in_c).transpose(0, 2, 1, 3, 4).reshape(k[0] * k[1] * k[2], -1, in_c)
             desc = _native.lisec_conv_desc(
                 batch=self.batch, in_d=in_d, in_h=in_h, in_w=in_w, in_c=in_c, kd=k[0], kh=k[1], kw=k[2],

@@ -19,7 +19,7 @@ def layer_reference(L, src: torch.Tensor) -> torch.Tensor:
     d = L.desc
     x = src.float().cpu().permute(0, 4, 1, 2, 3)
     NT = d.n_tiles * d.out_c
-    if d.group_kh:  # stored [kd][kw][kh][NT][C]
+    if d.group_kh == 1:  # stored [kd][kw][kh][NT][C]
         w = L.w.float().cpu().reshape(d.kd, d.kw, d.kh, NT, d.in_c).permute(3, 4, 0, 2, 1)
     else:
         w = L.w.float().cpu().reshape(d.kd, d.kh, d.kw, NT, d.in_c).permute(3, 4, 0, 1, 2)
@@ -62,7 +62,17 @@ def _halo_one_tile(k, stride_hw, in_c, out_c, n_tiles):
     return [(1, 1), (1, 0)]
 
 
-@pytest.mark.parametrize("schedule", [None, _plain, _two_tiles, _halo_one_tile])
+def _full_halo_one_tile(k, stride_hw, in_c, out_c, n_tiles):
+    return [(1, 2), (1, 0)]
+
+
+def _full_halo_two_tiles(k, stride_hw, in_c, out_c, n_tiles):
+    from lisec_b200.network import halo_schedule
+
+    return halo_schedule(k, stride_hw, in_c, out_c, n_tiles)
+
+
+@pytest.mark.parametrize("schedule", [None, _plain, _two_tiles, _halo_one_tile, _full_halo_one_tile, _full_halo_two_tiles])
 @pytest.mark.parametrize("nx,ny,batch", [(24, 40, 2), (16, 8, 1), (40, 136, 1)])
 def test_every_plan_matches_a_float32_convolution_of_its_own_operands(nx, ny, batch, schedule):
     from lisec_b200.network import DenseNetwork, default_schedule

@@ -15,7 +15,11 @@ batch = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 check = len(sys.argv) > 2 and sys.argv[2] == "check"
 pack = synthetic_network_pack(0)
 sched = os.environ.get("NET_SCHED")  # e.g. "1,1" = (m_tiles, group_kh) for every layer that accepts it
-if sched:
+if sched == "halo":
+    from lisec_b200.network import halo_schedule
+
+    net = DenseNetwork(pack, batch=batch, schedule=halo_schedule)
+elif sched:
     from lisec_b200.network import default_schedule
 
     want = tuple(int(x) for x in sched.split(","))
@@ -49,7 +53,7 @@ for L, ms in zip(net.layers, acc):
     fl = 2.0 * d.batch * od * oh * ow * d.kd * d.kh * d.kw * d.in_c * d.out_c * d.n_tiles
     tot += ms
     print("%-20s %8.3f ms  %7.1f TFLOP/s  tile %dx%d x%d%s" % (L.name, ms, fl / ms / 1e9, d.tile_w, d.tile_h, d.m_tiles,
-                                                               " kh-halo" if d.group_kh else ""))
+                                                               (" kh-halo" if d.group_kh == 1 else " halo" if d.group_kh == 2 else "")))
 t0 = torch.cuda.Event(enable_timing=True)
 t1 = torch.cuda.Event(enable_timing=True)
 t0.record()
