@@ -36,7 +36,9 @@
 namespace lisec {
 namespace {
 
-constexpr int kConvThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
+constexpr int kConvThreads = 352;  // warp 0 TMA, warps 1 and 10 MMA (one M-tile each), warps 2-9 epilogue
+constexpr int kSecondIssuerWarp = 10;
+constexpr int kHaloThreads = 320;  // halo plans: warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int kMaxTaps = 27;
 constexpr int kMaxStages = 8;
 constexpr uint32_t kABytes = 128 * 128;  // 128 positions x 64 bf16 channels
@@ -126,22 +128,18 @@ __device__ __forceinline__ void mma_bf16_ss_lo(uint32_t d_tmem, uint32_t a_lo, u
 }
 
 // the MMAs of one shared-memory stage: GROUP taps x MT M-tiles x 4 k-steps of 16 channels
-template <int GROUP, int MT>
-__device__ __forceinline__ void issue_stage(uint32_t a0, uint32_t b0, uint32_t d0, uint32_t N, uint32_t h_row16,
-                                            uint32_t bh, uint32_t idesc, uint32_t first) {
+template <int GROUP>
+__device__ __forceinline__ void issue_stage(uint32_t a0, uint32_t b0, uint32_t d, uint32_t N, uint32_t h_row16,
+                                            uint32_t m_rows, uint32_t idesc, uint32_t first) {
   const uint64_t proto = umma::make_desc_k_sw128(0);
   const uint32_t hi = (uint32_t)(proto >> 32), lo0 = (uint32_t)proto;
-  const uint32_t a_lo0 = lo0 + (a0 >> 4), b_lo0 = lo0 + (b0 >> 4), b_tap16 = N * 8u;  // N * 128 bytes / 16
+  const uint32_t a_lo0 = lo0 + (a0 >> 4) + m_rows * h_row16, b_lo0 = lo0 + (b0 >> 4), b_tap16 = N * 8u;  // N * 128 bytes / 16
 #pragma unroll
-  for (int g = 0; g < GROUP; ++g)
+  for (int g = 0; g < GROUP; ++g) {
+    const uint32_t a_lo = a_lo0 + (uint32_t)g * h_row16, b_lo = b_lo0 + (uint32_t)g * b_tap16;
 #pragma unroll
-    for (int m = 0; m < MT; ++m) {
-      const uint32_t a_lo = a_lo0 + (uint32_t)(g + m * bh) * h_row16, b_lo = b_lo0 + (uint32_t)g * b_tap16;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        mma_bf16_ss_lo(d0 + (uint32_t)m * N, a_lo + 2 * j, b_lo + 2 * j, hi, idesc,
-                       (g == 0 && j == 0) ? first : 1u);
-    }
+    for (int j = 0; j < 4; ++j) mma_bf16_ss_lo(d, a_lo + 2 * j, b_lo + 2 * j, hi, idesc, (g == 0 && j == 0) ? first : 1u);
+  }
 }
 
 __device__ __forceinline__ void mma_tf32_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
@@ -330,10 +328,10 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     prefetch_tensormap(&map_b);
     for (int s = 0; s < P.stages; ++s) {
       umma::mbar_init(bar_full(s), 1);
-      umma::mbar_init(bar_empty(s), 1);
+      umma::mbar_init(bar_empty(s), P.mt);  // one tcgen05.commit per issuing thread
     }
     for (int a = 0; a < 2; ++a) {
-      umma::mbar_init(bar_acc_full(a), 1);
+      umma::mbar_init(bar_acc_full(a), P.mt);
       umma::mbar_init(bar_acc_empty(a), 8);
     }
     umma::mbar_init_fence();
@@ -349,30 +347,29 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) producer_loop(P, map_a, map_b, base, bar0);
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+  } else if (warp == 1 || warp == kSecondIssuerWarp) {
+    // ===== MMA issuers: one thread per M-tile =====
+    // A 128x64x16 MMA is worth ~32 tensor-pipe cycles, but one thread needs ~80 cycles of dependent uniform-datapath
+    // instructions to issue it; with two M-tiles per CTA tile each gets its own issuing thread (own accumulators, the
+    // same shared-memory stage; a stage is released by both commits).
+    const int m = warp == 1 ? 0 : 1;
+    if (lane == 0 && m < P.mt) {
       const uint32_t idesc = make_idesc_bf16_k(128, P.N);
       int s = 0, acc = 0;
       uint32_t ph = 0, acc_ph = 0;
+      const uint32_t h_row16 = (uint32_t)P.bw * 8u;  // one H row of the A box in 16-byte units (a multiple of 1 KB when used)
       for (long long tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         umma::mbar_wait(bar_acc_empty(acc), acc_ph ^ 1u);
         umma::fence_after_sync();
-        const uint32_t d0 = tmem_base + (uint32_t)(acc * P.mt * P.N);
-        const uint32_t h_row16 = (uint32_t)P.bw * 8u;  // one H row of the A box in 16-byte units (a multiple of 1 KB when used)
-        const int variant = (P.group == 3 ? 2 : 0) + (P.mt == 2 ? 1 : 0);
+        const uint32_t d = tmem_base + (uint32_t)((acc * P.mt + m) * P.N);
         for (int kb = 0; kb < k_blocks; ++kb) {
           umma::mbar_wait(bar_full(s), ph);
           umma::fence_after_sync();
           const uint32_t a0 = base + (uint32_t)s * stage_bytes, b0 = a0 + P.a_bytes;
           const uint32_t first = kb != 0;
-          switch (variant) {
-            case 0: issue_stage<1, 1>(a0, b0, d0, (uint32_t)P.N, h_row16, (uint32_t)P.bh, idesc, first); break;
-            case 1: issue_stage<1, 2>(a0, b0, d0, (uint32_t)P.N, h_row16, (uint32_t)P.bh, idesc, first); break;
-            case 2: issue_stage<3, 1>(a0, b0, d0, (uint32_t)P.N, h_row16, (uint32_t)P.bh, idesc, first); break;
-            default: issue_stage<3, 2>(a0, b0, d0, (uint32_t)P.N, h_row16, (uint32_t)P.bh, idesc, first); break;
-          }
-          umma::mma_commit(bar_empty(s));  // the stage is free again once these MMAs have read it
+          if (P.group == 3) issue_stage<3>(a0, b0, d, (uint32_t)P.N, h_row16, (uint32_t)(m * P.bh), idesc, first);
+          else issue_stage<1>(a0, b0, d, (uint32_t)P.N, h_row16, (uint32_t)(m * P.bh), idesc, first);
+          umma::mma_commit(bar_empty(s));  // the stage is free again once both issuers' MMAs have read it
           if (++s == P.stages) { s = 0; ph ^= 1u; }
         }
         umma::mma_commit(bar_acc_full(acc));
@@ -419,7 +416,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 // loaded once per (kd, 64-channel block); M-tile m (8 wide, 16 high, two side by side) under tap (kh, kw) starts at box
 // row kh * 18 + kw + 8 m and its 8-row groups are one box line (18 rows = 2304 bytes) apart. Input traffic per output
 // drops 2.7x against the kh-halo plans; the weights stream through their own ring, three kw taps per slot.
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kHaloThreads, 1)
     conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ ConvParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -975,7 +972,7 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
 
 int32_t lisec_conv_plan_run(lisec_conv_plan* pl, void* stream) {
   if (!pl) return conv_fail(LISEC_ERR_BAD_ARG, "null plan");
-  cudaError_t e = pl->p.halo ? launch_pdl(conv_halo_kernel, pl->grid, kConvThreads, (size_t)pl->smem,
+  cudaError_t e = pl->p.halo ? launch_pdl(conv_halo_kernel, pl->grid, kHaloThreads, (size_t)pl->smem,
                                           static_cast<cudaStream_t>(stream), pl->map_a, pl->map_b, pl->p)
                   : pl->p.f32 ? launch_pdl(conv_igemm_f32_kernel, pl->grid, kConvF32Threads, (size_t)pl->smem,
                                          static_cast<cudaStream_t>(stream), pl->map_a, pl->map_b, pl->p)
