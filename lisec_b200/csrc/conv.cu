@@ -38,7 +38,6 @@ namespace {
 
 constexpr int kConvThreads = 352;  // warp 0 TMA, warps 1 and 10 MMA (one M-tile each), warps 2-9 epilogue
 constexpr int kSecondIssuerWarp = 10;
-constexpr int kHaloThreads = 320;  // halo plans: warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int kMaxTaps = 27;
 constexpr int kMaxStages = 8;
 constexpr uint32_t kABytes = 128 * 128;  // 128 positions x 64 bf16 channels
@@ -416,7 +415,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 // loaded once per (kd, 64-channel block); M-tile m (8 wide, 16 high, two side by side) under tap (kh, kw) starts at box
 // row kh * 18 + kw + 8 m and its 8-row groups are one box line (18 rows = 2304 bytes) apart. Input traffic per output
 // drops 2.7x against the kh-halo plans; the weights stream through their own ring, three kw taps per slot.
-__global__ void __launch_bounds__(kHaloThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 1)
     conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ ConvParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -439,14 +438,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
     prefetch_tensormap(&map_b);
     for (int s = 0; s < P.a_slots; ++s) {
       umma::mbar_init(bar_a_full(s), 1);
-      umma::mbar_init(bar_a_empty(s), 1);
+      umma::mbar_init(bar_a_empty(s), P.mt);  // one commit per issuing thread
     }
     for (int s = 0; s < P.b_slots; ++s) {
       umma::mbar_init(bar_b_full(s), 1);
-      umma::mbar_init(bar_b_empty(s), 1);
+      umma::mbar_init(bar_b_empty(s), P.mt);
     }
     for (int a = 0; a < 2; ++a) {
-      umma::mbar_init(bar_acc_full(a), 1);
+      umma::mbar_init(bar_acc_full(a), P.mt);
       umma::mbar_init(bar_acc_empty(a), 8);
     }
     umma::mbar_init_fence();
@@ -482,8 +481,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
           }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
+  } else if (warp == 1 || warp == kSecondIssuerWarp) {
+    const int m = warp == 1 ? 0 : 1;  // one issuing thread per M-tile (see conv_igemm_kernel)
+    if (lane == 0 && m < P.mt) {
       const uint32_t idesc = make_idesc_bf16_k(128, P.N);
       const uint64_t proto = umma::make_desc_k_sw128(0);
       const uint32_t lo0 = (uint32_t)proto, hi_b = (uint32_t)(proto >> 32);
@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
       for (long long tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         umma::mbar_wait(bar_acc_empty(acc), acc_ph ^ 1u);
         umma::fence_after_sync();
-        const uint32_t d0 = tmem_base + (uint32_t)(acc * P.mt * P.N);
+        const uint32_t d = tmem_base + (uint32_t)((acc * P.mt + m) * P.N);
         for (int st = 0; st < a_steps; ++st) {
           umma::mbar_wait(bar_a_full(as), aph);
           const uint32_t a_lo0 = lo0 + ((base + (uint32_t)as * P.a_slot_bytes) >> 4);
@@ -504,29 +504,25 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
             umma::fence_after_sync();
             const uint32_t b_lo0 = lo0 + ((b_base + (uint32_t)bs * b_slot_bytes) >> 4);
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw)
+            for (int kw = 0; kw < 3; ++kw) {
+              const uint32_t a_lo = a_lo0 + (uint32_t)kh * line16 + (uint32_t)(kw + 8 * m) * 8u;
+              const uint32_t b_lo = b_lo0 + (uint32_t)kw * b_tap16;
 #pragma unroll
-              for (int m = 0; m < 2; ++m) {
-                if (m < P.mt) {
-                  const uint32_t a_lo = a_lo0 + (uint32_t)kh * line16 + (uint32_t)(kw + 8 * m) * 8u;
-                  const uint32_t b_lo = b_lo0 + (uint32_t)kw * b_tap16;
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const uint32_t accum = (st | kh | kw | j) != 0;
-                    asm volatile(
-                        "{\n\t"
-                        ".reg .pred p;\n\t"
-                        ".reg .b64 da, db;\n\t"
-                        "mov.b64 da, {%1, %3};\n\t"
-                        "mov.b64 db, {%2, %4};\n\t"
-                        "setp.ne.b32 p, %6, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
-                        "}\n" ::"r"(d0 + (uint32_t)(m * P.N)),
-                        "r"(a_lo + 2 * j), "r"(b_lo + 2 * j), "r"(hi_a), "r"(hi_b), "r"(idesc), "r"(accum)
-                        : "memory");
-                  }
-                }
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t accum = (st | kh | kw | j) != 0;
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred p;\n\t"
+                    ".reg .b64 da, db;\n\t"
+                    "mov.b64 da, {%1, %3};\n\t"
+                    "mov.b64 db, {%2, %4};\n\t"
+                    "setp.ne.b32 p, %6, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+                    "}\n" ::"r"(d),
+                    "r"(a_lo + 2 * j), "r"(b_lo + 2 * j), "r"(hi_a), "r"(hi_b), "r"(idesc), "r"(accum)
+                    : "memory");
               }
+            }
             umma::mma_commit(bar_b_empty(bs));
             if (++bs == P.b_slots) { bs = 0; bph ^= 1u; }
           }
@@ -972,7 +968,7 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
 
 int32_t lisec_conv_plan_run(lisec_conv_plan* pl, void* stream) {
   if (!pl) return conv_fail(LISEC_ERR_BAD_ARG, "null plan");
-  cudaError_t e = pl->p.halo ? launch_pdl(conv_halo_kernel, pl->grid, kHaloThreads, (size_t)pl->smem,
+  cudaError_t e = pl->p.halo ? launch_pdl(conv_halo_kernel, pl->grid, kConvThreads, (size_t)pl->smem,
                                           static_cast<cudaStream_t>(stream), pl->map_a, pl->map_b, pl->p)
                   : pl->p.f32 ? launch_pdl(conv_igemm_f32_kernel, pl->grid, kConvF32Threads, (size_t)pl->smem,
                                          static_cast<cudaStream_t>(stream), pl->map_a, pl->map_b, pl->p)

@@ -79,9 +79,9 @@ def default_schedule(k, stride_hw: int, in_c: int, out_c: int, n_tiles: int) -> 
 def halo_schedule(k, stride_hw: int, in_c: int, out_c: int, n_tiles: int) -> List[Tuple[int, int]]:
     """default_schedule with the "halo" plans (group_kh = 2) first where they apply: one 18 x 18 input box per (kd, 64
     channels) serves all nine (kh, kw) taps — every tap is a descriptor into the same box (tools/umma_shift_probe.cu).
-    Measured on B200: L2 -> SM bytes of the Conv3D blocks drop another 1.6x, the time does not (955 TFLOP/s either
-    way): at N = 64 the kernel is then bound by the MMAs' own shared-memory operand reads (6 KB per 128x64x16 MMA) and
-    the issuing thread. Kept as an option for when the L2 is shared with something else."""
+    Measured on B200: L2 -> SM bytes of the Conv3D blocks drop another 1.6x; with one MMA-issuing thread per M-tile the
+    Conv3D blocks run at 1096 TFLOP/s (1040 with the kh-halo plans), the whole network 1.56 ms per 8 sweeps (1.60).
+    This is the schedule DenseNetwork uses."""
     cands = default_schedule(k, stride_hw, in_c, out_c, n_tiles)
     if stride_hw == 1 and k[1] == 3 and k[2] == 3 and out_c <= 128:
         cands = [(2, 2)] + cands
@@ -92,7 +92,7 @@ class DenseNetwork:
     """Plans and activation buffers for one batch size and grid. `grid` is the input buffer the front end writes."""
 
     def __init__(self, pack: dict, batch: int, nx: int = 200, ny: int = 400, nz: int = 8, device: int = 0,
-                 schedule=default_schedule, dtype: str = "bf16"):
+                 schedule=None, dtype: str = "bf16"):
         if nz != 8 or nx % 8 or ny % 8:
             raise ValueError("the Conv3D stack collapses nz = 8 to 1 and the RPN halves x, y three times: need nz = 8 "
                              "and nx, ny multiples of 8 (got %d, %d, %d)" % (nz, nx, ny))
@@ -104,7 +104,7 @@ class DenseNetwork:
         if dtype not in ("bf16", "f32"):
             raise ValueError("dtype must be 'bf16' or 'f32', got %r" % (dtype,))
         self.f32 = dtype == "f32"
-        self._schedule = (lambda *a: [(1, 0)]) if self.f32 else schedule
+        self._schedule = (lambda *a: [(1, 0)]) if self.f32 else (schedule or halo_schedule)
         pack = validate_network_pack(pack)
         dev = self.device
         f32 = self.f32
