@@ -251,6 +251,33 @@ void lisec_conv_plan_destroy(lisec_conv_plan* plan);
 /* Text of the last lisec_conv_* failure on the calling thread. */
 const char* lisec_conv_last_error(void);
 
+/* ---- lidar ingest: the step before the path ---------------------------------------------------
+ *
+ * Replaces the arithmetic of combine_lidar_data + rotate_points (model_training.py:65-98):
+ *     rawPoints = np.fromfile(path, float32).reshape(-1, 5)[:, :3]                  (:87-90)
+ *     points    = np.dot(Quaternion(rotation).rotation_matrix, rawPoints.T).T       (:65-69, :93)
+ *     points    = points + np.array(translation);  np.concatenate over the sensors  (:94, :96)
+ * A segment = the records of one sensor file; segments are concatenated in the order the reference appends them
+ * (LIDAR_TOP, LIDAR_FRONT_RIGHT, LIDAR_FRONT_LEFT per sweep, :74), any number of sweeps behind one another.
+ *   rotation     row-major 3x3 float64 = Quaternion(sensor['rotation']).rotation_matrix (built on the host,
+ *                lisec_b200/ingest.py: three quaternions per sweep are not device work)
+ *   translation  sensor['translation'] as float64 */
+typedef struct lisec_sensor_pose {
+  double rotation[9];
+  double translation[3];
+} lisec_sensor_pose;
+
+/* [async] records: device float32 [n, record_floats] (record_floats = 5 for the Lyft .bin files; the first three are
+ * x, y, z); segment_offsets: HOST int64 [n_segments + 1], in points, starting at 0; poses: HOST [n_segments];
+ * points: device float64 [n, 3] — exactly the array combine_lidar_data returns, ready for lisec_voxelize(...,
+ * LISEC_F64, ...). Bit-identical to numpy: float32 -> float64 widening, k-ascending FMA chain, then the float64 add.
+ * launches_out (may be NULL) receives the number of kernels launched (one per 24 segments). Stateless; errors through
+ * lisec_ingest_last_error() on the calling thread. */
+int32_t lisec_ingest_lidar(const float* records, int32_t record_floats, const int64_t* segment_offsets,
+                           const lisec_sensor_pose* poses, int32_t n_segments, double* points, void* stream,
+                           int32_t* launches_out);
+const char* lisec_ingest_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,10 @@ class lisec_conv_desc(C.Structure):
         "in_dtype", "out_split", "group_kh", "reserved")]
 
 
+class lisec_sensor_pose(C.Structure):
+    _fields_ = [("rotation", C.c_double * 9), ("translation", C.c_double * 3)]
+
+
 _H = C.c_void_p
 _VP = C.c_void_p
 _I32P = C.POINTER(C.c_int32)
@@ -109,6 +113,8 @@ SIGNATURES = {
     "lisec_split_tf32": (C.c_int32, [_VP, _VP, _VP, C.c_int64, _VP]),
     "lisec_conv_plan_destroy": (None, [_H]),
     "lisec_conv_last_error": (C.c_char_p, []),
+    "lisec_ingest_lidar": (C.c_int32, [_VP, C.c_int32, _I64P, C.POINTER(lisec_sensor_pose), C.c_int32, _VP, _VP, _I32P]),
+    "lisec_ingest_last_error": (C.c_char_p, []),
 }
 
 _lib = None

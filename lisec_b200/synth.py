@@ -67,3 +67,47 @@ def saturated_cloud(n_points: int = 1_000_000, n_sweeps: int = 10, seed0: int = 
     return np.ascontiguousarray(
         np.concatenate([lyft_like_sweep(per, seed0 + s, theta, tail=(s == 0)) for s in range(n_sweeps)])
     )
+
+
+class SyntheticLyftTables:
+    """The two tables of lyft_dataset_sdk.LyftDataset that combine_lidar_data reads through `.get(table, token)`
+    (model_training.py:81-84)."""
+
+    def __init__(self):
+        self.tables = {"sample_data": {}, "calibrated_sensor": {}}
+
+    def get(self, table: str, token: str) -> dict:
+        return self.tables[table][token]
+
+
+def synthetic_lyft_sample(data_dir: str, n_points: int = 3000, seed: int = 0, sensors=("LIDAR_TOP", "LIDAR_FRONT_RIGHT",
+                                                                                      "LIDAR_FRONT_LEFT")):
+    """Writes one sample's sensor files the way the Lyft dataset lays them out — `lidar/<token>.bin`, float32 records
+    (x, y, z, intensity, ring) in the SENSOR frame — and returns (sample, tables) for combine_lidar_data. The sensor
+    poses are Lyft-like: the roof lidar nearly level, the two bumper lidars yawed outwards and slightly rolled."""
+    import os
+
+    rng = np.random.default_rng(seed)
+    os.makedirs(os.path.join(data_dir, "lidar"), exist_ok=True)
+    tables = SyntheticLyftTables()
+    poses = {
+        "LIDAR_TOP": ([0.99995, 0.0021, -0.0047, 0.0083], [1.2018, 0.0034, 1.8312]),
+        "LIDAR_FRONT_RIGHT": ([0.9239, 0.0105, -0.0052, -0.3824], [2.0421, -0.6103, 0.6251]),
+        "LIDAR_FRONT_LEFT": ([0.9236, -0.0098, -0.0049, 0.3831], [2.0397, 0.6124, 0.6247]),
+    }
+    sample = {"data": {}}
+    per = [n_points // len(sensors)] * len(sensors)
+    per[0] += n_points - sum(per)
+    for k, (name, n) in enumerate(zip(sensors, per)):
+        r = rng.gamma(2.0, 9.0, size=n)
+        az = rng.uniform(0, 2 * np.pi, size=n)
+        rec = np.stack([r * np.cos(az), r * np.sin(az), rng.normal(-0.9, 0.7, size=n), rng.uniform(0, 255, size=n),
+                        rng.integers(0, 64, size=n).astype(np.float64)], axis=1).astype(np.float32)
+        token = "%s_%d" % (name.lower(), seed)
+        rec.tofile(os.path.join(data_dir, "lidar", token + ".bin"))
+        quat, trans = poses[name]
+        quat = (np.asarray(quat) + rng.normal(0, 1e-3, size=4)).tolist()  # not exactly unit: _normalise has work to do
+        tables.tables["sample_data"][token] = {"filename": "lidar/%s.bin" % token, "calibrated_sensor_token": "cs_" + token}
+        tables.tables["calibrated_sensor"]["cs_" + token] = {"rotation": quat, "translation": list(trans)}
+        sample["data"][name] = token
+    return sample, tables
