@@ -329,6 +329,24 @@ def run_native(args):
     ms_lidar_step = timed(step_lidar, n_k)
     ingest_bytes = n_pts * (5 * 4 + 3 * 8)
 
+    # the step after the path: rpnToRegion = decode + rotated-box NMS (maxBoxes=20,
+    # overlapThresh=0.) on the batch's 8 head tensors, one thread-block cluster per sample
+    from lisec_b200.decode import RegionDecoder
+
+    dec = RegionDecoder(local)
+    heads_np = [synth.synthetic_rpn_output(seed=100 + rank * SWEEPS_PER_GPU + s) for s in range(SWEEPS_PER_GPU)]
+    heads_dev = torch.from_numpy(np.stack([np.concatenate(h, axis=-1) for h in heads_np])).to(dev)
+    ms_regions = timed(lambda: dec.regions(heads_dev[..., :2], heads_dev[..., 2:]), n_k)
+    bx, sc = dec.decode(heads_dev[..., :2], heads_dev[..., 2:])
+    ms_nms = timed(lambda: dec.nms(bx, sc, 0., 20), n_k)
+    regions_cpu_s = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import decode_oracle as DO
+
+        t0 = time.perf_counter()
+        DO.non_max_suppression_vec(*DO.decode_boxes(*heads_np[0]), 0., 20)
+        regions_cpu_s = time.perf_counter() - t0
+
     # end to end through the host-buffer entry point
     n_w = min(args.warmup, 3)
     for i in range(n_w):
@@ -460,6 +478,16 @@ def run_native(args):
                              "sweeps_per_s_from_records": SWEEPS_PER_GPU / (ms_lidar_step * 1e-3),
                              "note": "35 MB per launch: launch latency, not bandwidth, sets the time; the step from "
                                      "records runs the front end on float64 points (24 B per point instead of 12)"},
+            "rpn_to_region": {"kernels": "decode_kernel + nms_kernel (8-CTA cluster per sample, survivors in distributed "
+                                         "shared memory)", "samples_per_call": SWEEPS_PER_GPU,
+                              "candidates_per_sample": dec.n, "max_boxes": 20, "overlap_thresh": 0.0,
+                              "ms_per_call": ms_regions, "nms_ms_per_call": ms_nms,
+                              "samples_per_s": SWEEPS_PER_GPU / (ms_regions * 1e-3),
+                              "bound": "latency: <= 21 dependent rounds of (cluster-wide arg-max, overlap tests)",
+                              "cpu_baseline": None if regions_cpu_s is None else {
+                                  "value": 1.0 / regions_cpu_s, "unit": "samples/s", "cores": 1, "kind": "port",
+                                  "sample": "one sample: the oracle's numpy decode + vectorised greedy NMS (the "
+                                            "reference's own Python loop takes ~16 s per sample)"}},
             "clocks": clocks,
         }
         if full is not None:

@@ -278,6 +278,46 @@ int32_t lisec_ingest_lidar(const float* records, int32_t record_floats, const in
                            int32_t* launches_out);
 const char* lisec_ingest_last_error(void);
 
+/* ---- RPN decode + non-maximum suppression: the step after the path ----------------------------
+ *
+ * Replaces rpnToRegion(labelsClass, labelsRegress) (rpnToRegion.py:115-164) on the two tensors model.predict returns:
+ * anchors at the cell centres (:137-144), applyRegrssion (:77-88), anchor-major flattening (:150-152), then
+ * nonMaxSuppressionFast(boxInfo, probInfo, maxBoxes=20, overlapThresh=0.) (:18-74) with calculateIoU of
+ * serialize_data.py:140-181 (rotated footprints, the reference's full-height z extents). */
+#define LISEC_MAX_ANCHORS 4
+
+typedef struct lisec_rpn_desc {
+  int32_t out_x, out_y, n_anchors;           /* Constants.nx // 2, Constants.ny // 2, len(Constants.anchors): 100, 200, 2 */
+  int32_t reserved;
+  double cell_x, cell_y;                     /* voxelXSize, voxelYSize of the output map: 2 * voxelx, 2 * voxely (:122-123) */
+  double anchor_z;                           /* A[2] = 1. (:139) */
+  double anchors[LISEC_MAX_ANCHORS][4];      /* Constants.anchors rows: length, width, height, yaw (Constants.py:17) */
+} lisec_rpn_desc;
+
+/* [async] prob: device float32, element (s, a, b, i) at prob[s*prob_batch_stride + (a*out_y + b)*prob_pitch + i];
+ * regress likewise with 7*n_anchors channels. boxes: device float64 [batch, N, 7] (x, y, z, l, w, h, yaw), scores:
+ * device float32 [batch, N], N = n_anchors*out_x*out_y, candidate index = i*out_x*out_y + a*out_y + b — boxInfo and
+ * probInfo of rpnToRegion.py:150-152. float64 arithmetic as numpy evaluates it; the exp is float32's. */
+int32_t lisec_rpn_decode(const lisec_rpn_desc* desc, const float* prob, int64_t prob_pitch, int64_t prob_batch_stride,
+                         const float* regress, int64_t reg_pitch, int64_t reg_batch_stride, int32_t batch,
+                         double* boxes, float* scores, void* stream);
+
+typedef struct lisec_nms_desc {
+  double overlap_thresh;   /* overlapThresh: a survivor is deleted when iou > overlap_thresh (>= 0)            */
+  int32_t max_boxes;       /* maxBoxes: the loop stops once len(pick) > maxBoxes, i.e. at most max_boxes + 1  */
+  int32_t reserved;
+  double margin_x, margin_y, limit_x, limit_y; /* the range test of :55-58: Constants.anchors[0][0], [0][1], 100, 100 */
+} lisec_nms_desc;
+
+/* [async] nonMaxSuppressionFast on `batch` independent samples (one thread-block cluster each). boxes: device float64
+ * [batch, n, 7]; scores: device float32 [batch, n]. Outputs (device): picks int32 [batch, max_boxes + 1] (flat candidate
+ * indices in pick order, -1 padded), n_picks int32 [batch], out_boxes float64 [batch, max_boxes + 1, 7], out_scores
+ * float32 [batch, max_boxes + 1] — boxInfo[pick], probInfo[pick] of :72-74. Score ties go to the larger index; NaN
+ * scores are picked last (numpy's argsort would pick them first). */
+int32_t lisec_nms_rotated(const lisec_nms_desc* desc, const double* boxes, const float* scores, int32_t n, int32_t batch,
+                          int32_t* picks, int32_t* n_picks, double* out_boxes, float* out_scores, void* stream);
+const char* lisec_decode_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

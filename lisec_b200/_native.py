@@ -80,6 +80,20 @@ class lisec_sensor_pose(C.Structure):
     _fields_ = [("rotation", C.c_double * 9), ("translation", C.c_double * 3)]
 
 
+LISEC_MAX_ANCHORS = 4
+
+
+class lisec_rpn_desc(C.Structure):
+    _fields_ = [("out_x", C.c_int32), ("out_y", C.c_int32), ("n_anchors", C.c_int32), ("reserved", C.c_int32),
+                ("cell_x", C.c_double), ("cell_y", C.c_double), ("anchor_z", C.c_double),
+                ("anchors", (C.c_double * 4) * LISEC_MAX_ANCHORS)]
+
+
+class lisec_nms_desc(C.Structure):
+    _fields_ = [("overlap_thresh", C.c_double), ("max_boxes", C.c_int32), ("reserved", C.c_int32),
+                ("margin_x", C.c_double), ("margin_y", C.c_double), ("limit_x", C.c_double), ("limit_y", C.c_double)]
+
+
 _H = C.c_void_p
 _VP = C.c_void_p
 _I32P = C.POINTER(C.c_int32)
@@ -115,6 +129,10 @@ SIGNATURES = {
     "lisec_conv_last_error": (C.c_char_p, []),
     "lisec_ingest_lidar": (C.c_int32, [_VP, C.c_int32, _I64P, C.POINTER(lisec_sensor_pose), C.c_int32, _VP, _VP, _I32P]),
     "lisec_ingest_last_error": (C.c_char_p, []),
+    "lisec_rpn_decode": (C.c_int32, [C.POINTER(lisec_rpn_desc), _VP, C.c_int64, C.c_int64, _VP, C.c_int64, C.c_int64,
+                                     C.c_int32, _VP, _VP, _VP]),
+    "lisec_nms_rotated": (C.c_int32, [C.POINTER(lisec_nms_desc), _VP, _VP, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, _VP]),
+    "lisec_decode_last_error": (C.c_char_p, []),
 }
 
 _lib = None

@@ -111,3 +111,23 @@ def synthetic_lyft_sample(data_dir: str, n_points: int = 3000, seed: int = 0, se
         tables.tables["calibrated_sensor"]["cs_" + token] = {"rotation": quat, "translation": list(trans)}
         sample["data"][name] = token
     return sample, tables
+
+
+def synthetic_rpn_output(seed: int = 0, out_x: int = 100, out_y: int = 200, n_anchors: int = 2, n_objects: int = 40):
+    """(labelsClass (out_x,out_y,n_anchors), labelsRegress (out_x,out_y,7*n_anchors)) float32, shaped like what
+    model.predict returns for one sample (Predict.py:38): a low, noisy score floor with `n_objects` bumps, small
+    regressions. Scores are distinct (the reference's argsort leaves tie order unspecified)."""
+    rng = np.random.default_rng(seed)
+    cls = rng.uniform(0.0, 0.3, size=(out_x, out_y, n_anchors))
+    for _ in range(n_objects):
+        a, b, i = rng.integers(0, out_x), rng.integers(0, out_y), rng.integers(0, n_anchors)
+        aa, bb = np.meshgrid(np.arange(out_x), np.arange(out_y), indexing="ij")
+        cls[:, :, i] += rng.uniform(0.4, 0.7) * np.exp(-((aa - a) ** 2 / 8.0 + (bb - b) ** 2 / 30.0))
+    cls = cls.astype(np.float32)
+    flat = cls.reshape(-1)
+    order = np.argsort(flat, kind="stable")
+    flat[order] = np.sort(flat) + np.arange(flat.size, dtype=np.float32) * np.float32(1e-7)  # break ties, keep the order
+    assert len(np.unique(flat)) == flat.size
+    reg = rng.normal(0.0, 0.25, size=(out_x, out_y, 7 * n_anchors))
+    reg[:, :, 6::7] = rng.normal(0.0, 0.6, size=(out_x, out_y, n_anchors))
+    return cls, reg.astype(np.float32)
