@@ -411,7 +411,8 @@ def run_native(args):
         ms_full_e2e = max_over_ranks(g0.elapsed_time(g1)) / args.steps
         full = {"ms_per_step": ms_full, "network_ms": ms_net, "flops_per_step": net.flops,
                 "ms_e2e": ms_full_e2e, "d2h": out_host.numel() * 4,
-                "launches_per_step": fe16.last_launch_count + len(net.layers)}
+                "launches_per_step": fe16.last_launch_count + net.launches_per_forward,
+                "net_launches": net.launches_per_forward}
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             # CPU side of the dense network: the oracle's torch-CPU float32 forward on one sweep's grid, all host threads
             from oracle import network_oracle as NO
@@ -502,8 +503,9 @@ def run_native(args):
                 "e2e": {"value": SWEEPS_PER_GPU * world / (full["ms_e2e"] * 1e-3), "unit": "sweeps/s",
                         "ms_per_step": full["ms_e2e"], "h2d_bytes_per_step": points_bytes,
                         "d2h_bytes_per_step": full["d2h"]},
-                "roofline": {"kernel": "conv_igemm_kernel x %d (middle Conv3D + RPN + heads), timed alone"
-                                       % (full["launches_per_step"] - fe.last_launch_count),
+                "roofline": {"kernel": "conv_halo_kernel / conv_igemm_kernel x %d + heads_combine (middle Conv3D + RPN + "
+                                       "heads; the transposed convolutions are folded into the head kernels), timed alone"
+                                       % (full["net_launches"] - 1),
                              "bound": "tensor", "achieved": tfl, "peak": tpk, "unit": "TFLOP/s", "frac": tfl / tpk,
                              "peak_source": tsrc, "algorithmic_flops_per_step": full["flops_per_step"],
                              "ms_per_step": full["network_ms"], "traffic": None}}

@@ -245,6 +245,14 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* desc, const void* in, cons
 int32_t lisec_conv_plan_run(lisec_conv_plan* plan, void* stream);
 /* [async] x[n] float32 -> hi[n], lo[n]: the operand planes a float32 plan reads (n a multiple of 4). */
 int32_t lisec_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+/* [async] The tail of createModel without the 768-channel concat tensor: Conv2DTranspose (no activation, model_training.py:
+ * 247-251) -> Concatenate (:252) -> ClassificationLayer / RegressionLayer (1x1, :253-254) is one linear map per RPN block.
+ * With each transposed kernel folded into its 256 rows of the head kernels on the host, three plans leave float32 tensors
+ *   c1 [batch, out_h, out_w, n_ch]                         (the k3 s1 block; its shift carries every bias)
+ *   c2 [batch, out_h/s2, out_w/s2, s2*s2*n_ch], c3 likewise with s3: channel group (i*s + j) -> pixel (s*h + i, s*w + j)
+ * and this call adds them into out [batch, out_h, out_w, n_ch] (n_ch = 2 + 14). All device pointers. */
+int32_t lisec_heads_combine(const float* c1, const float* c2, int32_t s2, const float* c3, int32_t s3, float* out,
+                            int32_t batch, int32_t out_h, int32_t out_w, int32_t n_ch, void* stream);
 /* out_dhw[3] = output depth, height, width (after the pixel shuffle). */
 int32_t lisec_conv_plan_output_shape(const lisec_conv_plan* plan, int32_t* out_dhw);
 void lisec_conv_plan_destroy(lisec_conv_plan* plan);

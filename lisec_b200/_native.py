@@ -124,6 +124,8 @@ SIGNATURES = {
     "lisec_conv_plan_create": (C.c_int32, [C.POINTER(lisec_conv_desc), _VP, _VP, _VP, _VP, _VP, C.POINTER(_H)]),
     "lisec_conv_plan_run": (C.c_int32, [_H, _VP]),
     "lisec_conv_plan_output_shape": (C.c_int32, [_H, _I32P]),
+    "lisec_heads_combine": (C.c_int32, [_VP, _VP, C.c_int32, _VP, C.c_int32, _VP, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_int32, _VP]),
     "lisec_split_tf32": (C.c_int32, [_VP, _VP, _VP, C.c_int64, _VP]),
     "lisec_conv_plan_destroy": (None, [_H]),
     "lisec_conv_last_error": (C.c_char_p, []),

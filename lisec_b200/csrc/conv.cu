@@ -693,6 +693,41 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restric
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
+// ---- heads combine -------------------------------------------------------------------------------------------------
+// Conv2DTranspose (no activation, :247-251) -> Concatenate (:252) -> the two 1x1 head convolutions (:253-254) is ONE
+// linear map per RPN block, so the host folds each transposed kernel with its 256 rows of the head kernels
+// (lisec_b200/network.py) and the three blocks leave small float32 tensors: c1 [B,H,W,n] at the output resolution (from
+// the k3 s1 block; carries every bias), c2 [B,H/s2,W/s2,s2*s2*n] and c3 [B,H/s3,W/s3,s3*s3*n] whose channel group
+// (i*s + j) belongs to output pixel (s*h + i, s*w + j). This kernel adds them: the 768-channel concat tensor (245 MB per 8
+// sweeps, written once and read once) never exists. Thread = (pixel, 4 channels).
+__global__ void __launch_bounds__(256)
+    heads_combine_kernel(const float* __restrict__ c1, const float* __restrict__ c2, int s2, const float* __restrict__ c3,
+                         int s3, float* __restrict__ out, int batch, int H, int W, int n) {
+  pdl_launch_dependents();
+  const int q = n >> 2;
+  const long long total = (long long)batch * H * W * q;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
+  if (gid >= total) return;
+  const int c = (int)(gid % q);
+  const long long pix = gid / q;
+  const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+  float4 v = __ldg(reinterpret_cast<const float4*>(c1 + pix * n) + c);
+  {
+    const int h2 = H / s2, w2 = W / s2;
+    const size_t p = ((size_t)b * h2 + y / s2) * w2 + x / s2;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(c2 + (p * (s2 * s2) + (y % s2) * s2 + (x % s2)) * n) + c);
+    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+  }
+  {
+    const int h3 = H / s3, w3 = W / s3;
+    const size_t p = ((size_t)b * h3 + y / s3) * w3 + x / s3;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(c3 + (p * (s3 * s3) + (y % s3) * s3 + (x % s3)) * n) + c);
+    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+  }
+  reinterpret_cast<float4*>(out + pix * n)[c] = v;
+}
+
 thread_local char g_conv_error[512] = "";
 
 int conv_fail(int status, const char* fmt, ...) {
@@ -975,6 +1010,21 @@ int32_t lisec_conv_plan_run(lisec_conv_plan* pl, void* stream) {
                             : launch_pdl(conv_igemm_kernel, pl->grid, kConvThreads, (size_t)pl->smem,
                                          static_cast<cudaStream_t>(stream), pl->map_a, pl->map_b, pl->p);
   if (e != cudaSuccess) return conv_fail(LISEC_ERR_CUDA, "conv launch: %s", cudaGetErrorString(e));
+  return LISEC_OK;
+}
+
+int32_t lisec_heads_combine(const float* c1, const float* c2, int32_t s2, const float* c3, int32_t s3, float* out,
+                            int32_t batch, int32_t out_h, int32_t out_w, int32_t n_ch, void* stream) {
+  if (!c1 || !c2 || !c3 || !out) return conv_fail(LISEC_ERR_BAD_ARG, "null argument");
+  if (batch < 0 || out_h <= 0 || out_w <= 0 || n_ch <= 0 || n_ch % 4 || s2 < 1 || s3 < 1 || out_h % s2 || out_w % s2 ||
+      out_h % s3 || out_w % s3)
+    return conv_fail(LISEC_ERR_BAD_CONFIG, "heads combine: n_ch a multiple of 4, out_h and out_w multiples of both strides");
+  const long long total = (long long)batch * out_h * out_w * (n_ch / 4);
+  if (total == 0) return LISEC_OK;
+  cudaError_t e = launch_pdl(heads_combine_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0,
+                             static_cast<cudaStream_t>(stream), c1, c2, (int)s2, c3, (int)s3, out, (int)batch, (int)out_h,
+                             (int)out_w, (int)n_ch);
+  if (e != cudaSuccess) return conv_fail(LISEC_ERR_CUDA, "heads combine: %s", cudaGetErrorString(e));
   return LISEC_OK;
 }
 

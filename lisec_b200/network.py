@@ -92,7 +92,7 @@ class DenseNetwork:
     """Plans and activation buffers for one batch size and grid. `grid` is the input buffer the front end writes."""
 
     def __init__(self, pack: dict, batch: int, nx: int = 200, ny: int = 400, nz: int = 8, device: int = 0,
-                 schedule=None, dtype: str = "bf16"):
+                 schedule=None, dtype: str = "bf16", fuse_heads: bool = True):
         if nz != 8 or nx % 8 or ny % 8:
             raise ValueError("the Conv3D stack collapses nz = 8 to 1 and the RPN halves x, y three times: need nz = 8 "
                              "and nx, ny multiples of 8 (got %d, %d, %d)" % (nz, nx, ny))
@@ -106,6 +106,7 @@ class DenseNetwork:
         self.f32 = dtype == "f32"
         self._schedule = (lambda *a: [(1, 0)]) if self.f32 else (schedule or halo_schedule)
         self._auto_schedule = schedule is None and not self.f32
+        self.fuse_heads = bool(fuse_heads)
         self._sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
         pack = validate_network_pack(pack)
         dev = self.device
@@ -136,7 +137,22 @@ class DenseNetwork:
         assert d == 1
         # ---- RPN (:245-251) ----
         h, w = nx, ny
-        self.concat = buf(B, 1, nx // 2, ny // 2, 768)
+        # Tail of the network (:247-254). Conv2DTranspose has no activation and no BatchNormalization behind it, Concatenate is
+        # a layout, the heads are 1x1 convolutions: per RPN block, transposed convolution -> its 256 rows of the head kernels
+        # is ONE linear map. fuse_heads folds them on the host (float64): block 1 becomes a 3x3 plan with 16 output columns
+        # at the output resolution, blocks 2 and 3 become 1x1 plans with s*s*16 columns at their own resolution, and
+        # lisec_heads_combine adds the three. The [B,100,200,768] concat tensor (245 MB per 8 sweeps, written and re-read)
+        # and 95 % of the tail's multiply-adds disappear; nothing is rounded to bf16 between the blocks and the heads.
+        Kh = np.concatenate([pack["ClassificationLayer/kernel"][0, 0], pack["RegressionLayer/kernel"][0, 0]],
+                            axis=1).astype(np.float64)  # (768, 16)
+        bh = np.concatenate([pack["ClassificationLayer/bias"], pack["RegressionLayer/bias"]]).astype(np.float64)
+        self.heads = buf(B, 1, nx // 2, ny // 2, 16, dtype=torch.float32, planes=False)
+        self._parts = []
+        if self.fuse_heads:
+            for (_, (tname, k, s, tc_in)), bi in zip(rpn_blocks(), range(3)):
+                bh = bh + pack[tname + "/bias"].astype(np.float64) @ Kh[256 * bi:256 * bi + 256]
+        else:
+            self.concat = buf(B, 1, nx // 2, ny // 2, 768)
         for bi, (convs, (tname, k, s, tc_in)) in enumerate(rpn_blocks()):
             pp = None
             for conv, bn, cin, cout, stride in convs:
@@ -153,7 +169,22 @@ class DenseNetwork:
                 src, h, w = dst, oh, ow
             F = pack[tname + "/kernel"].astype(np.float64)  # (k, k, 256, cin)
             bias = pack[tname + "/bias"].astype(np.float64)
-            if s == 1:  # 'same' k3 s1: out[y] = sum_ky in[y + 1 - ky] F[ky] = a 3x3 convolution with the flipped kernel
+            if self.fuse_heads:
+                Kb = Kh[256 * bi:256 * bi + 256]  # this block's rows of the head kernels
+                if s == 1:  # flipped 3x3 kernel (see below), then 256 -> 16 columns; every bias rides on this plan
+                    W = np.einsum("toc,on->tnc", F[::-1, ::-1].reshape(9, 256, tc_in), Kb)
+                    part = buf(B, 1, h, w, 16, dtype=torch.float32, planes=False)
+                    self._add(tname + "+heads", src, part, W, np.ones(16), bh, in_d=1, in_h=h, in_w=w, in_c=tc_in,
+                              k=(1, 3, 3), stride_d=1, stride_hw=1, pad=(0, 1, 1), out_c=16, relu=0,
+                              out_dtype=_native.LISEC_F32, out_split=0)
+                else:  # kernel == stride: column group (i, j) of a 1x1 GEMM belongs to output pixel (s y + i, s x + j)
+                    W = np.einsum("ijoc,on->ijnc", F, Kb).reshape(1, k * k * 16, tc_in)
+                    part = buf(B, 1, h, w, k * k * 16, dtype=torch.float32, planes=False)
+                    self._add(tname + "+heads", src, part, W, np.ones(k * k * 16), np.zeros(k * k * 16), in_d=1, in_h=h,
+                              in_w=w, in_c=tc_in, k=(1, 1, 1), stride_d=1, stride_hw=1, pad=(0, 0, 0), out_c=k * k * 16,
+                              relu=0, out_dtype=_native.LISEC_F32, out_split=0)
+                self._parts.append((part, s))
+            elif s == 1:  # 'same' k3 s1: out[y] = sum_ky in[y + 1 - ky] F[ky] = a 3x3 convolution with the flipped kernel
                 W = F[::-1, ::-1].reshape(9, 256, tc_in)
                 self._add(tname, src, self.concat, W, np.ones(256), bias, in_d=1, in_h=h, in_w=w, in_c=tc_in,
                           k=(1, 3, 3), stride_d=1, stride_hw=1, pad=(0, 1, 1), out_c=256, relu=0, out_pitch=768,
@@ -164,12 +195,10 @@ class DenseNetwork:
                           k=(1, 1, 1), stride_d=1, stride_hw=1, pad=(0, 0, 0), out_c=256, relu=0, out_pitch=768,
                           out_ch_off=256 * bi, n_tiles=k * k, shuffle=s)
         # ---- heads (:253-254): 2 + 14 columns of one 1x1 GEMM ----
-        Kh = np.concatenate([pack["ClassificationLayer/kernel"][0, 0], pack["RegressionLayer/kernel"][0, 0]], axis=1)
-        bh = np.concatenate([pack["ClassificationLayer/bias"], pack["RegressionLayer/bias"]]).astype(np.float64)
-        self.heads = buf(B, 1, nx // 2, ny // 2, 16, dtype=torch.float32, planes=False)
-        self._add("heads", self.concat, self.heads, Kh.astype(np.float64).T.reshape(1, 16, 768), np.ones(16), bh, in_d=1,
-                  in_h=nx // 2, in_w=ny // 2, in_c=768, k=(1, 1, 1), stride_d=1, stride_hw=1, pad=(0, 0, 0), out_c=16,
-                  relu=0, out_dtype=_native.LISEC_F32, out_split=0)
+        if not self.fuse_heads:
+            self._add("heads", self.concat, self.heads, Kh.T.reshape(1, 16, 768), np.ones(16), bh, in_d=1,
+                      in_h=nx // 2, in_w=ny // 2, in_c=768, k=(1, 1, 1), stride_d=1, stride_hw=1, pad=(0, 0, 0), out_c=16,
+                      relu=0, out_dtype=_native.LISEC_F32, out_split=0)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
 
     def _add(self, name, src, dst, W, scale, shift, *, in_d, in_h, in_w, in_c, k, stride_d, stride_hw, pad, out_c, relu,
@@ -258,6 +287,24 @@ class DenseNetwork:
                 if st != _native.LISEC_OK:
                     raise _native.LisecError(st, "%s: %s" % (L.name, self._lib.lisec_conv_last_error().decode()))
 
+    def combine_heads(self) -> None:
+        """fuse_heads: heads = the three blocks' folded contributions summed (one launch); otherwise nothing to do."""
+        if not self.fuse_heads:
+            return
+        (c1, s1), (c2, s2), (c3, s3) = self._parts
+        assert s1 == 1
+        with torch.cuda.device(self.device):
+            st = self._lib.lisec_heads_combine(C.c_void_p(c1.data_ptr()), C.c_void_p(c2.data_ptr()), s2,
+                                               C.c_void_p(c3.data_ptr()), s3, C.c_void_p(self.heads.data_ptr()),
+                                               self.batch, self.nx // 2, self.ny // 2, 16,
+                                               C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        if st != _native.LISEC_OK:
+            raise _native.LisecError(st, self._lib.lisec_conv_last_error().decode())
+
+    @property
+    def launches_per_forward(self) -> int:
+        return len(self.layers) + (1 if self.fuse_heads else 0) + (1 if self.f32 else 0)
+
     def forward(self, grid: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """prob [B, nx/2, ny/2, 2], regress [B, nx/2, ny/2, 14] (float32 views of one buffer) from self.grid."""
         if grid is not None and grid.data_ptr() != self.grid.data_ptr():
@@ -270,6 +317,7 @@ class DenseNetwork:
             if st != _native.LISEC_OK:
                 raise _native.LisecError(st, self._lib.lisec_conv_last_error().decode())
         self.run_layers()
+        self.combine_heads()
         return self.heads[:, 0, :, :, :2], self.heads[:, 0, :, :, 2:]
 
     def close(self) -> None:

@@ -72,13 +72,19 @@ def _full_halo_two_tiles(k, stride_hw, in_c, out_c, n_tiles):
     return halo_schedule(k, stride_hw, in_c, out_c, n_tiles)
 
 
-@pytest.mark.parametrize("schedule", [None, _plain, _two_tiles, _halo_one_tile, _full_halo_one_tile, _full_halo_two_tiles])
+@pytest.mark.parametrize("schedule", [None, "unfused", _plain, _two_tiles, _halo_one_tile, _full_halo_one_tile,
+                                      _full_halo_two_tiles])
 @pytest.mark.parametrize("nx,ny,batch", [(24, 40, 2), (16, 8, 1), (40, 136, 1)])
 def test_every_plan_matches_a_float32_convolution_of_its_own_operands(nx, ny, batch, schedule):
+    """"unfused": the tail as separate Conv2DTranspose (pixel-shuffle plans into the 768-channel concat buffer) and heads
+    plans; every other case runs the folded tail (transposed convolution x head kernels, lisec_heads_combine)."""
     from lisec_b200.network import DenseNetwork, default_schedule
     from lisec_b200.weights import synthetic_network_pack
 
-    net = DenseNetwork(synthetic_network_pack(1), batch=batch, nx=nx, ny=ny, schedule=schedule or default_schedule)
+    unfused = schedule == "unfused"
+    net = DenseNetwork(synthetic_network_pack(1), batch=batch, nx=nx, ny=ny,
+                       schedule=default_schedule if (unfused or schedule is None) else schedule, fuse_heads=not unfused)
+    assert any(L.desc.shuffle > 1 for L in net.layers) == unfused
     g = torch.Generator(device="cpu").manual_seed(5)
     net.grid.copy_(torch.randn(net.grid.shape, generator=g).clamp_(min=-0.5).to(torch.bfloat16))
     for i, L in enumerate(net.layers):
@@ -154,14 +160,38 @@ def test_network_matches_the_keras_oracle_float32():
         net.close()
 
 
-def test_network_matches_the_keras_oracle_bf16():
+def test_heads_combine_adds_the_three_blocks():
+    """lisec_heads_combine against the same sum in torch: group (i*s + j) of a low-resolution tensor -> pixel (s*h+i, s*w+j)."""
+    from lisec_b200 import _native
+    import ctypes as C
+
+    lib = _native.load()
+    g = torch.Generator(device="cpu").manual_seed(2)
+    B, H, W = 3, 24, 40
+    c1 = torch.randn((B, H, W, 16), generator=g)
+    c2 = torch.randn((B, H // 2, W // 2, 4 * 16), generator=g)
+    c3 = torch.randn((B, H // 4, W // 4, 16 * 16), generator=g)
+    out = torch.full((B, H, W, 16), float("nan"), device="cuda")
+    d1, d2, d3 = c1.cuda(), c2.cuda(), c3.cuda()
+    st = lib.lisec_heads_combine(d1.data_ptr(), d2.data_ptr(), 2, d3.data_ptr(), 4, out.data_ptr(), B, H, W, 16,
+                                 torch.cuda.current_stream().cuda_stream)
+    assert st == 0
+    up = lambda c, s: c.reshape(B, H // s, W // s, s, s, 16).permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, 16)  # noqa: E731
+    want = (c1 + up(c2, 2)) + up(c3, 4)
+    assert torch.equal(out.cpu(), want)
+    assert lib.lisec_heads_combine(d1.data_ptr(), d2.data_ptr(), 2, d3.data_ptr(), 4, out.data_ptr(), B, 26, W, 16, None) == -2
+
+
+@pytest.mark.parametrize("fuse_heads", [True, False])
+def test_network_matches_the_keras_oracle_bf16(fuse_heads):
     from lisec_b200.network import DenseNetwork
     from lisec_b200.weights import synthetic_network_pack
     from oracle import network_oracle as NO
 
     pack = synthetic_network_pack(0)
     nx, ny, batch = 24, 40, 2
-    net = DenseNetwork(pack, batch=batch, nx=nx, ny=ny)
+    net = DenseNetwork(pack, batch=batch, nx=nx, ny=ny, fuse_heads=fuse_heads)
+    assert len(net.layers) == (22 if fuse_heads else 23)
     g = torch.Generator(device="cpu").manual_seed(11)
     grid = torch.rand((batch, 8, nx, ny, 64), generator=g).to(torch.bfloat16)
     net.grid.copy_(grid)
