@@ -425,6 +425,41 @@ def run_native(args):
             full["cpu_network_s"] = time.perf_counter() - t0
         net.close()
         fe16.close()
+        if world == 1:
+            # configs[2] in float32 (3xTF32 plans on hi/lo planes, 1e-5 of the oracle): 4 sweeps per step, float32 grid
+            net32 = DenseNetwork(synthetic_network_pack(0), batch=4, device=local, dtype="f32")
+            off4 = offsets[:5]
+            pts4 = dev_batches[0][:4 * POINTS_PER_SWEEP]
+
+            def step_f32():
+                fe.forward(pts4, off4, out=net32.grid)
+                net32.forward()
+
+            full["f32"] = {"sweeps_per_step": 4, "ms_per_step": timed(step_f32, 5), "flops_per_step": net32.flops}
+            net32.close()
+            del net32
+            torch.cuda.empty_cache()
+    config4 = None
+    if world == 1:
+        # configs[3]: one aggregated 1 M-point cloud near T-cap saturation, voxelize + VFE (sparse output)
+        cloud = torch.from_numpy(synth.saturated_cloud(1_000_000)).to(dev)
+        fe4 = Frontend(device=local, max_points=cloud.shape[0], max_sweeps=1)
+        fe4.set_weights(pack)
+        fe4.voxelize(cloud, [0, cloud.shape[0]])
+        _, v4, in4, _, _ = fe4.counts()
+        feat4 = fe4.vfe(n_voxels=v4)
+
+        def step_c4():
+            fe4.voxelize(cloud, [0, cloud.shape[0]])
+            fe4.vfe(out=feat4)
+
+        ms_c4 = timed(step_c4, n_k)
+        config4 = {"workload": "configs[3]: one 1 M-point aggregated cloud (10 sweeps, tight range law), voxelize + VFE, "
+                               "sparse output [V,64]", "points": int(cloud.shape[0]), "voxels": int(v4),
+                   "points_in_range": int(in4), "ms_per_cloud": ms_c4, "points_per_s": cloud.shape[0] / (ms_c4 * 1e-3),
+                   "algorithmic_bytes": int(12 * cloud.shape[0] + v4 * (64 * 4 + 16)),
+                   "note": "VFE rows, not bytes, set the time here (T-cap saturated voxels: 35 rows each)"}
+        fe4.close()
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
@@ -489,6 +524,7 @@ def run_native(args):
                                   "value": 1.0 / regions_cpu_s, "unit": "samples/s", "cores": 1, "kind": "port",
                                   "sample": "one sample: the oracle's numpy decode + vectorised greedy NMS (the "
                                             "reference's own Python loop takes ~16 s per sample)"}},
+            "config4_saturated_cloud": config4,
             "clocks": clocks,
         }
         if full is not None:
@@ -509,6 +545,12 @@ def run_native(args):
                              "bound": "tensor", "achieved": tfl, "peak": tpk, "unit": "TFLOP/s", "frac": tfl / tpk,
                              "peak_source": tsrc, "algorithmic_flops_per_step": full["flops_per_step"],
                              "ms_per_step": full["network_ms"], "traffic": None}}
+            if "f32" in full:
+                f32 = full["f32"]
+                line["full_inference"]["float32"] = {
+                    "dtype": "f32 (3xTF32 tensor-core plans on hi/lo float32 planes; 1e-5 of the float64 oracle)",
+                    "sweeps_per_step": f32["sweeps_per_step"], "ms_per_step": f32["ms_per_step"],
+                    "value": f32["sweeps_per_step"] / (f32["ms_per_step"] * 1e-3), "unit": "sweeps/s"}
         if world == 1 and not args.no_cpu_baseline:
             pts0 = base[0]
             t_vox, t_vfe = cpu_reference_time_per_sweep(pts0, 1.0, 200, pack)
