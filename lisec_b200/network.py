@@ -320,6 +320,27 @@ class DenseNetwork:
         self.combine_heads()
         return self.heads[:, 0, :, :, :2], self.heads[:, 0, :, :, 2:]
 
+    def forward_to_host(self, out_pinned: torch.Tensor) -> None:
+        """forward() + the device-to-host copy of the fused head tensor [B,1,nx/2,ny/2,16] (float32: prob = channels 0-1,
+        regress = 2-15) into pinned memory, with the copy on a side stream: it runs under the NEXT call's kernels, and
+        the next call's head write waits for it. The caller synchronises (self.host_copy_done.synchronize()) before it
+        reads out_pinned."""
+        if not out_pinned.is_pinned() or out_pinned.dtype != torch.float32 or out_pinned.numel() != self.heads.numel():
+            raise ValueError("out_pinned must be pinned float32 with %d elements" % self.heads.numel())
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self.host_copy_done = torch.cuda.Event()
+            self._heads_ready = torch.cuda.Event()
+        else:
+            main.wait_event(self.host_copy_done)  # the previous copy still reads self.heads
+        self.forward()
+        self._heads_ready.record(main)
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._heads_ready)
+            out_pinned.view(self.heads.shape).copy_(self.heads, non_blocking=True)
+            self.host_copy_done.record(self._copy_stream)
+
     def close(self) -> None:
         for L in self.layers:
             if L.plan:

@@ -325,3 +325,28 @@ def test_predictMain_writes_the_reference_files(tmp_path):
     assert np.array_equal(np.load(tmp_path / "sample2_regress.npy"), np.load(one / "sample0_regress.npy"))
     with pytest.raises(NotImplementedError):
         compat.train(samples, None, "x.h5")
+
+
+def test_forward_to_host_pipelines_the_copy_and_keeps_the_results():
+    """Three back-to-back calls with different grids into two pinned buffers: each buffer holds its own call's heads."""
+    from lisec_b200.network import DenseNetwork
+    from lisec_b200.weights import synthetic_network_pack
+
+    net = DenseNetwork(synthetic_network_pack(0), batch=2, nx=24, ny=40)
+    g = torch.Generator(device="cpu").manual_seed(21)
+    grids = [torch.rand(net.grid.shape, generator=g).to(torch.bfloat16).cuda() for _ in range(3)]
+    want = []
+    for x in grids:
+        net.forward(x)
+        torch.cuda.synchronize()
+        want.append(net.heads.cpu().clone())
+    bufs = [torch.empty(net.heads.shape, dtype=torch.float32).pin_memory() for _ in range(3)]
+    for x, b in zip(grids, bufs):
+        net.grid.copy_(x)
+        net.forward_to_host(b)
+    net.host_copy_done.synchronize()
+    for b, w in zip(bufs, want):
+        assert torch.equal(b, w)
+    with pytest.raises(ValueError):
+        net.forward_to_host(torch.empty(4))
+    net.close()
