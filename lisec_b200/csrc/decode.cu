@@ -15,8 +15,9 @@
 // CTAs takes one sample: a CTA keeps its eighth of the candidates (score, centre, bounding radius as float32, survivor
 // bits) in shared memory for the whole run; per round the CTAs publish their local best, meet at ONE cluster barrier,
 // read each other's slot through distributed shared memory and test their own survivors against the pick. The float64
-// box of a candidate is only fetched when the float32 bounding circles (with a safety margin) touch; the overlap itself
-// is the reference's: polygon corners as boxToShapely builds them (serialize_data.py:151-163), area of the intersection
+// box of a candidate is only fetched when the float32 bounding circles (with a safety margin) touch; a float32
+// separating-axis screen then settles the pairs that are apart, or (for overlapThresh = 0, the reference's call site)
+// overlapping, by more than its own error bound; what remains gets the overlap the reference computes: polygon corners as boxToShapely builds them (serialize_data.py:151-163), area of the intersection
 // polygon (Sutherland-Hodgman, standing where shapely's .intersection().area stood), z overlap with the reference's
 // full-height extents (z -/+ h, :146-147), iou = intersect / (vol1 + vol2 - intersect) > overlapThresh. Every float64
 // operation is an explicit round-to-nearest intrinsic so that no FMA contraction separates it from the CPU restatement.
@@ -245,6 +246,10 @@ __global__ void __cluster_dims__(kNmsCluster, 1, 1) __launch_bounds__(kNmsThread
     const float pcx = (float)s_pick[0], pcy = (float)s_pick[1];
     const float pr = (float)(0.5 * sqrt(s_pick[3] * s_pick[3] + s_pick[4] * s_pick[4])) * 1.000001f + 1e-6f;
     const double vol_p = dmul(dmul(s_pick[3], s_pick[4]), s_pick[5]);
+    const float plf = (float)s_pick[3], pwf = (float)s_pick[4];
+    float psin, pcos;
+    sincosf((float)s_pick[6], &psin, &pcos);
+    const bool pick_positive = s_pick[3] > 0.0 && s_pick[4] > 0.0 && s_pick[5] > 0.0;
     for (int k = tid; k < cnt; k += kNmsThreads) {
       if (!((s_alive[k >> 5] >> (k & 31)) & 1u)) continue;
       const double* b = bx + (size_t)(c0 + k) * 7;
@@ -262,20 +267,52 @@ __global__ void __cluster_dims__(kNmsCluster, 1, 1) __launch_bounds__(kNmsThread
       }
       if (!del) {
         const float dx = fx - pcx, dy = fy - pcy, rr = s_r[k] + pr;
-        if (dx * dx + dy * dy <= rr * rr * 1.0001f + 1e-4f) {  // circles touch: the exact test decides
-          double cand[7];
+        if (dx * dx + dy * dy <= rr * rr * 1.0001f + 1e-4f) {  // circles touch
+          // float32 separating-axis screen (boxToShapely's rectangle: half-width along (cos, -sin), half-length along
+          // (sin, cos)): a gap or an overlap deeper than the float32 error bound decides; the rest goes the exact way.
+          const float cl = (float)b[3], cw = (float)b[4], cyaw = (float)b[6];
+          float cs, cc;
+          sincosf(cyaw, &cs, &cc);
+          const float ax[4][2] = {{pcos, -psin}, {psin, pcos}, {cc, -cs}, {cs, cc}};
+          float worst = -INFINITY;
+          bool decided_apart = false, finite = true;
 #pragma unroll
-          for (int q = 0; q < 7; ++q) cand[q] = b[q];
-          Quad cq;
-          box_corners(cand, cq);
-          // calculateIntersection(lastBox, box): box1 = the pick (rpnToRegion.py:64, serialize_data.py:140-148)
-          const double area = quad_intersection_area(s_quad, cq);
-          const double bot = fmax(dsub(s_pick[2], s_pick[5]), dsub(cand[2], cand[5]));
-          const double top = fmin(dadd(s_pick[2], s_pick[5]), dadd(cand[2], cand[5]));
-          const double inter = dmul(dsub(top, bot), area);
-          const double uni = dsub(dadd(vol_p, dmul(dmul(cand[3], cand[4]), cand[5])), inter);
-          const double iou = __ddiv_rn(inter, uni);
-          del = iou > P.thresh;
+          for (int a = 0; a < 4; ++a) {
+            const float dist = fabsf(dx * ax[a][0] + dy * ax[a][1]);
+            const float rp = 0.5f * (pwf * fabsf(ax[0][0] * ax[a][0] + ax[0][1] * ax[a][1]) +
+                                     plf * fabsf(ax[1][0] * ax[a][0] + ax[1][1] * ax[a][1]));
+            const float rc = 0.5f * (cw * fabsf(ax[2][0] * ax[a][0] + ax[2][1] * ax[a][1]) +
+                                     cl * fabsf(ax[3][0] * ax[a][0] + ax[3][1] * ax[a][1]));
+            const float gap = dist - (rp + rc), t = 1e-3f + 8e-6f * (dist + rp + rc + fabsf(fx) + fabsf(fy));
+            finite = finite && gap == gap && t == t;
+            decided_apart = decided_apart || gap > t;
+            worst = fmaxf(worst, gap + t);  // < 0 on every axis: overlap deeper than the error bound
+          }
+          const bool deep = finite && worst < 0.f && !decided_apart;  // NaN anywhere: exact path
+          const double ch = b[5], cz = b[2];
+          if (decided_apart && finite) {
+            del = false;  // area 0 -> iou = 0, never above a threshold >= 0
+          } else if (deep && P.thresh == 0.0 && pick_positive && cl > 0.f && cw > 0.f && ch > 0.0) {
+            // area > 0 and all sizes > 0: intersect has the sign of the z overlap, union >= 0 (0 only for coincident
+            // boxes, where the reference's division yields +inf): iou > 0 exactly when the z extents overlap
+            const double bot = fmax(dsub(s_pick[2], s_pick[5]), dsub(cz, ch));
+            const double top = fmin(dadd(s_pick[2], s_pick[5]), dadd(cz, ch));
+            del = dsub(top, bot) > 0.0;
+          } else {
+            double cand[7];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) cand[q] = b[q];
+            Quad cq;
+            box_corners(cand, cq);
+            // calculateIntersection(lastBox, box): box1 = the pick (rpnToRegion.py:64, serialize_data.py:140-148)
+            const double area = quad_intersection_area(s_quad, cq);
+            const double bot = fmax(dsub(s_pick[2], s_pick[5]), dsub(cand[2], cand[5]));
+            const double top = fmin(dadd(s_pick[2], s_pick[5]), dadd(cand[2], cand[5]));
+            const double inter = dmul(dsub(top, bot), area);
+            const double uni = dsub(dadd(vol_p, dmul(dmul(cand[3], cand[4]), cand[5])), inter);
+            const double iou = __ddiv_rn(inter, uni);
+            del = iou > P.thresh;
+          }
         }
       }
       if (del) atomicAnd(&s_alive[k >> 5], ~(1u << (k & 31)));
