@@ -28,6 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SWEEPS_PER_GPU = 8
+FULL_SWEEPS = 32  # configs[2]: full inference on 32 sweeps (per GPU and step)
 POINTS_PER_SWEEP = 100_000
 GRID = (8, 200, 400)
 C3 = 64
@@ -370,13 +371,20 @@ def run_native(args):
         from lisec_b200.network import DenseNetwork
         from lisec_b200.weights import synthetic_network_pack
 
-        fe16 = Frontend(device=local, max_points=SWEEPS_PER_GPU * POINTS_PER_SWEEP, max_sweeps=SWEEPS_PER_GPU,
-                        grid_dtype="bf16")
+        # configs[2] names 32 sweeps: one step = 32 sweeps per GPU (four of the 8-sweep batches behind one another)
+        FS = FULL_SWEEPS
+        fe16 = Frontend(device=local, max_points=FS * POINTS_PER_SWEEP, max_sweeps=FS, grid_dtype="bf16")
         fe16.set_weights(pack)
-        net = DenseNetwork(synthetic_network_pack(0), batch=SWEEPS_PER_GPU, device=local)
+        net = DenseNetwork(synthetic_network_pack(0), batch=FS, device=local)
+        reps = FS // SWEEPS_PER_GPU
+        offsets_f = np.arange(FS + 1, dtype=np.int64) * POINTS_PER_SWEEP
+        n_fb = 4
+        host_full = [torch.cat([host_batches[(reps * b + j) % N_BATCHES] for j in range(reps)]).pin_memory()
+                     for b in range(n_fb)]
+        dev_full = [t.cuda() for t in host_full]
 
         def step_full(i):
-            fe16.forward(dev_batches[i % N_BATCHES], offsets, out=net.grid)
+            fe16.forward(dev_full[i % n_fb], offsets_f, out=net.grid)
             net.forward()
 
         for i in range(args.warmup):
@@ -392,13 +400,13 @@ def run_native(args):
         ms_net = timed(lambda: net.forward(), n_k)
 
         # the same through host buffers: pinned points in, prob / regress (float32) back to pinned host memory
-        out_host = [torch.empty((SWEEPS_PER_GPU, 1, GRID[1] // 2, GRID[2] // 2, 16), dtype=torch.float32).pin_memory()
+        out_host = [torch.empty((FS, 1, GRID[1] // 2, GRID[2] // 2, 16), dtype=torch.float32).pin_memory()
                     for _ in range(2)]
 
         def step_full_e2e(i):
             # points in through the library's copy stream, heads out on the network's: both copies run under the
             # neighbouring steps' kernels; the timed region ends after the last copy (host_copy_done)
-            fe16.forward_host(host_batches[i % N_BATCHES], offsets, out=net.grid)
+            fe16.forward_host(host_full[i % n_fb], offsets_f, out=net.grid)
             net.forward_to_host(out_host[i % 2])
 
         for i in range(min(args.warmup, 3)):
@@ -420,7 +428,7 @@ def run_native(args):
             # CPU side of the dense network: the oracle's torch-CPU float32 forward on one sweep's grid, all host threads
             from oracle import network_oracle as NO
 
-            fe16.forward(dev_batches[0], offsets, out=net.grid)
+            fe16.forward(dev_full[0], offsets_f, out=net.grid)
             g1cpu = net.grid[:1].float().cpu().numpy()
             torch.set_num_threads(os.cpu_count() or 1)
             t0 = time.perf_counter()
@@ -535,12 +543,13 @@ def run_native(args):
             tfl = full["flops_per_step"] / (full["network_ms"] * 1e-3) / 1e12
             line["full_inference"] = {
                 "metric": "lidar sweeps/sec (voxelize+VFE+Conv3D+RPN+heads, full fwd)", "dtype": "bf16",
-                "workload": "configs[2] shape at the bench batch: 8 sweeps per GPU per step, outputs (8,100,200,2) + "
-                            "(8,100,200,14) float32",
-                "value": SWEEPS_PER_GPU * world / (full["ms_per_step"] * 1e-3), "unit": "sweeps/s",
+                "workload": "configs[2]: full VoxelNet inference on %d sweeps x 100k points per GPU per step, outputs "
+                            "(%d,100,200,2) + (%d,100,200,14) float32" % (FULL_SWEEPS, FULL_SWEEPS, FULL_SWEEPS),
+                "sweeps_per_step_per_gpu": FULL_SWEEPS,
+                "value": FULL_SWEEPS * world / (full["ms_per_step"] * 1e-3), "unit": "sweeps/s",
                 "ms_per_step": full["ms_per_step"], "gpu_launches_per_step": full["launches_per_step"],
-                "e2e": {"value": SWEEPS_PER_GPU * world / (full["ms_e2e"] * 1e-3), "unit": "sweeps/s",
-                        "ms_per_step": full["ms_e2e"], "h2d_bytes_per_step": points_bytes,
+                "e2e": {"value": FULL_SWEEPS * world / (full["ms_e2e"] * 1e-3), "unit": "sweeps/s",
+                        "ms_per_step": full["ms_e2e"], "h2d_bytes_per_step": FULL_SWEEPS * POINTS_PER_SWEEP * 12,
                         "d2h_bytes_per_step": full["d2h"]},
                 "roofline": {"kernel": "conv_halo_kernel / conv_igemm_kernel x %d + heads_combine (middle Conv3D + RPN + "
                                        "heads; the transposed convolutions are folded into the head kernels), timed alone"

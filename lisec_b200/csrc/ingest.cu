@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(kIngestThreads)
   if (tid < here) {
     const long long p = base + tid;
     int s = 0;
-    while (s + 1 < seg.n && p >= seg.off[s + 1]) ++s;
+    while (s + 1 < seg.n && base >= seg.off[s + 1]) ++s;  // uniform over the block: the segment of its first point
+    while (s + 1 < seg.n && p >= seg.off[s + 1]) ++s;     // a block rarely straddles a file boundary
     const double x = (double)s_in[tid * rec_floats], y = (double)s_in[tid * rec_floats + 1],
                  z = (double)s_in[tid * rec_floats + 2];
 #pragma unroll
