@@ -348,6 +348,35 @@ def run_native(args):
         DO.non_max_suppression_vec(*DO.decode_boxes(*heads_np[0]), 0., 20)
         regions_cpu_s = time.perf_counter() - t0
 
+    # configs[4], the pieces that exist: the step's one collective (all-reduce of the 6 491 024-element float32 gradient,
+    # NCCL) and the Keras SGD-Nesterov update over the flat parameter buffer. The backward pass is not built.
+    from lisec_b200.train import FlatParameters, SgdNesterov, allreduce_gradients
+    from lisec_b200.weights import synthetic_model_pack
+
+    # four copies of the buffers rotate (4 x 78 MB > the 126 MB L2): a real step's backward pass leaves none of them cached
+    mpack = synthetic_model_pack(0)
+    opts = [SgdNesterov(FlatParameters(mpack, device=dev)) for _ in range(4)]
+    for o in opts:
+        o.params.grad.normal_(0.0, 1e-3)
+    fp = opts[0].params
+    turn = [0]
+
+    def update_only():
+        turn[0] += 1
+        opts[turn[0] % 4].step(world_size=world)
+
+    def comm_and_update():
+        turn[0] += 1
+        o = opts[turn[0] % 4]
+        for w in allreduce_gradients(o.params.grad):
+            w.wait()
+        o.step(world_size=world)
+
+    ms_update = timed(update_only, 20)
+    barrier()
+    ms_comm_update = max_over_ranks(timed(comm_and_update, 20)) if world > 1 else ms_update
+    update_bytes = fp.numel_padded * 20
+
     # end to end through the host-buffer entry point
     n_w = min(args.warmup, 3)
     for i in range(n_w):
@@ -535,6 +564,14 @@ def run_native(args):
                                   "value": 1.0 / regions_cpu_s, "unit": "samples/s", "cores": 1, "kind": "port",
                                   "sample": "one sample: the oracle's numpy decode + vectorised greedy NMS (the "
                                             "reference's own Python loop takes ~16 s per sample)"}},
+            "train_step_pieces": {"built": "gradient all-reduce (NCCL, sum) + sgd_nesterov_kernel over the flat float32 "
+                                           "parameter buffer + the mse loss head; NOT the backward pass",
+                                  "parameters": fp.numel, "gradient_bytes": fp.numel * 4,
+                                  "sgd_update_ms": ms_update, "allreduce_plus_update_ms": ms_comm_update,
+                                  "roofline": {"kernel": "sgd_nesterov_kernel", "bound": "hbm",
+                                               "algorithmic_bytes_per_launch": update_bytes,
+                                               "achieved": update_bytes / (ms_update * 1e-3) / 1e9, "peak": hbm_peak,
+                                               "unit": "GB/s", "frac": update_bytes / (ms_update * 1e-3) / 1e9 / hbm_peak}},
             "config4_saturated_cloud": config4,
             "clocks": clocks,
         }

@@ -326,6 +326,25 @@ int32_t lisec_nms_rotated(const lisec_nms_desc* desc, const double* boxes, const
                           int32_t* picks, int32_t* n_picks, double* out_boxes, float* out_scores, void* stream);
 const char* lisec_decode_last_error(void);
 
+/* ---- training step: the pieces that exist (BASELINE configs[4]) ---------------------------------------
+ *
+ * model_training.train() (model_training.py:260-302) compiles the model with
+ *     optimizers.SGD(lr=0.01, decay=1e-6, momentum=0.9, nesterov=True), loss=['mse', 'mse']        (:295-296)
+ * Built: the loss head and the optimizer update over the flat parameter buffer, around the one collective of the step
+ * (NCCL all-reduce of the 6 491 024-element float32 gradient, lisec_b200/train.py). NOT built: the backward pass. */
+
+/* [async] One Keras SGD update (optimizer_v2 / resource_apply_keras_momentum) on n float32 parameters:
+ *   g = grad * grad_scale;  step = lr_t * g;  accum = accum * momentum - step;
+ *   var += nesterov ? accum * momentum - step : accum          with lr_t = lr / (1 + decay * iterations) from the host.
+ * grad_scale = 1 / world_size after a summing all-reduce. Device pointers, 16-byte aligned; float32 operation by
+ * operation (no FMA contraction): bit-identical to the numpy float32 restatement in oracle/train_oracle.py. */
+int32_t lisec_sgd_nesterov(float* var, float* accum, const float* grad, int64_t n, float grad_scale, float lr_t,
+                           float momentum, int32_t nesterov, void* stream);
+/* [async] 'mse' on one output tensor: *sum_sq += sum (y - target)^2 (double, device; the loss is sum_sq / n) and, when dy
+ * is not NULL, dy = 2 (y - target) / n — d loss / d y, where the backward pass starts. */
+int32_t lisec_mse_loss_grad(const float* y, const float* target, int64_t n, float* dy, double* sum_sq, void* stream);
+const char* lisec_train_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

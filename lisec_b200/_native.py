@@ -135,6 +135,9 @@ SIGNATURES = {
                                      C.c_int32, _VP, _VP, _VP]),
     "lisec_nms_rotated": (C.c_int32, [C.POINTER(lisec_nms_desc), _VP, _VP, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, _VP]),
     "lisec_decode_last_error": (C.c_char_p, []),
+    "lisec_sgd_nesterov": (C.c_int32, [_VP, _VP, _VP, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int32, _VP]),
+    "lisec_mse_loss_grad": (C.c_int32, [_VP, _VP, C.c_int64, _VP, _VP, _VP]),
+    "lisec_train_last_error": (C.c_char_p, []),
 }
 
 _lib = None

@@ -256,9 +256,10 @@ def predictMain(samples, outPath, level5Data, model, combine_lidar_data=None, dt
 
 
 def train(samples, level5Data, save_path):
-    """model_training.train (model_training.py:260-302). NOT BUILT: the training step (backward through the VFE stack
-    and the dense network, training-mode BatchNormalization, SGD-Nesterov, NCCL gradient all-reduce; BASELINE
-    configs[4]) is the next row of this library; inference is complete."""
+    """model_training.train (model_training.py:260-302). NOT BUILT: the backward pass (through the VFE stack and the
+    dense network, with training-mode BatchNormalization). What the step needs around it exists and is tested —
+    lisec_b200/train.py: flat parameter buffers, the NCCL gradient all-reduce, the Keras SGD-Nesterov update kernel, the
+    'mse' loss head; oracle/train_oracle.py restates the whole step. Inference is complete."""
     raise NotImplementedError("lisec_b200 implements the inference path (Predict.predictMain); train() is not built yet")
 
 

@@ -205,6 +205,10 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
     return fail(h, LISEC_ERR_CUDA, "device %d has compute capability %d.x; this library is built for sm_100a only",
                 c.device, major);
   LISEC_CUDA(h, cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, c.device));
+  if (const char* e = getenv("LISEC_VFE_CTAS")) {  // experiment knob: persistent CTAs of the VFE kernel (default: one per SM)
+    const int v = atoi(e);
+    if (v > 0 && v < h->sm_count) h->sm_count = v;
+  }
 
   h->rows_per_tile = vfe_rows_per_tile(g.T);
   h->ncells_cap = cells * c.max_sweeps;

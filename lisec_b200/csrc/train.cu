@@ -1,0 +1,134 @@
+// Training-step pieces that exist so far: the optimizer update and the loss head — NOT the
+// backward pass (lisec_b200/compat.py: train() says so). Reference model_training.py:295-299:
+//     sgd = optimizers.SGD(lr=0.01, decay=1e-6, momentum=0.9, nesterov=True);  model.compile(optimizer=sgd, loss=['mse', 'mse'])
+//
+// sgd_nesterov_kernel: one Keras SGD update (optimizer_v2, resource_apply_keras_momentum) over the FLAT parameter buffer
+// (6 491 024 float32 for this model) after the gradient all-reduce:
+//     g = grad * grad_scale          (grad_scale = 1 / world_size: the all-reduce sums)
+//     step = lr_t * g;  accum = accum * momentum - step;  var = var + (accum * momentum - step)   [nesterov]
+// evaluated operation by operation with round-to-nearest float32 intrinsics (no FMA contraction), i.e. bit for bit what
+// oracle/train_oracle.py: sgd_nesterov_update computes in numpy float32. HBM-bound: 12 B read + 8 B written per parameter
+// (130 MB per step: ~20 us at the measured copy bandwidth); 16-byte accesses, grid-stride over 148 x 8 CTAs.
+//
+// mse_loss_grad_kernel: loss=['mse','mse'] on one output: sum of (y - t)^2 into a double accumulator (scaled by 1/n on the
+// host side of the ABI) and d loss / d y = 2 (y - t) / n, the tensor the backward pass will start from.
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace lisec {
+
+namespace {
+
+__device__ __forceinline__ float sgd_one(float& var, float& acc, float g, float scale, float lr_t, float mom, int nesterov) {
+  const float step = __fmul_rn(lr_t, __fmul_rn(g, scale));
+  acc = __fsub_rn(__fmul_rn(acc, mom), step);
+  var = nesterov ? __fadd_rn(var, __fsub_rn(__fmul_rn(acc, mom), step)) : __fadd_rn(var, acc);
+  return var;
+}
+
+__global__ void __launch_bounds__(256)
+    sgd_nesterov_kernel(float* __restrict__ var, float* __restrict__ accum, const float* __restrict__ grad, long long n,
+                        float grad_scale, float lr_t, float momentum, int nesterov) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = reinterpret_cast<float4*>(var)[i];
+    float4 a = reinterpret_cast<float4*>(accum)[i];
+    const float4 g = __ldcs(reinterpret_cast<const float4*>(grad) + i);
+    sgd_one(v.x, a.x, g.x, grad_scale, lr_t, momentum, nesterov);
+    sgd_one(v.y, a.y, g.y, grad_scale, lr_t, momentum, nesterov);
+    sgd_one(v.z, a.z, g.z, grad_scale, lr_t, momentum, nesterov);
+    sgd_one(v.w, a.w, g.w, grad_scale, lr_t, momentum, nesterov);
+    reinterpret_cast<float4*>(var)[i] = v;
+    reinterpret_cast<float4*>(accum)[i] = a;
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = var[i], a = accum[i];
+    sgd_one(v, a, grad[i], grad_scale, lr_t, momentum, nesterov);
+    var[i] = v;
+    accum[i] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    mse_loss_grad_kernel(const float* __restrict__ y, const float* __restrict__ t, long long n, float* __restrict__ dy,
+                         double* __restrict__ sum_sq) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const float two_over_n = (float)(2.0 / (double)n);
+  double local = 0.0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float d = __fsub_rn(y[i], t[i]);
+    local += (double)d * (double)d;
+    if (dy) dy[i] = __fmul_rn(d, two_over_n);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  __shared__ double s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < 8; ++w) tot += s[w];
+    atomicAdd(sum_sq, tot);
+  }
+}
+
+thread_local char g_train_error[256] = "";
+
+int32_t train_fail(int32_t code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_train_error, sizeof(g_train_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+}  // namespace
+
+}  // namespace lisec
+
+using namespace lisec;
+
+extern "C" {
+
+const char* lisec_train_last_error(void) { return g_train_error; }
+
+int32_t lisec_sgd_nesterov(float* var, float* accum, const float* grad, int64_t n, float grad_scale, float lr_t,
+                           float momentum, int32_t nesterov, void* stream) {
+  if (n < 0) return train_fail(LISEC_ERR_BAD_ARG, "negative size");
+  if (n == 0) return LISEC_OK;
+  if (!var || !accum || !grad) return train_fail(LISEC_ERR_BAD_ARG, "null argument");
+  if (((uintptr_t)var | (uintptr_t)accum | (uintptr_t)grad) & 15)
+    return train_fail(LISEC_ERR_BAD_ARG, "buffers must be 16-byte aligned");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long blocks = ((n >> 2) + 255) / 256;
+  if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+  if (blocks < 1) blocks = 1;
+  cudaError_t e = launch_pdl(sgd_nesterov_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                             var, accum, grad, (long long)n, grad_scale, lr_t, momentum, (int)nesterov);
+  if (e != cudaSuccess) return train_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
+  return LISEC_OK;
+}
+
+int32_t lisec_mse_loss_grad(const float* y, const float* target, int64_t n, float* dy, double* sum_sq, void* stream) {
+  if (n <= 0 || !y || !target || !sum_sq) return train_fail(LISEC_ERR_BAD_ARG, "null argument or empty tensor");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long blocks = (n + 255) / 256;
+  if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+  cudaError_t e = launch_pdl(mse_loss_grad_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                             y, target, (long long)n, dy, sum_sq);
+  if (e != cudaSuccess) return train_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
+  return LISEC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+"""The pieces of model_training.train()'s step (model_training.py:295-299) that exist so far: flat parameter / gradient /
+accumulator buffers in the model's Keras weight order, the step's ONE collective (all-reduce of the 6 491 024-element
+float32 gradient: NCCL over NVLink on the GPUs, any torch.distributed backend for the host logic) and the Keras
+SGD-Nesterov update as one kernel over the flat buffer (lisec_sgd_nesterov), plus the 'mse' loss head
+(lisec_mse_loss_grad). The backward pass is NOT built: compat.train() still raises.
+
+Sweeps shard over ranks (lisec_b200/sharding.py), every rank holds the full model, gradients are summed across ranks and
+the 1 / world_size lands inside the update kernel (grad_scale) — one pass over the flat buffers per step."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+def trainable_names(pack: Dict[str, np.ndarray]) -> List[str]:
+    """Everything but BatchNormalization's moving statistics, in the pack's (= Keras creation) order."""
+    return [k for k in pack if "moving_" not in k]
+
+
+class FlatParameters:
+    """var / accum / grad as three flat float32 tensors, with per-weight views under the Keras names. Offsets are padded
+    to 4 elements so every weight starts 16-byte aligned."""
+
+    def __init__(self, pack: Dict[str, np.ndarray], device="cuda"):
+        self.names = trainable_names(pack)
+        self.shapes = {k: tuple(np.shape(pack[k])) for k in self.names}
+        self.offsets, off = {}, 0
+        for k in self.names:
+            self.offsets[k] = off
+            off += (int(np.prod(self.shapes[k])) + 3) // 4 * 4
+        self.numel_padded = off
+        self.numel = sum(int(np.prod(s)) for s in self.shapes.values())
+        self.device = torch.device(device)
+        self.var = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.accum = torch.zeros_like(self.var)
+        self.grad = torch.zeros_like(self.var)
+        for k in self.names:
+            self.view(self.var, k).copy_(torch.from_numpy(np.ascontiguousarray(pack[k], dtype=np.float32)))
+
+    def view(self, flat: torch.Tensor, name: str) -> torch.Tensor:
+        o, s = self.offsets[name], self.shapes[name]
+        return flat[o:o + int(np.prod(s))].view(s)
+
+    def to_pack(self) -> Dict[str, np.ndarray]:
+        return {k: self.view(self.var, k).cpu().numpy() for k in self.names}
+
+
+def allreduce_gradients(flat_grad: torch.Tensor, group=None, bucket_elems: int = 0):
+    """The step's collective: SUM the flat gradient over the ranks (the 1 / world_size is applied by the update kernel).
+    bucket_elems > 0 splits it into asynchronous chunks (what a backward pass would overlap with); returns the works."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return []
+    n = flat_grad.numel()
+    step = n if bucket_elems <= 0 else bucket_elems
+    return [dist.all_reduce(flat_grad[a:min(a + step, n)], op=dist.ReduceOp.SUM, group=group, async_op=True)
+            for a in range(0, n, step)]
+
+
+class SgdNesterov:
+    """optimizers.SGD(lr=0.01, decay=1e-6, momentum=0.9, nesterov=True) (model_training.py:295) on FlatParameters."""
+
+    def __init__(self, params: FlatParameters, lr=0.01, decay=1e-6, momentum=0.9, nesterov=True):
+        if params.device.type != "cuda":
+            raise RuntimeError("lisec_b200 has no CPU fallback: the update runs in lisec_sgd_nesterov on a CUDA device")
+        self._lib = N.load()
+        self.params, self.lr, self.decay, self.momentum, self.nesterov = params, lr, decay, momentum, nesterov
+        self.iterations = 0
+
+    def step(self, world_size: int = 1) -> None:
+        p = self.params
+        lr_t = np.float32(self.lr / (1.0 + self.decay * self.iterations))
+        with torch.cuda.device(p.device):
+            st = self._lib.lisec_sgd_nesterov(
+                C.c_void_p(p.var.data_ptr()), C.c_void_p(p.accum.data_ptr()), C.c_void_p(p.grad.data_ptr()),
+                p.numel_padded, C.c_float(1.0 / world_size), C.c_float(lr_t), C.c_float(self.momentum),
+                1 if self.nesterov else 0, C.c_void_p(torch.cuda.current_stream(p.device).cuda_stream))
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_train_last_error().decode("utf-8", "replace"))
+        self.iterations += 1
+
+
+def mse_loss_grad(y: torch.Tensor, target: torch.Tensor, want_grad: bool = True):
+    """One 'mse' term of loss=['mse','mse'] (:296): returns (loss as a 0-d float64 device tensor, d loss / d y or None)."""
+    if y.dtype != torch.float32 or target.dtype != torch.float32 or y.shape != target.shape or not y.is_cuda:
+        raise ValueError("y and target: cuda float32 tensors of one shape")
+    lib = N.load()
+    y, target = y.contiguous(), target.contiguous()
+    dy = torch.empty_like(y) if want_grad else None
+    acc = torch.zeros((), dtype=torch.float64, device=y.device)
+    with torch.cuda.device(y.device):
+        st = lib.lisec_mse_loss_grad(C.c_void_p(y.data_ptr()), C.c_void_p(target.data_ptr()), y.numel(),
+                                     C.c_void_p(dy.data_ptr() if want_grad else 0), C.c_void_p(acc.data_ptr()),
+                                     C.c_void_p(torch.cuda.current_stream(y.device).cuda_stream))
+    if st != N.LISEC_OK:
+        raise N.LisecError(st, lib.lisec_train_last_error().decode("utf-8", "replace"))
+    return acc / y.numel(), dy

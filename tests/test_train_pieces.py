@@ -1,0 +1,105 @@
+"""Training-step pieces (lisec_b200/train.py): flat buffers and the gradient all-reduce on CPU (gloo, world_size 2); the
+SGD-Nesterov and MSE kernels on the GPU against oracle/train_oracle.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from lisec_b200.weights import synthetic_model_pack
+from oracle import train_oracle as TO
+
+
+def test_flat_parameters_layout():
+    from lisec_b200.train import FlatParameters, trainable_names
+
+    pack = synthetic_model_pack(0)
+    fp = FlatParameters(pack, device="cpu")
+    assert fp.numel == 6_491_024 and fp.numel_padded % 4 == 0 and fp.numel_padded >= fp.numel
+    assert fp.names == trainable_names(pack) and all("moving_" not in k for k in fp.names)
+    for k in ("dense/kernel", "conv3d_1/bias", "RegressionLayer/kernel"):
+        assert fp.offsets[k] % 4 == 0
+        assert np.array_equal(fp.view(fp.var, k).numpy(), pack[k].astype(np.float32))
+    back = fp.to_pack()
+    assert all(np.array_equal(back[k], pack[k].astype(np.float32)) for k in fp.names)
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    from lisec_b200.train import allreduce_gradients
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    for w in allreduce_gradients(g, bucket_elems=300):  # 4 asynchronous buckets
+        w.wait()
+    # the update's grad_scale = 1 / world turns the sum into the mean
+    var, acc = TO.sgd_nesterov_update(np.zeros(1000, np.float32), np.zeros(1000, np.float32), g.numpy(), 0,
+                                      grad_scale=1.0 / world)
+    if rank == 0:
+        torch.save({"sum": g, "var": torch.from_numpy(var)}, out)
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world_size_2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_worker, args=(2, 29631, out), nprocs=2, join=True)
+    res = torch.load(out)
+    base = torch.arange(1000, dtype=torch.float32)
+    assert torch.equal(res["sum"], base * 3)  # ranks contributed 1x and 2x
+    mean = (base * 3).numpy() * np.float32(0.5)
+    assert np.array_equal(res["var"].numpy(), (np.float32(0) + (-(np.float32(0.01) * mean) * np.float32(0.9) - np.float32(0.01) * mean)))
+
+
+@pytest.mark.gpu
+def test_gpu_sgd_nesterov_bit_exact_against_the_oracle():
+    from lisec_b200.train import FlatParameters, SgdNesterov
+
+    pack = synthetic_model_pack(1)
+    fp = FlatParameters(pack)
+    opt = SgdNesterov(fp)
+    rng = np.random.default_rng(0)
+    var = fp.var.cpu().numpy().copy()
+    acc = np.zeros_like(var)
+    for it, world in enumerate((1, 8, 2)):
+        g = (rng.normal(size=fp.numel_padded) * 10 ** rng.uniform(-6, 2, size=fp.numel_padded)).astype(np.float32)
+        fp.grad.copy_(torch.from_numpy(g))
+        opt.step(world_size=world)
+        var, acc = TO.sgd_nesterov_update(var, acc, g, it, grad_scale=1.0 / world)
+        assert fp.var.cpu().numpy().tobytes() == var.tobytes() and fp.accum.cpu().numpy().tobytes() == acc.tobytes()
+    assert opt.iterations == 3
+    # plain momentum, odd length (scalar tail)
+    import ctypes as C
+
+    from lisec_b200 import _native as N
+
+    lib = N.load()
+    n = 1027
+    v, a, g = (torch.from_numpy(rng.normal(size=n).astype(np.float32)).cuda() for _ in range(3))
+    wv, wa = TO.sgd_nesterov_update(v.cpu().numpy(), a.cpu().numpy(), g.cpu().numpy(), 5, nesterov=False)
+    st = lib.lisec_sgd_nesterov(v.data_ptr(), a.data_ptr(), g.data_ptr(), n, C.c_float(1.0),
+                                C.c_float(np.float32(0.01 / (1 + 1e-6 * 5))), C.c_float(0.9), 0, None)
+    torch.cuda.synchronize()
+    assert st == 0 and v.cpu().numpy().tobytes() == wv.tobytes() and a.cpu().numpy().tobytes() == wa.tobytes()
+    assert lib.lisec_sgd_nesterov(v.data_ptr() + 4, a.data_ptr(), g.data_ptr(), 8, C.c_float(1.0), C.c_float(0.01),
+                                  C.c_float(0.9), 1, None) == -1  # LISEC_ERR_BAD_ARG
+
+
+@pytest.mark.gpu
+def test_gpu_mse_loss_and_gradient():
+    from lisec_b200.train import mse_loss_grad
+
+    rng = np.random.default_rng(1)
+    for shape in ((2, 100, 200, 14), (1, 100, 200, 2), (3, 7)):
+        y = rng.normal(size=shape).astype(np.float32)
+        t = rng.integers(0, 3, size=shape).astype(np.float32)
+        loss, dy = mse_loss_grad(torch.from_numpy(y).cuda(), torch.from_numpy(t).cuda())
+        want = ((y - t).astype(np.float64) ** 2).mean()  # the difference is float32's, squares and sum are float64's
+        assert abs(float(loss) - want) <= 1e-12 * max(1.0, want)
+        want_dy = (y - t) * np.float32(2.0 / y.size)
+        assert dy.cpu().numpy().tobytes() == want_dy.astype(np.float32).tobytes()
+    loss, dy = mse_loss_grad(torch.from_numpy(y).cuda(), torch.from_numpy(t).cuda(), want_grad=False)
+    assert dy is None
