@@ -276,6 +276,12 @@ def createModel(nx=K.nx, ny=K.ny, nz=K.nz, maxPoints=K.maxPoints, weights: Optio
 
 
 def load_model(path: str, custom_objects: Optional[dict] = None, nx=K.nx, ny=K.ny, nz=K.nz, maxPoints=K.maxPoints):
-    """Predict.py:51-52 / model_training.py:337-338. Reads a .npz weight pack with Keras layer names (h5py is not
-    available in this image; see lisec_b200/weights.py)."""
+    """Predict.py:51-52 / model_training.py:337-338. `path`: the Keras .h5 file model.save() wrote (read by
+    lisec_b200/h5weights.py — a reader of the HDF5 format itself, h5py is not in this image) or a .npz weight pack with
+    the same Keras weight names (lisec_b200/weights.py). custom_objects is accepted and ignored: RepeatLayer and
+    MaxPoolingVFELayer are part of the fused VFE kernel."""
+    if str(path).lower().endswith((".h5", ".hdf5", ".keras.h5")):
+        from .h5weights import read_keras_weights
+
+        return VoxelNetFrontEnd(nx, ny, nz, maxPoints, read_keras_weights(path))
     return VoxelNetFrontEnd(nx, ny, nz, maxPoints, load_npz(path))
