@@ -226,25 +226,27 @@ class VoxelNetFrontEnd:
         return [prob.contiguous().cpu().numpy(), reg.contiguous().cpu().numpy()]
 
 
-def predictMain(samples, outPath, level5Data, model, combine_lidar_data=None, dtype: str = "bf16", batch: int = 8):
+def predictMain(samples, outPath, level5Data, model, combine_lidar_data=None, dtype: str = "bf16", batch: int = 8,
+                dataDir: Optional[str] = None):
     """Predict.predictMain(samples, outPath, level5Data, model) (Predict.py:9-40): for every sample write
     `sample{i}_label.npy` (prob, (1, nx/2, ny/2, 2)) and `sample{i}_regress.npy` ((1, nx/2, ny/2, 14)) into outPath.
 
     The reference handles one sample per model.predict call; here up to `batch` samples share one pass (sweeps are
-    independent, the files are the same). Dataset I/O stays the reference's: `combine_lidar_data(sample, dataDir,
-    level5Data)` (model_training.py:73-98, needs lyft_dataset_sdk + pyquaternion) is passed in by the caller; it must
-    return the (n, 3) float array the reference's returns. dataDir is the caller's business (the reference hard-codes a
-    Windows path at Predict.py:12): a loader that needs it closes over it."""
+    independent, the files are the same). The points come from `combine_lidar_data(sample, dataDir, level5Data)`
+    (model_training.py:73-98): by default lisec_b200.ingest's GPU version (the sensor files under `dataDir`, which the
+    reference hard-codes at Predict.py:12 / Constants.py:4; `level5Data` only needs the SDK's `.get(table, token)`), or
+    any callable of that signature returning the (n, 3) float array."""
     import os
 
     if combine_lidar_data is None:
-        raise ValueError("pass the reference's combine_lidar_data (model_training.py:73) or an equivalent loader: "
-                         "dataset I/O is outside this library")
+        if dataDir is None:
+            raise ValueError("dataDir: the Lyft dataset directory (the reference's Constants.lyft_data_dir)")
+        from .ingest import combine_lidar_data
     cfg = (K.voxelx, K.voxely, K.voxelz, K.maxPoints, K.nx // 2, K.ny // 2, K.nz)
     for i0 in range(0, len(samples), batch):
         dense = []
         for sample in samples[i0:i0 + batch]:
-            pts = combine_lidar_data(sample, None, level5Data)
+            pts = combine_lidar_data(sample, dataDir, level5Data)
             t = VFE_preprocessing(pts, *cfg)                        # Predict.py:21-28
             t = sparse.reshape(t, (1,) + tuple(t.shape))            # Predict.py:29
             dense.append(sparse.to_dense(t, default_value=0., validate_indices=False))  # Predict.py:30
