@@ -8,7 +8,11 @@
 // address; slabs are 1 KB-aligned). One MMA has K = 8: k-step j inside a slab is the same descriptor advanced by 32
 // bytes. Measured with tools/umma_probe.cu (M=64, N=256, K=64): exact placement, 3xTF32 error 1.1e-6 of rms.
 // An MN-major tf32 operand needs the separate SWIZZLE_128B_BASE32B layout (plain SWIZZLE_128B MN-major yields zeros for
-// 32-bit types; probe variants 0/1, whose helpers live in the probe) — not used here.
+// 32-bit types; probe variants 0/1, whose helpers live in the probe) — not used here. For bf16 the plain MN-major
+// SWIZZLE_128B layout works as the canonical form says (tools/umma_mn_probe.cu, exact on B200): a TMA box [k rows][64
+// channels] IS an MN-major operand — instruction descriptor bits 15/16 (a_major/b_major) = 1, stride byte offset 1024
+// (8 k-rows), leading byte offset = distance between 64-channel boxes, one K = 16 step = +2048 bytes. This is what the
+// weight-gradient GEMM of the training step will read.
 #pragma once
 
 #include <cuda_runtime.h>
