@@ -345,6 +345,24 @@ int32_t lisec_sgd_nesterov(float* var, float* accum, const float* grad, int64_t 
 int32_t lisec_mse_loss_grad(const float* y, const float* target, int64_t n, float* dy, double* sum_sq, void* stream);
 const char* lisec_train_last_error(void);
 
+/* Weight gradient of one convolution layer on the tensor cores (lisec_b200/csrc/wgrad.cu) — the first backward kernel:
+ *   dw[tap][co][ci] = sum over output positions p of dy[p][co] * x[p * stride + tap - pad][ci]
+ * `desc` describes the FORWARD convolution (geometry fields, tile_w x tile_h = 128 positions; first version: bf16,
+ * stride_hw = 1, in_c and out_c multiples of 64 and <= 256, n_tiles = shuffle = 1). Device pointers:
+ *   x   bf16 [batch, in_d, in_h, in_w, in_c]      the layer's input
+ *   dy  bf16 [batch, out_d, out_h, out_w, out_c]  the gradient with respect to the convolution's output
+ *   dw  float32 [kd*kh*kw][out_c][in_c]           the layout the forward plans read their weights in
+ *   workspace  float32, lisec_conv_wgrad_workspace_bytes(desc) bytes (per-CTA partial sums, added in a fixed order:
+ *              the result is deterministic)
+ * [async] lisec_conv_wgrad_plan_run launches two kernels on `stream`. */
+typedef struct lisec_wgrad_plan lisec_wgrad_plan;
+int64_t lisec_conv_wgrad_workspace_bytes(const lisec_conv_desc* desc);
+int32_t lisec_conv_wgrad_plan_create(const lisec_conv_desc* desc, const void* x, const void* dy, float* workspace,
+                                     float* dw, lisec_wgrad_plan** plan);
+int32_t lisec_conv_wgrad_plan_run(lisec_wgrad_plan* plan, void* stream);
+void lisec_conv_wgrad_plan_destroy(lisec_wgrad_plan* plan);
+const char* lisec_wgrad_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

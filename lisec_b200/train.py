@@ -101,3 +101,50 @@ def mse_loss_grad(y: torch.Tensor, target: torch.Tensor, want_grad: bool = True)
     if st != N.LISEC_OK:
         raise N.LisecError(st, lib.lisec_train_last_error().decode("utf-8", "replace"))
     return acc / y.numel(), dy
+
+
+class ConvWgrad:
+    """dW of one convolution layer (lisec_conv_wgrad_plan_*, lisec_b200/csrc/wgrad.cu): x bf16 [B,D,H,W,C], dy bf16
+    [B,OD,OH,OW,N] -> dw float32 [taps, N, C] (the forward plans' weight layout). Buffers are bound at construction."""
+
+    def __init__(self, x: torch.Tensor, dy: torch.Tensor, k, stride_d: int, pad, tile=(16, 8)):
+        if x.dtype != torch.bfloat16 or dy.dtype != torch.bfloat16 or not x.is_cuda or x.dim() != 5 or dy.dim() != 5:
+            raise ValueError("x, dy: cuda bf16 [B, D, H, W, C]")
+        self._lib = N.load()
+        B, D, H, W, Cin = x.shape
+        self.x, self.dy = x.contiguous(), dy.contiguous()
+        self.desc = N.lisec_conv_desc(
+            batch=B, in_d=D, in_h=H, in_w=W, in_c=Cin, kd=k[0], kh=k[1], kw=k[2], stride_d=stride_d, stride_hw=1,
+            pad_d=pad[0], pad_h=pad[1], pad_w=pad[2], out_c=dy.shape[-1], n_tiles=1, shuffle=1, out_pitch=dy.shape[-1],
+            out_ch_off=0, relu=0, out_dtype=N.LISEC_F32, tile_w=tile[0], tile_h=tile[1], m_tiles=1, in_dtype=N.LISEC_BF16,
+            out_split=0, group_kh=0, reserved=0)
+        taps = k[0] * k[1] * k[2]
+        self.dw = torch.empty((taps, dy.shape[-1], Cin), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            ws = int(self._lib.lisec_conv_wgrad_workspace_bytes(C.byref(self.desc)))
+            self.workspace = torch.empty(ws // 4, dtype=torch.float32, device=x.device)
+            self.plan = C.c_void_p()
+            st = self._lib.lisec_conv_wgrad_plan_create(C.byref(self.desc), C.c_void_p(self.x.data_ptr()),
+                                                        C.c_void_p(self.dy.data_ptr()),
+                                                        C.c_void_p(self.workspace.data_ptr()),
+                                                        C.c_void_p(self.dw.data_ptr()), C.byref(self.plan))
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_wgrad_last_error().decode("utf-8", "replace"))
+
+    def run(self) -> torch.Tensor:
+        with torch.cuda.device(self.x.device):
+            st = self._lib.lisec_conv_wgrad_plan_run(self.plan, C.c_void_p(torch.cuda.current_stream(self.x.device).cuda_stream))
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_wgrad_last_error().decode("utf-8", "replace"))
+        return self.dw
+
+    def close(self):
+        if getattr(self, "plan", None):
+            self._lib.lisec_conv_wgrad_plan_destroy(self.plan)
+            self.plan = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -103,3 +103,42 @@ def test_gpu_mse_loss_and_gradient():
         assert dy.cpu().numpy().tobytes() == want_dy.astype(np.float32).tobytes()
     loss, dy = mse_loss_grad(torch.from_numpy(y).cuda(), torch.from_numpy(t).cuda(), want_grad=False)
     assert dy is None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [
+    dict(B=2, D=4, H=24, W=40, C=64, N=64, k=(3, 3, 3), sd=1, pad=(0, 1, 1)),    # conv3d_1's geometry, 27 taps (odd units)
+    dict(B=1, D=8, H=17, W=21, C=64, N=64, k=(3, 3, 3), sd=2, pad=(1, 1, 1)),    # stride 2 in depth, ragged tiles
+    dict(B=2, D=1, H=24, W=40, C=128, N=128, k=(1, 3, 3), sd=1, pad=(0, 1, 1)),  # RPN 128 -> 128: 18 units, 3 passes
+    dict(B=1, D=1, H=12, W=20, C=256, N=256, k=(1, 3, 3), sd=1, pad=(0, 1, 1)),  # RPN 256 -> 256: 9 passes
+    dict(B=3, D=1, H=16, W=16, C=64, N=128, k=(1, 1, 1), sd=1, pad=(0, 0, 0)),   # 1x1: a single (half-used) pair
+])
+def test_gpu_conv_wgrad_matches_autograd(case):
+    """dW from conv_wgrad_kernel against torch CPU float64 autograd of the same convolution on the same bf16 tensors."""
+    import torch.nn.functional as F
+
+    from lisec_b200.train import ConvWgrad
+
+    c = case
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn((c["B"], c["D"], c["H"], c["W"], c["C"]), generator=g).to(torch.bfloat16)
+    k = c["k"]
+    OD = (c["D"] + 2 * c["pad"][0] - k[0]) // c["sd"] + 1
+    OH, OW = c["H"] + 2 * c["pad"][1] - k[1] + 1, c["W"] + 2 * c["pad"][2] - k[2] + 1
+    dy = (torch.randn((c["B"], OD, OH, OW, c["N"]), generator=g) * 0.5).to(torch.bfloat16)
+    wg = ConvWgrad(x.cuda(), dy.cuda(), k, c["sd"], c["pad"])
+    wg.dw.fill_(float("nan"))
+    got = wg.run()
+    torch.cuda.synchronize()
+    got2 = wg.run().clone()  # a second launch: same bits (no atomics anywhere)
+    torch.cuda.synchronize()
+    w = torch.zeros((c["N"], c["C"]) + tuple(k), dtype=torch.float64, requires_grad=True)
+    y = F.conv3d(x.double().permute(0, 4, 1, 2, 3), w, None, stride=(c["sd"], 1, 1), padding=c["pad"])
+    (y * dy.double().permute(0, 4, 1, 2, 3)).sum().backward()
+    want = w.grad.permute(2, 3, 4, 0, 1).reshape(k[0] * k[1] * k[2], c["N"], c["C"])  # [tap][co][ci]
+    got = got.cpu().double()
+    assert torch.isfinite(got).all()
+    err = (got - want).abs().max() / want.abs().max()
+    assert err <= 2e-5, err  # bf16 products are exact in float32; what differs is the float32 summation order
+    assert torch.equal(got2.cpu().double(), got)
+    wg.close()
