@@ -343,6 +343,12 @@ int32_t lisec_sgd_nesterov(float* var, float* accum, const float* grad, int64_t 
 /* [async] 'mse' on one output tensor: *sum_sq += sum (y - target)^2 (double, device; the loss is sum_sq / n) and, when dy
  * is not NULL, dy = 2 (y - target) / n — d loss / d y, where the backward pass starts. */
 int32_t lisec_mse_loss_grad(const float* y, const float* target, int64_t n, float* dy, double* sum_sq, void* stream);
+/* [async] The weight operand of a data-gradient plan: the data gradient of a stride-1 convolution is a convolution of dy
+ * (lisec_conv_plan_* with pad' = k - 1 - pad, in_c' = out_c, out_c' = in_c) with the kernel flipped in d, h, w and its
+ * channel roles swapped. w: device float32 [kd*kh*kw][out_c][in_c] (master weights); out_bf16: device bf16
+ * [kd*kh*kw][in_c][out_c]. */
+int32_t lisec_weights_flip_transpose(const float* w, int32_t kd, int32_t kh, int32_t kw, int32_t out_c, int32_t in_c,
+                                     void* out_bf16, void* stream);
 const char* lisec_train_last_error(void);
 
 /* Weight gradient of one convolution layer on the tensor cores (lisec_b200/csrc/wgrad.cu) — the first backward kernel:

@@ -15,6 +15,8 @@
 #include <cstdarg>
 #include <cstdio>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace lisec {
@@ -79,6 +81,26 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// dgrad operand: the data gradient of a stride-1 convolution is a convolution of dY with the kernel flipped in every
+// spatial direction and its channel roles swapped: out[(kd-1-a, kh-1-b, kw-1-c)][ci][co] = w[(a, b, c)][co][ci]
+// (both in the forward plans' [tap][N][C] layout, float32 master weights in, bf16 operand out).
+__global__ void __launch_bounds__(256)
+    flip_transpose_kernel(const float* __restrict__ w, int kd, int kh, int kw, int n_out, int c_in,
+                          __nv_bfloat16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long total = (long long)kd * kh * kw * n_out * c_in;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  // i indexes the OUTPUT [tap'][ci][co] so that the writes are coalesced
+  const int co = (int)(i % n_out);
+  const int ci = (int)((i / n_out) % c_in);
+  const int tp = (int)(i / ((long long)n_out * c_in));
+  const int c = tp % kw, b = (tp / kw) % kh, a = tp / (kw * kh);
+  const int tap = ((kd - 1 - a) * kh + (kh - 1 - b)) * kw + (kw - 1 - c);
+  out[i] = __float2bfloat16(w[((long long)tap * n_out + co) * c_in + ci]);
+}
+
 thread_local char g_train_error[256] = "";
 
 int32_t train_fail(int32_t code, const char* fmt, ...) {
@@ -114,6 +136,17 @@ int32_t lisec_sgd_nesterov(float* var, float* accum, const float* grad, int64_t 
   if (blocks < 1) blocks = 1;
   cudaError_t e = launch_pdl(sgd_nesterov_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream),
                              var, accum, grad, (long long)n, grad_scale, lr_t, momentum, (int)nesterov);
+  if (e != cudaSuccess) return train_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
+  return LISEC_OK;
+}
+
+int32_t lisec_weights_flip_transpose(const float* w, int32_t kd, int32_t kh, int32_t kw, int32_t out_c, int32_t in_c,
+                                     void* out_bf16, void* stream) {
+  if (!w || !out_bf16 || kd < 1 || kh < 1 || kw < 1 || out_c < 1 || in_c < 1) return train_fail(LISEC_ERR_BAD_ARG, "bad argument");
+  const long long total = (long long)kd * kh * kw * out_c * in_c;
+  cudaError_t e = launch_pdl(flip_transpose_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0,
+                             static_cast<cudaStream_t>(stream), w, (int)kd, (int)kh, (int)kw, (int)out_c, (int)in_c,
+                             static_cast<__nv_bfloat16*>(out_bf16));
   if (e != cudaSuccess) return train_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
   return LISEC_OK;
 }

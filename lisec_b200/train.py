@@ -148,3 +148,71 @@ class ConvWgrad:
             self.close()
         except Exception:
             pass
+
+
+class ConvDgrad:
+    """dX of a stride-1 convolution layer: a FORWARD plan (lisec_conv_plan_*, the same TMA + tcgen05 kernels) over dy with
+    the kernel flipped and its channel roles swapped (lisec_weights_flip_transpose) and pad' = k - 1 - pad.
+    dy bf16 [B,OD,OH,OW,N] -> dx bf16 [B,D,H,W,C]; `w` is the layer's float32 master weight [taps, N, C]. Call
+    refresh_weights() after every optimizer step (the operand is a bf16 copy), then run()."""
+
+    def __init__(self, dy: torch.Tensor, w: torch.Tensor, k, pad, out_dtype=torch.bfloat16, tile=None):
+        if dy.dtype != torch.bfloat16 or not dy.is_cuda or dy.dim() != 5 or w.dtype != torch.float32 or w.dim() != 3:
+            raise ValueError("dy: cuda bf16 [B,OD,OH,OW,N]; w: cuda float32 [taps, N, C]")
+        self._lib = N.load()
+        B, OD, OH, OW, Nout = dy.shape
+        taps, n2, Cin = w.shape
+        if n2 != Nout or taps != k[0] * k[1] * k[2]:
+            raise ValueError("w does not match dy / k")
+        self.dy, self.w, self.k = dy.contiguous(), w, tuple(k)
+        p2 = tuple(k[i] - 1 - pad[i] for i in range(3))
+        D, H, W = (OD + 2 * p2[0] - k[0] + 1, OH + 2 * p2[1] - k[1] + 1, OW + 2 * p2[2] - k[2] + 1)
+        self.dx = torch.empty((B, D, H, W, Cin), dtype=out_dtype, device=dy.device)
+        self.wt = torch.empty((taps, Cin, Nout), dtype=torch.bfloat16, device=dy.device)
+        self.scale = torch.ones(Cin, dtype=torch.float32, device=dy.device)
+        self.shift = torch.zeros(Cin, dtype=torch.float32, device=dy.device)
+        if tile is None:
+            tile = (16, 8) if W >= 16 else (8, 16)
+        self.desc = N.lisec_conv_desc(
+            batch=B, in_d=OD, in_h=OH, in_w=OW, in_c=Nout, kd=k[0], kh=k[1], kw=k[2], stride_d=1, stride_hw=1,
+            pad_d=p2[0], pad_h=p2[1], pad_w=p2[2], out_c=Cin, n_tiles=1, shuffle=1, out_pitch=Cin, out_ch_off=0, relu=0,
+            out_dtype=N.LISEC_BF16 if out_dtype == torch.bfloat16 else N.LISEC_F32, tile_w=tile[0], tile_h=tile[1],
+            m_tiles=1, in_dtype=N.LISEC_BF16, out_split=0, group_kh=0, reserved=0)
+        self.refresh_weights()
+        self.plan = C.c_void_p()
+        with torch.cuda.device(dy.device):
+            st = self._lib.lisec_conv_plan_create(C.byref(self.desc), C.c_void_p(self.dy.data_ptr()),
+                                                  C.c_void_p(self.wt.data_ptr()), C.c_void_p(self.scale.data_ptr()),
+                                                  C.c_void_p(self.shift.data_ptr()), C.c_void_p(self.dx.data_ptr()),
+                                                  C.byref(self.plan))
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_conv_last_error().decode("utf-8", "replace"))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dy.device).cuda_stream)
+
+    def refresh_weights(self) -> None:
+        taps, Nout, Cin = self.w.shape
+        with torch.cuda.device(self.dy.device):
+            st = self._lib.lisec_weights_flip_transpose(C.c_void_p(self.w.data_ptr()), self.k[0], self.k[1], self.k[2], Nout,
+                                                        Cin, C.c_void_p(self.wt.data_ptr()), self._stream())
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_train_last_error().decode("utf-8", "replace"))
+
+    def run(self) -> torch.Tensor:
+        with torch.cuda.device(self.dy.device):
+            st = self._lib.lisec_conv_plan_run(self.plan, self._stream())
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_conv_last_error().decode("utf-8", "replace"))
+        return self.dx
+
+    def close(self):
+        if getattr(self, "plan", None):
+            self._lib.lisec_conv_plan_destroy(self.plan)
+            self.plan = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

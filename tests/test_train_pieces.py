@@ -142,3 +142,37 @@ def test_gpu_conv_wgrad_matches_autograd(case):
     assert err <= 2e-5, err  # bf16 products are exact in float32; what differs is the float32 summation order
     assert torch.equal(got2.cpu().double(), got)
     wg.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [
+    dict(B=2, D=4, H=24, W=40, C=64, N=64, k=(3, 3, 3), pad=(0, 1, 1)),    # conv3d_1: depth shrinks 4 -> 2, grows back
+    dict(B=2, D=1, H=24, W=40, C=128, N=128, k=(1, 3, 3), pad=(0, 1, 1)),  # RPN 128 -> 128
+    dict(B=1, D=1, H=12, W=20, C=128, N=256, k=(1, 3, 3), pad=(0, 1, 1)),  # 128 -> 256: dX has 128 channels
+    dict(B=3, D=1, H=16, W=16, C=64, N=64, k=(1, 1, 1), pad=(0, 0, 0)),    # the Dense(64 -> 64) behind a Conv3D
+])
+def test_gpu_conv_dgrad_matches_autograd(case):
+    """dX through a forward plan on dy with flipped, transposed weights, against torch CPU float64 autograd."""
+    import torch.nn.functional as F
+
+    from lisec_b200.train import ConvDgrad
+
+    c = case
+    k = c["k"]
+    g = torch.Generator(device="cpu").manual_seed(9)
+    OD = c["D"] + 2 * c["pad"][0] - k[0] + 1
+    OH, OW = c["H"] + 2 * c["pad"][1] - k[1] + 1, c["W"] + 2 * c["pad"][2] - k[2] + 1
+    dy = torch.randn((c["B"], OD, OH, OW, c["N"]), generator=g).to(torch.bfloat16)
+    w = (torch.randn((k[0] * k[1] * k[2], c["N"], c["C"]), generator=g) * 0.05).to(torch.bfloat16).float()
+    dg = ConvDgrad(dy.cuda(), w.cuda(), k, c["pad"], out_dtype=torch.float32)
+    dg.dx.fill_(float("nan"))
+    got = dg.run().cpu().double()
+    x = torch.zeros((c["B"], c["C"], c["D"], c["H"], c["W"]), dtype=torch.float64, requires_grad=True)
+    wt = w.double().reshape(k[0], k[1], k[2], c["N"], c["C"]).permute(3, 4, 0, 1, 2)
+    y = F.conv3d(x, wt, None, stride=1, padding=c["pad"])
+    (y * dy.double().permute(0, 4, 1, 2, 3)).sum().backward()
+    want = x.grad.permute(0, 2, 3, 4, 1)
+    assert got.shape == want.shape and torch.isfinite(got).all()
+    err = (got - want).abs().max() / want.abs().max()
+    assert err <= 2e-5, err
+    dg.close()
