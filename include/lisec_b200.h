@@ -351,6 +351,25 @@ int32_t lisec_weights_flip_transpose(const float* w, int32_t kd, int32_t kh, int
                                      void* out_bf16, void* stream);
 const char* lisec_train_last_error(void);
 
+/* Training-mode BatchNormalization on channels-last bf16 activations [positions][channels] (lisec_b200/csrc/bn.cu): the
+ * batch statistics of model.fit (model_training.py:171/194/204 under :299), deterministic two-stage reductions.
+ * channels in {8, 16, 32, 64, 128, 256}. workspace: lisec_bn_workspace_bytes(positions, channels) bytes. All pointers
+ * are device pointers; per-channel vectors are float32.
+ * forward  [async]: mean, invstd (of the biased batch variance + eps), scale = gamma * invstd, shift = beta - mean * scale
+ *                   are written; y = x * scale + shift (ReLU when relu != 0), bf16; moving_mean / moving_var (may be NULL)
+ *                   <- momentum * moving + (1 - momentum) * batch.
+ * backward [async]: g = dy (masked by y > 0 when relu != 0); dgamma = sum g * xhat, dbeta = sum g,
+ *                   dx = gamma * invstd * (g - mean(g) - xhat * mean(g * xhat)), bf16; mean_g / mean_gx are scratch outputs. */
+int64_t lisec_bn_workspace_bytes(int64_t positions, int32_t channels);
+int32_t lisec_bn_train_forward(const void* x, int64_t positions, int32_t channels, const float* gamma, const float* beta,
+                               float eps, float momentum, float* moving_mean, float* moving_var, int32_t relu, void* y,
+                               float* mean, float* invstd, float* scale, float* shift, void* workspace, void* stream);
+int32_t lisec_bn_train_backward(const void* x, const void* dy, const void* y, int64_t positions, int32_t channels,
+                                const float* gamma, const float* mean, const float* invstd, int32_t relu, void* dx,
+                                float* dgamma, float* dbeta, float* mean_g, float* mean_gx, void* workspace,
+                                void* stream);
+const char* lisec_bn_last_error(void);
+
 /* Weight gradient of one convolution layer on the tensor cores (lisec_b200/csrc/wgrad.cu) — the first backward kernel:
  *   dw[tap][co][ci] = sum over output positions p of dy[p][co] * x[p * stride + tap - pad][ci]
  * `desc` describes the FORWARD convolution (geometry fields, tile_w x tile_h = 128 positions; first version: bf16,

@@ -139,6 +139,12 @@ SIGNATURES = {
     "lisec_mse_loss_grad": (C.c_int32, [_VP, _VP, C.c_int64, _VP, _VP, _VP]),
     "lisec_weights_flip_transpose": (C.c_int32, [_VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _VP, _VP]),
     "lisec_train_last_error": (C.c_char_p, []),
+    "lisec_bn_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int32]),
+    "lisec_bn_train_forward": (C.c_int32, [_VP, C.c_int64, C.c_int32, _VP, _VP, C.c_float, C.c_float, _VP, _VP, C.c_int32,
+                                           _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "lisec_bn_train_backward": (C.c_int32, [_VP, _VP, _VP, C.c_int64, C.c_int32, _VP, _VP, _VP, C.c_int32, _VP, _VP, _VP,
+                                            _VP, _VP, _VP, _VP]),
+    "lisec_bn_last_error": (C.c_char_p, []),
     "lisec_conv_wgrad_workspace_bytes": (C.c_int64, [C.POINTER(lisec_conv_desc)]),
     "lisec_conv_wgrad_plan_create": (C.c_int32, [C.POINTER(lisec_conv_desc), _VP, _VP, _VP, _VP, C.POINTER(_H)]),
     "lisec_conv_wgrad_plan_run": (C.c_int32, [_H, _VP]),

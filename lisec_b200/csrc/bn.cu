@@ -1,0 +1,293 @@
+// Training-mode BatchNormalization for channels-last activations — forward statistics / apply and the backward pass
+// (DESIGN.md §4e). Reference: every BatchNormalization() of createModel runs in training mode under model.fit
+// (model_training.py:171, 194, 204, 299): y = gamma * (x - mean_B) / sqrt(var_B + 1e-3) + beta with the batch mean and the
+// biased batch variance over all positions, moving statistics updated with momentum 0.99.
+//
+// All four kernels stream [P positions][C channels] bf16 tensors once: HBM-bound (2 B read per element for the
+// statistics, 2 + 2 for apply, 6 + 2 for the backward pair). Reductions are deterministic: every block leaves its
+// partial sums (double) in its own slot, a finalize kernel adds the slots in order — no floating-point atomics.
+//   bn_stats_kernel        per block: sum x, sum x^2 per channel
+//   bn_finalize_kernel     mean, biased variance -> a = gamma / sqrt(var + eps), b = beta - mean * a; moving statistics
+//   bn_apply_kernel        y = x * a + b (optional ReLU), bf16
+//   bn_bwd_reduce_kernel   g = dy * (y > 0 if relu): per block sum g, sum g * xhat per channel
+//   bn_bwd_finalize_kernel dgamma = sum g xhat, dbeta = sum g; coefficients of the apply
+//   bn_bwd_apply_kernel    dx = gamma * invstd * (g - mean(g) - xhat * mean(g xhat)), bf16
+#include <cuda_bf16.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace lisec {
+namespace {
+
+constexpr int kBnThreads = 256;
+constexpr int kBnMaxC = 256;
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+
+// Two per-channel sums over the rows a block owns. Thread = (row lane, 8-channel chunk); a block's rows are
+// blockIdx.x, blockIdx.x + gridDim.x, ... in groups of rows_per_iter. MODE 0: (x, x^2). MODE 1: (g, g * xhat) with
+// g = dy masked by y > 0 (relu) and xhat = (x - mean) * invstd.
+template <int MODE>
+__global__ void __launch_bounds__(kBnThreads)
+    bn_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ invstd,
+                     long long P, int C, int relu, double* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int chunks = C >> 3, rows_per_iter = kBnThreads / chunks;
+  const int chunk = threadIdx.x % chunks, rl = threadIdx.x / chunks;
+  float s0[8], s1[8], mu[8], is[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    s0[i] = s1[i] = 0.f;
+    mu[i] = MODE == 1 ? mean[8 * chunk + i] : 0.f;
+    is[i] = MODE == 1 ? invstd[8 * chunk + i] : 0.f;
+  }
+  double d0[8], d1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d0[i] = d1[i] = 0.0;
+  int since = 0;
+  if (rl < rows_per_iter)
+    for (long long r = (long long)blockIdx.x * rows_per_iter + rl; r < P; r += (long long)gridDim.x * rows_per_iter) {
+      float xv[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + r * C + 8 * chunk), xv);
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s0[i] += xv[i];
+          s1[i] = fmaf(xv[i], xv[i], s1[i]);
+        }
+      } else {
+        float g[8], yv[8];
+        unpack8(*reinterpret_cast<const uint4*>(dy + r * C + 8 * chunk), g);
+        if (relu) unpack8(*reinterpret_cast<const uint4*>(y + r * C + 8 * chunk), yv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float gi = (relu && !(yv[i] > 0.f)) ? 0.f : g[i];
+          s0[i] += gi;
+          s1[i] = fmaf(gi, (xv[i] - mu[i]) * is[i], s1[i]);
+        }
+      }
+      if (++since == 64) {  // float partial sums are promoted every 64 rows
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          d0[i] += (double)s0[i];
+          d1[i] += (double)s1[i];
+          s0[i] = s1[i] = 0.f;
+        }
+        since = 0;
+      }
+    }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    d0[i] += (double)s0[i];
+    d1[i] += (double)s1[i];
+  }
+  __shared__ double sh[kBnThreads][2];
+  for (int i = 0; i < 8; ++i) {
+    sh[threadIdx.x][0] = d0[i];
+    sh[threadIdx.x][1] = d1[i];
+    __syncthreads();
+    if (rl == 0 && threadIdx.x < chunks) {  // fixed order over the block's row lanes
+      double a = 0.0, b = 0.0;
+      for (int q = 0; q < rows_per_iter; ++q) {
+        a += sh[q * chunks + chunk][0];
+        b += sh[q * chunks + chunk][1];
+      }
+      partial[((long long)blockIdx.x * 2 + 0) * C + 8 * chunk + i] = a;
+      partial[((long long)blockIdx.x * 2 + 1) * C + 8 * chunk + i] = b;
+    }
+    __syncthreads();
+  }
+}
+
+// MODE 0: statistics -> (mean, invstd, a, b) and the moving statistics. MODE 1: (dgamma, dbeta, c_mean_g, c_mean_gx).
+template <int MODE>
+__global__ void __launch_bounds__(kBnMaxC)
+    bn_finalize_kernel(const double* __restrict__ partial, int blocks, long long P, int C, float eps, float momentum,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ o0,
+                       float* __restrict__ o1, float* __restrict__ o2, float* __restrict__ o3,
+                       float* __restrict__ moving_mean, float* __restrict__ moving_var) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0, b = 0.0;
+  for (int g = 0; g < blocks; ++g) {
+    a += partial[((long long)g * 2 + 0) * C + c];
+    b += partial[((long long)g * 2 + 1) * C + c];
+  }
+  if (MODE == 0) {
+    const double mean = a / (double)P, var = fmax(b / (double)P - mean * mean, 0.0);
+    const double invstd = 1.0 / sqrt(var + (double)eps);
+    o0[c] = (float)mean;
+    o1[c] = (float)invstd;
+    const double sc = (double)gamma[c] * invstd;
+    o2[c] = (float)sc;
+    o3[c] = (float)((double)beta[c] - mean * sc);
+    if (moving_mean) {
+      moving_mean[c] = (float)((double)moving_mean[c] * momentum + mean * (1.0 - (double)momentum));
+      moving_var[c] = (float)((double)moving_var[c] * momentum + var * (1.0 - (double)momentum));
+    }
+  } else {
+    o0[c] = (float)b;                 // dgamma = sum g * xhat
+    o1[c] = (float)a;                 // dbeta  = sum g
+    o2[c] = (float)(a / (double)P);   // mean(g)
+    o3[c] = (float)(b / (double)P);   // mean(g * xhat)
+  }
+}
+
+__global__ void __launch_bounds__(kBnThreads)
+    bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
+                    long long n8, int chunks, int relu, __nv_bfloat16* __restrict__ y) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const int c0 = (int)(i % chunks) * 8;
+    float v[8];
+    unpack8(__ldcs(reinterpret_cast<const uint4*>(x) + i), v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k] = fmaf(v[k], a[c0 + k], b[c0 + k]);
+      if (relu) v[k] = fmaxf(v[k], 0.f);
+    }
+    reinterpret_cast<uint4*>(y)[i] = pack8(v);
+  }
+}
+
+__global__ void __launch_bounds__(kBnThreads)
+    bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                        const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                        const float* __restrict__ invstd, const float* __restrict__ gamma,
+                        const float* __restrict__ mean_g, const float* __restrict__ mean_gx, long long n8, int chunks,
+                        int relu, __nv_bfloat16* __restrict__ dx) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const int c0 = (int)(i % chunks) * 8;
+    float xv[8], g[8], yv[8], o[8];
+    unpack8(__ldcs(reinterpret_cast<const uint4*>(x) + i), xv);
+    unpack8(__ldcs(reinterpret_cast<const uint4*>(dy) + i), g);
+    if (relu) unpack8(__ldcs(reinterpret_cast<const uint4*>(y) + i), yv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = c0 + k;
+      const float gi = (relu && !(yv[k] > 0.f)) ? 0.f : g[k];
+      const float xhat = (xv[k] - mean[c]) * invstd[c];
+      o[k] = gamma[c] * invstd[c] * (gi - mean_g[c] - xhat * mean_gx[c]);
+    }
+    reinterpret_cast<uint4*>(dx)[i] = pack8(o);
+  }
+}
+
+thread_local char g_bn_error[256] = "";
+int32_t bn_fail(int32_t code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_bn_error, sizeof(g_bn_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int bn_blocks(long long P, int C) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int rows_per_iter = kBnThreads / (C / 8);
+  long long b = (P + rows_per_iter - 1) / rows_per_iter;
+  if (b > (long long)sms * 8) b = (long long)sms * 8;
+  return (int)(b < 1 ? 1 : b);
+}
+
+bool bn_shape_ok(long long P, int C) { return P > 0 && C >= 8 && C <= kBnMaxC && C % 8 == 0 && kBnThreads % (C / 8) == 0; }
+
+}  // namespace
+}  // namespace lisec
+
+using namespace lisec;
+
+extern "C" {
+
+const char* lisec_bn_last_error(void) { return g_bn_error; }
+
+int64_t lisec_bn_workspace_bytes(int64_t positions, int32_t channels) {
+  if (!bn_shape_ok(positions, channels)) return -1;
+  return (int64_t)bn_blocks(positions, channels) * 2 * channels * (int64_t)sizeof(double);
+}
+
+int32_t lisec_bn_train_forward(const void* x, int64_t positions, int32_t channels, const float* gamma, const float* beta,
+                               float eps, float momentum, float* moving_mean, float* moving_var, int32_t relu, void* y,
+                               float* mean, float* invstd, float* scale, float* shift, void* workspace, void* stream) {
+  if (!x || !gamma || !beta || !y || !mean || !invstd || !scale || !shift || !workspace)
+    return bn_fail(LISEC_ERR_BAD_ARG, "null argument");
+  if (!bn_shape_ok(positions, channels))
+    return bn_fail(LISEC_ERR_BAD_CONFIG, "channels: a multiple of 8 dividing 2048, at most %d", kBnMaxC);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = bn_blocks(positions, channels);
+  double* part = static_cast<double*>(workspace);
+  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
+  cudaError_t e = launch_pdl(bn_reduce_kernel<0>, dim3(blocks), dim3(kBnThreads), 0, st, xb, xb, xb, (const float*)mean,
+                             (const float*)invstd, (long long)positions, (int)channels, 0, part);
+  if (e == cudaSuccess)
+    e = launch_pdl(bn_finalize_kernel<0>, dim3(1), dim3(kBnMaxC), 0, st, (const double*)part, blocks, (long long)positions,
+                   (int)channels, eps, momentum, gamma, beta, mean, invstd, scale, shift, moving_mean, moving_var);
+  const long long n8 = positions * channels / 8;
+  long long ab = (n8 + kBnThreads - 1) / kBnThreads;
+  if (ab > 148 * 16) ab = 148 * 16;
+  if (e == cudaSuccess)
+    e = launch_pdl(bn_apply_kernel, dim3((unsigned)ab), dim3(kBnThreads), 0, st, xb, (const float*)scale,
+                   (const float*)shift, n8, (int)(channels / 8), (int)relu, static_cast<__nv_bfloat16*>(y));
+  if (e != cudaSuccess) return bn_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
+  return LISEC_OK;
+}
+
+int32_t lisec_bn_train_backward(const void* x, const void* dy, const void* y, int64_t positions, int32_t channels,
+                                const float* gamma, const float* mean, const float* invstd, int32_t relu, void* dx,
+                                float* dgamma, float* dbeta, float* mean_g, float* mean_gx, void* workspace,
+                                void* stream) {
+  if (!x || !dy || (relu && !y) || !gamma || !mean || !invstd || !dx || !dgamma || !dbeta || !mean_g || !mean_gx || !workspace)
+    return bn_fail(LISEC_ERR_BAD_ARG, "null argument");
+  if (!bn_shape_ok(positions, channels))
+    return bn_fail(LISEC_ERR_BAD_CONFIG, "channels: a multiple of 8 dividing 2048, at most %d", kBnMaxC);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = bn_blocks(positions, channels);
+  double* part = static_cast<double*>(workspace);
+  const __nv_bfloat16 *xb = static_cast<const __nv_bfloat16*>(x), *dyb = static_cast<const __nv_bfloat16*>(dy),
+                      *yb = static_cast<const __nv_bfloat16*>(relu ? y : x);
+  cudaError_t e = launch_pdl(bn_reduce_kernel<1>, dim3(blocks), dim3(kBnThreads), 0, st, xb, dyb, yb, mean, invstd,
+                             (long long)positions, (int)channels, (int)relu, part);
+  if (e == cudaSuccess)
+    e = launch_pdl(bn_finalize_kernel<1>, dim3(1), dim3(kBnMaxC), 0, st, (const double*)part, blocks, (long long)positions,
+                   (int)channels, 0.f, 0.f, gamma, gamma, dgamma, dbeta, mean_g, mean_gx, (float*)nullptr, (float*)nullptr);
+  const long long n8 = positions * channels / 8;
+  long long ab = (n8 + kBnThreads - 1) / kBnThreads;
+  if (ab > 148 * 16) ab = 148 * 16;
+  if (e == cudaSuccess)
+    e = launch_pdl(bn_bwd_apply_kernel, dim3((unsigned)ab), dim3(kBnThreads), 0, st, xb, dyb, yb, mean, invstd, gamma,
+                   (const float*)mean_g, (const float*)mean_gx, n8, (int)(channels / 8), (int)relu,
+                   static_cast<__nv_bfloat16*>(dx));
+  if (e != cudaSuccess) return bn_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
+  return LISEC_OK;
+}
+
+}  // extern "C"

@@ -216,3 +216,57 @@ class ConvDgrad:
             self.close()
         except Exception:
             pass
+
+
+class BatchNormTrain:
+    """Training-mode BatchNormalization (+ optional ReLU) on a channels-last bf16 activation (lisec_bn_train_*): forward()
+    leaves y and the batch statistics, backward(dy) returns dx and fills dgamma / dbeta. gamma, beta, moving_mean,
+    moving_var: float32 device vectors owned by the caller (views into FlatParameters / the model's state)."""
+
+    def __init__(self, x: torch.Tensor, gamma, beta, moving_mean=None, moving_var=None, relu=True, eps=1e-3, momentum=0.99):
+        if x.dtype != torch.bfloat16 or not x.is_cuda:
+            raise ValueError("x: cuda bf16, channels last")
+        self._lib = N.load()
+        self.x, self.relu, self.eps, self.momentum = x, bool(relu), eps, momentum
+        self.C = x.shape[-1]
+        self.P = x.numel() // self.C
+        self.gamma, self.beta, self.moving_mean, self.moving_var = gamma, beta, moving_mean, moving_var
+        dev = x.device
+        ws = int(self._lib.lisec_bn_workspace_bytes(self.P, self.C))
+        if ws < 0:
+            raise ValueError("unsupported channel count %d" % self.C)
+        self.workspace = torch.empty(ws // 8, dtype=torch.float64, device=dev)
+        vec = lambda: torch.empty(self.C, dtype=torch.float32, device=dev)  # noqa: E731
+        self.mean, self.invstd, self.scale, self.shift = vec(), vec(), vec(), vec()
+        self.dgamma, self.dbeta, self._mg, self._mgx = vec(), vec(), vec(), vec()
+        self.y = torch.empty_like(x)
+        self.dx = torch.empty_like(x)
+
+    def _p(self, t):
+        return C.c_void_p(0 if t is None else t.data_ptr())
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.x.device).cuda_stream)
+
+    def forward(self) -> torch.Tensor:
+        with torch.cuda.device(self.x.device):
+            st = self._lib.lisec_bn_train_forward(
+                self._p(self.x), self.P, self.C, self._p(self.gamma), self._p(self.beta), C.c_float(self.eps),
+                C.c_float(self.momentum), self._p(self.moving_mean), self._p(self.moving_var), int(self.relu),
+                self._p(self.y), self._p(self.mean), self._p(self.invstd), self._p(self.scale), self._p(self.shift),
+                self._p(self.workspace), self._stream())
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_bn_last_error().decode("utf-8", "replace"))
+        return self.y
+
+    def backward(self, dy: torch.Tensor) -> torch.Tensor:
+        if dy.dtype != torch.bfloat16 or dy.shape != self.x.shape:
+            raise ValueError("dy: bf16 of x's shape")
+        with torch.cuda.device(self.x.device):
+            st = self._lib.lisec_bn_train_backward(
+                self._p(self.x), self._p(dy.contiguous()), self._p(self.y), self.P, self.C, self._p(self.gamma),
+                self._p(self.mean), self._p(self.invstd), int(self.relu), self._p(self.dx), self._p(self.dgamma),
+                self._p(self.dbeta), self._p(self._mg), self._p(self._mgx), self._p(self.workspace), self._stream())
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_bn_last_error().decode("utf-8", "replace"))
+        return self.dx

@@ -176,3 +176,42 @@ def test_gpu_conv_dgrad_matches_autograd(case):
     err = (got - want).abs().max() / want.abs().max()
     assert err <= 2e-5, err
     dg.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,relu", [((2, 1, 24, 40, 128), True), ((1, 4, 17, 21, 64), False), ((3, 1, 9, 7, 256), True),
+                                        ((1, 1, 50, 100, 16), True)])
+def test_gpu_batchnorm_train_forward_backward(shape, relu):
+    """Training-mode BN (+ReLU) kernels against torch float64 autograd of the same formula on the same bf16 tensors."""
+    from lisec_b200.train import BatchNormTrain
+
+    g = torch.Generator(device="cpu").manual_seed(13)
+    C = shape[-1]
+    x = (torch.randn(shape, generator=g) * 1.5 + 0.3).to(torch.bfloat16)
+    dy = torch.randn(shape, generator=g).to(torch.bfloat16)
+    gamma = torch.rand(C, generator=g) + 0.5
+    beta = torch.randn(C, generator=g) * 0.2
+    mm, mv = torch.randn(C, generator=g), torch.rand(C, generator=g) + 0.5
+    bn = BatchNormTrain(x.cuda(), gamma.cuda(), beta.cuda(), mm.clone().cuda(), mv.clone().cuda(), relu=relu)
+    y = bn.forward().float().cpu()
+    dx = bn.backward(dy.cuda()).float().cpu()
+    xd = x.double().requires_grad_(True)
+    gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    axes = tuple(range(len(shape) - 1))
+    mean, var = xd.mean(dim=axes), xd.var(dim=axes, unbiased=False)
+    yd = (xd - mean) / torch.sqrt(var + 1e-3) * gd + bd
+    if relu:
+        yd = torch.relu(yd)
+    assert (y.double() - yd.detach()).abs().max() <= 2.0 ** -8 * max(1.0, float(yd.detach().abs().max()))  # one bf16 rounding
+    assert torch.allclose(bn.mean.cpu().double(), mean.detach(), rtol=0, atol=1e-6)
+    assert torch.allclose(bn.invstd.cpu().double(), 1 / torch.sqrt(var.detach() + 1e-3), rtol=1e-6, atol=0)
+    assert torch.allclose(bn.moving_mean.cpu().double(), mm.double() * 0.99 + mean.detach() * 0.01, rtol=0, atol=1e-6)
+    assert torch.allclose(bn.moving_var.cpu().double(), mv.double() * 0.99 + var.detach() * 0.01, rtol=1e-6, atol=1e-7)
+    # the kernel masks with ITS y (bf16): use the same mask in the reference so that borderline zeros cannot differ
+    mask = (y > 0).double() if relu else torch.ones_like(y, dtype=torch.float64)
+    yl = (xd - mean) / torch.sqrt(var + 1e-3) * gd + bd
+    (yl * (dy.double() * mask)).sum().backward()
+    scale = float(xd.grad.abs().max())
+    assert (dx.double() - xd.grad).abs().max() <= 2.0 ** -8 * scale + 1e-6
+    assert torch.allclose(bn.dgamma.cpu().double(), gd.grad, rtol=1e-5, atol=1e-4)
+    assert torch.allclose(bn.dbeta.cpu().double(), bd.grad, rtol=1e-5, atol=1e-4)
