@@ -382,6 +382,29 @@ def run_native(args):
     barrier()
     ms_comm_update = max_over_ranks(timed(comm_and_update, 20)) if world > 1 else ms_update
     update_bytes = fp.numel_padded * 20
+    bwd = None
+    if world == 1:
+        # the first Conv3D's weight gradient and the second Conv3D's data gradient at the bench batch (8 sweeps)
+        try:
+            from lisec_b200.train import ConvDgrad, ConvWgrad
+
+            xg = torch.randn((SWEEPS_PER_GPU, 8, 200, 400, 64), device=dev).to(torch.bfloat16)
+            dyg = torch.randn((SWEEPS_PER_GPU, 4, 200, 400, 64), device=dev).to(torch.bfloat16)
+            wg = ConvWgrad(xg, dyg, (3, 3, 3), 2, (1, 1, 1))
+            ms_wg = timed(wg.run, 5)
+            fl = 2.0 * SWEEPS_PER_GPU * 4 * 200 * 400 * 27 * 64 * 64
+            wg.close()
+            dy2 = torch.randn((SWEEPS_PER_GPU, 2, 200, 400, 64), device=dev).to(torch.bfloat16)
+            wm = torch.randn((27, 64, 64), device=dev) * 0.05
+            dg = ConvDgrad(dy2, wm, (3, 3, 3), (0, 1, 1))
+            ms_dg = timed(dg.run, 5)
+            dg.close()
+            bwd = {"conv3d_wgrad_ms": ms_wg, "conv3d_wgrad_tflops": fl / (ms_wg * 1e-3) / 1e12,
+                   "conv3d_1_dgrad_ms": ms_dg, "conv3d_1_dgrad_tflops": fl / (ms_dg * 1e-3) / 1e12}
+            del xg, dyg, dy2, wg, dg, wm
+        except Exception as exc:  # an auxiliary leg must not take the headline down with it
+            bwd = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        torch.cuda.empty_cache()
 
     # end to end through the host-buffer entry point
     n_w = min(args.warmup, 3)
@@ -570,10 +593,14 @@ def run_native(args):
                                   "value": 1.0 / regions_cpu_s, "unit": "samples/s", "cores": 1, "kind": "port",
                                   "sample": "one sample: the oracle's numpy decode + vectorised greedy NMS (the "
                                             "reference's own Python loop takes ~16 s per sample)"}},
-            "train_step_pieces": {"built": "gradient all-reduce (NCCL, sum) + sgd_nesterov_kernel over the flat float32 "
-                                           "parameter buffer + the mse loss head; NOT the backward pass",
+            "train_step_pieces": {"built": "gradient all-reduce (NCCL, sum), sgd_nesterov_kernel over the flat float32 parameter "
+                                           "buffer, the mse loss head, convolution weight gradients (conv_wgrad_kernel) and "
+                                           "stride-1 data gradients (forward plans on dy) on the tensor cores, training-mode "
+                                           "BatchNormalization forward / backward; NOT yet: strided / transposed layers' "
+                                           "backward, the VFE stack's backward, the step that chains them",
                                   "parameters": fp.numel, "gradient_bytes": fp.numel * 4,
                                   "sgd_update_ms": ms_update, "allreduce_plus_update_ms": ms_comm_update,
+                                  "backward_kernels": bwd,
                                   "roofline": {"kernel": "sgd_nesterov_kernel", "bound": "hbm",
                                                "algorithmic_bytes_per_launch": update_bytes,
                                                "achieved": update_bytes / (ms_update * 1e-3) / 1e9, "peak": hbm_peak,

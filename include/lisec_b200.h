@@ -349,6 +349,8 @@ int32_t lisec_mse_loss_grad(const float* y, const float* target, int64_t n, floa
  * [kd*kh*kw][in_c][out_c]. */
 int32_t lisec_weights_flip_transpose(const float* w, int32_t kd, int32_t kh, int32_t kw, int32_t out_c, int32_t in_c,
                                      void* out_bf16, void* stream);
+/* [async] float32 master weights -> the bf16 operand copy the plans read. */
+int32_t lisec_cast_f32_to_bf16(const float* w, int64_t n, void* out_bf16, void* stream);
 const char* lisec_train_last_error(void);
 
 /* Training-mode BatchNormalization on channels-last bf16 activations [positions][channels] (lisec_b200/csrc/bn.cu): the
@@ -368,6 +370,8 @@ int32_t lisec_bn_train_backward(const void* x, const void* dy, const void* y, in
                                 const float* gamma, const float* mean, const float* invstd, int32_t relu, void* dx,
                                 float* dgamma, float* dbeta, float* mean_g, float* mean_gx, void* workspace,
                                 void* stream);
+/* [async] sums[c] = sum over positions of x[p][c] (bf16 in, float32 out): the bias gradient of a convolution from dy. */
+int32_t lisec_channel_sums(const void* x, int64_t positions, int32_t channels, float* sums, void* workspace, void* stream);
 const char* lisec_bn_last_error(void);
 
 /* Weight gradient of one convolution layer on the tensor cores (lisec_b200/csrc/wgrad.cu) — the first backward kernel:

@@ -147,6 +147,8 @@ __global__ void __launch_bounds__(kBnMaxC)
       moving_mean[c] = (float)((double)moving_mean[c] * momentum + mean * (1.0 - (double)momentum));
       moving_var[c] = (float)((double)moving_var[c] * momentum + var * (1.0 - (double)momentum));
     }
+  } else if (MODE == 2) {
+    o0[c] = (float)a;  // plain column sums: a convolution's bias gradient = sum over positions of dy
   } else {
     o0[c] = (float)b;                 // dgamma = sum g * xhat
     o1[c] = (float)a;                 // dbeta  = sum g
@@ -257,6 +259,24 @@ int32_t lisec_bn_train_forward(const void* x, int64_t positions, int32_t channel
   if (e == cudaSuccess)
     e = launch_pdl(bn_apply_kernel, dim3((unsigned)ab), dim3(kBnThreads), 0, st, xb, (const float*)scale,
                    (const float*)shift, n8, (int)(channels / 8), (int)relu, static_cast<__nv_bfloat16*>(y));
+  if (e != cudaSuccess) return bn_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
+  return LISEC_OK;
+}
+
+int32_t lisec_channel_sums(const void* x, int64_t positions, int32_t channels, float* sums, void* workspace, void* stream) {
+  if (!x || !sums || !workspace) return bn_fail(LISEC_ERR_BAD_ARG, "null argument");
+  if (!bn_shape_ok(positions, channels))
+    return bn_fail(LISEC_ERR_BAD_CONFIG, "channels: a multiple of 8 dividing 2048, at most %d", kBnMaxC);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = bn_blocks(positions, channels);
+  double* part = static_cast<double*>(workspace);
+  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
+  cudaError_t e = launch_pdl(bn_reduce_kernel<0>, dim3(blocks), dim3(kBnThreads), 0, st, xb, xb, xb, (const float*)sums,
+                             (const float*)sums, (long long)positions, (int)channels, 0, part);
+  if (e == cudaSuccess)
+    e = launch_pdl(bn_finalize_kernel<2>, dim3(1), dim3(kBnMaxC), 0, st, (const double*)part, blocks, (long long)positions,
+                   (int)channels, 0.f, 0.f, (const float*)sums, (const float*)sums, sums, sums, sums, sums,
+                   (float*)nullptr, (float*)nullptr);
   if (e != cudaSuccess) return bn_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
   return LISEC_OK;
 }

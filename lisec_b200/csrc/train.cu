@@ -101,6 +101,14 @@ __global__ void __launch_bounds__(256)
   out[i] = __float2bfloat16(w[((long long)tap * n_out + co) * c_in + ci]);
 }
 
+// float32 master weights -> the bf16 operand copy the plans read (after every optimizer step)
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ w, long long n, __nv_bfloat16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = __float2bfloat16(w[i]);
+}
+
 thread_local char g_train_error[256] = "";
 
 int32_t train_fail(int32_t code, const char* fmt, ...) {
@@ -147,6 +155,17 @@ int32_t lisec_weights_flip_transpose(const float* w, int32_t kd, int32_t kh, int
   cudaError_t e = launch_pdl(flip_transpose_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0,
                              static_cast<cudaStream_t>(stream), w, (int)kd, (int)kh, (int)kw, (int)out_c, (int)in_c,
                              static_cast<__nv_bfloat16*>(out_bf16));
+  if (e != cudaSuccess) return train_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
+  return LISEC_OK;
+}
+
+int32_t lisec_cast_f32_to_bf16(const float* w, int64_t n, void* out_bf16, void* stream) {
+  if (n < 0 || (n > 0 && (!w || !out_bf16))) return train_fail(LISEC_ERR_BAD_ARG, "bad argument");
+  if (n == 0) return LISEC_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  cudaError_t e = launch_pdl(cast_bf16_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), w,
+                             (long long)n, static_cast<__nv_bfloat16*>(out_bf16));
   if (e != cudaSuccess) return train_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
   return LISEC_OK;
 }

@@ -17,7 +17,8 @@
 // this CTA's slice of a float32 partial buffer [grid][taps][N][C]; wgrad_reduce_kernel then adds the slices in a fixed
 // order (deterministic — no atomics), giving dW in the layout the forward plans read their weights in.
 //
-// First version: bf16 operands, float32 accumulation, stride_hw = 1, C and N multiples of 64, N <= 256. Each X box feeds
+// First version: bf16 operands, float32 accumulation, stride_hw 1 or 2 (the TMA's element stride), C and N multiples of
+// 64, N <= 256. Each X box feeds
 // only 8 MMAs, so this kernel is bound by L2 -> shared-memory delivery like the first forward kernel was
 // (profiles/conv_r1j_summary.txt); the halo-box trick of conv_halo_kernel applies here too and is the next step.
 #include <cuda.h>
@@ -45,7 +46,7 @@ struct WgradParams {
   int bw, bh;
   int units, pairs, pairs_per_pass, passes, nb, N, C, taps, stages;
   uint32_t stage_bytes;
-  int stride_d;
+  int stride_d, stride_hw;
   signed char t1[27], t2[27], t3[27];  // X box origin of a tap relative to the tile origin (w, h, d)
   float* partial;  // [grid][taps][N][C]
   long long slice;  // taps * N * C
@@ -140,8 +141,8 @@ __global__ void __launch_bounds__(kWgThreads, 1)
             for (int h = 0; h < 2; ++h) {
               const int u = min(2 * pair + h, P.units - 1);  // an odd unit count: the last pair loads its unit twice
               const int tap = u / cblocks, cb = u - tap * cblocks;
-              tma_load_5d(dst + h * kBox, &map_x, bar_full(s), 64 * cb, t.ow0 + P.t1[tap], t.oh0 + P.t2[tap],
-                          t.od * P.stride_d + P.t3[tap], t.b);
+              tma_load_5d(dst + h * kBox, &map_x, bar_full(s), 64 * cb, t.ow0 * P.stride_hw + P.t1[tap],
+                          t.oh0 * P.stride_hw + P.t2[tap], t.od * P.stride_d + P.t3[tap], t.b);
             }
             for (int n = 0; n < P.nb; ++n)
               tma_load_5d(dst + (2 + n) * kBox, &map_dy, bar_full(s), 64 * n, t.ow0, t.oh0, t.od, t.b);
@@ -284,14 +285,15 @@ int32_t lisec_conv_wgrad_plan_create(const lisec_conv_desc* d, const void* x, co
   if (!d || !x || !dy || !workspace || !dw || !out) return wg_fail(LISEC_ERR_BAD_ARG, "null argument");
   *out = nullptr;
   const int C = d->in_c, N = d->out_c, taps = d->kd * d->kh * d->kw;
-  if (d->stride_hw != 1) return wg_fail(LISEC_ERR_UNSUPPORTED, "wgrad: stride_hw = 1 only (first version)");
+  const int shw = d->stride_hw;
+  if (shw != 1 && shw != 2) return wg_fail(LISEC_ERR_UNSUPPORTED, "wgrad: stride_hw 1 or 2");
   if (C % 64 || N % 64 || N > 256 || C > 256) return wg_fail(LISEC_ERR_BAD_CONFIG, "wgrad: in_c, out_c multiples of 64, <= 256");
   if (taps > 27 || taps < 1) return wg_fail(LISEC_ERR_BAD_CONFIG, "wgrad: at most 27 taps");
   if (d->tile_w * d->tile_h != 128 || d->tile_w < 8 || (d->tile_w & (d->tile_w - 1)))
     return wg_fail(LISEC_ERR_BAD_CONFIG, "wgrad: tile_w * tile_h = 128, tile_w a power of two >= 8");
   if (d->n_tiles != 1 || d->shuffle > 1) return wg_fail(LISEC_ERR_UNSUPPORTED, "wgrad: plain convolutions only");
   const int OD = (d->in_d + 2 * d->pad_d - d->kd) / d->stride_d + 1;
-  const int OH = d->in_h + 2 * d->pad_h - d->kh + 1, OW = d->in_w + 2 * d->pad_w - d->kw + 1;
+  const int OH = (d->in_h + 2 * d->pad_h - d->kh) / shw + 1, OW = (d->in_w + 2 * d->pad_w - d->kw) / shw + 1;
   if (OD < 1 || OH < 1 || OW < 1) return wg_fail(LISEC_ERR_BAD_CONFIG, "empty output");
   EncodeTiledFn encode = wg_encode_fn();
   if (!encode) return wg_fail(LISEC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
@@ -321,6 +323,7 @@ int32_t lisec_conv_wgrad_plan_create(const lisec_conv_desc* d, const void* x, co
     return wg_fail(LISEC_ERR_BAD_CONFIG, "wgrad: no room for two stages");
   }
   p.stride_d = d->stride_d;
+  p.stride_hw = shw;
   int t = 0;
   for (int kd = 0; kd < d->kd; ++kd)
     for (int kh = 0; kh < d->kh; ++kh)
@@ -338,8 +341,11 @@ int32_t lisec_conv_wgrad_plan_create(const lisec_conv_desc* d, const void* x, co
     const cuuint64_t W = d->in_w, H = d->in_h, D = d->in_d, B = d->batch;
     cuuint64_t dims[5] = {(cuuint64_t)C, W, H, D, B};
     cuuint64_t strides[4] = {(cuuint64_t)C * 2, W * C * 2, H * W * C * 2, D * H * W * C * 2};
-    cuuint32_t box[5] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, 1, 1};
-    CUresult r = encode(&pl->map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr,
+    // stride_hw = 2: the TMA walks W and H with an element stride of 2 — the box spans 2 * tile positions of the input and
+    // delivers the tile's 128 positions
+    cuuint32_t box[5] = {64, (cuuint32_t)(p.bw * shw), (cuuint32_t)(p.bh * shw), 1, 1};
+    cuuint32_t xstr[5] = {1, (cuuint32_t)shw, (cuuint32_t)shw, 1, 1};
+    CUresult r = encode(&pl->map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, xstr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {

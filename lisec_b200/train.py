@@ -107,14 +107,14 @@ class ConvWgrad:
     """dW of one convolution layer (lisec_conv_wgrad_plan_*, lisec_b200/csrc/wgrad.cu): x bf16 [B,D,H,W,C], dy bf16
     [B,OD,OH,OW,N] -> dw float32 [taps, N, C] (the forward plans' weight layout). Buffers are bound at construction."""
 
-    def __init__(self, x: torch.Tensor, dy: torch.Tensor, k, stride_d: int, pad, tile=(16, 8)):
+    def __init__(self, x: torch.Tensor, dy: torch.Tensor, k, stride_d: int, pad, tile=(16, 8), stride_hw: int = 1):
         if x.dtype != torch.bfloat16 or dy.dtype != torch.bfloat16 or not x.is_cuda or x.dim() != 5 or dy.dim() != 5:
             raise ValueError("x, dy: cuda bf16 [B, D, H, W, C]")
         self._lib = N.load()
         B, D, H, W, Cin = x.shape
         self.x, self.dy = x.contiguous(), dy.contiguous()
         self.desc = N.lisec_conv_desc(
-            batch=B, in_d=D, in_h=H, in_w=W, in_c=Cin, kd=k[0], kh=k[1], kw=k[2], stride_d=stride_d, stride_hw=1,
+            batch=B, in_d=D, in_h=H, in_w=W, in_c=Cin, kd=k[0], kh=k[1], kw=k[2], stride_d=stride_d, stride_hw=stride_hw,
             pad_d=pad[0], pad_h=pad[1], pad_w=pad[2], out_c=dy.shape[-1], n_tiles=1, shuffle=1, out_pitch=dy.shape[-1],
             out_ch_off=0, relu=0, out_dtype=N.LISEC_F32, tile_w=tile[0], tile_h=tile[1], m_tiles=1, in_dtype=N.LISEC_BF16,
             out_split=0, group_kh=0, reserved=0)
@@ -270,3 +270,86 @@ class BatchNormTrain:
         if st != N.LISEC_OK:
             raise N.LisecError(st, self._lib.lisec_bn_last_error().decode("utf-8", "replace"))
         return self.dx
+
+
+class ConvBnReluTrain:
+    """One addConv2DLayer / Conv3D + BN stage in TRAINING mode (model_training.py:191-208 under fit): convolution with
+    bias (tensor-core plan on a bf16 copy of the float32 master weights) -> training-mode BatchNormalization -> ReLU,
+    and its backward: BN backward -> weight gradient (conv_wgrad_kernel), bias gradient (column sums), data gradient
+    (forward plan on dz with flipped, transposed weights). stride 1 only so far. Master weights: w float32
+    [taps, N, C], bias / gamma / beta float32 [N] (views into FlatParameters in a full model)."""
+
+    def __init__(self, x: torch.Tensor, w, bias, gamma, beta, k, pad, relu=True, moving_mean=None, moving_var=None,
+                 need_dx=True, tile=None):
+        self._lib = N.load()
+        B, D, H, W, Cin = x.shape
+        taps, Nout, c2 = w.shape
+        if c2 != Cin or taps != k[0] * k[1] * k[2]:
+            raise ValueError("w does not match x / k")
+        dev = x.device
+        self.x, self.w, self.bias, self.k, self.pad = x, w, bias, tuple(k), tuple(pad)
+        OD, OH, OW = D + 2 * pad[0] - k[0] + 1, H + 2 * pad[1] - k[1] + 1, W + 2 * pad[2] - k[2] + 1
+        self.w16 = torch.empty((taps, Nout, Cin), dtype=torch.bfloat16, device=dev)
+        self.z = torch.empty((B, OD, OH, OW, Nout), dtype=torch.bfloat16, device=dev)
+        self.ones = torch.ones(Nout, dtype=torch.float32, device=dev)
+        if tile is None:
+            tile = (16, 8) if OW >= 16 else (8, 16)
+        self.desc = N.lisec_conv_desc(
+            batch=B, in_d=D, in_h=H, in_w=W, in_c=Cin, kd=k[0], kh=k[1], kw=k[2], stride_d=1, stride_hw=1, pad_d=pad[0],
+            pad_h=pad[1], pad_w=pad[2], out_c=Nout, n_tiles=1, shuffle=1, out_pitch=Nout, out_ch_off=0, relu=0,
+            out_dtype=N.LISEC_BF16, tile_w=tile[0], tile_h=tile[1], m_tiles=1, in_dtype=N.LISEC_BF16, out_split=0,
+            group_kh=0, reserved=0)
+        self.refresh_weights()
+        self.plan = C.c_void_p()
+        with torch.cuda.device(dev):
+            st = self._lib.lisec_conv_plan_create(C.byref(self.desc), C.c_void_p(x.data_ptr()),
+                                                  C.c_void_p(self.w16.data_ptr()), C.c_void_p(self.ones.data_ptr()),
+                                                  C.c_void_p(bias.data_ptr()), C.c_void_p(self.z.data_ptr()),
+                                                  C.byref(self.plan))
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_conv_last_error().decode("utf-8", "replace"))
+        self.bn = BatchNormTrain(self.z, gamma, beta, moving_mean, moving_var, relu=relu)
+        self.wgrad = ConvWgrad(x, self.bn.dx, k, 1, pad, tile=tile)  # dz lands in bn.dx
+        self.dgrad = ConvDgrad(self.bn.dx, w, k, pad) if need_dx else None
+        self.dbias = torch.empty(Nout, dtype=torch.float32, device=dev)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.x.device).cuda_stream)
+
+    def refresh_weights(self) -> None:
+        """After an optimizer step: the bf16 operand copies of the master weights."""
+        with torch.cuda.device(self.x.device):
+            st = self._lib.lisec_cast_f32_to_bf16(C.c_void_p(self.w.data_ptr()), self.w.numel(),
+                                                  C.c_void_p(self.w16.data_ptr()), self._stream())
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_train_last_error().decode("utf-8", "replace"))
+        if getattr(self, "dgrad", None) is not None:
+            self.dgrad.refresh_weights()
+
+    def forward(self) -> torch.Tensor:
+        with torch.cuda.device(self.x.device):
+            st = self._lib.lisec_conv_plan_run(self.plan, self._stream())
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_conv_last_error().decode("utf-8", "replace"))
+        return self.bn.forward()
+
+    def backward(self, dy: torch.Tensor):
+        """dy: gradient with respect to this stage's output. Returns dx (or None); dw / dbias / bn.dgamma / bn.dbeta hold
+        the parameter gradients afterwards."""
+        dz = self.bn.backward(dy)
+        self.dw = self.wgrad.run()
+        with torch.cuda.device(self.x.device):
+            st = self._lib.lisec_channel_sums(C.c_void_p(dz.data_ptr()), self.bn.P, self.bn.C,
+                                              C.c_void_p(self.dbias.data_ptr()), C.c_void_p(self.bn.workspace.data_ptr()),
+                                              self._stream())
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_bn_last_error().decode("utf-8", "replace"))
+        return self.dgrad.run() if self.dgrad is not None else None
+
+    def close(self):
+        if getattr(self, "plan", None):
+            self._lib.lisec_conv_plan_destroy(self.plan)
+            self.plan = None
+        self.wgrad.close()
+        if self.dgrad is not None:
+            self.dgrad.close()

@@ -112,6 +112,8 @@ def test_gpu_mse_loss_and_gradient():
     dict(B=2, D=1, H=24, W=40, C=128, N=128, k=(1, 3, 3), sd=1, pad=(0, 1, 1)),  # RPN 128 -> 128: 18 units, 3 passes
     dict(B=1, D=1, H=12, W=20, C=256, N=256, k=(1, 3, 3), sd=1, pad=(0, 1, 1)),  # RPN 256 -> 256: 9 passes
     dict(B=3, D=1, H=16, W=16, C=64, N=128, k=(1, 1, 1), sd=1, pad=(0, 0, 0)),   # 1x1: a single (half-used) pair
+    dict(B=2, D=1, H=24, W=40, C=64, N=128, k=(1, 3, 3), sd=1, pad=(0, 1, 1), shw=2),  # first conv of an RPN block: stride 2
+    dict(B=1, D=1, H=18, W=22, C=128, N=256, k=(1, 3, 3), sd=1, pad=(0, 1, 1), shw=2),
 ])
 def test_gpu_conv_wgrad_matches_autograd(case):
     """dW from conv_wgrad_kernel against torch CPU float64 autograd of the same convolution on the same bf16 tensors."""
@@ -123,17 +125,18 @@ def test_gpu_conv_wgrad_matches_autograd(case):
     g = torch.Generator(device="cpu").manual_seed(5)
     x = torch.randn((c["B"], c["D"], c["H"], c["W"], c["C"]), generator=g).to(torch.bfloat16)
     k = c["k"]
+    shw = c.get("shw", 1)
     OD = (c["D"] + 2 * c["pad"][0] - k[0]) // c["sd"] + 1
-    OH, OW = c["H"] + 2 * c["pad"][1] - k[1] + 1, c["W"] + 2 * c["pad"][2] - k[2] + 1
+    OH, OW = (c["H"] + 2 * c["pad"][1] - k[1]) // shw + 1, (c["W"] + 2 * c["pad"][2] - k[2]) // shw + 1
     dy = (torch.randn((c["B"], OD, OH, OW, c["N"]), generator=g) * 0.5).to(torch.bfloat16)
-    wg = ConvWgrad(x.cuda(), dy.cuda(), k, c["sd"], c["pad"])
+    wg = ConvWgrad(x.cuda(), dy.cuda(), k, c["sd"], c["pad"], stride_hw=shw)
     wg.dw.fill_(float("nan"))
     got = wg.run()
     torch.cuda.synchronize()
     got2 = wg.run().clone()  # a second launch: same bits (no atomics anywhere)
     torch.cuda.synchronize()
     w = torch.zeros((c["N"], c["C"]) + tuple(k), dtype=torch.float64, requires_grad=True)
-    y = F.conv3d(x.double().permute(0, 4, 1, 2, 3), w, None, stride=(c["sd"], 1, 1), padding=c["pad"])
+    y = F.conv3d(x.double().permute(0, 4, 1, 2, 3), w, None, stride=(c["sd"], shw, shw), padding=c["pad"])
     (y * dy.double().permute(0, 4, 1, 2, 3)).sum().backward()
     want = w.grad.permute(2, 3, 4, 0, 1).reshape(k[0] * k[1] * k[2], c["N"], c["C"])  # [tap][co][ci]
     got = got.cpu().double()
@@ -215,3 +218,61 @@ def test_gpu_batchnorm_train_forward_backward(shape, relu):
     assert (dx.double() - xd.grad).abs().max() <= 2.0 ** -8 * scale + 1e-6
     assert torch.allclose(bn.dgamma.cpu().double(), gd.grad, rtol=1e-5, atol=1e-4)
     assert torch.allclose(bn.dbeta.cpu().double(), bd.grad, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [
+    dict(B=2, D=1, H=24, W=40, C=128, N=128, k=(1, 3, 3), pad=(0, 1, 1)),  # addConv2DLayer(128, 128, 3, 1, 1)
+    dict(B=2, D=4, H=16, W=24, C=64, N=64, k=(3, 3, 3), pad=(0, 1, 1)),    # Conv3D + BN of the second middle block
+])
+def test_gpu_conv_bn_relu_layer_trains_like_autograd(case):
+    """One conv(bias) -> BN(train) -> ReLU stage, forward and backward, then one SGD-Nesterov step on its weights:
+    against torch float64 autograd from the same bf16 input and bf16-representable weights. The stage keeps the
+    convolution output and dz in bf16 (2^-9): agreement 2-4e-3 of each tensor's scale, bar 1e-2."""
+    import torch.nn.functional as F
+
+    from lisec_b200.train import ConvBnReluTrain
+
+    c = case
+    k, pad = c["k"], c["pad"]
+    g = torch.Generator(device="cpu").manual_seed(17)
+    x = torch.randn((c["B"], c["D"], c["H"], c["W"], c["C"]), generator=g).to(torch.bfloat16)
+    taps = k[0] * k[1] * k[2]
+    w = (torch.randn((taps, c["N"], c["C"]), generator=g) * (1.0 / np.sqrt(taps * c["C"]))).to(torch.bfloat16).float()
+    bias, beta = torch.randn(c["N"], generator=g) * 0.1, torch.randn(c["N"], generator=g) * 0.1
+    gamma = torch.rand(c["N"], generator=g) + 0.5
+    layer = ConvBnReluTrain(x.cuda(), w.cuda(), bias.cuda(), gamma.cuda(), beta.cuda(), k, pad)
+    y = layer.forward().float().cpu()
+    dy = torch.randn(y.shape, generator=g).to(torch.bfloat16)
+    dx = layer.backward(dy.cuda()).float().cpu()
+    torch.cuda.synchronize()
+
+    xd = x.double().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    wd = w.double().reshape(k[0], k[1], k[2], c["N"], c["C"]).permute(3, 4, 0, 1, 2).requires_grad_(True)
+    bd, gd, btd = bias.double().requires_grad_(True), gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    z = F.conv3d(xd, wd, bd, padding=pad)
+    mean = z.mean(dim=(0, 2, 3, 4), keepdim=True)
+    var = z.var(dim=(0, 2, 3, 4), unbiased=False, keepdim=True)
+    lin = (z - mean) / torch.sqrt(var + 1e-3) * gd.view(1, -1, 1, 1, 1) + btd.view(1, -1, 1, 1, 1)
+    yd = torch.relu(lin)
+    # ReLU's gradient is a step: where |lin| is within bf16 rounding of zero the stage's mask (from ITS y) may differ from
+    # float64's, an O(1) change at isolated elements that says nothing about the kernels — the reference takes the stage's mask
+    mask = (y > 0).double().permute(0, 4, 1, 2, 3)
+    assert float(((lin.detach() > 0).double() - mask).abs().mean()) < 5e-3
+    (lin * mask * dy.double().permute(0, 4, 1, 2, 3)).sum().backward()
+
+    def close(got, want, tol):
+        got, want = got.double(), want.double()
+        emax = float((got - want).abs().max()) / float(want.abs().max())
+        el2 = float(((got - want) ** 2).sum().sqrt() / (want ** 2).sum().sqrt())
+        print("max err / max |ref| = %.3e, rel-L2 = %.3e" % (emax, el2))
+        return emax <= tol and el2 <= tol / 2
+
+    assert close(y.permute(0, 4, 1, 2, 3), yd.detach(), 1e-2)
+    assert close(dx.permute(0, 4, 1, 2, 3), xd.grad, 1e-2)
+    want_dw = wd.grad.permute(2, 3, 4, 0, 1).reshape(taps, c["N"], c["C"])
+    assert close(layer.dw.cpu(), want_dw, 1e-2)
+    assert close(layer.bn.dgamma.cpu(), gd.grad, 1e-2) and close(layer.bn.dbeta.cpu(), btd.grad, 1e-2)
+    # a bias in front of a training-mode BN has no effect: its gradient is zero up to rounding
+    assert float(layer.dbias.abs().max()) <= 1e-2 * float(layer.bn.dbeta.abs().max()) and float(bd.grad.abs().max()) < 1e-9
+    layer.close()
