@@ -349,6 +349,13 @@ int32_t lisec_mse_loss_grad(const float* y, const float* target, int64_t n, floa
  * [kd*kh*kw][in_c][out_c]. */
 int32_t lisec_weights_flip_transpose(const float* w, int32_t kd, int32_t kh, int32_t kw, int32_t out_c, int32_t in_c,
                                      void* out_bf16, void* stream);
+/* [async] out = dy where y > 0, else 0 (bf16, n a multiple of 8): ReLU backward where no BatchNormalization precedes it. */
+int32_t lisec_relu_backward(const void* dy, const void* y, int64_t n, void* out, void* stream);
+/* [async] Zero-dilation of a bf16 gradient tensor [batch, d, h, w, channels] into out [batch, out_d, out_h, out_w,
+ * channels] (cleared once by the caller): element (d, h, w) lands at (d*stride_d, h*stride_hw, w*stride_hw). The data
+ * gradient of a strided convolution is the stride-1 data gradient of the dilated dy. */
+int32_t lisec_dilate(const void* in, int32_t batch, int32_t d, int32_t h, int32_t w, int32_t channels, int32_t stride_d,
+                     int32_t stride_hw, int32_t out_d, int32_t out_h, int32_t out_w, void* out, void* stream);
 /* [async] float32 master weights -> the bf16 operand copy the plans read. */
 int32_t lisec_cast_f32_to_bf16(const float* w, int64_t n, void* out_bf16, void* stream);
 const char* lisec_train_last_error(void);

@@ -109,6 +109,48 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = __float2bfloat16(w[i]);
 }
 
+// ReLU backward for stages whose ReLU does not sit behind a BatchNormalization (the Dense of a Conv3D block):
+// out = dy where y > 0, else 0 (bf16, 8 elements per thread)
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, long long n8,
+                                                       uint4* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    uint4 g = __ldcs(dy + i);
+    const uint4 v = __ldcs(y + i);
+    const __nv_bfloat16* yv = reinterpret_cast<const __nv_bfloat16*>(&v);
+    __nv_bfloat16* gv = reinterpret_cast<__nv_bfloat16*>(&g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (!(__bfloat162float(yv[k]) > 0.f)) gv[k] = __float2bfloat16(0.f);
+    out[i] = g;
+  }
+}
+
+// Zero-dilation of a gradient tensor: the data gradient of a STRIDED convolution is the stride-1 data gradient of dy with
+// (stride - 1) zeros between its positions (and k - 1 - pad zeros around it, which the plan's own padding provides).
+// out [B, (D-1)*sd+1 + ed, (H-1)*s+1 + eh, (W-1)*s+1 + ew, C] is cleared by the caller once; the zeros never change.
+__global__ void __launch_bounds__(256)
+    dilate_kernel(const uint4* __restrict__ in, int B, int D, int H, int W, int c8, int sd, int s, int OD, int OH, int OW,
+                  uint4* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long total = (long long)B * D * H * W * c8;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % c8);
+    long long r = i / c8;
+    const int w = (int)(r % W);
+    r /= W;
+    const int h = (int)(r % H);
+    r /= H;
+    const int d = (int)(r % D);
+    const int b = (int)(r / D);
+    out[((((long long)b * OD + (long long)d * sd) * OH + (long long)h * s) * OW + (long long)w * s) * c8 + c] = __ldcs(in + i);
+  }
+}
+
 thread_local char g_train_error[256] = "";
 
 int32_t train_fail(int32_t code, const char* fmt, ...) {
@@ -155,6 +197,33 @@ int32_t lisec_weights_flip_transpose(const float* w, int32_t kd, int32_t kh, int
   cudaError_t e = launch_pdl(flip_transpose_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0,
                              static_cast<cudaStream_t>(stream), w, (int)kd, (int)kh, (int)kw, (int)out_c, (int)in_c,
                              static_cast<__nv_bfloat16*>(out_bf16));
+  if (e != cudaSuccess) return train_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
+  return LISEC_OK;
+}
+
+int32_t lisec_relu_backward(const void* dy, const void* y, int64_t n, void* out, void* stream) {
+  if (n < 0 || n % 8 || (n > 0 && (!dy || !y || !out))) return train_fail(LISEC_ERR_BAD_ARG, "n must be a multiple of 8");
+  if (n == 0) return LISEC_OK;
+  long long blocks = (n / 8 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cudaError_t e = launch_pdl(relu_bwd_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                             static_cast<const uint4*>(dy), static_cast<const uint4*>(y), (long long)(n / 8),
+                             static_cast<uint4*>(out));
+  if (e != cudaSuccess) return train_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
+  return LISEC_OK;
+}
+
+int32_t lisec_dilate(const void* in, int32_t batch, int32_t d, int32_t h, int32_t w, int32_t channels, int32_t stride_d,
+                     int32_t stride_hw, int32_t out_d, int32_t out_h, int32_t out_w, void* out, void* stream) {
+  if (!in || !out || channels % 8 || batch < 1 || d < 1 || h < 1 || w < 1 || stride_d < 1 || stride_hw < 1 ||
+      out_d < (d - 1) * stride_d + 1 || out_h < (h - 1) * stride_hw + 1 || out_w < (w - 1) * stride_hw + 1)
+    return train_fail(LISEC_ERR_BAD_ARG, "dilate: bad shape");
+  const long long total = (long long)batch * d * h * w * (channels / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cudaError_t e = launch_pdl(dilate_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                             static_cast<const uint4*>(in), (int)batch, (int)d, (int)h, (int)w, (int)(channels / 8),
+                             (int)stride_d, (int)stride_hw, (int)out_d, (int)out_h, (int)out_w, static_cast<uint4*>(out));
   if (e != cudaSuccess) return train_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
   return LISEC_OK;
 }

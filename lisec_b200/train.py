@@ -353,3 +353,57 @@ class ConvBnReluTrain:
         self.wgrad.close()
         if self.dgrad is not None:
             self.dgrad.close()
+
+
+class ConvDgradStrided:
+    """dX of a STRIDED convolution layer (stride_d and / or stride_hw = 2): dy is zero-dilated (lisec_dilate) and goes
+    through the stride-1 data-gradient plan. in_dhw = (D, H, W) of the layer's input. First version: the plan multiplies
+    the inserted zeros too (2x / 4x the MACs); the phase-decomposed form is the optimisation to come."""
+
+    def __init__(self, dy: torch.Tensor, w: torch.Tensor, k, pad, stride_d: int, stride_hw: int, in_dhw,
+                 out_dtype=torch.bfloat16):
+        self._lib = N.load()
+        B, OD, OH, OW, Nout = dy.shape
+        sizes = []
+        for n_out, n_in, kk, pp, ss in ((OD, in_dhw[0], k[0], pad[0], stride_d), (OH, in_dhw[1], k[1], pad[1], stride_hw),
+                                        (OW, in_dhw[2], k[2], pad[2], stride_hw)):
+            if (n_in + 2 * pp - kk) // ss + 1 != n_out:
+                raise ValueError("dy does not match the layer's geometry")
+            sizes.append((n_out - 1) * ss + 1 + (n_in + 2 * pp - kk) % ss)
+        self.dy, self.sd, self.s = dy.contiguous(), stride_d, stride_hw
+        self.dilated = torch.zeros((B, sizes[0], sizes[1], sizes[2], Nout), dtype=torch.bfloat16, device=dy.device)
+        self.inner = ConvDgrad(self.dilated, w, k, pad, out_dtype=out_dtype)
+        if tuple(self.inner.dx.shape[1:4]) != tuple(in_dhw):
+            raise RuntimeError("dilated data gradient has shape %s, expected %s" % (tuple(self.inner.dx.shape[1:4]), tuple(in_dhw)))
+        self.dx = self.inner.dx
+
+    def refresh_weights(self) -> None:
+        self.inner.refresh_weights()
+
+    def run(self) -> torch.Tensor:
+        B, OD, OH, OW, Nout = self.dy.shape
+        _, D2, H2, W2, _ = self.dilated.shape
+        with torch.cuda.device(self.dy.device):
+            st = self._lib.lisec_dilate(C.c_void_p(self.dy.data_ptr()), B, OD, OH, OW, Nout, self.sd, self.s, D2, H2, W2,
+                                        C.c_void_p(self.dilated.data_ptr()),
+                                        C.c_void_p(torch.cuda.current_stream(self.dy.device).cuda_stream))
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_train_last_error().decode("utf-8", "replace"))
+        return self.inner.run()
+
+    def close(self):
+        self.inner.close()
+
+
+def relu_backward(dy: torch.Tensor, y: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dy masked by y > 0 (bf16): the ReLU behind the Dense of a Conv3D block (model_training.py:195)."""
+    if dy.dtype != torch.bfloat16 or y.dtype != torch.bfloat16 or dy.shape != y.shape or not dy.is_cuda:
+        raise ValueError("dy, y: cuda bf16 of one shape")
+    lib = N.load()
+    out = torch.empty_like(dy) if out is None else out
+    with torch.cuda.device(dy.device):
+        st = lib.lisec_relu_backward(C.c_void_p(dy.contiguous().data_ptr()), C.c_void_p(y.contiguous().data_ptr()), dy.numel(),
+                                     C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream(dy.device).cuda_stream))
+    if st != N.LISEC_OK:
+        raise N.LisecError(st, lib.lisec_train_last_error().decode("utf-8", "replace"))
+    return out

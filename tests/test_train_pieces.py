@@ -276,3 +276,39 @@ def test_gpu_conv_bn_relu_layer_trains_like_autograd(case):
     # a bias in front of a training-mode BN has no effect: its gradient is zero up to rounding
     assert float(layer.dbias.abs().max()) <= 1e-2 * float(layer.bn.dbeta.abs().max()) and float(bd.grad.abs().max()) < 1e-9
     layer.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [
+    dict(B=1, D=8, H=16, W=24, C=64, N=64, k=(3, 3, 3), pad=(1, 1, 1), sd=2, s=1),    # first / third Conv3D: stride 2 in depth
+    dict(B=2, D=1, H=24, W=40, C=64, N=128, k=(1, 3, 3), pad=(0, 1, 1), sd=1, s=2),   # first conv of an RPN block
+    dict(B=1, D=1, H=17, W=23, C=128, N=128, k=(1, 3, 3), pad=(0, 1, 1), sd=1, s=2),  # odd sizes: an untouched last row / column
+])
+def test_gpu_strided_conv_dgrad_matches_autograd(case):
+    import torch.nn.functional as F
+
+    from lisec_b200.train import ConvDgradStrided, relu_backward
+
+    c = case
+    k = c["k"]
+    g = torch.Generator(device="cpu").manual_seed(23)
+    OD = (c["D"] + 2 * c["pad"][0] - k[0]) // c["sd"] + 1
+    OH, OW = (c["H"] + 2 * c["pad"][1] - k[1]) // c["s"] + 1, (c["W"] + 2 * c["pad"][2] - k[2]) // c["s"] + 1
+    dy = torch.randn((c["B"], OD, OH, OW, c["N"]), generator=g).to(torch.bfloat16)
+    w = (torch.randn((k[0] * k[1] * k[2], c["N"], c["C"]), generator=g) * 0.05).to(torch.bfloat16).float()
+    dg = ConvDgradStrided(dy.cuda(), w.cuda(), k, c["pad"], c["sd"], c["s"], (c["D"], c["H"], c["W"]), out_dtype=torch.float32)
+    got = dg.run().cpu().double()
+    got2 = dg.run().cpu().double()  # the dilated buffer's zeros are still zeros
+    x = torch.zeros((c["B"], c["C"], c["D"], c["H"], c["W"]), dtype=torch.float64, requires_grad=True)
+    wt = w.double().reshape(k[0], k[1], k[2], c["N"], c["C"]).permute(3, 4, 0, 1, 2)
+    y = F.conv3d(x, wt, None, stride=(c["sd"], c["s"], c["s"]), padding=c["pad"])
+    (y * dy.double().permute(0, 4, 1, 2, 3)).sum().backward()
+    want = x.grad.permute(0, 2, 3, 4, 1)
+    assert got.shape == want.shape
+    assert (got - want).abs().max() / want.abs().max() <= 2e-5 and torch.equal(got, got2)
+    dg.close()
+    # ReLU backward
+    yy = torch.randn((3, 5, 64), generator=g).to(torch.bfloat16)
+    dd = torch.randn((3, 5, 64), generator=g).to(torch.bfloat16)
+    out = relu_backward(dd.cuda(), yy.cuda()).cpu()
+    assert torch.equal(out, torch.where(yy > 0, dd, torch.zeros_like(dd)))
