@@ -171,20 +171,26 @@ class ConvDgrad:
         self.wt = torch.empty((taps, Cin, Nout), dtype=torch.bfloat16, device=dy.device)
         self.scale = torch.ones(Cin, dtype=torch.float32, device=dy.device)
         self.shift = torch.zeros(Cin, dtype=torch.float32, device=dy.device)
-        if tile is None:
-            tile = (16, 8) if W >= 16 else (8, 16)
-        self.desc = N.lisec_conv_desc(
-            batch=B, in_d=OD, in_h=OH, in_w=OW, in_c=Nout, kd=k[0], kh=k[1], kw=k[2], stride_d=1, stride_hw=1,
-            pad_d=p2[0], pad_h=p2[1], pad_w=p2[2], out_c=Cin, n_tiles=1, shuffle=1, out_pitch=Cin, out_ch_off=0, relu=0,
-            out_dtype=N.LISEC_BF16 if out_dtype == torch.bfloat16 else N.LISEC_F32, tile_w=tile[0], tile_h=tile[1],
-            m_tiles=1, in_dtype=N.LISEC_BF16, out_split=0, group_kh=0, reserved=0)
         self.refresh_weights()
         self.plan = C.c_void_p()
-        with torch.cuda.device(dy.device):
-            st = self._lib.lisec_conv_plan_create(C.byref(self.desc), C.c_void_p(self.dy.data_ptr()),
-                                                  C.c_void_p(self.wt.data_ptr()), C.c_void_p(self.scale.data_ptr()),
-                                                  C.c_void_p(self.shift.data_ptr()), C.c_void_p(self.dx.data_ptr()),
-                                                  C.byref(self.plan))
+        # the halo plans (one input box per (kd, 64 channels) serves all nine taps, two M-tiles) where they apply, else a
+        # plain one-M-tile plan
+        cands = [((8, 16), 2, 2)] if (k[1] == 3 and k[2] == 3 and Cin <= 128 and tile is None) else []
+        cands.append((tile or ((16, 8) if W >= 16 else (8, 16)), 1, 0))
+        st = N.LISEC_ERR_BAD_CONFIG
+        for tl, mt, gk in cands:
+            self.desc = N.lisec_conv_desc(
+                batch=B, in_d=OD, in_h=OH, in_w=OW, in_c=Nout, kd=k[0], kh=k[1], kw=k[2], stride_d=1, stride_hw=1,
+                pad_d=p2[0], pad_h=p2[1], pad_w=p2[2], out_c=Cin, n_tiles=1, shuffle=1, out_pitch=Cin, out_ch_off=0,
+                relu=0, out_dtype=N.LISEC_BF16 if out_dtype == torch.bfloat16 else N.LISEC_F32, tile_w=tl[0],
+                tile_h=tl[1], m_tiles=mt, in_dtype=N.LISEC_BF16, out_split=0, group_kh=gk, reserved=0)
+            with torch.cuda.device(dy.device):
+                st = self._lib.lisec_conv_plan_create(C.byref(self.desc), C.c_void_p(self.dy.data_ptr()),
+                                                      C.c_void_p(self.wt.data_ptr()), C.c_void_p(self.scale.data_ptr()),
+                                                      C.c_void_p(self.shift.data_ptr()), C.c_void_p(self.dx.data_ptr()),
+                                                      C.byref(self.plan))
+            if st != N.LISEC_ERR_BAD_CONFIG:
+                break
         if st != N.LISEC_OK:
             raise N.LisecError(st, self._lib.lisec_conv_last_error().decode("utf-8", "replace"))
 
