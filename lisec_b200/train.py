@@ -413,3 +413,107 @@ def relu_backward(dy: torch.Tensor, y: torch.Tensor, out: Optional[torch.Tensor]
     if st != N.LISEC_OK:
         raise N.LisecError(st, lib.lisec_train_last_error().decode("utf-8", "replace"))
     return out
+
+
+class Conv3dBlockTrain:
+    """One addConv3DLayer block in TRAINING mode (model_training.py:191-196): ZeroPadding3D -> Conv3D(bias, stride (sd,1,1))
+    -> BatchNormalization (batch statistics) -> Dense(64, no bias) -> ReLU, forward and backward, from the pieces above.
+    Master weights: w [27, N, C], bias [N], gamma / beta [N], wd [1, N2, N] (the Dense kernel as a 1x1 convolution in the
+    plans' [tap][out][in] layout), all float32 on the device."""
+
+    def __init__(self, x: torch.Tensor, w, bias, gamma, beta, wd, k, pad, stride_d=1, moving_mean=None, moving_var=None,
+                 need_dx=True):
+        self._lib = N.load()
+        B, D, H, W, Cin = x.shape
+        taps, Nout, _ = w.shape
+        N2 = wd.shape[1]
+        dev = x.device
+        self.x, self.w, self.wd, self.bias = x, w, wd, bias
+        OD = (D + 2 * pad[0] - k[0]) // stride_d + 1
+        OH, OW = H + 2 * pad[1] - k[1] + 1, W + 2 * pad[2] - k[2] + 1
+        tile = (16, 8) if OW >= 16 else (8, 16)
+        self.w16 = torch.empty((taps, Nout, Cin), dtype=torch.bfloat16, device=dev)
+        self.wd16 = torch.empty((1, N2, Nout), dtype=torch.bfloat16, device=dev)
+        self.z = torch.empty((B, OD, OH, OW, Nout), dtype=torch.bfloat16, device=dev)
+        self.y = torch.empty((B, OD, OH, OW, N2), dtype=torch.bfloat16, device=dev)
+        self.dv = torch.empty_like(self.y)
+        self.ones = torch.ones(max(Nout, N2), dtype=torch.float32, device=dev)
+        self.zeros = torch.zeros(N2, dtype=torch.float32, device=dev)
+        self.bn = BatchNormTrain(self.z, gamma, beta, moving_mean, moving_var, relu=False)
+
+        def plan(src, wt, shift, dst, kk, pp, sd, cin, cout, relu):
+            desc = N.lisec_conv_desc(
+                batch=B, in_d=src.shape[1], in_h=src.shape[2], in_w=src.shape[3], in_c=cin, kd=kk[0], kh=kk[1], kw=kk[2],
+                stride_d=sd, stride_hw=1, pad_d=pp[0], pad_h=pp[1], pad_w=pp[2], out_c=cout, n_tiles=1, shuffle=1,
+                out_pitch=cout, out_ch_off=0, relu=relu, out_dtype=N.LISEC_BF16, tile_w=tile[0], tile_h=tile[1], m_tiles=1,
+                in_dtype=N.LISEC_BF16, out_split=0, group_kh=0, reserved=0)
+            h = C.c_void_p()
+            with torch.cuda.device(dev):
+                st = self._lib.lisec_conv_plan_create(C.byref(desc), C.c_void_p(src.data_ptr()), C.c_void_p(wt.data_ptr()),
+                                                      C.c_void_p(self.ones.data_ptr()), C.c_void_p(shift.data_ptr()),
+                                                      C.c_void_p(dst.data_ptr()), C.byref(h))
+            if st != N.LISEC_OK:
+                raise N.LisecError(st, self._lib.lisec_conv_last_error().decode("utf-8", "replace"))
+            return h
+
+        self._dgrads = []
+        self.refresh_weights()
+        self.conv_plan = plan(x, self.w16, bias, self.z, k, pad, stride_d, Cin, Nout, 0)
+        self.dense_plan = plan(self.bn.y, self.wd16, self.zeros, self.y, (1, 1, 1), (0, 0, 0), 1, Nout, N2, 1)
+        self.dense_wgrad = ConvWgrad(self.bn.y, self.dv, (1, 1, 1), 1, (0, 0, 0), tile=tile)
+        self.dense_dgrad = ConvDgrad(self.dv, wd, (1, 1, 1), (0, 0, 0))            # du: gradient at the BN output
+        self.conv_wgrad = ConvWgrad(x, self.bn.dx, k, stride_d, pad, tile=tile)    # dz lands in bn.dx
+        self.conv_dgrad = None
+        if need_dx:
+            self.conv_dgrad = (ConvDgrad(self.bn.dx, w, k, pad) if stride_d == 1 else
+                               ConvDgradStrided(self.bn.dx, w, k, pad, stride_d, 1, (D, H, W)))
+        self._dgrads = [self.dense_dgrad] + ([self.conv_dgrad] if self.conv_dgrad is not None else [])
+        self.dbias = torch.empty(Nout, dtype=torch.float32, device=dev)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.x.device).cuda_stream)
+
+    def refresh_weights(self) -> None:
+        with torch.cuda.device(self.x.device):
+            for src, dst in ((self.w, self.w16), (self.wd, self.wd16)):
+                st = self._lib.lisec_cast_f32_to_bf16(C.c_void_p(src.data_ptr()), src.numel(), C.c_void_p(dst.data_ptr()),
+                                                      self._stream())
+                if st != N.LISEC_OK:
+                    raise N.LisecError(st, self._lib.lisec_train_last_error().decode("utf-8", "replace"))
+        for dg in self._dgrads:
+            dg.refresh_weights()
+
+    def _run(self, plan):
+        with torch.cuda.device(self.x.device):
+            st = self._lib.lisec_conv_plan_run(plan, self._stream())
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_conv_last_error().decode("utf-8", "replace"))
+
+    def forward(self) -> torch.Tensor:
+        self._run(self.conv_plan)
+        self.bn.forward()
+        self._run(self.dense_plan)
+        return self.y
+
+    def backward(self, dy: torch.Tensor):
+        relu_backward(dy, self.y, out=self.dv)
+        self.dwd = self.dense_wgrad.run()
+        du = self.dense_dgrad.run()
+        dz = self.bn.backward(du)
+        self.dw = self.conv_wgrad.run()
+        with torch.cuda.device(self.x.device):
+            st = self._lib.lisec_channel_sums(C.c_void_p(dz.data_ptr()), self.bn.P, self.bn.C,
+                                              C.c_void_p(self.dbias.data_ptr()), C.c_void_p(self.bn.workspace.data_ptr()),
+                                              self._stream())
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_bn_last_error().decode("utf-8", "replace"))
+        return self.conv_dgrad.run() if self.conv_dgrad is not None else None
+
+    def close(self):
+        for h in ("conv_plan", "dense_plan"):
+            if getattr(self, h, None):
+                self._lib.lisec_conv_plan_destroy(getattr(self, h))
+                setattr(self, h, None)
+        for o in (self.dense_wgrad, self.conv_wgrad, self.dense_dgrad, self.conv_dgrad):
+            if o is not None:
+                o.close()

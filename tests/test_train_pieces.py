@@ -312,3 +312,50 @@ def test_gpu_strided_conv_dgrad_matches_autograd(case):
     dd = torch.randn((3, 5, 64), generator=g).to(torch.bfloat16)
     out = relu_backward(dd.cuda(), yy.cuda()).cpu()
     assert torch.equal(out, torch.where(yy > 0, dd, torch.zeros_like(dd)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sd,pad,D", [(2, (1, 1, 1), 8), (1, (0, 1, 1), 4)])
+def test_gpu_conv3d_block_trains_like_autograd(sd, pad, D):
+    """addConv3DLayer in training mode — Conv3D(bias) -> BN(batch statistics) -> Dense(64, no bias) -> ReLU — forward and
+    backward against torch float64 autograd (the ReLU mask taken from the stage's own output, see the Conv2D test)."""
+    import torch.nn.functional as F
+
+    from lisec_b200.train import Conv3dBlockTrain
+
+    g = torch.Generator(device="cpu").manual_seed(29)
+    B, H, W, Cn = 2, 16, 24, 64
+    k = (3, 3, 3)
+    x = torch.randn((B, D, H, W, Cn), generator=g).to(torch.bfloat16)
+    w = (torch.randn((27, Cn, Cn), generator=g) / np.sqrt(27 * Cn)).to(torch.bfloat16).float()
+    wd = (torch.randn((1, Cn, Cn), generator=g) / np.sqrt(Cn)).to(torch.bfloat16).float()
+    bias, beta = torch.randn(Cn, generator=g) * 0.1, torch.randn(Cn, generator=g) * 0.1
+    gamma = torch.rand(Cn, generator=g) + 0.5
+    blk = Conv3dBlockTrain(x.cuda(), w.cuda(), bias.cuda(), gamma.cuda(), beta.cuda(), wd.cuda(), k, pad, stride_d=sd)
+    y = blk.forward().float().cpu()
+    dy = torch.randn(y.shape, generator=g).to(torch.bfloat16)
+    dx = blk.backward(dy.cuda()).float().cpu()
+    torch.cuda.synchronize()
+
+    xd = x.double().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    wv = w.double().reshape(3, 3, 3, Cn, Cn).permute(3, 4, 0, 1, 2).requires_grad_(True)
+    wdv = wd.double()[0].requires_grad_(True)  # [out][in]
+    gd, btd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    z = F.conv3d(xd, wv, bias.double(), stride=(sd, 1, 1), padding=pad)
+    mean, var = z.mean(dim=(0, 2, 3, 4), keepdim=True), z.var(dim=(0, 2, 3, 4), unbiased=False, keepdim=True)
+    u = (z - mean) / torch.sqrt(var + 1e-3) * gd.view(1, -1, 1, 1, 1) + btd.view(1, -1, 1, 1, 1)
+    lin = torch.einsum("ncdhw,kc->nkdhw", u, wdv)
+    mask = (y > 0).double().permute(0, 4, 1, 2, 3)
+    assert float(((lin.detach() > 0).double() - mask).abs().mean()) < 5e-3
+    (lin * mask * dy.double().permute(0, 4, 1, 2, 3)).sum().backward()
+
+    def close(got, want, tol=1e-2):
+        got, want = got.double(), want.double()
+        return float((got - want).abs().max()) <= tol * float(want.abs().max())
+
+    assert close(y.permute(0, 4, 1, 2, 3), torch.relu(lin.detach()))
+    assert close(dx.permute(0, 4, 1, 2, 3), xd.grad)
+    assert close(blk.dw.cpu(), wv.grad.permute(2, 3, 4, 0, 1).reshape(27, Cn, Cn))
+    assert close(blk.dwd.cpu()[0], wdv.grad)
+    assert close(blk.bn.dgamma.cpu(), gd.grad) and close(blk.bn.dbeta.cpu(), btd.grad)
+    blk.close()
