@@ -282,11 +282,11 @@ class ConvBnReluTrain:
     """One addConv2DLayer / Conv3D + BN stage in TRAINING mode (model_training.py:191-208 under fit): convolution with
     bias (tensor-core plan on a bf16 copy of the float32 master weights) -> training-mode BatchNormalization -> ReLU,
     and its backward: BN backward -> weight gradient (conv_wgrad_kernel), bias gradient (column sums), data gradient
-    (forward plan on dz with flipped, transposed weights). stride 1 only so far. Master weights: w float32
+    (forward plan on dz with flipped, transposed weights; zero-dilated dz for the stride-2 layers). Master weights: w float32
     [taps, N, C], bias / gamma / beta float32 [N] (views into FlatParameters in a full model)."""
 
     def __init__(self, x: torch.Tensor, w, bias, gamma, beta, k, pad, relu=True, moving_mean=None, moving_var=None,
-                 need_dx=True, tile=None):
+                 need_dx=True, tile=None, stride_hw: int = 1):
         self._lib = N.load()
         B, D, H, W, Cin = x.shape
         taps, Nout, c2 = w.shape
@@ -294,14 +294,15 @@ class ConvBnReluTrain:
             raise ValueError("w does not match x / k")
         dev = x.device
         self.x, self.w, self.bias, self.k, self.pad = x, w, bias, tuple(k), tuple(pad)
-        OD, OH, OW = D + 2 * pad[0] - k[0] + 1, H + 2 * pad[1] - k[1] + 1, W + 2 * pad[2] - k[2] + 1
+        s = stride_hw
+        OD, OH, OW = D + 2 * pad[0] - k[0] + 1, (H + 2 * pad[1] - k[1]) // s + 1, (W + 2 * pad[2] - k[2]) // s + 1
         self.w16 = torch.empty((taps, Nout, Cin), dtype=torch.bfloat16, device=dev)
         self.z = torch.empty((B, OD, OH, OW, Nout), dtype=torch.bfloat16, device=dev)
         self.ones = torch.ones(Nout, dtype=torch.float32, device=dev)
         if tile is None:
             tile = (16, 8) if OW >= 16 else (8, 16)
         self.desc = N.lisec_conv_desc(
-            batch=B, in_d=D, in_h=H, in_w=W, in_c=Cin, kd=k[0], kh=k[1], kw=k[2], stride_d=1, stride_hw=1, pad_d=pad[0],
+            batch=B, in_d=D, in_h=H, in_w=W, in_c=Cin, kd=k[0], kh=k[1], kw=k[2], stride_d=1, stride_hw=s, pad_d=pad[0],
             pad_h=pad[1], pad_w=pad[2], out_c=Nout, n_tiles=1, shuffle=1, out_pitch=Nout, out_ch_off=0, relu=0,
             out_dtype=N.LISEC_BF16, tile_w=tile[0], tile_h=tile[1], m_tiles=1, in_dtype=N.LISEC_BF16, out_split=0,
             group_kh=0, reserved=0)
@@ -315,8 +316,10 @@ class ConvBnReluTrain:
         if st != N.LISEC_OK:
             raise N.LisecError(st, self._lib.lisec_conv_last_error().decode("utf-8", "replace"))
         self.bn = BatchNormTrain(self.z, gamma, beta, moving_mean, moving_var, relu=relu)
-        self.wgrad = ConvWgrad(x, self.bn.dx, k, 1, pad, tile=tile)  # dz lands in bn.dx
-        self.dgrad = ConvDgrad(self.bn.dx, w, k, pad) if need_dx else None
+        self.wgrad = ConvWgrad(x, self.bn.dx, k, 1, pad, tile=tile, stride_hw=s)  # dz lands in bn.dx
+        self.dgrad = None
+        if need_dx:
+            self.dgrad = ConvDgrad(self.bn.dx, w, k, pad) if s == 1 else ConvDgradStrided(self.bn.dx, w, k, pad, 1, s, (D, H, W))
         self.dbias = torch.empty(Nout, dtype=torch.float32, device=dev)
 
     def _stream(self):

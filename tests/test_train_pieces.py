@@ -224,6 +224,7 @@ def test_gpu_batchnorm_train_forward_backward(shape, relu):
 @pytest.mark.parametrize("case", [
     dict(B=2, D=1, H=24, W=40, C=128, N=128, k=(1, 3, 3), pad=(0, 1, 1)),  # addConv2DLayer(128, 128, 3, 1, 1)
     dict(B=2, D=4, H=16, W=24, C=64, N=64, k=(3, 3, 3), pad=(0, 1, 1)),    # Conv3D + BN of the second middle block
+    dict(B=2, D=1, H=32, W=48, C=64, N=128, k=(1, 3, 3), pad=(0, 1, 1), s=2),  # addConv2DLayer(64, 128, 3, 2, 1): stride 2
 ])
 def test_gpu_conv_bn_relu_layer_trains_like_autograd(case):
     """One conv(bias) -> BN(train) -> ReLU stage, forward and backward, then one SGD-Nesterov step on its weights:
@@ -241,7 +242,8 @@ def test_gpu_conv_bn_relu_layer_trains_like_autograd(case):
     w = (torch.randn((taps, c["N"], c["C"]), generator=g) * (1.0 / np.sqrt(taps * c["C"]))).to(torch.bfloat16).float()
     bias, beta = torch.randn(c["N"], generator=g) * 0.1, torch.randn(c["N"], generator=g) * 0.1
     gamma = torch.rand(c["N"], generator=g) + 0.5
-    layer = ConvBnReluTrain(x.cuda(), w.cuda(), bias.cuda(), gamma.cuda(), beta.cuda(), k, pad)
+    shw = c.get("s", 1)
+    layer = ConvBnReluTrain(x.cuda(), w.cuda(), bias.cuda(), gamma.cuda(), beta.cuda(), k, pad, stride_hw=shw)
     y = layer.forward().float().cpu()
     dy = torch.randn(y.shape, generator=g).to(torch.bfloat16)
     dx = layer.backward(dy.cuda()).float().cpu()
@@ -250,7 +252,7 @@ def test_gpu_conv_bn_relu_layer_trains_like_autograd(case):
     xd = x.double().permute(0, 4, 1, 2, 3).requires_grad_(True)
     wd = w.double().reshape(k[0], k[1], k[2], c["N"], c["C"]).permute(3, 4, 0, 1, 2).requires_grad_(True)
     bd, gd, btd = bias.double().requires_grad_(True), gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
-    z = F.conv3d(xd, wd, bd, padding=pad)
+    z = F.conv3d(xd, wd, bd, stride=(1, shw, shw), padding=pad)
     mean = z.mean(dim=(0, 2, 3, 4), keepdim=True)
     var = z.var(dim=(0, 2, 3, 4), unbiased=False, keepdim=True)
     lin = (z - mean) / torch.sqrt(var + 1e-3) * gd.view(1, -1, 1, 1, 1) + btd.view(1, -1, 1, 1, 1)
