@@ -384,7 +384,7 @@ const char* lisec_bn_last_error(void);
 /* Weight gradient of one convolution layer on the tensor cores (lisec_b200/csrc/wgrad.cu) — the first backward kernel:
  *   dw[tap][co][ci] = sum over output positions p of dy[p][co] * x[p * stride + tap - pad][ci]
  * `desc` describes the FORWARD convolution (geometry fields, tile_w x tile_h = 128 positions; first version: bf16,
- * stride_hw = 1, in_c and out_c multiples of 64 and <= 256, n_tiles = shuffle = 1). Device pointers:
+ * stride_hw 1 or 2, in_c and out_c multiples of 64, out_c <= 256, in_c <= 1024, n_tiles = shuffle = 1). Device pointers:
  *   x   bf16 [batch, in_d, in_h, in_w, in_c]      the layer's input
  *   dy  bf16 [batch, out_d, out_h, out_w, out_c]  the gradient with respect to the convolution's output
  *   dw  float32 [kd*kh*kw][out_c][in_c]           the layout the forward plans read their weights in

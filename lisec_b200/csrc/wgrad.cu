@@ -37,7 +37,6 @@ namespace {
 
 constexpr int kWgThreads = 192;
 constexpr int kWgMaxStages = 4;
-constexpr int kWgMaxUnits = 27 * 4;  // 27 taps x 256 input channels
 constexpr uint32_t kBox = 128 * 128;  // one [128 positions][64 channels] bf16 box
 
 struct WgradParams {
@@ -287,7 +286,8 @@ int32_t lisec_conv_wgrad_plan_create(const lisec_conv_desc* d, const void* x, co
   const int C = d->in_c, N = d->out_c, taps = d->kd * d->kh * d->kw;
   const int shw = d->stride_hw;
   if (shw != 1 && shw != 2) return wg_fail(LISEC_ERR_UNSUPPORTED, "wgrad: stride_hw 1 or 2");
-  if (C % 64 || N % 64 || N > 256 || C > 256) return wg_fail(LISEC_ERR_BAD_CONFIG, "wgrad: in_c, out_c multiples of 64, <= 256");
+  if (C % 64 || N % 64 || N > 256 || C > 1024)
+    return wg_fail(LISEC_ERR_BAD_CONFIG, "wgrad: in_c, out_c multiples of 64; out_c <= 256, in_c <= 1024");
   if (taps > 27 || taps < 1) return wg_fail(LISEC_ERR_BAD_CONFIG, "wgrad: at most 27 taps");
   if (d->tile_w * d->tile_h != 128 || d->tile_w < 8 || (d->tile_w & (d->tile_w - 1)))
     return wg_fail(LISEC_ERR_BAD_CONFIG, "wgrad: tile_w * tile_h = 128, tile_w a power of two >= 8");
