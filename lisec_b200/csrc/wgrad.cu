@@ -12,7 +12,8 @@
 // Work decomposition. A "unit" is one (filter tap, 64-input-channel block): one X box per tile. Two units stacked make
 // the M = 128 rows of an MMA; N = all output channels (<= 256). A pair's accumulator D[128][N] lives in TMEM for a whole
 // PASS over the CTA's tiles (512 columns hold 512 / N pairs); a layer needs ceil(pairs / (512 / N)) passes. Per (pass,
-// tile, pair) one shared-memory stage carries [X unit a][X unit b][dY: N / 64 boxes] and feeds 8 MMAs (128 positions).
+// tile) the dY boxes (N / 64 of them) land once in one of two dY slots and are shared by the pass's pairs; per pair one
+// shared-memory stage carries [X unit a][X unit b] and feeds 8 MMAs (128 positions).
 // Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue: at the end of a pass they move the accumulators to
 // this CTA's slice of a float32 partial buffer [grid][taps][N][C]; wgrad_reduce_kernel then adds the slices in a fixed
 // order (deterministic — no atomics), giving dW in the layout the forward plans read their weights in.
@@ -36,7 +37,7 @@ namespace lisec {
 namespace {
 
 constexpr int kWgThreads = 192;
-constexpr int kWgMaxStages = 4;
+constexpr int kWgMaxStages = 6;
 constexpr uint32_t kBox = 128 * 128;  // one [128 positions][64 channels] bf16 box
 
 struct WgradParams {
@@ -44,7 +45,8 @@ struct WgradParams {
   long long total_tiles;
   int bw, bh;
   int units, pairs, pairs_per_pass, passes, nb, N, C, taps, stages;
-  uint32_t stage_bytes;
+  uint32_t stage_bytes;  // one X stage: two boxes
+  uint32_t dy_bytes;     // one dY slot: nb boxes (two slots, loaded once per tile and shared by the pass's pairs)
   int stride_d, stride_hw;
   signed char t1[27], t2[27], t3[27];  // X box origin of a tap relative to the tile origin (w, h, d)
   float* partial;  // [grid][taps][N][C]
@@ -66,6 +68,16 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a, uint64_t b
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
       "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// the same MMA with the descriptors as (low word, shared high word): the operand address lives in the low 14 bits of the
+// low word, so a K step is a 32-bit add (the issuing thread's instruction stream paces small MMAs)
+__device__ __forceinline__ void mma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                            uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(acc)
       : "memory");
 }
 // MN-major SWIZZLE_128B operand: 8 k-rows per 1 KB group (stride byte offset), 64-channel boxes `lbo` bytes apart
@@ -101,17 +113,25 @@ __global__ void __launch_bounds__(kWgThreads, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = umma::smem_u32(smem);
   if (base & 1023u) __trap();
-  const uint32_t bar0 = base + (uint32_t)P.stages * P.stage_bytes;
+  const uint32_t dy0 = base + (uint32_t)P.stages * P.stage_bytes;  // the two dY slots sit behind the X stages
+  const uint32_t bar0 = dy0 + 2u * P.dy_bytes;
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
   auto bar_empty = [&](int s) { return bar0 + 8u * (kWgMaxStages + s); };
-  const uint32_t bar_acc_full = bar0 + 8u * (2 * kWgMaxStages), bar_acc_empty = bar_acc_full + 8u;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (size_t)P.stages * P.stage_bytes + 8 * (2 * kWgMaxStages + 2));
+  auto bar_dy_full = [&](int s) { return bar0 + 8u * (2 * kWgMaxStages + s); };
+  auto bar_dy_empty = [&](int s) { return bar0 + 8u * (2 * kWgMaxStages + 2 + s); };
+  const uint32_t bar_acc_full = bar0 + 8u * (2 * kWgMaxStages + 4), bar_acc_empty = bar_acc_full + 8u;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (size_t)P.stages * P.stage_bytes + 2 * (size_t)P.dy_bytes +
+                                                    8 * (2 * kWgMaxStages + 6));
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
     for (int s = 0; s < P.stages; ++s) {
       umma::mbar_init(bar_full(s), 1);
       umma::mbar_init(bar_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      umma::mbar_init(bar_dy_full(s), 1);
+      umma::mbar_init(bar_dy_empty(s), 1);
     }
     umma::mbar_init(bar_acc_full, 1);
     umma::mbar_init(bar_acc_empty, 4);
@@ -127,12 +147,17 @@ __global__ void __launch_bounds__(kWgThreads, 1)
   const int cblocks = P.C / 64;
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
-      int s = 0;
-      uint32_t ph = 0;
+      int s = 0, ds = 0;
+      uint32_t ph = 0, dph = 0;
       for (int pass = 0; pass < P.passes; ++pass) {
         const int pair0 = pass * P.pairs_per_pass, pair1 = min(P.pairs, pair0 + P.pairs_per_pass);
         for (long long tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
           const WgTile t = wg_tile(P, tile);
+          umma::mbar_wait(bar_dy_empty(ds), dph ^ 1u);  // dY: once per tile, shared by every pair of the pass
+          mbar_arrive_expect_tx(bar_dy_full(ds), P.dy_bytes);
+          for (int n = 0; n < P.nb; ++n)
+            tma_load_5d(dy0 + (uint32_t)ds * P.dy_bytes + n * kBox, &map_dy, bar_dy_full(ds), 64 * n, t.ow0, t.oh0, t.od, t.b);
+          if (++ds == 2) { ds = 0; dph ^= 1u; }
           for (int pair = pair0; pair < pair1; ++pair) {
             umma::mbar_wait(bar_empty(s), ph ^ 1u);
             mbar_arrive_expect_tx(bar_full(s), P.stage_bytes);
@@ -143,8 +168,6 @@ __global__ void __launch_bounds__(kWgThreads, 1)
               tma_load_5d(dst + h * kBox, &map_x, bar_full(s), 64 * cb, t.ow0 * P.stride_hw + P.t1[tap],
                           t.oh0 * P.stride_hw + P.t2[tap], t.od * P.stride_d + P.t3[tap], t.b);
             }
-            for (int n = 0; n < P.nb; ++n)
-              tma_load_5d(dst + (2 + n) * kBox, &map_dy, bar_full(s), 64 * n, t.ow0, t.oh0, t.od, t.b);
             if (++s == P.stages) { s = 0; ph ^= 1u; }
           }
         }
@@ -155,26 +178,32 @@ __global__ void __launch_bounds__(kWgThreads, 1)
       // kind::f16, bf16 x bf16 -> f32, a_major = b_major = MN, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(P.N >> 3) << 17) |
                              ((128u >> 4) << 24);
-      int s = 0;
-      uint32_t ph = 0, acc_ph = 0;
+      const uint64_t proto = make_desc_mn(0, kBox);
+      const uint32_t lo0 = (uint32_t)proto, hi = (uint32_t)(proto >> 32);
+      int s = 0, ds = 0;
+      uint32_t ph = 0, dph = 0, acc_ph = 0;
       for (int pass = 0; pass < P.passes; ++pass) {
         const int pair0 = pass * P.pairs_per_pass, pair1 = min(P.pairs, pair0 + P.pairs_per_pass);
         umma::mbar_wait(bar_acc_empty, acc_ph ^ 1u);  // the epilogue has drained the previous pass
         umma::fence_after_sync();
         bool first_tile = true;
         for (long long tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+          umma::mbar_wait(bar_dy_full(ds), dph);
+          const uint32_t b0 = dy0 + (uint32_t)ds * P.dy_bytes;
           for (int pair = pair0; pair < pair1; ++pair) {
             umma::mbar_wait(bar_full(s), ph);
             umma::fence_after_sync();
-            const uint32_t a0 = base + (uint32_t)s * P.stage_bytes, b0 = a0 + 2 * kBox;
+            const uint32_t a0 = base + (uint32_t)s * P.stage_bytes;
             const uint32_t d = tmem_base + (uint32_t)((pair - pair0) * P.N);
+            const uint32_t a_lo = lo0 + (a0 >> 4), b_lo = lo0 + (b0 >> 4);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              mma_bf16(d, make_desc_mn(a0 + 2048u * j, kBox), make_desc_mn(b0 + 2048u * j, kBox), idesc,
-                       (first_tile && j == 0) ? 0u : 1u);
+              mma_bf16_lo(d, a_lo + 128u * j, b_lo + 128u * j, hi, idesc, (first_tile && j == 0) ? 0u : 1u);
             umma::mma_commit(bar_empty(s));
             if (++s == P.stages) { s = 0; ph ^= 1u; }
           }
+          umma::mma_commit(bar_dy_empty(ds));  // every MMA that reads this dY slot has been issued
+          if (++ds == 2) { ds = 0; dph ^= 1u; }
           first_tile = false;
         }
         umma::mma_commit(bar_acc_full);
@@ -315,8 +344,9 @@ int32_t lisec_conv_wgrad_plan_create(const lisec_conv_desc* d, const void* x, co
   p.pairs = (p.units + 1) / 2;
   p.pairs_per_pass = 512 / N;
   p.passes = (p.pairs + p.pairs_per_pass - 1) / p.pairs_per_pass;
-  p.stage_bytes = (uint32_t)(2 + p.nb) * kBox;
-  p.stages = (int)((200u * 1024u) / p.stage_bytes);
+  p.stage_bytes = 2u * kBox;
+  p.dy_bytes = (uint32_t)p.nb * kBox;
+  p.stages = (int)((200u * 1024u - 2u * p.dy_bytes) / p.stage_bytes);
   if (p.stages > kWgMaxStages) p.stages = kWgMaxStages;
   if (p.stages < 2) {
     delete pl;
@@ -335,7 +365,7 @@ int32_t lisec_conv_wgrad_plan_create(const lisec_conv_desc* d, const void* x, co
   p.partial = workspace;
   p.slice = (long long)taps * N * C;
   pl->dw = dw;
-  pl->smem = p.stages * (int)p.stage_bytes + 8 * (2 * kWgMaxStages + 2) + 16;
+  pl->smem = p.stages * (int)p.stage_bytes + 2 * (int)p.dy_bytes + 8 * (2 * kWgMaxStages + 6) + 16;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   {
     const cuuint64_t W = d->in_w, H = d->in_h, D = d->in_d, B = d->batch;
