@@ -11,7 +11,8 @@
 // 32-bit types; probe variants 0/1, whose helpers live in the probe) — not used here. For bf16 the plain MN-major
 // SWIZZLE_128B layout works as the canonical form says (tools/umma_mn_probe.cu, exact on B200): a TMA box [k rows][64
 // channels] IS an MN-major operand — instruction descriptor bits 15/16 (a_major/b_major) = 1, stride byte offset 1024
-// (8 k-rows), leading byte offset = distance between 64-channel boxes, one K = 16 step = +2048 bytes. This is what the
+// (8 k-rows), leading byte offset = distance between 64-channel boxes, one K = 16 step = +2048 bytes, and the K rows may
+// start at any row of the box (row shifts 1, 3, 19 exact: the swizzle follows the absolute address). This is what the
 // weight-gradient GEMM of the training step will read.
 #pragma once
 

@@ -16,7 +16,8 @@
 using namespace lisec::umma;
 
 constexpr int KP = 64;                      // positions (K)
-constexpr int BOX = KP * 128;               // bytes of one [KP][64] bf16 box
+constexpr int AROWS = KP + 32;              // the A boxes are taller: the K rows may start at any row `shift` of them
+constexpr int BOX = AROWS * 128;            // bytes of one [AROWS][64] bf16 box (B uses the first KP rows of its boxes)
 __host__ __device__ inline float a_val(int k, int m) { return (float)((k * 5 + m * 3) % 7); }
 __host__ __device__ inline float b_val(int k, int n) { return (float)((k * 3 + n * 11) % 5) - 2.f; }
 
@@ -43,17 +44,17 @@ __device__ inline void put(__nv_bfloat16* base, int k, int mn, float v) {
   base[box * (BOX / 2) + k * 64 + ((((c >> 3) ^ (k & 7)) << 3) | (c & 7))] = __float2bfloat16(v);
 }
 
-__global__ void __launch_bounds__(128, 1) probe(int lbo, int sbo, int kstep, float* out) {
+__global__ void __launch_bounds__(128, 1) probe(int lbo, int sbo, int kstep, int shift, float* out) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __nv_bfloat16* A = reinterpret_cast<__nv_bfloat16*>(smem);            // two boxes
   __nv_bfloat16* B = reinterpret_cast<__nv_bfloat16*>(smem + 2 * BOX);  // two boxes
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 4 * BOX);
   uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
   const uint32_t base = smem_u32(smem);
-  for (int i = threadIdx.x; i < KP * 128; i += 128) {
+  for (int i = threadIdx.x; i < AROWS * 128; i += 128) {
     const int k = i >> 7, mn = i & 127;
-    put(A, k, mn, a_val(k, mn));
-    put(B, k, mn, b_val(k, mn));
+    put(A, k, mn, a_val(k, mn));          // row k of the A boxes holds "position" k; the MMA reads rows shift .. shift + KP - 1
+    if (k < KP) put(B, k, mn, b_val(k, mn));
   }
   fence_async_smem();
   if (threadIdx.x == 0) {
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(128, 1) probe(int lbo, int sbo, int kstep, flo
     // kind::f16, bf16 x bf16 -> f32, a_major = b_major = MN (bits 15, 16), N = 128, M = 128
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
     for (int j = 0; j < KP / 16; ++j)
-      mma_bf16(tmem, make_desc(base + kstep * j, lbo, sbo), make_desc(base + 2 * BOX + kstep * j, lbo, sbo), idesc, j != 0);
+      mma_bf16(tmem, make_desc(base + shift * 128 + kstep * j, lbo, sbo), make_desc(base + 2 * BOX + kstep * j, lbo, sbo), idesc, j != 0);
     mma_commit(smem_u32(bar));
   }
   mbar_wait(smem_u32(bar), 0);
@@ -91,17 +92,25 @@ int main() {
   const int smem = 4 * BOX + 64;
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   std::vector<float> h(128 * 128), want(128 * 128);
-  for (int m = 0; m < 128; ++m)
-    for (int n = 0; n < 128; ++n) {
-      float s = 0.f;
-      for (int k = 0; k < KP; ++k) s += a_val(k, m) * b_val(k, n);
-      want[m * 128 + n] = s;
-    }
+  auto reference = [&](int shift) {
+    for (int m = 0; m < 128; ++m)
+      for (int n = 0; n < 128; ++n) {
+        float s = 0.f;
+        for (int k = 0; k < KP; ++k) s += a_val(shift + k, m) * b_val(k, n);
+        want[m * 128 + n] = s;
+      }
+  };
   // Measured on B200: the first line is exact (16384 / 16384); the others are not. (Candidates that step past the
   // operand, e.g. SBO = 2048, fault — they are not in the list.)
   const int cands[][3] = {{BOX, 1024, 2048}, {1024, BOX, 2048}, {BOX, 1024, 256}, {1024, BOX, 256}};
+  // row shifts: 0 (aligned), 8 (a whole swizzle atom), and starts in the middle of an atom — what reusing one haloed X
+  // box across the (kh, kw) taps of the weight gradient needs (as conv_halo_kernel does for the K-major forward operand)
+  const int shifts[] = {0, 8, 1, 3, 19};
+  for (int shift : shifts)
   for (auto& c : cands) {
-    probe<<<1, 128, smem>>>(c[0], c[1], c[2], d);
+    if (shift && &c != &cands[0]) continue;
+    reference(shift);
+    probe<<<1, 128, smem>>>(c[0], c[1], c[2], shift, d);
     if (cudaDeviceSynchronize() != cudaSuccess) {
       printf("lbo %5d sbo %5d kstep %4d: CUDA error %s\n", c[0], c[1], c[2], cudaGetErrorString(cudaGetLastError()));
       return 1;
@@ -114,8 +123,8 @@ int main() {
         ok += e;
         q[(m >> 6) * 2 + (n >> 6)] += e;
       }
-    printf("LBO %5d  SBO %5d  k-step %4d B : %5d / 16384 exact  (quadrants m<64,n<64: %4d  m<64,n>=64: %4d  m>=64,n<64: %4d  "
-           "m>=64,n>=64: %4d)\n", c[0], c[1], c[2], ok, q[0], q[1], q[2], q[3]);
+    printf("row shift %2d  LBO %5d  SBO %5d  k-step %4d B : %5d / 16384 exact  (quadrants m<64,n<64: %4d  m<64,n>=64: %4d  m>=64,n<64: %4d  "
+           "m>=64,n>=64: %4d)\n", shift, c[0], c[1], c[2], ok, q[0], q[1], q[2], q[3]);
   }
   return 0;
 }
