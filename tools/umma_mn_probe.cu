@@ -105,6 +105,30 @@ int main() {
   const int cands[][3] = {{BOX, 1024, 2048}, {1024, BOX, 2048}, {BOX, 1024, 256}, {1024, BOX, 256}};
   // row shifts: 0 (aligned), 8 (a whole swizzle atom), and starts in the middle of an atom — what reusing one haloed X
   // box across the (kh, kw) taps of the weight gradient needs (as conv_halo_kernel does for the K-major forward operand)
+  // Overlapping M blocks: a small LBO would make rows 64..127 of the M = 128 operand the SAME 64 channels read a few rows
+  // further down — two filter taps of one haloed box stacked into one MMA. Measured on B200: block 0 is exact, block 1 is
+  // NOT, for 128 B, 1 KB, 2304 B and 3 KB alike: M blocks must be separate boxes. A halo-box weight gradient therefore
+  // issues M = 64 MMAs per tap (or loads the box twice).
+  for (int lbo : {128, 18 * 128, 8 * 128, 24 * 128}) {
+    const int shift = 3;
+    for (int m = 0; m < 128; ++m)
+      for (int n = 0; n < 128; ++n) {
+        float acc = 0.f;
+        const int extra = m >= 64 ? lbo / 128 : 0;
+        for (int k = 0; k < KP; ++k) acc += a_val(shift + extra + k, m & 63) * b_val(k, n);
+        want[m * 128 + n] = acc;
+      }
+    probe<<<1, 128, smem>>>(lbo, 1024, 2048, shift, d);
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+      printf("overlapping blocks, LBO %d: CUDA error %s\n", lbo, cudaGetErrorString(cudaGetLastError()));
+      return 1;
+    }
+    cudaMemcpy(h.data(), d, h.size() * 4, cudaMemcpyDeviceToHost);
+    int ok = 0;
+    for (int i = 0; i < 128 * 128; ++i) ok += h[i] == want[i];
+    printf("overlapping M blocks: row shift %d, LBO %4d B (block 1 = block 0 moved %2d rows down): %5d / 16384 exact\n", shift, lbo,
+           lbo / 128, ok);
+  }
   const int shifts[] = {0, 8, 1, 3, 19};
   for (int shift : shifts)
   for (auto& c : cands) {
