@@ -143,3 +143,58 @@ def train_step(pack: Dict[str, np.ndarray], accum: Dict[str, np.ndarray], iterat
             batch = (mean if field == "moving_mean" else var).numpy()
             new_pack[k] = np.asarray(v, dtype=np.float64) * BN_MOMENTUM + batch * (1.0 - BN_MOMENTUM)
     return float(loss.detach()), new_pack, new_accum, gdict
+
+
+# ---- the VFE stack on ROWS WITH MULTIPLICITIES: the formulation the GPU training step will use ----------
+# The dense input holds three classes of rows: kept points (weight 1), per non-full voxel ONE virtual pad row standing for
+# its T - s identical zero rows (weight T - s), and ONE empty row standing for the 35 * n_empty rows of all empty voxels.
+# forward_train_rows() evaluates the same graph as forward_train()'s VFE section on that compact representation; the only
+# non-standard piece is the max over a voxel's rows, whose gradient must count a row's copies among the ties.
+class _WeightedSegmentMax(torch.autograd.Function):
+    """values [R, C], seg [R] (segment id per row, segments contiguous not required), weight [R] (copies per row) ->
+    per-segment max [S, C]. Backward: TensorFlow's reduce_max rule on the EXPANDED rows — the gradient is split equally
+    among tied copies — so compact row r receives weight_r * g / n_ties with n_ties = sum of the weights of tied rows."""
+
+    @staticmethod
+    def forward(ctx, values, seg, weight, n_seg):
+        out = torch.full((n_seg, values.shape[1]), -float("inf"), dtype=values.dtype)
+        out = out.scatter_reduce(0, seg.view(-1, 1).expand_as(values), values, reduce="amax", include_self=True)
+        ctx.save_for_backward(values, seg, weight, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        values, seg, weight, out = ctx.saved_tensors
+        tied = (values == out[seg]).to(values.dtype) * weight.view(-1, 1)
+        n_ties = torch.zeros_like(out).index_add_(0, seg, tied)
+        return tied * (g / n_ties)[seg], None, None, None
+
+
+def forward_train_rows(feat_rows, row_voxel, counts, n_cells_total, T, p, stats=None):
+    """feat_rows [R, 6] float64: the kept rows of all occupied voxels (voxel-major); row_voxel [R]; counts [V] = kept rows
+    per voxel (= min(points, T)); n_cells_total = N * nz * nx * ny. Returns (voxel_out [V, 64], empty_out [64], stats)."""
+    stats = {} if stats is None else stats
+    V = len(counts)
+    dt = feat_rows.dtype
+    nonfull = torch.nonzero(counts < T).view(-1)
+    n_empty = n_cells_total - V
+    M = float(n_cells_total * T)
+    # compact rows: [kept | virtual (one per non-full voxel) | empty (one)], weights and segment ids; the empty row is its
+    # own segment V
+    w = torch.cat([torch.ones(len(feat_rows), dtype=dt), (T - counts[nonfull]).to(dt), torch.tensor([float(T * n_empty)], dtype=dt)])
+    seg = torch.cat([row_voxel, nonfull, torch.tensor([V])])
+    x = torch.cat([feat_rows, torch.zeros((len(nonfull) + 1, feat_rows.shape[1]), dtype=dt)])
+
+    def bn_relu(u, name):
+        mean = (w.view(-1, 1) * u).sum(0) / M
+        var = (w.view(-1, 1) * u * u).sum(0) / M - mean * mean
+        stats[name] = (mean.detach(), var.detach())
+        return torch.relu((u - mean) / torch.sqrt(var + BN_EPS) * p[name + "/gamma"] + p[name + "/beta"])
+
+    for i in range(2):
+        h = bn_relu(x @ p[VFE_DENSE[i] + "/kernel"], VFE_BN[i])
+        pooled = _WeightedSegmentMax.apply(h, seg, w, V + 1)
+        x = torch.cat([pooled[seg], h], dim=1)
+    h = bn_relu(x @ p[VFE_DENSE[2] + "/kernel"], VFE_BN[2])
+    out = _WeightedSegmentMax.apply(h, seg, w, V + 1)
+    return out[:V], out[V], stats

@@ -108,3 +108,42 @@ def test_a_step_along_the_negative_gradient_descends_and_fit_moves_the_moving_st
     lr1 = 0.01 / (1 + 1e-6)
     k = "dense_2/kernel"
     assert np.allclose(accum2[k], 0.9 * accum[k] - lr1 * grads2[k], rtol=0, atol=1e-13)
+
+
+def test_vfe_on_rows_with_multiplicities_equals_the_dense_graph():
+    """kept rows (weight 1) + one virtual pad row per non-full voxel (weight T - s) + one empty row (weight
+    35 * n_empty) reproduce the dense VFE graph — outputs, batch statistics and every parameter gradient."""
+    pack = synthetic_model_pack(6)
+    rng = np.random.default_rng(5)
+    pts = np.concatenate([rng.uniform([-3.9, -0.9, 0.0], [3.9, 0.9, 1.95], size=(160, 3)),
+                          rng.uniform([0.5, 0.25, 0.5], [1.0, 0.5, 0.75], size=(9, 3)),
+                          np.tile([[1.3, 0.3, 0.6]], (3, 1))])  # duplicate points: exact ties between kept rows
+    vox = O.voxelize_np(pts, **ARGS)
+    T = 5
+    assert (vox["counts"] > T).any() and (vox["counts"] < T).any()
+    ind, val = O.coo_from_voxels(vox, T)
+    dense = torch.from_numpy(O.to_dense(ind, val, list(GRID) + [T, 6])[None])
+    names = [k for k in pack if k.split("/")[0] in TO.VFE_DENSE + TO.VFE_BN and "moving_" not in k]
+    gw = torch.from_numpy(rng.normal(size=(1,) + GRID + (64,)))  # an arbitrary upstream gradient on the grid
+
+    p1 = TO.to_params(pack)
+    _, _, stats1, grid1 = TO.forward_train(dense, p1)
+    g1 = torch.autograd.grad((grid1 * gw).sum(), [p1[k] for k in names])
+
+    kept = np.minimum(vox["counts"], T)
+    feats = vox["features"]  # [V, T, 6], zero padded
+    rows = torch.from_numpy(np.concatenate([feats[v, :kept[v]] for v in range(len(kept))]))
+    row_voxel = torch.from_numpy(np.repeat(np.arange(len(kept)), kept))
+    p2 = TO.to_params(pack)
+    n_cells = int(np.prod(GRID))
+    vout, eout, stats2 = TO.forward_train_rows(rows, row_voxel, torch.from_numpy(kept), n_cells, T, p2)
+    grid2 = eout.expand(GRID + (64,)).clone()
+    c = vox["coords"]
+    grid2[c[:, 0], c[:, 1], c[:, 2]] = vout
+    assert float((grid2 - grid1[0]).detach().abs().max()) < 1e-12
+    for bn in TO.VFE_BN:
+        assert float((stats1[bn][0] - stats2[bn][0]).abs().max()) < 1e-13
+        assert float((stats1[bn][1] - stats2[bn][1]).abs().max()) < 1e-13
+    g2 = torch.autograd.grad((grid2 * gw[0]).sum(), [p2[k] for k in names])
+    for k, a, b in zip(names, g1, g2):
+        assert float((a - b).abs().max()) <= 1e-10 * max(1.0, float(a.abs().max())), k
