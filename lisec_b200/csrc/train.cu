@@ -151,6 +151,19 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// float32 [P][c_in] -> bf16 [P][c_out] with zero padding of the channels (c_out >= c_in): the heads' 16-column gradient
+// widened to the 64 channels the tensor-core operands are made of.
+__global__ void __launch_bounds__(256)
+    pad_channels_kernel(const float* __restrict__ in, long long P, int c_in, int c_out, __nv_bfloat16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long total = P * c_out, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % c_out);
+    out[i] = __float2bfloat16(c < c_in ? in[(i / c_out) * c_in + c] : 0.f);
+  }
+}
+
 thread_local char g_train_error[256] = "";
 
 int32_t train_fail(int32_t code, const char* fmt, ...) {
@@ -224,6 +237,16 @@ int32_t lisec_dilate(const void* in, int32_t batch, int32_t d, int32_t h, int32_
   cudaError_t e = launch_pdl(dilate_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream),
                              static_cast<const uint4*>(in), (int)batch, (int)d, (int)h, (int)w, (int)(channels / 8),
                              (int)stride_d, (int)stride_hw, (int)out_d, (int)out_h, (int)out_w, static_cast<uint4*>(out));
+  if (e != cudaSuccess) return train_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
+  return LISEC_OK;
+}
+
+int32_t lisec_pad_channels_bf16(const float* in, int64_t positions, int32_t c_in, int32_t c_out, void* out_bf16, void* stream) {
+  if (!in || !out_bf16 || positions < 1 || c_in < 1 || c_out < c_in) return train_fail(LISEC_ERR_BAD_ARG, "bad argument");
+  long long blocks = (positions * c_out + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cudaError_t e = launch_pdl(pad_channels_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), in,
+                             (long long)positions, (int)c_in, (int)c_out, static_cast<__nv_bfloat16*>(out_bf16));
   if (e != cudaSuccess) return train_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
   return LISEC_OK;
 }

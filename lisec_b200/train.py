@@ -520,3 +520,97 @@ class Conv3dBlockTrain:
         for o in (self.dense_wgrad, self.conv_wgrad, self.dense_dgrad, self.conv_dgrad):
             if o is not None:
                 o.close()
+
+
+class HeadsTrain:
+    """ClassificationLayer + RegressionLayer in training (model_training.py:253-254): one 1x1 convolution 768 -> 2 + 14
+    with bias, float32 outputs; its backward from the float32 loss gradient dy [B,1,H,W,16]: dy is widened to 64 bf16
+    channels (lisec_pad_channels_bf16), the weight gradient is conv_wgrad_kernel's (rows 0..15 of its 64), the bias
+    gradient the column sums, the data gradient a plan with three 256-column N-tiles. w: float32 [1, 16, 768] ([tap][out][in]),
+    bias float32 [16]; x: bf16 [B,1,H,W,768] (the concat tensor)."""
+
+    def __init__(self, x: torch.Tensor, w, bias):
+        self._lib = N.load()
+        B, D, H, W, Cin = x.shape
+        dev = x.device
+        self.x, self.w, self.bias = x, w, bias
+        self.w16 = torch.empty((1, 16, Cin), dtype=torch.bfloat16, device=dev)
+        self.y = torch.empty((B, D, H, W, 16), dtype=torch.float32, device=dev)
+        self.dy64 = torch.empty((B, D, H, W, 64), dtype=torch.bfloat16, device=dev)
+        self.w64 = torch.zeros((1, 64, Cin), dtype=torch.float32, device=dev)  # rows 16.. stay zero
+        self.ones = torch.ones(Cin, dtype=torch.float32, device=dev)
+        self.zeros = torch.zeros(Cin, dtype=torch.float32, device=dev)
+        tile = (16, 8) if W >= 16 else (8, 16)
+
+        def plan(src, wt, scale, shift, dst, cin, cout, n_tiles, out_dtype):
+            desc = N.lisec_conv_desc(
+                batch=B, in_d=D, in_h=H, in_w=W, in_c=cin, kd=1, kh=1, kw=1, stride_d=1, stride_hw=1, pad_d=0, pad_h=0,
+                pad_w=0, out_c=cout, n_tiles=n_tiles, shuffle=1, out_pitch=cout * n_tiles, out_ch_off=0, relu=0,
+                out_dtype=out_dtype, tile_w=tile[0], tile_h=tile[1], m_tiles=1, in_dtype=N.LISEC_BF16, out_split=0,
+                group_kh=0, reserved=0)
+            h = C.c_void_p()
+            with torch.cuda.device(dev):
+                st = self._lib.lisec_conv_plan_create(C.byref(desc), C.c_void_p(src.data_ptr()), C.c_void_p(wt.data_ptr()),
+                                                      C.c_void_p(scale.data_ptr()), C.c_void_p(shift.data_ptr()),
+                                                      C.c_void_p(dst.data_ptr()), C.byref(h))
+            if st != N.LISEC_OK:
+                raise N.LisecError(st, self._lib.lisec_conv_last_error().decode("utf-8", "replace"))
+            return h
+
+        self.fwd_plan = plan(x, self.w16, self.ones, bias, self.y, Cin, 16, 1, N.LISEC_F32)
+        self.wgrad = ConvWgrad(x, self.dy64, (1, 1, 1), 1, (0, 0, 0), tile=tile)
+        # data gradient: dx[p][ci] = sum_n dy64[p][n] * w64[n][ci]: weights [1][ci = 768][n = 64] as three N-tiles of 256
+        self.wt16 = torch.empty((1, Cin, 64), dtype=torch.bfloat16, device=dev)
+        self.dx = torch.empty((B, D, H, W, Cin), dtype=torch.bfloat16, device=dev)
+        self.refresh_weights()
+        self.dgrad_plan = plan(self.dy64, self.wt16, self.ones, self.zeros, self.dx, 64, 256, Cin // 256, N.LISEC_BF16)
+        self.bn_ws = torch.empty(int(self._lib.lisec_bn_workspace_bytes(B * D * H * W, 64)) // 8, dtype=torch.float64, device=dev)
+        self.dbias64 = torch.empty(64, dtype=torch.float32, device=dev)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.x.device).cuda_stream)
+
+    def refresh_weights(self) -> None:
+        self.w64[:, :16].copy_(self.w)
+        with torch.cuda.device(self.x.device):
+            st = self._lib.lisec_cast_f32_to_bf16(C.c_void_p(self.w.data_ptr()), self.w.numel(), C.c_void_p(self.w16.data_ptr()),
+                                                  self._stream())
+            if st == N.LISEC_OK:
+                st = self._lib.lisec_weights_flip_transpose(C.c_void_p(self.w64.data_ptr()), 1, 1, 1, 64, self.w64.shape[2],
+                                                            C.c_void_p(self.wt16.data_ptr()), self._stream())
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_train_last_error().decode("utf-8", "replace"))
+
+    def _run(self, plan):
+        with torch.cuda.device(self.x.device):
+            st = self._lib.lisec_conv_plan_run(plan, self._stream())
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_conv_last_error().decode("utf-8", "replace"))
+
+    def forward(self) -> torch.Tensor:
+        self._run(self.fwd_plan)
+        return self.y
+
+    def backward(self, dy: torch.Tensor) -> torch.Tensor:
+        """dy: float32 [B,1,H,W,16] (mse_loss_grad's output for the two heads, concatenated). Returns dx (bf16); dw
+        [1,16,768] and dbias [16] hold the parameter gradients."""
+        P = dy.numel() // 16
+        with torch.cuda.device(self.x.device):
+            st = self._lib.lisec_pad_channels_bf16(C.c_void_p(dy.contiguous().data_ptr()), P, 16, 64,
+                                                   C.c_void_p(self.dy64.data_ptr()), self._stream())
+            if st == N.LISEC_OK:
+                st = self._lib.lisec_channel_sums(C.c_void_p(self.dy64.data_ptr()), P, 64, C.c_void_p(self.dbias64.data_ptr()),
+                                                  C.c_void_p(self.bn_ws.data_ptr()), self._stream())
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, (self._lib.lisec_train_last_error() or self._lib.lisec_bn_last_error()).decode("utf-8", "replace"))
+        self.dw = self.wgrad.run()[:, :16]
+        self.dbias = self.dbias64[:16]
+        self._run(self.dgrad_plan)
+        return self.dx
+
+    def close(self):
+        for h in ("fwd_plan", "dgrad_plan"):
+            if getattr(self, h, None):
+                self._lib.lisec_conv_plan_destroy(getattr(self, h))
+                setattr(self, h, None)
+        self.wgrad.close()

@@ -362,3 +362,41 @@ def test_gpu_conv3d_block_trains_like_autograd(sd, pad, D):
     assert close(blk.dwd.cpu()[0], wdv.grad)
     assert close(blk.bn.dgamma.cpu(), gd.grad) and close(blk.bn.dbeta.cpu(), btd.grad)
     blk.close()
+
+
+@pytest.mark.gpu
+def test_gpu_heads_train_forward_backward():
+    """The two 1x1 head convolutions (768 -> 2 + 14, bias) with the MSE loss on top: forward, loss, and the gradients with
+    respect to the head kernels, biases and the concat tensor, against torch float64 autograd."""
+    from lisec_b200.train import HeadsTrain, mse_loss_grad
+
+    g = torch.Generator(device="cpu").manual_seed(31)
+    B, H, W = 2, 24, 40
+    x = torch.randn((B, 1, H, W, 768), generator=g).to(torch.bfloat16)
+    w = (torch.randn((1, 16, 768), generator=g) / np.sqrt(768)).to(torch.bfloat16).float()
+    bias = torch.randn(16, generator=g) * 0.1
+    tc = torch.randint(0, 3, (B, 1, H, W, 2), generator=g).float()
+    tr = torch.randn((B, 1, H, W, 14), generator=g)
+    heads = HeadsTrain(x.cuda(), w.cuda(), bias.cuda())
+    y = heads.forward()
+    lc, dyc = mse_loss_grad(y[..., :2].contiguous(), tc.cuda())
+    lr, dyr = mse_loss_grad(y[..., 2:].contiguous(), tr.cuda())
+    dy = torch.cat([dyc, dyr], dim=-1)
+    dx = heads.backward(dy).float().cpu()
+    torch.cuda.synchronize()
+
+    xd = x.double().requires_grad_(True)
+    wd, bd = w.double()[0].requires_grad_(True), bias.double().requires_grad_(True)
+    yd = xd @ wd.t() + bd
+    loss = ((yd[..., :2] - tc.double()) ** 2).mean() + ((yd[..., 2:] - tr.double()) ** 2).mean()
+    loss.backward()
+    assert abs(float(lc + lr) - float(loss.detach())) <= 1e-5 * float(loss.detach())
+    assert float((y.cpu().double() - yd.detach()).abs().max()) <= 1e-4 * float(yd.detach().abs().max())
+
+    def close(got, want, tol):
+        return float((got.double() - want).abs().max()) <= tol * float(want.abs().max())
+
+    # dy is rounded to bf16 on its way into the tensor-core operands: 2^-9
+    assert close(heads.dw.cpu()[0], wd.grad, 5e-3) and close(heads.dbias.cpu(), bd.grad, 5e-3)
+    assert close(dx, xd.grad, 1e-2)
+    heads.close()
