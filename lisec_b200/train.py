@@ -614,3 +614,74 @@ class HeadsTrain:
                 self._lib.lisec_conv_plan_destroy(getattr(self, h))
                 setattr(self, h, None)
         self.wgrad.close()
+
+
+class ConvBiasTrain:
+    """A convolution with bias and nothing behind it, in training: the k3 s1 'same' Conv2DTranspose of RPN block 1
+    (model_training.py:247) is a 3x3 convolution with the kernel flipped (lisec_b200/network.py), so its training stage is
+    this one. Forward writes into a channel slice of a wider buffer (out_pitch / out_ch_off: the concat tensor); backward
+    takes a DENSE dy [B,D,H,W,N]. w: float32 [taps, N, C] in the plans' layout, bias float32 [N]."""
+
+    def __init__(self, x: torch.Tensor, w, bias, k, pad, out: torch.Tensor, out_ch_off: int, dy: torch.Tensor, need_dx=True):
+        self._lib = N.load()
+        B, D, H, W, Cin = x.shape
+        taps, Nout, _ = w.shape
+        dev = x.device
+        self.x, self.w, self.bias, self.dy = x, w, bias, dy
+        self.w16 = torch.empty((taps, Nout, Cin), dtype=torch.bfloat16, device=dev)
+        self.ones = torch.ones(Nout, dtype=torch.float32, device=dev)
+        tile = (16, 8) if W >= 16 else (8, 16)
+        self.desc = N.lisec_conv_desc(
+            batch=B, in_d=D, in_h=H, in_w=W, in_c=Cin, kd=k[0], kh=k[1], kw=k[2], stride_d=1, stride_hw=1, pad_d=pad[0],
+            pad_h=pad[1], pad_w=pad[2], out_c=Nout, n_tiles=1, shuffle=1, out_pitch=out.shape[-1], out_ch_off=out_ch_off,
+            relu=0, out_dtype=N.LISEC_BF16, tile_w=tile[0], tile_h=tile[1], m_tiles=1, in_dtype=N.LISEC_BF16, out_split=0,
+            group_kh=0, reserved=0)
+        self.dgrad = ConvDgrad(dy, w, k, pad) if need_dx else None
+        self.refresh_weights()
+        self.plan = C.c_void_p()
+        with torch.cuda.device(dev):
+            st = self._lib.lisec_conv_plan_create(C.byref(self.desc), C.c_void_p(x.data_ptr()), C.c_void_p(self.w16.data_ptr()),
+                                                  C.c_void_p(self.ones.data_ptr()), C.c_void_p(bias.data_ptr()),
+                                                  C.c_void_p(out.data_ptr()), C.byref(self.plan))
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_conv_last_error().decode("utf-8", "replace"))
+        self.wgrad = ConvWgrad(x, dy, k, 1, pad, tile=tile)
+        self.P = dy.numel() // Nout
+        self.ws = torch.empty(int(self._lib.lisec_bn_workspace_bytes(self.P, Nout)) // 8, dtype=torch.float64, device=dev)
+        self.dbias = torch.empty(Nout, dtype=torch.float32, device=dev)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.x.device).cuda_stream)
+
+    def refresh_weights(self) -> None:
+        with torch.cuda.device(self.x.device):
+            st = self._lib.lisec_cast_f32_to_bf16(C.c_void_p(self.w.data_ptr()), self.w.numel(), C.c_void_p(self.w16.data_ptr()),
+                                                  self._stream())
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_train_last_error().decode("utf-8", "replace"))
+        if self.dgrad is not None:
+            self.dgrad.refresh_weights()
+
+    def forward(self) -> None:
+        with torch.cuda.device(self.x.device):
+            st = self._lib.lisec_conv_plan_run(self.plan, self._stream())
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_conv_last_error().decode("utf-8", "replace"))
+
+    def backward(self):
+        """From self.dy (filled by the stage behind). Returns dx; dw / dbias hold the parameter gradients."""
+        self.dw = self.wgrad.run()
+        with torch.cuda.device(self.x.device):
+            st = self._lib.lisec_channel_sums(C.c_void_p(self.dy.data_ptr()), self.P, self.dy.shape[-1],
+                                              C.c_void_p(self.dbias.data_ptr()), C.c_void_p(self.ws.data_ptr()), self._stream())
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_bn_last_error().decode("utf-8", "replace"))
+        return self.dgrad.run() if self.dgrad is not None else None
+
+    def close(self):
+        if getattr(self, "plan", None):
+            self._lib.lisec_conv_plan_destroy(self.plan)
+            self.plan = None
+        self.wgrad.close()
+        if self.dgrad is not None:
+            self.dgrad.close()

@@ -400,3 +400,41 @@ def test_gpu_heads_train_forward_backward():
     assert close(heads.dw.cpu()[0], wd.grad, 5e-3) and close(heads.dbias.cpu(), bd.grad, 5e-3)
     assert close(dx, xd.grad, 1e-2)
     heads.close()
+
+
+@pytest.mark.gpu
+def test_gpu_transposed_k3s1_stage_into_a_concat_slice():
+    """RPN block 1's Conv2DTranspose(256, k3, s1, 'same') as its flipped-kernel convolution: forward into channels
+    256..511 of a 768-channel buffer, backward from a dense dy, against float64 autograd of F.conv_transpose2d itself."""
+    import torch.nn.functional as F
+
+    from lisec_b200.train import ConvBiasTrain
+
+    g = torch.Generator(device="cpu").manual_seed(37)
+    B, H, W, Cin, Co = 2, 24, 40, 128, 256
+    x = torch.randn((B, 1, H, W, Cin), generator=g).to(torch.bfloat16)
+    Fk = (torch.randn((3, 3, Co, Cin), generator=g) / np.sqrt(9 * Cin)).to(torch.bfloat16).float()  # Keras (kh, kw, out, in)
+    bias = torch.randn(Co, generator=g) * 0.1
+    w = Fk.flip(0, 1).reshape(9, Co, Cin).contiguous()  # the plans' [tap][out][in] of the equivalent convolution
+    concat = torch.full((B, 1, H, W, 768), 7.0, dtype=torch.bfloat16, device="cuda")
+    dy = torch.randn((B, 1, H, W, Co), generator=g).to(torch.bfloat16)
+    st = ConvBiasTrain(x.cuda(), w.cuda(), bias.cuda(), (1, 3, 3), (0, 1, 1), concat, 256, dy.cuda())
+    st.forward()
+    dx = st.backward().float().cpu()
+    torch.cuda.synchronize()
+    xd = x.double()[:, 0].permute(0, 3, 1, 2).requires_grad_(True)
+    Fd = Fk.double().permute(3, 2, 0, 1).requires_grad_(True)  # torch conv_transpose2d weight: (in, out, kh, kw)
+    bd = bias.double().requires_grad_(True)
+    yd = F.conv_transpose2d(xd, Fd, bd, stride=1, padding=1)
+    (yd * dy.double()[:, 0].permute(0, 3, 1, 2)).sum().backward()
+    got_y = concat[:, 0, :, :, 256:512].float().cpu().permute(0, 3, 1, 2)
+    assert float((got_y.double() - yd.detach()).abs().max()) <= 2.0 ** -8 * float(yd.detach().abs().max())
+    assert bool((concat[..., :256] == 7).all()) and bool((concat[..., 512:] == 7).all())  # the neighbours are untouched
+
+    def close(got, want, tol=2e-5):
+        return float((got.double() - want).abs().max()) <= tol * float(want.abs().max())
+
+    want_dw = Fd.grad.permute(2, 3, 1, 0).flip(0, 1).reshape(9, Co, Cin)  # back into the flipped [tap][out][in] layout
+    assert close(st.dw.cpu(), want_dw) and close(st.dbias.cpu(), bd.grad, 1e-5)
+    assert close(dx[:, 0].permute(0, 3, 1, 2), xd.grad, 2.0 ** -8)
+    st.close()
