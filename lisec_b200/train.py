@@ -685,3 +685,81 @@ class ConvBiasTrain:
         self.wgrad.close()
         if self.dgrad is not None:
             self.dgrad.close()
+
+
+class ConvTransposeBackward:
+    """Backward of a Conv2DTranspose whose kernel equals its stride s (RPN blocks 2 and 3, model_training.py:249, 251):
+    y[s*h + i, s*w + j] = x[h, w] . F[i, j] + b. With dy viewed as [B, H, s, W, s*Co] (the same memory: row s*h + i of the
+    output holds, for each w, the s*Co values of columns s*w .. s*w + s - 1), dx is a convolution over that view with
+    kh = s taps and no padding, and dF the matching weight gradient — both on the existing tensor-core kernels.
+    F: float32 [s, s, Co, Ci] (the Keras layout); dy: bf16 dense [B, 1, s*H, s*W, Co]; x: bf16 [B, 1, H, W, Ci]."""
+
+    def __init__(self, x: torch.Tensor, dy: torch.Tensor, F: torch.Tensor, s: int):
+        self._lib = N.load()
+        B, _, H, W, Ci = x.shape
+        Co = dy.shape[-1]
+        if tuple(dy.shape) != (B, 1, s * H, s * W, Co) or tuple(F.shape) != (s, s, Co, Ci) or s not in (2, 3):
+            raise ValueError("shapes do not describe a kernel = stride transposed convolution (s = 2 or 3)")
+        dev = x.device
+        self.s, self.F, self.dy = s, F, dy
+        self.dy_view = dy.view(B, H, s, W, s * Co)
+        self.x_view = x.view(B, H, 1, W, Ci)
+        tile = (128, 1)
+        # dx: weights [tap = i][n = ci][c = (j, co)]
+        self.w = torch.empty((s, Ci, s * Co), dtype=torch.float32, device=dev)
+        self.w16 = torch.empty((s, Ci, s * Co), dtype=torch.bfloat16, device=dev)
+        self.dx = torch.empty((B, H, 1, W, Ci), dtype=torch.bfloat16, device=dev)
+        self.ones = torch.ones(Ci, dtype=torch.float32, device=dev)
+        self.zeros = torch.zeros(Ci, dtype=torch.float32, device=dev)
+        self.refresh_weights()
+        desc = N.lisec_conv_desc(
+            batch=B, in_d=H, in_h=s, in_w=W, in_c=s * Co, kd=1, kh=s, kw=1, stride_d=1, stride_hw=1, pad_d=0, pad_h=0,
+            pad_w=0, out_c=Ci, n_tiles=1, shuffle=1, out_pitch=Ci, out_ch_off=0, relu=0, out_dtype=N.LISEC_BF16,
+            tile_w=tile[0], tile_h=tile[1], m_tiles=1, in_dtype=N.LISEC_BF16, out_split=0, group_kh=0, reserved=0)
+        self.plan = C.c_void_p()
+        with torch.cuda.device(dev):
+            st = self._lib.lisec_conv_plan_create(C.byref(desc), C.c_void_p(self.dy_view.data_ptr()),
+                                                  C.c_void_p(self.w16.data_ptr()), C.c_void_p(self.ones.data_ptr()),
+                                                  C.c_void_p(self.zeros.data_ptr()), C.c_void_p(self.dx.data_ptr()),
+                                                  C.byref(self.plan))
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_conv_last_error().decode("utf-8", "replace"))
+        self.wgrad = ConvWgrad(self.dy_view, self.x_view, (1, s, 1), 1, (0, 0, 0), tile=tile)  # -> [i][ci][(j, co)]
+        self.P = dy.numel() // Co
+        self.ws = torch.empty(int(self._lib.lisec_bn_workspace_bytes(self.P, Co)) // 8, dtype=torch.float64, device=dev)
+        self.dbias = torch.empty(Co, dtype=torch.float32, device=dev)
+        self.dy = dy
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dy.device).cuda_stream)
+
+    def refresh_weights(self) -> None:
+        s = self.s
+        # F[i, j, co, ci] -> w[i][ci][j*Co + co]: a permutation of a <= 1 MB tensor (torch indexing: plumbing, not arithmetic)
+        self.w.copy_(self.F.permute(0, 3, 1, 2).reshape(s, self.F.shape[3], s * self.F.shape[2]))
+        with torch.cuda.device(self.F.device):
+            st = self._lib.lisec_cast_f32_to_bf16(C.c_void_p(self.w.data_ptr()), self.w.numel(), C.c_void_p(self.w16.data_ptr()),
+                                                  self._stream())
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_train_last_error().decode("utf-8", "replace"))
+
+    def backward(self):
+        """Returns dx [B,1,H,W,Ci] (bf16); dF [s,s,Co,Ci] and dbias [Co] hold the parameter gradients."""
+        s, Co, Ci = self.s, self.F.shape[2], self.F.shape[3]
+        with torch.cuda.device(self.dy.device):
+            st = self._lib.lisec_conv_plan_run(self.plan, self._stream())
+            if st != N.LISEC_OK:
+                raise N.LisecError(st, self._lib.lisec_conv_last_error().decode("utf-8", "replace"))
+            st = self._lib.lisec_channel_sums(C.c_void_p(self.dy.data_ptr()), self.P, Co, C.c_void_p(self.dbias.data_ptr()),
+                                              C.c_void_p(self.ws.data_ptr()), self._stream())
+            if st != N.LISEC_OK:
+                raise N.LisecError(st, self._lib.lisec_bn_last_error().decode("utf-8", "replace"))
+        dw = self.wgrad.run()  # [i][ci][(j, co)]
+        self.dF = dw.view(s, Ci, s, Co).permute(0, 2, 3, 1)
+        return self.dx.view(self.dx.shape[0], 1, self.dx.shape[1], self.dx.shape[3], Ci)
+
+    def close(self):
+        if getattr(self, "plan", None):
+            self._lib.lisec_conv_plan_destroy(self.plan)
+            self.plan = None
+        self.wgrad.close()

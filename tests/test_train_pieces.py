@@ -438,3 +438,34 @@ def test_gpu_transposed_k3s1_stage_into_a_concat_slice():
     assert close(st.dw.cpu(), want_dw) and close(st.dbias.cpu(), bd.grad, 1e-5)
     assert close(dx[:, 0].permute(0, 3, 1, 2), xd.grad, 2.0 ** -8)
     st.close()
+
+
+@pytest.mark.gpu
+def test_gpu_transposed_kernel_equals_stride_backward():
+    """RPN block 2's Conv2DTranspose(256, k2, s2): dx, dF and dbias through the [B, H, s, W, s*Co] view of dy, against
+    float64 autograd of F.conv_transpose2d."""
+    import torch.nn.functional as F
+
+    from lisec_b200.train import ConvTransposeBackward
+
+    g = torch.Generator(device="cpu").manual_seed(41)
+    B, H, W, Ci, Co, s = 2, 12, 20, 128, 256, 2
+    x = torch.randn((B, 1, H, W, Ci), generator=g).to(torch.bfloat16)
+    Fk = (torch.randn((s, s, Co, Ci), generator=g) / np.sqrt(Ci)).to(torch.bfloat16).float()
+    dy = torch.randn((B, 1, s * H, s * W, Co), generator=g).to(torch.bfloat16)
+    tb = ConvTransposeBackward(x.cuda(), dy.cuda(), Fk.cuda(), s)
+    dx = tb.backward().float().cpu()
+    torch.cuda.synchronize()
+    xd = x.double()[:, 0].permute(0, 3, 1, 2).requires_grad_(True)
+    Fd = Fk.double().permute(3, 2, 0, 1).requires_grad_(True)  # (in, out, kh, kw)
+    bd = torch.zeros(Co, dtype=torch.float64, requires_grad=True)
+    yd = F.conv_transpose2d(xd, Fd, bd, stride=s)
+    (yd * dy.double()[:, 0].permute(0, 3, 1, 2)).sum().backward()
+
+    def close(got, want, tol):
+        return float((got.double() - want).abs().max()) <= tol * float(want.abs().max())
+
+    assert close(dx[:, 0].permute(0, 3, 1, 2), xd.grad, 2.0 ** -8)
+    assert close(tb.dF.cpu(), Fd.grad.permute(2, 3, 1, 0), 2e-5)
+    assert close(tb.dbias.cpu(), bd.grad, 1e-5)
+    tb.close()
