@@ -698,8 +698,8 @@ class ConvTransposeBackward:
         self._lib = N.load()
         B, _, H, W, Ci = x.shape
         Co = dy.shape[-1]
-        if tuple(dy.shape) != (B, 1, s * H, s * W, Co) or tuple(F.shape) != (s, s, Co, Ci) or s not in (2, 3):
-            raise ValueError("shapes do not describe a kernel = stride transposed convolution (s = 2 or 3)")
+        if tuple(dy.shape) != (B, 1, s * H, s * W, Co) or tuple(F.shape) != (s, s, Co, Ci) or s not in (2, 3, 4):
+            raise ValueError("shapes do not describe a kernel = stride transposed convolution (s = 2, 3 or 4)")
         dev = x.device
         self.s, self.F, self.dy = s, F, dy
         self.dy_view = dy.view(B, H, s, W, s * Co)

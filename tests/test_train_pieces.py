@@ -441,15 +441,16 @@ def test_gpu_transposed_k3s1_stage_into_a_concat_slice():
 
 
 @pytest.mark.gpu
-def test_gpu_transposed_kernel_equals_stride_backward():
-    """RPN block 2's Conv2DTranspose(256, k2, s2): dx, dF and dbias through the [B, H, s, W, s*Co] view of dy, against
-    float64 autograd of F.conv_transpose2d."""
+@pytest.mark.parametrize("s,Ci,H,W", [(2, 128, 12, 20), (4, 256, 6, 10)])
+def test_gpu_transposed_kernel_equals_stride_backward(s, Ci, H, W):
+    """RPN block 2's Conv2DTranspose(256, k2, s2) and block 3's (k4, s4): dx, dF and dbias through the [B, H, s, W, s*Co]
+    view of dy, against float64 autograd of F.conv_transpose2d."""
     import torch.nn.functional as F
 
     from lisec_b200.train import ConvTransposeBackward
 
     g = torch.Generator(device="cpu").manual_seed(41)
-    B, H, W, Ci, Co, s = 2, 12, 20, 128, 256, 2
+    B, Co = 2, 256
     x = torch.randn((B, 1, H, W, Ci), generator=g).to(torch.bfloat16)
     Fk = (torch.randn((s, s, Co, Ci), generator=g) / np.sqrt(Ci)).to(torch.bfloat16).float()
     dy = torch.randn((B, 1, s * H, s * W, Co), generator=g).to(torch.bfloat16)
