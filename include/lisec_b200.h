@@ -359,6 +359,9 @@ int32_t lisec_dilate(const void* in, int32_t batch, int32_t d, int32_t h, int32_
 /* [async] float32 [positions][c_in] -> bf16 [positions][c_out], channels c_in.. zero: the heads' 16-column gradient widened
  * to the 64 channels a tensor-core operand box holds. */
 int32_t lisec_pad_channels_bf16(const float* in, int64_t positions, int32_t c_in, int32_t c_out, void* out_bf16, void* stream);
+/* [async] a += b (bf16 tensors of n elements, n a multiple of 8; the sum is formed in float32): accumulation of the
+ * gradients of a tensor that has two consumers. */
+int32_t lisec_add_bf16(void* a, const void* b, int64_t n, void* stream);
 /* [async] float32 master weights -> the bf16 operand copy the plans read. */
 int32_t lisec_cast_f32_to_bf16(const float* w, int64_t n, void* out_bf16, void* stream);
 const char* lisec_train_last_error(void);

@@ -164,6 +164,26 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// a += b (bf16, float32 add, 8 elements per thread): the gradients of a tensor with two consumers (an RPN block's output
+// feeds the next block and its transposed convolution)
+__global__ void __launch_bounds__(256) add_bf16_kernel(uint4* __restrict__ a, const uint4* __restrict__ b, long long n8) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    uint4 x = a[i];
+    const uint4 y = __ldcs(b + i);
+    __nv_bfloat162* xv = reinterpret_cast<__nv_bfloat162*>(&x);
+    const __nv_bfloat162* yv = reinterpret_cast<const __nv_bfloat162*>(&y);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 p = __bfloat1622float2(xv[k]), q = __bfloat1622float2(yv[k]);
+      xv[k] = __floats2bfloat162_rn(p.x + q.x, p.y + q.y);
+    }
+    a[i] = x;
+  }
+}
+
 thread_local char g_train_error[256] = "";
 
 int32_t train_fail(int32_t code, const char* fmt, ...) {
@@ -247,6 +267,17 @@ int32_t lisec_pad_channels_bf16(const float* in, int64_t positions, int32_t c_in
   if (blocks > 148 * 16) blocks = 148 * 16;
   cudaError_t e = launch_pdl(pad_channels_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), in,
                              (long long)positions, (int)c_in, (int)c_out, static_cast<__nv_bfloat16*>(out_bf16));
+  if (e != cudaSuccess) return train_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
+  return LISEC_OK;
+}
+
+int32_t lisec_add_bf16(void* a, const void* b, int64_t n, void* stream) {
+  if (n < 0 || n % 8 || (n > 0 && (!a || !b))) return train_fail(LISEC_ERR_BAD_ARG, "n must be a multiple of 8");
+  if (n == 0) return LISEC_OK;
+  long long blocks = (n / 8 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cudaError_t e = launch_pdl(add_bf16_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                             static_cast<uint4*>(a), static_cast<const uint4*>(b), (long long)(n / 8));
   if (e != cudaSuccess) return train_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
   return LISEC_OK;
 }

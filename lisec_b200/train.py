@@ -404,6 +404,19 @@ class ConvDgradStrided:
         self.inner.close()
 
 
+def add_(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a += b on bf16 device tensors (lisec_add_bf16): gradient accumulation where a tensor has two consumers."""
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or a.shape != b.shape or not a.is_cuda or not a.is_contiguous():
+        raise ValueError("a, b: contiguous cuda bf16 tensors of one shape")
+    lib = N.load()
+    with torch.cuda.device(a.device):
+        st = lib.lisec_add_bf16(C.c_void_p(a.data_ptr()), C.c_void_p(b.contiguous().data_ptr()), a.numel(),
+                                C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream))
+    if st != N.LISEC_OK:
+        raise N.LisecError(st, lib.lisec_train_last_error().decode("utf-8", "replace"))
+    return a
+
+
 def relu_backward(dy: torch.Tensor, y: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dy masked by y > 0 (bf16): the ReLU behind the Dense of a Conv3D block (model_training.py:195)."""
     if dy.dtype != torch.bfloat16 or y.dtype != torch.bfloat16 or dy.shape != y.shape or not dy.is_cuda:
@@ -529,7 +542,7 @@ class HeadsTrain:
     gradient the column sums, the data gradient a plan with three 256-column N-tiles. w: float32 [1, 16, 768] ([tap][out][in]),
     bias float32 [16]; x: bf16 [B,1,H,W,768] (the concat tensor)."""
 
-    def __init__(self, x: torch.Tensor, w, bias):
+    def __init__(self, x: torch.Tensor, w, bias, dense_slices: bool = False):
         self._lib = N.load()
         B, D, H, W, Cin = x.shape
         dev = x.device
@@ -560,10 +573,17 @@ class HeadsTrain:
         self.fwd_plan = plan(x, self.w16, self.ones, bias, self.y, Cin, 16, 1, N.LISEC_F32)
         self.wgrad = ConvWgrad(x, self.dy64, (1, 1, 1), 1, (0, 0, 0), tile=tile)
         # data gradient: dx[p][ci] = sum_n dy64[p][n] * w64[n][ci]: weights [1][ci = 768][n = 64] as three N-tiles of 256
+        # (the concat tensor is three 256-channel blocks with three different producers: with dense_slices the gradient
+        # leaves as three dense [.., 256] tensors, one plan each, ready to be the dy of the three transposed stages)
         self.wt16 = torch.empty((1, Cin, 64), dtype=torch.bfloat16, device=dev)
-        self.dx = torch.empty((B, D, H, W, Cin), dtype=torch.bfloat16, device=dev)
         self.refresh_weights()
-        self.dgrad_plan = plan(self.dy64, self.wt16, self.ones, self.zeros, self.dx, 64, 256, Cin // 256, N.LISEC_BF16)
+        if dense_slices:
+            self.dx = [torch.empty((B, D, H, W, 256), dtype=torch.bfloat16, device=dev) for _ in range(Cin // 256)]
+            self.dgrad_plans = [plan(self.dy64, self.wt16[:, 256 * i:256 * i + 256], self.ones, self.zeros, self.dx[i], 64, 256, 1,
+                                     N.LISEC_BF16) for i in range(Cin // 256)]
+        else:
+            self.dx = torch.empty((B, D, H, W, Cin), dtype=torch.bfloat16, device=dev)
+            self.dgrad_plans = [plan(self.dy64, self.wt16, self.ones, self.zeros, self.dx, 64, 256, Cin // 256, N.LISEC_BF16)]
         self.bn_ws = torch.empty(int(self._lib.lisec_bn_workspace_bytes(B * D * H * W, 64)) // 8, dtype=torch.float64, device=dev)
         self.dbias64 = torch.empty(64, dtype=torch.float32, device=dev)
 
@@ -605,14 +625,15 @@ class HeadsTrain:
             raise N.LisecError(st, (self._lib.lisec_train_last_error() or self._lib.lisec_bn_last_error()).decode("utf-8", "replace"))
         self.dw = self.wgrad.run()[:, :16]
         self.dbias = self.dbias64[:16]
-        self._run(self.dgrad_plan)
+        for pl in self.dgrad_plans:
+            self._run(pl)
         return self.dx
 
     def close(self):
-        for h in ("fwd_plan", "dgrad_plan"):
-            if getattr(self, h, None):
-                self._lib.lisec_conv_plan_destroy(getattr(self, h))
-                setattr(self, h, None)
+        for pl in [getattr(self, "fwd_plan", None)] + list(getattr(self, "dgrad_plans", [])):
+            if pl:
+                self._lib.lisec_conv_plan_destroy(pl)
+        self.fwd_plan, self.dgrad_plans = None, []
         self.wgrad.close()
 
 

@@ -400,6 +400,17 @@ def test_gpu_heads_train_forward_backward():
     assert close(heads.dw.cpu()[0], wd.grad, 5e-3) and close(heads.dbias.cpu(), bd.grad, 5e-3)
     assert close(dx, xd.grad, 1e-2)
     heads.close()
+    # the same gradient as three dense 256-channel tensors (the dy of the three transposed-convolution stages), and a += b
+    from lisec_b200.train import add_
+
+    h3 = HeadsTrain(x.cuda(), w.cuda(), bias.cuda(), dense_slices=True)
+    h3.forward()
+    parts = h3.backward(dy)
+    assert len(parts) == 3 and torch.equal(torch.cat([p.float().cpu() for p in parts], dim=-1), dx)
+    acc = parts[0].clone()
+    add_(acc, parts[1])
+    assert torch.equal(acc.float().cpu(), (parts[0].float() + parts[1].float()).to(torch.bfloat16).float().cpu())
+    h3.close()
 
 
 @pytest.mark.gpu
