@@ -784,3 +784,174 @@ class ConvTransposeBackward:
             self._lib.lisec_conv_plan_destroy(self.plan)
             self.plan = None
         self.wgrad.close()
+
+
+class DenseNetworkTrainer:
+    """The dense network behind the voxel grid in TRAINING mode (model_training.py:236-254 under fit): three Conv3D blocks,
+    the RPN's sixteen Conv2D + BN + ReLU stages, the three transposed convolutions into the concat tensor, the heads and the
+    two MSE terms — forward, loss and the gradient of every one of its parameters, chained from the stages above.
+    `pack`: Keras-named float arrays (lisec_b200/weights.py); the float32 master weights live in self.params[name] in the
+    plans' layouts (see _to_plan_layout), their gradients in self.grads[name] after backward(). The VFE stack in front of
+    the grid is not part of this class (its training kernels are not built yet): `grid` is an input."""
+
+    def __init__(self, pack: dict, batch: int, nx: int, ny: int, nz: int = 8, device: int = 0):
+        from .weights import conv3d_blocks, rpn_blocks
+
+        self._lib = N.load()
+        dev = torch.device("cuda", device)
+        self.device = dev
+        B = batch
+        f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)  # noqa: E731
+        self.params, self.stages = {}, []
+        self.grid = torch.zeros((B, nz, nx, ny, 64), dtype=torch.bfloat16, device=dev)
+        P = self.params
+        x, d = self.grid, nz
+        self.c3 = []
+        for i, (conv, bn, dense, stride, pad) in enumerate(conv3d_blocks()):
+            P[conv + "/kernel"] = f32(np.asarray(pack[conv + "/kernel"]).reshape(27, 64, 64).transpose(0, 2, 1))
+            P[dense + "/kernel"] = f32(np.asarray(pack[dense + "/kernel"]).T[None])
+            for f in ("bias",):
+                P[conv + "/" + f] = f32(pack[conv + "/" + f])
+            for f in ("gamma", "beta", "moving_mean", "moving_variance"):
+                P[bn + "/" + f] = f32(pack[bn + "/" + f])
+            st = Conv3dBlockTrain(x, P[conv + "/kernel"], P[conv + "/bias"], P[bn + "/gamma"], P[bn + "/beta"],
+                                  P[dense + "/kernel"], (3, 3, 3), pad, stride_d=stride[0],
+                                  moving_mean=P[bn + "/moving_mean"], moving_var=P[bn + "/moving_variance"], need_dx=i > 0)
+            self.c3.append((st, conv, bn, dense))
+            x = st.y
+        assert x.shape[1] == 1
+        self.concat = torch.zeros((B, 1, nx // 2, ny // 2, 768), dtype=torch.bfloat16, device=dev)
+        self.blocks = []
+        for bi, (convs, (tname, k, s, tc_in)) in enumerate(rpn_blocks()):
+            stages = []
+            for conv, bn, cin, cout, stride in convs:
+                P[conv + "/kernel"] = f32(np.asarray(pack[conv + "/kernel"]).reshape(9, cin, cout).transpose(0, 2, 1))
+                P[conv + "/bias"] = f32(pack[conv + "/bias"])
+                for f in ("gamma", "beta", "moving_mean", "moving_variance"):
+                    P[bn + "/" + f] = f32(pack[bn + "/" + f])
+                st = ConvBnReluTrain(x, P[conv + "/kernel"], P[conv + "/bias"], P[bn + "/gamma"], P[bn + "/beta"], (1, 3, 3),
+                                     (0, 1, 1), moving_mean=P[bn + "/moving_mean"], moving_var=P[bn + "/moving_variance"],
+                                     stride_hw=stride)
+                stages.append((st, conv, bn))
+                x = st.bn.y
+            F = np.asarray(pack[tname + "/kernel"], dtype=np.float32)  # (k, k, 256, cin)
+            P[tname + "/bias"] = f32(pack[tname + "/bias"])
+            dy_t = torch.zeros((B, 1, nx // 2, ny // 2, 256), dtype=torch.bfloat16, device=dev)
+            if s == 1:
+                P[tname + "/kernel"] = f32(F[::-1, ::-1].reshape(9, 256, tc_in))  # the flipped-kernel convolution's layout
+                tail = ConvBiasTrain(x, P[tname + "/kernel"], P[tname + "/bias"], (1, 3, 3), (0, 1, 1), self.concat, 256 * bi, dy_t)
+            else:
+                P[tname + "/kernel"] = f32(F)  # Keras layout (k, k, 256, cin)
+                tail = _ShuffleTail(self._lib, x, P[tname + "/kernel"], P[tname + "/bias"], s, self.concat, 256 * bi, dy_t)
+            self.blocks.append((stages, tail, tname, s, dy_t, x))
+        Kh = np.concatenate([np.asarray(pack["ClassificationLayer/kernel"])[0, 0], np.asarray(pack["RegressionLayer/kernel"])[0, 0]], axis=1)
+        P["heads/kernel"] = f32(Kh.T[None])  # [1][16][768]: rows 0-1 ClassificationLayer, 2-15 RegressionLayer
+        P["heads/bias"] = f32(np.concatenate([pack["ClassificationLayer/bias"], pack["RegressionLayer/bias"]]))
+        self.heads = HeadsTrain(self.concat, P["heads/kernel"], P["heads/bias"], dense_slices=True)
+        self.grads = {}
+
+    def forward(self, grid: Optional[torch.Tensor] = None):
+        if grid is not None:
+            self.grid.copy_(grid)
+        for st, *_ in self.c3:
+            st.forward()
+        for stages, tail, *_ in self.blocks:
+            for st, *_ in stages:
+                st.forward()
+            tail.forward()
+        y = self.heads.forward()
+        return y[:, 0, :, :, :2], y[:, 0, :, :, 2:]
+
+    def loss_and_backward(self, y_class: torch.Tensor, y_regress: torch.Tensor) -> torch.Tensor:
+        """loss=['mse','mse'] (:296) on the last forward(), then the backward pass: self.grads[...] afterwards."""
+        y = self.heads.y
+        lc, dc = mse_loss_grad(y[..., :2].contiguous(), y_class.reshape(y[..., :2].shape).contiguous())
+        lr, dr = mse_loss_grad(y[..., 2:].contiguous(), y_regress.reshape(y[..., 2:].shape).contiguous())
+        parts = self.heads.backward(torch.cat([dc, dr], dim=-1))
+        G = self.grads
+        G["heads/kernel"], G["heads/bias"] = self.heads.dw, self.heads.dbias
+        carry = None  # gradient arriving at a block's output from the NEXT block
+        for bi in (2, 1, 0):
+            stages, tail, tname, s, dy_t, x_out = self.blocks[bi]
+            dy_t.copy_(parts[bi])
+            dx = tail.backward()
+            G[tname + "/kernel"], G[tname + "/bias"] = tail.dw, tail.dbias
+            if carry is not None:
+                add_(dx, carry)  # the block's output has two consumers
+            for st, conv, bn in reversed(stages):
+                dx = st.backward(dx)
+                G[conv + "/kernel"], G[conv + "/bias"] = st.dw, st.dbias
+                G[bn + "/gamma"], G[bn + "/beta"] = st.bn.dgamma, st.bn.dbeta
+            carry = dx
+        dx = carry
+        for st, conv, bn, dense in reversed(self.c3):
+            dx = st.backward(dx)
+            G[conv + "/kernel"], G[conv + "/bias"], G[dense + "/kernel"] = st.dw, st.dbias, st.dwd
+            G[bn + "/gamma"], G[bn + "/beta"] = st.bn.dgamma, st.bn.dbeta
+        return lc + lr
+
+    def close(self):
+        for st, *_ in self.c3:
+            st.close()
+        for stages, tail, *_ in self.blocks:
+            for st, *_ in stages:
+                st.close()
+            tail.close()
+        self.heads.close()
+
+
+class _ShuffleTail:
+    """A kernel = stride Conv2DTranspose in training: forward = the pixel-shuffle plan (a 1x1 GEMM with s*s N-tiles of 256
+    columns written to (s*h + i, s*w + j) of a concat slice), backward = ConvTransposeBackward."""
+
+    def __init__(self, lib, x, F, bias, s, concat, ch_off, dy):
+        self._lib, self.x, self.F, self.s = lib, x, F, s
+        B, _, H, W, Cin = x.shape
+        dev = x.device
+        self.w16 = torch.empty((1, s * s * 256, Cin), dtype=torch.bfloat16, device=dev)
+        self.wf = torch.empty((1, s * s * 256, Cin), dtype=torch.float32, device=dev)
+        self.ones = torch.ones(256, dtype=torch.float32, device=dev)
+        self.bwd = ConvTransposeBackward(x, dy, F, s)
+        self.refresh_weights()
+        tile = (16, 8) if W >= 16 else (8, 16)
+        desc = N.lisec_conv_desc(
+            batch=B, in_d=1, in_h=H, in_w=W, in_c=Cin, kd=1, kh=1, kw=1, stride_d=1, stride_hw=1, pad_d=0, pad_h=0, pad_w=0,
+            out_c=256, n_tiles=s * s, shuffle=s, out_pitch=concat.shape[-1], out_ch_off=ch_off, relu=0,
+            out_dtype=N.LISEC_BF16, tile_w=tile[0], tile_h=tile[1], m_tiles=1, in_dtype=N.LISEC_BF16, out_split=0, group_kh=0,
+            reserved=0)
+        self.plan = C.c_void_p()
+        with torch.cuda.device(dev):
+            st = lib.lisec_conv_plan_create(C.byref(desc), C.c_void_p(x.data_ptr()), C.c_void_p(self.w16.data_ptr()),
+                                            C.c_void_p(self.ones.data_ptr()), C.c_void_p(bias.data_ptr()),
+                                            C.c_void_p(concat.data_ptr()), C.byref(self.plan))
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, lib.lisec_conv_last_error().decode("utf-8", "replace"))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.x.device).cuda_stream)
+
+    def refresh_weights(self):
+        self.wf.copy_(self.F.reshape(1, -1, self.F.shape[3]))  # (i, j, co) major, ci contiguous: the plan's [N][C]
+        with torch.cuda.device(self.x.device):
+            st = self._lib.lisec_cast_f32_to_bf16(C.c_void_p(self.wf.data_ptr()), self.wf.numel(), C.c_void_p(self.w16.data_ptr()),
+                                                  self._stream())
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_train_last_error().decode("utf-8", "replace"))
+        self.bwd.refresh_weights()
+
+    def forward(self):
+        with torch.cuda.device(self.x.device):
+            st = self._lib.lisec_conv_plan_run(self.plan, self._stream())
+        if st != N.LISEC_OK:
+            raise N.LisecError(st, self._lib.lisec_conv_last_error().decode("utf-8", "replace"))
+
+    def backward(self):
+        dx = self.bwd.backward()
+        self.dw, self.dbias = self.bwd.dF, self.bwd.dbias
+        return dx
+
+    def close(self):
+        if self.plan:
+            self._lib.lisec_conv_plan_destroy(self.plan)
+            self.plan = None
+        self.bwd.close()

@@ -78,6 +78,12 @@ def forward_train(dense_input: torch.Tensor, p: Dict[str, torch.Tensor], unbiase
         x = torch.cat([pooled.expand(*h.shape[:-2], T, h.shape[-1]), h], dim=-1)  # RepeatLayer + Concatenate
     h = torch.relu(_bn_train(x @ p[VFE_DENSE[2] + "/kernel"], p, VFE_BN[2], stats))  # addFCN(., 64, 64) (:233)
     grid = h.amax(dim=-2)  # MaxPoolingVFELayer(combine=True) (:235): [N, nz, nx, ny, 64]
+    prob, reg = network_forward_train(grid, p, stats, unbiased_4d)
+    return prob, reg, stats, grid
+
+
+def network_forward_train(grid: torch.Tensor, p: Dict[str, torch.Tensor], stats: dict, unbiased_4d: bool = False):
+    """Everything behind the voxel grid [N, nz, nx, ny, 64] in training mode (:236-254): prob, regress."""
     x = grid.permute(0, 4, 1, 2, 3)
     for conv, bn, dense, stride, pad in conv3d_blocks():
         w = p[conv + "/kernel"].permute(4, 3, 0, 1, 2)
@@ -98,7 +104,7 @@ def forward_train(dense_input: torch.Tensor, p: Dict[str, torch.Tensor], unbiase
     for head in ("ClassificationLayer", "RegressionLayer"):
         w = p[head + "/kernel"].permute(3, 2, 0, 1)
         outs.append(F.conv2d(cat, w, p[head + "/bias"]).permute(0, 2, 3, 1))
-    return outs[0], outs[1], stats, grid
+    return outs[0], outs[1]
 
 
 def loss_mse2(prob, regress, y_class, y_regress):
