@@ -351,6 +351,8 @@ int32_t lisec_weights_flip_transpose(const float* w, int32_t kd, int32_t kh, int
                                      void* out_bf16, void* stream);
 /* [async] out = dy where y > 0, else 0 (bf16, n a multiple of 8): ReLU backward where no BatchNormalization precedes it. */
 int32_t lisec_relu_backward(const void* dy, const void* y, int64_t n, void* out, void* stream);
+/* [async] the same from a float32 dy (out stays bf16: it is a tensor-core operand). */
+int32_t lisec_relu_backward_f32(const float* dy, const void* y, int64_t n, void* out, void* stream);
 /* [async] Zero-dilation of a bf16 gradient tensor [batch, d, h, w, channels] into out [batch, out_d, out_h, out_w,
  * channels] (cleared once by the caller): element (d, h, w) lands at (d*stride_d, h*stride_hw, w*stride_hw). The data
  * gradient of a strided convolution is the stride-1 data gradient of the dilated dy. */
@@ -383,6 +385,12 @@ int32_t lisec_bn_train_backward(const void* x, const void* dy, const void* y, in
                                 const float* gamma, const float* mean, const float* invstd, int32_t relu, void* dx,
                                 float* dgamma, float* dbeta, float* mean_g, float* mean_gx, void* workspace,
                                 void* stream);
+/* The same backward pass from a FLOAT32 gradient tensor dy: the gradient arriving at a BatchNormalization has a large
+ * per-channel common mode that the backward pass removes — a bf16 copy of it keeps 8 bits of the wrong part. */
+int32_t lisec_bn_train_backward_f32(const void* x, const float* dy, const void* y, int64_t positions, int32_t channels,
+                                    const float* gamma, const float* mean, const float* invstd, int32_t relu, void* dx,
+                                    float* dgamma, float* dbeta, float* mean_g, float* mean_gx, void* workspace,
+                                    void* stream);
 /* [async] sums[c] = sum over positions of x[p][c] (bf16 in, float32 out): the bias gradient of a convolution from dy. */
 int32_t lisec_channel_sums(const void* x, int64_t positions, int32_t channels, float* sums, void* workspace, void* stream);
 const char* lisec_bn_last_error(void);

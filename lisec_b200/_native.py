@@ -146,10 +146,13 @@ SIGNATURES = {
                                             _VP, _VP, _VP, _VP]),
     "lisec_channel_sums": (C.c_int32, [_VP, C.c_int64, C.c_int32, _VP, _VP, _VP]),
     "lisec_relu_backward": (C.c_int32, [_VP, _VP, C.c_int64, _VP, _VP]),
+    "lisec_relu_backward_f32": (C.c_int32, [_VP, _VP, C.c_int64, _VP, _VP]),
     "lisec_dilate": (C.c_int32, [_VP] + [C.c_int32] * 10 + [_VP, _VP]),
     "lisec_pad_channels_bf16": (C.c_int32, [_VP, C.c_int64, C.c_int32, C.c_int32, _VP, _VP]),
     "lisec_add_bf16": (C.c_int32, [_VP, _VP, C.c_int64, _VP]),
     "lisec_cast_f32_to_bf16": (C.c_int32, [_VP, C.c_int64, _VP, _VP]),
+    "lisec_bn_train_backward_f32": (C.c_int32, [_VP, _VP, _VP, C.c_int64, C.c_int32, _VP, _VP, _VP, C.c_int32, _VP, _VP,
+                                                _VP, _VP, _VP, _VP, _VP]),
     "lisec_bn_last_error": (C.c_char_p, []),
     "lisec_conv_wgrad_workspace_bytes": (C.c_int64, [C.POINTER(lisec_conv_desc)]),
     "lisec_conv_wgrad_plan_create": (C.c_int32, [C.POINTER(lisec_conv_desc), _VP, _VP, _VP, _VP, C.POINTER(_H)]),

@@ -42,12 +42,24 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return v;
 }
 
+// the gradient tensor arriving at a BatchNormalization may be float32: its per-channel common mode is large against what
+// the backward pass keeps, so a bf16 copy of it loses the part that matters
+template <bool F32>
+__device__ __forceinline__ void load_dy8(const void* dy, long long idx8, float (&g)[8]) {
+  if (F32) {
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(dy) + 2 * idx8), b = __ldcs(reinterpret_cast<const float4*>(dy) + 2 * idx8 + 1);
+    g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
+  } else {
+    unpack8(__ldcs(reinterpret_cast<const uint4*>(dy) + idx8), g);
+  }
+}
+
 // Two per-channel sums over the rows a block owns. Thread = (row lane, 8-channel chunk); a block's rows are
 // blockIdx.x, blockIdx.x + gridDim.x, ... in groups of rows_per_iter. MODE 0: (x, x^2). MODE 1: (g, g * xhat) with
 // g = dy masked by y > 0 (relu) and xhat = (x - mean) * invstd.
-template <int MODE>
+template <int MODE, bool DYF32 = false>
 __global__ void __launch_bounds__(kBnThreads)
-    bn_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+    bn_reduce_kernel(const __nv_bfloat16* __restrict__ x, const void* __restrict__ dy,
                      const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ invstd,
                      long long P, int C, int relu, double* __restrict__ partial) {
   pdl_launch_dependents();
@@ -77,7 +89,7 @@ __global__ void __launch_bounds__(kBnThreads)
         }
       } else {
         float g[8], yv[8];
-        unpack8(*reinterpret_cast<const uint4*>(dy + r * C + 8 * chunk), g);
+        load_dy8<DYF32>(dy, (r * C + 8 * chunk) >> 3, g);
         if (relu) unpack8(*reinterpret_cast<const uint4*>(y + r * C + 8 * chunk), yv);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -176,8 +188,9 @@ __global__ void __launch_bounds__(kBnThreads)
   }
 }
 
+template <bool DYF32>
 __global__ void __launch_bounds__(kBnThreads)
-    bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+    bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const void* __restrict__ dy,
                         const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
                         const float* __restrict__ invstd, const float* __restrict__ gamma,
                         const float* __restrict__ mean_g, const float* __restrict__ mean_gx, long long n8, int chunks,
@@ -189,7 +202,7 @@ __global__ void __launch_bounds__(kBnThreads)
     const int c0 = (int)(i % chunks) * 8;
     float xv[8], g[8], yv[8], o[8];
     unpack8(__ldcs(reinterpret_cast<const uint4*>(x) + i), xv);
-    unpack8(__ldcs(reinterpret_cast<const uint4*>(dy) + i), g);
+    load_dy8<DYF32>(dy, i, g);
     if (relu) unpack8(__ldcs(reinterpret_cast<const uint4*>(y) + i), yv);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -281,7 +294,9 @@ int32_t lisec_channel_sums(const void* x, int64_t positions, int32_t channels, f
   return LISEC_OK;
 }
 
-int32_t lisec_bn_train_backward(const void* x, const void* dy, const void* y, int64_t positions, int32_t channels,
+}  // extern "C"
+
+static int32_t bn_backward_impl(const void* x, const void* dy, int dy_f32, const void* y, int64_t positions, int32_t channels,
                                 const float* gamma, const float* mean, const float* invstd, int32_t relu, void* dx,
                                 float* dgamma, float* dbeta, float* mean_g, float* mean_gx, void* workspace,
                                 void* stream) {
@@ -292,10 +307,12 @@ int32_t lisec_bn_train_backward(const void* x, const void* dy, const void* y, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int blocks = bn_blocks(positions, channels);
   double* part = static_cast<double*>(workspace);
-  const __nv_bfloat16 *xb = static_cast<const __nv_bfloat16*>(x), *dyb = static_cast<const __nv_bfloat16*>(dy),
-                      *yb = static_cast<const __nv_bfloat16*>(relu ? y : x);
-  cudaError_t e = launch_pdl(bn_reduce_kernel<1>, dim3(blocks), dim3(kBnThreads), 0, st, xb, dyb, yb, mean, invstd,
-                             (long long)positions, (int)channels, (int)relu, part);
+  const __nv_bfloat16 *xb = static_cast<const __nv_bfloat16*>(x), *yb = static_cast<const __nv_bfloat16*>(relu ? y : x);
+  const void* dyb = dy;
+  cudaError_t e = dy_f32 ? launch_pdl(bn_reduce_kernel<1, true>, dim3(blocks), dim3(kBnThreads), 0, st, xb, dyb, yb, mean, invstd,
+                                      (long long)positions, (int)channels, (int)relu, part)
+                         : launch_pdl(bn_reduce_kernel<1, false>, dim3(blocks), dim3(kBnThreads), 0, st, xb, dyb, yb, mean, invstd,
+                                      (long long)positions, (int)channels, (int)relu, part);
   if (e == cudaSuccess)
     e = launch_pdl(bn_finalize_kernel<1>, dim3(1), dim3(kBnMaxC), 0, st, (const double*)part, blocks, (long long)positions,
                    (int)channels, 0.f, 0.f, gamma, gamma, dgamma, dbeta, mean_g, mean_gx, (float*)nullptr, (float*)nullptr);
@@ -303,11 +320,33 @@ int32_t lisec_bn_train_backward(const void* x, const void* dy, const void* y, in
   long long ab = (n8 + kBnThreads - 1) / kBnThreads;
   if (ab > 148 * 16) ab = 148 * 16;
   if (e == cudaSuccess)
-    e = launch_pdl(bn_bwd_apply_kernel, dim3((unsigned)ab), dim3(kBnThreads), 0, st, xb, dyb, yb, mean, invstd, gamma,
-                   (const float*)mean_g, (const float*)mean_gx, n8, (int)(channels / 8), (int)relu,
-                   static_cast<__nv_bfloat16*>(dx));
+    e = dy_f32 ? launch_pdl(bn_bwd_apply_kernel<true>, dim3((unsigned)ab), dim3(kBnThreads), 0, st, xb, dyb, yb, mean, invstd,
+                            gamma, (const float*)mean_g, (const float*)mean_gx, n8, (int)(channels / 8), (int)relu,
+                            static_cast<__nv_bfloat16*>(dx))
+               : launch_pdl(bn_bwd_apply_kernel<false>, dim3((unsigned)ab), dim3(kBnThreads), 0, st, xb, dyb, yb, mean, invstd,
+                            gamma, (const float*)mean_g, (const float*)mean_gx, n8, (int)(channels / 8), (int)relu,
+                            static_cast<__nv_bfloat16*>(dx));
   if (e != cudaSuccess) return bn_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
   return LISEC_OK;
+}
+
+
+extern "C" {
+
+int32_t lisec_bn_train_backward(const void* x, const void* dy, const void* y, int64_t positions, int32_t channels,
+                                const float* gamma, const float* mean, const float* invstd, int32_t relu, void* dx,
+                                float* dgamma, float* dbeta, float* mean_g, float* mean_gx, void* workspace,
+                                void* stream) {
+  return bn_backward_impl(x, dy, 0, y, positions, channels, gamma, mean, invstd, relu, dx, dgamma, dbeta, mean_g, mean_gx,
+                          workspace, stream);
+}
+
+int32_t lisec_bn_train_backward_f32(const void* x, const float* dy, const void* y, int64_t positions, int32_t channels,
+                                    const float* gamma, const float* mean, const float* invstd, int32_t relu, void* dx,
+                                    float* dgamma, float* dbeta, float* mean_g, float* mean_gx, void* workspace,
+                                    void* stream) {
+  return bn_backward_impl(x, dy, 1, y, positions, channels, gamma, mean, invstd, relu, dx, dgamma, dbeta, mean_g, mean_gx,
+                          workspace, stream);
 }
 
 }  // extern "C"

@@ -128,6 +128,16 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const uint4* __restrict__
   }
 }
 
+// the same from a float32 gradient (the gradient tensors between stages are float32): out bf16
+__global__ void __launch_bounds__(256) relu_bwd_f32_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                                                           long long n, __nv_bfloat16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = __float2bfloat16(__bfloat162float(y[i]) > 0.f ? dy[i] : 0.f);
+}
+
 // Zero-dilation of a gradient tensor: the data gradient of a STRIDED convolution is the stride-1 data gradient of dy with
 // (stride - 1) zeros between its positions (and k - 1 - pad zeros around it, which the plan's own padding provides).
 // out [B, (D-1)*sd+1 + ed, (H-1)*s+1 + eh, (W-1)*s+1 + ew, C] is cleared by the caller once; the zeros never change.
@@ -242,6 +252,17 @@ int32_t lisec_relu_backward(const void* dy, const void* y, int64_t n, void* out,
   cudaError_t e = launch_pdl(relu_bwd_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream),
                              static_cast<const uint4*>(dy), static_cast<const uint4*>(y), (long long)(n / 8),
                              static_cast<uint4*>(out));
+  if (e != cudaSuccess) return train_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
+  return LISEC_OK;
+}
+
+int32_t lisec_relu_backward_f32(const float* dy, const void* y, int64_t n, void* out, void* stream) {
+  if (n < 0 || (n > 0 && (!dy || !y || !out))) return train_fail(LISEC_ERR_BAD_ARG, "bad argument");
+  if (n == 0) return LISEC_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cudaError_t e = launch_pdl(relu_bwd_f32_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), dy,
+                             static_cast<const __nv_bfloat16*>(y), (long long)n, static_cast<__nv_bfloat16*>(out));
   if (e != cudaSuccess) return train_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
   return LISEC_OK;
 }

@@ -266,10 +266,11 @@ class BatchNormTrain:
         return self.y
 
     def backward(self, dy: torch.Tensor) -> torch.Tensor:
-        if dy.dtype != torch.bfloat16 or dy.shape != self.x.shape:
-            raise ValueError("dy: bf16 of x's shape")
+        if dy.dtype not in (torch.bfloat16, torch.float32) or dy.shape != self.x.shape:
+            raise ValueError("dy: bf16 or float32 of x's shape")
+        fn = self._lib.lisec_bn_train_backward if dy.dtype == torch.bfloat16 else self._lib.lisec_bn_train_backward_f32
         with torch.cuda.device(self.x.device):
-            st = self._lib.lisec_bn_train_backward(
+            st = fn(
                 self._p(self.x), self._p(dy.contiguous()), self._p(self.y), self.P, self.C, self._p(self.gamma),
                 self._p(self.mean), self._p(self.invstd), int(self.relu), self._p(self.dx), self._p(self.dgamma),
                 self._p(self.dbeta), self._p(self._mg), self._p(self._mgx), self._p(self.workspace), self._stream())
@@ -286,7 +287,7 @@ class ConvBnReluTrain:
     [taps, N, C], bias / gamma / beta float32 [N] (views into FlatParameters in a full model)."""
 
     def __init__(self, x: torch.Tensor, w, bias, gamma, beta, k, pad, relu=True, moving_mean=None, moving_var=None,
-                 need_dx=True, tile=None, stride_hw: int = 1):
+                 need_dx=True, tile=None, stride_hw: int = 1, grad_dtype=torch.bfloat16):
         self._lib = N.load()
         B, D, H, W, Cin = x.shape
         taps, Nout, c2 = w.shape
@@ -319,7 +320,8 @@ class ConvBnReluTrain:
         self.wgrad = ConvWgrad(x, self.bn.dx, k, 1, pad, tile=tile, stride_hw=s)  # dz lands in bn.dx
         self.dgrad = None
         if need_dx:
-            self.dgrad = ConvDgrad(self.bn.dx, w, k, pad) if s == 1 else ConvDgradStrided(self.bn.dx, w, k, pad, 1, s, (D, H, W))
+            self.dgrad = (ConvDgrad(self.bn.dx, w, k, pad, out_dtype=grad_dtype) if s == 1 else
+                          ConvDgradStrided(self.bn.dx, w, k, pad, 1, s, (D, H, W), out_dtype=grad_dtype))
         self.dbias = torch.empty(Nout, dtype=torch.float32, device=dev)
 
     def _stream(self):
@@ -406,6 +408,8 @@ class ConvDgradStrided:
 
 def add_(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """a += b on bf16 device tensors (lisec_add_bf16): gradient accumulation where a tensor has two consumers."""
+    if a.dtype == torch.float32 and b.dtype == torch.float32 and a.shape == b.shape:
+        return a.add_(b)  # float32 gradient tensors: torch's elementwise add (plumbing between stages)
     if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or a.shape != b.shape or not a.is_cuda or not a.is_contiguous():
         raise ValueError("a, b: contiguous cuda bf16 tensors of one shape")
     lib = N.load()
@@ -419,13 +423,14 @@ def add_(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 def relu_backward(dy: torch.Tensor, y: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dy masked by y > 0 (bf16): the ReLU behind the Dense of a Conv3D block (model_training.py:195)."""
-    if dy.dtype != torch.bfloat16 or y.dtype != torch.bfloat16 or dy.shape != y.shape or not dy.is_cuda:
-        raise ValueError("dy, y: cuda bf16 of one shape")
+    if dy.dtype not in (torch.bfloat16, torch.float32) or y.dtype != torch.bfloat16 or dy.shape != y.shape or not dy.is_cuda:
+        raise ValueError("dy (bf16 or float32), y (bf16): cuda tensors of one shape")
     lib = N.load()
-    out = torch.empty_like(dy) if out is None else out
+    out = torch.empty_like(y) if out is None else out
+    fn = lib.lisec_relu_backward if dy.dtype == torch.bfloat16 else lib.lisec_relu_backward_f32
     with torch.cuda.device(dy.device):
-        st = lib.lisec_relu_backward(C.c_void_p(dy.contiguous().data_ptr()), C.c_void_p(y.contiguous().data_ptr()), dy.numel(),
-                                     C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream(dy.device).cuda_stream))
+        st = fn(C.c_void_p(dy.contiguous().data_ptr()), C.c_void_p(y.contiguous().data_ptr()), dy.numel(),
+                C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream(dy.device).cuda_stream))
     if st != N.LISEC_OK:
         raise N.LisecError(st, lib.lisec_train_last_error().decode("utf-8", "replace"))
     return out
@@ -438,7 +443,7 @@ class Conv3dBlockTrain:
     plans' [tap][out][in] layout), all float32 on the device."""
 
     def __init__(self, x: torch.Tensor, w, bias, gamma, beta, wd, k, pad, stride_d=1, moving_mean=None, moving_var=None,
-                 need_dx=True):
+                 need_dx=True, grad_dtype=torch.bfloat16):
         self._lib = N.load()
         B, D, H, W, Cin = x.shape
         taps, Nout, _ = w.shape
@@ -477,12 +482,12 @@ class Conv3dBlockTrain:
         self.conv_plan = plan(x, self.w16, bias, self.z, k, pad, stride_d, Cin, Nout, 0)
         self.dense_plan = plan(self.bn.y, self.wd16, self.zeros, self.y, (1, 1, 1), (0, 0, 0), 1, Nout, N2, 1)
         self.dense_wgrad = ConvWgrad(self.bn.y, self.dv, (1, 1, 1), 1, (0, 0, 0), tile=tile)
-        self.dense_dgrad = ConvDgrad(self.dv, wd, (1, 1, 1), (0, 0, 0))            # du: gradient at the BN output
+        self.dense_dgrad = ConvDgrad(self.dv, wd, (1, 1, 1), (0, 0, 0), out_dtype=grad_dtype)  # du: gradient at the BN output
         self.conv_wgrad = ConvWgrad(x, self.bn.dx, k, stride_d, pad, tile=tile)    # dz lands in bn.dx
         self.conv_dgrad = None
         if need_dx:
-            self.conv_dgrad = (ConvDgrad(self.bn.dx, w, k, pad) if stride_d == 1 else
-                               ConvDgradStrided(self.bn.dx, w, k, pad, stride_d, 1, (D, H, W)))
+            self.conv_dgrad = (ConvDgrad(self.bn.dx, w, k, pad, out_dtype=grad_dtype) if stride_d == 1 else
+                               ConvDgradStrided(self.bn.dx, w, k, pad, stride_d, 1, (D, H, W), out_dtype=grad_dtype))
         self._dgrads = [self.dense_dgrad] + ([self.conv_dgrad] if self.conv_dgrad is not None else [])
         self.dbias = torch.empty(Nout, dtype=torch.float32, device=dev)
 
@@ -643,7 +648,8 @@ class ConvBiasTrain:
     this one. Forward writes into a channel slice of a wider buffer (out_pitch / out_ch_off: the concat tensor); backward
     takes a DENSE dy [B,D,H,W,N]. w: float32 [taps, N, C] in the plans' layout, bias float32 [N]."""
 
-    def __init__(self, x: torch.Tensor, w, bias, k, pad, out: torch.Tensor, out_ch_off: int, dy: torch.Tensor, need_dx=True):
+    def __init__(self, x: torch.Tensor, w, bias, k, pad, out: torch.Tensor, out_ch_off: int, dy: torch.Tensor, need_dx=True,
+                 grad_dtype=torch.bfloat16):
         self._lib = N.load()
         B, D, H, W, Cin = x.shape
         taps, Nout, _ = w.shape
@@ -657,7 +663,7 @@ class ConvBiasTrain:
             pad_h=pad[1], pad_w=pad[2], out_c=Nout, n_tiles=1, shuffle=1, out_pitch=out.shape[-1], out_ch_off=out_ch_off,
             relu=0, out_dtype=N.LISEC_BF16, tile_w=tile[0], tile_h=tile[1], m_tiles=1, in_dtype=N.LISEC_BF16, out_split=0,
             group_kh=0, reserved=0)
-        self.dgrad = ConvDgrad(dy, w, k, pad) if need_dx else None
+        self.dgrad = ConvDgrad(dy, w, k, pad, out_dtype=grad_dtype) if need_dx else None
         self.refresh_weights()
         self.plan = C.c_void_p()
         with torch.cuda.device(dev):
@@ -715,7 +721,7 @@ class ConvTransposeBackward:
     kh = s taps and no padding, and dF the matching weight gradient — both on the existing tensor-core kernels.
     F: float32 [s, s, Co, Ci] (the Keras layout); dy: bf16 dense [B, 1, s*H, s*W, Co]; x: bf16 [B, 1, H, W, Ci]."""
 
-    def __init__(self, x: torch.Tensor, dy: torch.Tensor, F: torch.Tensor, s: int):
+    def __init__(self, x: torch.Tensor, dy: torch.Tensor, F: torch.Tensor, s: int, grad_dtype=torch.bfloat16):
         self._lib = N.load()
         B, _, H, W, Ci = x.shape
         Co = dy.shape[-1]
@@ -729,13 +735,14 @@ class ConvTransposeBackward:
         # dx: weights [tap = i][n = ci][c = (j, co)]
         self.w = torch.empty((s, Ci, s * Co), dtype=torch.float32, device=dev)
         self.w16 = torch.empty((s, Ci, s * Co), dtype=torch.bfloat16, device=dev)
-        self.dx = torch.empty((B, H, 1, W, Ci), dtype=torch.bfloat16, device=dev)
+        self.dx = torch.empty((B, H, 1, W, Ci), dtype=grad_dtype, device=dev)
         self.ones = torch.ones(Ci, dtype=torch.float32, device=dev)
         self.zeros = torch.zeros(Ci, dtype=torch.float32, device=dev)
         self.refresh_weights()
         desc = N.lisec_conv_desc(
             batch=B, in_d=H, in_h=s, in_w=W, in_c=s * Co, kd=1, kh=s, kw=1, stride_d=1, stride_hw=1, pad_d=0, pad_h=0,
-            pad_w=0, out_c=Ci, n_tiles=1, shuffle=1, out_pitch=Ci, out_ch_off=0, relu=0, out_dtype=N.LISEC_BF16,
+            pad_w=0, out_c=Ci, n_tiles=1, shuffle=1, out_pitch=Ci, out_ch_off=0, relu=0,
+            out_dtype=N.LISEC_BF16 if grad_dtype == torch.bfloat16 else N.LISEC_F32,
             tile_w=tile[0], tile_h=tile[1], m_tiles=1, in_dtype=N.LISEC_BF16, out_split=0, group_kh=0, reserved=0)
         self.plan = C.c_void_p()
         with torch.cuda.device(dev):
@@ -816,7 +823,8 @@ class DenseNetworkTrainer:
                 P[bn + "/" + f] = f32(pack[bn + "/" + f])
             st = Conv3dBlockTrain(x, P[conv + "/kernel"], P[conv + "/bias"], P[bn + "/gamma"], P[bn + "/beta"],
                                   P[dense + "/kernel"], (3, 3, 3), pad, stride_d=stride[0],
-                                  moving_mean=P[bn + "/moving_mean"], moving_var=P[bn + "/moving_variance"], need_dx=i > 0)
+                                  moving_mean=P[bn + "/moving_mean"], moving_var=P[bn + "/moving_variance"], need_dx=i > 0,
+                                  grad_dtype=torch.float32)
             self.c3.append((st, conv, bn, dense))
             x = st.y
         assert x.shape[1] == 1
@@ -831,7 +839,7 @@ class DenseNetworkTrainer:
                     P[bn + "/" + f] = f32(pack[bn + "/" + f])
                 st = ConvBnReluTrain(x, P[conv + "/kernel"], P[conv + "/bias"], P[bn + "/gamma"], P[bn + "/beta"], (1, 3, 3),
                                      (0, 1, 1), moving_mean=P[bn + "/moving_mean"], moving_var=P[bn + "/moving_variance"],
-                                     stride_hw=stride)
+                                     stride_hw=stride, grad_dtype=torch.float32)
                 stages.append((st, conv, bn))
                 x = st.bn.y
             F = np.asarray(pack[tname + "/kernel"], dtype=np.float32)  # (k, k, 256, cin)
@@ -839,7 +847,8 @@ class DenseNetworkTrainer:
             dy_t = torch.zeros((B, 1, nx // 2, ny // 2, 256), dtype=torch.bfloat16, device=dev)
             if s == 1:
                 P[tname + "/kernel"] = f32(F[::-1, ::-1].reshape(9, 256, tc_in))  # the flipped-kernel convolution's layout
-                tail = ConvBiasTrain(x, P[tname + "/kernel"], P[tname + "/bias"], (1, 3, 3), (0, 1, 1), self.concat, 256 * bi, dy_t)
+                tail = ConvBiasTrain(x, P[tname + "/kernel"], P[tname + "/bias"], (1, 3, 3), (0, 1, 1), self.concat, 256 * bi, dy_t,
+                                     grad_dtype=torch.float32)
             else:
                 P[tname + "/kernel"] = f32(F)  # Keras layout (k, k, 256, cin)
                 tail = _ShuffleTail(self._lib, x, P[tname + "/kernel"], P[tname + "/bias"], s, self.concat, 256 * bi, dy_t)
@@ -911,7 +920,7 @@ class _ShuffleTail:
         self.w16 = torch.empty((1, s * s * 256, Cin), dtype=torch.bfloat16, device=dev)
         self.wf = torch.empty((1, s * s * 256, Cin), dtype=torch.float32, device=dev)
         self.ones = torch.ones(256, dtype=torch.float32, device=dev)
-        self.bwd = ConvTransposeBackward(x, dy, F, s)
+        self.bwd = ConvTransposeBackward(x, dy, F, s, grad_dtype=torch.float32)
         self.refresh_weights()
         tile = (16, 8) if W >= 16 else (8, 16)
         desc = N.lisec_conv_desc(

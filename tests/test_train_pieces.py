@@ -115,6 +115,7 @@ def test_gpu_mse_loss_and_gradient():
     dict(B=2, D=1, H=24, W=40, C=64, N=128, k=(1, 3, 3), sd=1, pad=(0, 1, 1), shw=2),  # first conv of an RPN block: stride 2
     dict(B=1, D=1, H=18, W=22, C=128, N=256, k=(1, 3, 3), sd=1, pad=(0, 1, 1), shw=2),
     dict(B=2, D=1, H=12, W=20, C=768, N=64, k=(1, 1, 1), sd=1, pad=(0, 0, 0)),   # the heads' 768 input channels (dy padded to 64)
+    dict(B=2, D=1, H=3, W=5, C=256, N=256, k=(1, 3, 3), sd=1, pad=(0, 1, 1)),    # a map smaller than one tile
 ])
 def test_gpu_conv_wgrad_matches_autograd(case):
     """dW from conv_wgrad_kernel against torch CPU float64 autograd of the same convolution on the same bf16 tensors."""
