@@ -82,23 +82,33 @@ def forward_train(dense_input: torch.Tensor, p: Dict[str, torch.Tensor], unbiase
     return prob, reg, stats, grid
 
 
-def network_forward_train(grid: torch.Tensor, p: Dict[str, torch.Tensor], stats: dict, unbiased_4d: bool = False):
-    """Everything behind the voxel grid [N, nz, nx, ny, 64] in training mode (:236-254): prob, regress."""
+def _bf16_ste(x):
+    """Round to bfloat16 in the forward pass, identity in the backward pass (straight-through): the float64 gradient of a
+    network whose stored activations are bf16 — what a mixed-precision implementation computes up to float32 effects."""
+    return x + (x.detach().to(torch.bfloat16).to(x.dtype) - x.detach())
+
+
+def network_forward_train(grid: torch.Tensor, p: Dict[str, torch.Tensor], stats: dict, unbiased_4d: bool = False,
+                          bf16_activations: bool = False):
+    """Everything behind the voxel grid [N, nz, nx, ny, 64] in training mode (:236-254): prob, regress.
+    bf16_activations: every tensor the GPU chain stores in bf16 (convolution outputs, BN outputs, Dense outputs, the
+    concat tensor) is rounded to bf16 on the way forward."""
+    q = _bf16_ste if bf16_activations else (lambda t: t)
     x = grid.permute(0, 4, 1, 2, 3)
     for conv, bn, dense, stride, pad in conv3d_blocks():
         w = p[conv + "/kernel"].permute(4, 3, 0, 1, 2)
-        x = F.conv3d(x, w, p[conv + "/bias"], stride=stride, padding=pad)
-        x = _bn_train(x, p, bn, stats, channels_last=False)
-        x = torch.relu(torch.einsum("ncdhw,ck->nkdhw", x, p[dense + "/kernel"]))
+        x = q(F.conv3d(x, w, p[conv + "/bias"], stride=stride, padding=pad))
+        x = q(_bn_train(x, p, bn, stats, channels_last=False))
+        x = q(torch.relu(torch.einsum("ncdhw,ck->nkdhw", x, p[dense + "/kernel"])))
     x = x[:, :, 0]
     ups = []
     for convs, (tname, k, s, _) in rpn_blocks():
         for conv, bn, _, _, stride in convs:
             w = p[conv + "/kernel"].permute(3, 2, 0, 1)
-            x = F.conv2d(x, w, p[conv + "/bias"], stride=stride, padding=1)
-            x = torch.relu(_bn_train(x, p, bn, stats, channels_last=False, unbiased_moving=unbiased_4d))
+            x = q(F.conv2d(x, w, p[conv + "/bias"], stride=stride, padding=1))
+            x = q(torch.relu(_bn_train(x, p, bn, stats, channels_last=False, unbiased_moving=unbiased_4d)))
         wt = p[tname + "/kernel"].permute(3, 2, 0, 1)
-        ups.append(F.conv_transpose2d(x, wt, p[tname + "/bias"], stride=s, padding=(k - s) // 2))
+        ups.append(q(F.conv_transpose2d(x, wt, p[tname + "/bias"], stride=s, padding=(k - s) // 2)))
     cat = torch.cat(ups, dim=1)
     outs = []
     for head in ("ClassificationLayer", "RegressionLayer"):

@@ -8,8 +8,9 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("nx,ny,B,keras_init", [(24, 40, 2, False), (48, 80, 2, True)])
-def test_dense_network_training_forward_loss_and_gradients(nx, ny, B, keras_init):
+@pytest.mark.parametrize("nx,ny,B,keras_init,bf16_oracle", [(24, 40, 2, False, False), (48, 80, 2, True, False),
+                                                            (24, 40, 2, False, True)])
+def test_dense_network_training_forward_loss_and_gradients(nx, ny, B, keras_init, bf16_oracle):
     from lisec_b200.train import DenseNetworkTrainer
     from lisec_b200.weights import synthetic_network_pack
     from oracle import train_oracle as TO
@@ -40,7 +41,7 @@ def test_dense_network_training_forward_loss_and_gradients(nx, ny, B, keras_init
     torch.cuda.synchronize()
 
     p = TO.to_params(pack)
-    want_p, want_r = TO.network_forward_train(grid.double(), p, {})
+    want_p, want_r = TO.network_forward_train(grid.double(), p, {}, bf16_activations=bf16_oracle)
     want_loss = TO.loss_mse2(want_p, want_r, yc.double(), yr.double())
     names = [k for k, t in p.items() if t.requires_grad]
     grads = dict(zip(names, torch.autograd.grad(want_loss, [p[k] for k in names])))
@@ -92,7 +93,8 @@ def test_dense_network_training_forward_loss_and_gradients(nx, ny, B, keras_init
     # Everything further back keeps direction and size (cosine 0.73-0.93 against float64, norms within 25 %) but not more.
     # NOT YET EXPLAINED: every stage is exact in isolation with random inputs (tests/test_train_pieces.py), and the
     # discrepancy does not depend on the grid size, on the weights (seeded synthetic or Keras-style initial) or on the
-    # precision of the gradient tensors between the stages (bf16 or float32: same numbers) — see DESIGN.md §4e.
+    # precision of the gradient tensors between the stages (bf16 or float32: same numbers), nor on rounding the oracle's
+    # stored activations to bf16 (third case) — see DESIGN.md §4e.
     rest = [k for k in worst if k not in tight]
     assert all(cosines[k] >= 0.7 for k in rest), {k: cosines[k] for k in rest if cosines[k] < 0.7}
     assert all(0.8 <= ratios[k] <= 1.25 for k in rest), {k: ratios[k] for k in rest if not 0.8 <= ratios[k] <= 1.25}
