@@ -90,11 +90,11 @@ def test_dense_network_training_forward_loss_and_gradients(nx, ny, B, keras_init
                                                       "conv2d_transpose_1", "conv2d_transpose_2", "batch_normalization_9",
                                                       "batch_normalization_15", "batch_normalization_21")]
     assert len(tight) == 16 and all(worst[k] <= 0.15 for k in tight), {k: worst[k] for k in tight}
-    # Everything further back keeps direction and size (cosine 0.73-0.93 against float64, norms within 25 %) but not more.
-    # NOT YET EXPLAINED: every stage is exact in isolation with random inputs (tests/test_train_pieces.py), and the
-    # discrepancy does not depend on the grid size, on the weights (seeded synthetic or Keras-style initial) or on the
-    # precision of the gradient tensors between the stages (bf16 or float32: same numbers), nor on rounding the oracle's
-    # stored activations to bf16 (third case) — see DESIGN.md §4e.
+    # Everything further back keeps direction and size (cosine 0.73-0.93 against float64, norms within 25 %) but not more:
+    # the chained forward drifts from float64 by x1.17 per stage (0.17 % after one bf16 rounding, 11 % after 22 stages —
+    # tools/bisect_train_chain.py: smooth growth, no jump, i.e. no semantic difference), because every layer is
+    # renormalised by its own batch statistics; the parameter gradients there are weak correlations and amplify it.
+    # Independent of grid size, weights, the gradient tensors' precision and bf16 rounding in the oracle.
     rest = [k for k in worst if k not in tight]
     assert all(cosines[k] >= 0.7 for k in rest), {k: cosines[k] for k in rest if cosines[k] < 0.7}
     assert all(0.8 <= ratios[k] <= 1.25 for k in rest), {k: ratios[k] for k in rest if not 0.8 <= ratios[k] <= 1.25}
