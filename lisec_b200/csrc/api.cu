@@ -84,7 +84,7 @@ cudaError_t dev_alloc(lisec_handle* h, T** p, size_t n) {
 
 void free_workspace(Workspace& w) {
   void* ptrs[] = {w.count, w.cell_voxel, w.cell_of_point, w.list_unsorted, w.list_sorted, w.entry_voxel,
-                  w.voxel_cell, w.voxel_start, w.row_start, w.tile_first, w.tile_row0, w.row_voxel, w.row_feat,
+                  w.voxel_cell, w.voxel_start, w.row_start, w.tile_first, w.tile_row0, w.row_voxel, w.row_xyz,
                   w.block_sums, w.sweep_voxel_start,
                   w.totals, w.voxel_feat, w.c_empty, w.vfe_w, w.staging, w.empty_desc, w.trace};
   for (void* p : ptrs)
@@ -120,7 +120,7 @@ int do_voxelize(lisec_handle* h, const void* points, int dtype, const SweepOffse
   h->count_dirty = true;  // until the fill pass has been enqueued
   LISEC_CUDA(h, launch_point_pass(points, dtype, n_total, so, h->geom, h->ws, st, &h->launches));
   LISEC_CUDA(h, launch_cell_scan(so, h->geom, h->ws, h->scan_blocks_cap, st, &h->launches));
-  LISEC_CUDA(h, launch_fill_and_order(n_total, h->geom, h->rows_per_tile, h->ws, st, &h->launches));
+  LISEC_CUDA(h, launch_fill_and_order(points, dtype, n_total, h->geom, h->rows_per_tile, h->ws, st, &h->launches));
   h->count_dirty = false;
   h->last_points = points;
   h->last_dtype = dtype;
@@ -129,9 +129,13 @@ int do_voxelize(lisec_handle* h, const void* points, int dtype, const SweepOffse
   return LISEC_OK;
 }
 
+VfeProblem vfe_problem(const lisec_handle* h) {
+  return VfeProblem{h->ws.tile_first, h->ws.tile_row0, h->ws.row_voxel, h->ws.row_xyz,
+                    h->ws.row_start,  h->ws.totals + TOT_TILES, h->last_dtype};
+}
+
 int do_vfe(lisec_handle* h, float* voxel_feat, cudaStream_t st) {
-  LISEC_CUDA(h, launch_row_features(h->last_points, h->last_dtype, h->geom, h->ws, 2 * h->last_so.off[h->last_so.n], st, &h->launches));
-  const VfeProblem prob{h->ws.tile_first, h->ws.tile_row0, h->ws.row_voxel, h->ws.row_feat, h->ws.totals + TOT_TILES};
+  const VfeProblem prob = vfe_problem(h);
   LISEC_CUDA(h, launch_vfe(h->params, h->ws.vfe_w, prob, voxel_feat, h->sm_count, st, &h->launches,
                            reinterpret_cast<long long*>(h->ws.trace)));
   return LISEC_OK;
@@ -230,7 +234,7 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
   LISEC_CUDA(h, dev_alloc(h, &w.tile_first, (size_t)h->max_tiles + 2));
   LISEC_CUDA(h, dev_alloc(h, &w.tile_row0, (size_t)h->max_tiles + 2));
   LISEC_CUDA(h, dev_alloc(h, &w.row_voxel, P + V));
-  LISEC_CUDA(h, dev_alloc(h, &w.row_feat, 6 * (P + V)));
+  LISEC_CUDA(h, dev_alloc(h, reinterpret_cast<unsigned char**>(&w.row_xyz), 3 * sizeof(double) * (P + V)));
   LISEC_CUDA(h, dev_alloc(h, &w.block_sums, (size_t)3 * h->scan_blocks_cap + 4));
   LISEC_CUDA(h, dev_alloc(h, &w.sweep_voxel_start, (size_t)c.max_sweeps + 2));
   LISEC_CUDA(h, dev_alloc(h, &w.totals, (size_t)TOT_COUNT));
@@ -256,8 +260,9 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
   for (int b = 0; b < 2; ++b) LISEC_CUDA(h, cudaEventCreate(&h->ev_kernel[b]));
   LISEC_CUDA(h, dev_alloc(h, &w.empty_desc, (size_t)16));
   // the one-voxel problem whose VFE output is c_empty: 0 kept points, 1 pad row, 1 tile
-  // layout: tile_first {0,1} | tile_row0 {0,1} | n_tiles (int64) 1 | row_voxel {0} | pad | row_feat 6 x 0.f
-  int desc[16] = {0, 1, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  // layout: tile_first {0,1} | tile_row0 {0,1} = row_start {0,1} | n_tiles (int64) 1 | row_voxel {0 | pad flag} | pad |
+  //         row_xyz: 3 doubles (never used: the row is a pad row)
+  int desc[16] = {0, 1, 0, 1, 0, 0, kRowPadFlag, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const long long one = 1;
   std::memcpy(&desc[4], &one, sizeof(one));
   LISEC_CUDA(h, cudaMemcpy(w.empty_desc, desc, sizeof(desc), cudaMemcpyHostToDevice));
@@ -299,7 +304,10 @@ int32_t lisec_set_vfe_weights(lisec_handle* h, const lisec_vfe_weights* w, void*
   VfeSmall& p = h->params;
   const float* k0 = w->dense_kernel[0];
   for (int k = 0; k < 6; ++k)
-    for (int j = 0; j < 16; ++j) p.w1f[k][j] = k0[k * 16 + j];
+    for (int j = 0; j < 16; ++j) {
+      p.w1f[k][j] = k0[k * 16 + j];
+      if (k < 3) p.w1d[k][j] = (double)k0[k * 16 + j];
+    }
   // BatchNormalization at inference (Keras defaults, model_training.py:171): y = x*a + b
   float* A[3] = {p.a1, p.a2, p.a3};
   float* B[3] = {p.b1, p.b2, p.b3};
@@ -318,11 +326,11 @@ int32_t lisec_set_vfe_weights(lisec_handle* h, const lisec_vfe_weights* w, void*
     sgn3[m] = p.a3[m] < 0.f ? -1.f : 1.f;
     p.a3[m] = std::fabs(p.a3[m]);
   }
-  // blob = [W2P | W2X | W3^T hi image | W3^T lo image]; a Keras kernel is (C_in, C_out) row-major with the pooled
-  // half's rows first. dense_2 runs on the tensor core as 3xTF32: each weight is split into hi = rn_tf32(w) and
-  // lo = rn_tf32(w - hi) and laid out as the A operand W3^T[c_out][c_in] (K-major, 128-byte swizzle, umma.cuh).
+  // blob = [W3^T hi | W3^T lo | W2B hi | W2B lo]: tensor-core operand images (K-major, 128-byte swizzle, umma.cuh). Both
+  // dense layers run as 3xTF32: each weight is split into hi = rn_tf32(w) and lo = rn_tf32(w - hi). A Keras kernel is
+  // (C_in, C_out) row-major with the pooled half's rows first (Concatenate([pooling, layer]), :164-165).
   float* blob = h->wblob;
-  std::memcpy(blob, w->dense_kernel[1], sizeof(float) * 32 * 32);             // rows 0..15 = W2P, 16..31 = W2X
+  std::memset(blob, 0, sizeof(float) * kVfeBlobFloats);
   {
     auto tf32_rn = [](float x) {  // cvt.rna.tf32.f32: round to nearest, ties away, 10 explicit mantissa bits
       uint32_t u;
@@ -332,14 +340,27 @@ int32_t lisec_set_vfe_weights(lisec_handle* h, const lisec_vfe_weights* w, void*
       std::memcpy(&r, &u, 4);
       return r;
     };
-    unsigned char* hi = reinterpret_cast<unsigned char*>(blob + 32 * 32);
-    unsigned char* lo = hi + 64 * 64 * sizeof(float);
+    unsigned char* hi = reinterpret_cast<unsigned char*>(blob);
+    unsigned char* lo = hi + kVfeW3ImageFloats * sizeof(float);
     const float* k2 = w->dense_kernel[2];
     for (int k = 0; k < 64; ++k)
-      for (int m = 0; m < 64; ++m) {
+      for (int m = 0; m < 64; ++m) {  // A operand of the FCN: W3^T[c_out][c_in]
         const float v = k2[k * 64 + m] * sgn3[m];  // exact sign flip
         const float vh = tf32_rn(v), vl = tf32_rn(v - vh);
         const uint32_t off = umma::kmajor_offset(m, k, 64 * 128);
+        std::memcpy(hi + off, &vh, 4);
+        std::memcpy(lo + off, &vl, 4);
+      }
+    // B operand of the VFE-2 GEMM: W2B[n][k], n < 32: column n of the pooled half (k < 16), n >= 32: column n - 32 of
+    // the pointwise half (k >= 16); the other entries are zero, so the two halves' sums stay in separate accumulators
+    hi = reinterpret_cast<unsigned char*>(blob + 2 * kVfeW3ImageFloats);
+    lo = hi + kVfeW2ImageFloats * sizeof(float);
+    const float* k1 = w->dense_kernel[1];
+    for (int k = 0; k < 32; ++k)
+      for (int c = 0; c < 32; ++c) {
+        const float v = k1[k * 32 + c];
+        const float vh = tf32_rn(v), vl = tf32_rn(v - vh);
+        const uint32_t off = umma::kmajor_offset(k < 16 ? c : 32 + c, k, 0);
         std::memcpy(hi + off, &vh, 4);
         std::memcpy(lo + off, &vl, 4);
       }
@@ -348,8 +369,7 @@ int32_t lisec_set_vfe_weights(lisec_handle* h, const lisec_vfe_weights* w, void*
   // c_empty: the same kernel, run on one voxel that holds nothing but the pad row
   LISEC_CUDA(h, cudaMemcpyAsync(h->ws.vfe_w, blob, sizeof(float) * kVfeBlobFloats, cudaMemcpyHostToDevice, st));
   const int* d = h->ws.empty_desc;
-  const VfeProblem empty{d, d + 2, d + 6, reinterpret_cast<const float*>(d + 8),
-                         reinterpret_cast<const long long*>(d + 4)};
+  const VfeProblem empty{d, d + 2, d + 6, d + 8, d + 2, reinterpret_cast<const long long*>(d + 4), LISEC_F64};
   LISEC_CUDA(h, launch_vfe(p, h->ws.vfe_w, empty, h->ws.c_empty, h->sm_count, st, &h->launches));
   LISEC_CUDA(h, cudaStreamSynchronize(st));
   return LISEC_OK;
@@ -449,8 +469,7 @@ int32_t lisec_scatter_dense(lisec_handle* h, const float* voxel_feat, void* grid
 }
 
 static int fused_stage(lisec_handle* h, void* grid, cudaStream_t st) {
-  LISEC_CUDA(h, launch_row_features(h->last_points, h->last_dtype, h->geom, h->ws, 2 * h->last_so.off[h->last_so.n], st, &h->launches));
-  const VfeProblem prob{h->ws.tile_first, h->ws.tile_row0, h->ws.row_voxel, h->ws.row_feat, h->ws.totals + TOT_TILES};
+  const VfeProblem prob = vfe_problem(h);
   // one kernel: VFE (FP32 pipe + tensor core), voxel rows and the c_empty background written to the grid concurrently
   LISEC_CUDA(h, cudaEventRecord(h->ev_kernel[0], st));
   LISEC_CUDA(h, launch_vfe_to_grid(h->params, h->ws.vfe_w, prob, h->ws, h->geom, h->last_so.n, h->cfg.grid_dtype, grid,

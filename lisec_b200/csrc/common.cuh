@@ -26,19 +26,23 @@ struct SweepOffsets {
 };
 
 // Folded VFE parameters, primary architecture (model_training.py:231-233): 6->16 | 32->32 | 64->64.
-// VfeSmall travels as a __grid_constant__ kernel parameter (uniform-register operands for the one-row-per-thread
-// first layer and the BN epilogues); the larger matrices travel as one device blob that every CTA stages into shared
-// memory once: [W2P 16x32 | W2X 16x32] floats, row-major (C_in, C_out), then dense_2 as two tensor-core operand images
-// (tf32 hi part, tf32 lo part) of W3^T[c_out][c_in] in the K-major 128-byte-swizzled layout of umma.cuh, 2 slabs each.
-//   W2P / slab 0 = kernel rows that multiply the POOLED half  (Concatenate([pooling, layer]), :164-165)
-//   W2X / slab 1 = kernel rows that multiply the pointwise half
+// VfeSmall travels as a __grid_constant__ kernel parameter (every CTA copies the front stage's part into shared
+// memory once); the tensor-core operands travel as one device blob of four images in the K-major 128-byte-swizzled
+// layout of umma.cuh, each a tf32 hi part and a tf32 lo part (3xTF32):
+//   W3^T[c_out 64][c_in 64]  dense_2, A operand of the FCN GEMM, 2 slabs of 32 input channels:
+//                            slab 0 = kernel rows that multiply the POOLED half (Concatenate([pooling, layer]), :164-165)
+//   W2B[n 64][k 32]          dense_1, B operand of the VFE-2 GEMM, block-diagonal so that the two halves of the sum land
+//                            in SEPARATE accumulator columns: n < 32 = pooled half (k < 16), n >= 32 = pointwise half
 struct VfeSmall {
-  float w1f[6][16];      // dense (6,16); its product is evaluated in compensated float32 (vfe.cu, VFE-1)
+  float w1f[6][16];      // dense (6,16)
+  double w1d[3][16];     // its first three rows in float64 (the coarse part of the coordinates, see vfe.cu VFE-1)
   float a1[16], b1[16];  // BN folded: y = x*a + b, a = gamma*rsqrt(var+eps), b = beta - mean*a
   float a2[32], b2[32];
   float a3[64], b3[64];
 };
-constexpr int kVfeBlobFloats = 2 * 16 * 32 + 2 * 64 * 64;
+constexpr int kVfeW3ImageFloats = 64 * 64;  // one hi or lo image of W3^T
+constexpr int kVfeW2ImageFloats = 64 * 32;  // one hi or lo image of W2B
+constexpr int kVfeBlobFloats = 2 * kVfeW3ImageFloats + 2 * kVfeW2ImageFloats;  // [W3 hi | W3 lo | W2B hi | W2B lo]
 
 // totals[] slots (device, long long)
 enum {
@@ -51,7 +55,8 @@ enum {
   TOT_COUNT = 8
 };
 
-constexpr int kVfeThreads = 256;  // rows per VFE tile
+constexpr int kVfeThreads = 128;  // rows per VFE tile (one M = 128 accumulator block)
+constexpr int kRowPadFlag = 1 << 30;  // row_voxel[] bit: the row is its voxel's virtual pad row
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;     // cells per thread in the cell-table scans
 constexpr int kScanTile = kScanThreads * kScanItems;
@@ -71,8 +76,8 @@ struct Workspace {
   int* row_start = nullptr;    // offsets in VFE rows (kept + pad)
   int* tile_first = nullptr;   // first voxel of each VFE tile, [max_tiles + 2]
   // per VFE row, [max_points + max_voxels]: what the VFE kernel needs to start a tile with one coalesced read
-  int* row_voxel = nullptr;    // voxel row the VFE row belongs to
-  float* row_feat = nullptr;   // [rows][6] float32 features [x,y,z,x-cx,y-cy,z-cz] (zeros for a pad row)
+  int* row_voxel = nullptr;    // voxel row the VFE row belongs to (| kRowPadFlag for the virtual pad row)
+  void* row_xyz = nullptr;     // [rows][3] the point of every VFE row in the input dtype (unwritten for pad rows)
   int* tile_row0 = nullptr;    // first VFE row of each tile, [max_tiles + 2]
   int* block_sums = nullptr;   // [3][scan_blocks] reduce -> exclusive prefix
   int* sweep_voxel_start = nullptr;  // [max_sweeps + 1]
@@ -93,8 +98,8 @@ cudaError_t launch_point_pass(const void* pts, int pts_dtype, long long n_total,
                               const Geom& g, Workspace& w, cudaStream_t st, int* launches);
 cudaError_t launch_cell_scan(const SweepOffsets& so, const Geom& g, Workspace& w, int scan_blocks_cap,
                              cudaStream_t st, int* launches);
-cudaError_t launch_fill_and_order(long long n_total, const Geom& g, int rows_per_tile, Workspace& w,
-                                  cudaStream_t st, int* launches);
+cudaError_t launch_fill_and_order(const void* pts, int pts_dtype, long long n_total, const Geom& g, int rows_per_tile,
+                                  Workspace& w, cudaStream_t st, int* launches);
 cudaError_t launch_export(const void* pts, int pts_dtype, const SweepOffsets& so, const Geom& g,
                           const Workspace& w, long long max_voxels, int32_t* coords, int32_t* counts,
                           int32_t* point_idx, float* features, float* dense, cudaStream_t st, int* launches);
@@ -102,13 +107,12 @@ cudaError_t launch_export(const void* pts, int pts_dtype, const SweepOffsets& so
 struct VfeProblem {
   const int* tile_first;   // [n_tiles + 1] first voxel of each tile
   const int* tile_row0;    // [n_tiles + 1] first VFE row of each tile
-  const int* row_voxel;    // [rows]
-  const float* row_feat;   // [rows][6]
+  const int* row_voxel;    // [rows] (| kRowPadFlag)
+  const void* row_xyz;     // [rows][3] float32 or float64 (pts_dtype)
+  const int* row_start;    // [voxels + 1] first VFE row of each voxel
   const long long* n_tiles;
+  int pts_dtype;
 };
-// float64 centroid + float32 feature rows for every VFE row (model_training.py:134-141), contiguous in row order
-cudaError_t launch_row_features(const void* pts, int pts_dtype, const Geom& g, const Workspace& w, long long max_rows,
-                                cudaStream_t st, int* launches);
 cudaError_t launch_vfe(const VfeSmall& p, const float* wblob, const VfeProblem& prob,
                        float* voxel_feat, int sm_count, cudaStream_t st, int* launches, long long* prof = nullptr);
 // Fused VFE + dense grid: voxel rows go straight to their cells, a 9th warp per CTA streams c_empty into empty cells.

@@ -100,6 +100,30 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Two 8-column loads of the warp's 32 lanes (columns c0.. and c1..), one wait. The wait names every destination
+// register as an in/out operand, so no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld_2x8(uint32_t taddr0, uint32_t taddr1, float (&a)[8], float (&b)[8]) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr0)
+               : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr1)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = __uint_as_float(r[i]);
+    b[i] = __uint_as_float(r[8 + i]);
+  }
+}
+
 // ---- mbarrier ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t mbar_smem, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_smem), "r"(count) : "memory");
@@ -108,12 +132,28 @@ __device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar_smem) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar_smem) : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or the hint (ns) runs out,
+// instead of burning issue slots in a polling loop (ncu: 10 % of the VFE kernel's instructions were such polls)
 __device__ __forceinline__ bool mbar_try_wait(uint32_t mbar_smem, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(mbar_smem), "r"(parity), "r"(1000000u)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking test (the tensor thread polls several barriers)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t mbar_smem, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t"
       "}\n"
       : "=r"(ok)
@@ -131,10 +171,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar_smem, uint32_t parity) {
 // ---- 3xTF32 operand split: x = hi + lo with hi = rn_tf32(x), lo = rn_tf32(x - hi) --------------------------
 // (the tensor core reads only the top 19 bits of each 32-bit container; rounding here instead of letting it truncate
 // halves the representation error: |x - hi - lo| <= 2^-23 |x|)
+// cvt.rna.tf32.f32 (round to nearest, ties away) on a FINITE value as two integer instructions; the PTX conversion
+// itself compiles to four (it also passes inf / nan through), and the VFE kernel does ~40 of these per tile row.
 __device__ __forceinline__ float tf32_rn(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 __device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
   hi = tf32_rn(x);

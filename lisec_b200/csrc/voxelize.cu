@@ -359,15 +359,17 @@ __global__ void __launch_bounds__(256) fill_pass_kernel(const int* __restrict__ 
   }
 }
 
-// ---- K4: order pass (+ VFE tile boundaries) ---------------------------------------------------------------
-__global__ void __launch_bounds__(256) order_pass_kernel(const int* __restrict__ list_unsorted,
+// ---- K4: order pass (+ VFE tile boundaries, + the VFE row tables) -----------------------------------------
+template <typename PT>
+__global__ void __launch_bounds__(256) order_pass_kernel(const PT* __restrict__ pts,
+                                                         const int* __restrict__ list_unsorted,
                                                          const int* __restrict__ entry_voxel,
                                                          const int* __restrict__ voxel_start,
                                                          const int* __restrict__ row_start, int T,
                                                          int rows_per_tile, long long* __restrict__ totals,
                                                          int* __restrict__ list_sorted,
                                                          int* __restrict__ tile_first, int* __restrict__ tile_row0,
-                                                         int* __restrict__ row_voxel) {
+                                                         int* __restrict__ row_voxel, PT* __restrict__ row_xyz) {
   pdl_launch_dependents();
   pdl_wait();
   timeline_stamp(g_trace, TL_ORDER);
@@ -394,6 +396,8 @@ __global__ void __launch_bounds__(256) order_pass_kernel(const int* __restrict__
   const int s = voxel_start[v];
   const int n = voxel_start[v + 1] - s;
   const int p = list_unsorted[e];
+  // the point itself, fetched while the rank is counted: the VFE kernel reads its rows' coordinates contiguously
+  const PT px = __ldg(pts + 3 * (long long)p), py = __ldg(pts + 3 * (long long)p + 1), pz = __ldg(pts + 3 * (long long)p + 2);
   int rank = 0;
   if (n > 1) {
     // chunks of 8 independent loads, then the early exit: not among the first T in point order = dropped (:131)
@@ -410,7 +414,11 @@ __global__ void __launch_bounds__(256) order_pass_kernel(const int* __restrict__
     // VFE row tables: row_start[v] + rank is this point's row; a non-full voxel gets one virtual pad row after its points
     const int row = row_start[v] + rank;
     row_voxel[row] = v;
-    if (rank == 0 && n < T) row_voxel[row + n] = v;
+    if (rank == 0 && n < T) row_voxel[row + n] = v | kRowPadFlag;
+    PT* dst = row_xyz + 3 * (long long)row;
+    dst[0] = px;
+    dst[1] = py;
+    dst[2] = pz;
   }
 }
 
@@ -454,18 +462,27 @@ cudaError_t launch_cell_scan(const SweepOffsets& so, const Geom& g, Workspace& w
   return err;
 }
 
-cudaError_t launch_fill_and_order(long long n_total, const Geom& g, int rows_per_tile, Workspace& w,
-                                  cudaStream_t st, int* launches) {
+cudaError_t launch_fill_and_order(const void* pts, int pts_dtype, long long n_total, const Geom& g, int rows_per_tile,
+                                  Workspace& w, cudaStream_t st, int* launches) {
   if (n_total == 0) return cudaSuccess;
   const long long groups = (n_total + 3) / 4;
   cudaError_t err = launch_pdl(fill_pass_kernel, (unsigned)((groups + 255) / 256), 256, 0, st,
                                (const int*)w.cell_of_point, n_total, (const int*)w.cell_voxel,
                                (const int*)w.voxel_start, w.count, w.list_unsorted, w.entry_voxel);
   // entries <= points; threads beyond the device-side totals exit
-  if (err == cudaSuccess)
-    err = launch_pdl(order_pass_kernel, (unsigned)((n_total + 255) / 256), 256, 0, st, (const int*)w.list_unsorted,
-                     (const int*)w.entry_voxel, (const int*)w.voxel_start, (const int*)w.row_start, g.T, rows_per_tile,
-                     w.totals, w.list_sorted, w.tile_first, w.tile_row0, w.row_voxel);
+  if (err == cudaSuccess) {
+    const unsigned blocks = (unsigned)((n_total + 255) / 256);
+    if (pts_dtype == LISEC_F32)
+      err = launch_pdl(order_pass_kernel<float>, blocks, 256, 0, st, static_cast<const float*>(pts),
+                       (const int*)w.list_unsorted, (const int*)w.entry_voxel, (const int*)w.voxel_start,
+                       (const int*)w.row_start, g.T, rows_per_tile, w.totals, w.list_sorted, w.tile_first, w.tile_row0,
+                       w.row_voxel, static_cast<float*>(w.row_xyz));
+    else
+      err = launch_pdl(order_pass_kernel<double>, blocks, 256, 0, st, static_cast<const double*>(pts),
+                       (const int*)w.list_unsorted, (const int*)w.entry_voxel, (const int*)w.voxel_start,
+                       (const int*)w.row_start, g.T, rows_per_tile, w.totals, w.list_sorted, w.tile_first, w.tile_row0,
+                       w.row_voxel, static_cast<double*>(w.row_xyz));
+  }
   *launches += 2;
   return err;
 }
