@@ -190,6 +190,9 @@ int32_t lisec_last_fused_kernel_ms(lisec_handle* h, float* ms);
 /* Debug aid, inert unless the environment had LISEC_TRACE=1 at lisec_create(): cycle counters of the VFE kernel's pipeline
  * stages in the last VFE launch, int64 [256 CTAs][16 slots] (slot meaning: lisec_b200/csrc/vfe.cu). Synchronous. */
 int32_t lisec_debug_trace(lisec_handle* h, int64_t* out, int64_t n);
+/* Debug / test aid: copy one grouping table to the host (synchronous). which: 0 row_start, 1 row_voxel, 2 tile_first,
+   3 tile_row0, 4 chunk_ntiles, 5 chunk_first, 6 voxel_cell. */
+int32_t lisec_debug_table(lisec_handle* h, int32_t which, int32_t* out, int64_t n);
 
 /* Number of kernels the last call on this handle launched (bench.py's gpu_launches). */
 int32_t lisec_last_launch_count(const lisec_handle* h);

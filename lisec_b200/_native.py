@@ -120,6 +120,7 @@ SIGNATURES = {
     "lisec_voxel_counts_async": (C.c_int32, [_H, _VP, C.c_int64, _VP]),
     "lisec_last_fused_kernel_ms": (C.c_int32, [_H, _FP]),
     "lisec_debug_trace": (C.c_int32, [_H, _I64P, C.c_int64]),
+    "lisec_debug_table": (C.c_int32, [_H, C.c_int32, C.POINTER(C.c_int32), C.c_int64]),
     "lisec_last_launch_count": (C.c_int32, [_H]),
     "lisec_conv_plan_create": (C.c_int32, [C.POINTER(lisec_conv_desc), _VP, _VP, _VP, _VP, _VP, C.POINTER(_H)]),
     "lisec_conv_plan_run": (C.c_int32, [_H, _VP]),

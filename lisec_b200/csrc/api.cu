@@ -19,9 +19,9 @@ struct lisec_handle {
   VfeSmall params;
   float wblob[kVfeBlobFloats];
   int sm_count = 0;
-  int rows_per_tile = 0;
+  int rows_per_chunk = 0;
   long long max_voxels = 0;
-  long long max_tiles = 0;
+  long long max_chunks = 0;
   long long ncells_cap = 0;
   int scan_blocks_cap = 0;
   int64_t workspace_bytes = 0;
@@ -84,7 +84,8 @@ cudaError_t dev_alloc(lisec_handle* h, T** p, size_t n) {
 
 void free_workspace(Workspace& w) {
   void* ptrs[] = {w.count, w.cell_voxel, w.cell_of_point, w.list_unsorted, w.list_sorted, w.entry_voxel,
-                  w.voxel_cell, w.voxel_start, w.row_start, w.tile_first, w.tile_row0, w.row_voxel, w.row_xyz,
+                  w.voxel_cell, w.voxel_start, w.row_start, w.tile_first, w.tile_row0, w.chunk_first, w.chunk_row0,
+                  w.chunk_ntiles, w.row_voxel, w.row_xyz,
                   w.block_sums, w.sweep_voxel_start,
                   w.totals, w.voxel_feat, w.c_empty, w.vfe_w, w.staging, w.empty_desc, w.trace};
   for (void* p : ptrs)
@@ -120,7 +121,7 @@ int do_voxelize(lisec_handle* h, const void* points, int dtype, const SweepOffse
   h->count_dirty = true;  // until the fill pass has been enqueued
   LISEC_CUDA(h, launch_point_pass(points, dtype, n_total, so, h->geom, h->ws, st, &h->launches));
   LISEC_CUDA(h, launch_cell_scan(so, h->geom, h->ws, h->scan_blocks_cap, st, &h->launches));
-  LISEC_CUDA(h, launch_fill_and_order(points, dtype, n_total, h->geom, h->rows_per_tile, h->ws, st, &h->launches));
+  LISEC_CUDA(h, launch_fill_and_order(points, dtype, n_total, h->geom, h->rows_per_chunk, h->max_chunks, h->ws, st, &h->launches));
   h->count_dirty = false;
   h->last_points = points;
   h->last_dtype = dtype;
@@ -130,8 +131,8 @@ int do_voxelize(lisec_handle* h, const void* points, int dtype, const SweepOffse
 }
 
 VfeProblem vfe_problem(const lisec_handle* h) {
-  return VfeProblem{h->ws.tile_first, h->ws.tile_row0, h->ws.row_voxel, h->ws.row_xyz,
-                    h->ws.row_start,  h->ws.totals + TOT_TILES, h->last_dtype};
+  return VfeProblem{h->ws.tile_first, h->ws.tile_row0, h->ws.chunk_ntiles, h->ws.row_voxel, h->ws.row_xyz,
+                    h->ws.row_start,  h->ws.totals + TOT_CHUNKS, h->last_dtype};
 }
 
 int do_vfe(lisec_handle* h, float* voxel_feat, cudaStream_t st) {
@@ -214,10 +215,10 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
     if (v > 0 && v < h->sm_count) h->sm_count = v;
   }
 
-  h->rows_per_tile = vfe_rows_per_tile(g.T);
+  h->rows_per_chunk = vfe_rows_per_chunk(g.T);
   h->ncells_cap = cells * c.max_sweeps;
   h->max_voxels = c.max_points < h->ncells_cap ? c.max_points : h->ncells_cap;
-  h->max_tiles = (c.max_points + h->max_voxels) / h->rows_per_tile + 2;
+  h->max_chunks = (c.max_points + h->max_voxels) / h->rows_per_chunk + 2;
   h->scan_blocks_cap = (int)((h->ncells_cap + kScanTile - 1) / kScanTile);
 
   Workspace& w = h->ws;
@@ -231,8 +232,11 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
   LISEC_CUDA(h, dev_alloc(h, &w.voxel_cell, V));
   LISEC_CUDA(h, dev_alloc(h, &w.voxel_start, V + 1));
   LISEC_CUDA(h, dev_alloc(h, &w.row_start, V + 1));
-  LISEC_CUDA(h, dev_alloc(h, &w.tile_first, (size_t)h->max_tiles + 2));
-  LISEC_CUDA(h, dev_alloc(h, &w.tile_row0, (size_t)h->max_tiles + 2));
+  LISEC_CUDA(h, dev_alloc(h, &w.chunk_first, (size_t)h->max_chunks + 2));
+  LISEC_CUDA(h, dev_alloc(h, &w.chunk_row0, (size_t)h->max_chunks + 2));
+  LISEC_CUDA(h, dev_alloc(h, &w.chunk_ntiles, (size_t)h->max_chunks + 2));
+  LISEC_CUDA(h, dev_alloc(h, &w.tile_first, ((size_t)h->max_chunks + 2) * kChunkSlots));
+  LISEC_CUDA(h, dev_alloc(h, &w.tile_row0, ((size_t)h->max_chunks + 2) * kChunkSlots));
   LISEC_CUDA(h, dev_alloc(h, &w.row_voxel, P + V));
   LISEC_CUDA(h, dev_alloc(h, reinterpret_cast<unsigned char**>(&w.row_xyz), 3 * sizeof(double) * (P + V)));
   LISEC_CUDA(h, dev_alloc(h, &w.block_sums, (size_t)3 * h->scan_blocks_cap + 4));
@@ -258,13 +262,18 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
     LISEC_CUDA(h, set_trace_vfe(w.trace));
   }
   for (int b = 0; b < 2; ++b) LISEC_CUDA(h, cudaEventCreate(&h->ev_kernel[b]));
-  LISEC_CUDA(h, dev_alloc(h, &w.empty_desc, (size_t)16));
-  // the one-voxel problem whose VFE output is c_empty: 0 kept points, 1 pad row, 1 tile
-  // layout: tile_first {0,1} | tile_row0 {0,1} = row_start {0,1} | n_tiles (int64) 1 | row_voxel {0 | pad flag} | pad |
-  //         row_xyz: 3 doubles (never used: the row is a pad row)
-  int desc[16] = {0, 1, 0, 1, 0, 0, kRowPadFlag, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  LISEC_CUDA(h, dev_alloc(h, &w.empty_desc, (size_t)32));
+  // the one-voxel problem whose VFE output is c_empty: 0 kept points, 1 pad row, 1 chunk of 1 tile. Layout (ints; the
+  // arrays the kernel copies with 16-byte cp.async start on 16-byte boundaries):
+  //   [0..1] tile_first {0,1} ([1] doubles as chunk_ntiles {1}) | [2..3] tile_row0 {0,1} | [4..5] row_start {0,1} |
+  //   [8] row_voxel {0 | pad flag} | [12..13] n_chunks (int64) 1 | [16..21] row_xyz: 3 doubles (unused: a pad row)
+  int desc[32] = {0};
+  desc[1] = 1;
+  desc[3] = 1;
+  desc[5] = 1;
+  desc[8] = kRowPadFlag;
   const long long one = 1;
-  std::memcpy(&desc[4], &one, sizeof(one));
+  std::memcpy(&desc[12], &one, sizeof(one));
   LISEC_CUDA(h, cudaMemcpy(w.empty_desc, desc, sizeof(desc), cudaMemcpyHostToDevice));
   LISEC_CUDA(h, cudaMemset(w.totals, 0, sizeof(long long) * TOT_COUNT));
   return LISEC_OK;
@@ -369,7 +378,7 @@ int32_t lisec_set_vfe_weights(lisec_handle* h, const lisec_vfe_weights* w, void*
   // c_empty: the same kernel, run on one voxel that holds nothing but the pad row
   LISEC_CUDA(h, cudaMemcpyAsync(h->ws.vfe_w, blob, sizeof(float) * kVfeBlobFloats, cudaMemcpyHostToDevice, st));
   const int* d = h->ws.empty_desc;
-  const VfeProblem empty{d, d + 2, d + 6, d + 8, d + 2, reinterpret_cast<const long long*>(d + 4), LISEC_F64};
+  const VfeProblem empty{d, d + 2, d + 1, d + 8, d + 16, d + 4, reinterpret_cast<const long long*>(d + 12), LISEC_F64};
   LISEC_CUDA(h, launch_vfe(p, h->ws.vfe_w, empty, h->ws.c_empty, h->sm_count, st, &h->launches));
   LISEC_CUDA(h, cudaStreamSynchronize(st));
   return LISEC_OK;
@@ -565,6 +574,19 @@ int32_t lisec_debug_trace(lisec_handle* h, int64_t* out, int64_t n) {
     LISEC_CUDA(h, cudaMemset(row, 0xff, sizeof(unsigned long long)));
     LISEC_CUDA(h, cudaMemset(row + 1, 0, sizeof(unsigned long long)));
   }
+  return LISEC_OK;
+}
+
+// Debug / test aid: copy one of the grouping tables to the host (synchronous). which: 0 row_start, 1 row_voxel,
+// 2 tile_first, 3 tile_row0, 4 chunk_ntiles, 5 chunk_first, 6 voxel_cell.
+int32_t lisec_debug_table(lisec_handle* h, int32_t which, int32_t* out, int64_t n) {
+  if (!h || !out) return LISEC_ERR_BAD_ARG;
+  const int* src[] = {h->ws.row_start, h->ws.row_voxel, h->ws.tile_first, h->ws.tile_row0, h->ws.chunk_ntiles,
+                      h->ws.chunk_first, h->ws.voxel_cell};
+  if (which < 0 || which > 6) return fail(h, LISEC_ERR_BAD_ARG, "which = %d", which);
+  LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
+  LISEC_CUDA(h, cudaDeviceSynchronize());
+  LISEC_CUDA(h, cudaMemcpy(out, src[which], sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
   return LISEC_OK;
 }
 

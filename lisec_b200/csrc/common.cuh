@@ -49,13 +49,15 @@ enum {
   TOT_VOXELS = 0,
   TOT_ENTRIES = 1,  // in-range points
   TOT_ROWS = 2,     // kept rows + one pad row per non-full voxel
-  TOT_TILES = 3,
+  TOT_CHUNKS = 3,   // VFE chunks (runs of whole voxels with at most kVfeChunkRows rows; tiles are packed inside a chunk)
   TOT_NONFINITE = 4,
   TOT_OUT_OF_RANGE = 5,
   TOT_COUNT = 8
 };
 
 constexpr int kVfeThreads = 128;  // rows per VFE tile (one M = 128 accumulator block)
+constexpr int kVfeChunkRows = 4 * kVfeThreads;  // rows per VFE chunk
+constexpr int kChunkSlots = 12;  // tile-table entries per chunk (<= 9 tiles + the end sentinel)
 constexpr int kRowPadFlag = 1 << 30;  // row_voxel[] bit: the row is its voxel's virtual pad row
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;     // cells per thread in the cell-table scans
@@ -74,11 +76,14 @@ struct Workspace {
   int* voxel_cell = nullptr;
   int* voxel_start = nullptr;  // CSR offsets into list_*
   int* row_start = nullptr;    // offsets in VFE rows (kept + pad)
-  int* tile_first = nullptr;   // first voxel of each VFE tile, [max_tiles + 2]
+  int* chunk_first = nullptr;  // first voxel of each VFE chunk, [max_chunks + 2]
+  int* chunk_row0 = nullptr;   // first VFE row of each chunk
+  int* chunk_ntiles = nullptr; // tiles packed into each chunk
+  int* tile_first = nullptr;   // [max_chunks][kChunkSlots] first voxel of each tile of a chunk, then the end sentinel
   // per VFE row, [max_points + max_voxels]: what the VFE kernel needs to start a tile with one coalesced read
   int* row_voxel = nullptr;    // voxel row the VFE row belongs to (| kRowPadFlag for the virtual pad row)
   void* row_xyz = nullptr;     // [rows][3] the point of every VFE row in the input dtype (unwritten for pad rows)
-  int* tile_row0 = nullptr;    // first VFE row of each tile, [max_tiles + 2]
+  int* tile_row0 = nullptr;    // [max_chunks][kChunkSlots] first VFE row of each tile
   int* block_sums = nullptr;   // [3][scan_blocks] reduce -> exclusive prefix
   int* sweep_voxel_start = nullptr;  // [max_sweeps + 1]
   long long* totals = nullptr;       // [TOT_COUNT]
@@ -98,19 +103,20 @@ cudaError_t launch_point_pass(const void* pts, int pts_dtype, long long n_total,
                               const Geom& g, Workspace& w, cudaStream_t st, int* launches);
 cudaError_t launch_cell_scan(const SweepOffsets& so, const Geom& g, Workspace& w, int scan_blocks_cap,
                              cudaStream_t st, int* launches);
-cudaError_t launch_fill_and_order(const void* pts, int pts_dtype, long long n_total, const Geom& g, int rows_per_tile,
-                                  Workspace& w, cudaStream_t st, int* launches);
+cudaError_t launch_fill_and_order(const void* pts, int pts_dtype, long long n_total, const Geom& g, int rows_per_chunk,
+                                  long long max_chunks, Workspace& w, cudaStream_t st, int* launches);
 cudaError_t launch_export(const void* pts, int pts_dtype, const SweepOffsets& so, const Geom& g,
                           const Workspace& w, long long max_voxels, int32_t* coords, int32_t* counts,
                           int32_t* point_idx, float* features, float* dense, cudaStream_t st, int* launches);
 // The VFE problem description (device pointers): tiles -> rows -> (point, voxel); see Workspace.
 struct VfeProblem {
-  const int* tile_first;   // [n_tiles + 1] first voxel of each tile
-  const int* tile_row0;    // [n_tiles + 1] first VFE row of each tile
+  const int* tile_first;   // [n_chunks][kChunkSlots] first voxel of each tile of a chunk (entry ntiles = the end)
+  const int* tile_row0;    // [n_chunks][kChunkSlots] first VFE row
+  const int* chunk_ntiles; // [n_chunks]
   const int* row_voxel;    // [rows] (| kRowPadFlag)
   const void* row_xyz;     // [rows][3] float32 or float64 (pts_dtype)
   const int* row_start;    // [voxels + 1] first VFE row of each voxel
-  const long long* n_tiles;
+  const long long* n_chunks;
   int pts_dtype;
 };
 cudaError_t launch_vfe(const VfeSmall& p, const float* wblob, const VfeProblem& prob,
@@ -123,7 +129,7 @@ cudaError_t launch_grid_write(const Geom& g, int n_sweeps, int c3, int grid_dtyp
                               const float* voxel_feat, const float* c_empty, void* grid, int sm_count,
                               cudaStream_t st, int* launches);
 
-int vfe_rows_per_tile(int T);
+int vfe_rows_per_chunk(int T);
 cudaError_t set_trace_voxelize(unsigned long long* trace);
 cudaError_t set_trace_vfe(unsigned long long* trace);
 

@@ -4,7 +4,8 @@
 //
 // Work unit: a tile = a run of whole voxels holding at most 128 VFE rows (a row is a kept point, or the single
 // virtual zero row that stands for all identical pad rows of a non-full voxel) = one M = 128 block of
-// the tensor core. One persistent CTA per SM, warp-specialised:
+// the tensor core. Tiles are packed greedily inside chunks of <= 512 rows (tile_plan_kernel, voxelize.cu); chunks are
+// strided over the CTAs. One persistent CTA per SM, warp-specialised:
 //
 //   WRITER (warps 0-2, fused modes)  streams c_empty into the empty cells with TMA bulk stores (cp.async.bulk, evict-first)
 //   TENSOR (warp 3, one lane)        issues both GEMMs of every tile with tcgen05.mma kind::tf32 as 3xTF32
@@ -33,6 +34,8 @@
 // worst 6.7e-6 against the float64 oracle under the parity metric, bar 1e-5.
 #include <cuda_bf16.h>
 
+#include <cstdio>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -41,7 +44,7 @@
 
 namespace lisec {
 
-int vfe_rows_per_tile(int T) { return kVfeThreads - T + 1; }
+int vfe_rows_per_chunk(int T) { return kVfeChunkRows - T + 1; }  // a chunk: whole voxels, at most kVfeChunkRows rows
 
 namespace {
 
@@ -78,10 +81,12 @@ struct TileInfo {
   int voxcell[kVox];               // cell of each tile voxel (grid output modes)
 };
 // per tile in flight in the front stage (cp.async landing buffers)
+// (16-byte cp.async.cg chunks from 16-byte-aligned global addresses: every array starts up to 3 elements before the
+// tile's first entry, hence the + 4)
 struct TileMeta {
-  int rowvox[kRows];     // row -> voxel row (| kRowPadFlag)
-  int vrs[kVox + 4];     // voxel -> first VFE row (absolute), nv + 1 entries
-  int voxcell[kVox];     // voxel -> cell
+  int rowvox[kRows + 4];     // row -> voxel row (| kRowPadFlag)
+  int vrs[kVox + 4 + 4];     // voxel -> first VFE row (absolute), nv + 1 entries
+  int voxcell[kVox + 4];     // voxel -> cell
 };
 struct FrontParams {  // the front stage's share of VfeSmall, in shared memory (indexed by the thread's channel quarter)
   double w1d[3][16];
@@ -100,7 +105,8 @@ constexpr int OFF_W2L = OFF_W2H + kWSlab;           // W2B lo             |
 // per team: layer outputs for the max-pools (sH2 [kRows][32] floats, 16-byte chunks XOR-swizzled with the row; sH1
 // [kRows][16] lives in the same place, the team's stages being sequential), the tile's points, the landing buffers
 constexpr int kHBytes = kRows * 32 * 4;
-constexpr int kTeamBytes = kHBytes + kRows * 3 * 8 + kMetaSlots * (int)sizeof(TileMeta);
+constexpr int kXyzBytes = kRows * 3 * 8 + 16;
+constexpr int kTeamBytes = kHBytes + kXyzBytes + kMetaSlots * (int)sizeof(TileMeta);
 constexpr int OFF_TEAM = OFF_W2L + kWSlab;          // [2] x { H | PT xyz[kRows][3] | TileMeta[kMetaSlots] }
 constexpr int OFF_PAR = OFF_TEAM + 2 * kTeamBytes;
 constexpr int OFF_INFO = OFF_PAR + (int)sizeof(FrontParams);
@@ -193,7 +199,7 @@ __device__ __forceinline__ void background_writer(const int* __restrict__ cell_v
     for (int u = 0; u < U; ++u) {
       const int g = g0 + u * stride;
       const long long cell = ((long long)g << 5) + lane;
-      occ[u] = (g < ngroups && cell < ncells) ? __ldg(cell_voxel + cell) : 0;  // 0 = "not empty": nothing to write
+      occ[u] = (g < ngroups && cell < ncells) ? __ldcg(cell_voxel + cell) : 0;  // 0 = "not empty": nothing to write
     }
   };
   int occ[U], nxt[U];
@@ -233,13 +239,20 @@ __device__ __forceinline__ void warm_count_table(const int* __restrict__ count, 
     asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base + (i << 7)));
 }
 
-__device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc)
+// 16 bytes, L2 only (.cg): the sources are tables written by this kernel's predecessors under programmatic dependent
+// launch, and a load through L1 (.ca, or a plain ld) can return a line of the PREVIOUS call's table (tools/check_tables.py)
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc)
                : "memory");
 }
-__device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc)
-               : "memory");
+// copy elements [first, first + n) of a global array of 4- or 8-byte elements into sdst such that element `first` lands
+// at sdst[first & (16 / size - 1)]: whole 16-byte chunks from 16-byte-aligned addresses, chunk i by thread t0 + i
+template <typename T>
+__device__ __forceinline__ void cp_async_range(T* sdst, const T* gbase, size_t first, int n, int t, int nthreads) {
+  constexpr int per = 16 / (int)sizeof(T);
+  const size_t c0 = first / per;
+  const int chunks = (int)((first + n + per - 1) / per - c0);
+  for (int i = t; i < chunks; i += nthreads) cp_async16(sdst + per * i, gbase + per * (c0 + i));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -255,6 +268,43 @@ __device__ __forceinline__ uint32_t bar_x2_full(uint32_t smem_base) { return sme
 __device__ __forceinline__ uint32_t acc_addr(uint32_t tmem_base, int s) {
   return tmem_base + ((uint32_t)(16 * (s & 1)) << 16) + (uint32_t)(s >> 1) * kRows;
 }
+
+// ---- this CTA's tiles: chunks blockIdx.x, blockIdx.x + gridDim.x, ..., the tiles of each in order --------------
+// The tables are written by this kernel's predecessors in the stream, which under programmatic dependent launch may
+// still be running when this kernel starts: they are read with ld.global.cg AFTER griddepcontrol.wait. Never __ldg here:
+// a non-coherent load may be hoisted above the wait or served from a stale line (seen: tile headers of one problem
+// with the row tables of the next).
+__device__ __forceinline__ int count_my_tiles(const VfeProblem& prob, int n_chunks) {
+  int n = 0;
+  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) n += __ldcg(prob.chunk_ntiles + c);
+  return n;
+}
+struct TileCursor {  // walks every `step`-th tile of the CTA's sequence
+  int c, j, n, n_next;  // chunk, tile inside it, its tile count; the NEXT chunk's tile count, loaded a chunk ahead so
+                        // that crossing into it never waits for an L2 round trip (2-3 us beside the grid stream)
+  __device__ __forceinline__ int load_n(const VfeProblem& prob, int n_chunks, int chunk) const {
+    return chunk < n_chunks ? __ldcg(prob.chunk_ntiles + chunk) : 0;
+  }
+  __device__ __forceinline__ void settle(const VfeProblem& prob, int n_chunks) {
+    while (c < n_chunks && j >= n) {
+      j -= n;
+      c += gridDim.x;
+      n = n_next;
+      n_next = load_n(prob, n_chunks, c + gridDim.x);
+    }
+  }
+  __device__ __forceinline__ void init(const VfeProblem& prob, int n_chunks, int first) {
+    c = blockIdx.x;
+    n = load_n(prob, n_chunks, c);
+    n_next = load_n(prob, n_chunks, c + gridDim.x);
+    j = first;
+    settle(prob, n_chunks);
+  }
+  __device__ __forceinline__ void advance(const VfeProblem& prob, int n_chunks, int step) {
+    j += step;
+    settle(prob, n_chunks);
+  }
+};
 
 // ---- TENSOR stage: both GEMMs, issued by one thread (lane 0 of the tensor warp) ------------------------------
 // 3xTF32, small terms first so that their sum is not rounded against the large one.
@@ -437,9 +487,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // from here on: the grouping, the row tables and the occupancy map of this call
   if (MODE != 0) timeline_stamp(g_trace, TL_VFE);
-  const int n_tiles = (int)*prob.n_tiles;
-  // tiles are strided over the CTAs: this one owns ordinals it = 0 .. my_tiles-1, tile blockIdx.x + it * gridDim.x
-  const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int n_chunks = (int)*prob.n_chunks;
+  // chunks are strided over the CTAs; this one owns tile ordinals 0 .. my_tiles-1 = the tiles of its chunks in order
+  const int my_tiles = count_my_tiles(prob, n_chunks);
 
   if (warp_in_cta < kWriterWarps) {  // ---- WRITER ----
     if (MODE == 1)
@@ -470,8 +520,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
   const int row = 32 * (tw & 3) + lane, part = tw >> 2;
   unsigned char* team_base = smem + OFF_TEAM + team * kTeamBytes;
   float* sH = reinterpret_cast<float*>(team_base);
-  PT* sXYZ = reinterpret_cast<PT*>(team_base + kHBytes);
-  TileMeta* metas = reinterpret_cast<TileMeta*>(team_base + kHBytes + kRows * 3 * 8);
+  PT* sXYZbuf = reinterpret_cast<PT*>(team_base + kHBytes);
+  TileMeta* metas = reinterpret_cast<TileMeta*>(team_base + kHBytes + kXyzBytes);
   const FrontParams* fp = reinterpret_cast<const FrontParams*>(smem + OFF_PAR);
   const PT* g_xyz = static_cast<const PT*>(prob.row_xyz);
   const uint32_t tlane = tmem_base + ((uint32_t)(32 * (tw & 3)) << 16);
@@ -481,15 +531,17 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
 
   // tile header = (first voxel, first row) of the tile and of its successor; rows and voxels are contiguous
   struct Header { int v0, v1, r0, r1; };
-  const int tstride = gridDim.x;
-  auto load_header = [&](int k) {  // team-local tile k = ordinal 2k + team of this CTA
+  TileCursor cursor;
+  cursor.init(prob, n_chunks, team);
+  auto next_header = [&]() {  // the team's next tile (ordinals team, team + 2, ... of this CTA), or an empty header
     Header h{0, 0, 0, 0};
-    const int t = (int)blockIdx.x + (2 * k + team) * tstride;
-    if (k < n_mine) {
-      h.v0 = __ldg(prob.tile_first + t);
-      h.v1 = __ldg(prob.tile_first + t + 1);
-      h.r0 = __ldg(prob.tile_row0 + t);
-      h.r1 = __ldg(prob.tile_row0 + t + 1);
+    if (cursor.c < n_chunks) {
+      const int t = cursor.c * kChunkSlots + cursor.j;
+      h.v0 = __ldcg(prob.tile_first + t);
+      h.v1 = __ldcg(prob.tile_first + t + 1);
+      h.r0 = __ldcg(prob.tile_row0 + t);
+      h.r1 = __ldcg(prob.tile_row0 + t + 1);
+      cursor.advance(prob, n_chunks, 2);
     }
     return h;
   };
@@ -497,19 +549,16 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
   auto prefetch = [&](const Header& h, int k) {
     TileMeta* m = metas + (k & 1);
     const int nrows = h.r1 - h.r0, nv = h.v1 - h.v0;
-    for (int e = ttid; e < 3 * nrows; e += kTeamThreads) {
-      if (sizeof(PT) == 4) cp_async4(sXYZ + e, g_xyz + 3 * (size_t)h.r0 + e);
-      else cp_async8(sXYZ + e, g_xyz + 3 * (size_t)h.r0 + e);
-    }
-    if (ttid < nrows) cp_async4(m->rowvox + ttid, prob.row_voxel + h.r0 + ttid);
-    const int u = ttid - kRows;  // the other half of the team: the voxel tables
-    if (u >= 0) {
-      if (u <= nv) cp_async4(m->vrs + u, prob.row_start + h.v0 + u);
-      if (MODE != 0 && u < nv) cp_async4(m->voxcell + u, out.voxel_cell + h.v0 + u);
+    // warps 0-5: the points; warp 6: row -> voxel; warp 7: the voxel tables
+    if (ttid < 192) cp_async_range(sXYZbuf, g_xyz, 3 * (size_t)h.r0, 3 * nrows, ttid, 192);
+    else if (ttid < 224) cp_async_range(m->rowvox, prob.row_voxel, (size_t)h.r0, nrows, ttid - 192, 32);
+    else {
+      cp_async_range(m->vrs, prob.row_start, (size_t)h.v0, nv + 1, ttid - 224, 32);
+      if (MODE != 0) cp_async_range(m->voxcell, out.voxel_cell, (size_t)h.v0, nv, ttid - 224, 32);
     }
   };
 
-  Header cur = load_header(0), nxt = load_header(1);
+  Header cur = next_header(), nxt = next_header();
   if (n_mine > 0) prefetch(cur, 0);
   cp_async_commit();
   cp_async_wait_all();
@@ -518,9 +567,29 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
   for (int k = 0; k < n_mine; ++k) {
     const int i = 2 * k + team;  // tile ordinal of this CTA
     const Header h = cur;
-    const Header nxt2 = load_header(k + 2);
-    const TileMeta& m = metas[k & 1];
+    const Header nxt2 = next_header();
+    const TileMeta& mt = metas[k & 1];
     const int nrows = h.r1 - h.r0, nv = h.v1 - h.v0;
+    // the landing buffers start at the 16-byte chunk that holds the tile's first element
+    struct View { const int *rowvox, *vrs, *voxcell; } m;
+    m.rowvox = mt.rowvox + (h.r0 & 3);
+    m.vrs = mt.vrs + (h.v0 & 3);
+    m.voxcell = mt.voxcell + (h.v0 & 3);
+    const PT* sXYZ = sXYZbuf + (3 * (size_t)h.r0) % (16 / sizeof(PT));
+#ifdef LISEC_DEBUG_CHECKS
+    if (ttid == 0 && (nrows <= 0 || nrows > kRows || nv <= 0 || nv > kVox))
+      printf("BAD HEADER cta %d team %d k %d/%d: v %d..%d r %d..%d chunks %d my_tiles %d\n", (int)blockIdx.x, team, k, n_mine,
+             h.v0, h.v1, h.r0, h.r1, n_chunks, my_tiles);
+    if (row < nrows) {
+      const int rv = m.rowvox[row] & ~kRowPadFlag;
+      if (rv < h.v0 || rv >= h.v1) printf("BAD ROWVOX cta %d team %d k %d row %d rv %d v %d..%d\n", (int)blockIdx.x, team, k, row, rv, h.v0, h.v1);
+      else {
+        const int rs = m.vrs[rv - h.v0] - h.r0, re = m.vrs[rv - h.v0 + 1] - h.r0;
+        if (rs < 0 || re > nrows || rs >= re || row < rs || row >= re)
+          printf("BAD VRS cta %d team %d k %d row %d lv %d rs %d re %d nrows %d\n", (int)blockIdx.x, team, k, row, rv - h.v0, rs, re, nrows);
+      }
+    }
+#endif
 
     // ---- F1: centroid, features, VFE-1, max-pool, X1 ------------------------------------------------------------
     {

@@ -14,6 +14,8 @@
 //   order_pass   rank-by-counting inside each voxel segment, early exit at T: entry p lands at position
 //                #{q in voxel : q < p}. This is what makes the slot assignment deterministic in point order
 //                whatever order the atomics resolved in. Also marks the VFE tile boundaries and the row -> voxel table.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace lisec {
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_down_kernel(const int* __re
     totals[TOT_VOXELS] = carry.v;
     totals[TOT_ENTRIES] = carry.e;
     totals[TOT_ROWS] = carry.r;
-    totals[TOT_TILES] = 0;  // set by order_pass when there is at least one voxel
+    totals[TOT_CHUNKS] = 0;  // set by order_pass when there is at least one voxel
     voxel_start[carry.v] = carry.e;
     row_start[carry.v] = carry.r;
     sweep_voxel_start[n_sweeps] = carry.v;
@@ -330,9 +332,9 @@ __global__ void __launch_bounds__(256) fill_pass_kernel(const int* __restrict__ 
   // thread through each stage together so the round trips overlap
   int v[4], start[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) v[j] = cell[j] >= 0 ? __ldg(cell_voxel + cell[j]) : -1;
+  for (int j = 0; j < 4; ++j) v[j] = cell[j] >= 0 ? __ldcg(cell_voxel + cell[j]) : -1;  // (written by the predecessor kernel: no __ldg under PDL)
 #pragma unroll
-  for (int j = 0; j < 4; ++j) start[j] = cell[j] >= 0 ? __ldg(voxel_start + v[j]) : 0;
+  for (int j = 0; j < 4; ++j) start[j] = cell[j] >= 0 ? __ldcg(voxel_start + v[j]) : 0;
   unsigned peers[4];
   int old[4];
 #pragma unroll
@@ -366,36 +368,37 @@ __global__ void __launch_bounds__(256) order_pass_kernel(const PT* __restrict__ 
                                                          const int* __restrict__ entry_voxel,
                                                          const int* __restrict__ voxel_start,
                                                          const int* __restrict__ row_start, int T,
-                                                         int rows_per_tile, long long* __restrict__ totals,
+                                                         int rows_per_chunk, long long* __restrict__ totals,
                                                          int* __restrict__ list_sorted,
-                                                         int* __restrict__ tile_first, int* __restrict__ tile_row0,
+                                                         int* __restrict__ chunk_first, int* __restrict__ chunk_row0,
                                                          int* __restrict__ row_voxel, PT* __restrict__ row_xyz) {
   pdl_launch_dependents();
   pdl_wait();
   timeline_stamp(g_trace, TL_ORDER);
-  const long long n_entries = totals[TOT_ENTRIES];
-  const long long n_voxels = totals[TOT_VOXELS];
+  const long long n_entries = __ldcg(totals + TOT_ENTRIES);  // (predecessor-written tables: ld.global.cg, see tile_plan_kernel)
+  const long long n_voxels = __ldcg(totals + TOT_VOXELS);
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < n_voxels) {
-    // tile(v) = row_start[v] / rows_per_tile; a voxel has at most T rows < rows_per_tile, so consecutive voxels
-    // differ by at most one tile and every tile index up to the last one has a first voxel.
-    const int t = row_start[e] / rows_per_tile;
-    const int tprev = e > 0 ? row_start[e - 1] / rows_per_tile : -1;
+    // chunk(v) = row_start[v] / rows_per_chunk; a voxel has at most T rows < rows_per_chunk, so consecutive voxels
+    // differ by at most one chunk and every chunk index up to the last one has a first voxel.
+    const int rse = __ldcg(row_start + e);
+    const int t = rse / rows_per_chunk;
+    const int tprev = e > 0 ? __ldcg(row_start + e - 1) / rows_per_chunk : -1;
     if (t != tprev) {
-      tile_first[t] = (int)e;
-      tile_row0[t] = row_start[e];
+      chunk_first[t] = (int)e;
+      chunk_row0[t] = rse;
     }
     if (e == n_voxels - 1) {
-      tile_first[t + 1] = (int)n_voxels;
-      tile_row0[t + 1] = row_start[n_voxels];
-      totals[TOT_TILES] = t + 1;
+      chunk_first[t + 1] = (int)n_voxels;
+      chunk_row0[t + 1] = __ldcg(row_start + n_voxels);
+      totals[TOT_CHUNKS] = t + 1;
     }
   }
   if (e >= n_entries) return;
-  const int v = entry_voxel[e];
-  const int s = voxel_start[v];
-  const int n = voxel_start[v + 1] - s;
-  const int p = list_unsorted[e];
+  const int v = __ldcg(entry_voxel + e);
+  const int s = __ldcg(voxel_start + v);
+  const int n = __ldcg(voxel_start + v + 1) - s;
+  const int p = __ldcg(list_unsorted + e);
   // the point itself, fetched while the rank is counted: the VFE kernel reads its rows' coordinates contiguously
   const PT px = __ldg(pts + 3 * (long long)p), py = __ldg(pts + 3 * (long long)p + 1), pz = __ldg(pts + 3 * (long long)p + 2);
   int rank = 0;
@@ -404,7 +407,7 @@ __global__ void __launch_bounds__(256) order_pass_kernel(const PT* __restrict__ 
     for (int i0 = 0; i0 < n && rank < T; i0 += 8) {
       int q[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) q[u] = i0 + u < n ? list_unsorted[s + i0 + u] : 0x7fffffff;
+      for (int u = 0; u < 8; ++u) q[u] = i0 + u < n ? __ldcg(list_unsorted + s + i0 + u) : 0x7fffffff;
 #pragma unroll
       for (int u = 0; u < 8; ++u) rank += (q[u] < p);
     }
@@ -412,13 +415,54 @@ __global__ void __launch_bounds__(256) order_pass_kernel(const PT* __restrict__ 
   if (rank < T) {
     list_sorted[s + rank] = p;
     // VFE row tables: row_start[v] + rank is this point's row; a non-full voxel gets one virtual pad row after its points
-    const int row = row_start[v] + rank;
+    const int row = __ldcg(row_start + v) + rank;
     row_voxel[row] = v;
     if (rank == 0 && n < T) row_voxel[row + n] = v | kRowPadFlag;
     PT* dst = row_xyz + 3 * (long long)row;
     dst[0] = px;
     dst[1] = py;
     dst[2] = pz;
+  }
+}
+
+// ---- K5: tile plan ----------------------------------------------------------------------------------------
+// One warp per chunk packs the chunk's voxels greedily into tiles of at most kVfeThreads rows (a tile = whole voxels):
+// the next tile ends at the last voxel whose rows still fit. A voxel has >= 2 rows, so a tile has <= kVfeThreads / 2
+// voxels: two candidates per lane cover the search. Tiles of ~126 of 128 rows instead of the ~94 a fixed row stride
+// with its worst-case reserve would give.
+__global__ void __launch_bounds__(128) tile_plan_kernel(const int* __restrict__ chunk_first,
+                                                        const int* __restrict__ row_start,
+                                                        const long long* __restrict__ totals,
+                                                        int* __restrict__ tile_first, int* __restrict__ tile_row0,
+                                                        int* __restrict__ chunk_ntiles, int tile_rows) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = lane_id();
+  const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // (everything this kernel reads was written by its predecessors under programmatic dependent launch: ld.global.cg,
+  // never through L1 — a plain load here returned lines of the PREVIOUS call's tables: tools/check_tables.py)
+  if (c >= __ldcg(totals + TOT_CHUNKS)) return;
+  const int v_end = __ldcg(chunk_first + c + 1);
+  int b = __ldcg(chunk_first + c), j = 0;
+  int* tf = tile_first + c * kChunkSlots;
+  int* tr = tile_row0 + c * kChunkSlots;
+  while (b < v_end && j < kChunkSlots - 1) {
+    const int base = __ldcg(row_start + b);
+    const int e1 = b + 1 + lane, e2 = e1 + 32;
+    const bool ok1 = e1 <= v_end && __ldcg(row_start + e1) - base <= tile_rows;
+    const bool ok2 = e2 <= v_end && __ldcg(row_start + e2) - base <= tile_rows;
+    const int fit = __popc(__ballot_sync(0xffffffffu, ok1)) + __popc(__ballot_sync(0xffffffffu, ok2));  // monotone: a count
+    if (lane == 0) {
+      tf[j] = b;
+      tr[j] = base;
+    }
+    b += fit;  // fit >= 1: one voxel always fits
+    ++j;
+  }
+  if (lane == 0) {
+    tf[j] = v_end;
+    tr[j] = __ldcg(row_start + v_end);
+    chunk_ntiles[c] = j;
   }
 }
 
@@ -462,8 +506,8 @@ cudaError_t launch_cell_scan(const SweepOffsets& so, const Geom& g, Workspace& w
   return err;
 }
 
-cudaError_t launch_fill_and_order(const void* pts, int pts_dtype, long long n_total, const Geom& g, int rows_per_tile,
-                                  Workspace& w, cudaStream_t st, int* launches) {
+cudaError_t launch_fill_and_order(const void* pts, int pts_dtype, long long n_total, const Geom& g, int rows_per_chunk,
+                                  long long max_chunks, Workspace& w, cudaStream_t st, int* launches) {
   if (n_total == 0) return cudaSuccess;
   const long long groups = (n_total + 3) / 4;
   cudaError_t err = launch_pdl(fill_pass_kernel, (unsigned)((groups + 255) / 256), 256, 0, st,
@@ -475,15 +519,25 @@ cudaError_t launch_fill_and_order(const void* pts, int pts_dtype, long long n_to
     if (pts_dtype == LISEC_F32)
       err = launch_pdl(order_pass_kernel<float>, blocks, 256, 0, st, static_cast<const float*>(pts),
                        (const int*)w.list_unsorted, (const int*)w.entry_voxel, (const int*)w.voxel_start,
-                       (const int*)w.row_start, g.T, rows_per_tile, w.totals, w.list_sorted, w.tile_first, w.tile_row0,
+                       (const int*)w.row_start, g.T, rows_per_chunk, w.totals, w.list_sorted, w.chunk_first, w.chunk_row0,
                        w.row_voxel, static_cast<float*>(w.row_xyz));
     else
       err = launch_pdl(order_pass_kernel<double>, blocks, 256, 0, st, static_cast<const double*>(pts),
                        (const int*)w.list_unsorted, (const int*)w.entry_voxel, (const int*)w.voxel_start,
-                       (const int*)w.row_start, g.T, rows_per_tile, w.totals, w.list_sorted, w.tile_first, w.tile_row0,
+                       (const int*)w.row_start, g.T, rows_per_chunk, w.totals, w.list_sorted, w.chunk_first, w.chunk_row0,
                        w.row_voxel, static_cast<double*>(w.row_xyz));
   }
-  *launches += 2;
+  // chunks -> tiles (threads past the device-side chunk count exit)
+  static const int tile_rows = [] {  // experiment switch: rows per tile (<= kVfeThreads; needs >= T)
+    const char* e = getenv("LISEC_TILE_ROWS");
+    const int v = e ? atoi(e) : kVfeThreads;
+    return v >= 64 && v <= kVfeThreads ? v : kVfeThreads;
+  }();
+  if (err == cudaSuccess)
+    err = launch_pdl(tile_plan_kernel, (unsigned)((max_chunks * 32 + 127) / 128), 128, 0, st, (const int*)w.chunk_first,
+                     (const int*)w.row_start, (const long long*)w.totals, w.tile_first, w.tile_row0, w.chunk_ntiles,
+                     tile_rows);
+  *launches += 3;
   return err;
 }
 
