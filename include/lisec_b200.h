@@ -189,6 +189,35 @@ int32_t lisec_last_fused_kernel_ms(lisec_handle* h, float* ms);
 
 /* Debug aid, inert unless the environment had LISEC_TRACE=1 at lisec_create(): cycle counters of the VFE kernel's pipeline
  * stages in the last VFE launch, int64 [256 CTAs][16 slots] (slot meaning: lisec_b200/csrc/vfe.cu). Synchronous. */
+/* ---- the VFE stack in TRAINING mode (model_training.py:229-235 under fit(), :295-299) -------------------------------
+ * Forward with batch statistics and the backward pass on the grouping of the last lisec_voxelize(), evaluated on rows
+ * with multiplicities (kept points, one virtual pad row per non-full voxel, one row for all empty voxels) — the exact
+ * restatement of the dense graph that oracle/train_oracle.py: forward_train_rows() states. All pointers are DEVICE
+ * pointers to float32; kernels are row-major (C_in, C_out) as Keras stores them. */
+typedef struct lisec_vfe_train_params {
+  const float* dense_kernel[3];
+  const float* bn_gamma[3];
+  const float* bn_beta[3];
+  float* moving_mean[3]; /* updated in place: m <- m * momentum + batch * (1 - momentum); NULL: not tracked */
+  float* moving_var[3];
+  float bn_epsilon;  /* Keras default 1e-3 */
+  float bn_momentum; /* Keras default 0.99 */
+} lisec_vfe_train_params;
+typedef struct lisec_vfe_train_grads {
+  float* dkernel[3];
+  float* dgamma[3];
+  float* dbeta[3];
+} lisec_vfe_train_grads;
+/* [async] grid [n_sweeps, nz, nx, ny, 64] in the handle's grid_dtype: the VFE output in training mode, the empty voxels'
+ * (batch-statistics) output as the background. Keeps the activations for lisec_vfe_train_backward(). */
+int32_t lisec_vfe_train_forward(lisec_handle* h, const lisec_vfe_train_params* p, void* grid, void* stream);
+/* [async] dgrid: float32 [n_sweeps, nz, nx, ny, 64], the loss gradient w.r.t. the grid. Writes the parameter gradients. */
+int32_t lisec_vfe_train_backward(lisec_handle* h, const lisec_vfe_train_params* p, const float* dgrid,
+                                 const lisec_vfe_train_grads* g, void* stream);
+/* Test aid: per-voxel output rows of `layer` ([n_rows][C_layer], row n_voxels = the empty voxels) and its batch mean /
+ * inverse standard deviation. Synchronous. */
+int32_t lisec_vfe_train_read(lisec_handle* h, int32_t layer, float* out_rows, int64_t n_rows, float* mean, float* inv_std);
+
 int32_t lisec_debug_trace(lisec_handle* h, int64_t* out, int64_t n);
 /* Debug / test aid: copy one grouping table to the host (synchronous). which: 0 row_start, 1 row_voxel, 2 tile_first,
    3 tile_row0, 4 chunk_ntiles, 5 chunk_first, 6 voxel_cell. */

@@ -69,6 +69,22 @@ class lisec_vfe_weights(C.Structure):
     ]
 
 
+class lisec_vfe_train_params(C.Structure):  # DEVICE pointers
+    _fields_ = [
+        ("dense_kernel", C.c_void_p * 3),
+        ("bn_gamma", C.c_void_p * 3),
+        ("bn_beta", C.c_void_p * 3),
+        ("moving_mean", C.c_void_p * 3),
+        ("moving_var", C.c_void_p * 3),
+        ("bn_epsilon", C.c_float),
+        ("bn_momentum", C.c_float),
+    ]
+
+
+class lisec_vfe_train_grads(C.Structure):  # DEVICE pointers
+    _fields_ = [("dkernel", C.c_void_p * 3), ("dgamma", C.c_void_p * 3), ("dbeta", C.c_void_p * 3)]
+
+
 class lisec_conv_desc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "batch", "in_d", "in_h", "in_w", "in_c", "kd", "kh", "kw", "stride_d", "stride_hw", "pad_d", "pad_h", "pad_w",
@@ -121,6 +137,9 @@ SIGNATURES = {
     "lisec_last_fused_kernel_ms": (C.c_int32, [_H, _FP]),
     "lisec_debug_trace": (C.c_int32, [_H, _I64P, C.c_int64]),
     "lisec_debug_table": (C.c_int32, [_H, C.c_int32, C.POINTER(C.c_int32), C.c_int64]),
+    "lisec_vfe_train_forward": (C.c_int32, [_H, C.POINTER(lisec_vfe_train_params), _VP, _VP]),
+    "lisec_vfe_train_backward": (C.c_int32, [_H, C.POINTER(lisec_vfe_train_params), _VP, C.POINTER(lisec_vfe_train_grads), _VP]),
+    "lisec_vfe_train_read": (C.c_int32, [_H, C.c_int32, _FP, C.c_int64, _FP, _FP]),
     "lisec_last_launch_count": (C.c_int32, [_H]),
     "lisec_conv_plan_create": (C.c_int32, [C.POINTER(lisec_conv_desc), _VP, _VP, _VP, _VP, _VP, C.POINTER(_H)]),
     "lisec_conv_plan_run": (C.c_int32, [_H, _VP]),

@@ -7,79 +7,14 @@
 #include <cstring>
 #include <new>
 
-#include "common.cuh"
+#include "handle.cuh"
 #include "umma.cuh"
 
-using namespace lisec;
-
-struct lisec_handle {
-  lisec_config cfg;
-  Geom geom;
-  Workspace ws;
-  VfeSmall params;
-  float wblob[kVfeBlobFloats];
-  int sm_count = 0;
-  int rows_per_chunk = 0;
-  long long max_voxels = 0;
-  long long max_chunks = 0;
-  long long ncells_cap = 0;
-  int scan_blocks_cap = 0;
-  int64_t workspace_bytes = 0;
-  bool weights_set = false;
-  bool voxelized = false;
-  bool count_dirty = true;  // count table must be zero before a point pass; the fill pass leaves it zero
-  // last lisec_voxelize() inputs (export / VFE gather from them)
-  const void* last_points = nullptr;
-  int last_dtype = LISEC_F32;
-  SweepOffsets last_so;
-  int launches = 0;
-  // host-input pipeline: copies go on their own stream into alternating staging buffers, so the H2D copy of call i+1
-  // overlaps the kernels of call i
-  cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_copied[2] = {nullptr, nullptr};  // staging[b] holds the new points
-  cudaEvent_t ev_free[2] = {nullptr, nullptr};    // the kernels that read staging[b] have been enqueued and finished
-  void* staging2 = nullptr;                       // second staging buffer (the first is ws.staging)
-  int staging_idx = 0;
-  // CUDA events around the fused VFE + grid kernel of the last fused call (bench.py's live roofline figure)
-  cudaEvent_t ev_kernel[2] = {nullptr, nullptr};
-  bool kernel_timed = false;
-  char err[512];
-};
-
 namespace {
-
-int fail(lisec_handle* h, int code, const char* fmt, ...) {
-  if (h) {
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(h->err, sizeof(h->err), fmt, ap);
-    va_end(ap);
-  }
-  return code;
-}
-
-int cuda_fail(lisec_handle* h, cudaError_t e, const char* what) {
-  return fail(h, LISEC_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
-}
-
-#define LISEC_CUDA(h, call)                                 \
-  do {                                                      \
-    cudaError_t e_ = (call);                                \
-    if (e_ != cudaSuccess) return cuda_fail(h, e_, #call);  \
-  } while (0)
 
 bool is_pow2_double(double s) {
   int e;
   return s > 0 && std::frexp(s, &e) == 0.5;
-}
-
-template <typename T>
-cudaError_t dev_alloc(lisec_handle* h, T** p, size_t n) {
-  size_t bytes = n * sizeof(T);
-  bytes = (bytes + 255) & ~size_t(255);
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), bytes);
-  if (e == cudaSuccess) h->workspace_bytes += (int64_t)bytes;
-  return e;
 }
 
 void free_workspace(Workspace& w) {
@@ -283,6 +218,7 @@ void lisec_destroy(lisec_handle* h) {
   if (!h) return;
   if (h->sm_count > 0) cudaSetDevice(h->cfg.device);
   free_workspace(h->ws);
+  if (h->train) free_vfe_train_state(h->train);
   if (h->staging2) cudaFree(h->staging2);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (int b = 0; b < 2; ++b)

@@ -1,0 +1,618 @@
+// The VFE stack in TRAINING mode (model_training.py:229-235 under fit(), :299): forward with batch statistics and the
+// backward pass, on ROWS WITH MULTIPLICITIES — the exact restatement of the dense graph that oracle/train_oracle.py:
+// forward_train_rows() states and tests. The dense input holds three classes of rows:
+//   kept points                      weight 1
+//   one virtual pad row per non-full voxel, standing for its T - s identical zero rows      weight T - s
+//   ONE empty row standing for the T * n_empty rows of all empty voxels                     weight T * n_empty
+// Every BatchNormalization statistic is the weighted sum over these rows divided by M = n_cells * T; the per-voxel max
+// runs over a voxel's rows; its gradient is split equally among tied COPIES (TensorFlow's reduce_max rule), so compact
+// row r receives w_r * g / n_ties with n_ties = sum of the weights of the tied rows.
+//
+// The rows are the voxelizer's own VFE rows (row_start / row_voxel / row_xyz of the last lisec_voxelize(): kept rows and
+// the pad row of every voxel, contiguous), plus one more row for the empty voxels at index n_rows. Everything is O(rows):
+// ~115 k rows x 112 channels per 100 k-point sweep; one thread per row (or per voxel x 4 channels), float32 arithmetic,
+// every reduction in float64 with a fixed summation order (bit-reproducible, no atomics).
+#include <cuda_bf16.h>
+
+#include <new>
+
+#include "handle.cuh"
+#include "vfe_math.cuh"
+
+namespace lisec {
+
+constexpr int kTrBlocks = 296;      // persistent blocks of the reduction kernels (2 per SM)
+constexpr int kTrThreads = 256;
+
+struct VfeTrainState {
+  long long max_rows = 0, max_vox = 0;
+  float* x0 = nullptr;        // [rows][6] input features
+  float* w = nullptr;         // [rows] copies per compact row
+  int* seg = nullptr;         // [rows] voxel of the row (n_voxels for the empty row)
+  float* u[3] = {};           // [rows][C] dense outputs (pre-BN)
+  float* hh[3] = {};          // [rows][C] layer outputs (post ReLU)
+  float* pooled[3] = {};      // [voxels + 1][C] per-voxel max (row n_voxels: the empty voxels)
+  float* bn[3] = {};          // [6][C]: a = gamma * inv_std, b = beta - mean * a, mean, inv_std, S1 / M, S2 / M
+  float* gy = nullptr;        // [rows][64] gradient w.r.t. the BN output, then (in place) w.r.t. the dense output
+  float* gdir = nullptr;      // [rows][32] gradient reaching a layer's output through the next layer's pointwise half
+  float* ggath = nullptr;     // [rows][32] ... through the next layer's pooled half (summed per voxel by the pool backward)
+  float* gpool = nullptr;     // [voxels + 1][64] gradient w.r.t. the last layer's per-voxel max
+  double* partial = nullptr;  // [kTrBlocks][2 * 64] column-sum partials
+  float* wpartial = nullptr;  // [kTrBlocks][64 * 64] weight-gradient partials
+  float* bg = nullptr;        // [64] the empty voxels' output row (the grid's background)
+  int n_sweeps = 0;
+};
+
+void free_vfe_train_state(VfeTrainState* s) {
+  if (!s) return;
+  void* ptrs[] = {s->x0, s->w, s->seg, s->u[0], s->u[1], s->u[2], s->hh[0], s->hh[1], s->hh[2], s->pooled[0], s->pooled[1],
+                  s->pooled[2], s->bn[0], s->bn[1], s->bn[2], s->gy, s->gdir, s->ggath, s->gpool, s->partial, s->wpartial,
+                  s->bg};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete s;
+}
+
+namespace {
+
+constexpr int kC[3] = {16, 32, 64};
+
+// ---- rows: centroid + features (model_training.py:134-141), weights, segments ------------------------------
+template <typename PT>
+__global__ void __launch_bounds__(256) tr_rows_kernel(const PT* __restrict__ row_xyz, const int* __restrict__ row_start,
+                                                      const int* __restrict__ row_voxel,
+                                                      const long long* __restrict__ totals, long long ncells, int T,
+                                                      float* __restrict__ x0, float* __restrict__ w,
+                                                      int* __restrict__ seg) {
+  const long long V = totals[TOT_VOXELS], R = totals[TOT_ROWS];
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v > V) return;
+  if (v == V) {  // the empty voxels' row: zero input, T * n_empty copies
+#pragma unroll
+    for (int k = 0; k < 6; ++k) x0[R * 6 + k] = 0.f;
+    w[R] = (float)((double)T * (double)(ncells - V));
+    seg[R] = (int)V;
+    return;
+  }
+  const int rs = row_start[v], re = row_start[v + 1];
+  const bool pad = (row_voxel[re - 1] & kRowPadFlag) != 0;
+  const int n = re - rs - (pad ? 1 : 0);
+  double sx = 0.0, sy = 0.0, sz = 0.0;
+  for (int r = rs; r < rs + n; ++r) {  // np.mean: float64 adds in list order, one divide (:135)
+    sx += (double)row_xyz[3 * (size_t)r];
+    sy += (double)row_xyz[3 * (size_t)r + 1];
+    sz += (double)row_xyz[3 * (size_t)r + 2];
+  }
+  const double dn = (double)n;
+  const double cx = sx / dn, cy = sy / dn, cz = sz / dn;
+  for (int r = rs; r < rs + n; ++r) {
+    float f[6];
+    point_features((double)row_xyz[3 * (size_t)r], (double)row_xyz[3 * (size_t)r + 1], (double)row_xyz[3 * (size_t)r + 2],
+                   cx, cy, cz, f);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) x0[(size_t)r * 6 + k] = f[k];
+    w[r] = 1.f;
+    seg[r] = (int)v;
+  }
+  if (pad) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) x0[(size_t)(re - 1) * 6 + k] = 0.f;
+    w[re - 1] = (float)(T - n);
+    seg[re - 1] = (int)v;
+  }
+}
+
+// ---- dense forward: u[r] = in[r] * W, in = x0[r] (first layer) or [pooled_prev[seg[r]] | h_prev[r]] ---------
+template <int CIN, int COUT, bool CONCAT>
+__global__ void __launch_bounds__(kTrThreads) tr_dense_kernel(const float* __restrict__ x0,
+                                                              const float* __restrict__ pooled_prev,
+                                                              const float* __restrict__ h_prev,
+                                                              const int* __restrict__ seg, const float* __restrict__ W,
+                                                              const long long* __restrict__ totals,
+                                                              float* __restrict__ u) {
+  __shared__ float sW[CIN * COUT];
+  for (int i = threadIdx.x; i < CIN * COUT; i += kTrThreads) sW[i] = W[i];
+  __syncthreads();
+  const long long R = totals[TOT_ROWS] + 1;
+  const long long r = (long long)blockIdx.x * kTrThreads + threadIdx.x;
+  if (r >= R) return;
+  float in[CIN];
+  if (CONCAT) {
+    constexpr int H = CIN / 2;
+    const float* p = pooled_prev + (size_t)seg[r] * H;
+    const float* q = h_prev + (size_t)r * H;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      in[i] = p[i];
+      in[H + i] = q[i];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < CIN; ++i) in[i] = x0[(size_t)r * CIN + i];
+  }
+  float* dst = u + (size_t)r * COUT;
+#pragma unroll 4
+  for (int c = 0; c < COUT; ++c) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < CIN; ++i) acc = fmaf(in[i], sW[i * COUT + c], acc);
+    dst[c] = acc;
+  }
+}
+
+// ---- column sums over the rows, float64, fixed order ---------------------------------------------------------
+// MODE 0: Sa = sum w u, Sb = sum w u^2 (batch statistics).   MODE 1: Sa = sum gy, Sb = sum gy * xhat (BN backward).
+// MODE 2: Sa = sum a (plain column sum of a [n][C] array), Sb unused.
+// thread = (channel, row slice); a block's partial lands in partial[block][2 * C]
+template <int C, int MODE>
+__global__ void __launch_bounds__(kTrThreads) tr_colsum_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                               const float* __restrict__ w, const float* __restrict__ bn,
+                                                               const long long* __restrict__ n_ptr, long long n_extra,
+                                                               long long n_fixed, double* __restrict__ partial) {
+  constexpr int SL = kTrThreads / C;
+  __shared__ double red[2][kTrThreads];
+  const int c = threadIdx.x % C, sl = threadIdx.x / C;
+  const long long n = n_ptr ? *n_ptr + n_extra : n_fixed;
+  double sa = 0.0, sb = 0.0;
+  float mean = 0.f, inv = 0.f;
+  if (MODE == 1) {
+    mean = bn[2 * C + c];
+    inv = bn[3 * C + c];
+  }
+  for (long long r = (long long)blockIdx.x * SL + sl; r < n; r += (long long)gridDim.x * SL) {
+    const float v = a[(size_t)r * C + c];
+    if (MODE == 0) {
+      const double wv = (double)w[r] * (double)v;
+      sa += wv;
+      sb += wv * (double)v;
+    } else if (MODE == 1) {
+      sa += (double)v;
+      sb += (double)v * (double)((b[(size_t)r * C + c] - mean) * inv);
+    } else {
+      sa += (double)v;
+    }
+  }
+  red[0][threadIdx.x] = sa;
+  red[1][threadIdx.x] = sb;
+  __syncthreads();
+  if (sl == 0) {
+    for (int s = 1; s < SL; ++s) {
+      sa += red[0][s * C + c];
+      sb += red[1][s * C + c];
+    }
+    partial[(size_t)blockIdx.x * 2 * C + c] = sa;
+    partial[(size_t)blockIdx.x * 2 * C + C + c] = sb;
+  }
+}
+
+// batch statistics -> folded BN, moving statistics (momentum 0.99; the biased batch variance: these 6-D inputs take
+// Keras's non-fused BatchNormalization path)
+template <int C>
+__global__ void tr_stats_finalize_kernel(const double* __restrict__ partial, int nblocks, long long ncells, int T,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                         float momentum, float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                                         float* __restrict__ bn) {
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  double sa = 0.0, sb = 0.0;
+  for (int b = 0; b < nblocks; ++b) {
+    sa += partial[(size_t)b * 2 * C + c];
+    sb += partial[(size_t)b * 2 * C + C + c];
+  }
+  const double M = (double)ncells * (double)T;
+  const double mean = sa / M, var = fmax(sb / M - mean * mean, 0.0);
+  const double inv = 1.0 / sqrt(var + (double)eps);
+  const double a = (double)gamma[c] * inv;
+  bn[c] = (float)a;
+  bn[C + c] = (float)((double)beta[c] - mean * a);
+  bn[2 * C + c] = (float)mean;
+  bn[3 * C + c] = (float)inv;
+  if (moving_mean) {
+    moving_mean[c] = (float)((double)moving_mean[c] * momentum + mean * (1.0 - (double)momentum));
+    moving_var[c] = (float)((double)moving_var[c] * momentum + var * (1.0 - (double)momentum));
+  }
+}
+
+// BN backward sums -> dgamma = S2, dbeta = S1, and S1 / M, S2 / M for the data gradient
+template <int C>
+__global__ void tr_bn_bwd_finalize_kernel(const double* __restrict__ partial, int nblocks, long long ncells, int T,
+                                          float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ bn) {
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  double sa = 0.0, sb = 0.0;
+  for (int b = 0; b < nblocks; ++b) {
+    sa += partial[(size_t)b * 2 * C + c];
+    sb += partial[(size_t)b * 2 * C + C + c];
+  }
+  const double M = (double)ncells * (double)T;
+  dgamma[c] = (float)sb;
+  dbeta[c] = (float)sa;
+  bn[4 * C + c] = (float)(sa / M);
+  bn[5 * C + c] = (float)(sb / M);
+}
+
+// ---- BN + ReLU + per-voxel max: thread = (voxel, 4 channels) ------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) tr_act_pool_kernel(const float* __restrict__ u, const float* __restrict__ bn,
+                                                          const int* __restrict__ row_start,
+                                                          const long long* __restrict__ totals, float* __restrict__ h,
+                                                          float* __restrict__ pooled) {
+  constexpr int Q = C / 4;
+  const long long V = totals[TOT_VOXELS], R = totals[TOT_ROWS];
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long v = idx / Q;
+  const int q = (int)(idx % Q);
+  if (v > V) return;
+  const long long rs = v < V ? row_start[v] : R, re = v < V ? row_start[v + 1] : R + 1;
+  const float4 a = *reinterpret_cast<const float4*>(bn + 4 * q);
+  const float4 b = *reinterpret_cast<const float4*>(bn + C + 4 * q);
+  float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  for (long long r = rs; r < re; ++r) {
+    const float4 x = *reinterpret_cast<const float4*>(u + (size_t)r * C + 4 * q);
+    float4 y;
+    y.x = fmaxf(fmaf(x.x, a.x, b.x), 0.f);
+    y.y = fmaxf(fmaf(x.y, a.y, b.y), 0.f);
+    y.z = fmaxf(fmaf(x.z, a.z, b.z), 0.f);
+    y.w = fmaxf(fmaf(x.w, a.w, b.w), 0.f);
+    *reinterpret_cast<float4*>(h + (size_t)r * C + 4 * q) = y;
+    mx.x = fmaxf(mx.x, y.x); mx.y = fmaxf(mx.y, y.y); mx.z = fmaxf(mx.z, y.z); mx.w = fmaxf(mx.w, y.w);
+  }
+  *reinterpret_cast<float4*>(pooled + (size_t)v * C + 4 * q) = mx;
+}
+
+// ---- gradient arriving at the stack: d out[v] = dgrid[cell of v] ------------------------------------------
+__global__ void __launch_bounds__(256) tr_gather_dout_kernel(const float* __restrict__ dgrid,
+                                                             const int* __restrict__ voxel_cell,
+                                                             const long long* __restrict__ totals,
+                                                             float* __restrict__ gpool) {
+  const long long V = totals[TOT_VOXELS];
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long v = idx >> 4;
+  const int q = (int)(idx & 15);
+  if (v >= V) return;
+  *reinterpret_cast<float4*>(gpool + (size_t)v * 64 + 4 * q) =
+      *reinterpret_cast<const float4*>(dgrid + (size_t)voxel_cell[v] * 64 + 4 * q);
+}
+// the empty row's share: sum of dgrid over the EMPTY cells = (sum over all cells) - (sum over the occupied ones)
+__global__ void tr_empty_dout_kernel(const double* __restrict__ part_all, const double* __restrict__ part_occ, int nblocks,
+                                     const long long* __restrict__ totals, float* __restrict__ gpool) {
+  const int c = threadIdx.x;
+  if (c >= 64) return;
+  double all = 0.0, occ = 0.0;
+  for (int b = 0; b < nblocks; ++b) {
+    all += part_all[(size_t)b * 128 + c];
+    occ += part_occ[(size_t)b * 128 + c];
+  }
+  gpool[(size_t)totals[TOT_VOXELS] * 64 + c] = (float)(all - occ);
+}
+
+// ---- max + ReLU backward: thread = (voxel, 4 channels) -------------------------------------------------------
+// gradient w.r.t. the per-voxel max: gpool[v] (last layer) or the sum over the voxel's rows of ggath (the next layer's
+// pooled half); split equally among the tied copies; plus the next layer's pointwise half (gdir); through the ReLU.
+template <int C, bool LAST>
+__global__ void __launch_bounds__(256) tr_pool_bwd_kernel(const float* __restrict__ h, const float* __restrict__ pooled,
+                                                          const float* __restrict__ w, const float* __restrict__ gpool,
+                                                          const float* __restrict__ ggath, const float* __restrict__ gdir,
+                                                          const int* __restrict__ row_start,
+                                                          const long long* __restrict__ totals, float* __restrict__ gy) {
+  constexpr int Q = C / 4;
+  const long long V = totals[TOT_VOXELS], R = totals[TOT_ROWS];
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long v = idx / Q;
+  const int q = (int)(idx % Q);
+  if (v > V) return;
+  const long long rs = v < V ? row_start[v] : R, re = v < V ? row_start[v + 1] : R + 1;
+  const float4 p = *reinterpret_cast<const float4*>(pooled + (size_t)v * C + 4 * q);
+  float g[4], ties[4] = {0.f, 0.f, 0.f, 0.f};
+  if (LAST) {
+    const float4 t = *reinterpret_cast<const float4*>(gpool + (size_t)v * C + 4 * q);
+    g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
+  } else {
+    g[0] = g[1] = g[2] = g[3] = 0.f;
+  }
+  for (long long r = rs; r < re; ++r) {
+    const float4 x = *reinterpret_cast<const float4*>(h + (size_t)r * C + 4 * q);
+    const float wr = w[r];
+    ties[0] += x.x == p.x ? wr : 0.f;
+    ties[1] += x.y == p.y ? wr : 0.f;
+    ties[2] += x.z == p.z ? wr : 0.f;
+    ties[3] += x.w == p.w ? wr : 0.f;
+    if (!LAST) {
+      const float4 t = *reinterpret_cast<const float4*>(ggath + (size_t)r * C + 4 * q);
+      g[0] += t.x; g[1] += t.y; g[2] += t.z; g[3] += t.w;
+    }
+  }
+  const float pv[4] = {p.x, p.y, p.z, p.w};
+  for (long long r = rs; r < re; ++r) {
+    const float4 x = *reinterpret_cast<const float4*>(h + (size_t)r * C + 4 * q);
+    const float xv[4] = {x.x, x.y, x.z, x.w};
+    const float wr = w[r];
+    float out[4];
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!LAST) d = *reinterpret_cast<const float4*>(gdir + (size_t)r * C + 4 * q);
+    const float dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gh = dv[k] + (xv[k] == pv[k] ? wr * g[k] / ties[k] : 0.f);
+      out[k] = xv[k] > 0.f ? gh : 0.f;
+    }
+    *reinterpret_cast<float4*>(gy + (size_t)r * C + 4 * q) = make_float4(out[0], out[1], out[2], out[3]);
+  }
+}
+
+// ---- BN + dense backward (data): thread = row ----------------------------------------------------------------
+// gu = a * (gy - w * S1/M - w * xhat * S2/M) (weighted batch statistics), stored in place of gy;
+// g_in = gu * W^T -> first half: ggath (pooled path), second half: gdir (pointwise path) of the previous layer
+template <int CIN, int COUT, bool CONCAT>
+__global__ void __launch_bounds__(kTrThreads) tr_dense_bwd_kernel(const float* __restrict__ u,
+                                                                  const float* __restrict__ w,
+                                                                  const float* __restrict__ bn,
+                                                                  const float* __restrict__ W,
+                                                                  const long long* __restrict__ totals,
+                                                                  float* __restrict__ gy, float* __restrict__ ggath,
+                                                                  float* __restrict__ gdir) {
+  __shared__ float sW[CIN * COUT];
+  __shared__ float sBn[6 * COUT];
+  for (int i = threadIdx.x; i < CIN * COUT; i += kTrThreads) sW[i] = W[i];
+  for (int i = threadIdx.x; i < 6 * COUT; i += kTrThreads) sBn[i] = bn[i];
+  __syncthreads();
+  const long long R = totals[TOT_ROWS] + 1;
+  const long long r = (long long)blockIdx.x * kTrThreads + threadIdx.x;
+  if (r >= R) return;
+  const float wr = w[r];
+  float gin[CONCAT ? CIN : 1];
+  if (CONCAT) {
+#pragma unroll
+    for (int i = 0; i < CIN; ++i) gin[i] = 0.f;
+  }
+  float* g = gy + (size_t)r * COUT;
+  const float* ur = u + (size_t)r * COUT;
+#pragma unroll 2
+  for (int c = 0; c < COUT; ++c) {
+    const float xhat = (ur[c] - sBn[2 * COUT + c]) * sBn[3 * COUT + c];
+    const float gu = sBn[c] * (g[c] - wr * sBn[4 * COUT + c] - wr * xhat * sBn[5 * COUT + c]);
+    g[c] = gu;
+    if (CONCAT) {
+#pragma unroll
+      for (int i = 0; i < CIN; ++i) gin[i] = fmaf(gu, sW[i * COUT + c], gin[i]);
+    }
+  }
+  if (CONCAT) {
+    constexpr int H = CIN / 2;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      ggath[(size_t)r * H + i] = gin[i];
+      gdir[(size_t)r * H + i] = gin[H + i];
+    }
+  }
+}
+
+// ---- dense backward (weights): dW[i][j] = sum_r in[r][i] * gu[r][j] ------------------------------------------
+// persistent blocks; 32 rows at a time through shared memory; a thread owns entries tid, tid + 256, ... of the matrix
+template <int CIN, int COUT, bool CONCAT>
+__global__ void __launch_bounds__(kTrThreads) tr_wgrad_kernel(const float* __restrict__ x0,
+                                                              const float* __restrict__ pooled_prev,
+                                                              const float* __restrict__ h_prev,
+                                                              const int* __restrict__ seg, const float* __restrict__ gu,
+                                                              const long long* __restrict__ totals,
+                                                              float* __restrict__ wpartial) {
+  constexpr int RB = 32, E = CIN * COUT, PER = (E + kTrThreads - 1) / kTrThreads;
+  __shared__ float sIn[RB][CIN + 1];
+  __shared__ float sG[RB][COUT + 1];
+  const long long R = totals[TOT_ROWS] + 1;
+  float acc[PER];
+#pragma unroll
+  for (int k = 0; k < PER; ++k) acc[k] = 0.f;
+  for (long long r0 = (long long)blockIdx.x * RB; r0 < R; r0 += (long long)gridDim.x * RB) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < RB * CIN; t += kTrThreads) {
+      const int rr = t / CIN, i = t % CIN;
+      const long long r = r0 + rr;
+      float v = 0.f;
+      if (r < R) {
+        if (CONCAT) v = i < CIN / 2 ? pooled_prev[(size_t)seg[r] * (CIN / 2) + i] : h_prev[(size_t)r * (CIN / 2) + i - CIN / 2];
+        else v = x0[(size_t)r * CIN + i];
+      }
+      sIn[rr][i] = v;
+    }
+    for (int t = threadIdx.x; t < RB * COUT; t += kTrThreads) {
+      const int rr = t / COUT, j = t % COUT;
+      const long long r = r0 + rr;
+      sG[rr][j] = r < R ? gu[(size_t)r * COUT + j] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int e = threadIdx.x + k * kTrThreads;
+      if (e < E) {
+        const int i = e / COUT, j = e % COUT;
+        float a = acc[k];
+#pragma unroll 8
+        for (int rr = 0; rr < RB; ++rr) a = fmaf(sIn[rr][i], sG[rr][j], a);
+        acc[k] = a;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int e = threadIdx.x + k * kTrThreads;
+    if (e < E) wpartial[(size_t)blockIdx.x * E + e] = acc[k];
+  }
+}
+__global__ void tr_wgrad_reduce_kernel(const float* __restrict__ wpartial, int nblocks, int E, float* __restrict__ dW) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += (double)wpartial[(size_t)b * E + e];
+  dW[e] = (float)s;
+}
+
+__global__ void tr_copy_bg_kernel(const float* __restrict__ pooled, const long long* __restrict__ totals,
+                                  float* __restrict__ bg) {
+  if (threadIdx.x < 64) bg[threadIdx.x] = pooled[(size_t)totals[TOT_VOXELS] * 64 + threadIdx.x];
+}
+
+unsigned blocks_for(long long n, int per = 256) { return (unsigned)((n + per - 1) / per); }
+
+int ensure_state(lisec_handle* h) {
+  if (h->train) return LISEC_OK;
+  VfeTrainState* s = new (std::nothrow) VfeTrainState();
+  if (!s) return fail(h, LISEC_ERR_CUDA, "out of host memory");
+  h->train = s;
+  s->max_vox = h->max_voxels + 1;
+  s->max_rows = h->cfg.max_points + h->max_voxels + 1;
+  const size_t Rm = (size_t)s->max_rows, Vm = (size_t)s->max_vox;
+  LISEC_CUDA(h, dev_alloc(h, &s->x0, Rm * 6));
+  LISEC_CUDA(h, dev_alloc(h, &s->w, Rm));
+  LISEC_CUDA(h, dev_alloc(h, &s->seg, Rm));
+  for (int l = 0; l < 3; ++l) {
+    LISEC_CUDA(h, dev_alloc(h, &s->u[l], Rm * kC[l]));
+    LISEC_CUDA(h, dev_alloc(h, &s->hh[l], Rm * kC[l]));
+    LISEC_CUDA(h, dev_alloc(h, &s->pooled[l], Vm * kC[l]));
+    LISEC_CUDA(h, dev_alloc(h, &s->bn[l], (size_t)6 * kC[l]));
+  }
+  LISEC_CUDA(h, dev_alloc(h, &s->gy, Rm * 64));
+  LISEC_CUDA(h, dev_alloc(h, &s->gdir, Rm * 32));
+  LISEC_CUDA(h, dev_alloc(h, &s->ggath, Rm * 32));
+  LISEC_CUDA(h, dev_alloc(h, &s->gpool, Vm * 64));
+  LISEC_CUDA(h, dev_alloc(h, &s->partial, (size_t)2 * kTrBlocks * 128));
+  LISEC_CUDA(h, dev_alloc(h, &s->wpartial, (size_t)kTrBlocks * 64 * 64));
+  LISEC_CUDA(h, dev_alloc(h, &s->bg, (size_t)64));
+  return LISEC_OK;
+}
+
+template <int L>
+cudaError_t forward_layer(lisec_handle* h, const lisec_vfe_train_params* p, long long ncells, cudaStream_t st) {
+  VfeTrainState* s = h->train;
+  constexpr int CIN = L == 0 ? 6 : (L == 1 ? 32 : 64), COUT = L == 0 ? 16 : (L == 1 ? 32 : 64);
+  const long long* tot = h->ws.totals;
+  tr_dense_kernel<CIN, COUT, (L > 0)><<<blocks_for(s->max_rows), kTrThreads, 0, st>>>(
+      s->x0, L > 0 ? s->pooled[L - 1] : nullptr, L > 0 ? s->hh[L - 1] : nullptr, s->seg, p->dense_kernel[L], tot, s->u[L]);
+  tr_colsum_kernel<COUT, 0><<<kTrBlocks, kTrThreads, 0, st>>>(s->u[L], nullptr, s->w, nullptr, tot + TOT_ROWS, 1, 0,
+                                                             s->partial);
+  tr_stats_finalize_kernel<COUT><<<1, 64, 0, st>>>(s->partial, kTrBlocks, ncells, h->geom.T, p->bn_gamma[L], p->bn_beta[L],
+                                                  p->bn_epsilon, p->bn_momentum, p->moving_mean[L], p->moving_var[L],
+                                                  s->bn[L]);
+  tr_act_pool_kernel<COUT><<<blocks_for(s->max_vox * (COUT / 4)), 256, 0, st>>>(s->u[L], s->bn[L], h->ws.row_start, tot,
+                                                                              s->hh[L], s->pooled[L]);
+  h->launches += 4;
+  return cudaGetLastError();
+}
+
+template <int L>
+cudaError_t backward_layer(lisec_handle* h, const lisec_vfe_train_params* p, const lisec_vfe_train_grads* g,
+                           long long ncells, cudaStream_t st) {
+  VfeTrainState* s = h->train;
+  constexpr int CIN = L == 0 ? 6 : (L == 1 ? 32 : 64), COUT = L == 0 ? 16 : (L == 1 ? 32 : 64);
+  const long long* tot = h->ws.totals;
+  tr_pool_bwd_kernel<COUT, (L == 2)><<<blocks_for(s->max_vox * (COUT / 4)), 256, 0, st>>>(
+      s->hh[L], s->pooled[L], s->w, s->gpool, s->ggath, s->gdir, h->ws.row_start, tot, s->gy);
+  tr_colsum_kernel<COUT, 1><<<kTrBlocks, kTrThreads, 0, st>>>(s->gy, s->u[L], nullptr, s->bn[L], tot + TOT_ROWS, 1, 0,
+                                                             s->partial);
+  tr_bn_bwd_finalize_kernel<COUT><<<1, 64, 0, st>>>(s->partial, kTrBlocks, ncells, h->geom.T, g->dgamma[L], g->dbeta[L],
+                                                   s->bn[L]);
+  // (ggath / gdir of THIS layer have been consumed by the pool backward above: the data gradient may overwrite them)
+  tr_dense_bwd_kernel<CIN, COUT, (L > 0)><<<blocks_for(s->max_rows), kTrThreads, 0, st>>>(
+      s->u[L], s->w, s->bn[L], p->dense_kernel[L], tot, s->gy, s->ggath, s->gdir);
+  tr_wgrad_kernel<CIN, COUT, (L > 0)><<<kTrBlocks, kTrThreads, 0, st>>>(
+      s->x0, L > 0 ? s->pooled[L - 1] : nullptr, L > 0 ? s->hh[L - 1] : nullptr, s->seg, s->gy, tot, s->wpartial);
+  tr_wgrad_reduce_kernel<<<blocks_for(CIN * COUT), 256, 0, st>>>(s->wpartial, kTrBlocks, CIN * COUT, g->dkernel[L]);
+  h->launches += 6;
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_grid_write(const Geom& g, int n_sweeps, int c3, int grid_dtype, const int* cell_voxel,
+                              const float* voxel_feat, const float* c_empty, void* grid, int sm_count,
+                              cudaStream_t st, int* launches);
+
+}  // namespace lisec
+
+using namespace lisec;
+
+extern "C" {
+
+int32_t lisec_vfe_train_forward(lisec_handle* h, const lisec_vfe_train_params* p, void* grid, void* stream) {
+  if (!h) return LISEC_ERR_BAD_ARG;
+  if (!p || !grid) return fail(h, LISEC_ERR_BAD_ARG, "params / grid is NULL");
+  if (!h->voxelized) return fail(h, LISEC_ERR_STATE, "no lisec_voxelize() result on this handle");
+  for (int l = 0; l < 3; ++l)
+    if (!p->dense_kernel[l] || !p->bn_gamma[l] || !p->bn_beta[l])
+      return fail(h, LISEC_ERR_BAD_ARG, "training parameters of layer %d contain a NULL pointer", l);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
+  int rc = ensure_state(h);
+  if (rc) return rc;
+  h->launches = 0;
+  VfeTrainState* s = h->train;
+  s->n_sweeps = h->last_so.n;
+  const long long ncells = (long long)h->last_so.n * h->geom.cells;
+  if (h->last_dtype == LISEC_F32)
+    tr_rows_kernel<float><<<blocks_for(s->max_vox), 256, 0, st>>>(static_cast<const float*>(h->ws.row_xyz), h->ws.row_start,
+                                                               h->ws.row_voxel, h->ws.totals, ncells, h->geom.T, s->x0,
+                                                               s->w, s->seg);
+  else
+    tr_rows_kernel<double><<<blocks_for(s->max_vox), 256, 0, st>>>(static_cast<const double*>(h->ws.row_xyz),
+                                                                h->ws.row_start, h->ws.row_voxel, h->ws.totals, ncells,
+                                                                h->geom.T, s->x0, s->w, s->seg);
+  ++h->launches;
+  LISEC_CUDA(h, cudaGetLastError());
+  LISEC_CUDA(h, forward_layer<0>(h, p, ncells, st));
+  LISEC_CUDA(h, forward_layer<1>(h, p, ncells, st));
+  LISEC_CUDA(h, forward_layer<2>(h, p, ncells, st));
+  // the voxel rows into the grid, the empty voxels' output (row n_voxels of the last pooled table, an address only the
+  // device knows) as the background
+  tr_copy_bg_kernel<<<1, 64, 0, st>>>(s->pooled[2], h->ws.totals, s->bg);
+  ++h->launches;
+  LISEC_CUDA(h, cudaGetLastError());
+  LISEC_CUDA(h, launch_grid_write(h->geom, h->last_so.n, 64, h->cfg.grid_dtype, h->ws.cell_voxel, s->pooled[2], s->bg, grid,
+                                  h->sm_count, st, &h->launches));
+  return LISEC_OK;
+}
+
+int32_t lisec_vfe_train_backward(lisec_handle* h, const lisec_vfe_train_params* p, const float* dgrid,
+                                 const lisec_vfe_train_grads* g, void* stream) {
+  if (!h) return LISEC_ERR_BAD_ARG;
+  if (!p || !dgrid || !g) return fail(h, LISEC_ERR_BAD_ARG, "params / dgrid / grads is NULL");
+  if (!h->train || h->train->n_sweeps == 0) return fail(h, LISEC_ERR_STATE, "no lisec_vfe_train_forward() on this handle");
+  for (int l = 0; l < 3; ++l)
+    if (!g->dkernel[l] || !g->dgamma[l] || !g->dbeta[l] || !p->dense_kernel[l])
+      return fail(h, LISEC_ERR_BAD_ARG, "gradient outputs of layer %d contain a NULL pointer", l);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
+  h->launches = 0;
+  VfeTrainState* s = h->train;
+  const long long ncells = (long long)s->n_sweeps * h->geom.cells;
+  const long long* tot = h->ws.totals;
+  // d out[v] = dgrid[cell of v]; the empty row gets the sum over the empty cells
+  tr_gather_dout_kernel<<<blocks_for(s->max_vox * 16), 256, 0, st>>>(dgrid, h->ws.voxel_cell, tot, s->gpool);
+  tr_colsum_kernel<64, 2><<<kTrBlocks, kTrThreads, 0, st>>>(dgrid, nullptr, nullptr, nullptr, nullptr, 0, ncells, s->partial);
+  tr_colsum_kernel<64, 2><<<kTrBlocks, kTrThreads, 0, st>>>(s->gpool, nullptr, nullptr, nullptr, tot + TOT_VOXELS, 0, 0,
+                                                           s->partial + (size_t)kTrBlocks * 128);
+  tr_empty_dout_kernel<<<1, 64, 0, st>>>(s->partial, s->partial + (size_t)kTrBlocks * 128, kTrBlocks, tot, s->gpool);
+  h->launches += 4;
+  LISEC_CUDA(h, cudaGetLastError());
+  LISEC_CUDA(h, backward_layer<2>(h, p, g, ncells, st));
+  LISEC_CUDA(h, backward_layer<1>(h, p, g, ncells, st));
+  LISEC_CUDA(h, backward_layer<0>(h, p, g, ncells, st));
+  return LISEC_OK;
+}
+
+/* Test aid: the training forward's per-voxel output rows [n_voxels + 1][64] (the last row = the empty voxels) and the
+   batch statistics (mean, inverse standard deviation) of layer `layer`, copied to the host. Synchronous. */
+int32_t lisec_vfe_train_read(lisec_handle* h, int32_t layer, float* out_rows, int64_t n_rows, float* mean, float* inv_std) {
+  if (!h) return LISEC_ERR_BAD_ARG;
+  if (!h->train) return fail(h, LISEC_ERR_STATE, "no lisec_vfe_train_forward() on this handle");
+  if (layer < 0 || layer > 2) return fail(h, LISEC_ERR_BAD_ARG, "layer = %d", layer);
+  LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
+  LISEC_CUDA(h, cudaDeviceSynchronize());
+  const int C = kC[layer];
+  if (out_rows)
+    LISEC_CUDA(h, cudaMemcpy(out_rows, h->train->pooled[layer], sizeof(float) * (size_t)n_rows * C, cudaMemcpyDeviceToHost));
+  if (mean) LISEC_CUDA(h, cudaMemcpy(mean, h->train->bn[layer] + 2 * C, sizeof(float) * C, cudaMemcpyDeviceToHost));
+  if (inv_std) LISEC_CUDA(h, cudaMemcpy(inv_std, h->train->bn[layer] + 3 * C, sizeof(float) * C, cudaMemcpyDeviceToHost));
+  return LISEC_OK;
+}
+
+}  // extern "C"

@@ -793,6 +793,65 @@ class ConvTransposeBackward:
         self.wgrad.close()
 
 
+class VfeTrainer:
+    """The VFE stack (the first 23 Keras layers, model_training.py:229-235) in TRAINING mode on one GPU: forward with
+    batch statistics into the dense grid, backward from the grid's gradient to the gradients of dense*/kernel and
+    batch_normalization*/{gamma,beta} — lisec_vfe_train_forward / _backward (lisec_b200/csrc/vfe_train.cu), evaluated on
+    rows with multiplicities exactly as oracle/train_oracle.py: forward_train_rows() states it.
+    `params`: Keras-named float32 CUDA tensors (dense/kernel (6,16), batch_normalization/gamma, ..., moving statistics
+    updated in place); `grads`: tensors of the same names and shapes that receive the gradients."""
+
+    def __init__(self, frontend, params: Dict[str, torch.Tensor], grads: Dict[str, torch.Tensor], eps=1e-3, momentum=0.99):
+        from .weights import VFE_BN, VFE_DENSE
+
+        self.fe, self._lib = frontend, N.load()
+        self.params, self.grads = params, grads
+        P, G = N.lisec_vfe_train_params(), N.lisec_vfe_train_grads()
+        for i, (d, b) in enumerate(zip(VFE_DENSE, VFE_BN)):
+            for t in (params[d + "/kernel"], params[b + "/gamma"], params[b + "/beta"], grads[d + "/kernel"],
+                      grads[b + "/gamma"], grads[b + "/beta"]):
+                if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+                    raise ValueError("VfeTrainer wants contiguous float32 CUDA tensors")
+            P.dense_kernel[i] = params[d + "/kernel"].data_ptr()
+            P.bn_gamma[i] = params[b + "/gamma"].data_ptr()
+            P.bn_beta[i] = params[b + "/beta"].data_ptr()
+            mm, mv = params.get(b + "/moving_mean"), params.get(b + "/moving_variance")
+            P.moving_mean[i] = mm.data_ptr() if mm is not None else None
+            P.moving_var[i] = mv.data_ptr() if mv is not None else None
+            G.dkernel[i] = grads[d + "/kernel"].data_ptr()
+            G.dgamma[i] = grads[b + "/gamma"].data_ptr()
+            G.dbeta[i] = grads[b + "/beta"].data_ptr()
+        P.bn_epsilon, P.bn_momentum = eps, momentum
+        self._P, self._G = P, G
+
+    def forward(self, points, sweep_offsets, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """voxelize + the VFE stack with batch statistics -> grid [n_sweeps, nz, nx, ny, 64] (the handle's grid dtype)."""
+        fe = self.fe
+        fe.voxelize(points, sweep_offsets)
+        if out is None:
+            out = fe.new_grid(fe._n_sweeps)
+        with torch.cuda.device(fe.device):
+            fe._check(self._lib.lisec_vfe_train_forward(fe._h, C.byref(self._P), C.c_void_p(out.data_ptr()), fe._stream()))
+        return out
+
+    def backward(self, dgrid: torch.Tensor) -> None:
+        fe = self.fe
+        if dgrid.dtype != torch.float32 or not dgrid.is_contiguous():
+            raise ValueError("dgrid: contiguous float32 [n_sweeps, nz, nx, ny, 64]")
+        with torch.cuda.device(fe.device):
+            fe._check(self._lib.lisec_vfe_train_backward(fe._h, C.byref(self._P), C.c_void_p(dgrid.data_ptr()),
+                                                         C.byref(self._G), fe._stream()))
+
+    def read_layer(self, layer: int, n_voxels: int):
+        """(per-voxel output rows [n_voxels + 1, C], batch mean [C], batch variance [C]) of `layer` — a test aid."""
+        Cl = (16, 32, 64)[layer]
+        rows = np.zeros((n_voxels + 1, Cl), np.float32)
+        mean, inv = np.zeros(Cl, np.float32), np.zeros(Cl, np.float32)
+        fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
+        self.fe._check(self._lib.lisec_vfe_train_read(self.fe._h, layer, fp(rows), n_voxels + 1, fp(mean), fp(inv)))
+        return rows, mean, 1.0 / inv.astype(np.float64) ** 2 - 1e-3
+
+
 class DenseNetworkTrainer:
     """The dense network behind the voxel grid in TRAINING mode (model_training.py:236-254 under fit): three Conv3D blocks,
     the RPN's sixteen Conv2D + BN + ReLU stages, the three transposed convolutions into the concat tensor, the heads and the
