@@ -257,18 +257,80 @@ def predictMain(samples, outPath, level5Data, model, combine_lidar_data=None, dt
             np.save(os.path.join(outPath, "sample%d_regress.npy" % (i0 + j)), regress[j:j + 1])  # Predict.py:40
 
 
-def train(samples, level5Data, save_path):
-    """model_training.train (model_training.py:260-302). NOT BUILT: the backward pass (through the VFE stack and the
-    dense network, with training-mode BatchNormalization). What the step needs around it exists and is tested —
-    lisec_b200/train.py: flat parameter buffers, the NCCL gradient all-reduce, the Keras SGD-Nesterov update kernel, the
-    'mse' loss head; oracle/train_oracle.py restates the whole step. Inference is complete."""
-    raise NotImplementedError("lisec_b200 implements the inference path (Predict.predictMain); train() is not built yet")
+def save_model(pack: dict, save_path: str) -> None:
+    """model.save(save_path) (model_training.py:302, 346): `.h5` in Keras's weight layout (lisec_b200/h5write.py), anything
+    else as an .npz weight pack. Either loads back with load_model()."""
+    if str(save_path).lower().endswith((".h5", ".hdf5")):
+        from .h5write import write_keras_weights
+
+        write_keras_weights(save_path, pack)
+    else:
+        from .weights import save_npz
+
+        save_npz(save_path, pack)
 
 
-def train_with_model(samples, level5Data, model_path, save_path):
-    """model_training.train_with_model (model_training.py:305-346). NOT BUILT, see train()."""
-    raise NotImplementedError("lisec_b200 implements the inference path (Predict.predictMain); train_with_model() is "
-                              "not built yet")
+def _fit(pack, samples, level5Data, save_path, labels_dir, steps_per_epoch, batch_size, dataDir, combine_lidar_data, device,
+         labels):
+    import os
+
+    from .train import TrainStep
+
+    if combine_lidar_data is None:
+        if dataDir is None:
+            raise ValueError("dataDir: the Lyft dataset directory (the reference's Constants.lyft_data_dir)")
+        from .ingest import combine_lidar_data
+    clouds = [np.ascontiguousarray(combine_lidar_data(s, dataDir, level5Data)) for s in samples]  # :266-283
+    if labels is None:  # :288-290 (the reference spells the path with a Windows separator)
+        def load(name):
+            for cand in (os.path.join(labels_dir, name), labels_dir + "\\" + name):
+                if os.path.exists(cand):
+                    return np.load(cand, allow_pickle=True)
+            raise FileNotFoundError(os.path.join(labels_dir, name))
+        labels = (load("labelsClass.npy"), load("regressClass.npy"))
+    outClass, outRegress = (np.asarray(a, dtype=np.float32) for a in labels)
+    if len(outClass) < len(clouds) or len(outRegress) < len(clouds):
+        raise ValueError("%d samples but %d / %d label entries" % (len(clouds), len(outClass), len(outRegress)))
+    n = len(clouds)
+    step = TrainStep(pack, batch=batch_size, max_points=batch_size * max(len(c) for c in clouds), device=device,
+                     nx=K.nx, ny=K.ny, nz=K.nz)
+    dev = torch.device("cuda", device)
+    yc, yr = torch.from_numpy(outClass).to(dev), torch.from_numpy(outRegress).to(dev)
+    history = []
+    for it in range(steps_per_epoch):  # fit(batch_size=1, epochs=1, steps_per_epoch=180) (:299)
+        idx = [(it * batch_size + b) % n for b in range(batch_size)]
+        pts = np.concatenate([clouds[i] for i in idx])
+        off = np.cumsum([0] + [len(clouds[i]) for i in idx]).tolist()
+        loss = step.step(pts, off, yc[idx].contiguous(), yr[idx].contiguous())
+        history.append(loss)
+    history = [float(l) for l in history]  # one host read-back at the end
+    out = step.to_pack()
+    step.close()
+    save_model(out, save_path)  # :302
+    return {"loss": history}
+
+
+def train(samples, level5Data, save_path, labels_dir="labels3", steps_per_epoch=180, batch_size=1, dataDir=None,
+          combine_lidar_data=None, device=0, seed=0, labels=None):
+    """model_training.train(samples, level5Data, save_path) (model_training.py:260-302): voxelize every sample, load the
+    labels (`labels_dir`/labelsClass.npy, regressClass.npy, or `labels=(cls, reg)`), createModel(), SGD(lr=0.01, decay=1e-6,
+    momentum=0.9, nesterov=True), loss=['mse','mse'], fit(batch_size=1, epochs=1, steps_per_epoch=180), model.save.
+    Every step runs on the GPU (lisec_b200/train.py: TrainStep): the VFE stack with batch statistics, the dense network
+    as bf16 tensor-core plans with float32 master weights, both backward passes, the Keras update. The samples are not
+    densified (the reference stacks 1.1 GB per sample at :279-285); the step walks them one per iteration, cyclically.
+    Returns history.history (the per-step losses), which the reference prints (:301)."""
+    from .weights import keras_default_init_pack
+
+    return _fit(keras_default_init_pack(seed), samples, level5Data, save_path, labels_dir, steps_per_epoch, batch_size,
+                dataDir, combine_lidar_data, device, labels)
+
+
+def train_with_model(samples, level5Data, model_path, save_path, labels_dir="labels3", steps_per_epoch=180, batch_size=1,
+                     dataDir=None, combine_lidar_data=None, device=0, labels=None):
+    """model_training.train_with_model (model_training.py:305-346): as train(), starting from load_model(model_path)."""
+    model = load_model(model_path)
+    return _fit(model.pack, samples, level5Data, save_path, labels_dir, steps_per_epoch, batch_size, dataDir,
+                combine_lidar_data, device, labels)
 
 
 def createModel(nx=K.nx, ny=K.ny, nz=K.nz, maxPoints=K.maxPoints, weights: Optional[dict] = None, seed: int = 0):

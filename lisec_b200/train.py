@@ -793,6 +793,89 @@ class ConvTransposeBackward:
         self.wgrad.close()
 
 
+def plan_layout(name: str, arr: np.ndarray) -> np.ndarray:
+    """Keras layout -> the layout the training plans keep their float32 master weights in (DenseNetworkTrainer).
+    A pure permutation of the elements, so the elementwise SGD update can run on either layout."""
+    from .weights import conv3d_blocks, rpn_blocks
+
+    a = np.asarray(arr, dtype=np.float32)
+    leaf = name.split("/")[1]
+    if leaf != "kernel":
+        return np.ascontiguousarray(a)
+    base = name.split("/")[0]
+    c3 = {c: d for c, _, d, _, _ in conv3d_blocks()}
+    if base in c3:
+        return np.ascontiguousarray(a.reshape(27, 64, 64).transpose(0, 2, 1))
+    if base in c3.values():
+        return np.ascontiguousarray(a.T[None])
+    for convs, (tname, k, s, cin) in rpn_blocks():
+        for conv, _, ci, co, _ in convs:
+            if base == conv:
+                return np.ascontiguousarray(a.reshape(9, ci, co).transpose(0, 2, 1))
+        if base == tname:
+            return np.ascontiguousarray(a[::-1, ::-1].reshape(9, 256, cin)) if s == 1 else np.ascontiguousarray(a)
+    raise KeyError(name)
+
+
+def keras_layout(name: str, arr: np.ndarray) -> np.ndarray:
+    """The inverse of plan_layout()."""
+    from .weights import conv3d_blocks, rpn_blocks
+
+    a = np.asarray(arr, dtype=np.float32)
+    leaf = name.split("/")[1]
+    if leaf != "kernel":
+        return np.ascontiguousarray(a)
+    base = name.split("/")[0]
+    c3 = {c: d for c, _, d, _, _ in conv3d_blocks()}
+    if base in c3:
+        return np.ascontiguousarray(a.transpose(0, 2, 1).reshape(3, 3, 3, 64, 64))
+    if base in c3.values():
+        return np.ascontiguousarray(a[0].T)
+    for convs, (tname, k, s, cin) in rpn_blocks():
+        for conv, _, ci, co, _ in convs:
+            if base == conv:
+                return np.ascontiguousarray(a.transpose(0, 2, 1).reshape(3, 3, ci, co))
+        if base == tname:
+            return np.ascontiguousarray(a.reshape(3, 3, 256, cin)[::-1, ::-1]) if s == 1 else np.ascontiguousarray(a)
+    raise KeyError(name)
+
+
+class FlatStore:
+    """One flat float32 buffer each for the variables, the optimizer accumulators and the gradients of the WHOLE model,
+    carved into per-weight views as the trainers ask for them (every view 16-byte aligned): one SGD kernel launch and one
+    all-reduce per step cover everything. Duck-compatible with FlatParameters for SgdNesterov."""
+
+    def __init__(self, capacity: int, device):
+        self.device = torch.device(device)
+        self.var = torch.zeros(capacity, dtype=torch.float32, device=self.device)
+        self.accum = torch.zeros_like(self.var)
+        self.grad = torch.zeros_like(self.var)
+        self.offsets, self.shapes, self.used = {}, {}, 0
+
+    def alloc(self, name: str, arr: np.ndarray) -> torch.Tensor:
+        a = np.ascontiguousarray(arr, dtype=np.float32)
+        n = a.size
+        if self.used + n > self.var.numel():
+            raise RuntimeError("FlatStore capacity exceeded")
+        self.offsets[name], self.shapes[name] = self.used, a.shape
+        v = self.var[self.used:self.used + n].view(a.shape)
+        v.copy_(torch.from_numpy(a))
+        self.used += (n + 3) // 4 * 4
+        return v
+
+    def grad_view(self, name: str) -> torch.Tensor:
+        o, sh = self.offsets[name], self.shapes[name]
+        return self.grad[o:o + int(np.prod(sh))].view(sh)
+
+    def var_view(self, name: str) -> torch.Tensor:
+        o, sh = self.offsets[name], self.shapes[name]
+        return self.var[o:o + int(np.prod(sh))].view(sh)
+
+    @property
+    def numel_padded(self) -> int:
+        return self.used
+
+
 class VfeTrainer:
     """The VFE stack (the first 23 Keras layers, model_training.py:229-235) in TRAINING mode on one GPU: forward with
     batch statistics into the dense grid, backward from the grid's gradient to the gradients of dense*/kernel and
@@ -860,29 +943,39 @@ class DenseNetworkTrainer:
     plans' layouts (see _to_plan_layout), their gradients in self.grads[name] after backward(). The VFE stack in front of
     the grid is not part of this class (its training kernels are not built yet): `grid` is an input."""
 
-    def __init__(self, pack: dict, batch: int, nx: int, ny: int, nz: int = 8, device: int = 0):
+    def __init__(self, pack: dict, batch: int, nx: int, ny: int, nz: int = 8, device: int = 0, alloc=None,
+                 need_grid_grad: bool = False):
+        """alloc(name, float32 array) -> CUDA tensor holding it: where a trainable weight's master copy lives (default:
+        its own tensor; TrainStep hands out views of one flat buffer). need_grid_grad: also compute d loss / d grid
+        (float32, self.grid_grad after loss_and_backward) for the VFE stack in front."""
         from .weights import conv3d_blocks, rpn_blocks
 
         self._lib = N.load()
         dev = torch.device("cuda", device)
         self.device = dev
         B = batch
-        f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)  # noqa: E731
+        own = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)  # noqa: E731
+
+        def mk(name, a):  # trainable weights go through alloc(); moving statistics stay in tensors of their own
+            return alloc(name, a) if (alloc is not None and "moving_" not in name) else own(a)
+
         self.params, self.stages = {}, []
+        self.grid_grad = None
         self.grid = torch.zeros((B, nz, nx, ny, 64), dtype=torch.bfloat16, device=dev)
         P = self.params
         x, d = self.grid, nz
         self.c3 = []
         for i, (conv, bn, dense, stride, pad) in enumerate(conv3d_blocks()):
-            P[conv + "/kernel"] = f32(np.asarray(pack[conv + "/kernel"]).reshape(27, 64, 64).transpose(0, 2, 1))
-            P[dense + "/kernel"] = f32(np.asarray(pack[dense + "/kernel"]).T[None])
+            P[conv + "/kernel"] = mk(conv + "/kernel", np.asarray(pack[conv + "/kernel"]).reshape(27, 64, 64).transpose(0, 2, 1))
+            P[dense + "/kernel"] = mk(dense + "/kernel", np.asarray(pack[dense + "/kernel"]).T[None])
             for f in ("bias",):
-                P[conv + "/" + f] = f32(pack[conv + "/" + f])
+                P[conv + "/" + f] = mk(conv + "/" + f, pack[conv + "/" + f])
             for f in ("gamma", "beta", "moving_mean", "moving_variance"):
-                P[bn + "/" + f] = f32(pack[bn + "/" + f])
+                P[bn + "/" + f] = mk(bn + "/" + f, pack[bn + "/" + f])
             st = Conv3dBlockTrain(x, P[conv + "/kernel"], P[conv + "/bias"], P[bn + "/gamma"], P[bn + "/beta"],
                                   P[dense + "/kernel"], (3, 3, 3), pad, stride_d=stride[0],
-                                  moving_mean=P[bn + "/moving_mean"], moving_var=P[bn + "/moving_variance"], need_dx=i > 0,
+                                  moving_mean=P[bn + "/moving_mean"], moving_var=P[bn + "/moving_variance"],
+                                  need_dx=i > 0 or need_grid_grad,
                                   grad_dtype=torch.float32)
             self.c3.append((st, conv, bn, dense))
             x = st.y
@@ -892,29 +985,29 @@ class DenseNetworkTrainer:
         for bi, (convs, (tname, k, s, tc_in)) in enumerate(rpn_blocks()):
             stages = []
             for conv, bn, cin, cout, stride in convs:
-                P[conv + "/kernel"] = f32(np.asarray(pack[conv + "/kernel"]).reshape(9, cin, cout).transpose(0, 2, 1))
-                P[conv + "/bias"] = f32(pack[conv + "/bias"])
+                P[conv + "/kernel"] = mk(conv + "/kernel", np.asarray(pack[conv + "/kernel"]).reshape(9, cin, cout).transpose(0, 2, 1))
+                P[conv + "/bias"] = mk(conv + "/bias", pack[conv + "/bias"])
                 for f in ("gamma", "beta", "moving_mean", "moving_variance"):
-                    P[bn + "/" + f] = f32(pack[bn + "/" + f])
+                    P[bn + "/" + f] = mk(bn + "/" + f, pack[bn + "/" + f])
                 st = ConvBnReluTrain(x, P[conv + "/kernel"], P[conv + "/bias"], P[bn + "/gamma"], P[bn + "/beta"], (1, 3, 3),
                                      (0, 1, 1), moving_mean=P[bn + "/moving_mean"], moving_var=P[bn + "/moving_variance"],
                                      stride_hw=stride, grad_dtype=torch.float32)
                 stages.append((st, conv, bn))
                 x = st.bn.y
             F = np.asarray(pack[tname + "/kernel"], dtype=np.float32)  # (k, k, 256, cin)
-            P[tname + "/bias"] = f32(pack[tname + "/bias"])
+            P[tname + "/bias"] = mk(tname + "/bias", pack[tname + "/bias"])
             dy_t = torch.zeros((B, 1, nx // 2, ny // 2, 256), dtype=torch.bfloat16, device=dev)
             if s == 1:
-                P[tname + "/kernel"] = f32(F[::-1, ::-1].reshape(9, 256, tc_in))  # the flipped-kernel convolution's layout
+                P[tname + "/kernel"] = mk(tname + "/kernel", F[::-1, ::-1].reshape(9, 256, tc_in))  # the flipped-kernel convolution's layout
                 tail = ConvBiasTrain(x, P[tname + "/kernel"], P[tname + "/bias"], (1, 3, 3), (0, 1, 1), self.concat, 256 * bi, dy_t,
                                      grad_dtype=torch.float32)
             else:
-                P[tname + "/kernel"] = f32(F)  # Keras layout (k, k, 256, cin)
+                P[tname + "/kernel"] = mk(tname + "/kernel", F)  # Keras layout (k, k, 256, cin)
                 tail = _ShuffleTail(self._lib, x, P[tname + "/kernel"], P[tname + "/bias"], s, self.concat, 256 * bi, dy_t)
             self.blocks.append((stages, tail, tname, s, dy_t, x))
         Kh = np.concatenate([np.asarray(pack["ClassificationLayer/kernel"])[0, 0], np.asarray(pack["RegressionLayer/kernel"])[0, 0]], axis=1)
-        P["heads/kernel"] = f32(Kh.T[None])  # [1][16][768]: rows 0-1 ClassificationLayer, 2-15 RegressionLayer
-        P["heads/bias"] = f32(np.concatenate([pack["ClassificationLayer/bias"], pack["RegressionLayer/bias"]]))
+        P["heads/kernel"] = mk("heads/kernel", Kh.T[None])  # [1][16][768]: rows 0-1 ClassificationLayer, 2-15 RegressionLayer
+        P["heads/bias"] = mk("heads/bias", np.concatenate([pack["ClassificationLayer/bias"], pack["RegressionLayer/bias"]]))
         self.heads = HeadsTrain(self.concat, P["heads/kernel"], P["heads/bias"], dense_slices=True)
         self.grads = {}
 
@@ -954,9 +1047,20 @@ class DenseNetworkTrainer:
         dx = carry
         for st, conv, bn, dense in reversed(self.c3):
             dx = st.backward(dx)
+            self.grid_grad = dx  # after the loop: the first block's data gradient = d loss / d grid (or None)
             G[conv + "/kernel"], G[conv + "/bias"], G[dense + "/kernel"] = st.dw, st.dbias, st.dwd
             G[bn + "/gamma"], G[bn + "/beta"] = st.bn.dgamma, st.bn.dbeta
         return lc + lr
+
+    def refresh_weights(self) -> None:
+        """After the float32 master weights changed (an optimizer step): re-derive the plans' bf16 operand copies."""
+        for st, *_ in self.c3:
+            st.refresh_weights()
+        for stages, tail, *_ in self.blocks:
+            for st, *_ in stages:
+                st.refresh_weights()
+            tail.refresh_weights()
+        self.heads.refresh_weights()
 
     def close(self):
         for st, *_ in self.c3:
@@ -966,6 +1070,83 @@ class DenseNetworkTrainer:
                 st.close()
             tail.close()
         self.heads.close()
+
+
+class TrainStep:
+    """One fit() step of model_training.train() (model_training.py:295-299) on one GPU, the whole model:
+    voxelize -> VFE stack with batch statistics (VfeTrainer) -> dense network (DenseNetworkTrainer, bf16 tensor-core plans,
+    float32 master weights) -> loss=['mse','mse'] -> backward through both -> [NCCL all-reduce of the flat gradient, summed;
+    per-replica BatchNormalization statistics] -> optimizers.SGD(lr=0.01, decay=1e-6, momentum=0.9, nesterov=True) on one
+    flat buffer -> the plans' operand copies refreshed. `pack`: Keras-named float arrays of the whole createModel()."""
+
+    def __init__(self, pack: dict, batch: int, max_points: int, device: int = 0, nx: int = 200, ny: int = 400, nz: int = 8,
+                 lr=0.01, decay=1e-6, momentum=0.9, nesterov=True, group=None, bucket_elems: int = 0):
+        from .frontend import Frontend
+        from .weights import VFE_BN, VFE_DENSE
+
+        self.group, self.bucket_elems, self.batch = group, bucket_elems, batch
+        dev = torch.device("cuda", device)
+        n_train = sum(int(np.prod(np.shape(v))) for k, v in pack.items() if "moving_" not in k)
+        self.store = FlatStore(n_train + 4 * len(pack), dev)
+        self.fe = Frontend(device=device, max_points=max_points, max_sweeps=batch, grid_dtype="bf16",
+                           max_voxel=(nx // 2, ny // 2, nz))
+        # the VFE stack's parameters first (Keras creation order), Keras layout
+        self.vfe_params, vfe_grads = {}, {}
+        for d, b in zip(VFE_DENSE, VFE_BN):
+            for k in (d + "/kernel", b + "/gamma", b + "/beta"):
+                self.vfe_params[k] = self.store.alloc(k, pack[k])
+            for f in ("moving_mean", "moving_variance"):
+                self.vfe_params[b + "/" + f] = torch.from_numpy(np.ascontiguousarray(pack[b + "/" + f], dtype=np.float32)).to(dev)
+        self.dense = DenseNetworkTrainer(pack, batch, nx, ny, nz, device=device, alloc=self.store.alloc, need_grid_grad=True)
+        for k in list(self.vfe_params):
+            if "moving_" not in k:
+                vfe_grads[k] = self.store.grad_view(k)
+        self.vfe = VfeTrainer(self.fe, self.vfe_params, vfe_grads)
+        self.opt = SgdNesterov(self.store, lr, decay, momentum, nesterov)
+        self.pack_names = list(pack)
+        self.exposed_allreduce_ms = None
+
+    def step(self, points, sweep_offsets, y_class: torch.Tensor, y_regress: torch.Tensor) -> torch.Tensor:
+        """points: (n, 3) host or device array of the batch's sweeps, concatenated; labels: float32 CUDA tensors
+        (B, nx/2, ny/2, 2) and (B, nx/2, ny/2, 14). Returns the loss (0-d float64 device tensor)."""
+        import torch.distributed as dist
+
+        self.vfe.forward(points, sweep_offsets, out=self.dense.grid)
+        self.dense.forward()
+        loss = self.dense.loss_and_backward(y_class, y_regress)
+        self.vfe.backward(self.dense.grid_grad.contiguous())
+        for name, g in self.dense.grads.items():  # the dense network's gradients into the flat buffer (plan layout)
+            self.store.grad_view(name).copy_(g.reshape(self.store.shapes[name]))
+        world = 1
+        if dist.is_available() and dist.is_initialized():
+            world = dist.get_world_size(self.group)
+            for w in allreduce_gradients(self.store.grad[:self.store.numel_padded], self.group, self.bucket_elems):
+                w.wait()
+        self.opt.step(world)
+        self.dense.refresh_weights()
+        return loss
+
+    def to_pack(self) -> Dict[str, np.ndarray]:
+        """The model's weights under the Keras names and in the Keras layouts (what model.save() persists)."""
+        out = {}
+        P = self.dense.params
+        for k in self.pack_names:
+            base, leaf = k.split("/")
+            if k in self.vfe_params:
+                out[k] = self.vfe_params[k].detach().cpu().numpy().copy()
+            elif base in ("ClassificationLayer", "RegressionLayer"):
+                sl = slice(0, 2) if base == "ClassificationLayer" else slice(2, 16)
+                if leaf == "kernel":
+                    out[k] = np.ascontiguousarray(P["heads/kernel"][0, sl].detach().cpu().numpy().T[None, None])
+                else:
+                    out[k] = P["heads/bias"][sl].detach().cpu().numpy().copy()
+            else:
+                out[k] = keras_layout(k, P[k].detach().cpu().numpy())
+        return out
+
+    def close(self):
+        self.dense.close()
+        self.fe.close()
 
 
 class _ShuffleTail:

@@ -141,6 +141,30 @@ def synthetic_network_pack(seed: int = 0) -> dict:
     return pack
 
 
+def keras_default_init_pack(seed: int = 0) -> dict:
+    """What createModel() (model_training.py:222-257) holds before fit(): Keras's default initialisers — Glorot-uniform
+    kernels, zero biases, gamma = 1, beta = 0, moving_mean = 0, moving_variance = 1 (seeded here; Keras seeds from the clock)."""
+    rng = np.random.default_rng(seed)
+    shapes = {}
+    for d, b, sh in zip(VFE_DENSE, VFE_BN, VFE_SHAPES):
+        shapes[d + "/kernel"] = sh
+        for f in BN_FIELDS:
+            shapes[b + "/" + f] = (sh[1],)
+    shapes.update(network_shapes())
+    pack = {}
+    for name, shape in shapes.items():
+        leaf = name.split("/")[1]
+        if leaf == "kernel":
+            rf = int(np.prod(shape[:-2]))
+            lim = np.sqrt(6.0 / (rf * (shape[-2] + shape[-1])))
+            pack[name] = rng.uniform(-lim, lim, size=shape).astype(np.float32)
+        elif leaf in ("gamma", "moving_variance"):
+            pack[name] = np.ones(shape, np.float32)
+        else:
+            pack[name] = np.zeros(shape, np.float32)
+    return pack
+
+
 def synthetic_model_pack(seed: int = 0) -> dict:
     pack = synthetic_vfe_pack(seed)
     pack.update(synthetic_network_pack(seed))
