@@ -100,19 +100,25 @@ def run_reference(args):
         threadpool_limits(limits=cores)
     except Exception:
         pass
-    frac, slab = 0.1, 50
+    # one step = whole units of the reference's CPU path: the literal-loop voxelizer on ONE WHOLE sweep (100k points,
+    # model_training.py:112-152) + the dense VFE stack on ONE WHOLE z-plane (200 x 400 voxels x 35 slots, :229-235).
+    # A sweep is 8 such planes of identical shape and cost, so seconds per sweep = t_voxelizer + 8 * t_plane; the planes
+    # are not all evaluated so that the arm ends within minutes (stated in `sample` and `extrapolated`).
     for _ in range(args.warmup):
-        cpu_reference_time_per_sweep(pts, frac / 4, 10, pack)
-    per_sweep = []
+        cpu_reference_time_per_sweep(pts, 0.02, 10, pack)
+    per_sweep, t_v, t_p = [], [], []
     t_begin = time.perf_counter()
     for _ in range(args.steps):
-        tv, tf = cpu_reference_time_per_sweep(pts, frac, slab, pack)
+        tv, tf = cpu_reference_time_per_sweep(pts, 1.0, 200, pack)  # tf is already scaled x8 (one plane of eight)
         per_sweep.append(tv + tf)
+        t_v.append(tv)
+        t_p.append(tf / 8)
     wall = time.perf_counter() - t_begin
     sec = float(np.mean(per_sweep))
     value = 1.0 / sec
-    sample = ("per step: literal-loop voxelizer on 10%% of one 100k-point sweep (x10) + dense VFE stack on a "
-              "[1,%d,400,35,6] slab (x%d) -> seconds per sweep; numpy float32, BLAS threads" % (slab, 8 * 200 // slab))
+    sample = ("per step: literal-loop voxelizer on one whole 100k-point sweep (%.2f s, 1 core: pure Python as in the "
+              "reference) + dense VFE stack on one whole z-plane [1,200,400,35,6] (%.2f s, numpy float32, BLAS threads); "
+              "seconds per sweep = voxelizer + 8 x plane" % (float(np.mean(t_v)), float(np.mean(t_p))))
     line = {
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": "sweeps/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -120,7 +126,9 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sweeps_per_gpu": SWEEPS_PER_GPU, "points_per_sweep": POINTS_PER_SWEEP},
         "points_per_s": value * POINTS_PER_SWEEP,
-        "cpu_baseline": {"value": value, "unit": "sweeps/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "sweeps/s", "cores": cores, "kind": "port", "sample": sample,
+                         "extrapolated": "the 8 z-planes of a sweep from one (identical shape and cost)",
+                         "seconds_per_sweep": sec},
         "e2e": {"value": value, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -286,7 +294,13 @@ def run_native(args):
     barrier()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     launches = fe.last_launch_count * args.steps
-    ms_kernel = fe.last_fused_kernel_ms  # the dominant kernel inside the last timed step, CUDA events on its stream
+    # the dominant kernel's launch duration, CUDA events on its stream around every launch of a second pass over the same
+    # steps (reading the events synchronises, so this pass is not the timed one): the AVERAGE over all of them
+    k_ms = []
+    for i in range(args.steps):
+        step(i)
+        k_ms.append(fe.last_fused_kernel_ms)
+    ms_kernel = float(np.mean(k_ms))
 
     # stages, each timed alone on the launching stream with CUDA events (the fused stage is the dominant kernel)
     def timed(fn, n):
@@ -405,6 +419,96 @@ def run_native(args):
         except Exception as exc:  # an auxiliary leg must not take the headline down with it
             bwd = {"error": "%s: %s" % (type(exc).__name__, exc)}
         torch.cuda.empty_cache()
+
+    # configs[1] as BASELINE.json words it: ONE batch of 8 sweeps sharded over the N GPUs (strong scaling: 8 / N sweeps per
+    # GPU and step). No collective; with 1 sweep per GPU the launch chain (7 kernels, ~25 us of algorithmic work) is the cost.
+    strong = None
+    if SWEEPS_PER_GPU % world == 0:
+        spg = SWEEPS_PER_GPU // world
+        off_s = offsets[:spg + 1]
+        grid_s = grid[:spg]
+        views = [b[:spg * POINTS_PER_SWEEP] for b in dev_batches]
+
+        def step_strong(i):
+            fe.forward(views[i % N_BATCHES], off_s, out=grid_s)
+
+        for i in range(args.warmup):
+            step_strong(i)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(args.steps):
+            step_strong(i)
+        s1.record()
+        barrier()
+        ms_strong = max_over_ranks(s0.elapsed_time(s1)) / args.steps
+        strong = {"workload": "configs[1], strong scaling: one batch of 8 sweeps over %d GPU(s), %d sweep(s) per GPU and step"
+                              % (world, spg), "sweeps_total": SWEEPS_PER_GPU, "sweeps_per_gpu": spg,
+                  "ms_per_step": ms_strong, "value": SWEEPS_PER_GPU / (ms_strong * 1e-3), "unit": "sweeps/s",
+                  "scaling": "strong",
+                  "limiter": "launch chain of 7 dependent kernels + the tail of a 148-CTA persistent kernel on %.0f MB of "
+                             "grid per GPU: latency, not bandwidth, once a GPU holds 1-2 sweeps" % (spg * 163.84)}
+
+    # configs[4]: the train() step (model_training.py:295-299), 2 sweeps per GPU (16 sweeps on 8 GPUs): voxelize, VFE stack
+    # with batch statistics, dense network (bf16 plans, float32 master weights), mse + mse, both backward passes, the NCCL
+    # all-reduce of the flat gradient, the Keras SGD-Nesterov update. Per-replica BatchNormalization statistics.
+    train = None
+    try:
+        from lisec_b200.train import TrainStep
+        from lisec_b200.weights import keras_default_init_pack
+
+        TB = 2
+        tstep = TrainStep(keras_default_init_pack(0), batch=TB, max_points=TB * POINTS_PER_SWEEP, device=local)
+        gl = torch.Generator(device="cpu").manual_seed(77 + rank)
+        y_cls = torch.randint(0, 3, (TB, GRID[1] // 2, GRID[2] // 2, 2), generator=gl).float().to(dev)
+        y_reg = (torch.randn((TB, GRID[1] // 2, GRID[2] // 2, 14), generator=gl) * 0.5).to(dev)
+        t_off = offsets[:TB + 1]
+        t_pts = [b[:TB * POINTS_PER_SWEEP] for b in dev_batches]
+        losses = []
+
+        def step_train(i):
+            losses.append(tstep.step(t_pts[i % N_BATCHES], t_off, y_cls, y_reg))
+
+        n_t = max(5, min(args.steps, 20))
+        for i in range(3):
+            step_train(i)
+        barrier()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for i in range(n_t):
+            step_train(i)
+        t1e.record()
+        barrier()
+        ms_train = max_over_ranks(t0e.elapsed_time(t1e)) / n_t
+        # where the step's time goes (each part timed alone, same buffers)
+        parts = {
+            "vfe_train_forward_ms": timed(lambda: tstep.vfe.forward(t_pts[0], t_off, out=tstep.dense.grid), 5),
+            "dense_forward_ms": timed(tstep.dense.forward, 5),
+            "dense_loss_backward_ms": timed(lambda: tstep.dense.loss_and_backward(y_cls, y_reg), 5),
+            "vfe_train_backward_ms": timed(lambda: tstep.vfe.backward(tstep.dense.grid_grad), 5),
+        }
+        flat = tstep.store.grad[:tstep.store.numel_padded]
+
+        def only_allreduce():
+            for w_ in allreduce_gradients(flat):
+                w_.wait()
+
+        parts["allreduce_ms"] = max_over_ranks(timed(only_allreduce, 10)) if world > 1 else 0.0
+        parts["sgd_update_ms"] = timed(lambda: tstep.opt.step(world), 10)
+        train = {"workload": "configs[4]: model_training.train() step, %d sweeps x 100k points per GPU (%d sweeps per step on "
+                             "%d GPU(s)), fwd + bwd + NCCL gradient all-reduce + SGD-Nesterov" % (TB, TB * world, world),
+                 "sweeps_per_step": TB * world, "ms_per_step": ms_train, "steps_per_s": 1e3 / ms_train,
+                 "value": TB * world / (ms_train * 1e-3), "unit": "sweeps/s", "dtype": "bf16 plans, f32 master weights, f32 VFE",
+                 "parameters": int(tstep.store.numel_padded), "gradient_bytes": int(tstep.store.numel_padded) * 4,
+                 "loss_first": float(losses[0]), "loss_last": float(losses[-1]), "parts": parts,
+                 "allreduce_share": parts["allreduce_ms"] / ms_train,
+                 "bn_statistics": "per replica (what a data-parallel Keras run does); the reference is batch_size=1 on one device",
+                 "note": "the all-reduce is issued after the backward pass (one bucket): all of it is exposed"}
+        tstep.close()
+        del tstep
+        torch.cuda.empty_cache()
+    except Exception as exc:  # an auxiliary leg must not take the headline down with it
+        train = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
     # end to end through the host-buffer entry point
     n_w = min(args.warmup, 3)
@@ -538,11 +642,14 @@ def run_native(args):
         e2e_value = total_sweeps / (ms_e2e * 1e-3)
         achieved = grid_bytes / (ms_kernel * 1e-3) / 1e9
         step_alg_bytes = points_bytes + grid_bytes  # 12*P + nz*nx*ny*C3*4 per sweep, x8 sweeps
-        traffic = None
+        # DRAM traffic of the dominant kernel: ncu counters cannot be read inside an untraced run, so the figure is the
+        # one of this round's committed `ncu --set full` capture of the same kernel on the same workload (source named)
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "fused_traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
         line = {
             "metric": METRIC, "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -558,13 +665,14 @@ def run_native(args):
                     "result": "per-sweep voxel counts + totals (the grid stays on the GPU for the Conv3D); H2D of step i+1 "
                               "overlaps the kernels of step i, totals read back asynchronously"},
             "gpu_launches": launches,
-            "roofline": {"kernel": "vfe_kernel<1> (fused VFE + dense-grid write), timed inside the last timed step",
+            "roofline": {"kernel": "vfe_kernel<1> (fused VFE + dense-grid write), average over %d launches inside whole steps" % len(k_ms),
                          "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": grid_bytes,
-                         "ms_per_launch": ms_kernel,
+                         "ms_per_launch": ms_kernel, "ms_per_launch_min": float(np.min(k_ms)),
+                         "ms_per_launch_max": float(np.max(k_ms)), "traffic_source": traffic_src,
                          "note": "HBM is the roofline the path is graded on; the same kernel carries the whole VFE stack "
-                                 "(FP32 pipe for VFE-1/VFE-2, tcgen05 3xTF32 for the FCN), which is what bounds it"},
+                                 "(VFE-1 on the FP32 pipe, VFE-2 and the FCN on tcgen05 as 3xTF32), which is what bounds it"},
             "roofline_grid_writer": {"kernel": "grid_write_f32_c64 (standalone writer, lisec_scatter_dense)",
                                      "bound": "hbm", "achieved": grid_bytes / (ms_writer * 1e-3) / 1e9, "peak": hbm_peak,
                                      "unit": "GB/s", "frac": grid_bytes / (ms_writer * 1e-3) / 1e9 / hbm_peak,
@@ -593,11 +701,9 @@ def run_native(args):
                                   "value": 1.0 / regions_cpu_s, "unit": "samples/s", "cores": 1, "kind": "port",
                                   "sample": "one sample: the oracle's numpy decode + vectorised greedy NMS (the "
                                             "reference's own Python loop takes ~16 s per sample)"}},
-            "train_step_pieces": {"built": "gradient all-reduce (NCCL, sum), sgd_nesterov_kernel over the flat float32 parameter "
-                                           "buffer, the mse loss head, convolution weight gradients (conv_wgrad_kernel) and "
-                                           "stride-1 data gradients (forward plans on dy) on the tensor cores, training-mode "
-                                           "BatchNormalization forward / backward; NOT yet: strided / transposed layers' "
-                                           "backward, the VFE stack's backward, the step that chains them",
+            "train_step_pieces": {"built": "pieces of the training step timed alone at the 8-sweep bench batch (the whole step: "
+                                           "train_step): the flat-gradient all-reduce (NCCL, sum) + sgd_nesterov_kernel, the "
+                                           "first Conv3D's weight gradient (conv_wgrad_kernel) and the second one's data gradient",
                                   "parameters": fp.numel, "gradient_bytes": fp.numel * 4,
                                   "sgd_update_ms": ms_update, "allreduce_plus_update_ms": ms_comm_update,
                                   "backward_kernels": bwd,
@@ -606,6 +712,8 @@ def run_native(args):
                                                "achieved": update_bytes / (ms_update * 1e-3) / 1e9, "peak": hbm_peak,
                                                "unit": "GB/s", "frac": update_bytes / (ms_update * 1e-3) / 1e9 / hbm_peak}},
             "config4_saturated_cloud": config4,
+            "strong_scaling": strong,
+            "train_step": train,
             "clocks": clocks,
         }
         if full is not None:
@@ -686,7 +794,7 @@ def main():
         args.warmup = 1 if args.warmup is None else args.warmup
         run_reference(args)
     else:
-        args.steps = 30 if args.steps is None else args.steps
+        args.steps = 200 if args.steps is None else args.steps
         args.warmup = max(3, 5 if args.warmup is None else args.warmup)
         run_native(args)
 
