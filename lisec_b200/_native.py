@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblisec_b200.so")
+LIB_PATH = os.environ.get("LISEC_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblisec_b200.so")
 
 LISEC_OK = 0
 LISEC_ERR_BAD_CONFIG = -2

@@ -106,7 +106,8 @@ constexpr int OFF_W2L = OFF_W2H + kWSlab;           // W2B lo             |
 // [kRows][16] lives in the same place, the team's stages being sequential), the tile's points, the landing buffers
 constexpr int kHBytes = kRows * 32 * 4;
 constexpr int kXyzBytes = kRows * 3 * 8 + 16;
-constexpr int kTeamBytes = kHBytes + kXyzBytes + kMetaSlots * (int)sizeof(TileMeta);
+constexpr int kHdrBytes = 4 * 16;  // ring of 4 tile headers (v0, v1, r0, r1), written by one thread of the team
+constexpr int kTeamBytes = kHBytes + kXyzBytes + kMetaSlots * (int)sizeof(TileMeta) + kHdrBytes;
 constexpr int OFF_TEAM = OFF_W2L + kWSlab;          // [2] x { H | PT xyz[kRows][3] | TileMeta[kMetaSlots] }
 constexpr int OFF_PAR = OFF_TEAM + 2 * kTeamBytes;
 constexpr int OFF_INFO = OFF_PAR + (int)sizeof(FrontParams);
@@ -522,6 +523,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
   float* sH = reinterpret_cast<float*>(team_base);
   PT* sXYZbuf = reinterpret_cast<PT*>(team_base + kHBytes);
   TileMeta* metas = reinterpret_cast<TileMeta*>(team_base + kHBytes + kXyzBytes);
+  int4* hdr_ring = reinterpret_cast<int4*>(team_base + kHBytes + kXyzBytes + kMetaSlots * sizeof(TileMeta));
   const FrontParams* fp = reinterpret_cast<const FrontParams*>(smem + OFF_PAR);
   const PT* g_xyz = static_cast<const PT*>(prob.row_xyz);
   const uint32_t tlane = tmem_base + ((uint32_t)(32 * (tw & 3)) << 16);
@@ -530,20 +532,28 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
   const int n_mine = (my_tiles + 1 - team) >> 1;  // tiles of this team
 
   // tile header = (first voxel, first row) of the tile and of its successor; rows and voxels are contiguous
+  // tile header = (first voxel, end voxel, first row, end row); rows and voxels of a tile are contiguous. ONE thread of
+  // the team walks the CTA's tile sequence (ordinals team, team + 2, ...) two tiles ahead and leaves the headers in a
+  // ring in shared memory; the other 255 threads carry no cursor state (registers are what this kernel is short of).
   struct Header { int v0, v1, r0, r1; };
+  const bool walker = ttid == kTeamThreads - 1;
   TileCursor cursor;
-  cursor.init(prob, n_chunks, team);
-  auto next_header = [&]() {  // the team's next tile (ordinals team, team + 2, ... of this CTA), or an empty header
-    Header h{0, 0, 0, 0};
+  if (walker) cursor.init(prob, n_chunks, team);
+  auto publish_header = [&](int k) {  // walker only: header of the team's tile k -> ring slot k & 3
+    int4 h = make_int4(0, 0, 0, 0);
     if (cursor.c < n_chunks) {
       const int t = cursor.c * kChunkSlots + cursor.j;
-      h.v0 = __ldcg(prob.tile_first + t);
-      h.v1 = __ldcg(prob.tile_first + t + 1);
-      h.r0 = __ldcg(prob.tile_row0 + t);
-      h.r1 = __ldcg(prob.tile_row0 + t + 1);
+      h.x = __ldcg(prob.tile_first + t);
+      h.y = __ldcg(prob.tile_first + t + 1);
+      h.z = __ldcg(prob.tile_row0 + t);
+      h.w = __ldcg(prob.tile_row0 + t + 1);
       cursor.advance(prob, n_chunks, 2);
     }
-    return h;
+    hdr_ring[k & 3] = h;
+  };
+  auto read_header = [&](int k) {
+    const int4 h = hdr_ring[k & 3];
+    return Header{h.x, h.y, h.z, h.w};
   };
   // asynchronous copy of a tile's points (contiguous in row order) and row / voxel tables into the landing buffers
   auto prefetch = [&](const Header& h, int k) {
@@ -558,16 +568,20 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
     }
   };
 
-  Header cur = next_header(), nxt = next_header();
-  if (n_mine > 0) prefetch(cur, 0);
+  if (walker) {
+    publish_header(0);
+    publish_header(1);
+  }
+  team_sync(team);
+  if (n_mine > 0) prefetch(read_header(0), 0);
   cp_async_commit();
   cp_async_wait_all();
   team_sync(team);
 
   for (int k = 0; k < n_mine; ++k) {
     const int i = 2 * k + team;  // tile ordinal of this CTA
-    const Header h = cur;
-    const Header nxt2 = next_header();
+    const Header h = read_header(k);
+    if (walker) publish_header(k + 2);  // (ring slot (k + 2) & 3 was last read two iterations ago)
     const TileMeta& mt = metas[k & 1];
     const int nrows = h.r1 - h.r0, nv = h.v1 - h.v0;
     // the landing buffers start at the 16-byte chunk that holds the tile's first element
@@ -659,7 +673,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
     }
     team_sync(team);
     // the point buffer and the other landing buffer are free: the team's next tile is on its way while this one is worked on
-    if (k + 1 < n_mine) prefetch(nxt, k + 1);
+    if (k + 1 < n_mine) prefetch(read_header(k + 1), k + 1);
     cp_async_commit();
     {  // MaxPoolingVFELayer over T (:160) + RepeatLayer + the pooled half of Concatenate (:164-165): item = (voxel, 4 channels)
       const int v = ttid >> 2, c = ttid & 3;
@@ -764,9 +778,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
     __syncwarp();
     if (lane == 0) umma::mbar_arrive(bar_x2_full(smem_base));  // 8 warps -> the tensor thread issues this tile's FCN
     cp_async_wait_all();
-    team_sync(team);  // publishes the landing buffers; sH may be overwritten
-    cur = nxt;
-    nxt = nxt2;
+    team_sync(team);  // publishes the landing buffers and the walker's header; sH may be overwritten
   }
   asm volatile("bar.sync 3, %0;" ::"n"(kFrontThreads + kBackThreads) : "memory");
   if (MODE != 0 && tid == 0) {  // (threadIdx.x != 0 here: stamp by hand)
