@@ -197,6 +197,12 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
     LISEC_CUDA(h, set_trace_vfe(w.trace));
   }
   for (int b = 0; b < 2; ++b) LISEC_CUDA(h, cudaEventCreate(&h->ev_kernel[b]));
+  LISEC_CUDA(h, cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) LISEC_CUDA(h, cudaEventCreateWithFlags(&h->ev_side[b], cudaEventDisableTiming));
+  if (const char* e = getenv("LISEC_BLIND_FRACTION")) {
+    const double v = atof(e);
+    if (v >= 0.0 && v <= 0.9) h->blind_fraction = v;
+  }
   LISEC_CUDA(h, dev_alloc(h, &w.empty_desc, (size_t)32));
   // the one-voxel problem whose VFE output is c_empty: 0 kept points, 1 pad row, 1 chunk of 1 tile. Layout (ints; the
   // arrays the kernel copies with 16-byte cp.async start on 16-byte boundaries):
@@ -221,6 +227,9 @@ void lisec_destroy(lisec_handle* h) {
   if (h->train) free_vfe_train_state(h->train);
   if (h->staging2) cudaFree(h->staging2);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  for (int b = 0; b < 2; ++b)
+    if (h->ev_side[b]) cudaEventDestroy(h->ev_side[b]);
   for (int b = 0; b < 2; ++b)
     if (h->ev_kernel[b]) cudaEventDestroy(h->ev_kernel[b]);
   for (int b = 0; b < 2; ++b) {
@@ -413,12 +422,12 @@ int32_t lisec_scatter_dense(lisec_handle* h, const float* voxel_feat, void* grid
   return LISEC_OK;
 }
 
-static int fused_stage(lisec_handle* h, void* grid, cudaStream_t st) {
+static int fused_stage(lisec_handle* h, void* grid, int first_group, cudaStream_t st) {
   const VfeProblem prob = vfe_problem(h);
   // one kernel: VFE (FP32 pipe + tensor core), voxel rows and the c_empty background written to the grid concurrently
   LISEC_CUDA(h, cudaEventRecord(h->ev_kernel[0], st));
   LISEC_CUDA(h, launch_vfe_to_grid(h->params, h->ws.vfe_w, prob, h->ws, h->geom, h->last_so.n, h->cfg.grid_dtype, grid,
-                                   h->sm_count, st, &h->launches));
+                                   first_group, h->sm_count, st, &h->launches));
   LISEC_CUDA(h, cudaEventRecord(h->ev_kernel[1], st));
   h->kernel_timed = true;
   return LISEC_OK;
@@ -426,9 +435,23 @@ static int fused_stage(lisec_handle* h, void* grid, cudaStream_t st) {
 
 static int frontend(lisec_handle* h, const void* dev_points, int dtype, const SweepOffsets& so, void* grid,
                     cudaStream_t st) {
+  // The grouping chain (~75 us of latency-bound kernels) leaves HBM idle, and the background does not depend on it for
+  // cells that are simply overwritten later: a side stream fills a prefix of the grid with c_empty meanwhile; the fused
+  // kernel starts after both, writes the prefix's occupied cells over it and streams the rest of the background itself.
+  const long long ngroups = ((long long)so.n * h->geom.cells + 31) >> 5;
+  const int first_group = (int)(h->blind_fraction * (double)ngroups);
+  if (first_group > 0) {
+    LISEC_CUDA(h, cudaEventRecord(h->ev_side[0], st));  // everything queued before this call (the grid's last readers)
+    LISEC_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->ev_side[0], 0));
+    LISEC_CUDA(h, launch_grid_fill(h->cfg.grid_dtype, h->ws.c_empty, grid, (long long)first_group << 5, h->sm_count,
+                                   h->side_stream));
+    LISEC_CUDA(h, cudaEventRecord(h->ev_side[1], h->side_stream));
+    ++h->launches;
+  }
   int rc = do_voxelize(h, dev_points, dtype, so, st);
   if (rc) return rc;
-  return fused_stage(h, grid, st);
+  if (first_group > 0) LISEC_CUDA(h, cudaStreamWaitEvent(st, h->ev_side[1], 0));
+  return fused_stage(h, grid, first_group, st);
 }
 
 int32_t lisec_vfe_scatter_fused(lisec_handle* h, void* grid, void* stream) {
@@ -439,7 +462,7 @@ int32_t lisec_vfe_scatter_fused(lisec_handle* h, void* grid, void* stream) {
   if (!h->voxelized) return fail(h, LISEC_ERR_STATE, "no lisec_voxelize() result on this handle");
   LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
   h->launches = 0;
-  return fused_stage(h, grid, static_cast<cudaStream_t>(stream));
+  return fused_stage(h, grid, 0, static_cast<cudaStream_t>(stream));
 }
 
 int32_t lisec_frontend_forward(lisec_handle* h, const void* points, int32_t dtype, const int64_t* sweep_offsets,

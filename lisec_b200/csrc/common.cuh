@@ -124,7 +124,10 @@ cudaError_t launch_vfe(const VfeSmall& p, const float* wblob, const VfeProblem& 
 // Fused VFE + dense grid: voxel rows go straight to their cells, a 9th warp per CTA streams c_empty into empty cells.
 cudaError_t launch_vfe_to_grid(const VfeSmall& p, const float* wblob,
                                const VfeProblem& prob, const Workspace& w, const Geom& g, int n_sweeps, int grid_dtype,
-                               void* grid, int sm_count, cudaStream_t st, int* launches);
+                               void* grid, int first_group, int sm_count, cudaStream_t st, int* launches);
+// c_empty into cells [0, ncells) regardless of occupancy (the blind prefix, see scatter.cu)
+cudaError_t launch_grid_fill(int grid_dtype, const float* c_empty, void* grid, long long ncells, int sm_count,
+                             cudaStream_t st);
 cudaError_t launch_grid_write(const Geom& g, int n_sweeps, int c3, int grid_dtype, const int* cell_voxel,
                               const float* voxel_feat, const float* c_empty, void* grid, int sm_count,
                               cudaStream_t st, int* launches);

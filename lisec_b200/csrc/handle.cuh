@@ -43,6 +43,12 @@ struct lisec_handle {
   // CUDA events around the fused VFE + grid kernel of the last fused call (bench.py's live roofline figure)
   cudaEvent_t ev_kernel[2] = {nullptr, nullptr};
   bool kernel_timed = false;
+  // the blind background prefix (an experiment, off by default: LISEC_BLIND_FRACTION): a side stream fills the first
+  // `blind_fraction` of the grid while the grouping chain runs. Measured: the chain makes no progress beside the fill
+  // (0.357 -> 0.401 / 0.426 / 0.457 ms per step at 0.2 / 0.33 / 0.45), so nothing is gained.
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_side[2] = {nullptr, nullptr};
+  double blind_fraction = 0.0;
   lisec::VfeTrainState* train = nullptr;  // allocated by the first lisec_vfe_train_forward()
   char err[512];
 };

@@ -94,6 +94,41 @@ __global__ void __launch_bounds__(256) grid_write_bf16_c64(const int* __restrict
 
 }  // namespace
 
+// The background of cells [0, ncells) without looking at the occupancy map: every cell gets c_empty. The front end
+// runs this for a PREFIX of the grid on a side stream while the grouping chain (which leaves HBM idle) still decides
+// which cells are occupied; the fused kernel then writes the occupied cells of that prefix over it and streams the
+// rest of the background itself. 16-byte streaming stores, a warp covers 512 contiguous bytes per instruction.
+template <typename GT>
+__global__ void __launch_bounds__(256) grid_fill_kernel(const float* __restrict__ c_empty, GT* __restrict__ grid,
+                                                        long long ncells) {
+  constexpr int kLanesPerCell = 64 * (int)sizeof(GT) / 16;  // 16 (f32) or 8 (bf16)
+  const int piece = threadIdx.x % kLanesPerCell;
+  float4 val;
+  if (sizeof(GT) == 4) {
+    val = reinterpret_cast<const float4*>(c_empty)[piece];
+  } else {
+    unsigned p[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = pack_bf16x2(c_empty[8 * piece + 2 * i], c_empty[8 * piece + 2 * i + 1]);
+    val = make_float4(__uint_as_float(p[0]), __uint_as_float(p[1]), __uint_as_float(p[2]), __uint_as_float(p[3]));
+  }
+  const long long n16 = ncells * kLanesPerCell;  // 16-byte pieces; piece index i belongs to lane i % kLanesPerCell
+  float4* dst = reinterpret_cast<float4*>(grid);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
+    st_stream(dst + i, val);
+}
+
+cudaError_t launch_grid_fill(int grid_dtype, const float* c_empty, void* grid, long long ncells, int sm_count,
+                             cudaStream_t st) {
+  if (ncells <= 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)sm_count * 4;  // 4 x 256 threads per SM: leaves half an SM's thread slots to the chain
+  if (grid_dtype == LISEC_F32)
+    grid_fill_kernel<float><<<blocks, 256, 0, st>>>(c_empty, static_cast<float*>(grid), ncells);
+  else
+    grid_fill_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(c_empty, static_cast<__nv_bfloat16*>(grid), ncells);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_grid_write(const Geom& g, int n_sweeps, int c3, int grid_dtype, const int* cell_voxel,
                               const float* voxel_feat, const float* c_empty, void* grid, int sm_count,
                               cudaStream_t st, int* launches) {

@@ -154,6 +154,7 @@ struct VfeOutput {
   const float* c_empty;
   long long ncells;
   const int* warm;       // the per-cell count table: pulled back into L2 for the NEXT call's point pass (see the writer)
+  int first_group;       // 32-cell groups below this one already hold the background (grid_fill_kernel, scatter.cu)
 };
 
 // ---- background writer (fused modes, warps 0-2) --------------------------------------------------------------
@@ -179,8 +180,8 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 
 template <typename GT>
 __device__ __forceinline__ void background_writer(const int* __restrict__ cell_voxel, const float* __restrict__ c_empty,
-                                                  GT* __restrict__ grid, long long ncells, unsigned char* sBg,
-                                                  int wtid) {
+                                                  GT* __restrict__ grid, long long ncells, int first_group,
+                                                  unsigned char* sBg, int wtid) {
   constexpr int kWarps = kWriterWarps;
   const int lane = wtid & 31, wwarp = wtid >> 5;
   // fill the tile: kBgCells cells x 64 channels of GT, every cell = c_empty (rounded once for bf16)
@@ -204,7 +205,7 @@ __device__ __forceinline__ void background_writer(const int* __restrict__ cell_v
     }
   };
   int occ[U], nxt[U];
-  int g0 = blockIdx.x * kWarps + wwarp;
+  int g0 = first_group + blockIdx.x * kWarps + wwarp;
   load_occ(g0, occ);
   for (; g0 < ngroups; g0 += U * stride) {
     load_occ(g0 + U * stride, nxt);
@@ -494,11 +495,11 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
 
   if (warp_in_cta < kWriterWarps) {  // ---- WRITER ----
     if (MODE == 1)
-      background_writer(out.cell_voxel, out.c_empty, static_cast<float*>(out.grid), out.ncells, smem + OFF_BG,
-                        (int)threadIdx.x);
+      background_writer(out.cell_voxel, out.c_empty, static_cast<float*>(out.grid), out.ncells, out.first_group,
+                        smem + OFF_BG, (int)threadIdx.x);
     if (MODE == 2)
-      background_writer(out.cell_voxel, out.c_empty, static_cast<__nv_bfloat16*>(out.grid), out.ncells, smem + OFF_BG,
-                        (int)threadIdx.x);
+      background_writer(out.cell_voxel, out.c_empty, static_cast<__nv_bfloat16*>(out.grid), out.ncells,
+                        out.first_group, smem + OFF_BG, (int)threadIdx.x);
     if (MODE != 0 && out.warm) warm_count_table(out.warm, out.ncells, (int)threadIdx.x);
     return;
   }
@@ -812,15 +813,16 @@ static cudaError_t launch_vfe_dtype(const VfeSmall& p, const float* wblob, const
 
 cudaError_t launch_vfe(const VfeSmall& p, const float* wblob, const VfeProblem& prob, float* voxel_feat, int sm_count,
                        cudaStream_t st, int* launches, long long*) {
-  const VfeOutput out{voxel_feat, nullptr, nullptr, nullptr, nullptr, 0, nullptr};
+  const VfeOutput out{voxel_feat, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0};
   ++*launches;
   return launch_vfe_dtype<0>(p, wblob, prob, out, sm_count, st);
 }
 
 cudaError_t launch_vfe_to_grid(const VfeSmall& p, const float* wblob, const VfeProblem& prob, const Workspace& w,
-                               const Geom& g, int n_sweeps, int grid_dtype, void* grid, int sm_count, cudaStream_t st,
-                               int* launches) {
-  const VfeOutput out{nullptr, grid, w.voxel_cell, w.cell_voxel, w.c_empty, (long long)n_sweeps * g.cells, w.count};
+                               const Geom& g, int n_sweeps, int grid_dtype, void* grid, int first_group, int sm_count,
+                               cudaStream_t st, int* launches) {
+  const VfeOutput out{nullptr, grid, w.voxel_cell, w.cell_voxel, w.c_empty, (long long)n_sweeps * g.cells, w.count,
+                      first_group};
   ++*launches;
   return grid_dtype == LISEC_F32 ? launch_vfe_dtype<1>(p, wblob, prob, out, sm_count, st)
                                  : launch_vfe_dtype<2>(p, wblob, prob, out, sm_count, st);
