@@ -185,7 +185,7 @@ __device__ __forceinline__ void background_writer(const int* __restrict__ cell_v
   constexpr int kWarps = kWriterWarps;
   const int lane = wtid & 31, wwarp = wtid >> 5;
   // fill the tile: kBgCells cells x 64 channels of GT, every cell = c_empty (rounded once for bf16)
-  for (int i = wtid; i < kBgCells * 64; i += 32 * kWriterWarps) {
+  for (int i = wtid; i < kBgCells * 64; i += 32 * kWarps) {
     if (sizeof(GT) == 4) reinterpret_cast<float*>(sBg)[i] = c_empty[i & 63];
     else reinterpret_cast<__nv_bfloat16*>(sBg)[i] = __float2bfloat16_rn(c_empty[i & 63]);
   }

@@ -125,8 +125,16 @@ def nonMaxSuppressionFast(boxInfo, probInfo, overlapThresh=0.9, maxBoxes=300):  
     if len(probInfo) == 0:
         return [], []
     dec = _decoder(K.nx // 2, K.ny // 2)
+    # the kernel ranks float32 scores (what the network's heads emit and Predict.predictMain saves). Scores that do not
+    # survive the cast — float64 values between float32 neighbours, NaN — would be ranked differently from the
+    # reference's np.argsort on the original array: refuse them instead of answering with another order.
+    p64 = np.asarray(probInfo, dtype=np.float64)
+    p32 = p64.astype(np.float32)
+    if np.isnan(p64).any() or not np.array_equal(p32.astype(np.float64), p64):
+        raise ValueError("nonMaxSuppressionFast: scores must be finite-or-inf float32-representable values (the "
+                         "network's float32 head outputs); got values a float32 ranking would order differently")
     b = torch.from_numpy(np.ascontiguousarray(boxInfo, dtype=np.float64)).to(dec.device)[None]
-    s = torch.from_numpy(np.ascontiguousarray(probInfo, dtype=np.float32)).to(dec.device)[None]
+    s = torch.from_numpy(np.ascontiguousarray(p32)).to(dec.device)[None]
     picks, n_picks, out_b, _ = dec.nms(b, s, overlapThresh, maxBoxes)
     k = int(n_picks[0])
     pick = picks[0, :k].cpu().numpy()

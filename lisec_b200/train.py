@@ -229,11 +229,16 @@ class BatchNormTrain:
     leaves y and the batch statistics, backward(dy) returns dx and fills dgamma / dbeta. gamma, beta, moving_mean,
     moving_var: float32 device vectors owned by the caller (views into FlatParameters / the model's state)."""
 
-    def __init__(self, x: torch.Tensor, gamma, beta, moving_mean=None, moving_var=None, relu=True, eps=1e-3, momentum=0.99):
+    def __init__(self, x: torch.Tensor, gamma, beta, moving_mean=None, moving_var=None, relu=True, eps=1e-3, momentum=0.99,
+                 unbiased_moving: bool = False):
+        """unbiased_moving: update moving_variance with the Bessel-corrected batch variance var * P / (P - 1), as Keras's
+        FUSED BatchNormalization does (the path rank-4 inputs take; rank-5/6 inputs take the non-fused one with the biased
+        variance in the TensorFlow versions of the reference's era). The normalisation itself always uses the biased one."""
         if x.dtype != torch.bfloat16 or not x.is_cuda:
             raise ValueError("x: cuda bf16, channels last")
         self._lib = N.load()
         self.x, self.relu, self.eps, self.momentum = x, bool(relu), eps, momentum
+        self.unbiased_moving = bool(unbiased_moving)
         self.C = x.shape[-1]
         self.P = x.numel() // self.C
         self.gamma, self.beta, self.moving_mean, self.moving_var = gamma, beta, moving_mean, moving_var
@@ -263,6 +268,10 @@ class BatchNormTrain:
                 self._p(self.workspace), self._stream())
         if st != N.LISEC_OK:
             raise N.LisecError(st, self._lib.lisec_bn_last_error().decode("utf-8", "replace"))
+        if self.unbiased_moving and self.moving_var is not None and self.P > 1:
+            # the kernel added (1 - m) * var; the fused path's var * P / (P - 1) differs by (1 - m) * var / (P - 1)
+            var = self.invstd.double().pow(-2) - self.eps
+            self.moving_var.add_(((1.0 - self.momentum) / (self.P - 1) * var).float())
         return self.y
 
     def backward(self, dy: torch.Tensor) -> torch.Tensor:
@@ -316,7 +325,8 @@ class ConvBnReluTrain:
                                                   C.byref(self.plan))
         if st != N.LISEC_OK:
             raise N.LisecError(st, self._lib.lisec_conv_last_error().decode("utf-8", "replace"))
-        self.bn = BatchNormTrain(self.z, gamma, beta, moving_mean, moving_var, relu=relu)
+        self.bn = BatchNormTrain(self.z, gamma, beta, moving_mean, moving_var, relu=relu,
+                                 unbiased_moving=(k[0] == 1))  # Conv2D stages: rank-4 input, Keras's fused path
         self.wgrad = ConvWgrad(x, self.bn.dx, k, 1, pad, tile=tile, stride_hw=s)  # dz lands in bn.dx
         self.dgrad = None
         if need_dx:

@@ -323,7 +323,7 @@ def test_predictMain_writes_the_reference_files(tmp_path):
         assert np.isfinite(p).all() and np.isfinite(r).all()
     assert np.array_equal(np.load(tmp_path / "sample2_label.npy"), np.load(one / "sample0_label.npy"))
     assert np.array_equal(np.load(tmp_path / "sample2_regress.npy"), np.load(one / "sample0_regress.npy"))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):  # train() exists (tests/test_gpu_train_step.py); without a data source it says so
         compat.train(samples, None, "x.h5")
 
 
