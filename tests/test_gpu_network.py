@@ -199,10 +199,18 @@ def test_network_matches_the_keras_oracle_bf16(fuse_heads):
     torch.cuda.synchronize()
     want_p, want_r = NO.network_forward(grid.float().numpy(), pack)
     assert prob.shape == want_p.shape and reg.shape == want_r.shape
-    # bf16 operands and activations, float32 accumulation: north_star's bf16 bar, 2e-2 of the tensor's scale
-    for got, want in ((prob, want_p), (reg, want_r)):
+    # bf16 operands and activations, float32 accumulation. Three readings of north_star's "within 2e-2 relative (bf16)":
+    #   max |err| / max |ref| (the tensor's scale)  <= 2e-2   met
+    #   relative L2                                  <= 1e-2   met
+    #   element-wise, err / max(|ref|, rms(ref)) — the metric of the VFE tests — measured 2-3e-2: OVER the 2e-2 bar for the
+    #   worst of ~10^5 outputs (22 layers each round their activations to bf16); asserted at 4e-2 and printed, so the
+    #   number is on record rather than hidden behind the looser metric. The float32 mode (1e-5) is the accurate one.
+    for name, got, want in (("prob", prob, want_p), ("regress", reg, want_r)):
         emax, el2 = scale_err(got.cpu().numpy(), want)
+        eelem = rel_err(got.cpu().numpy(), want)
+        print("bf16 network %-8s max/scale %.3e  rel-L2 %.3e  element-wise %.3e" % (name, emax, el2, eelem))
         assert emax <= 2e-2 and el2 <= 1e-2, (emax, el2)
+        assert eelem <= 4e-2, eelem
     net.close()
 
 
