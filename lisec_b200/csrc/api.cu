@@ -54,9 +54,9 @@ int do_voxelize(lisec_handle* h, const void* points, int dtype, const SweepOffse
   }
   h->voxelized = false;
   h->count_dirty = true;  // until the fill pass has been enqueued
-  LISEC_CUDA(h, launch_point_pass(points, dtype, n_total, so, h->geom, h->ws, st, &h->launches));
-  LISEC_CUDA(h, launch_cell_scan(so, h->geom, h->ws, h->scan_blocks_cap, st, &h->launches));
-  LISEC_CUDA(h, launch_fill_and_order(points, dtype, n_total, h->geom, h->rows_per_chunk, h->max_chunks, h->ws, st, &h->launches));
+  LISEC_CUDA(h, launch_point_pass(points, dtype, n_total, so, h->geom, h->ws, h->max_chunks, st, &h->launches));
+  LISEC_CUDA(h, launch_cell_scan(so, h->geom, h->ws, h->scan_blocks_cap, h->rows_per_chunk, st, &h->launches));
+  LISEC_CUDA(h, launch_fill_and_order(points, dtype, n_total, h->geom, h->max_chunks, h->ws, st, &h->launches));
   h->count_dirty = false;
   h->last_points = points;
   h->last_dtype = dtype;

@@ -76,8 +76,8 @@ struct Workspace {
   int* voxel_cell = nullptr;
   int* voxel_start = nullptr;  // CSR offsets into list_*
   int* row_start = nullptr;    // offsets in VFE rows (kept + pad)
-  int* chunk_first = nullptr;  // first voxel of each VFE chunk, [max_chunks + 2]
-  int* chunk_row0 = nullptr;   // first VFE row of each chunk
+  int* chunk_first = nullptr;  // first voxel of each VFE chunk, [max_chunks + 2] (atomicMin marks of scan_down)
+  int* chunk_row0 = nullptr;   // (unused)
   int* chunk_ntiles = nullptr; // tiles packed into each chunk
   int* tile_first = nullptr;   // [max_chunks][kChunkSlots] first voxel of each tile of a chunk, then the end sentinel
   // per VFE row, [max_points + max_voxels]: what the VFE kernel needs to start a tile with one coalesced read
@@ -100,11 +100,11 @@ constexpr int kTraceCtas = 256, kTraceSlots = 16;
 
 // ---- launchers (each returns the cudaError_t of its launches) --------------------------------------------
 cudaError_t launch_point_pass(const void* pts, int pts_dtype, long long n_total, const SweepOffsets& so,
-                              const Geom& g, Workspace& w, cudaStream_t st, int* launches);
+                              const Geom& g, Workspace& w, long long chunk_cap, cudaStream_t st, int* launches);
 cudaError_t launch_cell_scan(const SweepOffsets& so, const Geom& g, Workspace& w, int scan_blocks_cap,
-                             cudaStream_t st, int* launches);
-cudaError_t launch_fill_and_order(const void* pts, int pts_dtype, long long n_total, const Geom& g, int rows_per_chunk,
-                                  long long max_chunks, Workspace& w, cudaStream_t st, int* launches);
+                             int rows_per_chunk, cudaStream_t st, int* launches);
+cudaError_t launch_fill_and_order(const void* pts, int pts_dtype, long long n_total, const Geom& g, long long max_chunks,
+                                  Workspace& w, cudaStream_t st, int* launches);
 cudaError_t launch_export(const void* pts, int pts_dtype, const SweepOffsets& so, const Geom& g,
                           const Workspace& w, long long max_voxels, int32_t* coords, int32_t* counts,
                           int32_t* point_idx, float* features, float* dense, cudaStream_t st, int* launches);
@@ -147,7 +147,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 // Debug timeline (LISEC_TRACE=1): every kernel stamps the moment its pdl_wait() returned — i.e. the moment its
 // predecessor completed — into rows 200+k of the trace buffer ([0] = earliest CTA, [1] = latest stamp). Kernel ids:
-enum { TL_POINT = 0, TL_SCAN_REDUCE, TL_SCAN_DOWN, TL_FILL, TL_ORDER, TL_ROWFEAT, TL_VFE, TL_VFE_END, TL_COUNT };
+enum { TL_POINT = 0, TL_SCAN_REDUCE, TL_SCAN_DOWN, TL_FILL, TL_ORDER, TL_WRITER_END, TL_VFE, TL_VFE_END, TL_COUNT };
 constexpr int kTimelineRow0 = 200;
 __device__ __forceinline__ void timeline_stamp(unsigned long long* trace, int k) {
   if (trace && threadIdx.x == 0) {

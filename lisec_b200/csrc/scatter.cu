@@ -12,6 +12,8 @@
 // store instruction.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace lisec {
@@ -121,7 +123,12 @@ __global__ void __launch_bounds__(256) grid_fill_kernel(const float* __restrict_
 cudaError_t launch_grid_fill(int grid_dtype, const float* c_empty, void* grid, long long ncells, int sm_count,
                              cudaStream_t st) {
   if (ncells <= 0) return cudaSuccess;
-  const unsigned blocks = (unsigned)sm_count * 4;  // 4 x 256 threads per SM: leaves half an SM's thread slots to the chain
+  static const int per_sm = [] {  // experiment switch: fill CTAs per SM (default 4 x 256 threads: half an SM's thread slots)
+    const char* e = getenv("LISEC_FILL_CTAS_PER_SM");
+    const int v = e ? atoi(e) : 4;
+    return v >= 1 && v <= 8 ? v : 4;
+  }();
+  const unsigned blocks = (unsigned)sm_count * per_sm;
   if (grid_dtype == LISEC_F32)
     grid_fill_kernel<float><<<blocks, 256, 0, st>>>(c_empty, static_cast<float*>(grid), ncells);
   else

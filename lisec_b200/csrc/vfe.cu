@@ -500,6 +500,14 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
     if (MODE == 2)
       background_writer(out.cell_voxel, out.c_empty, static_cast<__nv_bfloat16*>(out.grid), out.ncells,
                         out.first_group, smem + OFF_BG, (int)threadIdx.x);
+    if (MODE != 0 && threadIdx.x == 0) {  // debug timeline: when this CTA's background was done
+      unsigned long long* tr = g_trace;
+      if (tr) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        atomicMax(tr + (size_t)(kTimelineRow0 + TL_WRITER_END) * kTraceSlots + 1, now);
+      }
+    }
     if (MODE != 0 && out.warm) warm_count_table(out.warm, out.ncells, (int)threadIdx.x);
     return;
   }

@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const int* __
 // grand totals, writes them and the sentinels.
 __global__ void __launch_bounds__(kScanThreads) scan_down_kernel(const int* __restrict__ count, long long ncells,
                                                                  int T, int cells_per_sweep, int nblocks, int n_sweeps,
+                                                                 int rows_per_chunk, int* __restrict__ chunk_first,
                                                                  const int* __restrict__ block_sums,
                                                                  long long* __restrict__ totals,
                                                                  int* __restrict__ cell_voxel,
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_down_kernel(const int* __re
     totals[TOT_VOXELS] = carry.v;
     totals[TOT_ENTRIES] = carry.e;
     totals[TOT_ROWS] = carry.r;
-    totals[TOT_CHUNKS] = 0;  // set by order_pass when there is at least one voxel
+    totals[TOT_CHUNKS] = carry.r > 0 ? (carry.r - 1) / rows_per_chunk + 1 : 0;
     voxel_start[carry.v] = carry.e;
     row_start[carry.v] = carry.r;
     sweep_voxel_start[n_sweeps] = carry.v;
@@ -288,6 +289,12 @@ __global__ void __launch_bounds__(kScanThreads) scan_down_kernel(const int* __re
         voxel_cell[run.v] = cell;
         voxel_start[run.v] = run.e;
         row_start[run.v] = run.r;
+        // VFE chunks: chunk(v) = row_start[v] / rows_per_chunk. A voxel has at most T rows < rows_per_chunk, so the first
+        // voxel of chunk t starts less than T rows into it: only those voxels (~7 %) compete for chunk_first[t]
+        // (preset to a huge value). The chunk count comes from the row total (last block): it may name one trailing
+        // chunk that no voxel starts in, which the tile plan leaves with zero tiles.
+        const int t = run.r / rows_per_chunk;
+        if (run.r - t * rows_per_chunk < T) atomicMin(chunk_first + t, run.v);
         run = tri_add(run, tri_of_count(c[i], T));
       }
     }
@@ -308,14 +315,71 @@ __global__ void __launch_bounds__(kScanThreads) scan_down_kernel(const int* __re
 }
 
 // ---- K3: fill pass ----------------------------------------------------------------------------------------
+// Tile plan (blocks past the fill blocks of fill_pass_kernel): one warp per chunk packs the chunk's voxels greedily
+// into tiles of at most kVfeThreads rows (a tile = whole voxels): the next tile ends at the last voxel whose rows still
+// fit. A voxel has >= 2 rows, so a tile has <= kVfeThreads / 2 voxels: two candidates per lane cover the search. Tiles
+// ~93 % full instead of the 73 % a fixed row stride with its worst-case reserve (T - 1 rows) gives. The chunk's row
+// offsets arrive in one round trip; the walk stays in shared memory. It needs only what scan_down left (row_start, the
+// chunk marks), so it rides in the fill pass's launch: as a kernel of its own at the end of the chain it cost 13 us per
+// step (launch, drain, and the VFE kernel's start-up behind it).
+constexpr int kPlanVox = kVfeChunkRows / 2 + 4;  // row offsets of a chunk: <= kVfeChunkRows / 2 voxels + the end entry
+__device__ __forceinline__ void plan_chunk_tiles(long long c, int lane, int* rs, const int* __restrict__ chunk_first,
+                                                 const int* __restrict__ row_start,
+                                                 const long long* __restrict__ totals, int* __restrict__ tile_first,
+                                                 int* __restrict__ tile_row0, int* __restrict__ chunk_ntiles) {
+  // (everything read here was written by scan_down under programmatic dependent launch: ld.global.cg, never through L1
+  // — a plain load here returned lines of the PREVIOUS call's tables: tools/check_tables.py)
+  const long long n_chunks = __ldcg(totals + TOT_CHUNKS);
+  if (c >= n_chunks) return;
+  const int V = (int)__ldcg(totals + TOT_VOXELS);
+  const int v0 = min(__ldcg(chunk_first + c), V);  // (a trailing chunk no voxel starts in keeps the preset: empty)
+  const int v_end = c + 1 < n_chunks ? min(__ldcg(chunk_first + c + 1), V) : V;
+  const int nv = v_end - v0;
+  for (int i = lane; i <= nv; i += 32) rs[i] = __ldcg(row_start + v0 + i);
+  __syncwarp();
+  int b = 0, j = 0;
+  int* tf = tile_first + c * kChunkSlots;
+  int* tr = tile_row0 + c * kChunkSlots;
+  while (b < nv && j < kChunkSlots - 1) {
+    const int base = rs[b];
+    const int e1 = b + 1 + lane, e2 = e1 + 32;
+    const bool ok1 = e1 <= nv && rs[e1] - base <= kVfeThreads;
+    const bool ok2 = e2 <= nv && rs[e2] - base <= kVfeThreads;
+    const int fit = __popc(__ballot_sync(0xffffffffu, ok1)) + __popc(__ballot_sync(0xffffffffu, ok2));  // monotone: a count
+    if (lane == 0) {
+      tf[j] = v0 + b;
+      tr[j] = base;
+    }
+    b += fit;  // fit >= 1: one voxel always fits
+    ++j;
+  }
+  if (lane == 0) {
+    tf[j] = v_end;
+    tr[j] = rs[nv];
+    chunk_ntiles[c] = j;
+  }
+}
+
 __global__ void __launch_bounds__(256) fill_pass_kernel(const int* __restrict__ cell_of_point, long long n_total,
                                                         const int* __restrict__ cell_voxel,
                                                         const int* __restrict__ voxel_start,
                                                         int* __restrict__ count, int* __restrict__ list_unsorted,
-                                                        int* __restrict__ entry_voxel) {
+                                                        int* __restrict__ entry_voxel, unsigned fill_blocks,
+                                                        const int* __restrict__ chunk_first,
+                                                        const int* __restrict__ row_start,
+                                                        const long long* __restrict__ totals,
+                                                        int* __restrict__ tile_first, int* __restrict__ tile_row0,
+                                                        int* __restrict__ chunk_ntiles) {
+  __shared__ int s_rs[8][kPlanVox];
   pdl_launch_dependents();
   pdl_wait();
   timeline_stamp(g_trace, TL_FILL);
+  if (blockIdx.x >= fill_blocks) {  // the tile plan's blocks: 8 chunks each
+    const int wib = threadIdx.x >> 5;
+    plan_chunk_tiles((long long)(blockIdx.x - fill_blocks) * 8 + wib, lane_id(), s_rs[wib], chunk_first, row_start, totals,
+                     tile_first, tile_row0, chunk_ntiles);
+    return;
+  }
   const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long p0 = grp * 4;
   int cell[4] = {-1, -1, -1, -1};
@@ -368,32 +432,14 @@ __global__ void __launch_bounds__(256) order_pass_kernel(const PT* __restrict__ 
                                                          const int* __restrict__ entry_voxel,
                                                          const int* __restrict__ voxel_start,
                                                          const int* __restrict__ row_start, int T,
-                                                         int rows_per_chunk, long long* __restrict__ totals,
+                                                         const long long* __restrict__ totals,
                                                          int* __restrict__ list_sorted,
-                                                         int* __restrict__ chunk_first, int* __restrict__ chunk_row0,
                                                          int* __restrict__ row_voxel, PT* __restrict__ row_xyz) {
   pdl_launch_dependents();
   pdl_wait();
   timeline_stamp(g_trace, TL_ORDER);
-  const long long n_entries = __ldcg(totals + TOT_ENTRIES);  // (predecessor-written tables: ld.global.cg, see tile_plan_kernel)
-  const long long n_voxels = __ldcg(totals + TOT_VOXELS);
+  const long long n_entries = __ldcg(totals + TOT_ENTRIES);  // (predecessor-written tables: ld.global.cg, never through L1 — DESIGN.md §4)
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < n_voxels) {
-    // chunk(v) = row_start[v] / rows_per_chunk; a voxel has at most T rows < rows_per_chunk, so consecutive voxels
-    // differ by at most one chunk and every chunk index up to the last one has a first voxel.
-    const int rse = __ldcg(row_start + e);
-    const int t = rse / rows_per_chunk;
-    const int tprev = e > 0 ? __ldcg(row_start + e - 1) / rows_per_chunk : -1;
-    if (t != tprev) {
-      chunk_first[t] = (int)e;
-      chunk_row0[t] = rse;
-    }
-    if (e == n_voxels - 1) {
-      chunk_first[t + 1] = (int)n_voxels;
-      chunk_row0[t + 1] = __ldcg(row_start + n_voxels);
-      totals[TOT_CHUNKS] = t + 1;
-    }
-  }
   if (e >= n_entries) return;
   const int v = __ldcg(entry_voxel + e);
   const int s = __ldcg(voxel_start + v);
@@ -425,47 +471,6 @@ __global__ void __launch_bounds__(256) order_pass_kernel(const PT* __restrict__ 
   }
 }
 
-// ---- K5: tile plan ----------------------------------------------------------------------------------------
-// One warp per chunk packs the chunk's voxels greedily into tiles of at most kVfeThreads rows (a tile = whole voxels):
-// the next tile ends at the last voxel whose rows still fit. A voxel has >= 2 rows, so a tile has <= kVfeThreads / 2
-// voxels: two candidates per lane cover the search. Tiles of ~126 of 128 rows instead of the ~94 a fixed row stride
-// with its worst-case reserve would give.
-__global__ void __launch_bounds__(128) tile_plan_kernel(const int* __restrict__ chunk_first,
-                                                        const int* __restrict__ row_start,
-                                                        const long long* __restrict__ totals,
-                                                        int* __restrict__ tile_first, int* __restrict__ tile_row0,
-                                                        int* __restrict__ chunk_ntiles, int tile_rows) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int lane = lane_id();
-  const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  // (everything this kernel reads was written by its predecessors under programmatic dependent launch: ld.global.cg,
-  // never through L1 — a plain load here returned lines of the PREVIOUS call's tables: tools/check_tables.py)
-  if (c >= __ldcg(totals + TOT_CHUNKS)) return;
-  const int v_end = __ldcg(chunk_first + c + 1);
-  int b = __ldcg(chunk_first + c), j = 0;
-  int* tf = tile_first + c * kChunkSlots;
-  int* tr = tile_row0 + c * kChunkSlots;
-  while (b < v_end && j < kChunkSlots - 1) {
-    const int base = __ldcg(row_start + b);
-    const int e1 = b + 1 + lane, e2 = e1 + 32;
-    const bool ok1 = e1 <= v_end && __ldcg(row_start + e1) - base <= tile_rows;
-    const bool ok2 = e2 <= v_end && __ldcg(row_start + e2) - base <= tile_rows;
-    const int fit = __popc(__ballot_sync(0xffffffffu, ok1)) + __popc(__ballot_sync(0xffffffffu, ok2));  // monotone: a count
-    if (lane == 0) {
-      tf[j] = b;
-      tr[j] = base;
-    }
-    b += fit;  // fit >= 1: one voxel always fits
-    ++j;
-  }
-  if (lane == 0) {
-    tf[j] = v_end;
-    tr[j] = __ldcg(row_start + v_end);
-    chunk_ntiles[c] = j;
-  }
-}
-
 }  // namespace
 
 // ---- launchers --------------------------------------------------------------------------------------------
@@ -474,10 +479,13 @@ cudaError_t set_trace_voxelize(unsigned long long* trace) {
 }
 
 cudaError_t launch_point_pass(const void* pts, int pts_dtype, long long n_total, const SweepOffsets& so,
-                              const Geom& g, Workspace& w, cudaStream_t st, int* launches) {
+                              const Geom& g, Workspace& w, long long chunk_cap, cudaStream_t st, int* launches) {
   cudaError_t err = cudaMemsetAsync(w.totals, 0, sizeof(long long) * TOT_COUNT, st);
   if (err != cudaSuccess) return err;
   if (n_total == 0) return cudaSuccess;
+  // chunk_first is found by atomicMin (scan_down): preset to 0x7f7f7f7f, above any voxel index
+  err = cudaMemsetAsync(w.chunk_first, 0x7f, sizeof(int) * (size_t)(chunk_cap + 2), st);
+  if (err != cudaSuccess) return err;
   const long long groups = (n_total + 3) / 4;
   const unsigned blocks = (unsigned)((groups + 255) / 256);
   auto* tot = reinterpret_cast<unsigned long long*>(w.totals);
@@ -492,7 +500,7 @@ cudaError_t launch_point_pass(const void* pts, int pts_dtype, long long n_total,
 }
 
 cudaError_t launch_cell_scan(const SweepOffsets& so, const Geom& g, Workspace& w, int scan_blocks_cap,
-                             cudaStream_t st, int* launches) {
+                             int rows_per_chunk, cudaStream_t st, int* launches) {
   const long long ncells = (long long)so.n * g.cells;
   const int nblocks = (int)((ncells + kScanTile - 1) / kScanTile);
   if (nblocks > scan_blocks_cap) return cudaErrorInvalidValue;
@@ -500,44 +508,37 @@ cudaError_t launch_cell_scan(const SweepOffsets& so, const Geom& g, Workspace& w
                                nblocks, w.block_sums);
   if (err == cudaSuccess)
     err = launch_pdl(scan_down_kernel, nblocks, kScanThreads, 0, st, (const int*)w.count, ncells, g.T, g.cells, nblocks,
-                     so.n, (const int*)w.block_sums, w.totals, w.cell_voxel, w.voxel_cell, w.voxel_start, w.row_start,
-                     w.sweep_voxel_start);
+                     so.n, rows_per_chunk, w.chunk_first, (const int*)w.block_sums, w.totals, w.cell_voxel, w.voxel_cell,
+                     w.voxel_start, w.row_start, w.sweep_voxel_start);
   *launches += 2;
   return err;
 }
 
-cudaError_t launch_fill_and_order(const void* pts, int pts_dtype, long long n_total, const Geom& g, int rows_per_chunk,
-                                  long long max_chunks, Workspace& w, cudaStream_t st, int* launches) {
+cudaError_t launch_fill_and_order(const void* pts, int pts_dtype, long long n_total, const Geom& g, long long max_chunks,
+                                  Workspace& w, cudaStream_t st, int* launches) {
   if (n_total == 0) return cudaSuccess;
   const long long groups = (n_total + 3) / 4;
-  cudaError_t err = launch_pdl(fill_pass_kernel, (unsigned)((groups + 255) / 256), 256, 0, st,
-                               (const int*)w.cell_of_point, n_total, (const int*)w.cell_voxel,
-                               (const int*)w.voxel_start, w.count, w.list_unsorted, w.entry_voxel);
+  const unsigned fill_blocks = (unsigned)((groups + 255) / 256);
+  const unsigned plan_blocks = (unsigned)((max_chunks + 7) / 8);  // the tile plan rides in the same launch (8 chunks per block)
+  cudaError_t err = launch_pdl(fill_pass_kernel, fill_blocks + plan_blocks, 256, 0, st, (const int*)w.cell_of_point, n_total,
+                               (const int*)w.cell_voxel, (const int*)w.voxel_start, w.count, w.list_unsorted,
+                               w.entry_voxel, fill_blocks, (const int*)w.chunk_first, (const int*)w.row_start,
+                               (const long long*)w.totals, w.tile_first, w.tile_row0, w.chunk_ntiles);
   // entries <= points; threads beyond the device-side totals exit
   if (err == cudaSuccess) {
     const unsigned blocks = (unsigned)((n_total + 255) / 256);
     if (pts_dtype == LISEC_F32)
       err = launch_pdl(order_pass_kernel<float>, blocks, 256, 0, st, static_cast<const float*>(pts),
                        (const int*)w.list_unsorted, (const int*)w.entry_voxel, (const int*)w.voxel_start,
-                       (const int*)w.row_start, g.T, rows_per_chunk, w.totals, w.list_sorted, w.chunk_first, w.chunk_row0,
-                       w.row_voxel, static_cast<float*>(w.row_xyz));
+                       (const int*)w.row_start, g.T, (const long long*)w.totals, w.list_sorted, w.row_voxel,
+                       static_cast<float*>(w.row_xyz));
     else
       err = launch_pdl(order_pass_kernel<double>, blocks, 256, 0, st, static_cast<const double*>(pts),
                        (const int*)w.list_unsorted, (const int*)w.entry_voxel, (const int*)w.voxel_start,
-                       (const int*)w.row_start, g.T, rows_per_chunk, w.totals, w.list_sorted, w.chunk_first, w.chunk_row0,
-                       w.row_voxel, static_cast<double*>(w.row_xyz));
+                       (const int*)w.row_start, g.T, (const long long*)w.totals, w.list_sorted, w.row_voxel,
+                       static_cast<double*>(w.row_xyz));
   }
-  // chunks -> tiles (threads past the device-side chunk count exit)
-  static const int tile_rows = [] {  // experiment switch: rows per tile (<= kVfeThreads; needs >= T)
-    const char* e = getenv("LISEC_TILE_ROWS");
-    const int v = e ? atoi(e) : kVfeThreads;
-    return v >= 64 && v <= kVfeThreads ? v : kVfeThreads;
-  }();
-  if (err == cudaSuccess)
-    err = launch_pdl(tile_plan_kernel, (unsigned)((max_chunks * 32 + 127) / 128), 128, 0, st, (const int*)w.chunk_first,
-                     (const int*)w.row_start, (const long long*)w.totals, w.tile_first, w.tile_row0, w.chunk_ntiles,
-                     tile_rows);
-  *launches += 3;
+  *launches += 2;
   return err;
 }
 

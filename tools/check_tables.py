@@ -27,9 +27,7 @@ def check(fe, tag):
     assert (np.diff(rs) >= 2).all() or V == 0
     want = np.repeat(np.arange(V), np.diff(rs))
     bad_rv = int((rv != want).sum())
-    n_chunks = (rows + 0) // 478 + 1 if V else 0
-    # chunk count = chunk of the last voxel + 1
-    n_chunks = int(rs[V - 1] // 478 + 1) if V else 0
+    n_chunks = (rows - 1) // 478 + 1 if V else 0  # (may name one trailing chunk no voxel starts in: zero tiles)
     nt = table(fe, 4, max(n_chunks, 1))[:n_chunks]
     tf = table(fe, 2, max(n_chunks, 1) * SLOTS).reshape(-1, SLOTS)[:n_chunks]
     tr = table(fe, 3, max(n_chunks, 1) * SLOTS).reshape(-1, SLOTS)[:n_chunks]
@@ -37,7 +35,7 @@ def check(fe, tag):
     prev_end = 0
     for c in range(n_chunks):
         n = int(nt[c])
-        if not (1 <= n <= SLOTS - 1) or tf[c, 0] != prev_end:
+        if not (0 <= n <= SLOTS - 1) or tf[c, 0] != prev_end or (n == 0 and c != n_chunks - 1):
             bad += 1
             continue
         for j in range(n + 1):

@@ -13,7 +13,7 @@ os.environ["LISEC_TRACE"] = "1"
 from lisec_b200 import Frontend, synth  # noqa: E402
 from lisec_b200.weights import synthetic_vfe_pack  # noqa: E402
 
-NAMES = ["point_pass", "scan_reduce", "scan_down", "fill_pass", "order_pass", "row_features", "vfe_kernel<1>", "end"]
+NAMES = ["point_pass", "scan_reduce", "scan_down", "fill_pass", "order_pass", "(unused)", "vfe_kernel<1>", "end"]
 batches = [synth.sweep_batch(8, 100_000, seed0=8 * b) for b in range(3)]
 fe = Frontend(device=0, max_points=800_000, max_sweeps=8)
 fe.set_weights(synthetic_vfe_pack(0))
@@ -45,9 +45,13 @@ for i in range(n):
     lo, hi = read()
     start = lo.copy()
     start[7] = hi[7]
+    start[5] = hi[5]  # the writers' end (latest CTA)
     acc += start - start[0]
 acc /= n
 print("in-step timeline, us after the point pass started (mean of %d steps):" % n)
-for k in range(7):
+for k in (0, 1, 2, 3):
     print("  %-14s starts %7.1f   runs %6.1f" % (NAMES[k], acc[k] / 1e3, (acc[k + 1] - acc[k]) / 1e3))
-print("  end            %7.1f" % (acc[7] / 1e3))
+print("  %-14s starts %7.1f   runs %6.1f" % (NAMES[4], acc[4] / 1e3, (acc[6] - acc[4]) / 1e3))
+print("  %-14s starts %7.1f" % (NAMES[6], acc[6] / 1e3))
+print("  background writers done (last CTA) %7.1f" % (acc[5] / 1e3))
+print("  VFE pipeline done (last CTA)       %7.1f" % (acc[7] / 1e3))
