@@ -582,7 +582,21 @@ def run_native(args):
         g1.record()
         barrier()
         ms_full_e2e = max_over_ranks(g0.elapsed_time(g1)) / args.steps
-        full = {"ms_per_step": ms_full, "network_ms": ms_net, "flops_per_step": net.flops,
+        # the first Conv3D gathering from the sparse front-end output (no dense grid), same batches
+        sparse_ms = None
+        try:
+            net_s = DenseNetwork(synthetic_network_pack(0), batch=FS, device=local)
+            net_s.attach_frontend(fe16)
+
+            def step_sparse(i):
+                net_s.forward_sparse(dev_full[i % n_fb], offsets_f)
+
+            sparse_ms = timed(lambda: step_sparse(0), n_k)
+            net_s.close()
+            del net_s
+        except Exception as exc:
+            sparse_ms = "%s: %s" % (type(exc).__name__, exc)
+        full = {"ms_per_step": ms_full, "network_ms": ms_net, "flops_per_step": net.flops, "sparse_ms": sparse_ms,
                 "ms_e2e": ms_full_e2e, "d2h": out_host[0].numel() * 4,
                 "launches_per_step": fe16.last_launch_count + net.launches_per_forward,
                 "net_launches": net.launches_per_forward}
@@ -726,6 +740,11 @@ def run_native(args):
                 "sweeps_per_step_per_gpu": FULL_SWEEPS,
                 "value": FULL_SWEEPS * world / (full["ms_per_step"] * 1e-3), "unit": "sweeps/s",
                 "ms_per_step": full["ms_per_step"], "gpu_launches_per_step": full["launches_per_step"],
+                "sparse_first_conv": {"ms_per_step": full["sparse_ms"],
+                                      "note": "the same step with the first Conv3D gathering its input boxes from the occupancy "
+                                              "map + voxel rows + c_empty (lisec_conv_plan_set_gather): no dense grid written or "
+                                              "read, outputs bit-identical; not the default while it is slower (its box "
+                                              "producer is bound by dependent L2 round trips)"},
                 "e2e": {"value": FULL_SWEEPS * world / (full["ms_e2e"] * 1e-3), "unit": "sweeps/s",
                         "ms_per_step": full["ms_e2e"], "h2d_bytes_per_step": FULL_SWEEPS * POINTS_PER_SWEEP * 12,
                         "d2h_bytes_per_step": full["d2h"]},

@@ -218,6 +218,8 @@ int32_t lisec_vfe_train_backward(lisec_handle* h, const lisec_vfe_train_params* 
  * inverse standard deviation. Synchronous. */
 int32_t lisec_vfe_train_read(lisec_handle* h, int32_t layer, float* out_rows, int64_t n_rows, float* mean, float* inv_std);
 
+/* Device pointers of the handle's occupancy map (of the last lisec_voxelize()) and c_empty, and its voxel capacity. */
+int32_t lisec_workspace_pointers(lisec_handle* h, const int32_t** cell_voxel, const float** c_empty, int64_t* max_voxels);
 int32_t lisec_debug_trace(lisec_handle* h, int64_t* out, int64_t n);
 /* Debug / test aid: copy one grouping table to the host (synchronous). which: 0 row_start, 1 row_voxel, 2 tile_first,
    3 tile_row0, 4 chunk_ntiles, 5 chunk_first, 6 voxel_cell. */
@@ -275,6 +277,12 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* desc, const void* in, cons
                                const float* shift, void* out, lisec_conv_plan** plan);
 /* [async] One kernel launch on `stream`. */
 int32_t lisec_conv_plan_run(lisec_conv_plan* plan, void* stream);
+/* SURVEY §8f rank 1 (model_training.py:235-236): the first Conv3D reads the front end's SPARSE output — occupancy map
+ * (cell -> voxel row or -1, lisec_workspace_pointers), float32 voxel rows [V,64] (lisec_vfe_forward), c_empty — and builds
+ * its input boxes in shared memory itself; the dense voxel grid is never written or read. For halo plans (group_kh = 2)
+ * with in_c = 64; the plan's `in` pointer is then unused. Bit-identical to the same plan on the materialised bf16 grid. */
+int32_t lisec_conv_plan_set_gather(lisec_conv_plan* plan, const int32_t* cell_voxel, const float* voxel_feat,
+                                   const float* c_empty);
 /* [async] x[n] float32 -> hi[n], lo[n]: the operand planes a float32 plan reads (n a multiple of 4). */
 int32_t lisec_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
 /* [async] The tail of createModel without the 768-channel concat tensor: Conv2DTranspose (no activation, model_training.py:

@@ -143,6 +143,8 @@ SIGNATURES = {
     "lisec_last_launch_count": (C.c_int32, [_H]),
     "lisec_conv_plan_create": (C.c_int32, [C.POINTER(lisec_conv_desc), _VP, _VP, _VP, _VP, _VP, C.POINTER(_H)]),
     "lisec_conv_plan_run": (C.c_int32, [_H, _VP]),
+    "lisec_conv_plan_set_gather": (C.c_int32, [_H, _VP, _VP, _VP]),
+    "lisec_workspace_pointers": (C.c_int32, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "lisec_conv_plan_output_shape": (C.c_int32, [_H, _I32P]),
     "lisec_heads_combine": (C.c_int32, [_VP, _VP, C.c_int32, _VP, C.c_int32, _VP, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_int32, _VP]),

@@ -549,6 +549,16 @@ int32_t lisec_debug_table(lisec_handle* h, int32_t which, int32_t* out, int64_t 
   return LISEC_OK;
 }
 
+// Device pointers of what a consumer needs to read the front end's SPARSE output in place (the first Conv3D's gather
+// plans, lisec_conv_plan_set_gather): the occupancy map of the last lisec_voxelize() and c_empty. Stable for the handle's life.
+int32_t lisec_workspace_pointers(lisec_handle* h, const int32_t** cell_voxel, const float** c_empty, int64_t* max_voxels) {
+  if (!h) return LISEC_ERR_BAD_ARG;
+  if (cell_voxel) *cell_voxel = h->ws.cell_voxel;
+  if (c_empty) *c_empty = h->ws.c_empty;
+  if (max_voxels) *max_voxels = h->max_voxels;
+  return LISEC_OK;
+}
+
 int32_t lisec_voxel_counts_async(lisec_handle* h, void* pinned_out, int64_t pinned_bytes, void* stream) {
   if (!h) return LISEC_ERR_BAD_ARG;
   if (!pinned_out) return fail(h, LISEC_ERR_BAD_ARG, "pinned_out is NULL");

@@ -71,6 +71,13 @@ struct ConvParams {
   const float* scale;
   const float* shift;
   void* out;
+  // gather source (halo plans of the FIRST Conv3D, lisec_conv_plan_set_gather): the input boxes are built in shared
+  // memory from the front end's sparse output — occupancy map, voxel rows, c_empty — instead of being read from a dense
+  // grid: the 82 MB-per-sweep bf16 grid is never written or read (model_training.py:235-236)
+  int gather, in_d, in_h, in_w;
+  const int* g_cell_voxel;    // [batch * in_d * in_h * in_w] voxel row of the cell or -1
+  const float* g_voxel_feat;  // [voxels][64] float32 VFE rows
+  const float* g_c_empty;     // [64]
 };
 
 // ---- PTX helpers not in umma.cuh ---------------------------------------------------------------------------
@@ -415,7 +422,18 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 // loaded once per (kd, 64-channel block); M-tile m (8 wide, 16 high, two side by side) under tap (kh, kw) starts at box
 // row kh * 18 + kw + 8 m and its 8-row groups are one box line (18 rows = 2304 bytes) apart. Input traffic per output
 // drops 2.7x against the kh-halo plans; the weights stream through their own ring, three kw taps per slot.
-__global__ void __launch_bounds__(kConvThreads, 1)
+// GATHER variant (first Conv3D behind the VFE stack): two more warps (11, 12) build the input boxes themselves. A box is
+// 18 x 18 positions x 64 bf16 channels = 324 rows of 128 bytes in the layout the TMA would have delivered (row r =
+// h * 18 + w, 16-byte chunks XOR-swizzled with bits 7..9 of the row's absolute shared-memory address). A lane takes rows
+// lane, lane + 32, ...: cell -> voxel through the occupancy map, then the voxel's float32 row rounded to bf16 (the same
+// one rounding the dense bf16 grid holds), or c_empty, or zeros outside the grid (ZeroPadding3D, :192). 92 % of the cells
+// are empty, so a box costs ~26 row gathers and 2592 16-byte shared-memory stores. Gather plans have four box slots; box n
+// goes to warp n & 3 and slot n & 3 (a box is two dependent L2 round trips: four in flight keep up with the MMAs); the
+// weights keep coming through warp 0's TMA.
+constexpr int kGatherWarps = 4;  // one per input-box slot
+constexpr int kConvGatherThreads = kConvThreads + 32 * kGatherWarps;
+template <bool GATHER>
+__global__ void __launch_bounds__(GATHER ? kConvGatherThreads : kConvThreads, 1)
     conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ ConvParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -433,8 +451,13 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   auto bar_acc_full = [&](int a) { return bar0 + 8u * (24 + a); };
   auto bar_acc_empty = [&](int a) { return bar0 + 8u * (26 + a); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bar0 - base) + 8 * 28);
+  uint4* s_cempty = reinterpret_cast<uint4*>(smem + (bar0 - base) + 8 * 28 + 16);  // GATHER: c_empty as 64 bf16
+  if (GATHER && warp == 11 && lane < 8) {
+    const float* c = P.g_c_empty + 8 * lane;
+    s_cempty[lane] = make_uint4(pack2(c[0], c[1]), pack2(c[2], c[3]), pack2(c[4], c[5]), pack2(c[6], c[7]));
+  }
   if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&map_a);
+    if (!GATHER) prefetch_tensormap(&map_a);
     prefetch_tensormap(&map_b);
     for (int s = 0; s < P.a_slots; ++s) {
       umma::mbar_init(bar_a_full(s), 1);
@@ -466,11 +489,13 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         const TileCoord t = decode_tile(P, tile);
         for (int kd = 0; kd < P.kd_n; ++kd)
           for (int cb = 0; cb < P.c_blocks; ++cb) {
-            umma::mbar_wait(bar_a_empty(as), aph ^ 1u);
-            mbar_arrive_expect_tx(bar_a_full(as), P.a_box_bytes);
-            tma_load_5d(base + (uint32_t)as * P.a_slot_bytes, &map_a, bar_a_full(as), 64 * cb, t.ow0 + P.t1[0],
-                        t.oh0 + P.t2[0], t.od * P.stride_d + kd + P.t3[0], t.b);
-            if (++as == P.a_slots) { as = 0; aph ^= 1u; }
+            if (!GATHER) {
+              umma::mbar_wait(bar_a_empty(as), aph ^ 1u);
+              mbar_arrive_expect_tx(bar_a_full(as), P.a_box_bytes);
+              tma_load_5d(base + (uint32_t)as * P.a_slot_bytes, &map_a, bar_a_full(as), 64 * cb, t.ow0 + P.t1[0],
+                          t.oh0 + P.t2[0], t.od * P.stride_d + kd + P.t3[0], t.b);
+              if (++as == P.a_slots) { as = 0; aph ^= 1u; }
+            }
             for (int kh = 0; kh < 3; ++kh) {
               umma::mbar_wait(bar_b_empty(bs), bph ^ 1u);
               mbar_arrive_expect_tx(bar_b_full(bs), b_slot_bytes);
@@ -531,6 +556,62 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         }
         umma::mma_commit(bar_acc_full(acc));
         if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+      }
+    }
+  } else if (GATHER && warp >= 11) {
+    const int g = warp - 11;  // boxes g, g + 4, ... of this CTA's sequence, always into slot g
+    const int rows = P.box_w * (P.bh + 2);
+    unsigned char* slot = smem + (size_t)g * P.a_slot_bytes;
+    const uint32_t slot_addr = base + (uint32_t)g * P.a_slot_bytes;
+    long long n = 0;     // box ordinal of this CTA
+    uint32_t use = 0;    // how often this warp has filled its slot
+    for (long long tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(P, tile);
+      for (int kd = 0; kd < P.kd_n; ++kd, ++n) {  // (c_blocks == 1 for gather plans)
+        if ((n & (kGatherWarps - 1)) != g) continue;
+        const int w0 = t.ow0 + P.t1[0], h0 = t.oh0 + P.t2[0], dz = t.od * P.stride_d + kd + P.t3[0];
+        const bool d_ok = dz >= 0 && dz < P.in_d;
+        const long long plane = ((long long)t.b * P.in_d + dz) * P.in_h;
+        // the occupancy words of the lane's rows first (independent loads), before waiting for the slot
+        int vox[11];
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+          const int r = lane + 32 * k;
+          const int hh = r / P.box_w, ww = r - hh * P.box_w;
+          const int h = h0 + hh, w = w0 + ww;
+          const bool ok = r < rows && d_ok && h >= 0 && h < P.in_h && w >= 0 && w < P.in_w;
+          vox[k] = ok ? __ldcg(P.g_cell_voxel + (plane + h) * P.in_w + w) : -2;  // -1: empty cell, -2: outside the grid
+        }
+        umma::mbar_wait(bar_a_empty(g), (use & 1u) ^ 1u);
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+          const int r = lane + 32 * k;
+          if (r >= rows) break;
+          uint4 ch[8];
+          if (vox[k] >= 0) {
+            const float4* src = reinterpret_cast<const float4*>(P.g_voxel_feat + (size_t)vox[k] * 64);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 a = __ldcg(src + 2 * c), b = __ldcg(src + 2 * c + 1);
+              ch[c] = make_uint4(pack2(a.x, a.y), pack2(a.z, a.w), pack2(b.x, b.y), pack2(b.z, b.w));
+            }
+          } else if (vox[k] == -1) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) ch[c] = s_cempty[c];
+          } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) ch[c] = make_uint4(0u, 0u, 0u, 0u);
+          }
+          const uint32_t row_addr = slot_addr + (uint32_t)r * 128u;
+          const uint32_t sw = (row_addr >> 7) & 7u;
+          unsigned char* row_ptr = slot + (size_t)r * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(row_ptr + (((uint32_t)c ^ sw) << 4)) = ch[c];
+        }
+        umma::fence_async_smem();  // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(bar_a_full(g));
+        ++use;
       }
     }
   } else {
@@ -908,6 +989,13 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
   p.scale = scale;
   p.shift = shift;
   p.out = out;
+  p.gather = 0;
+  p.in_d = d->in_d;
+  p.in_h = d->in_h;
+  p.in_w = d->in_w;
+  p.g_cell_voxel = nullptr;
+  p.g_voxel_feat = nullptr;
+  p.g_c_empty = nullptr;
   // hi / lo output planes: [2][batch, out_d, out_h*shuffle, out_w*shuffle, out_pitch]
   p.out_lo_off = d->out_split ? (long long)d->batch * OD * ((long long)OH * shuffle) * ((long long)OW * shuffle) * d->out_pitch : 0;
   int box_h = p.bh * mt + group - 1, box_w = p.bw;
@@ -929,7 +1017,7 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
     p.a_bytes = p.a_box_bytes;
     p.stage_bytes = 0;
     p.stages = 0;
-    pl->smem = (int)(2u * p.a_slot_bytes + (uint32_t)b_slots * b_slot) + 8 * 28 + 16;
+    pl->smem = (int)(2u * p.a_slot_bytes + (uint32_t)b_slots * b_slot) + 8 * 28 + 16 + 128;  // (+ c_empty for gather plans)
   } else {
     p.a_bytes = (uint32_t)(p.bw * box_h) * 128u;
     p.stage_bytes = (p.a_bytes + (uint32_t)(group * N) * 128u) * (f32 ? 2u : 1u);
@@ -990,7 +1078,9 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_igemm_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    e = cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   if (e != cudaSuccess) {
     delete pl;
     return conv_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
@@ -1001,9 +1091,33 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
   return LISEC_OK;
 }
 
+int32_t lisec_conv_plan_set_gather(lisec_conv_plan* pl, const int32_t* cell_voxel, const float* voxel_feat,
+                                   const float* c_empty) {
+  if (!pl || !cell_voxel || !voxel_feat || !c_empty) return conv_fail(LISEC_ERR_BAD_ARG, "null argument");
+  if (!pl->p.halo || pl->p.c_blocks != 1 || pl->p.box_w * (pl->p.bh + 2) > 11 * 32)
+    return conv_fail(LISEC_ERR_BAD_CONFIG, "gather source: a halo plan with 64 input channels and a box of <= 352 positions");
+  // four box slots (one per gather warp) and what is left for the weight ring
+  const uint32_t b_slot = 3u * (uint32_t)pl->p.N * 128u;
+  const uint32_t room = 220u * 1024u - (uint32_t)kGatherWarps * pl->p.a_slot_bytes;
+  int b_slots = (int)(room / b_slot);
+  if (b_slots > 8) b_slots = 8;
+  if (b_slots < 2) return conv_fail(LISEC_ERR_BAD_CONFIG, "gather source: no room for two weight slots beside four box slots");
+  pl->p.a_slots = kGatherWarps;
+  pl->p.b_slots = b_slots;
+  pl->smem = (int)((uint32_t)kGatherWarps * pl->p.a_slot_bytes + (uint32_t)b_slots * b_slot) + 8 * 28 + 16 + 128;
+  pl->p.gather = 1;
+  pl->p.g_cell_voxel = cell_voxel;
+  pl->p.g_voxel_feat = voxel_feat;
+  pl->p.g_c_empty = c_empty;
+  return LISEC_OK;
+}
+
 int32_t lisec_conv_plan_run(lisec_conv_plan* pl, void* stream) {
   if (!pl) return conv_fail(LISEC_ERR_BAD_ARG, "null plan");
-  cudaError_t e = pl->p.halo ? launch_pdl(conv_halo_kernel, pl->grid, kConvThreads, (size_t)pl->smem,
+  cudaError_t e = pl->p.halo && pl->p.gather
+                      ? launch_pdl(conv_halo_kernel<true>, pl->grid, kConvGatherThreads, (size_t)pl->smem,
+                                   static_cast<cudaStream_t>(stream), pl->map_a, pl->map_b, pl->p)
+                  : pl->p.halo ? launch_pdl(conv_halo_kernel<false>, pl->grid, kConvThreads, (size_t)pl->smem,
                                           static_cast<cudaStream_t>(stream), pl->map_a, pl->map_b, pl->p)
                   : pl->p.f32 ? launch_pdl(conv_igemm_f32_kernel, pl->grid, kConvF32Threads, (size_t)pl->smem,
                                          static_cast<cudaStream_t>(stream), pl->map_a, pl->map_b, pl->p)

@@ -301,6 +301,29 @@ class DenseNetwork:
         if st != _native.LISEC_OK:
             raise _native.LisecError(st, self._lib.lisec_conv_last_error().decode())
 
+    def attach_frontend(self, fe) -> None:
+        """the first Conv3D gathers its input straight from `fe`'s sparse output (occupancy map of the
+        last voxelize, the float32 voxel rows in self.voxel_feat, c_empty): the dense grid is never written or read. Then
+        forward_sparse(points, offsets) replaces fe.forward(..., out=net.grid) + net.forward()."""
+        if self.f32:
+            raise ValueError("the gather source is a bf16 plan")
+        cv, ce, mv = C.c_void_p(), C.c_void_p(), C.c_int64()
+        fe._check(self._lib.lisec_workspace_pointers(fe._h, C.byref(cv), C.byref(ce), C.byref(mv)))
+        self.voxel_feat = torch.empty((int(mv.value), 64), dtype=torch.float32, device=self.device)
+        st = self._lib.lisec_conv_plan_set_gather(self.layers[0].plan, cv, C.c_void_p(self.voxel_feat.data_ptr()), ce)
+        if st != _native.LISEC_OK:
+            raise _native.LisecError(st, self._lib.lisec_conv_last_error().decode())
+        self._fe = fe
+
+    def forward_sparse(self, points, sweep_offsets) -> Tuple[torch.Tensor, torch.Tensor]:
+        """voxelize + VFE rows (no grid) + the network, the first Conv3D reading the sparse rows (attach_frontend)."""
+        fe = self._fe
+        fe.voxelize(points, sweep_offsets)
+        fe.vfe(out=self.voxel_feat)
+        self.run_layers()
+        self.combine_heads()
+        return self.heads[:, 0, :, :, :2], self.heads[:, 0, :, :, 2:]
+
     @property
     def launches_per_forward(self) -> int:
         return len(self.layers) + (1 if self.fuse_heads else 0) + (1 if self.f32 else 0)

@@ -358,3 +358,35 @@ def test_forward_to_host_pipelines_the_copy_and_keeps_the_results():
     with pytest.raises(ValueError):
         net.forward_to_host(torch.empty(4))
     net.close()
+
+
+def test_first_conv3d_gathers_from_the_sparse_front_end_output():
+    """SURVEY §8f rank 1 (model_training.py:235-236): the first Conv3D builds its input boxes from the occupancy map, the
+    float32 voxel rows and c_empty — no dense grid — and the network's outputs are BIT-IDENTICAL to the path through the
+    materialised bf16 grid (same one rounding of every feature, same MMA order)."""
+    from lisec_b200 import Frontend, synth
+    from lisec_b200.network import DenseNetwork
+    from lisec_b200.weights import synthetic_network_pack, synthetic_vfe_pack
+
+    B = 2
+    sweeps = [synth.lyft_like_sweep(30_000, seed=21), synth.lyft_like_sweep(25_000, seed=22)]
+    pts = np.concatenate(sweeps)
+    off = [0, len(sweeps[0]), len(pts)]
+    fe = Frontend(device=0, max_points=len(pts), max_sweeps=B, grid_dtype="bf16")
+    fe.set_weights(synthetic_vfe_pack(1))
+    pack = synthetic_network_pack(1)
+    dense = DenseNetwork(pack, batch=B)
+    fe.forward(pts, off, out=dense.grid)
+    want_p, want_r = (t.clone() for t in dense.forward())
+    sparse = DenseNetwork(pack, batch=B)
+    sparse.attach_frontend(fe)
+    sparse.grid.fill_(float("nan"))  # the grid is not an input any more
+    got_p, got_r = sparse.forward_sparse(pts, off)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got_p).all() and torch.isfinite(got_r).all()
+    assert torch.equal(got_p, want_p) and torch.equal(got_r, want_r)
+    # and the first block's activations themselves
+    assert torch.equal(sparse.layers[0].dst, dense.layers[0].dst)
+    dense.close()
+    sparse.close()
+    fe.close()
