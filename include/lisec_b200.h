@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define LISEC_ABI_VERSION 1
+#define LISEC_ABI_VERSION 2
 #define LISEC_MAX_SWEEPS 64 /* sweeps per call (sweep_offsets travels as a kernel parameter) */
 
 typedef enum lisec_status {
@@ -59,12 +59,16 @@ typedef struct lisec_config {
   int32_t max_voxel_x;               /* maxVoxelX = nx/2               (100)                               */
   int32_t max_voxel_y;               /* maxVoxelY = ny/2               (200)                               */
   int32_t max_voxel_z;               /* maxVoxelZ = nz                 (8)                                 */
-  int32_t c1, c2, c3;                /* VFE-1 / VFE-2 / FCN output widths (model_training.py:231-233: 16, 32, 64) */
+  int32_t c1, c2, c3;                /* VFE-1 / VFE-2 / FCN output widths: (16, 32, 64) = model_training.py:231-233 as it
+                                        stands, or (16, 64, 128) = the graph model.png shows             */
   int32_t grid_dtype;                /* lisec_dtype of the dense grid: LISEC_F32 or LISEC_BF16             */
   int32_t max_sweeps;                /* capacity: sweeps per call, <= LISEC_MAX_SWEEPS                     */
   int64_t max_points;                /* capacity: points per call, summed over its sweeps                  */
   int32_t device;                    /* CUDA device ordinal                                                */
-  int32_t reserved;
+  int32_t fcn_post_dense;            /* 0: addFCN = Dense -> BN -> ReLU (model_training.py:169-174 as it stands);
+                                        1: Dense -> BN -> Dense(units, relu, no bias) — the line commented out at :172,
+                                        the graph model.png shows. (16, 32, 64) with 0 runs the tensor-core kernel
+                                        (vfe.cu); every other supported combination the float32 kernel (vfe_generic.cu). */
 } lisec_config;
 
 /*
@@ -74,6 +78,9 @@ typedef struct lisec_config {
  *   dense_2  kernel (2*c2, c3) + batch_normalization_2 {...}[c3]       rows 0..c2-1 multiply the POOLED half
  * Kernels are row-major (C_in, C_out), bias-free (model_training.py:184). BatchNormalization uses
  * bn_epsilon (Keras default 1e-3, model_training.py:171). All pointers are HOST pointers to float32.
+ * With lisec_config.fcn_post_dense = 1 every FCN has a second Dense behind its BatchNormalization (Keras then names the
+ * six kernels dense, dense_1 | dense_2, dense_3 | dense_4, dense_5): post_dense_kernel[l] is (c_l, c_l), row-major,
+ * bias-free, followed by the ReLU; it is ignored (may be NULL) with fcn_post_dense = 0.
  */
 typedef struct lisec_vfe_weights {
   const float* dense_kernel[3];
@@ -83,6 +90,7 @@ typedef struct lisec_vfe_weights {
   const float* bn_var[3];
   float bn_epsilon;
   int32_t reserved;
+  const float* post_dense_kernel[3];
 } lisec_vfe_weights;
 
 typedef struct lisec_handle lisec_handle;

@@ -13,9 +13,10 @@ LIB_PATH = os.environ.get("LISEC_LIB_PATH") or os.path.join(os.path.dirname(os.p
 
 LISEC_OK = 0
 LISEC_ERR_BAD_CONFIG = -2
+LISEC_ERR_UNSUPPORTED = -6
 LISEC_F32, LISEC_F64, LISEC_BF16 = 0, 1, 2
 LISEC_MAX_SWEEPS = 64
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 STATUS_NAMES = {
     0: "LISEC_OK",
@@ -50,7 +51,7 @@ class lisec_config(C.Structure):
         ("max_sweeps", C.c_int32),
         ("max_points", C.c_int64),
         ("device", C.c_int32),
-        ("reserved", C.c_int32),
+        ("fcn_post_dense", C.c_int32),
     ]
 
 
@@ -66,6 +67,7 @@ class lisec_vfe_weights(C.Structure):
         ("bn_var", _FP * 3),
         ("bn_epsilon", C.c_float),
         ("reserved", C.c_int32),
+        ("post_dense_kernel", _FP * 3),
     ]
 
 

@@ -34,14 +34,15 @@ import torch
 
 from . import constants as K
 from .frontend import Frontend
-from .weights import load_npz, synthetic_model_pack
+from .weights import CURRENT, Architecture, detect_architecture, load_npz, synthetic_model_pack
 
 _FRONTENDS: dict = {}
 
 
-def _frontend(cfg_key, n_points: int, n_sweeps: int, device: int = 0, grid_dtype: str = "f32") -> Frontend:
-    """One Frontend per (geometry, device, grid dtype); re-created with doubled capacity when a call outgrows it."""
-    key = (cfg_key, device, grid_dtype)
+def _frontend(cfg_key, n_points: int, n_sweeps: int, device: int = 0, grid_dtype: str = "f32",
+              arch: Architecture = CURRENT) -> Frontend:
+    """One Frontend per (geometry, device, grid dtype, graph); re-created with doubled capacity when a call outgrows it."""
+    key = (cfg_key, device, grid_dtype, arch)
     fe = _FRONTENDS.get(key)
     need_pts, need_sw = max(n_points, 1), max(n_sweeps, 1)
     if fe is None or fe.cfg.max_points < need_pts or fe.cfg.max_sweeps < need_sw:
@@ -52,7 +53,8 @@ def _frontend(cfg_key, n_points: int, n_sweeps: int, device: int = 0, grid_dtype
         if fe is not None:
             fe.close()
         fe = Frontend(device=device, max_points=cap_pts, max_sweeps=cap_sw, voxel_size=(xs, ys, zs),
-                      sample_size=T, max_voxel=(mx, my, mz), grid_dtype=grid_dtype)
+                      sample_size=T, max_voxel=(mx, my, mz), grid_dtype=grid_dtype, widths=arch.widths,
+                      post_dense=arch.post_dense)
         if weights is not None:
             fe.set_weights(weights)
             fe._pack = weights
@@ -177,12 +179,15 @@ class MaxPoolingVFELayer:  # model_training.py:44-61
 
 class VoxelNetFrontEnd:
     """createModel (model_training.py:222-257) with its weights: the first 23 Keras layers (VFE stack, :229-235) as the
-    fused front-end kernels, the rest (:236-256) as tensor-core convolution plans."""
+    fused front-end kernels, the rest (:236-256) as tensor-core convolution plans. `arch` names the graph the weights
+    belong to (lisec_b200.weights.Architecture; None: read it off the kernels' shapes, as load_model() reads it off the
+    .h5's own model_config): createModel() as it stands, or the older graph model.png shows."""
 
-    def __init__(self, nx, ny, nz, maxPoints, pack: dict):
+    def __init__(self, nx, ny, nz, maxPoints, pack: dict, arch: Optional[Architecture] = None):
         self.grid = (nz, nx, ny)
         self.maxPoints = maxPoints
         self.pack = pack
+        self.arch = arch if arch is not None else detect_architecture(pack)
         self._nets: dict = {}
 
     def _run_frontend(self, x: DenseVoxelInput, device: int, grid_dtype: str, out=None) -> torch.Tensor:
@@ -198,14 +203,14 @@ class VoxelNetFrontEnd:
         dt = np.float32 if dts == {np.dtype("float32")} else np.float64
         pts = np.concatenate([s._points.astype(dt, copy=False) for s in x.sweeps])
         off = np.cumsum([0] + [len(s._points) for s in x.sweeps]).astype(np.int64)
-        fe = _frontend(cfg, len(pts), len(x.sweeps), device, grid_dtype)
+        fe = _frontend(cfg, len(pts), len(x.sweeps), device, grid_dtype, self.arch)
         if getattr(fe, "_pack", None) is not self.pack:
             fe.set_weights(self.pack)
             fe._pack = self.pack
         return fe.forward_host(pts, off, out=out)
 
     def predict_voxel_grid(self, x: DenseVoxelInput, device: int = 0) -> torch.Tensor:
-        """The float32 [N, nz, nx, ny, 64] tensor the reference's first Conv3D consumes (:235-236), on the GPU."""
+        """The float32 [N, nz, nx, ny, C3] tensor the reference's first Conv3D consumes (:235-236), on the GPU."""
         return self._run_frontend(x, device, "f32")
 
     def predict(self, x: DenseVoxelInput, device: int = 0, dtype: str = "bf16") -> list:
@@ -220,7 +225,8 @@ class VoxelNetFrontEnd:
         net = self._nets.get(key)
         if net is None:
             nz, nx, ny = self.grid
-            net = self._nets[key] = DenseNetwork(self.pack, batch=n, nx=nx, ny=ny, nz=nz, device=device, dtype=dtype)
+            net = self._nets[key] = DenseNetwork(self.pack, batch=n, nx=nx, ny=ny, nz=nz, device=device, dtype=dtype,
+                                                 arch=self.arch)
         self._run_frontend(x, device, "f32" if dtype == "f32" else "bf16", out=net.grid)
         prob, reg = net.forward()
         return [prob.contiguous().cpu().numpy(), reg.contiguous().cpu().numpy()]
@@ -329,14 +335,21 @@ def train_with_model(samples, level5Data, model_path, save_path, labels_dir="lab
                      dataDir=None, combine_lidar_data=None, device=0, labels=None):
     """model_training.train_with_model (model_training.py:305-346): as train(), starting from load_model(model_path)."""
     model = load_model(model_path)
+    if model.arch != CURRENT:
+        raise ValueError("train_with_model: %s holds the graph %s; the training step is built for the graph train() creates "
+                         "(createModel, model_training.py:222-257: %s) — inference (predictMain) runs either"
+                         % (model_path, model.arch, CURRENT))
     return _fit(model.pack, samples, level5Data, save_path, labels_dir, steps_per_epoch, batch_size, dataDir,
                 combine_lidar_data, device, labels)
 
 
-def createModel(nx=K.nx, ny=K.ny, nz=K.nz, maxPoints=K.maxPoints, weights: Optional[dict] = None, seed: int = 0):
+def createModel(nx=K.nx, ny=K.ny, nz=K.nz, maxPoints=K.maxPoints, weights: Optional[dict] = None, seed: int = 0,
+                arch: Optional[Architecture] = None):
     """model_training.py:222. Keras would random-initialise; `weights` (Keras-named arrays) or a seeded synthetic
-    pack stands in."""
-    return VoxelNetFrontEnd(nx, ny, nz, maxPoints, weights if weights is not None else synthetic_model_pack(seed))
+    pack stands in. arch: None = the graph createModel() builds today (or, with `weights`, the one they were saved from)."""
+    if weights is None:
+        weights = synthetic_model_pack(seed, arch or CURRENT)
+    return VoxelNetFrontEnd(nx, ny, nz, maxPoints, weights, arch)
 
 
 def load_model(path: str, custom_objects: Optional[dict] = None, nx=K.nx, ny=K.ny, nz=K.nz, maxPoints=K.maxPoints):

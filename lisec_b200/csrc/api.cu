@@ -70,8 +70,54 @@ VfeProblem vfe_problem(const lisec_handle* h) {
                     h->ws.row_start,  h->ws.totals + TOT_CHUNKS, h->last_dtype};
 }
 
+VfeProblem empty_problem(const lisec_handle* h) {
+  const int* d = h->ws.empty_desc;
+  return VfeProblem{d, d + 2, d + 1, d + 8, d + 16, d + 4, reinterpret_cast<const long long*>(d + 12), LISEC_F64};
+}
+
+// vfe_generic.cu's parameter block: the Keras kernels as they are, BatchNormalization folded to y = z * a + b in float32
+// (Keras inference, model_training.py:171), the FCNs' second Dense where the graph has one. c_empty = the same kernel on
+// the one-voxel problem that holds nothing but a pad row.
+int set_generic_weights(lisec_handle* h, const lisec_vfe_weights* w, cudaStream_t st) {
+  const lisec_config& c = h->cfg;
+  const bool post = c.fcn_post_dense != 0;
+  const int C[3] = {c.c1, c.c2, c.c3};
+  float a[3][128], b[3][128];
+  GenericVfeWeights g;
+  for (int l = 0; l < 3; ++l) {
+    if (post && !w->post_dense_kernel[l])
+      return fail(h, LISEC_ERR_BAD_ARG, "fcn_post_dense = 1 but post_dense_kernel[%d] is NULL", l);
+    for (int j = 0; j < C[l]; ++j) {
+      a[l][j] = (1.0f / std::sqrt(w->bn_var[l][j] + w->bn_epsilon)) * w->bn_gamma[l][j];
+      b[l][j] = w->bn_beta[l][j] - w->bn_mean[l][j] * a[l][j];
+    }
+    g.dense[l] = w->dense_kernel[l];
+    g.a[l] = a[l];
+    g.b[l] = b[l];
+    g.post[l] = post ? w->post_dense_kernel[l] : nullptr;
+  }
+  const size_t n = vfe_generic_param_floats(c.c1, c.c2, c.c3, post);
+  float* host = new (std::nothrow) float[n];
+  if (!host) return fail(h, LISEC_ERR_CUDA, "out of host memory");
+  vfe_generic_pack(c.c1, c.c2, c.c3, post, g, host);
+  cudaError_t e = cudaMemcpyAsync(h->generic_params, host, sizeof(float) * n, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  delete[] host;
+  LISEC_CUDA(h, e);
+  h->weights_set = true;
+  LISEC_CUDA(h, launch_vfe_generic(c.c1, c.c2, c.c3, post, h->generic_params, empty_problem(h), h->ws.c_empty,
+                                   h->sm_count, st, &h->launches));
+  LISEC_CUDA(h, cudaStreamSynchronize(st));
+  return LISEC_OK;
+}
+
 int do_vfe(lisec_handle* h, float* voxel_feat, cudaStream_t st) {
   const VfeProblem prob = vfe_problem(h);
+  if (h->generic) {
+    LISEC_CUDA(h, launch_vfe_generic(h->cfg.c1, h->cfg.c2, h->cfg.c3, h->cfg.fcn_post_dense != 0, h->generic_params, prob,
+                                     voxel_feat, h->sm_count, st, &h->launches));
+    return LISEC_OK;
+  }
   LISEC_CUDA(h, launch_vfe(h->params, h->ws.vfe_w, prob, voxel_feat, h->sm_count, st, &h->launches,
                            reinterpret_cast<long long*>(h->ws.trace)));
   return LISEC_OK;
@@ -109,10 +155,14 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
     return fail(h, LISEC_ERR_BAD_CONFIG, "max_voxel_{x,y,z} must be >= 1");
   if (c.sample_size < 2 || c.sample_size > 64)
     return fail(h, LISEC_ERR_BAD_CONFIG, "sample_size = %d, supported range is 2..64", c.sample_size);
-  if (c.c1 != 16 || c.c2 != 32 || c.c3 != 64)
+  if (!vfe_generic_supports(c.c1, c.c2, c.c3))
     return fail(h, LISEC_ERR_UNSUPPORTED,
-                "VFE widths (%d,%d,%d): only the current createModel widths (16,32,64) are built", c.c1, c.c2,
-                c.c3);
+                "VFE widths (%d,%d,%d): built are (16,32,64) = createModel as it stands and (16,64,128) = model.png's",
+                c.c1, c.c2, c.c3);
+  if (c.fcn_post_dense != 0 && c.fcn_post_dense != 1)
+    return fail(h, LISEC_ERR_BAD_CONFIG, "fcn_post_dense = %d, need 0 or 1", c.fcn_post_dense);
+  h->generic = !(c.c1 == 16 && c.c2 == 32 && c.c3 == 64 && c.fcn_post_dense == 0);
+  if (const char* e = getenv("LISEC_GENERIC_VFE"); e && e[0] == '1') h->generic = true;  // cross-check switch
   if (c.grid_dtype != LISEC_F32 && c.grid_dtype != LISEC_BF16)
     return fail(h, LISEC_ERR_BAD_CONFIG, "grid_dtype must be LISEC_F32 or LISEC_BF16");
   if (c.max_sweeps < 1 || c.max_sweeps > LISEC_MAX_SWEEPS)
@@ -180,6 +230,8 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
   LISEC_CUDA(h, dev_alloc(h, &w.voxel_feat, V * (size_t)c.c3));
   LISEC_CUDA(h, dev_alloc(h, &w.c_empty, (size_t)c.c3));
   LISEC_CUDA(h, dev_alloc(h, &w.vfe_w, (size_t)kVfeBlobFloats));
+  if (h->generic)
+    LISEC_CUDA(h, dev_alloc(h, &h->generic_params, vfe_generic_param_floats(c.c1, c.c2, c.c3, c.fcn_post_dense != 0)));
   LISEC_CUDA(h, dev_alloc(h, reinterpret_cast<unsigned char**>(&w.staging), P * 3 * sizeof(double)));
   LISEC_CUDA(h, dev_alloc(h, reinterpret_cast<unsigned char**>(&h->staging2), P * 3 * sizeof(double)));
   LISEC_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -225,6 +277,7 @@ void lisec_destroy(lisec_handle* h) {
   if (h->sm_count > 0) cudaSetDevice(h->cfg.device);
   free_workspace(h->ws);
   if (h->train) free_vfe_train_state(h->train);
+  if (h->generic_params) cudaFree(h->generic_params);
   if (h->staging2) cudaFree(h->staging2);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
@@ -255,6 +308,7 @@ int32_t lisec_set_vfe_weights(lisec_handle* h, const lisec_vfe_weights* w, void*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   LISEC_CUDA(h, cudaSetDevice(h->cfg.device));
   h->launches = 0;
+  if (h->generic) return set_generic_weights(h, w, st);
   VfeSmall& p = h->params;
   const float* k0 = w->dense_kernel[0];
   for (int k = 0; k < 6; ++k)
@@ -322,9 +376,7 @@ int32_t lisec_set_vfe_weights(lisec_handle* h, const lisec_vfe_weights* w, void*
   h->weights_set = true;
   // c_empty: the same kernel, run on one voxel that holds nothing but the pad row
   LISEC_CUDA(h, cudaMemcpyAsync(h->ws.vfe_w, blob, sizeof(float) * kVfeBlobFloats, cudaMemcpyHostToDevice, st));
-  const int* d = h->ws.empty_desc;
-  const VfeProblem empty{d, d + 2, d + 1, d + 8, d + 16, d + 4, reinterpret_cast<const long long*>(d + 12), LISEC_F64};
-  LISEC_CUDA(h, launch_vfe(p, h->ws.vfe_w, empty, h->ws.c_empty, h->sm_count, st, &h->launches));
+  LISEC_CUDA(h, launch_vfe(p, h->ws.vfe_w, empty_problem(h), h->ws.c_empty, h->sm_count, st, &h->launches));
   LISEC_CUDA(h, cudaStreamSynchronize(st));
   return LISEC_OK;
 }
@@ -424,6 +476,16 @@ int32_t lisec_scatter_dense(lisec_handle* h, const float* voxel_feat, void* grid
 
 static int fused_stage(lisec_handle* h, void* grid, int first_group, cudaStream_t st) {
   const VfeProblem prob = vfe_problem(h);
+  if (h->generic) {  // two kernels: the float32 VFE into the handle's voxel rows, then every grid cell written once
+    LISEC_CUDA(h, cudaEventRecord(h->ev_kernel[0], st));
+    int rc = do_vfe(h, h->ws.voxel_feat, st);
+    if (rc) return rc;
+    LISEC_CUDA(h, launch_grid_write(h->geom, h->last_so.n, h->cfg.c3, h->cfg.grid_dtype, h->ws.cell_voxel,
+                                    h->ws.voxel_feat, h->ws.c_empty, grid, h->sm_count, st, &h->launches));
+    LISEC_CUDA(h, cudaEventRecord(h->ev_kernel[1], st));
+    h->kernel_timed = true;
+    return LISEC_OK;
+  }
   // one kernel: VFE (FP32 pipe + tensor core), voxel rows and the c_empty background written to the grid concurrently
   LISEC_CUDA(h, cudaEventRecord(h->ev_kernel[0], st));
   LISEC_CUDA(h, launch_vfe_to_grid(h->params, h->ws.vfe_w, prob, h->ws, h->geom, h->last_so.n, h->cfg.grid_dtype, grid,
@@ -439,7 +501,7 @@ static int frontend(lisec_handle* h, const void* dev_points, int dtype, const Sw
   // cells that are simply overwritten later: a side stream fills a prefix of the grid with c_empty meanwhile; the fused
   // kernel starts after both, writes the prefix's occupied cells over it and streams the rest of the background itself.
   const long long ngroups = ((long long)so.n * h->geom.cells + 31) >> 5;
-  const int first_group = (int)(h->blind_fraction * (double)ngroups);
+  const int first_group = h->generic ? 0 : (int)(h->blind_fraction * (double)ngroups);
   if (first_group > 0) {
     LISEC_CUDA(h, cudaEventRecord(h->ev_side[0], st));  // everything queued before this call (the grid's last readers)
     LISEC_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->ev_side[0], 0));

@@ -132,6 +132,20 @@ cudaError_t launch_grid_write(const Geom& g, int n_sweeps, int c3, int grid_dtyp
                               const float* voxel_feat, const float* c_empty, void* grid, int sm_count,
                               cudaStream_t st, int* launches);
 
+// The generic VFE kernel (vfe_generic.cu): any supported (c1, c2, c3) and either FCN variant, float32 FMAs. `post` = the
+// FCN's second Dense (model_training.py:172, commented-out variant); a / b = BatchNormalization folded to y = z * a + b.
+struct GenericVfeWeights {
+  const float* dense[3];
+  const float* a[3];
+  const float* b[3];
+  const float* post[3];
+};
+bool vfe_generic_supports(int c1, int c2, int c3);
+size_t vfe_generic_param_floats(int c1, int c2, int c3, bool post);
+void vfe_generic_pack(int c1, int c2, int c3, bool post, const GenericVfeWeights& w, float* out);
+cudaError_t launch_vfe_generic(int c1, int c2, int c3, bool post, const float* params, const VfeProblem& prob,
+                               float* voxel_feat, int sm_count, cudaStream_t st, int* launches);
+
 int vfe_rows_per_chunk(int T);
 cudaError_t set_trace_voxelize(unsigned long long* trace);
 cudaError_t set_trace_vfe(unsigned long long* trace);

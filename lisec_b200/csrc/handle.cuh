@@ -50,6 +50,9 @@ struct lisec_handle {
   cudaEvent_t ev_side[2] = {nullptr, nullptr};
   double blind_fraction = 0.0;
   lisec::VfeTrainState* train = nullptr;  // allocated by the first lisec_vfe_train_forward()
+  // the float32 VFE kernel for every graph but the current createModel's (vfe_generic.cu); also under LISEC_GENERIC_VFE=1
+  bool generic = false;
+  float* generic_params = nullptr;  // device parameter block (GenericLayout)
   char err[512];
 };
 

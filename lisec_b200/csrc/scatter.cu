@@ -7,9 +7,9 @@
 // unmasked network's output for an all-zero voxel is a non-zero constant). No memset + scatter:
 // that would write the occupied rows twice.
 //
-// HBM-bound: 256 B (f32) / 128 B (bf16) stored per cell against 4 B of occupancy map read. A warp takes 32
+// HBM-bound: C3 x 4 B (f32) / C3 x 2 B (bf16) stored per cell against 4 B of occupancy map read. A warp takes 32
 // consecutive cells: one coalesced 128 B map load, then 16-byte streaming stores, 512 contiguous bytes per
-// store instruction.
+// store instruction. C3 = 64 (the current createModel) or 128 (the graph model.png shows).
 #include <cuda_bf16.h>
 
 #include <cstdlib>
@@ -23,73 +23,45 @@ namespace {
 __device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream(uint4* p, uint4 v) { __stcs(p, v); }
 
-// f32 grid, C3 = 64: 16 lanes x float4 cover one cell; a warp stores 2 cells per instruction.
-__global__ void __launch_bounds__(256) grid_write_f32_c64(const int* __restrict__ cell_voxel,
-                                                          const float* __restrict__ voxel_feat,
-                                                          const float* __restrict__ c_empty,
-                                                          float* __restrict__ grid, long long ncells) {
-  const int lane = threadIdx.x & 31;
-  const int sub = lane >> 4;   // which of the 2 cells of a store
-  const int chunk = lane & 15; // which float4 of the 64-channel row
-  const float4 bg = reinterpret_cast<const float4*>(c_empty)[chunk];
-  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const long long ngroups = (ncells + 31) >> 5;
-  for (long long grp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < ngroups; grp += warps) {
-    const long long base = grp << 5;
-    const int my = (base + lane < ncells) ? __ldg(cell_voxel + base + lane) : -1;
-    float4 val[16];
-    int vox[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      vox[i] = __shfl_sync(0xffffffffu, my, 2 * i + sub);
-      val[i] = bg;
-    }
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (vox[i] >= 0) val[i] = __ldg(reinterpret_cast<const float4*>(voxel_feat + (size_t)vox[i] * 64) + chunk);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const long long cell = base + 2 * i + sub;
-      if (cell < ncells) st_stream(reinterpret_cast<float4*>(grid + cell * 64) + chunk, val[i]);
-    }
-  }
-}
-
 __device__ __forceinline__ unsigned pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<unsigned*>(&h);
 }
 
-// bf16 grid, C3 = 64: 8 lanes x 16 B cover one cell; a warp stores 4 cells per instruction. Values are rounded
-// once from the float32 result (c_empty included).
-__global__ void __launch_bounds__(256) grid_write_bf16_c64(const int* __restrict__ cell_voxel,
-                                                           const float* __restrict__ voxel_feat,
-                                                           const float* __restrict__ c_empty,
-                                                           __nv_bfloat16* __restrict__ grid, long long ncells) {
+// 16 bytes of a cell's row: 4 float32 channels, or 8 channels rounded once from the float32 result to bf16
+template <typename GT>
+__device__ __forceinline__ float4 row_piece(const float* __restrict__ row, int piece) {
+  if (sizeof(GT) == 4) return __ldg(reinterpret_cast<const float4*>(row) + piece);
+  const float4 f0 = __ldg(reinterpret_cast<const float4*>(row) + 2 * piece);
+  const float4 f1 = __ldg(reinterpret_cast<const float4*>(row) + 2 * piece + 1);
+  return make_float4(__uint_as_float(pack_bf16x2(f0.x, f0.y)), __uint_as_float(pack_bf16x2(f0.z, f0.w)),
+                     __uint_as_float(pack_bf16x2(f1.x, f1.y)), __uint_as_float(pack_bf16x2(f1.z, f1.w)));
+}
+
+// C channels of GT per cell: kLanes = C * sizeof(GT) / 16 lanes x 16 B cover one cell (8: bf16 C = 64; 16: f32 C = 64 or
+// bf16 C = 128; 32: f32 C = 128), so a warp stores 32 / kLanes cells = 512 contiguous bytes per instruction.
+template <int C, typename GT>
+__global__ void __launch_bounds__(256) grid_write_kernel(const int* __restrict__ cell_voxel,
+                                                         const float* __restrict__ voxel_feat,
+                                                         const float* __restrict__ c_empty, GT* __restrict__ grid,
+                                                         long long ncells) {
+  constexpr int kLanes = C * (int)sizeof(GT) / 16;
+  constexpr int kCellsPerStore = 32 / kLanes;
   const int lane = threadIdx.x & 31;
-  const int sub = lane >> 3;
-  const int chunk = lane & 7;  // 8 channels
-  const float4 b0 = reinterpret_cast<const float4*>(c_empty)[2 * chunk];
-  const float4 b1 = reinterpret_cast<const float4*>(c_empty)[2 * chunk + 1];
-  const uint4 bg = make_uint4(pack_bf16x2(b0.x, b0.y), pack_bf16x2(b0.z, b0.w), pack_bf16x2(b1.x, b1.y),
-                              pack_bf16x2(b1.z, b1.w));
+  const int sub = lane / kLanes;
+  const int piece = lane % kLanes;
+  const float4 bg = row_piece<GT>(c_empty, piece);
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const long long ngroups = (ncells + 31) >> 5;
   for (long long grp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < ngroups; grp += warps) {
     const long long base = grp << 5;
     const int my = (base + lane < ncells) ? __ldg(cell_voxel + base + lane) : -1;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int vox = __shfl_sync(0xffffffffu, my, 4 * i + sub);
-      uint4 val = bg;
-      if (vox >= 0) {
-        const float4* src = reinterpret_cast<const float4*>(voxel_feat + (size_t)vox * 64) + 2 * chunk;
-        const float4 f0 = __ldg(src), f1 = __ldg(src + 1);
-        val = make_uint4(pack_bf16x2(f0.x, f0.y), pack_bf16x2(f0.z, f0.w), pack_bf16x2(f1.x, f1.y),
-                         pack_bf16x2(f1.z, f1.w));
-      }
-      const long long cell = base + 4 * i + sub;
-      if (cell < ncells) st_stream(reinterpret_cast<uint4*>(grid + cell * 64) + chunk, val);
+#pragma unroll 8
+    for (int i = 0; i < kLanes; ++i) {
+      const int vox = __shfl_sync(0xffffffffu, my, kCellsPerStore * i + sub);
+      const float4 val = vox >= 0 ? row_piece<GT>(voxel_feat + (size_t)vox * C, piece) : bg;
+      const long long cell = base + kCellsPerStore * i + sub;
+      if (cell < ncells) st_stream(reinterpret_cast<float4*>(grid + cell * C) + piece, val);
     }
   }
 }
@@ -136,21 +108,29 @@ cudaError_t launch_grid_fill(int grid_dtype, const float* c_empty, void* grid, l
   return cudaGetLastError();
 }
 
+template <int C>
+static void grid_write_launch(int grid_dtype, unsigned blocks, cudaStream_t st, const int* cell_voxel,
+                              const float* voxel_feat, const float* c_empty, void* grid, long long ncells) {
+  if (grid_dtype == LISEC_F32)
+    grid_write_kernel<C, float><<<blocks, 256, 0, st>>>(cell_voxel, voxel_feat, c_empty, static_cast<float*>(grid), ncells);
+  else
+    grid_write_kernel<C, __nv_bfloat16><<<blocks, 256, 0, st>>>(cell_voxel, voxel_feat, c_empty,
+                                                               static_cast<__nv_bfloat16*>(grid), ncells);
+}
+
 cudaError_t launch_grid_write(const Geom& g, int n_sweeps, int c3, int grid_dtype, const int* cell_voxel,
                               const float* voxel_feat, const float* c_empty, void* grid, int sm_count,
                               cudaStream_t st, int* launches) {
-  if (c3 != 64) return cudaErrorInvalidValue;
+  if (c3 != 64 && c3 != 128) return cudaErrorInvalidValue;
   const long long ncells = (long long)n_sweeps * g.cells;
   if (ncells == 0) return cudaSuccess;
   long long blocks = ((ncells + 31) / 32 + 7) / 8;  // 8 warps per block, one 32-cell group per warp
   const long long cap = (long long)sm_count * 8 * 4; // grid-stride beyond 4 waves of 8 resident CTAs per SM
   if (blocks > cap) blocks = cap;
-  if (grid_dtype == LISEC_F32)
-    grid_write_f32_c64<<<(unsigned)blocks, 256, 0, st>>>(cell_voxel, voxel_feat, c_empty,
-                                                         static_cast<float*>(grid), ncells);
+  if (c3 == 64)
+    grid_write_launch<64>(grid_dtype, (unsigned)blocks, st, cell_voxel, voxel_feat, c_empty, grid, ncells);
   else
-    grid_write_bf16_c64<<<(unsigned)blocks, 256, 0, st>>>(cell_voxel, voxel_feat, c_empty,
-                                                          static_cast<__nv_bfloat16*>(grid), ncells);
+    grid_write_launch<128>(grid_dtype, (unsigned)blocks, st, cell_voxel, voxel_feat, c_empty, grid, ncells);
   ++*launches;
   return cudaGetLastError();
 }

@@ -536,6 +536,10 @@ extern "C" {
 int32_t lisec_vfe_train_forward(lisec_handle* h, const lisec_vfe_train_params* p, void* grid, void* stream) {
   if (!h) return LISEC_ERR_BAD_ARG;
   if (!p || !grid) return fail(h, LISEC_ERR_BAD_ARG, "params / grid is NULL");
+  if (h->cfg.c1 != 16 || h->cfg.c2 != 32 || h->cfg.c3 != 64 || h->cfg.fcn_post_dense)
+    return fail(h, LISEC_ERR_UNSUPPORTED, "training is built for the graph train() creates (createModel, model_training.py:"
+                "222-257: widths 16, 32, 64, Dense-BN-ReLU); this handle holds (%d, %d, %d, post_dense = %d)", h->cfg.c1,
+                h->cfg.c2, h->cfg.c3, h->cfg.fcn_post_dense);
   if (!h->voxelized) return fail(h, LISEC_ERR_STATE, "no lisec_voxelize() result on this handle");
   for (int l = 0; l < 3; ++l)
     if (!p->dense_kernel[l] || !p->bn_gamma[l] || !p->bn_beta[l])

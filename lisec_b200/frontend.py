@@ -18,7 +18,7 @@ import torch
 
 from . import _native as N
 from . import constants as K
-from .weights import VFE_BN, VFE_DENSE, validate_vfe_pack
+from .weights import Architecture, validate_vfe_pack, vfe_layers
 
 ArrayLike = Union[np.ndarray, torch.Tensor]
 
@@ -59,7 +59,10 @@ class Frontend:
         sample_size: int = K.maxPoints,
         max_voxel=(K.nx // 2, K.ny // 2, K.nz),
         widths=K.vfe_widths,
+        post_dense: bool = False,
     ):
+        """widths / post_dense: the graph the weights belong to (lisec_b200.weights.Architecture) — (16, 32, 64),
+        False is createModel() as it stands (model_training.py:229-235); (16, 64, 128), True is the graph model.png shows."""
         if not torch.cuda.is_available():
             raise RuntimeError("lisec_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self._lib = N.load()
@@ -71,8 +74,9 @@ class Frontend:
             max_voxel_x=max_voxel[0], max_voxel_y=max_voxel[1], max_voxel_z=max_voxel[2],
             c1=widths[0], c2=widths[1], c3=widths[2],
             grid_dtype=N.LISEC_F32 if grid_dtype == "f32" else N.LISEC_BF16,
-            max_sweeps=max_sweeps, max_points=max_points, device=device, reserved=0,
+            max_sweeps=max_sweeps, max_points=max_points, device=device, fcn_post_dense=int(bool(post_dense)),
         )
+        self.arch = Architecture(int(widths[0]), int(widths[1]), int(widths[2]), bool(post_dense))
         self.cfg = cfg
         self.T = sample_size
         self.c3 = widths[2]
@@ -118,12 +122,14 @@ class Frontend:
     # ---- weights -----------------------------------------------------------------------------------------
     def set_weights(self, pack: dict, bn_epsilon: float = K.bn_epsilon) -> None:
         """pack: Keras-named arrays (lisec_b200.weights); what load_model()/createModel() would hold for the first
-        23 layers (model_training.py:229-235)."""
-        p = validate_vfe_pack(pack)
+        23 layers (model_training.py:229-235) — 26 with the FCNs' second Dense (Architecture.post_dense)."""
+        p = validate_vfe_pack(pack, self.arch)
         w = N.lisec_vfe_weights()
         fp = C.POINTER(C.c_float)
-        for i, (d, b) in enumerate(zip(VFE_DENSE, VFE_BN)):
+        for i, (d, b, post, _, _) in enumerate(vfe_layers(self.arch)):
             w.dense_kernel[i] = p[d + "/kernel"].ctypes.data_as(fp)
+            if post:
+                w.post_dense_kernel[i] = p[post + "/kernel"].ctypes.data_as(fp)
             w.bn_gamma[i] = p[b + "/gamma"].ctypes.data_as(fp)
             w.bn_beta[i] = p[b + "/beta"].ctypes.data_as(fp)
             w.bn_mean[i] = p[b + "/moving_mean"].ctypes.data_as(fp)

@@ -8,6 +8,8 @@ affine tails are folded on the host in float64 before anything is rounded to the
       conv -> BN -> Dense is linear up to the ReLU:   W'[tap,ci,n] = sum_c K[tap,ci,c] g[c] Wd[c,n],
       shift'[n] = sum_c ((bias[c] - mean[c]) g[c] + beta[c]) Wd[c,n],  g = gamma / sqrt(var + 1e-3)  -> one plan, ReLU
   addConv2DLayer (:201-208)  Conv2D(bias) + BatchNormalization + ReLU -> scale = g, shift = (bias - mean) g + beta
+      with Architecture.post_dense (the line commented out at :205 switched on, the graph model.png shows): Conv2D + BN +
+      Dense(cout, relu, no bias) folds exactly like addConv3DLayer; the grid and the first Conv3D then carry C3 = 128 channels
   Conv2DTranspose (:245,248,251, padding='same')  k3 s1 = 3x3 convolution with the kernel flipped; k2 s2 / k4 s4 do not
       overlap = 1x1 GEMMs with k*k groups of 256 columns, pixel-shuffled by the epilogue. Each writes its 256-channel
       slice of the Concatenate (:252) buffer directly.
@@ -29,7 +31,7 @@ import numpy as np
 import torch
 
 from . import _native
-from .weights import conv3d_blocks, rpn_blocks, validate_network_pack
+from .weights import CURRENT, Architecture, conv2d_post_dense, conv3d_blocks, rpn_blocks, validate_network_pack
 
 BN_EPS = 1e-3
 
@@ -92,7 +94,7 @@ class DenseNetwork:
     """Plans and activation buffers for one batch size and grid. `grid` is the input buffer the front end writes."""
 
     def __init__(self, pack: dict, batch: int, nx: int = 200, ny: int = 400, nz: int = 8, device: int = 0,
-                 schedule=None, dtype: str = "bf16", fuse_heads: bool = True):
+                 schedule=None, dtype: str = "bf16", fuse_heads: bool = True, arch: Architecture = CURRENT):
         if nz != 8 or nx % 8 or ny % 8:
             raise ValueError("the Conv3D stack collapses nz = 8 to 1 and the RPN halves x, y three times: need nz = 8 "
                              "and nx, ny multiples of 8 (got %d, %d, %d)" % (nz, nx, ny))
@@ -108,7 +110,9 @@ class DenseNetwork:
         self._auto_schedule = schedule is None and not self.f32
         self.fuse_heads = bool(fuse_heads)
         self._sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
-        pack = validate_network_pack(pack)
+        self.arch = arch
+        pack = validate_network_pack(pack, arch)
+        c3 = arch.c3
         dev = self.device
         f32 = self.f32
 
@@ -118,22 +122,22 @@ class DenseNetwork:
             return torch.zeros(shape, dtype=dtype or torch.bfloat16, device=dev)
 
         B = batch
-        self.grid = buf(B, nz, nx, ny, 64, planes=False)  # what the front end writes: bf16, or plain float32
-        self.grid_planes = buf(B, nz, nx, ny, 64) if f32 else self.grid
+        self.grid = buf(B, nz, nx, ny, c3, planes=False)  # what the front end writes: bf16, or plain float32
+        self.grid_planes = buf(B, nz, nx, ny, c3) if f32 else self.grid
         self.layers: List[_Layer] = []
         # ---- middle: three Conv3D blocks (:236-238) ----
-        src, d = self.grid_planes, nz
-        for conv, bn, dense, stride, pad in conv3d_blocks():
-            K = pack[conv + "/kernel"].astype(np.float64).reshape(27, 64, 64)  # [tap (kd,kh,kw)][ci][c]
+        src, d, cin3 = self.grid_planes, nz, c3
+        for conv, bn, dense, stride, pad in conv3d_blocks(arch):
+            K = pack[conv + "/kernel"].astype(np.float64).reshape(27, cin3, 64)  # [tap (kd,kh,kw)][ci][c]
             g, b0 = _bn_fold(pack, bn)
             Wd = pack[dense + "/kernel"].astype(np.float64)
             W = np.einsum("tic,c,cn->tni", K, g, Wd)
             shift = (pack[conv + "/bias"].astype(np.float64) * g + b0) @ Wd
             od = (d + 2 * pad[0] - 3) // stride[0] + 1
             dst = buf(B, od, nx, ny, 64)
-            self._add(conv, src, dst, W, np.ones(64), shift, in_d=d, in_h=nx, in_w=ny, in_c=64, k=(3, 3, 3),
+            self._add(conv, src, dst, W, np.ones(64), shift, in_d=d, in_h=nx, in_w=ny, in_c=cin3, k=(3, 3, 3),
                       stride_d=stride[0], stride_hw=1, pad=pad, out_c=64, relu=1)
-            src, d = dst, od
+            src, d, cin3 = dst, od, 64
         assert d == 1
         # ---- RPN (:245-251) ----
         h, w = nx, ny
@@ -153,6 +157,7 @@ class DenseNetwork:
                 bh = bh + pack[tname + "/bias"].astype(np.float64) @ Kh[256 * bi:256 * bi + 256]
         else:
             self.concat = buf(B, 1, nx // 2, ny // 2, 768)
+        post = conv2d_post_dense(arch)
         for bi, (convs, (tname, k, s, tc_in)) in enumerate(rpn_blocks()):
             pp = None
             for conv, bn, cin, cout, stride in convs:
@@ -160,6 +165,11 @@ class DenseNetwork:
                 g, b0 = _bn_fold(pack, bn)
                 W = K.transpose(0, 2, 1)
                 shift = pack[conv + "/bias"].astype(np.float64) * g + b0
+                if conv in post:  # Conv2D -> BN -> Dense(relu): linear up to the ReLU, folded like the Conv3D blocks
+                    Wd = pack[post[conv] + "/kernel"].astype(np.float64)
+                    W = np.einsum("tic,c,cn->tni", K, g, Wd)
+                    shift = shift @ Wd
+                    g = np.ones(cout)
                 oh, ow = h // stride, w // stride
                 if pp is None:
                     pp = [buf(B, 1, oh, ow, cout), buf(B, 1, oh, ow, cout)]
@@ -307,6 +317,8 @@ class DenseNetwork:
         forward_sparse(points, offsets) replaces fe.forward(..., out=net.grid) + net.forward()."""
         if self.f32:
             raise ValueError("the gather source is a bf16 plan")
+        if self.arch.c3 != 64 or fe.c3 != 64:
+            raise ValueError("the gather source reads 64-channel voxel rows (createModel as it stands)")
         cv, ce, mv = C.c_void_p(), C.c_void_p(), C.c_int64()
         fe._check(self._lib.lisec_workspace_pointers(fe._h, C.byref(cv), C.byref(ce), C.byref(mv)))
         self.voxel_feat = torch.empty((int(mv.value), 64), dtype=torch.float32, device=self.device)

@@ -8,7 +8,76 @@ reference checkout and h5py is not in this image, so packs travel as .npz with t
 """
 from __future__ import annotations
 
+from dataclasses import dataclass
+
 import numpy as np
+
+
+@dataclass(frozen=True)
+class Architecture:
+    """Which of the reference's two graphs a weight set belongs to.
+
+    post_dense = False  the current code: FCN = Dense -> BatchNormalization -> ReLU (model_training.py:169-174) and
+                        Conv2D -> BatchNormalization -> ReLU (:201-208); VFE widths 16 | 32 | 64 (:231-233).
+    post_dense = True   the graph model.png shows, i.e. the lines commented out at :172 and :205 switched on: FCN =
+                        Dense -> BatchNormalization -> Dense(units, relu, no bias) and Conv2D -> BatchNormalization ->
+                        Dense(relu); VFE widths 16 | 64 | 128, so the grid and the first Conv3D's input carry 128 channels.
+    A Keras .h5 embeds its own graph and Predict.py:51-52 uses load_model(), so either may arrive; detect_architecture()
+    tells them apart by the kernels' shapes. Keras numbers Dense layers in creation order, so the names shift:
+    post_dense puts two Dense layers into every FCN (dense, dense_1 | dense_2, dense_3 | dense_4, dense_5), three behind
+    the Conv3D blocks (dense_6..8) and sixteen behind the RPN's Conv2D layers (dense_9..24): 25, as model.png counts."""
+    c1: int = 16
+    c2: int = 32
+    c3: int = 64
+    post_dense: bool = False
+
+    @property
+    def widths(self):
+        return (self.c1, self.c2, self.c3)
+
+
+CURRENT = Architecture()
+MODEL_PNG = Architecture(16, 64, 128, True)
+SUPPORTED_WIDTHS = ((16, 32, 64), (16, 64, 128))  # what liblisec_b200.so instantiates (lisec_create checks)
+
+
+def _suffix(base: str, i: int) -> str:
+    return base if i == 0 else "%s_%d" % (base, i)
+
+
+def vfe_layers(arch: Architecture = CURRENT):
+    """[(dense name, bn name, post-dense name or None, cin, cout)] of the three FCNs (:231-233) in creation order."""
+    out, n = [], 0
+    for i, (cin, cout) in enumerate(((6, arch.c1), (2 * arch.c1, arch.c2), (2 * arch.c2, arch.c3))):
+        d = _suffix("dense", n)
+        n += 1
+        post = None
+        if arch.post_dense:
+            post = _suffix("dense", n)
+            n += 1
+        out.append((d, _suffix("batch_normalization", i), post, cin, cout))
+    return out
+
+
+def _dense_after_vfe(arch: Architecture) -> int:
+    return 6 if arch.post_dense else 3
+
+
+def detect_architecture(pack: dict) -> Architecture:
+    """The graph a Keras-named weight set was saved from, by the shapes of its first Dense kernels."""
+    k0 = np.shape(pack["dense/kernel"])
+    k1 = np.shape(pack["dense_1/kernel"])
+    if len(k0) != 2 or k0[0] != 6 or len(k1) != 2:
+        raise ValueError("dense/kernel %s, dense_1/kernel %s: not a VoxelNet front end of this reference" % (k0, k1))
+    c1 = int(k0[1])
+    if k1 == (c1, c1):  # the FCN's second Dense
+        if "dense_5/kernel" not in pack:
+            raise ValueError("dense_1/kernel is (%d,%d) — the Dense-BN-Dense FCN — but dense_5/kernel is missing" % k1)
+        return Architecture(c1, int(np.shape(pack["dense_2/kernel"])[1]), int(np.shape(pack["dense_4/kernel"])[1]), True)
+    if k1[0] != 2 * c1:
+        raise ValueError("dense_1/kernel has %d rows: expected %d (concat) or %d (second FCN Dense)" % (k1[0], 2 * c1, c1))
+    return Architecture(c1, int(k1[1]), int(np.shape(pack["dense_2/kernel"])[1]), False)
+
 
 VFE_DENSE = ("dense", "dense_1", "dense_2")
 VFE_BN = ("batch_normalization", "batch_normalization_1", "batch_normalization_2")
@@ -16,40 +85,48 @@ VFE_SHAPES = ((6, 16), (32, 32), (64, 64))
 BN_FIELDS = ("gamma", "beta", "moving_mean", "moving_variance")
 
 
-def vfe_keys():
+def vfe_keys(arch: Architecture = CURRENT):
     keys = []
-    for d, b in zip(VFE_DENSE, VFE_BN):
+    for d, b, post, _, _ in vfe_layers(arch):
         keys.append(d + "/kernel")
         keys.extend(b + "/" + f for f in BN_FIELDS)
+        if post:
+            keys.append(post + "/kernel")
     return keys
 
 
-def synthetic_vfe_pack(seed: int = 0) -> dict:
+def synthetic_vfe_pack(seed: int = 0, arch: Architecture = CURRENT) -> dict:
     """Seeded stand-in for the missing .h5: Glorot-uniform kernels (the Keras Dense default) and non-trivial BN
     statistics, so that c_empty != 0 and the pad rows really do take part in the max-pools."""
     rng = np.random.default_rng(seed)
     pack = {}
-    for d, b, (cin, cout) in zip(VFE_DENSE, VFE_BN, VFE_SHAPES):
+    for d, b, post, cin, cout in vfe_layers(arch):
         lim = np.sqrt(6.0 / (cin + cout))
         pack[d + "/kernel"] = rng.uniform(-lim, lim, size=(cin, cout)).astype(np.float32)
         pack[b + "/gamma"] = rng.uniform(0.5, 1.5, size=cout).astype(np.float32)
         pack[b + "/beta"] = rng.uniform(-0.3, 0.3, size=cout).astype(np.float32)
         pack[b + "/moving_mean"] = rng.uniform(-0.5, 0.5, size=cout).astype(np.float32)
         pack[b + "/moving_variance"] = rng.uniform(0.3, 2.0, size=cout).astype(np.float32)
+        if post:
+            lim = np.sqrt(6.0 / (2 * cout))
+            pack[post + "/kernel"] = rng.uniform(-lim, lim, size=(cout, cout)).astype(np.float32)
     return pack
 
 
-def validate_vfe_pack(pack: dict) -> dict:
+def validate_vfe_pack(pack: dict, arch: Architecture = CURRENT) -> dict:
     out = {}
-    for d, b, shape in zip(VFE_DENSE, VFE_BN, VFE_SHAPES):
-        k = np.ascontiguousarray(pack[d + "/kernel"], dtype=np.float32)
-        if k.shape != shape:
-            raise ValueError("%s/kernel has shape %s, expected %s" % (d, k.shape, shape))
-        out[d + "/kernel"] = k
+    for d, b, post, cin, cout in vfe_layers(arch):
+        for name, shape in ((d, (cin, cout)),) + (((post, (cout, cout)),) if post else ()):
+            if name + "/kernel" not in pack:
+                raise KeyError("weight pack has no %s/kernel" % name)
+            k = np.ascontiguousarray(pack[name + "/kernel"], dtype=np.float32)
+            if k.shape != shape:
+                raise ValueError("%s/kernel has shape %s, expected %s" % (name, k.shape, shape))
+            out[name + "/kernel"] = k
         for f in BN_FIELDS:
             v = np.ascontiguousarray(pack[b + "/" + f], dtype=np.float32)
-            if v.shape != (shape[1],):
-                raise ValueError("%s/%s has shape %s, expected (%d,)" % (b, f, v.shape, shape[1]))
+            if v.shape != (cout,):
+                raise ValueError("%s/%s has shape %s, expected (%d,)" % (b, f, v.shape, cout))
             out[b + "/" + f] = v
     return out
 
@@ -68,15 +145,21 @@ def load_npz(path: str) -> dict:
 #   conv2d[_k] kernel (3,3,Cin,Cout) + bias     | batch_normalization_{6..21}
 #   conv2d_transpose[_k] kernel (k,k,Cout,Cin) + bias (Keras keeps transposed kernels output-channel-first)
 #   ClassificationLayer kernel (1,1,768,2) + bias, RegressionLayer kernel (1,1,768,14) + bias
-def _suffix(base: str, i: int) -> str:
-    return base if i == 0 else "%s_%d" % (base, i)
-
-
-def conv3d_blocks():
+def conv3d_blocks(arch: Architecture = CURRENT):
     """[(conv3d name, bn name, dense name, stride (z,x,y), pad (z,x,y))] — addConv3DLayer calls at :236-238."""
     geo = [((2, 1, 1), (1, 1, 1)), ((1, 1, 1), (0, 1, 1)), ((2, 1, 1), (1, 1, 1))]
-    return [(_suffix("conv3d", i), "batch_normalization_%d" % (3 + i), "dense_%d" % (3 + i), s, p)
+    d0 = _dense_after_vfe(arch)
+    return [(_suffix("conv3d", i), "batch_normalization_%d" % (3 + i), "dense_%d" % (d0 + i), s, p)
             for i, (s, p) in enumerate(geo)]
+
+
+def conv2d_post_dense(arch: Architecture = CURRENT) -> dict:
+    """{conv2d name: name of the Dense(relu) behind its BatchNormalization} — the variant of addConv2DLayer commented out
+    at :205 (empty for the current code, whose Conv2D layers end in Activation('relu'))."""
+    if not arch.post_dense:
+        return {}
+    d0 = _dense_after_vfe(arch) + 3
+    return {_suffix("conv2d", i): "dense_%d" % (d0 + i) for i in range(16)}
 
 
 def rpn_blocks():
@@ -93,20 +176,23 @@ def rpn_blocks():
     return blocks
 
 
-def network_shapes() -> dict:
+def network_shapes(arch: Architecture = CURRENT) -> dict:
     shapes = {}
-    for c, b, d, _, _ in conv3d_blocks():
-        shapes[c + "/kernel"] = (3, 3, 3, 64, 64)
+    for i, (c, b, d, _, _) in enumerate(conv3d_blocks(arch)):
+        shapes[c + "/kernel"] = (3, 3, 3, arch.c3 if i == 0 else 64, 64)
         shapes[c + "/bias"] = (64,)
         for f in BN_FIELDS:
             shapes[b + "/" + f] = (64,)
         shapes[d + "/kernel"] = (64, 64)
+    post = conv2d_post_dense(arch)
     for convs, (tname, k, s, cin) in rpn_blocks():
         for c, b, ci, co, _ in convs:
             shapes[c + "/kernel"] = (3, 3, ci, co)
             shapes[c + "/bias"] = (co,)
             for f in BN_FIELDS:
                 shapes[b + "/" + f] = (co,)
+            if c in post:
+                shapes[post[c] + "/kernel"] = (co, co)
         shapes[tname + "/kernel"] = (k, k, 256, cin)
         shapes[tname + "/bias"] = (256,)
     shapes["ClassificationLayer/kernel"] = (1, 1, 768, 2)
@@ -116,12 +202,12 @@ def network_shapes() -> dict:
     return shapes
 
 
-def synthetic_network_pack(seed: int = 0) -> dict:
+def synthetic_network_pack(seed: int = 0, arch: Architecture = CURRENT) -> dict:
     """Seeded stand-in for the dense half of the missing .h5: Glorot-uniform kernels (Keras default), small non-zero
     biases and non-trivial BN statistics. Merged with synthetic_vfe_pack(seed) it is a whole createModel()."""
     rng = np.random.default_rng(1000 + seed)
     pack = {}
-    for name, shape in network_shapes().items():
+    for name, shape in network_shapes(arch).items():
         leaf = name.split("/")[1]
         if leaf == "kernel":
             rf = int(np.prod(shape[:-2]))
@@ -165,15 +251,23 @@ def keras_default_init_pack(seed: int = 0) -> dict:
     return pack
 
 
-def synthetic_model_pack(seed: int = 0) -> dict:
-    pack = synthetic_vfe_pack(seed)
-    pack.update(synthetic_network_pack(seed))
+def synthetic_model_pack(seed: int = 0, arch: Architecture = CURRENT) -> dict:
+    pack = synthetic_vfe_pack(seed, arch)
+    pack.update(synthetic_network_pack(seed, arch))
     return pack
 
 
-def validate_network_pack(pack: dict) -> dict:
+# model.png's graph predates the heads' names (:253-254): Keras auto-named them after the 16 RPN convolutions
+HEAD_ALIASES = {"ClassificationLayer": "conv2d_16", "RegressionLayer": "conv2d_17"}
+
+
+def validate_network_pack(pack: dict, arch: Architecture = CURRENT) -> dict:
     out = {}
-    for name, shape in network_shapes().items():
+    for name, shape in network_shapes(arch).items():
+        layer, leaf = name.split("/")
+        if name not in pack and layer in HEAD_ALIASES and HEAD_ALIASES[layer] + "/" + leaf in pack:
+            pack = dict(pack)
+            pack[name] = pack[HEAD_ALIASES[layer] + "/" + leaf]
         if name not in pack:
             raise KeyError("weight pack has no %s" % name)
         v = np.ascontiguousarray(pack[name], dtype=np.float32)

@@ -210,30 +210,50 @@ def _bn(x, pack, name, dtype):
     return x * inv + (b - m * inv)
 
 
-def _fcn(x, pack, i, dtype):
-    # addFCN (:169-174): addDenseLayer (bias-free Dense over the last axis, :178-186) -> BatchNormalization -> ReLU
-    k = pack[DENSE[i] + "/kernel"].astype(dtype)
-    y = (x.reshape(-1, x.shape[-1]) @ k).reshape(x.shape[:-1] + (k.shape[1],))
-    y = _bn(y, pack, BN[i], dtype)
+def _dense(x, pack, name, dtype):
+    # addDenseLayer (:178-186): a bias-free Dense over the last axis (the Reshape pair around it changes nothing)
+    k = pack[name + "/kernel"].astype(dtype)
+    return (x.reshape(-1, x.shape[-1]) @ k).reshape(x.shape[:-1] + (k.shape[1],))
+
+
+def _fcn_names(pack, post_dense):
+    """Keras names of the three FCNs' layers, [(dense, bn, second dense or None)]: Dense layers are numbered in creation
+    order, so the Dense -> BN -> Dense variant (the line commented out at :172, the graph model.png shows) owns two each."""
+    if post_dense is None:  # tell the two graphs apart by dense_1: (2*c1, c2) in the current code, (c1, c1) in the other
+        post_dense = pack["dense_1/kernel"].shape[0] == pack["dense/kernel"].shape[1]
+    d = ["dense"] + ["dense_%d" % i for i in range(1, 6)]
+    if post_dense:
+        return [(d[0], BN[0], d[1]), (d[2], BN[1], d[3]), (d[4], BN[2], d[5])]
+    return [(d[0], BN[0], None), (d[1], BN[1], None), (d[2], BN[2], None)]
+
+
+def _fcn(x, pack, names, dtype):
+    # addFCN (:169-174): addDenseLayer -> BatchNormalization -> ReLU; in the variant at :172, -> Dense(units, relu) instead
+    dense, bn, post = names
+    y = _bn(_dense(x, pack, dense, dtype), pack, bn, dtype)
+    if post is not None:
+        y = _dense(y, pack, post, dtype)
     return np.maximum(y, dtype(0))
 
 
-def _vfe_layer(x, pack, i, dtype):
+def _vfe_layer(x, pack, names, dtype):
     # addVFELayer (:155-166): FCN -> MaxPoolingVFELayer (max over axis -2, keepdims) -> RepeatLayer -> Concatenate
-    layer = _fcn(x, pack, i, dtype)
+    layer = _fcn(x, pack, names, dtype)
     pooling = layer.max(axis=-2, keepdims=True)  # includes the pad rows: nothing is masked anywhere
     pooling = np.repeat(pooling, layer.shape[-2], axis=-2)
     return np.concatenate([pooling, layer], axis=-1)  # [pooled, pointwise] (:164-165)
 
 
-def vfe_forward(x, pack, dtype=np.float64):
+def vfe_forward(x, pack, dtype=np.float64, post_dense=None):
     """model_training.py:229-235 on a tensor [..., T, 6] (the dense [N,nz,nx,ny,T,6] input, or any batch of voxels).
-    Returns [..., 64] — MaxPoolingVFELayer(combine=True) output."""
+    Returns [..., C3] — MaxPoolingVFELayer(combine=True) output. The widths come from the kernels' shapes; post_dense
+    selects the FCN variant (None: read it off the shapes)."""
+    names = _fcn_names(pack, post_dense)
     x = np.asarray(x).astype(dtype)  # the Keras model casts its input to float32
-    out = _vfe_layer(x, pack, 0, dtype)    # addVFELayer(in, 6, 32)
-    out = _vfe_layer(out, pack, 1, dtype)  # addVFELayer(., 32, 64)
-    out = _fcn(out, pack, 2, dtype)        # addFCN(., 64, 64)
-    return out.max(axis=-2)                # MaxPoolingVFELayer(combine=True)
+    out = _vfe_layer(x, pack, names[0], dtype)    # addVFELayer(in, 6, 32)
+    out = _vfe_layer(out, pack, names[1], dtype)  # addVFELayer(., 32, 64)
+    out = _fcn(out, pack, names[2], dtype)        # addFCN(., 64, 64)
+    return out.max(axis=-2)                       # MaxPoolingVFELayer(combine=True)
 
 
 def c_empty(pack, T, dtype=np.float64):
@@ -255,7 +275,8 @@ def vfe_forward_dense_chunked(dense_fn, pack, grid_zxy, T, dtype=np.float32, chu
     evaluated one z-slab at a time so the float32 intermediates (5.7 GB per tensor at full size) stay bounded.
     dense_fn(z0, z1) returns the dense input slab [z1-z0, nx, ny, T, 6]."""
     nz, nx, ny = grid_zxy
-    out = np.empty((nz, nx, ny, 64), dtype=dtype)
+    c3 = pack[_fcn_names(pack, None)[2][0] + "/kernel"].shape[1]
+    out = np.empty((nz, nx, ny, c3), dtype=dtype)
     for z0 in range(0, nz, chunk_z):
         z1 = min(nz, z0 + chunk_z)
         out[z0:z1] = vfe_forward(dense_fn(z0, z1), pack, dtype)

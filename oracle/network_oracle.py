@@ -15,6 +15,8 @@ Follows reference model_training.py:
   createModel     :245-254   blocks (128,q=3) (128,q=5) (256,q=5); Conv2DTranspose(256, k3 s1 / k2 s2 / k4 s4, 'same');
                               Concatenate; ClassificationLayer (2) and RegressionLayer (14): 1x1, linear
 Keras defaults: BatchNormalization(axis=-1, epsilon=1e-3) in inference mode; channels_last everywhere.
+arch.post_dense (lisec_b200.weights.Architecture) switches on the lines the reference has commented out — :205, Conv2D ->
+BatchNormalization -> Dense(cout, relu, no bias) instead of -> ReLU — and the 128-channel grid: the graph model.png shows.
 """
 from __future__ import annotations
 
@@ -22,7 +24,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from lisec_b200.weights import conv3d_blocks, rpn_blocks
+from lisec_b200.weights import CURRENT, Architecture, conv2d_post_dense, conv3d_blocks, rpn_blocks
 
 BN_EPS = 1e-3
 
@@ -38,10 +40,10 @@ def _bn(x, pack, name, dtype):
     return (x - m.view(shape)) * (g / torch.sqrt(v + BN_EPS)).view(shape) + b.view(shape)
 
 
-def middle_forward(grid: np.ndarray, pack: dict, dtype=torch.float64) -> torch.Tensor:
-    """grid [N, nz, nx, ny, 64] (the VFE output) -> [N, 64, nx, ny] (channels-first) after the three Conv3D blocks."""
+def middle_forward(grid: np.ndarray, pack: dict, dtype=torch.float64, arch: Architecture = CURRENT) -> torch.Tensor:
+    """grid [N, nz, nx, ny, C3] (the VFE output) -> [N, 64, nx, ny] (channels-first) after the three Conv3D blocks."""
     x = _t(grid, dtype).permute(0, 4, 1, 2, 3)  # N C D(z) H(x) W(y)
-    for conv, bn, dense, stride, pad in conv3d_blocks():
+    for conv, bn, dense, stride, pad in conv3d_blocks(arch):
         w = _t(pack[conv + "/kernel"], dtype).permute(4, 3, 0, 1, 2)  # (kd,kh,kw,cin,cout) -> (cout,cin,kd,kh,kw)
         x = F.conv3d(x, w, _t(pack[conv + "/bias"], dtype), stride=stride, padding=pad)
         x = _bn(x, pack, bn, dtype)
@@ -53,14 +55,18 @@ def middle_forward(grid: np.ndarray, pack: dict, dtype=torch.float64) -> torch.T
     return x[:, :, 0]
 
 
-def rpn_forward(x: torch.Tensor, pack: dict, dtype=torch.float64):
+def rpn_forward(x: torch.Tensor, pack: dict, dtype=torch.float64, arch: Architecture = CURRENT):
     """[N, 64, nx, ny] -> prob [N, nx/2, ny/2, 2], regress [N, nx/2, ny/2, 14] (channels-last, like model.predict)."""
     ups = []
+    post = conv2d_post_dense(arch)
     for convs, (tname, k, s, _) in rpn_blocks():
         for conv, bn, _, _, stride in convs:
             w = _t(pack[conv + "/kernel"], dtype).permute(3, 2, 0, 1)  # (kh,kw,cin,cout) -> (cout,cin,kh,kw)
             x = F.conv2d(x, w, _t(pack[conv + "/bias"], dtype), stride=stride, padding=1)
-            x = torch.relu(_bn(x, pack, bn, dtype))
+            x = _bn(x, pack, bn, dtype)
+            if conv in post:  # addDenseLayer(layer, cout, 'relu') (:205)
+                x = torch.einsum("nchw,ck->nkhw", x, _t(pack[post[conv] + "/kernel"], dtype))
+            x = torch.relu(x)
         # Keras Conv2DTranspose kernel (kh,kw,cout,cin); 'same' => output = input * stride: k3 s1 crops 1, k == s crops 0
         wt = _t(pack[tname + "/kernel"], dtype).permute(3, 2, 0, 1)  # -> torch (cin, cout, kh, kw)
         ups.append(F.conv_transpose2d(x, wt, _t(pack[tname + "/bias"], dtype), stride=s, padding=(k - s) // 2))
@@ -72,8 +78,8 @@ def rpn_forward(x: torch.Tensor, pack: dict, dtype=torch.float64):
     return outs[0], outs[1]
 
 
-def network_forward(grid: np.ndarray, pack: dict, dtype=torch.float64):
+def network_forward(grid: np.ndarray, pack: dict, dtype=torch.float64, arch: Architecture = CURRENT):
     """Everything behind MaxPoolingVFELayer(combine=True) (:235): numpy prob, regress."""
     with torch.no_grad():
-        p, r = rpn_forward(middle_forward(grid, pack, dtype), pack, dtype)
+        p, r = rpn_forward(middle_forward(grid, pack, dtype, arch), pack, dtype, arch)
     return p.numpy(), r.numpy()

@@ -34,18 +34,24 @@ def test_config_struct_layout_matches_header():
     # 3 doubles, 9 int32, (pad) int64, 2 int32 -> 80 bytes with natural alignment
     assert C.sizeof(N.lisec_config) == 80
     assert N.lisec_config.max_points.offset == 64
-    assert C.sizeof(N.lisec_vfe_weights) == 15 * 8 + 8
+    assert N.lisec_config.fcn_post_dense.offset == 76
+    assert C.sizeof(N.lisec_vfe_weights) == 15 * 8 + 8 + 3 * 8
+    assert N.lisec_vfe_weights.post_dense_kernel.offset == 128
 
 
 def test_bad_config_is_rejected_with_a_message():
     lib = N.load()
     cfg = N.lisec_config(voxel_x=0.5, voxel_y=0.25, voxel_z=0.25, sample_size=35, max_voxel_x=100, max_voxel_y=200,
-                         max_voxel_z=8, c1=16, c2=64, c3=128, grid_dtype=0, max_sweeps=1, max_points=1000, device=0)
+                         max_voxel_z=8, c1=16, c2=48, c3=96, grid_dtype=0, max_sweeps=1, max_points=1000, device=0)
     h = C.c_void_p()
-    st = lib.lisec_create(C.byref(cfg), C.byref(h))
-    assert st == -6 and b"16,32,64" in lib.lisec_last_error(h)
+    st = lib.lisec_create(C.byref(cfg), C.byref(h))  # widths of neither graph the reference has had
+    assert st == -6 and b"16,32,64" in lib.lisec_last_error(h) and b"16,64,128" in lib.lisec_last_error(h)
     lib.lisec_destroy(h)
-    cfg.c2, cfg.c3, cfg.sample_size = 32, 64, 1
+    cfg.c2, cfg.c3, cfg.fcn_post_dense = 64, 128, 2
+    st = lib.lisec_create(C.byref(cfg), C.byref(h))
+    assert st == -2 and b"fcn_post_dense" in lib.lisec_last_error(h)
+    lib.lisec_destroy(h)
+    cfg.c2, cfg.c3, cfg.fcn_post_dense, cfg.sample_size = 32, 64, 0, 1
     st = lib.lisec_create(C.byref(cfg), C.byref(h))
     assert st == -2
     lib.lisec_destroy(h)
