@@ -89,31 +89,47 @@ def _bf16_ste(x):
 
 
 def network_forward_train(grid: torch.Tensor, p: Dict[str, torch.Tensor], stats: dict, unbiased_4d: bool = False,
-                          bf16_activations: bool = False):
+                          bf16_activations: bool = False, teacher: Dict[str, torch.Tensor] = None):
     """Everything behind the voxel grid [N, nz, nx, ny, 64] in training mode (:236-254): prob, regress.
     bf16_activations: every tensor the GPU chain stores in bf16 (convolution outputs, BN outputs, Dense outputs, the
-    concat tensor) is rounded to bf16 on the way forward."""
+    concat tensor) is rounded to bf16 on the way forward.
+    teacher: {layer name: that layer group's OUTPUT as another implementation computed it} (channels-first for the
+    convolution stages — keyed by the conv3d / conv2d / conv2d_transpose name —, channels-last for the two heads). Where
+    given, the stage's output VALUE is replaced by the teacher's while the gradient still flows through the float64 stage
+    (straight-through): autograd then yields the exact float64 gradient of every parameter AT THE OTHER IMPLEMENTATION'S
+    OPERATING POINT — the same ReLU masks, batch statistics of the same inputs, the same loss residual. It separates a
+    wrong backward pass (which would still disagree) from forward drift amplified by the network (which disappears)."""
     q = _bf16_ste if bf16_activations else (lambda t: t)
+    teacher = teacher or {}
+
+    def force(name, t):
+        g = teacher.get(name)
+        if g is None:
+            return t
+        if tuple(g.shape) != tuple(t.shape):
+            raise ValueError("teacher[%s] has shape %s, the stage's output %s" % (name, tuple(g.shape), tuple(t.shape)))
+        return g.to(t.dtype) + (t - t.detach())
+
     x = grid.permute(0, 4, 1, 2, 3)
     for conv, bn, dense, stride, pad in conv3d_blocks():
         w = p[conv + "/kernel"].permute(4, 3, 0, 1, 2)
         x = q(F.conv3d(x, w, p[conv + "/bias"], stride=stride, padding=pad))
         x = q(_bn_train(x, p, bn, stats, channels_last=False))
-        x = q(torch.relu(torch.einsum("ncdhw,ck->nkdhw", x, p[dense + "/kernel"])))
+        x = force(conv, q(torch.relu(torch.einsum("ncdhw,ck->nkdhw", x, p[dense + "/kernel"]))))
     x = x[:, :, 0]
     ups = []
     for convs, (tname, k, s, _) in rpn_blocks():
         for conv, bn, _, _, stride in convs:
             w = p[conv + "/kernel"].permute(3, 2, 0, 1)
             x = q(F.conv2d(x, w, p[conv + "/bias"], stride=stride, padding=1))
-            x = q(torch.relu(_bn_train(x, p, bn, stats, channels_last=False, unbiased_moving=unbiased_4d)))
+            x = force(conv, q(torch.relu(_bn_train(x, p, bn, stats, channels_last=False, unbiased_moving=unbiased_4d))))
         wt = p[tname + "/kernel"].permute(3, 2, 0, 1)
-        ups.append(q(F.conv_transpose2d(x, wt, p[tname + "/bias"], stride=s, padding=(k - s) // 2)))
+        ups.append(force(tname, q(F.conv_transpose2d(x, wt, p[tname + "/bias"], stride=s, padding=(k - s) // 2))))
     cat = torch.cat(ups, dim=1)
     outs = []
     for head in ("ClassificationLayer", "RegressionLayer"):
         w = p[head + "/kernel"].permute(3, 2, 0, 1)
-        outs.append(F.conv2d(cat, w, p[head + "/bias"]).permute(0, 2, 3, 1))
+        outs.append(force(head, F.conv2d(cat, w, p[head + "/bias"]).permute(0, 2, 3, 1)))
     return outs[0], outs[1]
 
 
