@@ -1,6 +1,7 @@
 """The training-step oracle (oracle/train_oracle.py; reference model_training.py:222-257, 295-299): consistency with the
 inference oracles, gradients against finite differences, the Keras SGD formula, and that fit() steps reduce the loss."""
 import numpy as np
+import pytest
 import torch
 
 from lisec_b200.weights import synthetic_model_pack
@@ -147,3 +148,32 @@ def test_vfe_on_rows_with_multiplicities_equals_the_dense_graph():
     g2 = torch.autograd.grad((grid2 * gw[0]).sum(), [p2[k] for k in names])
     for k, a, b in zip(names, g1, g2):
         assert float((a - b).abs().max()) <= 1e-10 * max(1.0, float(a.abs().max())), k
+
+
+def test_teacher_forcing_replaces_values_and_keeps_the_gradient_path():
+    """network_forward_train(teacher=...): the straight-through device the GPU backward-chain gate is built on
+    (tests/test_gpu_train_network.py). Forcing the oracle's OWN outputs changes nothing; forcing other values moves the
+    loss residual (and with it every gradient) while the gradient still reaches the layers in front of the forced one."""
+    from lisec_b200.weights import synthetic_network_pack
+
+    pack = synthetic_network_pack(1)
+    g = torch.Generator().manual_seed(0)
+    grid = torch.rand((1, 8, 8, 16, 64), generator=g, dtype=torch.float64)
+    yc = torch.rand((1, 4, 8, 2), generator=g, dtype=torch.float64)
+    yr = torch.rand((1, 4, 8, 14), generator=g, dtype=torch.float64)
+
+    def run(teacher):
+        p = TO.to_params(pack)
+        prob, reg = TO.network_forward_train(grid, p, {}, teacher=teacher)
+        loss = TO.loss_mse2(prob, reg, yc, yr)
+        names = ["conv3d/kernel", "conv2d_7/kernel", "ClassificationLayer/bias"]
+        return prob.detach(), reg.detach(), float(loss.detach()), torch.autograd.grad(loss, [p[k] for k in names])
+
+    prob, reg, loss, grads = run(None)
+    _, _, loss_same, grads_same = run({"ClassificationLayer": prob, "RegressionLayer": reg})
+    assert loss_same == loss and all(torch.equal(a, b) for a, b in zip(grads, grads_same))
+    p2, _, loss_forced, grads_forced = run({"ClassificationLayer": prob + 0.5})
+    assert torch.equal(p2, prob + 0.5) and loss_forced != loss
+    assert float(grads_forced[0].abs().max()) > 0 and not torch.allclose(grads_forced[0], grads[0])
+    with pytest.raises(ValueError):
+        run({"conv2d_7": prob})
