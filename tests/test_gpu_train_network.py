@@ -151,18 +151,24 @@ def test_chain_gradients_are_the_exact_gradients_at_the_chains_own_operating_poi
     grid = torch.rand((B, 8, nx, ny, 64), generator=g).to(torch.bfloat16)
     yc = torch.randint(0, 3, (B, nx // 2, ny // 2, 2), generator=g).float()
     yr = torch.randn((B, nx // 2, ny // 2, 14), generator=g) * 0.5
-    net = DenseNetworkTrainer(pack, B, nx, ny)
+    net = DenseNetworkTrainer(pack, B, nx, ny, need_grid_grad=True)
     net.forward(grid.cuda())
     loss = net.loss_and_backward(yc.cuda(), yr.cuda())
     torch.cuda.synchronize()
 
     p = TO.to_params(pack)
-    want_p, want_r = TO.network_forward_train(grid.double(), p, {}, teacher=gpu_activations(net), bf16_activations=bf16_oracle)
+    grid64 = grid.double().requires_grad_()
+    want_p, want_r = TO.network_forward_train(grid64, p, {}, teacher=gpu_activations(net), bf16_activations=bf16_oracle)
     want_loss = TO.loss_mse2(want_p, want_r, yc.double(), yr.double())
     assert abs(float(loss) - float(want_loss.detach())) <= 1e-5 * float(want_loss.detach())  # same outputs, same loss
     names = [k for k, t in p.items() if t.requires_grad]
-    grads = dict(zip(names, torch.autograd.grad(want_loss, [p[k] for k in names])))
+    all_grads = torch.autograd.grad(want_loss, [p[k] for k in names] + [grid64])
+    grads = dict(zip(names, all_grads[:-1]))
     worst, cosines, ratios = compare_gradients(net, grads, rel_l2, verbose=False)
+    # d loss / d grid: what the VFE stack's backward pass receives from this chain (TrainStep)
+    worst["d loss / d grid"] = rel_l2(net.grid_grad, all_grads[-1])
+    gg, ww = net.grid_grad.double().cpu().reshape(-1), all_grads[-1].reshape(-1)
+    cosines["d loss / d grid"] = float((gg * ww).sum() / (gg.norm() * ww.norm()))
     bar, cos_bar = (2e-2, 0.9995) if bf16_oracle else (0.2, 0.98)
     bad = {k: (round(worst[k], 4), round(cosines[k], 4)) for k in worst if worst[k] > bar or cosines[k] < cos_bar}
     print("teacher-forced (bf16 oracle %s): worst rel-L2 %.3e (%s), median %.3e, min cosine %.4f" %
