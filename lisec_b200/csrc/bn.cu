@@ -132,20 +132,49 @@ __global__ void __launch_bounds__(kBnThreads)
 }
 
 // MODE 0: statistics -> (mean, invstd, a, b) and the moving statistics. MODE 1: (dgamma, dbeta, c_mean_g, c_mean_gx).
+// One block of kBnFinThreads threads: thread (slice s, channel c) adds the partials of blocks s, s + S, s + 2S, ... (four
+// independent running sums, combined in a fixed order, so that the loads overlap instead of queueing behind one dependent
+// chain of float64 adds — a single thread per channel walking all ~1200 slots took 100+ us per call, 40 % of a training
+// step), then thread (0, c) adds the S slice sums in order. The summation order is fixed: results are bit-reproducible.
+constexpr int kBnFinThreads = 1024;
 template <int MODE>
-__global__ void __launch_bounds__(kBnMaxC)
+__global__ void __launch_bounds__(kBnFinThreads)
     bn_finalize_kernel(const double* __restrict__ partial, int blocks, long long P, int C, float eps, float momentum,
                        const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ o0,
                        float* __restrict__ o1, float* __restrict__ o2, float* __restrict__ o3,
                        float* __restrict__ moving_mean, float* __restrict__ moving_var) {
   pdl_launch_dependents();
   pdl_wait();
-  const int c = threadIdx.x;
-  if (c >= C) return;
+  __shared__ double sa[kBnFinThreads], sb[kBnFinThreads];
+  const int S = kBnFinThreads / C;  // slices (C <= 256: S >= 4)
+  const int c = threadIdx.x % C, sl = threadIdx.x / C;
   double a = 0.0, b = 0.0;
-  for (int g = 0; g < blocks; ++g) {
-    a += partial[((long long)g * 2 + 0) * C + c];
-    b += partial[((long long)g * 2 + 1) * C + c];
+  if (sl < S) {
+    double a4[4] = {0.0, 0.0, 0.0, 0.0}, b4[4] = {0.0, 0.0, 0.0, 0.0};
+    int g = sl;
+    for (; g + 3 * S < blocks; g += 4 * S) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a4[u] += __ldcg(partial + ((long long)(g + u * S) * 2 + 0) * C + c);
+        b4[u] += __ldcg(partial + ((long long)(g + u * S) * 2 + 1) * C + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u)  // at most three slots are left
+      if (g + u * S < blocks) {
+        a4[u] += __ldcg(partial + ((long long)(g + u * S) * 2 + 0) * C + c);
+        b4[u] += __ldcg(partial + ((long long)(g + u * S) * 2 + 1) * C + c);
+      }
+    a = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+    b = (b4[0] + b4[1]) + (b4[2] + b4[3]);
+  }
+  sa[threadIdx.x] = a;
+  sb[threadIdx.x] = b;
+  __syncthreads();
+  if (sl != 0) return;
+  for (int k = 1; k < S; ++k) {
+    a += sa[k * C + c];
+    b += sb[k * C + c];
   }
   if (MODE == 0) {
     const double mean = a / (double)P, var = fmax(b / (double)P - mean * mean, 0.0);
@@ -264,7 +293,7 @@ int32_t lisec_bn_train_forward(const void* x, int64_t positions, int32_t channel
   cudaError_t e = launch_pdl(bn_reduce_kernel<0>, dim3(blocks), dim3(kBnThreads), 0, st, xb, xb, xb, (const float*)mean,
                              (const float*)invstd, (long long)positions, (int)channels, 0, part);
   if (e == cudaSuccess)
-    e = launch_pdl(bn_finalize_kernel<0>, dim3(1), dim3(kBnMaxC), 0, st, (const double*)part, blocks, (long long)positions,
+    e = launch_pdl(bn_finalize_kernel<0>, dim3(1), dim3(kBnFinThreads), 0, st, (const double*)part, blocks, (long long)positions,
                    (int)channels, eps, momentum, gamma, beta, mean, invstd, scale, shift, moving_mean, moving_var);
   const long long n8 = positions * channels / 8;
   long long ab = (n8 + kBnThreads - 1) / kBnThreads;
@@ -287,7 +316,7 @@ int32_t lisec_channel_sums(const void* x, int64_t positions, int32_t channels, f
   cudaError_t e = launch_pdl(bn_reduce_kernel<0>, dim3(blocks), dim3(kBnThreads), 0, st, xb, xb, xb, (const float*)sums,
                              (const float*)sums, (long long)positions, (int)channels, 0, part);
   if (e == cudaSuccess)
-    e = launch_pdl(bn_finalize_kernel<2>, dim3(1), dim3(kBnMaxC), 0, st, (const double*)part, blocks, (long long)positions,
+    e = launch_pdl(bn_finalize_kernel<2>, dim3(1), dim3(kBnFinThreads), 0, st, (const double*)part, blocks, (long long)positions,
                    (int)channels, 0.f, 0.f, (const float*)sums, (const float*)sums, sums, sums, sums, sums,
                    (float*)nullptr, (float*)nullptr);
   if (e != cudaSuccess) return bn_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
@@ -314,7 +343,7 @@ static int32_t bn_backward_impl(const void* x, const void* dy, int dy_f32, const
                          : launch_pdl(bn_reduce_kernel<1, false>, dim3(blocks), dim3(kBnThreads), 0, st, xb, dyb, yb, mean, invstd,
                                       (long long)positions, (int)channels, (int)relu, part);
   if (e == cudaSuccess)
-    e = launch_pdl(bn_finalize_kernel<1>, dim3(1), dim3(kBnMaxC), 0, st, (const double*)part, blocks, (long long)positions,
+    e = launch_pdl(bn_finalize_kernel<1>, dim3(1), dim3(kBnFinThreads), 0, st, (const double*)part, blocks, (long long)positions,
                    (int)channels, 0.f, 0.f, gamma, gamma, dgamma, dbeta, mean_g, mean_gx, (float*)nullptr, (float*)nullptr);
   const long long n8 = positions * channels / 8;
   long long ab = (n8 + kBnThreads - 1) / kBnThreads;

@@ -185,6 +185,31 @@ __global__ void __launch_bounds__(kTrThreads) tr_colsum_kernel(const float* __re
   }
 }
 
+// column c of the blocks' partial sums [nblocks][2][C], in a fixed order: eight independent running sums (blocks b = 0..7
+// mod 8) keep eight loads in flight instead of one dependent chain of float64 adds, then one fixed-order combination
+template <int C>
+__device__ __forceinline__ void sum_partials(const double* __restrict__ partial, int nblocks, int c, double& sa, double& sb) {
+  double a8[8], b8[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) a8[u] = b8[u] = 0.0;
+  int b = 0;
+  for (; b + 7 < nblocks; b += 8) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a8[u] += partial[(size_t)(b + u) * 2 * C + c];
+      b8[u] += partial[(size_t)(b + u) * 2 * C + C + c];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 7; ++u)
+    if (b + u < nblocks) {
+      a8[u] += partial[(size_t)(b + u) * 2 * C + c];
+      b8[u] += partial[(size_t)(b + u) * 2 * C + C + c];
+    }
+  sa = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
+  sb = ((b8[0] + b8[1]) + (b8[2] + b8[3])) + ((b8[4] + b8[5]) + (b8[6] + b8[7]));
+}
+
 // batch statistics -> folded BN, moving statistics (momentum 0.99; the biased batch variance: these 6-D inputs take
 // Keras's non-fused BatchNormalization path)
 template <int C>
@@ -195,10 +220,7 @@ __global__ void tr_stats_finalize_kernel(const double* __restrict__ partial, int
   const int c = threadIdx.x;
   if (c >= C) return;
   double sa = 0.0, sb = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    sa += partial[(size_t)b * 2 * C + c];
-    sb += partial[(size_t)b * 2 * C + C + c];
-  }
+  sum_partials<C>(partial, nblocks, c, sa, sb);
   const double M = (double)ncells * (double)T;
   const double mean = sa / M, var = fmax(sb / M - mean * mean, 0.0);
   const double inv = 1.0 / sqrt(var + (double)eps);
@@ -220,10 +242,7 @@ __global__ void tr_bn_bwd_finalize_kernel(const double* __restrict__ partial, in
   const int c = threadIdx.x;
   if (c >= C) return;
   double sa = 0.0, sb = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    sa += partial[(size_t)b * 2 * C + c];
-    sb += partial[(size_t)b * 2 * C + C + c];
-  }
+  sum_partials<C>(partial, nblocks, c, sa, sb);
   const double M = (double)ncells * (double)T;
   dgamma[c] = (float)sb;
   dbeta[c] = (float)sa;
@@ -442,9 +461,16 @@ __global__ void __launch_bounds__(kTrThreads) tr_wgrad_kernel(const float* __res
 __global__ void tr_wgrad_reduce_kernel(const float* __restrict__ wpartial, int nblocks, int E, float* __restrict__ dW) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
-  double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += (double)wpartial[(size_t)b * E + e];
-  dW[e] = (float)s;
+  double s4[4] = {0.0, 0.0, 0.0, 0.0};  // four loads in flight; fixed order
+  int b = 0;
+  for (; b + 3 < nblocks; b += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s4[u] += (double)wpartial[(size_t)(b + u) * E + e];
+  }
+#pragma unroll
+  for (int u = 0; u < 3; ++u)
+    if (b + u < nblocks) s4[u] += (double)wpartial[(size_t)(b + u) * E + e];
+  dW[e] = (float)((s4[0] + s4[1]) + (s4[2] + s4[3]));
 }
 
 __global__ void tr_copy_bg_kernel(const float* __restrict__ pooled, const long long* __restrict__ totals,

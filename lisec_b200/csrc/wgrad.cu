@@ -252,11 +252,29 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   pdl_wait();
   const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 * 4 >= n) return;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int g = 0; g < slices; ++g) {
-    const float4 v = __ldcs(reinterpret_cast<const float4*>(partial + (long long)g * n) + i4);
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  // four running sums (slices g = 0, 1, 2, 3 mod 4) so that four loads are in flight; combined in a fixed order
+  float4 a4[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) a4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int g = 0;
+  for (; g + 3 < slices; g += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(partial + (long long)(g + u) * n) + i4);
+      a4[u].x += v.x; a4[u].y += v.y; a4[u].z += v.z; a4[u].w += v.w;
+    }
   }
+#pragma unroll
+  for (int u = 0; u < 3; ++u)
+    if (g + u < slices) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(partial + (long long)(g + u) * n) + i4);
+      a4[u].x += v.x; a4[u].y += v.y; a4[u].z += v.z; a4[u].w += v.w;
+    }
+  float4 acc;
+  acc.x = (a4[0].x + a4[1].x) + (a4[2].x + a4[3].x);
+  acc.y = (a4[0].y + a4[1].y) + (a4[2].y + a4[3].y);
+  acc.z = (a4[0].z + a4[1].z) + (a4[2].z + a4[3].z);
+  acc.w = (a4[0].w + a4[1].w) + (a4[2].w + a4[3].w);
   reinterpret_cast<float4*>(dw)[i4] = acc;
 }
 

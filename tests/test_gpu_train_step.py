@@ -60,6 +60,36 @@ def test_train_step_loss_matches_the_oracle_and_descends():
         assert after[k].shape == pack[k].shape and np.isfinite(after[k]).all(), k
 
 
+def test_graph_replay_is_the_eager_step():
+    """TrainStep(use_graph=True) captures the dense network's forward + loss + backward and the operand refresh after one
+    eager step and replays them: the same kernels on the same buffers — the weights after five steps must be IDENTICAL to
+    the eager run's (every reduction that feeds a gradient has a fixed order); the reported loss is a float64 sum built
+    with atomics, equal to rounding."""
+    from lisec_b200.train import TrainStep
+    from lisec_b200.weights import synthetic_model_pack
+
+    nx, ny, nz, B = 24, 40, 8, 2
+    pack = {k: np.asarray(v, np.float32) for k, v in synthetic_model_pack(4).items()}
+    batches = []
+    for i in range(5):  # a different batch every step: replays must read the new inputs
+        clouds = small_clouds(B, 10 + i)
+        g = torch.Generator(device="cpu").manual_seed(i)
+        batches.append((np.concatenate(clouds), np.cumsum([0] + [len(c) for c in clouds]).tolist(),
+                        torch.randint(0, 3, (B, nx // 2, ny // 2, 2), generator=g).float().cuda(),
+                        (torch.randn((B, nx // 2, ny // 2, 14), generator=g) * 0.5).cuda()))
+    out = {}
+    for mode in (False, True):
+        step = TrainStep(pack, batch=B, max_points=max(len(b[0]) for b in batches), nx=nx, ny=ny, nz=nz, lr=0.002,
+                         use_graph=mode)
+        losses = [float(step.step(*b)) for b in batches]
+        assert (step._graph_dense is not None) == mode
+        out[mode] = (losses, step.to_pack())
+        step.close()
+    assert np.allclose(out[False][0], out[True][0], rtol=1e-12, atol=0), (out[False][0], out[True][0])
+    for k in pack:
+        assert np.array_equal(out[False][1][k], out[True][1][k]), k
+
+
 def test_compat_train_runs_and_saves_a_loadable_model(tmp_path):
     from lisec_b200 import compat
     from lisec_b200 import constants as K
