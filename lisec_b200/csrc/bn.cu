@@ -132,11 +132,13 @@ __global__ void __launch_bounds__(kBnThreads)
 }
 
 // MODE 0: statistics -> (mean, invstd, a, b) and the moving statistics. MODE 1: (dgamma, dbeta, c_mean_g, c_mean_gx).
-// One block of kBnFinThreads threads: thread (slice s, channel c) adds the partials of blocks s, s + S, s + 2S, ... (four
-// independent running sums, combined in a fixed order, so that the loads overlap instead of queueing behind one dependent
-// chain of float64 adds — a single thread per channel walking all ~1200 slots took 100+ us per call, 40 % of a training
-// step), then thread (0, c) adds the S slice sums in order. The summation order is fixed: results are bit-reproducible.
+// Grid = C / 8 blocks of kBnFinThreads threads; a block owns 8 channels (64 contiguous bytes of every slot) and its
+// thread (slice s, channel c) adds the partials of blocks s, s + S, s + 2S, ... (S = 128 slices, four independent running
+// sums combined in a fixed order, so that the loads overlap instead of queueing behind one dependent chain of float64
+// adds), then thread (0, c) adds the S slice sums in order. One thread per channel walking all ~1200 slots — the first
+// version — took 100+ us per call, 40 % of a training step. The summation order is fixed: results are bit-reproducible.
 constexpr int kBnFinThreads = 1024;
+constexpr int kBnFinChannels = 8;
 template <int MODE>
 __global__ void __launch_bounds__(kBnFinThreads)
     bn_finalize_kernel(const double* __restrict__ partial, int blocks, long long P, int C, float eps, float momentum,
@@ -146,10 +148,11 @@ __global__ void __launch_bounds__(kBnFinThreads)
   pdl_launch_dependents();
   pdl_wait();
   __shared__ double sa[kBnFinThreads], sb[kBnFinThreads];
-  const int S = kBnFinThreads / C;  // slices (C <= 256: S >= 4)
-  const int c = threadIdx.x % C, sl = threadIdx.x / C;
+  constexpr int S = kBnFinThreads / kBnFinChannels;
+  const int lc = threadIdx.x % kBnFinChannels, sl = threadIdx.x / kBnFinChannels;
+  const int c = blockIdx.x * kBnFinChannels + lc;
   double a = 0.0, b = 0.0;
-  if (sl < S) {
+  {
     double a4[4] = {0.0, 0.0, 0.0, 0.0}, b4[4] = {0.0, 0.0, 0.0, 0.0};
     int g = sl;
     for (; g + 3 * S < blocks; g += 4 * S) {
@@ -173,8 +176,8 @@ __global__ void __launch_bounds__(kBnFinThreads)
   __syncthreads();
   if (sl != 0) return;
   for (int k = 1; k < S; ++k) {
-    a += sa[k * C + c];
-    b += sb[k * C + c];
+    a += sa[k * kBnFinChannels + lc];
+    b += sb[k * kBnFinChannels + lc];
   }
   if (MODE == 0) {
     const double mean = a / (double)P, var = fmax(b / (double)P - mean * mean, 0.0);
@@ -293,7 +296,7 @@ int32_t lisec_bn_train_forward(const void* x, int64_t positions, int32_t channel
   cudaError_t e = launch_pdl(bn_reduce_kernel<0>, dim3(blocks), dim3(kBnThreads), 0, st, xb, xb, xb, (const float*)mean,
                              (const float*)invstd, (long long)positions, (int)channels, 0, part);
   if (e == cudaSuccess)
-    e = launch_pdl(bn_finalize_kernel<0>, dim3(1), dim3(kBnFinThreads), 0, st, (const double*)part, blocks, (long long)positions,
+    e = launch_pdl(bn_finalize_kernel<0>, dim3(channels / kBnFinChannels), dim3(kBnFinThreads), 0, st, (const double*)part, blocks, (long long)positions,
                    (int)channels, eps, momentum, gamma, beta, mean, invstd, scale, shift, moving_mean, moving_var);
   const long long n8 = positions * channels / 8;
   long long ab = (n8 + kBnThreads - 1) / kBnThreads;
@@ -316,7 +319,7 @@ int32_t lisec_channel_sums(const void* x, int64_t positions, int32_t channels, f
   cudaError_t e = launch_pdl(bn_reduce_kernel<0>, dim3(blocks), dim3(kBnThreads), 0, st, xb, xb, xb, (const float*)sums,
                              (const float*)sums, (long long)positions, (int)channels, 0, part);
   if (e == cudaSuccess)
-    e = launch_pdl(bn_finalize_kernel<2>, dim3(1), dim3(kBnFinThreads), 0, st, (const double*)part, blocks, (long long)positions,
+    e = launch_pdl(bn_finalize_kernel<2>, dim3(channels / kBnFinChannels), dim3(kBnFinThreads), 0, st, (const double*)part, blocks, (long long)positions,
                    (int)channels, 0.f, 0.f, (const float*)sums, (const float*)sums, sums, sums, sums, sums,
                    (float*)nullptr, (float*)nullptr);
   if (e != cudaSuccess) return bn_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
@@ -343,7 +346,7 @@ static int32_t bn_backward_impl(const void* x, const void* dy, int dy_f32, const
                          : launch_pdl(bn_reduce_kernel<1, false>, dim3(blocks), dim3(kBnThreads), 0, st, xb, dyb, yb, mean, invstd,
                                       (long long)positions, (int)channels, (int)relu, part);
   if (e == cudaSuccess)
-    e = launch_pdl(bn_finalize_kernel<1>, dim3(1), dim3(kBnFinThreads), 0, st, (const double*)part, blocks, (long long)positions,
+    e = launch_pdl(bn_finalize_kernel<1>, dim3(channels / kBnFinChannels), dim3(kBnFinThreads), 0, st, (const double*)part, blocks, (long long)positions,
                    (int)channels, 0.f, 0.f, gamma, gamma, dgamma, dbeta, mean_g, mean_gx, (float*)nullptr, (float*)nullptr);
   const long long n8 = positions * channels / 8;
   long long ab = (n8 + kBnThreads - 1) / kBnThreads;

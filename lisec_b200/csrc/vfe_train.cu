@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kTrThreads) tr_dense_kernel(const float* __res
                                                               const int* __restrict__ seg, const float* __restrict__ W,
                                                               const long long* __restrict__ totals,
                                                               float* __restrict__ u) {
-  __shared__ float sW[CIN * COUT];
+  __shared__ __align__(16) float sW[CIN * COUT];
   for (int i = threadIdx.x; i < CIN * COUT; i += kTrThreads) sW[i] = W[i];
   __syncthreads();
   const long long R = totals[TOT_ROWS] + 1;
@@ -131,12 +131,27 @@ __global__ void __launch_bounds__(kTrThreads) tr_dense_kernel(const float* __res
     for (int i = 0; i < CIN; ++i) in[i] = x0[(size_t)r * CIN + i];
   }
   float* dst = u + (size_t)r * COUT;
-#pragma unroll 4
-  for (int c = 0; c < COUT; ++c) {
-    float acc = 0.f;
+  // eight outputs at a time: two 16-byte broadcast loads of the weights per eight FMAs (summation order over i unchanged)
+#pragma unroll 1
+  for (int c = 0; c < COUT; c += 8) {
+    float acc[8];
 #pragma unroll
-    for (int i = 0; i < CIN; ++i) acc = fmaf(in[i], sW[i * COUT + c], acc);
-    dst[c] = acc;
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < CIN; ++i) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&sW[i * COUT + c]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&sW[i * COUT + c + 4]);
+      acc[0] = fmaf(in[i], w0.x, acc[0]);
+      acc[1] = fmaf(in[i], w0.y, acc[1]);
+      acc[2] = fmaf(in[i], w0.z, acc[2]);
+      acc[3] = fmaf(in[i], w0.w, acc[3]);
+      acc[4] = fmaf(in[i], w1.x, acc[4]);
+      acc[5] = fmaf(in[i], w1.y, acc[5]);
+      acc[6] = fmaf(in[i], w1.z, acc[6]);
+      acc[7] = fmaf(in[i], w1.w, acc[7]);
+    }
+    *reinterpret_cast<float4*>(dst + c) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(dst + c + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
 }
 
@@ -370,9 +385,9 @@ __global__ void __launch_bounds__(kTrThreads) tr_dense_bwd_kernel(const float* _
                                                                   const long long* __restrict__ totals,
                                                                   float* __restrict__ gy, float* __restrict__ ggath,
                                                                   float* __restrict__ gdir) {
-  __shared__ float sW[CIN * COUT];
+  __shared__ __align__(16) float sWT[COUT * CIN];  // transposed: [c][i], so that four input channels are one 16-byte load
   __shared__ float sBn[6 * COUT];
-  for (int i = threadIdx.x; i < CIN * COUT; i += kTrThreads) sW[i] = W[i];
+  for (int e = threadIdx.x; e < CIN * COUT; e += kTrThreads) sWT[(e % COUT) * CIN + e / COUT] = W[e];
   for (int i = threadIdx.x; i < 6 * COUT; i += kTrThreads) sBn[i] = bn[i];
   __syncthreads();
   const long long R = totals[TOT_ROWS] + 1;
@@ -393,7 +408,13 @@ __global__ void __launch_bounds__(kTrThreads) tr_dense_bwd_kernel(const float* _
     g[c] = gu;
     if (CONCAT) {
 #pragma unroll
-      for (int i = 0; i < CIN; ++i) gin[i] = fmaf(gu, sW[i * COUT + c], gin[i]);
+      for (int i = 0; i < CIN; i += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&sWT[c * CIN + i]);
+        gin[i] = fmaf(gu, w4.x, gin[i]);
+        gin[i + 1] = fmaf(gu, w4.y, gin[i + 1]);
+        gin[i + 2] = fmaf(gu, w4.z, gin[i + 2]);
+        gin[i + 3] = fmaf(gu, w4.w, gin[i + 3]);
+      }
     }
   }
   if (CONCAT) {
@@ -415,13 +436,23 @@ __global__ void __launch_bounds__(kTrThreads) tr_wgrad_kernel(const float* __res
                                                               const int* __restrict__ seg, const float* __restrict__ gu,
                                                               const long long* __restrict__ totals,
                                                               float* __restrict__ wpartial) {
-  constexpr int RB = 32, E = CIN * COUT, PER = (E + kTrThreads - 1) / kTrThreads;
-  __shared__ float sIn[RB][CIN + 1];
-  __shared__ float sG[RB][COUT + 1];
+  // a thread owns a T x T block of the matrix (T = 4 for 64 x 64, 2 for 32 x 32: 256 threads cover it), so that one row of
+  // the chunk costs two vector loads from shared memory per T * T FMAs; the 6 x 16 first layer keeps one entry per thread.
+  // Every entry still adds its rows in ascending order: the sums are bit-identical to the one-entry-per-thread version.
+  constexpr int RB = 32, E = CIN * COUT;
+  constexpr int T = E == 16 * kTrThreads ? 4 : (E == 4 * kTrThreads ? 2 : 1);
+  constexpr int PADI = T > 1 ? 4 : 1;
+  __shared__ __align__(16) float sIn[RB][CIN + PADI];
+  __shared__ __align__(16) float sG[RB][COUT + PADI];
   const long long R = totals[TOT_ROWS] + 1;
-  float acc[PER];
+  float acc[T][T];
 #pragma unroll
-  for (int k = 0; k < PER; ++k) acc[k] = 0.f;
+  for (int a = 0; a < T; ++a)
+#pragma unroll
+    for (int b = 0; b < T; ++b) acc[a][b] = 0.f;
+  const int i0 = T > 1 ? (threadIdx.x / (COUT / T)) * T : threadIdx.x / COUT;
+  const int j0 = T > 1 ? (threadIdx.x % (COUT / T)) * T : threadIdx.x % COUT;
+  const bool mine = T > 1 || threadIdx.x < E;
   for (long long r0 = (long long)blockIdx.x * RB; r0 < R; r0 += (long long)gridDim.x * RB) {
     __syncthreads();
     for (int t = threadIdx.x; t < RB * CIN; t += kTrThreads) {
@@ -440,22 +471,36 @@ __global__ void __launch_bounds__(kTrThreads) tr_wgrad_kernel(const float* __res
       sG[rr][j] = r < R ? gu[(size_t)r * COUT + j] : 0.f;
     }
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-      const int e = threadIdx.x + k * kTrThreads;
-      if (e < E) {
-        const int i = e / COUT, j = e % COUT;
-        float a = acc[k];
+    if (mine) {
 #pragma unroll 8
-        for (int rr = 0; rr < RB; ++rr) a = fmaf(sIn[rr][i], sG[rr][j], a);
-        acc[k] = a;
+      for (int rr = 0; rr < RB; ++rr) {
+        float xi[T], gj[T];
+        if (T == 4) {
+          const float4 x4 = *reinterpret_cast<const float4*>(&sIn[rr][i0]);
+          const float4 g4 = *reinterpret_cast<const float4*>(&sG[rr][j0]);
+          xi[0] = x4.x; xi[1] = x4.y; xi[T - 2] = x4.z; xi[T - 1] = x4.w;
+          gj[0] = g4.x; gj[1] = g4.y; gj[T - 2] = g4.z; gj[T - 1] = g4.w;
+        } else if (T == 2) {
+          const float2 x2 = *reinterpret_cast<const float2*>(&sIn[rr][i0]);
+          const float2 g2 = *reinterpret_cast<const float2*>(&sG[rr][j0]);
+          xi[0] = x2.x; xi[T - 1] = x2.y;
+          gj[0] = g2.x; gj[T - 1] = g2.y;
+        } else {
+          xi[0] = sIn[rr][i0];
+          gj[0] = sG[rr][j0];
+        }
+#pragma unroll
+        for (int a = 0; a < T; ++a)
+#pragma unroll
+          for (int b = 0; b < T; ++b) acc[a][b] = fmaf(xi[a], gj[b], acc[a][b]);
       }
     }
   }
+  if (mine) {
 #pragma unroll
-  for (int k = 0; k < PER; ++k) {
-    const int e = threadIdx.x + k * kTrThreads;
-    if (e < E) wpartial[(size_t)blockIdx.x * E + e] = acc[k];
+    for (int a = 0; a < T; ++a)
+#pragma unroll
+      for (int b = 0; b < T; ++b) wpartial[(size_t)blockIdx.x * E + (size_t)(i0 + a) * COUT + j0 + b] = acc[a][b];
   }
 }
 __global__ void tr_wgrad_reduce_kernel(const float* __restrict__ wpartial, int nblocks, int E, float* __restrict__ dW) {
