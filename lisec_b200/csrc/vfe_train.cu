@@ -122,9 +122,10 @@ __global__ void __launch_bounds__(kTrThreads) tr_dense_kernel(const float* __res
     const float* p = pooled_prev + (size_t)seg[r] * H;
     const float* q = h_prev + (size_t)r * H;
 #pragma unroll
-    for (int i = 0; i < H; ++i) {
-      in[i] = p[i];
-      in[H + i] = q[i];
+    for (int i = 0; i < H; i += 4) {  // 16-byte pieces of the two half rows
+      const float4 p4 = *reinterpret_cast<const float4*>(p + i), q4 = *reinterpret_cast<const float4*>(q + i);
+      in[i] = p4.x; in[i + 1] = p4.y; in[i + 2] = p4.z; in[i + 3] = p4.w;
+      in[H + i] = q4.x; in[H + i + 1] = q4.y; in[H + i + 2] = q4.z; in[H + i + 3] = q4.w;
     }
   } else {
 #pragma unroll
@@ -401,28 +402,40 @@ __global__ void __launch_bounds__(kTrThreads) tr_dense_bwd_kernel(const float* _
   }
   float* g = gy + (size_t)r * COUT;
   const float* ur = u + (size_t)r * COUT;
-#pragma unroll 2
-  for (int c = 0; c < COUT; ++c) {
-    const float xhat = (ur[c] - sBn[2 * COUT + c]) * sBn[3 * COUT + c];
-    const float gu = sBn[c] * (g[c] - wr * sBn[4 * COUT + c] - wr * xhat * sBn[5 * COUT + c]);
-    g[c] = gu;
+  // the row in 16-byte pieces (a thread's row is 4 * COUT contiguous bytes: scalar accesses would fetch every sector 8 times)
+#pragma unroll 1
+  for (int c = 0; c < COUT; c += 4) {
+    const float4 u4 = *reinterpret_cast<const float4*>(ur + c);
+    const float4 g4 = *reinterpret_cast<const float4*>(g + c);
+    const float uu[4] = {u4.x, u4.y, u4.z, u4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+    float guv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float xhat = (uu[k] - sBn[2 * COUT + c + k]) * sBn[3 * COUT + c + k];
+      guv[k] = sBn[c + k] * (gg[k] - wr * sBn[4 * COUT + c + k] - wr * xhat * sBn[5 * COUT + c + k]);
+    }
+    *reinterpret_cast<float4*>(g + c) = make_float4(guv[0], guv[1], guv[2], guv[3]);
     if (CONCAT) {
 #pragma unroll
-      for (int i = 0; i < CIN; i += 4) {
-        const float4 w4 = *reinterpret_cast<const float4*>(&sWT[c * CIN + i]);
-        gin[i] = fmaf(gu, w4.x, gin[i]);
-        gin[i + 1] = fmaf(gu, w4.y, gin[i + 1]);
-        gin[i + 2] = fmaf(gu, w4.z, gin[i + 2]);
-        gin[i + 3] = fmaf(gu, w4.w, gin[i + 3]);
+      for (int k = 0; k < 4; ++k) {
+        const float gu = guv[k];
+#pragma unroll
+        for (int i = 0; i < CIN; i += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(&sWT[(c + k) * CIN + i]);
+          gin[i] = fmaf(gu, w4.x, gin[i]);
+          gin[i + 1] = fmaf(gu, w4.y, gin[i + 1]);
+          gin[i + 2] = fmaf(gu, w4.z, gin[i + 2]);
+          gin[i + 3] = fmaf(gu, w4.w, gin[i + 3]);
+        }
       }
     }
   }
   if (CONCAT) {
     constexpr int H = CIN / 2;
 #pragma unroll
-    for (int i = 0; i < H; ++i) {
-      ggath[(size_t)r * H + i] = gin[i];
-      gdir[(size_t)r * H + i] = gin[H + i];
+    for (int i = 0; i < H; i += 4) {
+      *reinterpret_cast<float4*>(ggath + (size_t)r * H + i) = make_float4(gin[i], gin[i + 1], gin[i + 2], gin[i + 3]);
+      *reinterpret_cast<float4*>(gdir + (size_t)r * H + i) = make_float4(gin[H + i], gin[H + i + 1], gin[H + i + 2], gin[H + i + 3]);
     }
   }
 }
