@@ -1102,6 +1102,7 @@ class TrainStep:
 
         self.group, self.bucket_elems, self.batch = group, bucket_elems, batch
         self.use_graph = bool(use_graph)
+        self.collective = True  # False: skip the all-reduce (a measurement aid: the step's compute alone)
         self._graph_dense = self._graph_refresh = None
         self._steps = 0
         dev = torch.device("cuda", device)
@@ -1116,6 +1117,7 @@ class TrainStep:
                 self.vfe_params[k] = self.store.alloc(k, pack[k])
             for f in ("moving_mean", "moving_variance"):
                 self.vfe_params[b + "/" + f] = torch.from_numpy(np.ascontiguousarray(pack[b + "/" + f], dtype=np.float32)).to(dev)
+        self._vfe_end = self.store.used  # flat layout: [VFE stack | dense network]
         self.dense = DenseNetworkTrainer(pack, batch, nx, ny, nz, device=device, alloc=self.store.alloc, need_grid_grad=True)
         for k in list(self.vfe_params):
             if "moving_" not in k:
@@ -1148,12 +1150,18 @@ class TrainStep:
                 loss = self._loss.clone()
             else:
                 loss = self._dense_region(self._yc, self._yr)
-        self.vfe.backward(self._grid_grad)
-        world = 1
-        if dist.is_available() and dist.is_initialized():
+        # The collective overlaps the rest of the backward pass: the dense network's gradients (25.9 MB, all but 21 KB of the
+        # flat buffer) are complete here and their all-reduce runs on NCCL's stream WHILE the VFE stack's backward (~1.3 ms)
+        # runs on the compute stream; only the VFE stack's own 21 KB are reduced after it.
+        world, works = 1, []
+        if self.collective and dist.is_available() and dist.is_initialized():
             world = dist.get_world_size(self.group)
-            for w in allreduce_gradients(self.store.grad[:self.store.numel_padded], self.group, self.bucket_elems):
-                w.wait()
+            works = allreduce_gradients(self.store.grad[self._vfe_end:self.store.numel_padded], self.group, self.bucket_elems)
+        self.vfe.backward(self._grid_grad)
+        if world > 1:
+            works += allreduce_gradients(self.store.grad[:self._vfe_end], self.group)
+        for w in works:
+            w.wait()
         self.opt.step(world)
         if self.use_graph and self._graph_refresh is None and self._steps >= 1:
             torch.cuda.synchronize(self.dense.device)
