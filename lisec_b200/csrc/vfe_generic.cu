@@ -1,5 +1,5 @@
 // The VFE stack for EVERY graph the reference's .h5 may hold — parametric in the widths (C1, C2, C3) and in
-// the FCN variant — in plain float32 FMAs, one thread per VFE row:
+// the FCN variant — in plain float32 FMAs:
 //   POST = false  addFCN as the code stands: Dense -> BatchNormalization -> ReLU                    (model_training.py:169-174)
 //   POST = true   the line commented out at :172 switched on (the graph model.png shows):
 //                 Dense -> BatchNormalization -> Dense(units, relu, no bias)
@@ -11,10 +11,14 @@
 // voxels per tile; every non-full voxel's virtual pad row is a row of its tile with a zero input), so the pad rows need
 // no special case: they run through the stack like any other row and join their voxel's max.
 //
-// Per tile, 128 threads: thread t owns row t. A Dense layer is CIN x COUT FMAs per thread with the input row in registers
-// and the weights fetched as warp-uniform float4 loads (read-only path; the whole weight set, <= 157 KB, lives in L1/L2);
-// the outputs go to the thread's own row of a shared-memory tile, where the per-voxel max (one thread per voxel x 4
-// channels) finds them. Bound by the FP32 pipe: 39 264 MACs per row for (16, 64, 128, POST), 5 216 for (16, 32, 64).
+// Per tile, 512 threads around one shared-memory tile [128 rows][<= 128 channels (+4)]. A Dense layer is a register-tiled
+// GEMM on it: thread (row group, column group) owns 4 rows x COUT/16 columns, reads its rows' inputs as 16-byte pieces
+// from the tile and the weights as 16-byte read-only loads (the whole weight set, <= 157 KB, lives in L1/L2), and writes
+// the outputs back into the tile behind a barrier — at the column offset that leaves room for the pooled half, so that
+// Concatenate([pooling, layer]) is a layout, not a copy. The per-voxel max (one thread per voxel x 4 channels) then
+// writes the pooled half of every row of the voxel (RepeatLayer). Bound by the FP32 pipe: 39 264 MACs per row for
+// (16, 64, 128, POST), 5 216 for (16, 32, 64). (First version: one thread per row with the input row in registers and one
+// weight load per FMA — 12 TFLOP/s, bound by the L1 data pipe: profiles/vfe_generic_r2_summary.txt.)
 #include "common.cuh"
 #include "vfe_math.cuh"
 
@@ -22,8 +26,9 @@ namespace lisec {
 
 namespace {
 
-constexpr int kGenThreads = 128;  // = rows per tile
-constexpr int kGenVox = 64;       // voxels per tile
+constexpr int kGenThreads = 512;
+constexpr int kGenRows = 128;  // rows per tile
+constexpr int kGenVox = 64;    // voxels per tile
 
 template <int C1, int C2, int C3, bool POST>
 struct GenericLayout {
@@ -40,111 +45,134 @@ struct GenericLayout {
   __host__ __device__ static constexpr int b(int s) { return a(s) + cout(s); }
   __host__ __device__ static constexpr int d(int s) { return b(s) + cout(s); }
   static constexpr int total = stage_floats(0) + stage_floats(1) + stage_floats(2);
-  static constexpr int kCH = C3 > C2 ? (C3 > C1 ? C3 : C1) : (C2 > C1 ? C2 : C1);  // widest row the tile holds
-  static constexpr int kHS = kCH + 4;                                                // row stride: conflict-free float4 rows
-  static constexpr int kCP = C2 > C1 ? C2 : C1;                                      // widest pooled row that is re-read
-  static constexpr size_t smem = sizeof(float) * ((size_t)kGenThreads * kHS + (size_t)kGenVox * kCP) +
-                                 sizeof(double) * 3 * kGenVox + sizeof(int) * (kGenVox + 4);
+  static constexpr int kCW = 2 * C2 > C3 ? 2 * C2 : C3;  // widest row the tile holds: a concat input or the last output
+  static constexpr int kXS = kCW + 4;                     // row stride in floats: 16-byte rows, conflict-free
+  static constexpr size_t smem = sizeof(float) * (size_t)kGenRows * kXS + sizeof(double) * 3 * kGenVox +
+                                 sizeof(int) * (kGenVox + 4 + kGenRows);
 };
 
-// out[c] = act(affine(sum_i in[i] * W[i][c])), eight columns at a time, into the thread's shared-memory row
-template <int CIN, int COUT, bool AFFINE, bool RELU>
-__device__ __forceinline__ void row_dense(const float (&in)[CIN], const float* __restrict__ W, const float* __restrict__ a,
-                                          const float* __restrict__ b, float* __restrict__ dst) {
-#pragma unroll 1
-  for (int c = 0; c < COUT; c += 8) {
-    float acc[8];
+// T[row][out_col + c] = act(affine(sum_k T[row][in_col + k] * W[k][c])) for the tile's 128 rows, in place: every thread
+// finishes reading its input rows before anybody writes (the barrier in the middle), and the outputs are visible to all
+// when the function returns. A warp's 32 lanes are 32 column groups (16 for the 16-column first layer) and its rows are
+// the same for every lane: the input loads are pure broadcasts, a weight load covers 32 x CT contiguous floats — the L1
+// data pipe sees ~0.2 wavefronts per FMA instruction (the 4-row x 8-column tile of the previous version: ~0.6, and it
+// was what bounded the kernel, profiles/vfe_generic_r2_summary.txt). Thread = RT rows x CT columns.
+template <int CIN, int COUT, int XS, bool AFFINE, bool RELU>
+__device__ __forceinline__ void tile_dense(float* __restrict__ T, int in_col, int out_col, const float* __restrict__ W,
+                                           const float* __restrict__ a, const float* __restrict__ b, int tid) {
+  constexpr int CG = COUT >= 64 ? 32 : 16;        // column groups = lanes that differ in their columns (narrow layers: 16, two row groups per warp)
+  constexpr int CT = COUT / CG;                   // columns per thread: 4, 2 or 1
+  constexpr int RT = kGenRows / (kGenThreads / CG);  // rows per thread: 8 (4 for the first layer)
+  const int rg = tid / CG, cg = tid % CG;
+  float acc[RT][CT];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int r = 0; r < RT; ++r)
 #pragma unroll
-    for (int i = 0; i < CIN; ++i) {
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + i * COUT + c));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + i * COUT + c + 4));
-      acc[0] = fmaf(in[i], w0.x, acc[0]);
-      acc[1] = fmaf(in[i], w0.y, acc[1]);
-      acc[2] = fmaf(in[i], w0.z, acc[2]);
-      acc[3] = fmaf(in[i], w0.w, acc[3]);
-      acc[4] = fmaf(in[i], w1.x, acc[4]);
-      acc[5] = fmaf(in[i], w1.y, acc[5]);
-      acc[6] = fmaf(in[i], w1.z, acc[6]);
-      acc[7] = fmaf(in[i], w1.w, acc[7]);
+    for (int c = 0; c < CT; ++c) acc[r][c] = 0.f;
+  const float* x0 = T + (size_t)(RT * rg) * XS + in_col;
+  const float* wc = W + cg * CT;
+  auto fma_k = [&](const float (&xv)[RT], int k) {  // one input channel: CT weights, RT x CT FMAs
+    float w[CT];
+    if (CT == 4) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wc + (size_t)k * COUT));
+      w[0] = w0.x; w[1 % CT] = w0.y; w[2 % CT] = w0.z; w[3 % CT] = w0.w;  // (% CT: in bounds in the other instantiations)
+    } else if (CT == 2) {
+      const float2 w0 = __ldg(reinterpret_cast<const float2*>(wc + (size_t)k * COUT));
+      w[0] = w0.x; w[1 % CT] = w0.y;
+    } else {
+      w[0] = __ldg(wc + (size_t)k * COUT);
     }
-    if (AFFINE) {  // BatchNormalization at inference, folded on the host: y = z * a + b
-      const float4 a0 = __ldg(reinterpret_cast<const float4*>(a + c)), a1 = __ldg(reinterpret_cast<const float4*>(a + c + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + c)), b1 = __ldg(reinterpret_cast<const float4*>(b + c + 4));
-      acc[0] = fmaf(acc[0], a0.x, b0.x);
-      acc[1] = fmaf(acc[1], a0.y, b0.y);
-      acc[2] = fmaf(acc[2], a0.z, b0.z);
-      acc[3] = fmaf(acc[3], a0.w, b0.w);
-      acc[4] = fmaf(acc[4], a1.x, b1.x);
-      acc[5] = fmaf(acc[5], a1.y, b1.y);
-      acc[6] = fmaf(acc[6], a1.z, b1.z);
-      acc[7] = fmaf(acc[7], a1.w, b1.w);
-    }
-    if (RELU) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = fmaxf(acc[k], 0.f);
+    for (int r = 0; r < RT; ++r)
+#pragma unroll
+      for (int c = 0; c < CT; ++c) acc[r][c] = fmaf(xv[r], w[c], acc[r][c]);
+  };
+  if (CIN % 4 == 0) {
+#pragma unroll 2
+    for (int k = 0; k < CIN; k += 4) {
+      float4 x[RT];
+#pragma unroll
+      for (int r = 0; r < RT; ++r) x[r] = *reinterpret_cast<const float4*>(x0 + (size_t)r * XS + k);
+      float xv[RT];
+#pragma unroll
+      for (int r = 0; r < RT; ++r) xv[r] = x[r].x;
+      fma_k(xv, k);
+#pragma unroll
+      for (int r = 0; r < RT; ++r) xv[r] = x[r].y;
+      fma_k(xv, k + 1);
+#pragma unroll
+      for (int r = 0; r < RT; ++r) xv[r] = x[r].z;
+      fma_k(xv, k + 2);
+#pragma unroll
+      for (int r = 0; r < RT; ++r) xv[r] = x[r].w;
+      fma_k(xv, k + 3);
     }
-    *reinterpret_cast<float4*>(dst + c) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    *reinterpret_cast<float4*>(dst + c + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  } else {  // the first layer's six input features
+#pragma unroll
+    for (int k = 0; k < CIN; ++k) {
+      float xv[RT];
+#pragma unroll
+      for (int r = 0; r < RT; ++r) xv[r] = x0[(size_t)r * XS + k];
+      fma_k(xv, k);
+    }
   }
+  __syncthreads();
+  float* y0 = T + (size_t)(RT * rg) * XS + out_col + cg * CT;
+  float sa[CT], sb[CT];
+#pragma unroll
+  for (int c = 0; c < CT; ++c) {  // BatchNormalization at inference, folded on the host: y = z * a + b
+    sa[c] = AFFINE ? __ldg(a + cg * CT + c) : 1.f;
+    sb[c] = AFFINE ? __ldg(b + cg * CT + c) : 0.f;
+  }
+#pragma unroll
+  for (int r = 0; r < RT; ++r) {
+    float v[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      v[c] = AFFINE ? fmaf(acc[r][c], sa[c], sb[c]) : acc[r][c];
+      if (RELU) v[c] = fmaxf(v[c], 0.f);
+    }
+    float* y = y0 + (size_t)r * XS;
+    if (CT == 4) *reinterpret_cast<float4*>(y) = make_float4(v[0], v[1 % CT], v[2 % CT], v[3 % CT]);
+    else if (CT == 2) *reinterpret_cast<float2*>(y) = make_float2(v[0], v[1 % CT]);
+    else y[0] = v[0];
+  }
+  __syncthreads();
 }
 
-// one FCN on the thread's row: Dense -> BN -> ReLU, or Dense -> BN -> Dense -> ReLU; result in hrow[0..COUT)
-template <int CIN, int COUT, bool POST>
-__device__ __forceinline__ void row_fcn(const float (&in)[CIN], const float* __restrict__ W, const float* __restrict__ a,
-                                        const float* __restrict__ b, const float* __restrict__ D, float* __restrict__ hrow) {
-  row_dense<CIN, COUT, true, !POST>(in, W, a, b, hrow);
-  if (POST) {
-    float u[COUT];
-#pragma unroll
-    for (int i = 0; i < COUT; i += 4) {
-      const float4 v = *reinterpret_cast<const float4*>(hrow + i);
-      u[i] = v.x;
-      u[i + 1] = v.y;
-      u[i + 2] = v.z;
-      u[i + 3] = v.w;
-    }
-    row_dense<COUT, COUT, false, true>(u, D, nullptr, nullptr, hrow);
-  }
+// one FCN on the tile: Dense -> BN -> ReLU, or Dense -> BN -> Dense -> ReLU; input at columns [in_col, in_col + CIN),
+// result at [out_col, out_col + COUT)
+template <int CIN, int COUT, int XS, bool POST>
+__device__ __forceinline__ void tile_fcn(float* __restrict__ T, int in_col, int out_col, const float* __restrict__ W,
+                                         const float* __restrict__ a, const float* __restrict__ b,
+                                         const float* __restrict__ D, int tid) {
+  tile_dense<CIN, COUT, XS, true, !POST>(T, in_col, out_col, W, a, b, tid);
+  if (POST) tile_dense<COUT, COUT, XS, false, true>(T, out_col, out_col, D, nullptr, nullptr, tid);
 }
 
-// per-voxel max over the voxel's rows of the tile (kept rows and, for a non-full voxel, its pad row): MaxPoolingVFELayer
-template <int C, int HS>
-__device__ __forceinline__ void pool_rows(const float* __restrict__ H, const int* __restrict__ rs, int nvox, int tid,
-                                          float* __restrict__ dst, int dst_stride) {
+// MaxPoolingVFELayer: per-voxel max over the voxel's rows of the tile (kept rows and, for a non-full voxel, its pad row)
+// of columns [col, col + C). REPEAT: RepeatLayer + the pooled half of Concatenate — the max goes to columns [0, C) of
+// every row of the voxel; otherwise it is the voxel's output row (MaxPoolingVFELayer(combine=True)) in `dst`.
+template <int C, int XS, bool REPEAT>
+__device__ __forceinline__ void pool_rows(float* __restrict__ T, int col, const int* __restrict__ rs, int nvox, int tid,
+                                          float* __restrict__ dst) {
   constexpr int G = C / 4;
   for (int item = tid; item < nvox * G; item += kGenThreads) {
     const int v = item / G, g = item - v * G;
     const int r0 = rs[v], r1 = rs[v + 1];
-    float4 m = *reinterpret_cast<const float4*>(H + (size_t)r0 * HS + 4 * g);
+    float4 m = *reinterpret_cast<const float4*>(T + (size_t)r0 * XS + col + 4 * g);
     for (int r = r0 + 1; r < r1; ++r) {
-      const float4 x = *reinterpret_cast<const float4*>(H + (size_t)r * HS + 4 * g);
+      const float4 x = *reinterpret_cast<const float4*>(T + (size_t)r * XS + col + 4 * g);
       m.x = fmaxf(m.x, x.x);
       m.y = fmaxf(m.y, x.y);
       m.z = fmaxf(m.z, x.z);
       m.w = fmaxf(m.w, x.w);
     }
-    *reinterpret_cast<float4*>(dst + (size_t)v * dst_stride + 4 * g) = m;
-  }
-}
-
-// [pooled[voxel] | own row]: Concatenate([pooling, layer]) (:164-165) as the next Dense's input row
-template <int C>
-__device__ __forceinline__ void load_concat(const float* __restrict__ pooled, const float* __restrict__ hrow,
-                                            float (&in)[2 * C]) {
-#pragma unroll
-  for (int i = 0; i < C; i += 4) {
-    const float4 p = *reinterpret_cast<const float4*>(pooled + i);
-    const float4 h = *reinterpret_cast<const float4*>(hrow + i);
-    in[i] = p.x;
-    in[i + 1] = p.y;
-    in[i + 2] = p.z;
-    in[i + 3] = p.w;
-    in[C + i] = h.x;
-    in[C + i + 1] = h.y;
-    in[C + i + 2] = h.z;
-    in[C + i + 3] = h.w;
+    if (REPEAT) {
+      for (int r = r0; r < r1; ++r) *reinterpret_cast<float4*>(T + (size_t)r * XS + 4 * g) = m;
+    } else {
+      *reinterpret_cast<float4*>(dst + (size_t)v * C + 4 * g) = m;
+    }
   }
 }
 
@@ -152,24 +180,22 @@ template <int C1, int C2, int C3, bool POST, typename PT>
 __global__ void __launch_bounds__(kGenThreads) vfe_generic_kernel(const float* __restrict__ params, const VfeProblem prob,
                                                                   float* __restrict__ voxel_feat) {
   using L = GenericLayout<C1, C2, C3, POST>;
-  constexpr int HS = L::kHS, CP = L::kCP;
+  constexpr int XS = L::kXS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* H = reinterpret_cast<float*>(smem_raw);          // [128][HS] the tile's rows, current layer
-  float* PL = H + (size_t)kGenThreads * HS;                // [64][CP] per-voxel max of the current layer
-  double* cen = reinterpret_cast<double*>(PL + (size_t)kGenVox * CP);  // [64][3] centroids
-  int* rs = reinterpret_cast<int*>(cen + 3 * kGenVox);    // [65] first row of each voxel, relative to the tile
+  float* T = reinterpret_cast<float*>(smem_raw);                          // [128][XS] the tile
+  double* cen = reinterpret_cast<double*>(T + (size_t)kGenRows * XS);     // [64][3] centroids
+  int* rs = reinterpret_cast<int*>(cen + 3 * kGenVox);                    // [65] first row of each voxel, tile-relative
 
   const int t = threadIdx.x;
   const PT* __restrict__ xyz = static_cast<const PT*>(prob.row_xyz);
   const long long n_chunks = *prob.n_chunks;
-  float* hrow = H + (size_t)t * HS;
   for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
     const int nt = prob.chunk_ntiles[c];
     for (int j = 0; j < nt; ++j) {
       const int v0 = prob.tile_first[c * kChunkSlots + j], v1 = prob.tile_first[c * kChunkSlots + j + 1];
       const int r0 = prob.tile_row0[c * kChunkSlots + j], r1 = prob.tile_row0[c * kChunkSlots + j + 1];
       const int nvox = v1 - v0, nrows = r1 - r0;
-      __syncthreads();  // the previous tile's readers are done with rs / cen / PL / H
+      __syncthreads();  // the previous tile's readers are done with rs / cen / T
       if (t <= nvox) rs[t] = prob.row_start[v0 + t] - r0;
       if (t < nvox) {  // np.mean(currPoints, axis=0): float64 adds in list order, one divide (model_training.py:135)
         const int a = prob.row_start[v0 + t], e = prob.row_start[v0 + t + 1];
@@ -186,63 +212,55 @@ __global__ void __launch_bounds__(kGenThreads) vfe_generic_kernel(const float* _
         cen[3 * t + 2] = sz / dn;
       }
       __syncthreads();
-      const bool live = t < nrows;
-      int lv = 0;
-      // ---- addVFELayer(in, 6, 2*C1) ----
-      if (live) {
-        const int rv = prob.row_voxel[r0 + t];
-        lv = (rv & ~kRowPadFlag) - v0;
+      if (t < kGenRows) {  // the tile's input rows: columns [0, 6); rows past the tile's end stay zero (never pooled)
         float f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // the pad row: the dense input's zero rows (:141-142)
-        if (!(rv & kRowPadFlag)) {
-          const size_t r = (size_t)(r0 + t);
-          point_features((double)xyz[3 * r], (double)xyz[3 * r + 1], (double)xyz[3 * r + 2], cen[3 * lv], cen[3 * lv + 1],
-                         cen[3 * lv + 2], f);
+        if (t < nrows) {
+          const int rv = prob.row_voxel[r0 + t];
+          if (!(rv & kRowPadFlag)) {
+            const int lv = rv - v0;
+            const size_t r = (size_t)(r0 + t);
+            point_features((double)xyz[3 * r], (double)xyz[3 * r + 1], (double)xyz[3 * r + 2], cen[3 * lv], cen[3 * lv + 1],
+                           cen[3 * lv + 2], f);
+          }
         }
-        row_fcn<6, C1, POST>(f, params + L::w(0), params + L::a(0), params + L::b(0), params + L::d(0), hrow);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) T[(size_t)t * XS + k] = f[k];
       }
       __syncthreads();
-      pool_rows<C1, HS>(H, rs, nvox, t, PL, CP);
+      // ---- addVFELayer(in, 6, 2*C1): the FCN's output at columns [C1, 2 C1), the pooled half in front of it ----
+      tile_fcn<6, C1, XS, POST>(T, 0, C1, params + L::w(0), params + L::a(0), params + L::b(0), params + L::d(0), t);
+      pool_rows<C1, XS, true>(T, C1, rs, nvox, t, nullptr);
       __syncthreads();
       // ---- addVFELayer(., 2*C1, 2*C2) ----
-      if (live) {
-        float in[2 * C1];
-        load_concat<C1>(PL + (size_t)lv * CP, hrow, in);
-        row_fcn<2 * C1, C2, POST>(in, params + L::w(1), params + L::a(1), params + L::b(1), params + L::d(1), hrow);
-      }
-      __syncthreads();
-      pool_rows<C2, HS>(H, rs, nvox, t, PL, CP);
+      tile_fcn<2 * C1, C2, XS, POST>(T, 0, C2, params + L::w(1), params + L::a(1), params + L::b(1), params + L::d(1), t);
+      pool_rows<C2, XS, true>(T, C2, rs, nvox, t, nullptr);
       __syncthreads();
       // ---- addFCN(., 2*C2, C3) + MaxPoolingVFELayer(combine=True) ----
-      if (live) {
-        float in[2 * C2];
-        load_concat<C2>(PL + (size_t)lv * CP, hrow, in);
-        row_fcn<2 * C2, C3, POST>(in, params + L::w(2), params + L::a(2), params + L::b(2), params + L::d(2), hrow);
-      }
-      __syncthreads();
-      pool_rows<C3, HS>(H, rs, nvox, t, voxel_feat + (size_t)v0 * C3, C3);
+      tile_fcn<2 * C2, C3, XS, POST>(T, 0, 0, params + L::w(2), params + L::a(2), params + L::b(2), params + L::d(2), t);
+      pool_rows<C3, XS, false>(T, 0, rs, nvox, t, voxel_feat + (size_t)v0 * C3);
     }
   }
+}
+
+template <typename K>
+cudaError_t launch_kernel(K k, size_t smem, const float* params, const VfeProblem& prob, float* voxel_feat, int sm_count,
+                          cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 1;  // resident CTAs per SM (registers: 512 threads x ~120 allow one for the wide graphs, two for the narrow)
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kGenThreads, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  k<<<(unsigned)(sm_count * per_sm), kGenThreads, smem, st>>>(params, prob, voxel_feat);
+  return cudaGetLastError();
 }
 
 template <int C1, int C2, int C3, bool POST>
 cudaError_t launch_one(const float* params, const VfeProblem& prob, float* voxel_feat, int sm_count, cudaStream_t st) {
   using L = GenericLayout<C1, C2, C3, POST>;
-  int per_sm = (int)((220 * 1024) / L::smem);
-  if (per_sm > 6) per_sm = 6;
-  if (per_sm < 1) per_sm = 1;
-  const unsigned blocks = (unsigned)(sm_count * per_sm);
-  if (prob.pts_dtype == LISEC_F32) {
-    auto k = vfe_generic_kernel<C1, C2, C3, POST, float>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem);
-    if (e != cudaSuccess) return e;
-    k<<<blocks, kGenThreads, L::smem, st>>>(params, prob, voxel_feat);
-  } else {
-    auto k = vfe_generic_kernel<C1, C2, C3, POST, double>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem);
-    if (e != cudaSuccess) return e;
-    k<<<blocks, kGenThreads, L::smem, st>>>(params, prob, voxel_feat);
-  }
-  return cudaGetLastError();
+  if (prob.pts_dtype == LISEC_F32)
+    return launch_kernel(vfe_generic_kernel<C1, C2, C3, POST, float>, L::smem, params, prob, voxel_feat, sm_count, st);
+  return launch_kernel(vfe_generic_kernel<C1, C2, C3, POST, double>, L::smem, params, prob, voxel_feat, sm_count, st);
 }
 
 template <int C1, int C2, int C3, bool POST>
