@@ -640,6 +640,31 @@ def run_native(args):
             net32.close()
             del net32
             torch.cuda.empty_cache()
+            # the OTHER graph the reference's .h5 may hold (model.png — VFE widths 16 | 64 | 128, Dense-BN-Dense
+            # FCNs, Conv2D-BN-Dense RPN layers): the float32 VFE kernel (vfe_generic.cu) + a 128-channel grid + the same plans
+            try:
+                from lisec_b200.weights import MODEL_PNG, synthetic_model_pack
+
+                pk = synthetic_model_pack(0, MODEL_PNG)
+                fe_o = Frontend(device=local, max_points=SWEEPS_PER_GPU * POINTS_PER_SWEEP, max_sweeps=SWEEPS_PER_GPU,
+                                grid_dtype="bf16", widths=MODEL_PNG.widths, post_dense=True)
+                fe_o.set_weights(pk)
+                net_o = DenseNetwork(pk, batch=SWEEPS_PER_GPU, device=local, arch=MODEL_PNG)
+
+                def step_older():
+                    fe_o.forward(dev_batches[0], offsets, out=net_o.grid)
+                    net_o.forward()
+
+                ms_o = timed(step_older, 5)
+                full["older_graph"] = {"sweeps_per_step": SWEEPS_PER_GPU, "ms_per_step": ms_o,
+                                       "frontend_ms": timed(lambda: fe_o.forward(dev_batches[0], offsets, out=net_o.grid), 5),
+                                       "flops_per_step": net_o.flops}
+                net_o.close()
+                fe_o.close()
+                del net_o, fe_o
+                torch.cuda.empty_cache()
+            except Exception as exc:
+                full["older_graph"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     config4 = None
     if world == 1:
         # configs[3]: one aggregated 1 M-point cloud near T-cap saturation, voxelize + VFE (sparse output)
@@ -774,6 +799,14 @@ def run_native(args):
                     "dtype": "f32 (3xTF32 tensor-core plans on hi/lo float32 planes; 1e-5 of the float64 oracle)",
                     "sweeps_per_step": f32["sweeps_per_step"], "ms_per_step": f32["ms_per_step"],
                     "value": f32["sweeps_per_step"] / (f32["ms_per_step"] * 1e-3), "unit": "sweeps/s"}
+            if "older_graph" in full:
+                og = dict(full["older_graph"])
+                if "ms_per_step" in og:
+                    og.update({"value": og["sweeps_per_step"] / (og["ms_per_step"] * 1e-3), "unit": "sweeps/s",
+                               "workload": "the same inference step for the graph model.png shows (VFE 16 | 64 | 128 with "
+                                           "Dense-BN-Dense FCNs in float32 FMAs, 128-channel bf16 grid, Conv2D-BN-Dense RPN "
+                                           "layers folded into the same tensor-core plans): SURVEY §2.4, DESIGN §4a"})
+                line["full_inference"]["older_graph"] = og
         if world == 1 and not args.no_cpu_baseline:
             pts0 = base[0]
             t_vox, t_vfe = cpu_reference_time_per_sweep(pts0, 1.0, 200, pack)

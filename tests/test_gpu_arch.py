@@ -90,6 +90,35 @@ def test_float32_vfe_kernel_matches_the_oracle_on_every_graph(arch, seed):
     fb.close()
 
 
+def test_older_graph_on_float64_points_ragged_sweeps_and_another_sample_size():
+    """The float32 kernel away from the defaults: float64 points (the reference's own dtype, model_training.py:93-94), three
+    sweeps of which one is empty, T = 20 on a reduced grid — voxel rows, c_empty and the grid against the oracle."""
+    arch, Tn, mx, my, mz = MODEL_PNG, 20, 16, 24, 4
+    ref = dict(xSize=0.5, ySize=0.25, zSize=0.25, sampleSize=Tn, maxVoxelX=mx, maxVoxelY=my, maxVoxelZ=mz)
+    rng = np.random.default_rng(9)
+    a = np.stack([rng.uniform(-8.5, 8.5, 9000), rng.uniform(-6.5, 6.5, 9000), rng.uniform(-0.2, 1.2, 9000)], axis=1)
+    a[:3000, :2] *= 0.1  # a dense core: voxels far past T
+    b = np.stack([rng.uniform(-3, 3, 700), rng.uniform(-2, 2, 700), rng.uniform(0, 1, 700)], axis=1)
+    sweeps = [a, np.zeros((0, 3)), b]
+    pts = np.concatenate(sweeps)
+    off = np.cumsum([0] + [len(s) for s in sweeps]).tolist()
+    pack = synthetic_vfe_pack(7, arch)
+    fe = make_frontend(arch, max_points=len(pts), max_sweeps=3, grid_dtype="f32", max_voxel=(mx, my, mz), sample_size=Tn)
+    fe.set_weights(pack)
+    grid = fe.forward(pts, off).cpu().numpy()
+    assert grid.shape == (3, mz, 2 * mx, 2 * my, arch.c3) and grid.dtype == np.float32
+    ce = O.c_empty(pack, Tn)
+    assert within(fe.c_empty(), ce) <= 1e-5
+    for s, p in enumerate(sweeps):
+        vox = O.voxelize_np(p, **ref)
+        want = O.scatter_dense(vox["coords"], O.vfe_forward(vox["features"].astype(np.float32), pack), ce,
+                               (mz, 2 * mx, 2 * my), dtype=np.float64)
+        e = within(grid[s], want)
+        assert e <= 1e-5, (s, e)
+    assert (grid[1] == fe.c_empty()).all()  # the empty sweep: background only
+    fe.close()
+
+
 def test_float32_and_tensor_core_vfe_kernels_agree_on_the_graph_they_share():
     pack = synthetic_vfe_pack(1)
     sweeps = [synth.lyft_like_sweep(40_000, seed=2), synth.lyft_like_sweep(25_000, seed=3)]
