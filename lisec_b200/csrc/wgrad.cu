@@ -21,13 +21,16 @@
 // First version: bf16 operands, float32 accumulation, stride_hw 1 or 2 (the TMA's element stride), C and N multiples of
 // 64, N <= 256. Each X box feeds
 // only 8 MMAs, so this kernel is bound by L2 -> shared-memory delivery like the first forward kernel was
-// (profiles/conv_r1j_summary.txt); the halo-box trick of conv_halo_kernel applies here too and is the next step.
+// (profiles/conv_r1j_summary.txt). conv_wgrad_halo_kernel (below) applies the halo-box trick of conv_halo_kernel to the
+// layers that dominate the step — the 3 x 3 x 3, 64 -> 64 Conv3D blocks: ONE [18][10][64] input box per (kd, tile) serves
+// all nine (kh, kw) taps, each tap a descriptor into the same box.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -51,6 +54,8 @@ struct WgradParams {
   signed char t1[27], t2[27], t3[27];  // X box origin of a tap relative to the tile origin (w, h, d)
   float* partial;  // [grid][taps][N][C]
   long long slice;  // taps * N * C
+  // halo mode: one X box per (kd, 64-channel block, tile); kd_n * cblocks boxes = passes
+  int halo, boxes, pad_w, pad_h, pad_d, kd_n;
 };
 
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
@@ -86,6 +91,17 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t addr, uint32_t lbo) {
   d |= (uint64_t)((addr >> 4) & 0x3fff);
   d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
   d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// the same with an explicit stride between the 8-row k groups (a halo box: rows of 8 positions are a box row apart)
+__device__ __forceinline__ uint64_t make_desc_mn2(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
@@ -245,6 +261,153 @@ __global__ void __launch_bounds__(kWgThreads, 1)
   if (warp == 1) umma::tmem_dealloc<512>(tmem_base);
 }
 
+
+// ---- halo mode: 3 x 3 (kh, kw) taps out of one input box -----------------------------------------------------------
+// Tile = 16 (h) x 8 (w) output positions; the input box of a (kd, 64-channel block) is [18][10] positions x 64 channels,
+// 128 bytes per position (SWIZZLE_128B, written by one TMA load, zero-filled outside the tensor = the convolution's
+// padding). The K dimension of the MMAs is positions: an 8-position k group = the 8 w positions of one h row = 8
+// consecutive 128-byte rows of the box, the next k group is one BOX ROW further (10 x 128 bytes: the descriptor's stride
+// byte offset), and tap (kh, kw) is the same walk started (kh * 10 + kw) positions into the box. The two taps of a pair
+// sit in the two 64-row halves of M: the descriptor's leading byte offset is the distance between their starts. Nine taps
+// = five pairs (the last one half empty) = 320 accumulator columns; one pass over the tiles per box.
+constexpr int kHaloBw = 8, kHaloBh = 16, kHaloRow = (kHaloBw + 2) * 128;       // bytes of one box row
+constexpr uint32_t kHaloBoxBytes = (kHaloBw + 2) * (kHaloBh + 2) * 128;          // 23 040 delivered by the TMA
+constexpr uint32_t kHaloStage = (kHaloBoxBytes + 1023u) & ~1023u;                // 23 552: stages stay 1 KB aligned
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+    conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
+                           const __grid_constant__ WgradParams P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = umma::smem_u32(smem);
+  if (base & 1023u) __trap();
+  const uint32_t dy0 = base + (uint32_t)P.stages * P.stage_bytes;
+  const uint32_t bar0 = dy0 + 2u * P.dy_bytes;
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (kWgMaxStages + s); };
+  auto bar_dy_full = [&](int s) { return bar0 + 8u * (2 * kWgMaxStages + s); };
+  auto bar_dy_empty = [&](int s) { return bar0 + 8u * (2 * kWgMaxStages + 2 + s); };
+  const uint32_t bar_acc_full = bar0 + 8u * (2 * kWgMaxStages + 4), bar_acc_empty = bar_acc_full + 8u;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (size_t)P.stages * P.stage_bytes + 2 * (size_t)P.dy_bytes +
+                                                    8 * (2 * kWgMaxStages + 6));
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
+    for (int s = 0; s < P.stages; ++s) {
+      umma::mbar_init(bar_full(s), 1);
+      umma::mbar_init(bar_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      umma::mbar_init(bar_dy_full(s), 1);
+      umma::mbar_init(bar_dy_empty(s), 1);
+    }
+    umma::mbar_init(bar_acc_full, 1);
+    umma::mbar_init(bar_acc_empty, 4);
+    umma::mbar_init_fence();
+  }
+  if (warp == 1) umma::tmem_alloc<512>(tmem_slot);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  const int cblocks = P.C / 64;
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer: per box (= pass), per tile: the dY tile and ONE halo box =====
+      int s = 0, ds = 0;
+      uint32_t ph = 0, dph = 0;
+      for (int box = 0; box < P.boxes; ++box) {
+        const int kd = box / cblocks, cb = box - kd * cblocks;
+        for (long long tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+          const WgTile t = wg_tile(P, tile);
+          umma::mbar_wait(bar_dy_empty(ds), dph ^ 1u);
+          mbar_arrive_expect_tx(bar_dy_full(ds), P.dy_bytes);
+          for (int n = 0; n < P.nb; ++n)
+            tma_load_5d(dy0 + (uint32_t)ds * P.dy_bytes + n * kBox, &map_dy, bar_dy_full(ds), 64 * n, t.ow0, t.oh0, t.od, t.b);
+          if (++ds == 2) { ds = 0; dph ^= 1u; }
+          umma::mbar_wait(bar_empty(s), ph ^ 1u);
+          mbar_arrive_expect_tx(bar_full(s), kHaloBoxBytes);
+          tma_load_5d(base + (uint32_t)s * P.stage_bytes, &map_x, bar_full(s), 64 * cb, t.ow0 - P.pad_w, t.oh0 - P.pad_h,
+                      t.od * P.stride_d + kd - P.pad_d, t.b);
+          if (++s == P.stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(P.N >> 3) << 17) |
+                             ((128u >> 4) << 24);
+      int s = 0, ds = 0;
+      uint32_t ph = 0, dph = 0, acc_ph = 0;
+      for (int box = 0; box < P.boxes; ++box) {
+        umma::mbar_wait(bar_acc_empty, acc_ph ^ 1u);  // the epilogue has drained the previous box's accumulators
+        umma::fence_after_sync();
+        bool first_tile = true;
+        for (long long tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+          umma::mbar_wait(bar_dy_full(ds), dph);
+          umma::mbar_wait(bar_full(s), ph);
+          umma::fence_after_sync();
+          const uint32_t a0 = base + (uint32_t)s * P.stage_bytes, b0 = dy0 + (uint32_t)ds * P.dy_bytes;
+          const uint64_t bdesc = make_desc_mn2(b0, kBox, 1024);
+#pragma unroll
+          for (int p = 0; p < 5; ++p) {
+            const int ta = 2 * p, tb = p < 4 ? 2 * p + 1 : 8;
+            const uint32_t offa = (uint32_t)((ta / 3) * (kHaloBw + 2) + ta % 3) * 128u;
+            const uint32_t offb = (uint32_t)((tb / 3) * (kHaloBw + 2) + tb % 3) * 128u;
+            const uint32_t lbo = p < 4 ? offb - offa : 128u;  // (the last pair's upper half is not read back)
+            const uint64_t adesc = make_desc_mn2(a0 + offa, lbo, kHaloRow);
+            const uint32_t d = tmem_base + (uint32_t)(p * P.N);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)  // K = 16 positions = two box rows of 8
+              mma_bf16(d, adesc + (uint64_t)((2u * kHaloRow * j) >> 4), bdesc + (uint64_t)(128u * j), idesc,
+                       (first_tile && j == 0) ? 0u : 1u);
+          }
+          umma::mma_commit(bar_empty(s));
+          if (++s == P.stages) { s = 0; ph ^= 1u; }
+          umma::mma_commit(bar_dy_empty(ds));
+          if (++ds == 2) { ds = 0; dph ^= 1u; }
+          first_tile = false;
+        }
+        umma::mma_commit(bar_acc_full);
+        acc_ph ^= 1u;
+      }
+    }
+  } else {
+    // ===== epilogue: once per box, TMEM -> this CTA's slice of the partial buffer =====
+    const int q = warp & 3, m = 32 * q + lane;  // TMEM lane: tap 2p + (m >= 64) of the box, input channel m % 64
+    float* slice = P.partial + (long long)blockIdx.x * P.slice;
+    uint32_t acc_ph = 0;
+    for (int box = 0; box < P.boxes; ++box) {
+      const int kd = box / cblocks, cb = box - kd * cblocks;
+      umma::mbar_wait(bar_acc_full, acc_ph);
+      umma::fence_after_sync();
+      for (int p = 0; p < 5; ++p) {
+        const int tin = 2 * p + (m >> 6);
+        const bool valid = tin < 9;
+        const int tap = kd * 9 + (valid ? tin : 0);
+        float* dst = slice + ((long long)tap * P.N) * P.C + 64 * cb + (m & 63);
+        for (int c0 = 0; c0 < P.N; c0 += 32) {
+          float x[32];
+          umma::tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(p * P.N + c0), x);
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dst[(long long)(c0 + i) * P.C] = x[i];
+          }
+        }
+      }
+      umma::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(bar_acc_empty);
+      acc_ph ^= 1u;
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) umma::tmem_dealloc<512>(tmem_base);
+}
+
 // dW[i] = sum over the CTAs' slices, in slice order
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int slices, long long n,
                                                            float* __restrict__ dw) {
@@ -349,6 +512,16 @@ int32_t lisec_conv_wgrad_plan_create(const lisec_conv_desc* d, const void* x, co
   WgradParams& p = pl->p;
   p.bw = d->tile_w;
   p.bh = d->tile_h;
+  // halo mode (conv_wgrad_halo_kernel): the 3 x 3 (kh, kw), stride-1, 64-output-channel layers = the Conv3D blocks
+  {
+    const char* e = getenv("LISEC_WGRAD_HALO");
+    p.halo = (shw == 1 && d->kh == 3 && d->kw == 3 && d->pad_h == 1 && d->pad_w == 1 && N == 64 && 5 * N <= 512 &&
+              !(e && e[0] == '0')) ? 1 : 0;
+  }
+  if (p.halo) {
+    p.bw = kHaloBw;
+    p.bh = kHaloBh;
+  }
   p.tiles_w = (OW + p.bw - 1) / p.bw;
   p.tiles_h = (OH + p.bh - 1) / p.bh;
   p.out_d = OD;
@@ -362,8 +535,13 @@ int32_t lisec_conv_wgrad_plan_create(const lisec_conv_desc* d, const void* x, co
   p.pairs = (p.units + 1) / 2;
   p.pairs_per_pass = 512 / N;
   p.passes = (p.pairs + p.pairs_per_pass - 1) / p.pairs_per_pass;
-  p.stage_bytes = 2u * kBox;
+  p.stage_bytes = p.halo ? kHaloStage : 2u * kBox;
   p.dy_bytes = (uint32_t)p.nb * kBox;
+  p.boxes = d->kd * (C / 64);
+  p.kd_n = d->kd;
+  p.pad_w = d->pad_w;
+  p.pad_h = d->pad_h;
+  p.pad_d = d->pad_d;
   p.stages = (int)((200u * 1024u - 2u * p.dy_bytes) / p.stage_bytes);
   if (p.stages > kWgMaxStages) p.stages = kWgMaxStages;
   if (p.stages < 2) {
@@ -392,6 +570,10 @@ int32_t lisec_conv_wgrad_plan_create(const lisec_conv_desc* d, const void* x, co
     // stride_hw = 2: the TMA walks W and H with an element stride of 2 — the box spans 2 * tile positions of the input and
     // delivers the tile's 128 positions
     cuuint32_t box[5] = {64, (cuuint32_t)(p.bw * shw), (cuuint32_t)(p.bh * shw), 1, 1};
+    if (p.halo) {  // the tile plus one position on every side in W and H
+      box[1] = (cuuint32_t)(p.bw + 2);
+      box[2] = (cuuint32_t)(p.bh + 2);
+    }
     cuuint32_t xstr[5] = {1, (cuuint32_t)shw, (cuuint32_t)shw, 1, 1};
     CUresult r = encode(&pl->map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, xstr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -418,6 +600,7 @@ int32_t lisec_conv_wgrad_plan_create(const lisec_conv_desc* d, const void* x, co
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   if (e != cudaSuccess) {
     delete pl;
     return wg_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
@@ -430,7 +613,10 @@ int32_t lisec_conv_wgrad_plan_create(const lisec_conv_desc* d, const void* x, co
 int32_t lisec_conv_wgrad_plan_run(lisec_wgrad_plan* pl, void* stream) {
   if (!pl) return wg_fail(LISEC_ERR_BAD_ARG, "null plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = launch_pdl(conv_wgrad_kernel, pl->grid, kWgThreads, (size_t)pl->smem, st, pl->map_x, pl->map_dy, pl->p);
+  cudaError_t e = pl->p.halo ? launch_pdl(conv_wgrad_halo_kernel, pl->grid, kWgThreads, (size_t)pl->smem, st, pl->map_x,
+                                          pl->map_dy, pl->p)
+                             : launch_pdl(conv_wgrad_kernel, pl->grid, kWgThreads, (size_t)pl->smem, st, pl->map_x, pl->map_dy,
+                                          pl->p);
   if (e == cudaSuccess) {
     const long long n = pl->p.slice;
     e = launch_pdl(wgrad_reduce_kernel, dim3((unsigned)((n / 4 + 255) / 256)), dim3(256), 0, st,
