@@ -28,6 +28,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -431,6 +432,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 // goes to warp n & 3 and slot n & 3 (a box is two dependent L2 round trips: four in flight keep up with the MMAs); the
 // weights keep coming through warp 0's TMA.
 constexpr int kGatherWarps = 4;  // one per input-box slot
+constexpr int kGatherList = 352;  // (row, voxel) entries of a warp's list of occupied rows: every row of a box
 constexpr int kConvGatherThreads = kConvThreads + 32 * kGatherWarps;
 template <bool GATHER>
 __global__ void __launch_bounds__(GATHER ? kConvGatherThreads : kConvThreads, 1)
@@ -558,17 +560,35 @@ __global__ void __launch_bounds__(GATHER ? kConvGatherThreads : kConvThreads, 1)
         if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
       }
     }
-  } else if (GATHER && warp >= 11) {
-    const int g = warp - 11;  // boxes g, g + 4, ... of this CTA's sequence, always into slot g
+  } else if (GATHER && warp >= 11 && warp - 11 < P.a_slots) {
+    const int g = warp - 11;  // boxes g, g + a_slots, ... of this CTA's sequence, always into slot g
     const int rows = P.box_w * (P.bh + 2);
     unsigned char* slot = smem + (size_t)g * P.a_slot_bytes;
     const uint32_t slot_addr = base + (uint32_t)g * P.a_slot_bytes;
     long long n = 0;     // box ordinal of this CTA
     uint32_t use = 0;    // how often this warp has filled its slot
+    // 92 % of the cells are empty: the slot is filled with c_empty rows ONCE, and a box then only writes the rows that are
+    // occupied or outside the grid, plus the rows its predecessor in this slot left different from c_empty (`dirty`: bit k
+    // = the lane's row lane + 32 k) — ~60 rows of 8 stores instead of 324.
+    unsigned dirty = 0;
+    int2* s_list = reinterpret_cast<int2*>(reinterpret_cast<unsigned char*>(s_cempty) + 128) + (size_t)g * kGatherList;
+    auto store_row = [&](int r, const uint4 (&ch)[8]) {
+      const uint32_t row_addr = slot_addr + (uint32_t)r * 128u;
+      const uint32_t sw = (row_addr >> 7) & 7u;
+      unsigned char* row_ptr = slot + (size_t)r * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(row_ptr + (((uint32_t)c ^ sw) << 4)) = ch[c];
+    };
+    {
+      uint4 ce[8];  // (s_cempty was written before the set-up barrier)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) ce[c] = s_cempty[c];
+      for (int r = lane; r < rows; r += 32) store_row(r, ce);
+    }
     for (long long tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(P, tile);
       for (int kd = 0; kd < P.kd_n; ++kd, ++n) {  // (c_blocks == 1 for gather plans)
-        if ((n & (kGatherWarps - 1)) != g) continue;
+        if ((int)(n % P.a_slots) != g) continue;
         const int w0 = t.ow0 + P.t1[0], h0 = t.oh0 + P.t2[0], dz = t.od * P.stride_d + kd + P.t3[0];
         const bool d_ok = dz >= 0 && dz < P.in_d;
         const long long plane = ((long long)t.b * P.in_d + dz) * P.in_h;
@@ -583,37 +603,62 @@ __global__ void __launch_bounds__(GATHER ? kConvGatherThreads : kConvThreads, 1)
           vox[k] = ok ? __ldcg(P.g_cell_voxel + (plane + h) * P.in_w + w) : -2;  // -1: empty cell, -2: outside the grid
         }
         umma::mbar_wait(bar_a_empty(g), (use & 1u) ^ 1u);
+        // rows without a voxel behind them: zeros outside the grid, c_empty back where the slot's last box left something
+        // else. The occupied rows are only LISTED here (row, voxel), compacted over the warp: fetching them inside this
+        // loop costs one dependent L2 round trip per k for the whole warp (some lane has an occupied row at almost every
+        // k) — eleven per box. (Fetching the list's first 32 rows BEFORE the wait, so that the slot is not held for a
+        // round trip, measured slower: 0.78 against 0.70 ms.)
+        int n_occ = 0;
 #pragma unroll
         for (int k = 0; k < 11; ++k) {
           const int r = lane + 32 * k;
-          if (r >= rows) break;
+          const bool occ = r < rows && vox[k] >= 0;
+          const unsigned m = __ballot_sync(0xffffffffu, occ);
+          if (occ) {
+            s_list[n_occ + __popc(m & ((1u << lane) - 1u))] = make_int2(r, vox[k]);
+            dirty |= 1u << k;
+          }
+          n_occ += __popc(m);
+          if (r >= rows || occ) continue;
           uint4 ch[8];
-          if (vox[k] >= 0) {
-            const float4* src = reinterpret_cast<const float4*>(P.g_voxel_feat + (size_t)vox[k] * 64);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 a = __ldcg(src + 2 * c), b = __ldcg(src + 2 * c + 1);
-              ch[c] = make_uint4(pack2(a.x, a.y), pack2(a.z, a.w), pack2(b.x, b.y), pack2(b.z, b.w));
-            }
-          } else if (vox[k] == -1) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) ch[c] = s_cempty[c];
-          } else {
+          if (vox[k] == -2) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) ch[c] = make_uint4(0u, 0u, 0u, 0u);
-          }
-          const uint32_t row_addr = slot_addr + (uint32_t)r * 128u;
-          const uint32_t sw = (row_addr >> 7) & 7u;
-          unsigned char* row_ptr = slot + (size_t)r * 128;
+            store_row(r, ch);
+            dirty |= 1u << k;
+          } else if (dirty & (1u << k)) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(row_ptr + (((uint32_t)c ^ sw) << 4)) = ch[c];
+            for (int c = 0; c < 8; ++c) ch[c] = s_cempty[c];
+            store_row(r, ch);
+            dirty &= ~(1u << k);
+          }
         }
+        __syncwarp();
+        for (int i0 = 0; i0 < n_occ; i0 += 32) {  // one occupied row per lane and round: a single round trip for ~26 rows
+          const int i = i0 + lane;
+          if (i < n_occ) {
+            const int2 e = s_list[i];
+            const float4* src = reinterpret_cast<const float4*>(P.g_voxel_feat + (size_t)e.y * 64);
+            float4 f[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) f[c] = __ldcg(src + c);
+            uint4 ch[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              ch[c] = make_uint4(pack2(f[2 * c].x, f[2 * c].y), pack2(f[2 * c].z, f[2 * c].w), pack2(f[2 * c + 1].x, f[2 * c + 1].y),
+                                 pack2(f[2 * c + 1].z, f[2 * c + 1].w));
+            store_row(e.x, ch);
+          }
+        }
+        __syncwarp();  // (the list is rewritten by the next box)
         umma::fence_async_smem();  // generic-proxy writes -> visible to the tensor core
         __syncwarp();
         if (lane == 0) umma::mbar_arrive(bar_a_full(g));
         ++use;
       }
     }
+  } else if (GATHER && warp >= 11) {
+    // a gather warp without a box slot (a_slots < kGatherWarps): nothing to do
   } else {
     const int q = warp & 3, row = 32 * q + lane, half = (warp - 2) >> 2;
     const int ncols = P.N >= 64 ? P.N / 2 : (half == 0 ? P.N : 0), col0 = P.N >= 64 ? half * (P.N / 2) : 0;
@@ -1009,6 +1054,10 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
     const uint32_t room = 220u * 1024u - 2u * p.a_slot_bytes;
     int b_slots = (int)(room / b_slot);
     if (b_slots > 8) b_slots = 8;
+    if (const char* e = getenv("LISEC_CONV_B_SLOTS")) {  // experiment: a shallower weight ring
+      const int v = atoi(e);
+      if (v >= 2 && v < b_slots) b_slots = v;
+    }
     if (b_slots < 2) {
       delete pl;
       return conv_fail(LISEC_ERR_BAD_CONFIG, "halo plan: no room for two weight slots of %u bytes", b_slot);
@@ -1096,15 +1145,24 @@ int32_t lisec_conv_plan_set_gather(lisec_conv_plan* pl, const int32_t* cell_voxe
   if (!pl || !cell_voxel || !voxel_feat || !c_empty) return conv_fail(LISEC_ERR_BAD_ARG, "null argument");
   if (!pl->p.halo || pl->p.c_blocks != 1 || pl->p.box_w * (pl->p.bh + 2) > 11 * 32)
     return conv_fail(LISEC_ERR_BAD_CONFIG, "gather source: a halo plan with 64 input channels and a box of <= 352 positions");
-  // four box slots (one per gather warp) and what is left for the weight ring
+  // box slots (one per active gather warp) and what is left for the weight ring: 2 / 3 / 4 box slots measured 0.77 / 0.70 /
+  // 0.71 ms (8 sweeps; 0.48 ms from the dense grid). The weight ring's depth is not what limits it (the dense plan with
+  // two weight slots instead of five: 0.492 against 0.486 ms).
+  int a_slots = 3;
+  if (const char* e = getenv("LISEC_GATHER_SLOTS")) {
+    const int v = atoi(e);
+    if (v >= 2 && v <= kGatherWarps) a_slots = v;
+  }
   const uint32_t b_slot = 3u * (uint32_t)pl->p.N * 128u;
-  const uint32_t room = 220u * 1024u - (uint32_t)kGatherWarps * pl->p.a_slot_bytes;
+  const uint32_t room = 214u * 1024u - (uint32_t)a_slots * pl->p.a_slot_bytes;
   int b_slots = (int)(room / b_slot);
   if (b_slots > 8) b_slots = 8;
-  if (b_slots < 2) return conv_fail(LISEC_ERR_BAD_CONFIG, "gather source: no room for two weight slots beside four box slots");
-  pl->p.a_slots = kGatherWarps;
+  if (b_slots < 2) return conv_fail(LISEC_ERR_BAD_CONFIG, "gather source: no room for two weight slots beside the box slots");
+  pl->p.a_slots = a_slots;
   pl->p.b_slots = b_slots;
-  pl->smem = (int)((uint32_t)kGatherWarps * pl->p.a_slot_bytes + (uint32_t)b_slots * b_slot) + 8 * 28 + 16 + 128;
+  pl->smem = (int)((uint32_t)a_slots * pl->p.a_slot_bytes + (uint32_t)b_slots * b_slot) + 8 * 28 + 16 + 128 +
+             kGatherWarps * kGatherList * (int)sizeof(int2);
+  if (pl->smem > 232448) return conv_fail(LISEC_ERR_BAD_CONFIG, "gather source: %d bytes of shared memory", pl->smem);
   pl->p.gather = 1;
   pl->p.g_cell_voxel = cell_voxel;
   pl->p.g_voxel_feat = voxel_feat;
