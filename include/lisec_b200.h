@@ -421,8 +421,9 @@ const char* lisec_train_last_error(void);
  * channels in {8, 16, 32, 64, 128, 256}. workspace: lisec_bn_workspace_bytes(positions, channels) bytes. All pointers
  * are device pointers; per-channel vectors are float32.
  * forward  [async]: mean, invstd (of the biased batch variance + eps), scale = gamma * invstd, shift = beta - mean * scale
- *                   are written; y = x * scale + shift (ReLU when relu != 0), bf16; moving_mean / moving_var (may be NULL)
- *                   <- momentum * moving + (1 - momentum) * batch.
+ *                   are written; y = x * scale + shift (ReLU when relu & 1), bf16; moving_mean / moving_var (may be NULL)
+ *                   <- momentum * moving + (1 - momentum) * batch. relu & 2: the moving variance takes the Bessel-
+ *                   corrected batch variance var * P / (P - 1), as Keras's FUSED BatchNormalization does (rank-4 inputs).
  * backward [async]: g = dy (masked by y > 0 when relu != 0); dgamma = sum g * xhat, dbeta = sum g,
  *                   dx = gamma * invstd * (g - mean(g) - xhat * mean(g * xhat)), bf16; mean_g / mean_gx are scratch outputs. */
 int64_t lisec_bn_workspace_bytes(int64_t positions, int32_t channels);

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kBnFinThreads)
     bn_finalize_kernel(const double* __restrict__ partial, int blocks, long long P, int C, float eps, float momentum,
                        const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ o0,
                        float* __restrict__ o1, float* __restrict__ o2, float* __restrict__ o3,
-                       float* __restrict__ moving_mean, float* __restrict__ moving_var) {
+                       float* __restrict__ moving_mean, float* __restrict__ moving_var, int unbiased_moving) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ double sa[kBnFinThreads], sb[kBnFinThreads];
@@ -189,7 +189,9 @@ __global__ void __launch_bounds__(kBnFinThreads)
     o3[c] = (float)((double)beta[c] - mean * sc);
     if (moving_mean) {
       moving_mean[c] = (float)((double)moving_mean[c] * momentum + mean * (1.0 - (double)momentum));
-      moving_var[c] = (float)((double)moving_var[c] * momentum + var * (1.0 - (double)momentum));
+      // Keras's fused BatchNormalization (rank-4 inputs) feeds the Bessel-corrected variance to the moving average
+      const double mv = (unbiased_moving && P > 1) ? var * (double)P / (double)(P - 1) : var;
+      moving_var[c] = (float)((double)moving_var[c] * momentum + mv * (1.0 - (double)momentum));
     }
   } else if (MODE == 2) {
     o0[c] = (float)a;  // plain column sums: a convolution's bias gradient = sum over positions of dy
@@ -297,13 +299,14 @@ int32_t lisec_bn_train_forward(const void* x, int64_t positions, int32_t channel
                              (const float*)invstd, (long long)positions, (int)channels, 0, part);
   if (e == cudaSuccess)
     e = launch_pdl(bn_finalize_kernel<0>, dim3(channels / kBnFinChannels), dim3(kBnFinThreads), 0, st, (const double*)part, blocks, (long long)positions,
-                   (int)channels, eps, momentum, gamma, beta, mean, invstd, scale, shift, moving_mean, moving_var);
+                   (int)channels, eps, momentum, gamma, beta, mean, invstd, scale, shift, moving_mean, moving_var,
+                   (int)((relu >> 1) & 1));
   const long long n8 = positions * channels / 8;
   long long ab = (n8 + kBnThreads - 1) / kBnThreads;
   if (ab > 148 * 16) ab = 148 * 16;
   if (e == cudaSuccess)
     e = launch_pdl(bn_apply_kernel, dim3((unsigned)ab), dim3(kBnThreads), 0, st, xb, (const float*)scale,
-                   (const float*)shift, n8, (int)(channels / 8), (int)relu, static_cast<__nv_bfloat16*>(y));
+                   (const float*)shift, n8, (int)(channels / 8), (int)(relu & 1), static_cast<__nv_bfloat16*>(y));
   if (e != cudaSuccess) return bn_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
   return LISEC_OK;
 }
@@ -321,7 +324,7 @@ int32_t lisec_channel_sums(const void* x, int64_t positions, int32_t channels, f
   if (e == cudaSuccess)
     e = launch_pdl(bn_finalize_kernel<2>, dim3(channels / kBnFinChannels), dim3(kBnFinThreads), 0, st, (const double*)part, blocks, (long long)positions,
                    (int)channels, 0.f, 0.f, (const float*)sums, (const float*)sums, sums, sums, sums, sums,
-                   (float*)nullptr, (float*)nullptr);
+                   (float*)nullptr, (float*)nullptr, 0);
   if (e != cudaSuccess) return bn_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
   return LISEC_OK;
 }
@@ -347,7 +350,7 @@ static int32_t bn_backward_impl(const void* x, const void* dy, int dy_f32, const
                                       (long long)positions, (int)channels, (int)relu, part);
   if (e == cudaSuccess)
     e = launch_pdl(bn_finalize_kernel<1>, dim3(channels / kBnFinChannels), dim3(kBnFinThreads), 0, st, (const double*)part, blocks, (long long)positions,
-                   (int)channels, 0.f, 0.f, gamma, gamma, dgamma, dbeta, mean_g, mean_gx, (float*)nullptr, (float*)nullptr);
+                   (int)channels, 0.f, 0.f, gamma, gamma, dgamma, dbeta, mean_g, mean_gx, (float*)nullptr, (float*)nullptr, 0);
   const long long n8 = positions * channels / 8;
   long long ab = (n8 + kBnThreads - 1) / kBnThreads;
   if (ab > 148 * 16) ab = 148 * 16;

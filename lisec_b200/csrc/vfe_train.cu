@@ -201,29 +201,33 @@ __global__ void __launch_bounds__(kTrThreads) tr_colsum_kernel(const float* __re
   }
 }
 
-// column c of the blocks' partial sums [nblocks][2][C], in a fixed order: eight independent running sums (blocks b = 0..7
-// mod 8) keep eight loads in flight instead of one dependent chain of float64 adds, then one fixed-order combination
+// Column sums of the blocks' partials [nblocks][2][C] in a fixed order, by a block of kFinThreads threads that owns 8
+// channels (blockIdx.x * 8 ..): thread (slice, channel) adds blocks slice, slice + 128, ..., thread (0, channel) then adds
+// the 128 slice sums in order. (One thread per channel walking all 296 slots in a dependent chain of float64 adds took
+// ~55 us per call, six calls per step.) Returns true for the threads that hold a channel's totals.
+constexpr int kFinThreads = 1024, kFinChannels = 8;
 template <int C>
-__device__ __forceinline__ void sum_partials(const double* __restrict__ partial, int nblocks, int c, double& sa, double& sb) {
-  double a8[8], b8[8];
-#pragma unroll
-  for (int u = 0; u < 8; ++u) a8[u] = b8[u] = 0.0;
-  int b = 0;
-  for (; b + 7 < nblocks; b += 8) {
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      a8[u] += partial[(size_t)(b + u) * 2 * C + c];
-      b8[u] += partial[(size_t)(b + u) * 2 * C + C + c];
-    }
+__device__ __forceinline__ bool sum_partials(const double* __restrict__ partial, int nblocks, int& c, double& sa, double& sb) {
+  __shared__ double s_a[kFinThreads], s_b[kFinThreads];
+  constexpr int S = kFinThreads / kFinChannels;
+  const int lc = threadIdx.x % kFinChannels, sl = threadIdx.x / kFinChannels;
+  c = blockIdx.x * kFinChannels + lc;
+  double a = 0.0, b = 0.0;
+  for (int g = sl; g < nblocks; g += S) {
+    a += partial[(size_t)g * 2 * C + c];
+    b += partial[(size_t)g * 2 * C + C + c];
   }
-#pragma unroll
-  for (int u = 0; u < 7; ++u)
-    if (b + u < nblocks) {
-      a8[u] += partial[(size_t)(b + u) * 2 * C + c];
-      b8[u] += partial[(size_t)(b + u) * 2 * C + C + c];
-    }
-  sa = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
-  sb = ((b8[0] + b8[1]) + (b8[2] + b8[3])) + ((b8[4] + b8[5]) + (b8[6] + b8[7]));
+  s_a[threadIdx.x] = a;
+  s_b[threadIdx.x] = b;
+  __syncthreads();
+  if (sl != 0) return false;
+  for (int k = 1; k < S; ++k) {
+    a += s_a[k * kFinChannels + lc];
+    b += s_b[k * kFinChannels + lc];
+  }
+  sa = a;
+  sb = b;
+  return true;
 }
 
 // batch statistics -> folded BN, moving statistics (momentum 0.99; the biased batch variance: these 6-D inputs take
@@ -233,10 +237,9 @@ __global__ void tr_stats_finalize_kernel(const double* __restrict__ partial, int
                                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                          float momentum, float* __restrict__ moving_mean, float* __restrict__ moving_var,
                                          float* __restrict__ bn) {
-  const int c = threadIdx.x;
-  if (c >= C) return;
+  int c;
   double sa = 0.0, sb = 0.0;
-  sum_partials<C>(partial, nblocks, c, sa, sb);
+  if (!sum_partials<C>(partial, nblocks, c, sa, sb)) return;
   const double M = (double)ncells * (double)T;
   const double mean = sa / M, var = fmax(sb / M - mean * mean, 0.0);
   const double inv = 1.0 / sqrt(var + (double)eps);
@@ -255,10 +258,9 @@ __global__ void tr_stats_finalize_kernel(const double* __restrict__ partial, int
 template <int C>
 __global__ void tr_bn_bwd_finalize_kernel(const double* __restrict__ partial, int nblocks, long long ncells, int T,
                                           float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ bn) {
-  const int c = threadIdx.x;
-  if (c >= C) return;
+  int c;
   double sa = 0.0, sb = 0.0;
-  sum_partials<C>(partial, nblocks, c, sa, sb);
+  if (!sum_partials<C>(partial, nblocks, c, sa, sb)) return;
   const double M = (double)ncells * (double)T;
   dgamma[c] = (float)sb;
   dbeta[c] = (float)sa;
@@ -309,16 +311,19 @@ __global__ void __launch_bounds__(256) tr_gather_dout_kernel(const float* __rest
       *reinterpret_cast<const float4*>(dgrid + (size_t)voxel_cell[v] * 64 + 4 * q);
 }
 // the empty row's share: sum of dgrid over the EMPTY cells = (sum over all cells) - (sum over the occupied ones)
-__global__ void tr_empty_dout_kernel(const double* __restrict__ part_all, const double* __restrict__ part_occ, int nblocks,
-                                     const long long* __restrict__ totals, float* __restrict__ gpool) {
-  const int c = threadIdx.x;
-  if (c >= 64) return;
-  double all = 0.0, occ = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    all += part_all[(size_t)b * 128 + c];
-    occ += part_occ[(size_t)b * 128 + c];
-  }
-  gpool[(size_t)totals[TOT_VOXELS] * 64 + c] = (float)(all - occ);
+__global__ void __launch_bounds__(1024) tr_empty_dout_kernel(const double* __restrict__ part_all,
+                                                             const double* __restrict__ part_occ, int nblocks,
+                                                             const long long* __restrict__ totals, float* __restrict__ gpool) {
+  // 8 channels per block x 128 slices of the partial slots, fixed order (as sum_partials, defined further down)
+  __shared__ double s_d[1024];
+  const int lc = threadIdx.x & 7, sl = threadIdx.x >> 3, c = blockIdx.x * 8 + lc;
+  double d = 0.0;
+  for (int b = sl; b < nblocks; b += 128) d += part_all[(size_t)b * 128 + c] - part_occ[(size_t)b * 128 + c];
+  s_d[threadIdx.x] = d;
+  __syncthreads();
+  if (sl != 0) return;
+  for (int k = 1; k < 128; ++k) d += s_d[k * 8 + lc];
+  gpool[(size_t)totals[TOT_VOXELS] * 64 + c] = (float)d;
 }
 
 // ---- max + ReLU backward: thread = (voxel, 4 channels) -------------------------------------------------------
@@ -574,7 +579,7 @@ cudaError_t forward_layer(lisec_handle* h, const lisec_vfe_train_params* p, long
       s->x0, L > 0 ? s->pooled[L - 1] : nullptr, L > 0 ? s->hh[L - 1] : nullptr, s->seg, p->dense_kernel[L], tot, s->u[L]);
   tr_colsum_kernel<COUT, 0><<<kTrBlocks, kTrThreads, 0, st>>>(s->u[L], nullptr, s->w, nullptr, tot + TOT_ROWS, 1, 0,
                                                              s->partial);
-  tr_stats_finalize_kernel<COUT><<<1, 64, 0, st>>>(s->partial, kTrBlocks, ncells, h->geom.T, p->bn_gamma[L], p->bn_beta[L],
+  tr_stats_finalize_kernel<COUT><<<COUT / kFinChannels, kFinThreads, 0, st>>>(s->partial, kTrBlocks, ncells, h->geom.T, p->bn_gamma[L], p->bn_beta[L],
                                                   p->bn_epsilon, p->bn_momentum, p->moving_mean[L], p->moving_var[L],
                                                   s->bn[L]);
   tr_act_pool_kernel<COUT><<<blocks_for(s->max_vox * (COUT / 4)), 256, 0, st>>>(s->u[L], s->bn[L], h->ws.row_start, tot,
@@ -593,7 +598,7 @@ cudaError_t backward_layer(lisec_handle* h, const lisec_vfe_train_params* p, con
       s->hh[L], s->pooled[L], s->w, s->gpool, s->ggath, s->gdir, h->ws.row_start, tot, s->gy);
   tr_colsum_kernel<COUT, 1><<<kTrBlocks, kTrThreads, 0, st>>>(s->gy, s->u[L], nullptr, s->bn[L], tot + TOT_ROWS, 1, 0,
                                                              s->partial);
-  tr_bn_bwd_finalize_kernel<COUT><<<1, 64, 0, st>>>(s->partial, kTrBlocks, ncells, h->geom.T, g->dgamma[L], g->dbeta[L],
+  tr_bn_bwd_finalize_kernel<COUT><<<COUT / kFinChannels, kFinThreads, 0, st>>>(s->partial, kTrBlocks, ncells, h->geom.T, g->dgamma[L], g->dbeta[L],
                                                    s->bn[L]);
   // (ggath / gdir of THIS layer have been consumed by the pool backward above: the data gradient may overwrite them)
   tr_dense_bwd_kernel<CIN, COUT, (L > 0)><<<blocks_for(s->max_rows), kTrThreads, 0, st>>>(
@@ -678,7 +683,7 @@ int32_t lisec_vfe_train_backward(lisec_handle* h, const lisec_vfe_train_params* 
   tr_colsum_kernel<64, 2><<<kTrBlocks, kTrThreads, 0, st>>>(dgrid, nullptr, nullptr, nullptr, nullptr, 0, ncells, s->partial);
   tr_colsum_kernel<64, 2><<<kTrBlocks, kTrThreads, 0, st>>>(s->gpool, nullptr, nullptr, nullptr, tot + TOT_VOXELS, 0, 0,
                                                            s->partial + (size_t)kTrBlocks * 128);
-  tr_empty_dout_kernel<<<1, 64, 0, st>>>(s->partial, s->partial + (size_t)kTrBlocks * 128, kTrBlocks, tot, s->gpool);
+  tr_empty_dout_kernel<<<8, 1024, 0, st>>>(s->partial, s->partial + (size_t)kTrBlocks * 128, kTrBlocks, tot, s->gpool);
   h->launches += 4;
   LISEC_CUDA(h, cudaGetLastError());
   LISEC_CUDA(h, backward_layer<2>(h, p, g, ncells, st));

@@ -263,15 +263,12 @@ class BatchNormTrain:
         with torch.cuda.device(self.x.device):
             st = self._lib.lisec_bn_train_forward(
                 self._p(self.x), self.P, self.C, self._p(self.gamma), self._p(self.beta), C.c_float(self.eps),
-                C.c_float(self.momentum), self._p(self.moving_mean), self._p(self.moving_var), int(self.relu),
+                C.c_float(self.momentum), self._p(self.moving_mean), self._p(self.moving_var),
+                int(self.relu) | (2 if self.unbiased_moving else 0),  # bit 1: Bessel-corrected moving variance (in the kernel)
                 self._p(self.y), self._p(self.mean), self._p(self.invstd), self._p(self.scale), self._p(self.shift),
                 self._p(self.workspace), self._stream())
         if st != N.LISEC_OK:
             raise N.LisecError(st, self._lib.lisec_bn_last_error().decode("utf-8", "replace"))
-        if self.unbiased_moving and self.moving_var is not None and self.P > 1:
-            # the kernel added (1 - m) * var; the fused path's var * P / (P - 1) differs by (1 - m) * var / (P - 1)
-            var = self.invstd.double().pow(-2) - self.eps
-            self.moving_var.add_(((1.0 - self.momentum) / (self.P - 1) * var).float())
         return self.y
 
     def backward(self, dy: torch.Tensor) -> torch.Tensor:
