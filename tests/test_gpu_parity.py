@@ -375,6 +375,39 @@ def test_other_sample_sizes_small_grid(T):
     f.close()
 
 
+@pytest.mark.parametrize("size", [(0.3, 0.2, 0.25), (0.7, 0.1, 0.3)])
+def test_voxel_sizes_that_are_not_powers_of_two(size):
+    """get_voxel divides by the voxel size (model_training.py:103-107). Constants.py's sizes are powers of two, where
+    x * (1 / size) is the same float64 as x / size; for any other size the kernel must really divide. Points ON cell
+    borders (k * size in float64, and its float64 neighbours) and on the range limits are where a reciprocal would differ:
+    coordinates, counts, ordered lists and feature rows bit-exact against the oracle."""
+    from lisec_b200 import Frontend
+
+    xs, ys, zs = size
+    mx, my, mz, T = 20, 30, 6, 35
+    args = dict(xSize=xs, ySize=ys, zSize=zs, sampleSize=T, maxVoxelX=mx, maxVoxelY=my, maxVoxelZ=mz)
+    rng = np.random.default_rng(17)
+    n = 20_000
+    pts = np.stack([rng.uniform(-mx * xs * 1.05, mx * xs * 1.05, n), rng.uniform(-my * ys * 1.05, my * ys * 1.05, n),
+                    rng.uniform(-0.1 * zs, mz * zs * 1.05, n)], axis=1)
+    kx, ky, kz = rng.integers(-mx - 1, mx + 2, 3000), rng.integers(-my - 1, my + 2, 3000), rng.integers(-1, mz + 2, 3000)
+    border = np.stack([kx * xs, ky * ys, kz * zs], axis=1)  # exactly on cell borders, the range limits included
+    up, down = np.nextafter(border, np.inf), np.nextafter(border, -np.inf)
+    pts = np.concatenate([pts, border, up, down])
+    rng.shuffle(pts)
+    f = Frontend(max_points=len(pts), max_sweeps=1, voxel_size=size, max_voxel=(mx, my, mz), sample_size=T)
+    f.voxelize(pts, [0, len(pts)])
+    vs = f.export()
+    ref = O.voxelize_np(pts, **args)
+    assert ref["n_out_of_range"] > 0 and len(ref["counts"]) > 1000
+    assert vs.n_dropped_out_of_range == ref["n_out_of_range"]
+    assert np.array_equal(vs.coords.cpu().numpy()[:, 1:], ref["coords"])
+    assert np.array_equal(vs.counts.cpu().numpy(), ref["counts"])
+    assert np.array_equal(vs.point_idx.cpu().numpy(), ref["point_idx"])
+    assert vs.features.cpu().numpy().tobytes() == ref["features"].astype(np.float32).tobytes()
+    f.close()
+
+
 def test_bf16_fused_grid_every_cell_written():
     from lisec_b200 import Frontend
 
