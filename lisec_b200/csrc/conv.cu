@@ -572,13 +572,24 @@ __global__ void __launch_bounds__(GATHER ? kConvGatherThreads : kConvThreads, 1)
     // = the lane's row lane + 32 k) — ~60 rows of 8 stores instead of 324.
     unsigned dirty = 0;
     int2* s_list = reinterpret_cast<int2*>(reinterpret_cast<unsigned char*>(s_cempty) + 128) + (size_t)g * kGatherList;
+    // a row's 16-byte chunks are XOR-swizzled with bits 7..9 of its absolute address; slots are 1 KB aligned, so that is
+    // row & 7 — for the lane's own rows (lane + 32 k) simply lane & 7
     auto store_row = [&](int r, const uint4 (&ch)[8]) {
-      const uint32_t row_addr = slot_addr + (uint32_t)r * 128u;
-      const uint32_t sw = (row_addr >> 7) & 7u;
+      const uint32_t sw = (uint32_t)r & 7u;
       unsigned char* row_ptr = slot + (size_t)r * 128;
 #pragma unroll
       for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(row_ptr + (((uint32_t)c ^ sw) << 4)) = ch[c];
     };
+    // what does not depend on the box: (h, w) of the lane's rows inside a box (the only division), packed h << 16 | w
+    int hw[11];
+    unsigned valid = 0;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+      const int r = lane + 32 * k;
+      const int hh = r / P.box_w;
+      hw[k] = (hh << 16) | (r - hh * P.box_w);
+      if (r < rows) valid |= 1u << k;
+    }
     {
       uint4 ce[8];  // (s_cempty was written before the set-up barrier)
 #pragma unroll
@@ -591,47 +602,40 @@ __global__ void __launch_bounds__(GATHER ? kConvGatherThreads : kConvThreads, 1)
         if ((int)(n % P.a_slots) != g) continue;
         const int w0 = t.ow0 + P.t1[0], h0 = t.oh0 + P.t2[0], dz = t.od * P.stride_d + kd + P.t3[0];
         const bool d_ok = dz >= 0 && dz < P.in_d;
-        const long long plane = ((long long)t.b * P.in_d + dz) * P.in_h;
+        const int* cells = P.g_cell_voxel + (((long long)t.b * P.in_d + dz) * P.in_h + h0) * P.in_w + w0;
         // the occupancy words of the lane's rows first (independent loads), before waiting for the slot
         int vox[11];
 #pragma unroll
         for (int k = 0; k < 11; ++k) {
-          const int r = lane + 32 * k;
-          const int hh = r / P.box_w, ww = r - hh * P.box_w;
-          const int h = h0 + hh, w = w0 + ww;
-          const bool ok = r < rows && d_ok && h >= 0 && h < P.in_h && w >= 0 && w < P.in_w;
-          vox[k] = ok ? __ldcg(P.g_cell_voxel + (plane + h) * P.in_w + w) : -2;  // -1: empty cell, -2: outside the grid
+          const int hh = hw[k] >> 16, ww = hw[k] & 0xffff;
+          const bool ok = ((valid >> k) & 1u) && d_ok && (unsigned)(h0 + hh) < (unsigned)P.in_h &&
+                          (unsigned)(w0 + ww) < (unsigned)P.in_w;
+          vox[k] = ok ? __ldcg(cells + hh * P.in_w + ww) : -2;  // -1: empty cell, -2: outside the grid
         }
         umma::mbar_wait(bar_a_empty(g), (use & 1u) ^ 1u);
         // rows without a voxel behind them: zeros outside the grid, c_empty back where the slot's last box left something
-        // else. The occupied rows are only LISTED here (row, voxel), compacted over the warp: fetching them inside this
-        // loop costs one dependent L2 round trip per k for the whole warp (some lane has an occupied row at almost every
-        // k) — eleven per box. (Fetching the list's first 32 rows BEFORE the wait, so that the slot is not held for a
-        // round trip, measured slower: 0.78 against 0.70 ms.)
+        // else (one store path for both). The occupied rows are only LISTED here (row, voxel), compacted over the warp:
+        // fetching them inside this loop costs one dependent L2 round trip per k for the whole warp (some lane has an
+        // occupied row at almost every k) — eleven per box. (Fetching the list's first 32 rows BEFORE the wait, so that
+        // the slot is not held for a round trip, measured slower: 0.78 against 0.70 ms.)
         int n_occ = 0;
+        const uint32_t lane_sw = (uint32_t)lane & 7u;
 #pragma unroll
         for (int k = 0; k < 11; ++k) {
-          const int r = lane + 32 * k;
-          const bool occ = r < rows && vox[k] >= 0;
+          const unsigned bit = 1u << k;
+          const bool live = (valid & bit) != 0;
+          const bool occ = live && vox[k] >= 0;
           const unsigned m = __ballot_sync(0xffffffffu, occ);
-          if (occ) {
-            s_list[n_occ + __popc(m & ((1u << lane) - 1u))] = make_int2(r, vox[k]);
-            dirty |= 1u << k;
-          }
+          if (occ) s_list[n_occ + __popc(m & ((1u << lane) - 1u))] = make_int2(lane + 32 * k, vox[k]);
           n_occ += __popc(m);
-          if (r >= rows || occ) continue;
-          uint4 ch[8];
-          if (vox[k] == -2) {
+          const bool zero = live && vox[k] == -2;
+          if (zero || (live && !occ && (dirty & bit))) {
+            unsigned char* row_ptr = slot + (size_t)(lane + 32 * k) * 128;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) ch[c] = make_uint4(0u, 0u, 0u, 0u);
-            store_row(r, ch);
-            dirty |= 1u << k;
-          } else if (dirty & (1u << k)) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) ch[c] = s_cempty[c];
-            store_row(r, ch);
-            dirty &= ~(1u << k);
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<uint4*>(row_ptr + (((uint32_t)c ^ lane_sw) << 4)) = zero ? make_uint4(0u, 0u, 0u, 0u) : s_cempty[c];
           }
+          dirty = (occ || zero) ? (dirty | bit) : (dirty & ~bit);
         }
         __syncwarp();
         for (int i0 = 0; i0 < n_occ; i0 += 32) {  // one occupied row per lane and round: a single round trip for ~26 rows
