@@ -103,11 +103,30 @@ def mse_loss_grad(y: torch.Tensor, target: torch.Tensor, want_grad: bool = True)
     return acc / y.numel(), dy
 
 
+class _GradSink:
+    """Where the stage under construction should write its parameter gradients: {"dw" | "dwd" | "dgamma" | "dbeta":
+    float32 CUDA tensor}. DenseNetworkTrainer fills it with views of the caller's flat gradient buffer (TrainStep), so that
+    the weight-gradient plans and the BatchNormalization backward write straight into the buffer the all-reduce and the
+    optimizer read — no per-tensor copies after the backward pass. Empty: every stage owns its gradient tensors."""
+    current: Dict[str, torch.Tensor] = {}
+
+    @staticmethod
+    def take(key: str, shape, device) -> torch.Tensor:
+        t = _GradSink.current.get(key)
+        if t is None:
+            return torch.empty(shape, dtype=torch.float32, device=device)
+        if t.numel() != int(np.prod(shape)) or not t.is_contiguous() or t.dtype != torch.float32:
+            raise ValueError("gradient sink %r: %s does not hold shape %s" % (key, tuple(t.shape), tuple(shape)))
+        return t.view(shape)
+
+
 class ConvWgrad:
     """dW of one convolution layer (lisec_conv_wgrad_plan_*, lisec_b200/csrc/wgrad.cu): x bf16 [B,D,H,W,C], dy bf16
     [B,OD,OH,OW,N] -> dw float32 [taps, N, C] (the forward plans' weight layout). Buffers are bound at construction."""
 
-    def __init__(self, x: torch.Tensor, dy: torch.Tensor, k, stride_d: int, pad, tile=(16, 8), stride_hw: int = 1):
+    def __init__(self, x: torch.Tensor, dy: torch.Tensor, k, stride_d: int, pad, tile=(16, 8), stride_hw: int = 1,
+                 sink: Optional[str] = None):
+        """sink: the _GradSink key this plan's dw should be taken from (None: a tensor of its own)."""
         if x.dtype != torch.bfloat16 or dy.dtype != torch.bfloat16 or not x.is_cuda or x.dim() != 5 or dy.dim() != 5:
             raise ValueError("x, dy: cuda bf16 [B, D, H, W, C]")
         self._lib = N.load()
@@ -119,7 +138,8 @@ class ConvWgrad:
             out_ch_off=0, relu=0, out_dtype=N.LISEC_F32, tile_w=tile[0], tile_h=tile[1], m_tiles=1, in_dtype=N.LISEC_BF16,
             out_split=0, group_kh=0, reserved=0)
         taps = k[0] * k[1] * k[2]
-        self.dw = torch.empty((taps, dy.shape[-1], Cin), dtype=torch.float32, device=x.device)
+        shape = (taps, dy.shape[-1], Cin)
+        self.dw = _GradSink.take(sink, shape, x.device) if sink else torch.empty(shape, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             ws = int(self._lib.lisec_conv_wgrad_workspace_bytes(C.byref(self.desc)))
             self.workspace = torch.empty(ws // 4, dtype=torch.float32, device=x.device)
@@ -249,7 +269,8 @@ class BatchNormTrain:
         self.workspace = torch.empty(ws // 8, dtype=torch.float64, device=dev)
         vec = lambda: torch.empty(self.C, dtype=torch.float32, device=dev)  # noqa: E731
         self.mean, self.invstd, self.scale, self.shift = vec(), vec(), vec(), vec()
-        self.dgamma, self.dbeta, self._mg, self._mgx = vec(), vec(), vec(), vec()
+        self.dgamma, self.dbeta = _GradSink.take("dgamma", (self.C,), dev), _GradSink.take("dbeta", (self.C,), dev)
+        self._mg, self._mgx = vec(), vec()
         self.y = torch.empty_like(x)
         self.dx = torch.empty_like(x)
 
@@ -324,7 +345,7 @@ class ConvBnReluTrain:
             raise N.LisecError(st, self._lib.lisec_conv_last_error().decode("utf-8", "replace"))
         self.bn = BatchNormTrain(self.z, gamma, beta, moving_mean, moving_var, relu=relu,
                                  unbiased_moving=(k[0] == 1))  # Conv2D stages: rank-4 input, Keras's fused path
-        self.wgrad = ConvWgrad(x, self.bn.dx, k, 1, pad, tile=tile, stride_hw=s)  # dz lands in bn.dx
+        self.wgrad = ConvWgrad(x, self.bn.dx, k, 1, pad, tile=tile, stride_hw=s, sink="dw")  # dz lands in bn.dx
         self.dgrad = None
         if need_dx:
             self.dgrad = (ConvDgrad(self.bn.dx, w, k, pad, out_dtype=grad_dtype) if s == 1 else
@@ -486,9 +507,9 @@ class Conv3dBlockTrain:
         self.refresh_weights()
         self.conv_plan = plan(x, self.w16, bias, self.z, k, pad, stride_d, Cin, Nout, 0)
         self.dense_plan = plan(self.bn.y, self.wd16, self.zeros, self.y, (1, 1, 1), (0, 0, 0), 1, Nout, N2, 1)
-        self.dense_wgrad = ConvWgrad(self.bn.y, self.dv, (1, 1, 1), 1, (0, 0, 0), tile=tile)
+        self.dense_wgrad = ConvWgrad(self.bn.y, self.dv, (1, 1, 1), 1, (0, 0, 0), tile=tile, sink="dwd")
         self.dense_dgrad = ConvDgrad(self.dv, wd, (1, 1, 1), (0, 0, 0), out_dtype=grad_dtype)  # du: gradient at the BN output
-        self.conv_wgrad = ConvWgrad(x, self.bn.dx, k, stride_d, pad, tile=tile)    # dz lands in bn.dx
+        self.conv_wgrad = ConvWgrad(x, self.bn.dx, k, stride_d, pad, tile=tile, sink="dw")    # dz lands in bn.dx
         self.conv_dgrad = None
         if need_dx:
             self.conv_dgrad = (ConvDgrad(self.bn.dx, w, k, pad, out_dtype=grad_dtype) if stride_d == 1 else
@@ -672,10 +693,10 @@ class ConvBiasTrain:
                                                   C.c_void_p(out.data_ptr()), C.byref(self.plan))
         if st != N.LISEC_OK:
             raise N.LisecError(st, self._lib.lisec_conv_last_error().decode("utf-8", "replace"))
-        self.wgrad = ConvWgrad(x, dy, k, 1, pad, tile=tile)
+        self.wgrad = ConvWgrad(x, dy, k, 1, pad, tile=tile, sink="dw")
         self.P = dy.numel() // Nout
         self.ws = torch.empty(int(self._lib.lisec_bn_workspace_bytes(self.P, Nout)) // 8, dtype=torch.float64, device=dev)
-        self.dbias = torch.empty(Nout, dtype=torch.float32, device=dev)
+        self.dbias = _GradSink.take("dbias", (Nout,), dev)
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.x.device).cuda_stream)
@@ -944,10 +965,12 @@ class DenseNetworkTrainer:
     the grid is not part of this class (its training kernels are not built yet): `grid` is an input."""
 
     def __init__(self, pack: dict, batch: int, nx: int, ny: int, nz: int = 8, device: int = 0, alloc=None,
-                 need_grid_grad: bool = False):
+                 need_grid_grad: bool = False, grad_alloc=None):
         """alloc(name, float32 array) -> CUDA tensor holding it: where a trainable weight's master copy lives (default:
         its own tensor; TrainStep hands out views of one flat buffer). need_grid_grad: also compute d loss / d grid
-        (float32, self.grid_grad after loss_and_backward) for the VFE stack in front."""
+        (float32, self.grid_grad after loss_and_backward) for the VFE stack in front. grad_alloc(name) -> the float32 CUDA
+        tensor that weight's gradient belongs in (TrainStep: a view of the flat gradient buffer): the weight-gradient plans
+        and BatchNormalization backward kernels of the plain stages then write there directly (_GradSink)."""
         from .weights import conv3d_blocks, rpn_blocks
 
         self._lib = N.load()
@@ -959,8 +982,13 @@ class DenseNetworkTrainer:
         def mk(name, a):  # trainable weights go through alloc(); moving statistics stay in tensors of their own
             return alloc(name, a) if (alloc is not None and "moving_" not in name) else own(a)
 
+        _GradSink.current = {}  # (nothing left over from a construction that failed half way)
         self.params, self.stages = {}, []
+        self.zero_grads = set()  # biases in front of a training-mode BatchNormalization: gradient identically zero
         self.grid_grad = None
+
+        def sink(**names):  # the gradient tensors of the stage constructed next
+            _GradSink.current = {k: grad_alloc(v) for k, v in names.items()} if grad_alloc is not None else {}
         self.grid = torch.zeros((B, nz, nx, ny, 64), dtype=torch.bfloat16, device=dev)
         P = self.params
         x, d = self.grid, nz
@@ -972,6 +1000,8 @@ class DenseNetworkTrainer:
                 P[conv + "/" + f] = mk(conv + "/" + f, pack[conv + "/" + f])
             for f in ("gamma", "beta", "moving_mean", "moving_variance"):
                 P[bn + "/" + f] = mk(bn + "/" + f, pack[bn + "/" + f])
+            sink(dw=conv + "/kernel", dwd=dense + "/kernel", dgamma=bn + "/gamma", dbeta=bn + "/beta")
+            self.zero_grads.add(conv + "/bias")
             st = Conv3dBlockTrain(x, P[conv + "/kernel"], P[conv + "/bias"], P[bn + "/gamma"], P[bn + "/beta"],
                                   P[dense + "/kernel"], (3, 3, 3), pad, stride_d=stride[0],
                                   moving_mean=P[bn + "/moving_mean"], moving_var=P[bn + "/moving_variance"],
@@ -989,6 +1019,8 @@ class DenseNetworkTrainer:
                 P[conv + "/bias"] = mk(conv + "/bias", pack[conv + "/bias"])
                 for f in ("gamma", "beta", "moving_mean", "moving_variance"):
                     P[bn + "/" + f] = mk(bn + "/" + f, pack[bn + "/" + f])
+                sink(dw=conv + "/kernel", dgamma=bn + "/gamma", dbeta=bn + "/beta")
+                self.zero_grads.add(conv + "/bias")
                 st = ConvBnReluTrain(x, P[conv + "/kernel"], P[conv + "/bias"], P[bn + "/gamma"], P[bn + "/beta"], (1, 3, 3),
                                      (0, 1, 1), moving_mean=P[bn + "/moving_mean"], moving_var=P[bn + "/moving_variance"],
                                      stride_hw=stride, grad_dtype=torch.float32)
@@ -999,16 +1031,20 @@ class DenseNetworkTrainer:
             dy_t = torch.zeros((B, 1, nx // 2, ny // 2, 256), dtype=torch.bfloat16, device=dev)
             if s == 1:
                 P[tname + "/kernel"] = mk(tname + "/kernel", F[::-1, ::-1].reshape(9, 256, tc_in))  # the flipped-kernel convolution's layout
+                sink(dw=tname + "/kernel", dbias=tname + "/bias")
                 tail = ConvBiasTrain(x, P[tname + "/kernel"], P[tname + "/bias"], (1, 3, 3), (0, 1, 1), self.concat, 256 * bi, dy_t,
                                      grad_dtype=torch.float32)
             else:
                 P[tname + "/kernel"] = mk(tname + "/kernel", F)  # Keras layout (k, k, 256, cin)
+                sink()
                 tail = _ShuffleTail(self._lib, x, P[tname + "/kernel"], P[tname + "/bias"], s, self.concat, 256 * bi, dy_t)
             self.blocks.append((stages, tail, tname, s, dy_t, x))
         Kh = np.concatenate([np.asarray(pack["ClassificationLayer/kernel"])[0, 0], np.asarray(pack["RegressionLayer/kernel"])[0, 0]], axis=1)
         P["heads/kernel"] = mk("heads/kernel", Kh.T[None])  # [1][16][768]: rows 0-1 ClassificationLayer, 2-15 RegressionLayer
         P["heads/bias"] = mk("heads/bias", np.concatenate([pack["ClassificationLayer/bias"], pack["RegressionLayer/bias"]]))
+        sink()
         self.heads = HeadsTrain(self.concat, P["heads/kernel"], P["heads/bias"], dense_slices=True)
+        _GradSink.current = {}
         self.grads = {}
 
     def forward(self, grid: Optional[torch.Tensor] = None):
@@ -1108,7 +1144,8 @@ class TrainStep:
             for f in ("moving_mean", "moving_variance"):
                 self.vfe_params[b + "/" + f] = torch.from_numpy(np.ascontiguousarray(pack[b + "/" + f], dtype=np.float32)).to(dev)
         self._vfe_end = self.store.used  # flat layout: [VFE stack | dense network]
-        self.dense = DenseNetworkTrainer(pack, batch, nx, ny, nz, device=device, alloc=self.store.alloc, need_grid_grad=True)
+        self.dense = DenseNetworkTrainer(pack, batch, nx, ny, nz, device=device, alloc=self.store.alloc, need_grid_grad=True,
+                                         grad_alloc=self.store.grad_view)
         for k in list(self.vfe_params):
             if "moving_" not in k:
                 vfe_grads[k] = self.store.grad_view(k)
@@ -1171,8 +1208,10 @@ class TrainStep:
         self.dense.forward()
         loss = self.dense.loss_and_backward(y_class, y_regress)
         self._grid_grad = self.dense.grid_grad.contiguous()
-        for name, g in self.dense.grads.items():
-            self.store.grad_view(name).copy_(g.reshape(self.store.shapes[name]))
+        for name, g in self.dense.grads.items():  # what the stages did not write into the flat buffer themselves
+            dst = self.store.grad_view(name)
+            if g.data_ptr() != dst.data_ptr() and name not in self.dense.zero_grads:
+                dst.copy_(g.reshape(self.store.shapes[name]))
         return loss
 
     def to_pack(self) -> Dict[str, np.ndarray]:
