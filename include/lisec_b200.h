@@ -414,6 +414,16 @@ int32_t lisec_pad_channels_bf16(const float* in, int64_t positions, int32_t c_in
 int32_t lisec_add_bf16(void* a, const void* b, int64_t n, void* stream);
 /* [async] float32 master weights -> the bf16 operand copy the plans read. */
 int32_t lisec_cast_f32_to_bf16(const float* w, int64_t n, void* out_bf16, void* stream);
+/* [async] All of a training step's operand refreshes in one launch. entries: DEVICE array of n (<= 256) entries, `first`
+ * = the running sum of the entries' element counts (kd*kh*kw*out_c*in_c), total = its end. mode 0: dst[j] = bf16(src[j]);
+ * mode 1: lisec_weights_flip_transpose of src into dst. */
+typedef struct lisec_refresh_entry {
+  const float* src;
+  void* dst;
+  int64_t first;
+  int32_t kd, kh, kw, out_c, in_c, mode;
+} lisec_refresh_entry;
+int32_t lisec_refresh_operands(const lisec_refresh_entry* entries, int32_t n, int64_t total, void* stream);
 const char* lisec_train_last_error(void);
 
 /* Training-mode BatchNormalization on channels-last bf16 activations [positions][channels] (lisec_b200/csrc/bn.cu): the

@@ -175,6 +175,7 @@ SIGNATURES = {
     "lisec_pad_channels_bf16": (C.c_int32, [_VP, C.c_int64, C.c_int32, C.c_int32, _VP, _VP]),
     "lisec_add_bf16": (C.c_int32, [_VP, _VP, C.c_int64, _VP]),
     "lisec_cast_f32_to_bf16": (C.c_int32, [_VP, C.c_int64, _VP, _VP]),
+    "lisec_refresh_operands": (C.c_int32, [_VP, C.c_int32, C.c_int64, _VP]),
     "lisec_bn_train_backward_f32": (C.c_int32, [_VP, _VP, _VP, C.c_int64, C.c_int32, _VP, _VP, _VP, C.c_int32, _VP, _VP,
                                                 _VP, _VP, _VP, _VP, _VP]),
     "lisec_bn_last_error": (C.c_char_p, []),

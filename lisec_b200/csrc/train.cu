@@ -101,6 +101,40 @@ __global__ void __launch_bounds__(256)
   out[i] = __float2bfloat16(w[((long long)tap * n_out + co) * c_in + ci]);
 }
 
+// Every operand refresh of a training step in ONE launch: a table of (float32 source, bf16 destination, first element,
+// shape, mode) entries — mode 0 a plain cast, mode 1 the flip + transpose above — walked by element index. After an
+// optimizer step every layer's operand copies are re-derived from its master weights: ~90 launches of 2-5 us otherwise.
+constexpr int kRefreshMax = 256;
+__global__ void __launch_bounds__(256) refresh_operands_kernel(const lisec_refresh_entry* __restrict__ tab, int n, long long total) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ long long s_first[kRefreshMax + 1];
+  for (int e = threadIdx.x; e < n; e += blockDim.x) s_first[e] = tab[e].first;
+  if (threadIdx.x == 0) s_first[n] = total;
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int lo = 0, hi = n;  // the entry with first[e] <= i < first[e + 1]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_first[mid] <= i) lo = mid; else hi = mid;
+    }
+    const lisec_refresh_entry& t = tab[lo];
+    const long long j = i - s_first[lo];
+    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(t.dst);
+    if (t.mode == 0) {
+      out[j] = __float2bfloat16(t.src[j]);
+    } else {  // j indexes the OUTPUT [tap'][ci][co]
+      const int co = (int)(j % t.out_c);
+      const int ci = (int)((j / t.out_c) % t.in_c);
+      const int tp = (int)(j / ((long long)t.out_c * t.in_c));
+      const int c = tp % t.kw, b = (tp / t.kw) % t.kh, a = tp / (t.kw * t.kh);
+      const int tap = ((t.kd - 1 - a) * t.kh + (t.kh - 1 - b)) * t.kw + (t.kw - 1 - c);
+      out[j] = __float2bfloat16(t.src[((long long)tap * t.out_c + co) * t.in_c + ci]);
+    }
+  }
+}
+
 // float32 master weights -> the bf16 operand copy the plans read (after every optimizer step)
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ w, long long n, __nv_bfloat16* __restrict__ out) {
   pdl_launch_dependents();
@@ -240,6 +274,16 @@ int32_t lisec_weights_flip_transpose(const float* w, int32_t kd, int32_t kh, int
   cudaError_t e = launch_pdl(flip_transpose_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0,
                              static_cast<cudaStream_t>(stream), w, (int)kd, (int)kh, (int)kw, (int)out_c, (int)in_c,
                              static_cast<__nv_bfloat16*>(out_bf16));
+  if (e != cudaSuccess) return train_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
+  return LISEC_OK;
+}
+
+int32_t lisec_refresh_operands(const lisec_refresh_entry* entries, int32_t n, int64_t total, void* stream) {
+  if (!entries || n < 1 || n > kRefreshMax || total < 1) return train_fail(LISEC_ERR_BAD_ARG, "1..%d entries", kRefreshMax);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  cudaError_t e = launch_pdl(refresh_operands_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                             entries, (int)n, (long long)total);
   if (e != cudaSuccess) return train_fail(LISEC_ERR_CUDA, "%s", cudaGetErrorString(e));
   return LISEC_OK;
 }

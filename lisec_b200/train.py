@@ -103,6 +103,29 @@ def mse_loss_grad(y: torch.Tensor, target: torch.Tensor, want_grad: bool = True)
     return acc / y.numel(), dy
 
 
+class _RefreshBatch:
+    """While `recording` is a list, the operand refreshes of the stages (float32 master weights -> the plans' bf16 operand
+    copies: a cast, or the data-gradient plans' flip + transpose) are RECORDED instead of launched: (src, dst, elements,
+    kd, kh, kw, out_c, in_c, mode). DenseNetworkTrainer records its plain stages once and then refreshes all of them with
+    one lisec_refresh_operands launch per step."""
+    recording: Optional[list] = None
+
+
+def _refresh_cast(lib, src: torch.Tensor, dst: torch.Tensor, stream) -> int:
+    if _RefreshBatch.recording is not None:
+        _RefreshBatch.recording.append((src.data_ptr(), dst.data_ptr(), src.numel(), 1, 1, 1, 0, 0, 0))
+        return N.LISEC_OK
+    return lib.lisec_cast_f32_to_bf16(C.c_void_p(src.data_ptr()), src.numel(), C.c_void_p(dst.data_ptr()), stream)
+
+
+def _refresh_flip(lib, w: torch.Tensor, k, n_out: int, c_in: int, dst: torch.Tensor, stream) -> int:
+    if _RefreshBatch.recording is not None:
+        _RefreshBatch.recording.append((w.data_ptr(), dst.data_ptr(), w.numel(), k[0], k[1], k[2], n_out, c_in, 1))
+        return N.LISEC_OK
+    return lib.lisec_weights_flip_transpose(C.c_void_p(w.data_ptr()), k[0], k[1], k[2], n_out, c_in, C.c_void_p(dst.data_ptr()),
+                                            stream)
+
+
 class _GradSink:
     """Where the stage under construction should write its parameter gradients: {"dw" | "dwd" | "dgamma" | "dbeta":
     float32 CUDA tensor}. DenseNetworkTrainer fills it with views of the caller's flat gradient buffer (TrainStep), so that
@@ -220,8 +243,7 @@ class ConvDgrad:
     def refresh_weights(self) -> None:
         taps, Nout, Cin = self.w.shape
         with torch.cuda.device(self.dy.device):
-            st = self._lib.lisec_weights_flip_transpose(C.c_void_p(self.w.data_ptr()), self.k[0], self.k[1], self.k[2], Nout,
-                                                        Cin, C.c_void_p(self.wt.data_ptr()), self._stream())
+            st = _refresh_flip(self._lib, self.w, self.k, Nout, Cin, self.wt, self._stream())
         if st != N.LISEC_OK:
             raise N.LisecError(st, self._lib.lisec_train_last_error().decode("utf-8", "replace"))
 
@@ -358,8 +380,7 @@ class ConvBnReluTrain:
     def refresh_weights(self) -> None:
         """After an optimizer step: the bf16 operand copies of the master weights."""
         with torch.cuda.device(self.x.device):
-            st = self._lib.lisec_cast_f32_to_bf16(C.c_void_p(self.w.data_ptr()), self.w.numel(),
-                                                  C.c_void_p(self.w16.data_ptr()), self._stream())
+            st = _refresh_cast(self._lib, self.w, self.w16, self._stream())
         if st != N.LISEC_OK:
             raise N.LisecError(st, self._lib.lisec_train_last_error().decode("utf-8", "replace"))
         if getattr(self, "dgrad", None) is not None:
@@ -523,8 +544,7 @@ class Conv3dBlockTrain:
     def refresh_weights(self) -> None:
         with torch.cuda.device(self.x.device):
             for src, dst in ((self.w, self.w16), (self.wd, self.wd16)):
-                st = self._lib.lisec_cast_f32_to_bf16(C.c_void_p(src.data_ptr()), src.numel(), C.c_void_p(dst.data_ptr()),
-                                                      self._stream())
+                st = _refresh_cast(self._lib, src, dst, self._stream())
                 if st != N.LISEC_OK:
                     raise N.LisecError(st, self._lib.lisec_train_last_error().decode("utf-8", "replace"))
         for dg in self._dgrads:
@@ -703,8 +723,7 @@ class ConvBiasTrain:
 
     def refresh_weights(self) -> None:
         with torch.cuda.device(self.x.device):
-            st = self._lib.lisec_cast_f32_to_bf16(C.c_void_p(self.w.data_ptr()), self.w.numel(), C.c_void_p(self.w16.data_ptr()),
-                                                  self._stream())
+            st = _refresh_cast(self._lib, self.w, self.w16, self._stream())
         if st != N.LISEC_OK:
             raise N.LisecError(st, self._lib.lisec_train_last_error().decode("utf-8", "replace"))
         if self.dgrad is not None:
@@ -1089,13 +1108,38 @@ class DenseNetworkTrainer:
         return lc + lr
 
     def refresh_weights(self) -> None:
-        """After the float32 master weights changed (an optimizer step): re-derive the plans' bf16 operand copies."""
-        for st, *_ in self.c3:
-            st.refresh_weights()
+        """After the float32 master weights changed (an optimizer step): re-derive the plans' bf16 operand copies. The
+        plain stages' refreshes (casts and flip-transposes, ~45 of them) are recorded once and run as ONE launch."""
+        plain = [st for st, *_ in self.c3]
         for stages, tail, *_ in self.blocks:
-            for st, *_ in stages:
-                st.refresh_weights()
-            tail.refresh_weights()
+            plain += [st for st, *_ in stages]
+            if isinstance(tail, ConvBiasTrain):
+                plain.append(tail)
+        if getattr(self, "_refresh_table", None) is None:
+            rec: list = []
+            _RefreshBatch.recording = rec
+            try:
+                for st in plain:
+                    st.refresh_weights()
+            finally:
+                _RefreshBatch.recording = None
+            tab = np.zeros(len(rec), dtype=np.dtype([("src", "<u8"), ("dst", "<u8"), ("first", "<i8"), ("kd", "<i4"), ("kh", "<i4"),
+                                                     ("kw", "<i4"), ("out_c", "<i4"), ("in_c", "<i4"), ("mode", "<i4")]))
+            first = 0
+            for i, (src, dst, n, kd, kh, kw, oc, ic, mode) in enumerate(rec):
+                tab[i] = (src, dst, first, kd, kh, kw, oc, ic, mode)
+                first += n
+            self._refresh_total = first
+            self._refresh_table = torch.from_numpy(tab.view(np.uint8).copy()).to(self.device)
+            self._refresh_n = len(rec)
+        with torch.cuda.device(self.device):
+            st_ = self._lib.lisec_refresh_operands(C.c_void_p(self._refresh_table.data_ptr()), self._refresh_n, self._refresh_total,
+                                                   C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        if st_ != N.LISEC_OK:
+            raise N.LisecError(st_, self._lib.lisec_train_last_error().decode("utf-8", "replace"))
+        for stages, tail, *_ in self.blocks:
+            if not isinstance(tail, ConvBiasTrain):
+                tail.refresh_weights()
         self.heads.refresh_weights()
 
     def close(self):
