@@ -563,7 +563,20 @@ int32_t lisec_frontend_forward_host(lisec_handle* h, const void* points_host, in
   void* staging = b ? h->staging2 : h->ws.staging;
   // copy stream: wait until the kernels of two calls ago are done with this buffer, then copy
   LISEC_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_free[b], 0));
-  if (bytes) LISEC_CUDA(h, cudaMemcpyAsync(staging, points_host, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+  // In pieces: the end-to-end step is bound by this copy (9.6 MB per 8 sweeps beside a kernel that saturates HBM), and on
+  // this pool's hosts the rate of a pinned copy is not monotonic in its size (tools/pcie_probe.py). Measured end to end
+  // (tools/e2e_probe.py, two boxes): one copy 0.443 / 0.390 ms per step, 3.2 MB pieces 0.380 / 0.372 ms, 1.6 MB 0.375,
+  // 2.4 MB and 4.8 MB no better or worse than one copy.
+  static const size_t piece = [] {
+    const char* e = getenv("LISEC_H2D_PIECE_BYTES");
+    const long long v = e ? atoll(e) : 3200000LL;
+    return (size_t)(v >= 65536 ? v : 3200000LL) & ~(size_t)255;
+  }();
+  for (size_t off = 0; off < bytes; off += piece) {
+    const size_t nb = bytes - off < piece ? bytes - off : piece;
+    LISEC_CUDA(h, cudaMemcpyAsync(static_cast<unsigned char*>(staging) + off, static_cast<const unsigned char*>(points_host) + off,
+                                  nb, cudaMemcpyHostToDevice, h->copy_stream));
+  }
   LISEC_CUDA(h, cudaEventRecord(h->ev_copied[b], h->copy_stream));
   // compute stream: wait for the copy, run the path, release the buffer
   LISEC_CUDA(h, cudaStreamWaitEvent(st, h->ev_copied[b], 0));

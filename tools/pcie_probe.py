@@ -43,3 +43,19 @@ def split():
 
 ms = timed(split)
 print("9.6 MB H2D as two halves on two streams: %.3f ms %5.1f GB/s" % (ms, n / ms / 1e6))
+
+
+# the same 9.6 MB as SEQUENTIAL pieces on one stream (the per-copy rate above is not monotonic in the size)
+for piece in (1_200_000, 2_400_000, 3_200_000, 4_800_000):
+    def chunks(piece=piece):
+        for a in range(0, n, piece):
+            d[a:a + piece].copy_(h[a:a + piece], non_blocking=True)
+    ms = timed(chunks)
+    print("9.6 MB H2D as sequential pieces of %.1f MB: %.3f ms %5.1f GB/s" % (piece / 1e6, ms, n / ms / 1e6))
+# and with the host buffer freshly written by the CPU before every copy (as a real producer would leave it)
+import numpy as np
+hn = h.numpy()
+def fresh():
+    hn[::4096] += 1
+    d.copy_(h, non_blocking=True)
+print("9.6 MB H2D, host buffer touched before each copy: %.3f ms" % timed(fresh))
