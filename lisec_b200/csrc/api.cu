@@ -572,8 +572,9 @@ int32_t lisec_frontend_forward_host(lisec_handle* h, const void* points_host, in
     const long long v = e ? atoll(e) : 3200000LL;
     return (size_t)(v >= 65536 ? v : 3200000LL) & ~(size_t)255;
   }();
-  for (size_t off = 0; off < bytes; off += piece) {
-    const size_t nb = bytes - off < piece ? bytes - off : piece;
+  const size_t step_bytes = bytes > (size_t)24 << 20 ? bytes : piece;  // large copies run at the link rate as they are
+  for (size_t off = 0; off < bytes; off += step_bytes) {
+    const size_t nb = bytes - off < step_bytes ? bytes - off : step_bytes;
     LISEC_CUDA(h, cudaMemcpyAsync(static_cast<unsigned char*>(staging) + off, static_cast<const unsigned char*>(points_host) + off,
                                   nb, cudaMemcpyHostToDevice, h->copy_stream));
   }
