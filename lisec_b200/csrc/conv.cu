@@ -428,9 +428,10 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 // h * 18 + w, 16-byte chunks XOR-swizzled with bits 7..9 of the row's absolute shared-memory address). A lane takes rows
 // lane, lane + 32, ...: cell -> voxel through the occupancy map, then the voxel's float32 row rounded to bf16 (the same
 // one rounding the dense bf16 grid holds), or c_empty, or zeros outside the grid (ZeroPadding3D, :192). 92 % of the cells
-// are empty, so a box costs ~26 row gathers and 2592 16-byte shared-memory stores. Gather plans have four box slots; box n
-// goes to warp n & 3 and slot n & 3 (a box is two dependent L2 round trips: four in flight keep up with the MMAs); the
-// weights keep coming through warp 0's TMA.
+// are empty: a slot is filled with c_empty rows once and a box rewrites only what differs (occupied rows, rows outside
+// the grid, rows its predecessor in the slot changed). Gather plans have three box slots by default (LISEC_GATHER_SLOTS);
+// box n goes to warp and slot n mod 3 (a box is two dependent L2 round trips — occupancy words, then the occupied rows,
+// compacted over the warp so that they cost one trip instead of eleven); the weights keep coming through warp 0's TMA.
 constexpr int kGatherWarps = 4;  // one per input-box slot
 constexpr int kGatherList = 352;  // (row, voxel) entries of a warp's list of occupied rows: every row of a box
 constexpr int kConvGatherThreads = kConvThreads + 32 * kGatherWarps;
