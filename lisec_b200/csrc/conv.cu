@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 // loaded once per (kd, 64-channel block); M-tile m (8 wide, 16 high, two side by side) under tap (kh, kw) starts at box
 // row kh * 18 + kw + 8 m and its 8-row groups are one box line (18 rows = 2304 bytes) apart. Input traffic per output
 // drops 2.7x against the kh-halo plans; the weights stream through their own ring, three kw taps per slot.
-// GATHER variant (first Conv3D behind the VFE stack): two more warps (11, 12) build the input boxes themselves. A box is
+// GATHER variant (first Conv3D behind the VFE stack): up to four more warps (11-14) build the input boxes themselves. A box is
 // 18 x 18 positions x 64 bf16 channels = 324 rows of 128 bytes in the layout the TMA would have delivered (row r =
 // h * 18 + w, 16-byte chunks XOR-swizzled with bits 7..9 of the row's absolute shared-memory address). A lane takes rows
 // lane, lane + 32, ...: cell -> voxel through the occupancy map, then the voxel's float32 row rounded to bf16 (the same
