@@ -224,7 +224,7 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
   LISEC_CUDA(h, dev_alloc(h, &w.tile_row0, ((size_t)h->max_chunks + 2) * kChunkSlots));
   LISEC_CUDA(h, dev_alloc(h, &w.row_voxel, P + V));
   LISEC_CUDA(h, dev_alloc(h, reinterpret_cast<unsigned char**>(&w.row_xyz), 3 * sizeof(double) * (P + V)));
-  LISEC_CUDA(h, dev_alloc(h, &w.block_sums, (size_t)3 * h->scan_blocks_cap + 4));
+  LISEC_CUDA(h, dev_alloc(h, &w.block_sums, (size_t)4 * h->scan_blocks_cap + 4));  // (v, e, r, -) per scan block
   LISEC_CUDA(h, dev_alloc(h, &w.sweep_voxel_start, (size_t)c.max_sweeps + 2));
   LISEC_CUDA(h, dev_alloc(h, &w.totals, (size_t)TOT_COUNT));
   LISEC_CUDA(h, dev_alloc(h, &w.voxel_feat, V * (size_t)c.c3));

@@ -7,9 +7,9 @@ namespace lisec {
 
 template <typename PT>
 __device__ __forceinline__ void load_point(const PT* __restrict__ pts, long long p, PT& x, PT& y, PT& z) {
-  x = __ldg(pts + 3 * p);
-  y = __ldg(pts + 3 * p + 1);
-  z = __ldg(pts + 3 * p + 2);
+  x = __ldcg(pts + 3 * p);  // (L2 loads: the caller rewrites its point buffer between calls)
+  y = __ldcg(pts + 3 * p + 1);
+  z = __ldcg(pts + 3 * p + 2);
 }
 
 // [x, y, z, x-cx, y-cy, z-cz]: subtraction in float64, one rounding to float32 (model_training.py:137-140 and the

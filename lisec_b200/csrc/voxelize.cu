@@ -59,10 +59,13 @@ template <typename PT>
 struct Vec4Load;
 template <>
 struct Vec4Load<float> {
-  // 4 points = 12 floats = three 16-byte loads
+  // 4 points = 12 floats = three 16-byte loads. L2 loads (.cg): the points are rewritten between calls (a caller's buffer,
+  // the alternating staging buffers of the host entry point) and this kernel is launched under programmatic dependent
+  // launch, where a line still sitting in an SM's L1 from an earlier call has been seen to be served again;
+  // the points are read once, so L1 has nothing to give here anyway.
   static __device__ __forceinline__ void load(const float* base, long long g, float (&v)[12]) {
     const float4* p = reinterpret_cast<const float4*>(base) + 3 * g;
-    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    float4 a = __ldcg(p), b = __ldcg(p + 1), c = __ldcg(p + 2);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
     v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
@@ -74,7 +77,7 @@ struct Vec4Load<double> {
     const double2* p = reinterpret_cast<const double2*>(base) + 6 * g;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-      double2 a = __ldg(p + i);
+      double2 a = __ldcg(p + i);
       v[2 * i] = a.x;
       v[2 * i + 1] = a.y;
     }
@@ -198,14 +201,17 @@ __device__ __forceinline__ Tri block_exclusive(Tri x, Tri* total, Tri* smem /*[8
 
 __device__ __forceinline__ void load_counts(const int* __restrict__ count, long long base, long long ncells,
                                             int (&c)[kScanItems]) {
+  // (L2 loads: the table is written by the kernels in front under programmatic dependent launch)
   if (base + kScanItems <= ncells) {
     const int4* p = reinterpret_cast<const int4*>(count + base);
-    int4 a = p[0], b = p[1];
-    c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w;
-    c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+#pragma unroll
+    for (int q = 0; q < kScanItems / 4; ++q) {
+      const int4 a = __ldcg(p + q);
+      c[4 * q] = a.x; c[4 * q + 1] = a.y; c[4 * q + 2] = a.z; c[4 * q + 3] = a.w;
+    }
   } else {
 #pragma unroll
-    for (int i = 0; i < kScanItems; ++i) c[i] = (base + i < ncells) ? count[base + i] : 0;
+    for (int i = 0; i < kScanItems; ++i) c[i] = (base + i < ncells) ? __ldcg(count + base + i) : 0;
   }
 }
 
@@ -225,9 +231,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const int* __
   Tri total;
   block_exclusive(t, &total, smem);
   if (threadIdx.x == 0) {
-    block_sums[blockIdx.x] = total.v;
-    block_sums[nblocks + blockIdx.x] = total.e;
-    block_sums[2 * nblocks + blockIdx.x] = total.r;
+    reinterpret_cast<int4*>(block_sums)[blockIdx.x] = make_int4(total.v, total.e, total.r, 0);  // one 16-byte slot per block
   }
 }
 
@@ -252,8 +256,11 @@ __global__ void __launch_bounds__(kScanThreads) scan_down_kernel(const int* __re
   int c[kScanItems];
   load_counts(count, base, ncells, c);
   Tri before{0, 0, 0};
-  for (int j = threadIdx.x; j < (int)blockIdx.x; j += kScanThreads)
-    before = tri_add(before, Tri{block_sums[j], block_sums[nblocks + j], block_sums[2 * nblocks + j]});
+  for (int j = threadIdx.x; j < (int)blockIdx.x; j += kScanThreads) {
+    // one 16-byte L2 load per earlier block (the sums were written by scan_reduce under programmatic dependent launch)
+    const int4 s4 = __ldcg(reinterpret_cast<const int4*>(block_sums) + j);
+    before = tri_add(before, Tri{s4.x, s4.y, s4.z});
+  }
   Tri prefix;
   block_exclusive(before, &prefix, smem);  // only its block total is wanted: the sum over all earlier blocks
   __syncthreads();                         // smem is reused below
@@ -305,8 +312,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_down_kernel(const int* __re
   }
   if (base + kScanItems <= ncells) {
     int4* p = reinterpret_cast<int4*>(cell_voxel + base);
-    p[0] = make_int4(cv[0], cv[1], cv[2], cv[3]);
-    p[1] = make_int4(cv[4], cv[5], cv[6], cv[7]);
+#pragma unroll
+    for (int q = 0; q < kScanItems / 4; ++q) p[q] = make_int4(cv[4 * q], cv[4 * q + 1], cv[4 * q + 2], cv[4 * q + 3]);
   } else {
 #pragma unroll
     for (int i = 0; i < kScanItems; ++i)
@@ -446,7 +453,7 @@ __global__ void __launch_bounds__(256) order_pass_kernel(const PT* __restrict__ 
   const int n = __ldcg(voxel_start + v + 1) - s;
   const int p = __ldcg(list_unsorted + e);
   // the point itself, fetched while the rank is counted: the VFE kernel reads its rows' coordinates contiguously
-  const PT px = __ldg(pts + 3 * (long long)p), py = __ldg(pts + 3 * (long long)p + 1), pz = __ldg(pts + 3 * (long long)p + 2);
+  const PT px = __ldcg(pts + 3 * (long long)p), py = __ldcg(pts + 3 * (long long)p + 1), pz = __ldcg(pts + 3 * (long long)p + 2);
   int rank = 0;
   if (n > 1) {
     // chunks of 8 independent loads, then the early exit: not among the first T in point order = dropped (:131)
