@@ -275,7 +275,8 @@ typedef struct lisec_conv_desc {
                         2: "halo" plan for 3x3 taps, stride_hw = 1, out_c <= 128, tile 8 x 16: ONE box with a 1-position
                         halo per (kd, 64 channels) serves all nine (kh, kw) taps; m_tiles stack along W; weights in
                         the plain [kd][kh][kw] order */
-  int32_t reserved;
+  int32_t reserved;  /* bit 0: scale / shift are rewritten between runs (a trainable bias): the epilogue reads them through
+                        L2 instead of the read-only path. Other bits: 0 */
 } lisec_conv_desc;
 
 typedef struct lisec_conv_plan lisec_conv_plan;

@@ -47,10 +47,10 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 template <bool F32>
 __device__ __forceinline__ void load_dy8(const void* dy, long long idx8, float (&g)[8]) {
   if (F32) {
-    const float4 a = __ldcs(reinterpret_cast<const float4*>(dy) + 2 * idx8), b = __ldcs(reinterpret_cast<const float4*>(dy) + 2 * idx8 + 1);
+    const float4 a = __ldcg(reinterpret_cast<const float4*>(dy) + 2 * idx8), b = __ldcg(reinterpret_cast<const float4*>(dy) + 2 * idx8 + 1);
     g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
   } else {
-    unpack8(__ldcs(reinterpret_cast<const uint4*>(dy) + idx8), g);
+    unpack8(__ldcg(reinterpret_cast<const uint4*>(dy) + idx8), g);
   }
 }
 
@@ -66,12 +66,22 @@ __global__ void __launch_bounds__(kBnThreads)
   pdl_wait();
   const int chunks = C >> 3, rows_per_iter = kBnThreads / chunks;
   const int chunk = threadIdx.x % chunks, rl = threadIdx.x / chunks;
+  // (MODE 1) mean / invstd were written by the kernels in front: through L2 into shared memory once per block, not 16
+  // L2 loads per thread
+  __shared__ float s_mean[MODE == 1 ? kBnMaxC : 1], s_invstd[MODE == 1 ? kBnMaxC : 1];
+  if (MODE == 1) {
+    for (int c = threadIdx.x; c < C; c += kBnThreads) {
+      s_mean[c] = __ldcg(mean + c);
+      s_invstd[c] = __ldcg(invstd + c);
+    }
+    __syncthreads();
+  }
   float s0[8], s1[8], mu[8], is[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     s0[i] = s1[i] = 0.f;
-    mu[i] = MODE == 1 ? mean[8 * chunk + i] : 0.f;
-    is[i] = MODE == 1 ? invstd[8 * chunk + i] : 0.f;
+    mu[i] = MODE == 1 ? s_mean[8 * chunk + i] : 0.f;
+    is[i] = MODE == 1 ? s_invstd[8 * chunk + i] : 0.f;
   }
   double d0[8], d1[8];
 #pragma unroll
@@ -208,14 +218,23 @@ __global__ void __launch_bounds__(kBnThreads)
                     long long n8, int chunks, int relu, __nv_bfloat16* __restrict__ y) {
   pdl_launch_dependents();
   pdl_wait();
+  // scale / shift were written by the finalize kernel in front of this one: fetched through L2 once per block into shared
+  // memory (programmatic dependent launch: see common.cuh), read from there per element. (Holding them in registers
+  // instead cost the occupancy this memory-bound kernel lives on: 4x slower.)
+  __shared__ float s_a[kBnMaxC], s_b[kBnMaxC];
+  for (int c = threadIdx.x; c < chunks * 8; c += blockDim.x) {
+    s_a[c] = __ldcg(a + c);
+    s_b[c] = __ldcg(b + c);
+  }
+  __syncthreads();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
     const int c0 = (int)(i % chunks) * 8;
     float v[8];
-    unpack8(__ldcs(reinterpret_cast<const uint4*>(x) + i), v);
+    unpack8(__ldcg(reinterpret_cast<const uint4*>(x) + i), v);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      v[k] = fmaf(v[k], a[c0 + k], b[c0 + k]);
+      v[k] = fmaf(v[k], s_a[c0 + k], s_b[c0 + k]);
       if (relu) v[k] = fmaxf(v[k], 0.f);
     }
     reinterpret_cast<uint4*>(y)[i] = pack8(v);
@@ -231,19 +250,30 @@ __global__ void __launch_bounds__(kBnThreads)
                         int relu, __nv_bfloat16* __restrict__ dx) {
   pdl_launch_dependents();
   pdl_wait();
+  // the per-channel coefficients of this step (written by the kernels in front): through L2 into shared memory, once
+  __shared__ float s_mu[kBnMaxC], s_is[kBnMaxC], s_gs[kBnMaxC], s_mg[kBnMaxC], s_mgx[kBnMaxC];
+  for (int c = threadIdx.x; c < chunks * 8; c += blockDim.x) {
+    const float is = __ldcg(invstd + c);
+    s_mu[c] = __ldcg(mean + c);
+    s_is[c] = is;
+    s_gs[c] = __ldcg(gamma + c) * is;
+    s_mg[c] = __ldcg(mean_g + c);
+    s_mgx[c] = __ldcg(mean_gx + c);
+  }
+  __syncthreads();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
     const int c0 = (int)(i % chunks) * 8;
     float xv[8], g[8], yv[8], o[8];
-    unpack8(__ldcs(reinterpret_cast<const uint4*>(x) + i), xv);
+    unpack8(__ldcg(reinterpret_cast<const uint4*>(x) + i), xv);
     load_dy8<DYF32>(dy, i, g);
-    if (relu) unpack8(__ldcs(reinterpret_cast<const uint4*>(y) + i), yv);
+    if (relu) unpack8(__ldcg(reinterpret_cast<const uint4*>(y) + i), yv);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int c = c0 + k;
       const float gi = (relu && !(yv[k] > 0.f)) ? 0.f : g[k];
-      const float xhat = (xv[k] - mean[c]) * invstd[c];
-      o[k] = gamma[c] * invstd[c] * (gi - mean_g[c] - xhat * mean_gx[c]);
+      const float xhat = (xv[k] - s_mu[c]) * s_is[c];
+      o[k] = s_gs[c] * (gi - s_mg[c] - xhat * s_mgx[c]);
     }
     reinterpret_cast<uint4*>(dx)[i] = pack8(o);
   }

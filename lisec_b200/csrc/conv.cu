@@ -71,6 +71,7 @@ struct ConvParams {
   long long out_pitch;
   const float* scale;
   const float* shift;
+  int affine_rewritten;  // lisec_conv_desc.reserved & 1: scale / shift change between runs (a trainable bias): L2 loads
   void* out;
   // gather source (halo plans of the FIRST Conv3D, lisec_conv_plan_set_gather): the input boxes are built in shared
   // memory from the front end's sparse output — occupancy map, voxel rows, c_empty — instead of being read from a dense
@@ -223,7 +224,9 @@ __device__ __forceinline__ void store_chunk(const ConvParams& P, const float (&x
   const float4* sf = reinterpret_cast<const float4*>(P.shift + sidx0);
 #pragma unroll
   for (int i = 0; i < NV / 4; ++i) {
-    const float4 a = __ldg(sc + i), b = __ldg(sf + i);
+    // (inference: constants, through L1. A plan whose bias an optimizer rewrites between runs reads them through L2 — the
+    // kernel is launched under programmatic dependent launch, where an L1 line of an earlier run can be served again)
+    const float4 a = P.affine_rewritten ? __ldcg(sc + i) : __ldg(sc + i), b = P.affine_rewritten ? __ldcg(sf + i) : __ldg(sf + i);
     y[4 * i] = fmaf(x[4 * i], a.x, b.x);
     y[4 * i + 1] = fmaf(x[4 * i + 1], a.y, b.y);
     y[4 * i + 2] = fmaf(x[4 * i + 2], a.z, b.z);
@@ -812,7 +815,7 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restric
   pdl_launch_dependents();
   pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const float4 v = __ldcs(x + i);
+    const float4 v = __ldcg(x + i);
     float4 h, l;
     umma::tf32_split(v.x, h.x, l.x);
     umma::tf32_split(v.y, h.y, l.y);
@@ -843,17 +846,17 @@ __global__ void __launch_bounds__(256)
   const int c = (int)(gid % q);
   const long long pix = gid / q;
   const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
-  float4 v = __ldg(reinterpret_cast<const float4*>(c1 + pix * n) + c);
+  float4 v = __ldcg(reinterpret_cast<const float4*>(c1 + pix * n) + c);  // (the parts were written by the plans in front)
   {
     const int h2 = H / s2, w2 = W / s2;
     const size_t p = ((size_t)b * h2 + y / s2) * w2 + x / s2;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(c2 + (p * (s2 * s2) + (y % s2) * s2 + (x % s2)) * n) + c);
+    const float4 a = __ldcg(reinterpret_cast<const float4*>(c2 + (p * (s2 * s2) + (y % s2) * s2 + (x % s2)) * n) + c);
     v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
   }
   {
     const int h3 = H / s3, w3 = W / s3;
     const size_t p = ((size_t)b * h3 + y / s3) * w3 + x / s3;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(c3 + (p * (s3 * s3) + (y % s3) * s3 + (x % s3)) * n) + c);
+    const float4 a = __ldcg(reinterpret_cast<const float4*>(c3 + (p * (s3 * s3) + (y % s3) * s3 + (x % s3)) * n) + c);
     v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
   }
   reinterpret_cast<float4*>(out + pix * n)[c] = v;
@@ -1038,6 +1041,7 @@ int32_t lisec_conv_plan_create(const lisec_conv_desc* d, const void* in, const v
   p.out_pitch = d->out_pitch;
   p.scale = scale;
   p.shift = shift;
+  p.affine_rewritten = d->reserved & 1;
   p.out = out;
   p.gather = 0;
   p.in_d = d->in_d;

@@ -64,14 +64,14 @@ __global__ void __launch_bounds__(256)
   const double ay = __dadd_rn(__dmul_rn((double)b, P.cell_y), P.cell_y / 2);
   const double l = P.anchors[i][0], w = P.anchors[i][1], h = P.anchors[i][2];
   double* o = boxes + ((size_t)s * n + c) * 7;
-  o[0] = __dadd_rn(__dmul_rn((double)__ldg(t + 0), l), ax);  // tx * l + x (:80)
-  o[1] = __dadd_rn(__dmul_rn((double)__ldg(t + 1), w), ay);
-  o[2] = __dadd_rn(__dmul_rn((double)__ldg(t + 2), h), P.anchor_z);
-  o[3] = __dmul_rn((double)expf(__ldg(t + 3)), l);  // np.exp(tl) * l: the exp is float32's (:83)
-  o[4] = __dmul_rn((double)expf(__ldg(t + 4)), w);
-  o[5] = __dmul_rn((double)expf(__ldg(t + 5)), h);
-  o[6] = __dadd_rn((double)__ldg(t + 6), P.anchors[i][3]);
-  scores[(size_t)s * n + c] = __ldg(prob + (size_t)s * P.prob_batch + (size_t)pos * P.prob_pitch + i);
+  o[0] = __dadd_rn(__dmul_rn((double)__ldcg(t + 0), l), ax);  // tx * l + x (:80)
+  o[1] = __dadd_rn(__dmul_rn((double)__ldcg(t + 1), w), ay);
+  o[2] = __dadd_rn(__dmul_rn((double)__ldcg(t + 2), h), P.anchor_z);
+  o[3] = __dmul_rn((double)expf(__ldcg(t + 3)), l);  // np.exp(tl) * l: the exp is float32's (:83)
+  o[4] = __dmul_rn((double)expf(__ldcg(t + 4)), w);
+  o[5] = __dmul_rn((double)expf(__ldcg(t + 5)), h);
+  o[6] = __dadd_rn((double)__ldcg(t + 6), P.anchors[i][3]);
+  scores[(size_t)s * n + c] = __ldcg(prob + (size_t)s * P.prob_batch + (size_t)pos * P.prob_pitch + i);
 }
 
 // ---- geometry (serialize_data.py:140-181) ---------------------------------------------------------------------------

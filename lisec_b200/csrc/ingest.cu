@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(kIngestThreads)
   const int here = (int)min((long long)kIngestThreads, n_points - base);
   pdl_wait();
   const float* src = rec + base * rec_floats;
-  for (int i = tid; i < here * rec_floats; i += kIngestThreads) s_in[i] = __ldcs(src + i);
+  for (int i = tid; i < here * rec_floats; i += kIngestThreads) s_in[i] = __ldcg(src + i);
   __syncthreads();
   if (tid < here) {
     const long long p = base + tid;

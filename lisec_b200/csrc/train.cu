@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256)
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 v = reinterpret_cast<float4*>(var)[i];
     float4 a = reinterpret_cast<float4*>(accum)[i];
-    const float4 g = __ldcs(reinterpret_cast<const float4*>(grad) + i);
+    const float4 g = __ldcg(reinterpret_cast<const float4*>(grad) + i);
     sgd_one(v.x, a.x, g.x, grad_scale, lr_t, momentum, nesterov);
     sgd_one(v.y, a.y, g.y, grad_scale, lr_t, momentum, nesterov);
     sgd_one(v.z, a.z, g.z, grad_scale, lr_t, momentum, nesterov);
@@ -151,8 +151,8 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const uint4* __restrict__
   pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
-    uint4 g = __ldcs(dy + i);
-    const uint4 v = __ldcs(y + i);
+    uint4 g = __ldcg(dy + i);
+    const uint4 v = __ldcg(y + i);
     const __nv_bfloat16* yv = reinterpret_cast<const __nv_bfloat16*>(&v);
     __nv_bfloat16* gv = reinterpret_cast<__nv_bfloat16*>(&g);
 #pragma unroll
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256)
     r /= H;
     const int d = (int)(r % D);
     const int b = (int)(r / D);
-    out[((((long long)b * OD + (long long)d * sd) * OH + (long long)h * s) * OW + (long long)w * s) * c8 + c] = __ldcs(in + i);
+    out[((((long long)b * OD + (long long)d * sd) * OH + (long long)h * s) * OW + (long long)w * s) * c8 + c] = __ldcg(in + i);
   }
 }
 
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256) add_bf16_kernel(uint4* __restrict__ a, co
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
     uint4 x = a[i];
-    const uint4 y = __ldcs(b + i);
+    const uint4 y = __ldcg(b + i);
     __nv_bfloat162* xv = reinterpret_cast<__nv_bfloat162*>(&x);
     const __nv_bfloat162* yv = reinterpret_cast<const __nv_bfloat162*>(&y);
 #pragma unroll

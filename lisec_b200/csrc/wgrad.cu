@@ -423,14 +423,14 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   for (; g + 3 < slices; g += 4) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const float4 v = __ldcs(reinterpret_cast<const float4*>(partial + (long long)(g + u) * n) + i4);
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(partial + (long long)(g + u) * n) + i4);
       a4[u].x += v.x; a4[u].y += v.y; a4[u].z += v.z; a4[u].w += v.w;
     }
   }
 #pragma unroll
   for (int u = 0; u < 3; ++u)
     if (g + u < slices) {
-      const float4 v = __ldcs(reinterpret_cast<const float4*>(partial + (long long)(g + u) * n) + i4);
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(partial + (long long)(g + u) * n) + i4);
       a4[u].x += v.x; a4[u].y += v.y; a4[u].z += v.z; a4[u].w += v.w;
     }
   float4 acc;

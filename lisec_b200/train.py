@@ -355,7 +355,7 @@ class ConvBnReluTrain:
             batch=B, in_d=D, in_h=H, in_w=W, in_c=Cin, kd=k[0], kh=k[1], kw=k[2], stride_d=1, stride_hw=s, pad_d=pad[0],
             pad_h=pad[1], pad_w=pad[2], out_c=Nout, n_tiles=1, shuffle=1, out_pitch=Nout, out_ch_off=0, relu=0,
             out_dtype=N.LISEC_BF16, tile_w=tile[0], tile_h=tile[1], m_tiles=1, in_dtype=N.LISEC_BF16, out_split=0,
-            group_kh=0, reserved=0)
+            group_kh=0, reserved=0)  # (the bias in front of a training-mode BN never changes: its gradient is zero)
         self.refresh_weights()
         self.plan = C.c_void_p()
         with torch.cuda.device(dev):
@@ -514,7 +514,7 @@ class Conv3dBlockTrain:
                 batch=B, in_d=src.shape[1], in_h=src.shape[2], in_w=src.shape[3], in_c=cin, kd=kk[0], kh=kk[1], kw=kk[2],
                 stride_d=sd, stride_hw=1, pad_d=pp[0], pad_h=pp[1], pad_w=pp[2], out_c=cout, n_tiles=1, shuffle=1,
                 out_pitch=cout, out_ch_off=0, relu=relu, out_dtype=N.LISEC_BF16, tile_w=tile[0], tile_h=tile[1], m_tiles=1,
-                in_dtype=N.LISEC_BF16, out_split=0, group_kh=0, reserved=0)
+                in_dtype=N.LISEC_BF16, out_split=0, group_kh=0, reserved=0)  # (the bias in front of a training-mode BN never changes: its gradient is zero)
             h = C.c_void_p()
             with torch.cuda.device(dev):
                 st = self._lib.lisec_conv_plan_create(C.byref(desc), C.c_void_p(src.data_ptr()), C.c_void_p(wt.data_ptr()),
@@ -606,7 +606,7 @@ class HeadsTrain:
                 batch=B, in_d=D, in_h=H, in_w=W, in_c=cin, kd=1, kh=1, kw=1, stride_d=1, stride_hw=1, pad_d=0, pad_h=0,
                 pad_w=0, out_c=cout, n_tiles=n_tiles, shuffle=1, out_pitch=cout * n_tiles, out_ch_off=0, relu=0,
                 out_dtype=out_dtype, tile_w=tile[0], tile_h=tile[1], m_tiles=1, in_dtype=N.LISEC_BF16, out_split=0,
-                group_kh=0, reserved=0)
+                group_kh=0, reserved=1)  # bit 0: the bias is a trainable weight, rewritten between runs
             h = C.c_void_p()
             with torch.cuda.device(dev):
                 st = self._lib.lisec_conv_plan_create(C.byref(desc), C.c_void_p(src.data_ptr()), C.c_void_p(wt.data_ptr()),
@@ -703,7 +703,7 @@ class ConvBiasTrain:
             batch=B, in_d=D, in_h=H, in_w=W, in_c=Cin, kd=k[0], kh=k[1], kw=k[2], stride_d=1, stride_hw=1, pad_d=pad[0],
             pad_h=pad[1], pad_w=pad[2], out_c=Nout, n_tiles=1, shuffle=1, out_pitch=out.shape[-1], out_ch_off=out_ch_off,
             relu=0, out_dtype=N.LISEC_BF16, tile_w=tile[0], tile_h=tile[1], m_tiles=1, in_dtype=N.LISEC_BF16, out_split=0,
-            group_kh=0, reserved=0)
+            group_kh=0, reserved=1)  # bit 0: the bias is a trainable weight, rewritten between runs
         self.dgrad = ConvDgrad(dy, w, k, pad, out_dtype=grad_dtype) if need_dx else None
         self.refresh_weights()
         self.plan = C.c_void_p()
@@ -1299,7 +1299,7 @@ class _ShuffleTail:
             batch=B, in_d=1, in_h=H, in_w=W, in_c=Cin, kd=1, kh=1, kw=1, stride_d=1, stride_hw=1, pad_d=0, pad_h=0, pad_w=0,
             out_c=256, n_tiles=s * s, shuffle=s, out_pitch=concat.shape[-1], out_ch_off=ch_off, relu=0,
             out_dtype=N.LISEC_BF16, tile_w=tile[0], tile_h=tile[1], m_tiles=1, in_dtype=N.LISEC_BF16, out_split=0, group_kh=0,
-            reserved=0)
+            reserved=1)  # bit 0: the bias is a trainable weight, rewritten between runs
         self.plan = C.c_void_p()
         with torch.cuda.device(dev):
             st = lib.lisec_conv_plan_create(C.byref(desc), C.c_void_p(x.data_ptr()), C.c_void_p(self.w16.data_ptr()),
