@@ -5,11 +5,33 @@
 
 namespace lisec {
 
+// One point (three PT, 3 * sizeof(PT)-byte stride) in two L2 loads instead of three: the pair that is 2 * sizeof(PT)
+// aligned as one vector load. L2 loads (.cg): the caller rewrites its point buffer between calls (common.cuh).
 template <typename PT>
-__device__ __forceinline__ void load_point(const PT* __restrict__ pts, long long p, PT& x, PT& y, PT& z) {
-  x = __ldcg(pts + 3 * p);  // (L2 loads: the caller rewrites its point buffer between calls)
-  y = __ldcg(pts + 3 * p + 1);
-  z = __ldcg(pts + 3 * p + 2);
+__device__ __forceinline__ void load_point(const PT* __restrict__ pts, long long p, PT& x, PT& y, PT& z);
+template <>
+__device__ __forceinline__ void load_point<float>(const float* __restrict__ pts, long long p, float& x, float& y, float& z) {
+  const float* q = pts + 3 * p;
+  if ((p & 1) == 0) {  // 12 p bytes from a 16-byte aligned base: 8-byte aligned for even p
+    const float2 a = __ldcg(reinterpret_cast<const float2*>(q));
+    x = a.x; y = a.y; z = __ldcg(q + 2);
+  } else {
+    x = __ldcg(q);
+    const float2 a = __ldcg(reinterpret_cast<const float2*>(q + 1));
+    y = a.x; z = a.y;
+  }
+}
+template <>
+__device__ __forceinline__ void load_point<double>(const double* __restrict__ pts, long long p, double& x, double& y, double& z) {
+  const double* q = pts + 3 * p;
+  if ((p & 1) == 0) {  // 24 p bytes: 16-byte aligned for even p
+    const double2 a = __ldcg(reinterpret_cast<const double2*>(q));
+    x = a.x; y = a.y; z = __ldcg(q + 2);
+  } else {
+    x = __ldcg(q);
+    const double2 a = __ldcg(reinterpret_cast<const double2*>(q + 1));
+    y = a.x; z = a.y;
+  }
 }
 
 // [x, y, z, x-cx, y-cy, z-cz]: subtraction in float64, one rounding to float32 (model_training.py:137-140 and the

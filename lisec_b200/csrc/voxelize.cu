@@ -17,6 +17,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "vfe_math.cuh"
 
 namespace lisec {
 
@@ -256,10 +257,22 @@ __global__ void __launch_bounds__(kScanThreads) scan_down_kernel(const int* __re
   int c[kScanItems];
   load_counts(count, base, ncells, c);
   Tri before{0, 0, 0};
-  for (int j = threadIdx.x; j < (int)blockIdx.x; j += kScanThreads) {
-    // one 16-byte L2 load per earlier block (the sums were written by scan_reduce under programmatic dependent launch)
-    const int4 s4 = __ldcg(reinterpret_cast<const int4*>(block_sums) + j);
-    before = tri_add(before, Tri{s4.x, s4.y, s4.z});
+  {
+    // one 16-byte L2 load per earlier block (the sums were written by scan_reduce under programmatic dependent launch),
+    // four in flight per thread: a block walks up to ~10 of them per thread, and one L2 round trip each would be most of
+    // the kernel
+    const int4* sums = reinterpret_cast<const int4*>(block_sums);
+    const int nb = (int)blockIdx.x;
+    int j = threadIdx.x;
+    for (; j + 3 * kScanThreads < nb; j += 4 * kScanThreads) {
+      const int4 a = __ldcg(sums + j), b = __ldcg(sums + j + kScanThreads), c2 = __ldcg(sums + j + 2 * kScanThreads),
+                 d = __ldcg(sums + j + 3 * kScanThreads);
+      before = tri_add(before, Tri{a.x + b.x + c2.x + d.x, a.y + b.y + c2.y + d.y, a.z + b.z + c2.z + d.z});
+    }
+    for (; j < nb; j += kScanThreads) {
+      const int4 a = __ldcg(sums + j);
+      before = tri_add(before, Tri{a.x, a.y, a.z});
+    }
   }
   Tri prefix;
   block_exclusive(before, &prefix, smem);  // only its block total is wanted: the sum over all earlier blocks
@@ -453,7 +466,8 @@ __global__ void __launch_bounds__(256) order_pass_kernel(const PT* __restrict__ 
   const int n = __ldcg(voxel_start + v + 1) - s;
   const int p = __ldcg(list_unsorted + e);
   // the point itself, fetched while the rank is counted: the VFE kernel reads its rows' coordinates contiguously
-  const PT px = __ldcg(pts + 3 * (long long)p), py = __ldcg(pts + 3 * (long long)p + 1), pz = __ldcg(pts + 3 * (long long)p + 2);
+  PT px, py, pz;
+  load_point(pts, (long long)p, px, py, pz);
   int rank = 0;
   if (n > 1) {
     // chunks of 8 independent loads, then the early exit: not among the first T in point order = dropped (:131)
