@@ -48,15 +48,19 @@ int check_offsets(lisec_handle* h, const int64_t* off, int n_sweeps, SweepOffset
 
 int do_voxelize(lisec_handle* h, const void* points, int dtype, const SweepOffsets& so, cudaStream_t st) {
   const long long n_total = so.off[so.n];
-  if (h->count_dirty) {
+  if (h->count_dirty) {  // first call, or a call that failed half way: the state the kernels otherwise leave behind
     LISEC_CUDA(h, cudaMemsetAsync(h->ws.count, 0, sizeof(int) * (size_t)h->ncells_cap, st));
+    LISEC_CUDA(h, cudaMemsetAsync(h->ws.totals, 0, sizeof(long long) * TOT_COUNT, st));
+    LISEC_CUDA(h, cudaMemsetAsync(h->ws.chunk_first, 0x7f, sizeof(int) * ((size_t)h->max_chunks + 2), st));
+    LISEC_CUDA(h, cudaMemsetAsync(h->ws.block_sums + (size_t)4 * h->scan_blocks_cap, 0,
+                                  sizeof(int) * 4 * ((size_t)h->scan_blocks_cap / kScanGroup + 1), st));  // the scans' group totals
     h->count_dirty = false;
   }
   h->voxelized = false;
   h->count_dirty = true;  // until the fill pass has been enqueued
   LISEC_CUDA(h, launch_point_pass(points, dtype, n_total, so, h->geom, h->ws, h->max_chunks, st, &h->launches));
   LISEC_CUDA(h, launch_cell_scan(so, h->geom, h->ws, h->scan_blocks_cap, h->rows_per_chunk, st, &h->launches));
-  LISEC_CUDA(h, launch_fill_and_order(points, dtype, n_total, h->geom, h->max_chunks, h->ws, st, &h->launches));
+  LISEC_CUDA(h, launch_fill_and_order(points, dtype, n_total, h->geom, h->max_chunks, h->scan_blocks_cap, h->ws, st, &h->launches));
   h->count_dirty = false;
   h->last_points = points;
   h->last_dtype = dtype;
@@ -224,7 +228,9 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
   LISEC_CUDA(h, dev_alloc(h, &w.tile_row0, ((size_t)h->max_chunks + 2) * kChunkSlots));
   LISEC_CUDA(h, dev_alloc(h, &w.row_voxel, P + V));
   LISEC_CUDA(h, dev_alloc(h, reinterpret_cast<unsigned char**>(&w.row_xyz), 3 * sizeof(double) * (P + V)));
-  LISEC_CUDA(h, dev_alloc(h, &w.block_sums, (size_t)4 * h->scan_blocks_cap + 4));  // (v, e, r, -) per scan block
+  // (v, e, r, -) per scan block and per group of kScanGroup blocks (the groups: accumulated by atomics, zero between calls)
+  LISEC_CUDA(h, dev_alloc(h, &w.block_sums, (size_t)8 * h->scan_blocks_cap + 4));
+  LISEC_CUDA(h, cudaMemset(w.block_sums, 0, sizeof(int) * ((size_t)8 * h->scan_blocks_cap + 4)));
   LISEC_CUDA(h, dev_alloc(h, &w.sweep_voxel_start, (size_t)c.max_sweeps + 2));
   LISEC_CUDA(h, dev_alloc(h, &w.totals, (size_t)TOT_COUNT));
   LISEC_CUDA(h, dev_alloc(h, &w.voxel_feat, V * (size_t)c.c3));

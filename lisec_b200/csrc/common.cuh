@@ -53,16 +53,20 @@ enum {
   TOT_CHUNKS = 3,   // VFE chunks (runs of whole voxels with at most kVfeChunkRows rows; tiles are packed inside a chunk)
   TOT_NONFINITE = 4,
   TOT_OUT_OF_RANGE = 5,
+  TOT_ACC_NONFINITE = 6,     // the point pass's running drop counters: moved to the two slots above and zeroed again by
+  TOT_ACC_OUT_OF_RANGE = 7,  // scan_down, so that no call starts with a memset (zero between calls)
   TOT_COUNT = 8
 };
 
 constexpr int kVfeThreads = 128;  // rows per VFE tile (one M = 128 accumulator block)
 constexpr int kVfeChunkRows = 4 * kVfeThreads;  // rows per VFE chunk
+constexpr int kChunkFirstPreset = 0x7f7f7f7f;  // chunk_first[] between calls: above any voxel index (atomicMin target)
 constexpr int kChunkSlots = 12;  // tile-table entries per chunk (<= 9 tiles + the end sentinel)
 constexpr int kRowPadFlag = 1 << 30;  // row_voxel[] bit: the row is its voxel's virtual pad row
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;     // cells per thread in the cell-table scans (16 measured slower: scan_down 20.5 -> 23.3 us)
 constexpr int kScanTile = kScanThreads * kScanItems;
+constexpr int kScanGroup = 32;    // scan blocks per group of the two-level block totals
 
 struct Workspace {
   // cell tables, [max_sweeps * cells]
@@ -85,7 +89,7 @@ struct Workspace {
   int* row_voxel = nullptr;    // voxel row the VFE row belongs to (| kRowPadFlag for the virtual pad row)
   void* row_xyz = nullptr;     // [rows][3] the point of every VFE row in the input dtype (unwritten for pad rows)
   int* tile_row0 = nullptr;    // [max_chunks][kChunkSlots] first VFE row of each tile
-  int* block_sums = nullptr;   // [scan_blocks][4] (voxels, entries, rows, -) of each scan block: reduce -> exclusive prefix
+  int* block_sums = nullptr;   // [cap][4] (voxels, entries, rows, -) of each scan block | [cap / kScanGroup + 1][4] of each group of blocks
   int* sweep_voxel_start = nullptr;  // [max_sweeps + 1]
   long long* totals = nullptr;       // [TOT_COUNT]
   float* voxel_feat = nullptr;       // [max_voxels, c3] for the fused entry point
@@ -105,7 +109,7 @@ cudaError_t launch_point_pass(const void* pts, int pts_dtype, long long n_total,
 cudaError_t launch_cell_scan(const SweepOffsets& so, const Geom& g, Workspace& w, int scan_blocks_cap,
                              int rows_per_chunk, cudaStream_t st, int* launches);
 cudaError_t launch_fill_and_order(const void* pts, int pts_dtype, long long n_total, const Geom& g, long long max_chunks,
-                                  Workspace& w, cudaStream_t st, int* launches);
+                                  int scan_blocks_cap, Workspace& w, cudaStream_t st, int* launches);
 cudaError_t launch_export(const void* pts, int pts_dtype, const SweepOffsets& so, const Geom& g,
                           const Workspace& w, long long max_voxels, int32_t* coords, int32_t* counts,
                           int32_t* point_idx, float* features, float* dense, cudaStream_t st, int* launches);

@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // from here on: the grouping, the row tables and the occupancy map of this call
   if (MODE != 0) timeline_stamp(g_trace, TL_VFE);
-  const int n_chunks = (int)*prob.n_chunks;
+  const int n_chunks = (int)__ldcg(prob.n_chunks);  // (written by scan_down of this call: through L2, like every table)
   // chunks are strided over the CTAs; this one owns tile ordinals 0 .. my_tiles-1 = the tiles of its chunks in order
   const int my_tiles = count_my_tiles(prob, n_chunks);
 

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kGenThreads) vfe_generic_kernel(const float* _
 
   const int t = threadIdx.x;
   const PT* __restrict__ xyz = static_cast<const PT*>(prob.row_xyz);
-  const long long n_chunks = *prob.n_chunks;
+  const long long n_chunks = __ldcg(prob.n_chunks);  // (written by scan_down of this call: through L2)
   for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
     const int nt = prob.chunk_ntiles[c];
     for (int j = 0; j < nt; ++j) {

@@ -92,7 +92,10 @@ __global__ void __launch_bounds__(256) point_pass_kernel(const PT* __restrict__ 
                                                          const __grid_constant__ Geom g,
                                                          int* __restrict__ cell_of_point, int* __restrict__ count,
                                                          unsigned long long* __restrict__ totals) {
+  __shared__ int s_drop[2];
   pdl_launch_dependents();
+  if (threadIdx.x == 0) s_drop[0] = s_drop[1] = 0;
+  __syncthreads();
   pdl_wait();
   timeline_stamp(g_trace, TL_POINT);
   const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -145,15 +148,22 @@ __global__ void __launch_bounds__(256) point_pass_kernel(const PT* __restrict__ 
       if (lane == __ffs(peers) - 1) atomicAdd(&count[cell[j]], __popc(peers));
     }
   }
-  // dropped-point statistics: one atomic per warp
+  // dropped-point statistics: reduced over the warp, then over the block in shared memory — ONE global atomic per block
+  // and counter. (One per warp was 6 250 read-modify-writes of the same L2 line per 8-sweep call, which the L2 slice that
+  // owns the line takes one after the other; the kernel is not complete until they have drained.)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     n_oor += __shfl_xor_sync(0xffffffffu, n_oor, o);
     n_nonf += __shfl_xor_sync(0xffffffffu, n_nonf, o);
   }
   if (lane == 0) {
-    if (n_oor) atomicAdd(&totals[TOT_OUT_OF_RANGE], (unsigned long long)n_oor);
-    if (n_nonf) atomicAdd(&totals[TOT_NONFINITE], (unsigned long long)n_nonf);
+    if (n_oor) atomicAdd(&s_drop[0], n_oor);
+    if (n_nonf) atomicAdd(&s_drop[1], n_nonf);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_drop[0]) atomicAdd(&totals[TOT_ACC_OUT_OF_RANGE], (unsigned long long)s_drop[0]);
+    if (s_drop[1]) atomicAdd(&totals[TOT_ACC_NONFINITE], (unsigned long long)s_drop[1]);
   }
 }
 
@@ -217,7 +227,7 @@ __device__ __forceinline__ void load_counts(const int* __restrict__ count, long 
 }
 
 __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const int* __restrict__ count, long long ncells,
-                                                                   int T, int nblocks,
+                                                                   int T, int nblocks, int group_offset,
                                                                    int* __restrict__ block_sums) {
   __shared__ Tri smem[kScanThreads / 32 + 1];
   pdl_launch_dependents();
@@ -231,18 +241,30 @@ __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const int* __
   for (int i = 0; i < kScanItems; ++i) t = tri_add(t, tri_of_count(c[i], T));
   Tri total;
   block_exclusive(t, &total, smem);
+  // Two-level totals: the block's own (sums[b]) and, by three fire-and-forget atomics, the running total of its GROUP of
+  // kScanGroup consecutive blocks (grp[b / kScanGroup]; zeroed again by the order pass). A scan_down block then needs the
+  // groups before its own plus the blocks before it inside its group: one load per thread, one round trip. (Every block
+  // used to add up the totals of ALL blocks before it: 3 M loads = 50 MB of L2 traffic per 8-sweep call, up to three
+  // dependent round trips in front of every block's own scan. A last-block-done spine inside this kernel was measured
+  // too: it costs this kernel more (+6.8 us: a fence and a ticket per block, one block's serial tail) than it saves there.)
   if (threadIdx.x == 0) {
-    reinterpret_cast<int4*>(block_sums)[blockIdx.x] = make_int4(total.v, total.e, total.r, 0);  // one 16-byte slot per block
+    int4* sums = reinterpret_cast<int4*>(block_sums);
+    sums[blockIdx.x] = make_int4(total.v, total.e, total.r, 0);  // one 16-byte slot per block
+    if (total.v) {
+      int* grp = reinterpret_cast<int*>(sums + group_offset + (blockIdx.x / kScanGroup));
+      atomicAdd(grp, total.v);
+      atomicAdd(grp + 1, total.e);
+      atomicAdd(grp + 2, total.r);
+    }
   }
 }
 
-// Second pass. There is no separate "spine" kernel: a block gets its exclusive prefix by summing the totals of the
-// blocks before it (at most nblocks/256 coalesced L2 loads per thread), and the last block, which thereby holds the
-// grand totals, writes them and the sentinels.
+// Second pass. There is no separate "spine" kernel: a block gets its exclusive prefix from scan_reduce's two-level
+// totals, and the last block, which thereby holds the grand totals, writes them and the sentinels.
 __global__ void __launch_bounds__(kScanThreads) scan_down_kernel(const int* __restrict__ count, long long ncells,
                                                                  int T, int cells_per_sweep, int nblocks, int n_sweeps,
                                                                  int rows_per_chunk, int* __restrict__ chunk_first,
-                                                                 const int* __restrict__ block_sums,
+                                                                 const int* __restrict__ block_sums, int group_offset,
                                                                  long long* __restrict__ totals,
                                                                  int* __restrict__ cell_voxel,
                                                                  int* __restrict__ voxel_cell,
@@ -258,19 +280,13 @@ __global__ void __launch_bounds__(kScanThreads) scan_down_kernel(const int* __re
   load_counts(count, base, ncells, c);
   Tri before{0, 0, 0};
   {
-    // one 16-byte L2 load per earlier block (the sums were written by scan_reduce under programmatic dependent launch),
-    // four in flight per thread: a block walks up to ~10 of them per thread, and one L2 round trip each would be most of
-    // the kernel
+    // the sum over all earlier blocks = the groups before this block's group + the blocks before it inside the group:
+    // one 16-byte L2 load per thread (the sums were written by scan_reduce under programmatic dependent launch)
     const int4* sums = reinterpret_cast<const int4*>(block_sums);
-    const int nb = (int)blockIdx.x;
-    int j = threadIdx.x;
-    for (; j + 3 * kScanThreads < nb; j += 4 * kScanThreads) {
-      const int4 a = __ldcg(sums + j), b = __ldcg(sums + j + kScanThreads), c2 = __ldcg(sums + j + 2 * kScanThreads),
-                 d = __ldcg(sums + j + 3 * kScanThreads);
-      before = tri_add(before, Tri{a.x + b.x + c2.x + d.x, a.y + b.y + c2.y + d.y, a.z + b.z + c2.z + d.z});
-    }
-    for (; j < nb; j += kScanThreads) {
-      const int4 a = __ldcg(sums + j);
+    const int4* grp = sums + group_offset;
+    const int g = (int)blockIdx.x / kScanGroup, in_group = (int)blockIdx.x % kScanGroup;
+    for (int j = threadIdx.x; j < g + in_group; j += kScanThreads) {
+      const int4 a = __ldcg(j < g ? grp + j : sums + g * kScanGroup + (j - g));
       before = tri_add(before, Tri{a.x, a.y, a.z});
     }
   }
@@ -289,6 +305,12 @@ __global__ void __launch_bounds__(kScanThreads) scan_down_kernel(const int* __re
     totals[TOT_ENTRIES] = carry.e;
     totals[TOT_ROWS] = carry.r;
     totals[TOT_CHUNKS] = carry.r > 0 ? (carry.r - 1) / rows_per_chunk + 1 : 0;
+    // the point pass's drop counters (complete: that kernel has finished) become this call's figures and are left zero
+    // for the next call — a call begins with a kernel, not with a memset
+    totals[TOT_NONFINITE] = __ldcg(totals + TOT_ACC_NONFINITE);
+    totals[TOT_OUT_OF_RANGE] = __ldcg(totals + TOT_ACC_OUT_OF_RANGE);
+    totals[TOT_ACC_NONFINITE] = 0;
+    totals[TOT_ACC_OUT_OF_RANGE] = 0;
     voxel_start[carry.v] = carry.e;
     row_start[carry.v] = carry.r;
     sweep_voxel_start[n_sweeps] = carry.v;
@@ -454,16 +476,35 @@ __global__ void __launch_bounds__(256) order_pass_kernel(const PT* __restrict__ 
                                                          const int* __restrict__ row_start, int T,
                                                          const long long* __restrict__ totals,
                                                          int* __restrict__ list_sorted,
-                                                         int* __restrict__ row_voxel, PT* __restrict__ row_xyz) {
+                                                         int* __restrict__ row_voxel, PT* __restrict__ row_xyz,
+                                                         int* __restrict__ chunk_first, long long chunk_cap,
+                                                         int* __restrict__ scan_groups, int n_group_ints) {
   pdl_launch_dependents();
   pdl_wait();
   timeline_stamp(g_trace, TL_ORDER);
-  const long long n_entries = __ldcg(totals + TOT_ENTRIES);  // (predecessor-written tables: ld.global.cg, never through L1 — DESIGN.md §4)
+  // The totals are fetched by ONE thread per block: with a load per warp, 25 000 warps asked the same L2 slice for the
+  // same 32 bytes, one after the other, before any of them could start. (Predecessor-written: ld.global.cg)
+  __shared__ long long s_tot[2];
+  if (threadIdx.x == 0) {
+    s_tot[0] = __ldcg(totals + TOT_ENTRIES);
+    s_tot[1] = __ldcg(totals + TOT_CHUNKS);
+  }
+  __syncthreads();
+  const long long n_entries = s_tot[0];
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  {
+    // The chunk marks (atomicMin targets of scan_down) have been consumed by the tile plan in the fill pass's launch:
+    // put the preset back for the next call, so that no call starts with a memset.
+    const long long used = min(s_tot[1] + 2, chunk_cap);
+    for (long long i = e; i < used; i += (long long)gridDim.x * blockDim.x) chunk_first[i] = kChunkFirstPreset;
+    // likewise the scans' group totals (accumulated by atomics in scan_reduce, read by scan_down)
+    for (long long i = e; i < n_group_ints; i += (long long)gridDim.x * blockDim.x) scan_groups[i] = 0;
+  }
   if (e >= n_entries) return;
   const int v = __ldcg(entry_voxel + e);
   const int s = __ldcg(voxel_start + v);
   const int n = __ldcg(voxel_start + v + 1) - s;
+  const int row0 = __ldcg(row_start + v);
   const int p = __ldcg(list_unsorted + e);
   // the point itself, fetched while the rank is counted: the VFE kernel reads its rows' coordinates contiguously
   PT px, py, pz;
@@ -482,7 +523,7 @@ __global__ void __launch_bounds__(256) order_pass_kernel(const PT* __restrict__ 
   if (rank < T) {
     list_sorted[s + rank] = p;
     // VFE row tables: row_start[v] + rank is this point's row; a non-full voxel gets one virtual pad row after its points
-    const int row = __ldcg(row_start + v) + rank;
+    const int row = row0 + rank;
     row_voxel[row] = v;
     if (rank == 0 && n < T) row_voxel[row + n] = v | kRowPadFlag;
     PT* dst = row_xyz + 3 * (long long)row;
@@ -501,12 +542,13 @@ cudaError_t set_trace_voxelize(unsigned long long* trace) {
 
 cudaError_t launch_point_pass(const void* pts, int pts_dtype, long long n_total, const SweepOffsets& so,
                               const Geom& g, Workspace& w, long long chunk_cap, cudaStream_t st, int* launches) {
-  cudaError_t err = cudaMemsetAsync(w.totals, 0, sizeof(long long) * TOT_COUNT, st);
-  if (err != cudaSuccess) return err;
+  // No memsets here: totals[] is rewritten by scan_down (which also zeroes the drop counters this kernel adds to), and
+  // the chunk marks (atomicMin targets of scan_down, preset kChunkFirstPreset) are put back by the order pass; both are
+  // initialised by lisec_create and by do_voxelize's recovery path (api.cu). A call is a chain of kernels only, so the
+  // point pass's programmatic launch overlaps the previous call's last kernel.
+  cudaError_t err = cudaSuccess;
+  (void)chunk_cap;
   if (n_total == 0) return cudaSuccess;
-  // chunk_first is found by atomicMin (scan_down): preset to 0x7f7f7f7f, above any voxel index
-  err = cudaMemsetAsync(w.chunk_first, 0x7f, sizeof(int) * (size_t)(chunk_cap + 2), st);
-  if (err != cudaSuccess) return err;
   const long long groups = (n_total + 3) / 4;
   const unsigned blocks = (unsigned)((groups + 255) / 256);
   auto* tot = reinterpret_cast<unsigned long long*>(w.totals);
@@ -525,18 +567,19 @@ cudaError_t launch_cell_scan(const SweepOffsets& so, const Geom& g, Workspace& w
   const long long ncells = (long long)so.n * g.cells;
   const int nblocks = (int)((ncells + kScanTile - 1) / kScanTile);
   if (nblocks > scan_blocks_cap) return cudaErrorInvalidValue;
+  // block_sums = [cap] block totals | [cap / kScanGroup + 1] group totals (16-byte slots; zero between calls)
   cudaError_t err = launch_pdl(scan_reduce_kernel, nblocks, kScanThreads, 0, st, (const int*)w.count, ncells, g.T,
-                               nblocks, w.block_sums);
+                               nblocks, scan_blocks_cap, w.block_sums);
   if (err == cudaSuccess)
     err = launch_pdl(scan_down_kernel, nblocks, kScanThreads, 0, st, (const int*)w.count, ncells, g.T, g.cells, nblocks,
-                     so.n, rows_per_chunk, w.chunk_first, (const int*)w.block_sums, w.totals, w.cell_voxel, w.voxel_cell,
-                     w.voxel_start, w.row_start, w.sweep_voxel_start);
+                     so.n, rows_per_chunk, w.chunk_first, (const int*)w.block_sums, scan_blocks_cap, w.totals, w.cell_voxel,
+                     w.voxel_cell, w.voxel_start, w.row_start, w.sweep_voxel_start);
   *launches += 2;
   return err;
 }
 
 cudaError_t launch_fill_and_order(const void* pts, int pts_dtype, long long n_total, const Geom& g, long long max_chunks,
-                                  Workspace& w, cudaStream_t st, int* launches) {
+                                  int scan_blocks_cap, Workspace& w, cudaStream_t st, int* launches) {
   if (n_total == 0) return cudaSuccess;
   const long long groups = (n_total + 3) / 4;
   const unsigned fill_blocks = (unsigned)((groups + 255) / 256);
@@ -552,12 +595,14 @@ cudaError_t launch_fill_and_order(const void* pts, int pts_dtype, long long n_to
       err = launch_pdl(order_pass_kernel<float>, blocks, 256, 0, st, static_cast<const float*>(pts),
                        (const int*)w.list_unsorted, (const int*)w.entry_voxel, (const int*)w.voxel_start,
                        (const int*)w.row_start, g.T, (const long long*)w.totals, w.list_sorted, w.row_voxel,
-                       static_cast<float*>(w.row_xyz));
+                       static_cast<float*>(w.row_xyz), w.chunk_first, max_chunks + 2,
+                       w.block_sums + 4 * (size_t)scan_blocks_cap, 4 * (scan_blocks_cap / kScanGroup + 1));
     else
       err = launch_pdl(order_pass_kernel<double>, blocks, 256, 0, st, static_cast<const double*>(pts),
                        (const int*)w.list_unsorted, (const int*)w.entry_voxel, (const int*)w.voxel_start,
                        (const int*)w.row_start, g.T, (const long long*)w.totals, w.list_sorted, w.row_voxel,
-                       static_cast<double*>(w.row_xyz));
+                       static_cast<double*>(w.row_xyz), w.chunk_first, max_chunks + 2,
+                       w.block_sums + 4 * (size_t)scan_blocks_cap, 4 * (scan_blocks_cap / kScanGroup + 1));
   }
   *launches += 2;
   return err;
