@@ -505,6 +505,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
       if (tr) {
         unsigned long long now;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        atomicMin(tr + (size_t)(kTimelineRow0 + TL_WRITER_END) * kTraceSlots, now);  // earliest CTA
         atomicMax(tr + (size_t)(kTimelineRow0 + TL_WRITER_END) * kTraceSlots + 1, now);
       }
     }
@@ -795,6 +796,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
     if (tr) {
       unsigned long long now;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+      atomicMin(tr + (size_t)(kTimelineRow0 + TL_VFE_END) * kTraceSlots, now);  // earliest CTA
       atomicMax(tr + (size_t)(kTimelineRow0 + TL_VFE_END) * kTraceSlots + 1, now);
     }
   }

@@ -426,12 +426,12 @@ __global__ void __launch_bounds__(256) fill_pass_kernel(const int* __restrict__ 
   const long long p0 = grp * 4;
   int cell[4] = {-1, -1, -1, -1};
   if (p0 + 3 < n_total) {
-    int4 c = reinterpret_cast<const int4*>(cell_of_point)[grp];
+    int4 c = __ldcg(reinterpret_cast<const int4*>(cell_of_point) + grp);  // (written by the point pass of this call: through L2)
     cell[0] = c.x; cell[1] = c.y; cell[2] = c.z; cell[3] = c.w;
   } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (p0 + j < n_total) cell[j] = cell_of_point[p0 + j];
+      if (p0 + j < n_total) cell[j] = __ldcg(cell_of_point + p0 + j);
   }
   const int lane = lane_id();
   // the chain cell -> voxel -> segment start -> slot is three dependent L2 round trips: run the four points of the

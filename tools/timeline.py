@@ -34,6 +34,7 @@ for i in range(4):
 torch.cuda.synchronize()
 read()  # re-arm
 acc = np.zeros(8)
+first = np.zeros(2)  # the EARLIEST CTA's writer / VFE-pipeline end
 n = 10
 for i in range(n):
     for j in range(3):  # three back-to-back steps; the stamps keep the min/max, so measure them one at a time
@@ -47,11 +48,13 @@ for i in range(n):
     start[7] = hi[7]
     start[5] = hi[5]  # the writers' end (latest CTA)
     acc += start - start[0]
+    first += np.array([lo[5], lo[7]]) - start[0]
 acc /= n
+first /= n
 print("in-step timeline, us after the point pass started (mean of %d steps):" % n)
 for k in (0, 1, 2, 3):
     print("  %-14s starts %7.1f   runs %6.1f" % (NAMES[k], acc[k] / 1e3, (acc[k + 1] - acc[k]) / 1e3))
 print("  %-14s starts %7.1f   runs %6.1f" % (NAMES[4], acc[4] / 1e3, (acc[6] - acc[4]) / 1e3))
 print("  %-14s starts %7.1f" % (NAMES[6], acc[6] / 1e3))
-print("  background writers done (last CTA) %7.1f" % (acc[5] / 1e3))
-print("  VFE pipeline done (last CTA)       %7.1f" % (acc[7] / 1e3))
+print("  background writers done (first / last CTA) %7.1f / %7.1f" % (first[0] / 1e3, acc[5] / 1e3))
+print("  VFE pipeline done (first / last CTA)       %7.1f / %7.1f" % (first[1] / 1e3, acc[7] / 1e3))
