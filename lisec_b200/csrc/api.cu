@@ -22,7 +22,7 @@ void free_workspace(Workspace& w) {
                   w.voxel_cell, w.voxel_start, w.row_start, w.tile_first, w.tile_row0, w.chunk_first, w.chunk_row0,
                   w.chunk_ntiles, w.row_voxel, w.row_xyz,
                   w.block_sums, w.sweep_voxel_start,
-                  w.totals, w.voxel_feat, w.c_empty, w.vfe_w, w.staging, w.empty_desc, w.trace};
+                  w.totals, w.voxel_feat, w.c_empty, w.vfe_w, w.staging, w.empty_desc, w.trace, w.writer_claim};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   w = Workspace();
@@ -233,6 +233,8 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
   LISEC_CUDA(h, cudaMemset(w.block_sums, 0, sizeof(int) * ((size_t)8 * h->scan_blocks_cap + 4)));
   LISEC_CUDA(h, dev_alloc(h, &w.sweep_voxel_start, (size_t)c.max_sweeps + 2));
   LISEC_CUDA(h, dev_alloc(h, &w.totals, (size_t)TOT_COUNT));
+  LISEC_CUDA(h, dev_alloc(h, &w.writer_claim, (size_t)4));
+  LISEC_CUDA(h, cudaMemset(w.writer_claim, 0, sizeof(int) * 4));
   LISEC_CUDA(h, dev_alloc(h, &w.voxel_feat, V * (size_t)c.c3));
   LISEC_CUDA(h, dev_alloc(h, &w.c_empty, (size_t)c.c3));
   LISEC_CUDA(h, dev_alloc(h, &w.vfe_w, (size_t)kVfeBlobFloats));

@@ -89,6 +89,7 @@ struct Workspace {
   int* row_voxel = nullptr;    // voxel row the VFE row belongs to (| kRowPadFlag for the virtual pad row)
   void* row_xyz = nullptr;     // [rows][3] the point of every VFE row in the input dtype (unwritten for pad rows)
   int* tile_row0 = nullptr;    // [max_chunks][kChunkSlots] first VFE row of each tile
+  int* writer_claim = nullptr; // [2] the fused kernel's background writers: next batch of cells, finished warps (vfe.cu)
   int* block_sums = nullptr;   // [cap][4] (voxels, entries, rows, -) of each scan block | [cap / kScanGroup + 1][4] of each group of blocks
   int* sweep_voxel_start = nullptr;  // [max_sweeps + 1]
   long long* totals = nullptr;       // [TOT_COUNT]

@@ -155,6 +155,7 @@ struct VfeOutput {
   long long ncells;
   const int* warm;       // the per-cell count table: pulled back into L2 for the NEXT call's point pass (see the writer)
   int first_group;       // 32-cell groups below this one already hold the background (grid_fill_kernel, scatter.cu)
+  int* writer_claim;     // [2] the writers' batch counter and finished-warp count, zero between launches (background_writer)
 };
 
 // ---- background writer (fused modes, warps 0-2) --------------------------------------------------------------
@@ -181,7 +182,7 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 template <typename GT>
 __device__ __forceinline__ void background_writer(const int* __restrict__ cell_voxel, const float* __restrict__ c_empty,
                                                   GT* __restrict__ grid, long long ncells, int first_group,
-                                                  unsigned char* sBg, int wtid) {
+                                                  int* __restrict__ claim, unsigned char* sBg, int wtid) {
   constexpr int kWarps = kWriterWarps;
   const int lane = wtid & 31, wwarp = wtid >> 5;
   // fill the tile: kBgCells cells x 64 channels of GT, every cell = c_empty (rounded once for bf16)
@@ -194,21 +195,30 @@ __device__ __forceinline__ void background_writer(const int* __restrict__ cell_v
   const unsigned src = (unsigned)__cvta_generic_to_shared(sBg);
   const unsigned long long policy = l2_evict_first_policy();
   const int ngroups = (int)((ncells + 31) >> 5);
-  const int stride = gridDim.x * kWarps;
-  constexpr int U = 4;  // 32-cell groups per step; the next step's occupancy words are already in flight
-  auto load_occ = [&](int g0, int (&occ)[U]) {
+  // Batches of U consecutive 32-cell groups (32 KB of float32 grid) are CLAIMED, not assigned: the writer warps of the
+  // 148 CTAs do not run at one speed beside the VFE stages (equal static shares finished 86 us apart, tools/timeline.py),
+  // and an SM whose writers are late is also where the VFE pipeline is late. claim[0] = next batch, claim[1] = writer
+  // warps that have finished; the last one zeroes both for the next launch. Lane 0 claims two iterations ahead (an
+  // iteration is ~3 us, the atomic's round trip ~1-3), the next batch's occupancy words are in flight one ahead.
+  constexpr int U = 4;
+  const int nbatches = (ngroups - first_group + U - 1) / U;
+  auto load_occ = [&](int b, int (&occ)[U]) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int g = g0 + u * stride;
+      const int g = first_group + b * U + u;
       const long long cell = ((long long)g << 5) + lane;
-      occ[u] = (g < ngroups && cell < ncells) ? __ldcg(cell_voxel + cell) : 0;  // 0 = "not empty": nothing to write
+      occ[u] = (b < nbatches && g < ngroups && cell < ncells) ? __ldcg(cell_voxel + cell) : 0;  // 0 = "not empty": nothing to write
     }
   };
+  auto claim_one = [&]() { return lane == 0 ? atomicAdd(claim, 1) : 0; };
+  int b_cur = __shfl_sync(0xffffffffu, claim_one(), 0);
+  int pending = claim_one();  // (lane 0's register; first read one iteration later)
   int occ[U], nxt[U];
-  int g0 = first_group + blockIdx.x * kWarps + wwarp;
-  load_occ(g0, occ);
-  for (; g0 < ngroups; g0 += U * stride) {
-    load_occ(g0 + U * stride, nxt);
+  load_occ(b_cur, occ);
+  while (b_cur < nbatches) {
+    const int b_nxt = __shfl_sync(0xffffffffu, pending, 0);
+    pending = claim_one();
+    load_occ(b_nxt, nxt);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const unsigned empty = __ballot_sync(0xffffffffu, occ[u] < 0);
@@ -216,7 +226,7 @@ __device__ __forceinline__ void background_writer(const int* __restrict__ cell_v
       if (starts) {
         const unsigned rest = ~(empty >> lane);  // zeros shift in on top, so rest == 0 only for lane 0 of a full group
         const int len = rest ? __ffs(rest) - 1 : 32;  // consecutive empty cells from this lane on
-        GT* dst = grid + (((long long)(g0 + u * stride) << 5) + lane) * 64;
+        GT* dst = grid + (((long long)(first_group + b_cur * U + u) << 5) + lane) * 64;
         const int first = len < kBgCells ? len : kBgCells;  // the source tile holds kBgCells cells
         bulk_store(dst, src, (unsigned)(first * 64 * sizeof(GT)), policy);
         if (len > kBgCells) bulk_store(dst + kBgCells * 64, src, (unsigned)((len - kBgCells) * 64 * sizeof(GT)), policy);
@@ -225,8 +235,18 @@ __device__ __forceinline__ void background_writer(const int* __restrict__ cell_v
     bulk_commit();
 #pragma unroll
     for (int u = 0; u < U; ++u) occ[u] = nxt[u];
+    b_cur = b_nxt;
   }
   bulk_wait_all();  // the tile must outlive every read of it; also makes the writes complete before the warp retires
+  if (lane == 0) {
+    if (pending < 0) __trap();  // (waits for the claim still in flight: none may land after the counter's reset)
+    __threadfence();
+    if (atomicAdd(claim + 1, 1) == (int)gridDim.x * kWarps - 1) {
+      claim[0] = 0;
+      claim[1] = 0;
+      __threadfence();
+    }
+  }
 }
 
 // The grid stream has just pushed everything else out of L2, and the next call's point pass starts with ~0.5 M
@@ -496,10 +516,10 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
   if (warp_in_cta < kWriterWarps) {  // ---- WRITER ----
     if (MODE == 1)
       background_writer(out.cell_voxel, out.c_empty, static_cast<float*>(out.grid), out.ncells, out.first_group,
-                        smem + OFF_BG, (int)threadIdx.x);
+                        out.writer_claim, smem + OFF_BG, (int)threadIdx.x);
     if (MODE == 2)
       background_writer(out.cell_voxel, out.c_empty, static_cast<__nv_bfloat16*>(out.grid), out.ncells,
-                        out.first_group, smem + OFF_BG, (int)threadIdx.x);
+                        out.first_group, out.writer_claim, smem + OFF_BG, (int)threadIdx.x);
     if (MODE != 0 && threadIdx.x == 0) {  // debug timeline: when this CTA's background was done
       unsigned long long* tr = g_trace;
       if (tr) {
@@ -823,7 +843,7 @@ static cudaError_t launch_vfe_dtype(const VfeSmall& p, const float* wblob, const
 
 cudaError_t launch_vfe(const VfeSmall& p, const float* wblob, const VfeProblem& prob, float* voxel_feat, int sm_count,
                        cudaStream_t st, int* launches, long long*) {
-  const VfeOutput out{voxel_feat, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0};
+  const VfeOutput out{voxel_feat, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr};
   ++*launches;
   return launch_vfe_dtype<0>(p, wblob, prob, out, sm_count, st);
 }
@@ -832,7 +852,7 @@ cudaError_t launch_vfe_to_grid(const VfeSmall& p, const float* wblob, const VfeP
                                const Geom& g, int n_sweeps, int grid_dtype, void* grid, int first_group, int sm_count,
                                cudaStream_t st, int* launches) {
   const VfeOutput out{nullptr, grid, w.voxel_cell, w.cell_voxel, w.c_empty, (long long)n_sweeps * g.cells, w.count,
-                      first_group};
+                      first_group, w.writer_claim};
   ++*launches;
   return grid_dtype == LISEC_F32 ? launch_vfe_dtype<1>(p, wblob, prob, out, sm_count, st)
                                  : launch_vfe_dtype<2>(p, wblob, prob, out, sm_count, st);
