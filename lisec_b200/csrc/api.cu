@@ -22,7 +22,7 @@ void free_workspace(Workspace& w) {
                   w.voxel_cell, w.voxel_start, w.row_start, w.tile_first, w.tile_row0, w.chunk_first, w.chunk_row0,
                   w.chunk_ntiles, w.row_voxel, w.row_xyz,
                   w.block_sums, w.sweep_voxel_start,
-                  w.totals, w.voxel_feat, w.c_empty, w.vfe_w, w.staging, w.empty_desc, w.trace, w.writer_claim};
+                  w.totals, w.voxel_feat, w.c_empty, w.vfe_w, w.staging, w.empty_desc, w.trace, w.writer_claim, w.tile_hdr};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   w = Workspace();
@@ -71,12 +71,12 @@ int do_voxelize(lisec_handle* h, const void* points, int dtype, const SweepOffse
 
 VfeProblem vfe_problem(const lisec_handle* h) {
   return VfeProblem{h->ws.tile_first, h->ws.tile_row0, h->ws.chunk_ntiles, h->ws.row_voxel, h->ws.row_xyz,
-                    h->ws.row_start,  h->ws.totals + TOT_CHUNKS, h->last_dtype};
+                    h->ws.row_start,  h->ws.totals + TOT_CHUNKS, h->last_dtype, h->ws.tile_hdr};
 }
 
 VfeProblem empty_problem(const lisec_handle* h) {
   const int* d = h->ws.empty_desc;
-  return VfeProblem{d, d + 2, d + 1, d + 8, d + 16, d + 4, reinterpret_cast<const long long*>(d + 12), LISEC_F64};
+  return VfeProblem{d, d + 2, d + 1, d + 8, d + 16, d + 4, reinterpret_cast<const long long*>(d + 12), LISEC_F64, d + 24};
 }
 
 // vfe_generic.cu's parameter block: the Keras kernels as they are, BatchNormalization folded to y = z * a + b in float32
@@ -226,6 +226,7 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
   LISEC_CUDA(h, dev_alloc(h, &w.chunk_ntiles, (size_t)h->max_chunks + 2));
   LISEC_CUDA(h, dev_alloc(h, &w.tile_first, ((size_t)h->max_chunks + 2) * kChunkSlots));
   LISEC_CUDA(h, dev_alloc(h, &w.tile_row0, ((size_t)h->max_chunks + 2) * kChunkSlots));
+  LISEC_CUDA(h, dev_alloc(h, &w.tile_hdr, ((size_t)h->max_chunks + 2) * kChunkSlots * 4));
   LISEC_CUDA(h, dev_alloc(h, &w.row_voxel, P + V));
   LISEC_CUDA(h, dev_alloc(h, reinterpret_cast<unsigned char**>(&w.row_xyz), 3 * sizeof(double) * (P + V)));
   // (v, e, r, -) per scan block and per group of kScanGroup blocks (the groups: accumulated by atomics, zero between calls)
@@ -267,11 +268,14 @@ int32_t lisec_create(const lisec_config* cfg, lisec_handle** out) {
   // the one-voxel problem whose VFE output is c_empty: 0 kept points, 1 pad row, 1 chunk of 1 tile. Layout (ints; the
   // arrays the kernel copies with 16-byte cp.async start on 16-byte boundaries):
   //   [0..1] tile_first {0,1} ([1] doubles as chunk_ntiles {1}) | [2..3] tile_row0 {0,1} | [4..5] row_start {0,1} |
-  //   [8] row_voxel {0 | pad flag} | [12..13] n_chunks (int64) 1 | [16..21] row_xyz: 3 doubles (unused: a pad row)
+  //   [8] row_voxel {0 | pad flag} | [12..13] n_chunks (int64) 1 | [16..21] row_xyz: 3 doubles (unused: a pad row) |
+  //   [24..27] tile_hdr {0, 1, 0, 1}
   int desc[32] = {0};
   desc[1] = 1;
   desc[3] = 1;
   desc[5] = 1;
+  desc[25] = 1;
+  desc[27] = 1;
   desc[8] = kRowPadFlag;
   const long long one = 1;
   std::memcpy(&desc[12], &one, sizeof(one));

@@ -88,6 +88,7 @@ struct Workspace {
   // per VFE row, [max_points + max_voxels]: what the VFE kernel needs to start a tile with one coalesced read
   int* row_voxel = nullptr;    // voxel row the VFE row belongs to (| kRowPadFlag for the virtual pad row)
   void* row_xyz = nullptr;     // [rows][3] the point of every VFE row in the input dtype (unwritten for pad rows)
+  int* tile_hdr = nullptr;     // [max_chunks][kChunkSlots][4] (first voxel, end voxel, first row, end row) of each tile
   int* tile_row0 = nullptr;    // [max_chunks][kChunkSlots] first VFE row of each tile
   int* writer_claim = nullptr; // [2] the fused kernel's background writers: next batch of cells, finished warps (vfe.cu)
   int* block_sums = nullptr;   // [cap][4] (voxels, entries, rows, -) of each scan block | [cap / kScanGroup + 1][4] of each group of blocks
@@ -124,6 +125,8 @@ struct VfeProblem {
   const int* row_start;    // [voxels + 1] first VFE row of each voxel
   const long long* n_chunks;
   int pts_dtype;
+  const int* tile_hdr;     // [n_chunks][kChunkSlots][4] the same tiles as (first voxel, end voxel, first row, end row): ONE
+                           // 16-byte-aligned record per tile, which vfe_kernel's walkers fetch with an asynchronous copy
 };
 cudaError_t launch_vfe(const VfeSmall& p, const float* wblob, const VfeProblem& prob,
                        float* voxel_feat, int sm_count, cudaStream_t st, int* launches, long long* prof = nullptr);

@@ -569,17 +569,17 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
   const bool walker = ttid == kTeamThreads - 1;
   TileCursor cursor;
   if (walker) cursor.init(prob, n_chunks, team);
-  auto publish_header = [&](int k) {  // walker only: header of the team's tile k -> ring slot k & 3
-    int4 h = make_int4(0, 0, 0, 0);
+  // walker only: header of the team's tile k -> ring slot k & 3, by an ASYNCHRONOUS 16-byte copy of the tile's record
+  // (tile_hdr, written by the tile plan). With four loads and a store the walker waited a whole L2 round trip here at the
+  // top of every tile — 2-3 us beside the grid stream — and its team for it at the next barrier; the copy lands with the
+  // team's other cp.async traffic (same commit group, waited for at the end of the iteration, a tile before it is read).
+  auto publish_header = [&](int k) {
     if (cursor.c < n_chunks) {
-      const int t = cursor.c * kChunkSlots + cursor.j;
-      h.x = __ldcg(prob.tile_first + t);
-      h.y = __ldcg(prob.tile_first + t + 1);
-      h.z = __ldcg(prob.tile_row0 + t);
-      h.w = __ldcg(prob.tile_row0 + t + 1);
+      cp_async16(&hdr_ring[k & 3], reinterpret_cast<const int4*>(prob.tile_hdr) + (cursor.c * kChunkSlots + cursor.j));
       cursor.advance(prob, n_chunks, 2);
+    } else {
+      hdr_ring[k & 3] = make_int4(0, 0, 0, 0);
     }
-    hdr_ring[k & 3] = h;
   };
   auto read_header = [&](int k) {
     const int4 h = hdr_ring[k & 3];
@@ -601,6 +601,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1)
   if (walker) {
     publish_header(0);
     publish_header(1);
+    cp_async_commit();
+    cp_async_wait_all();  // the first two are needed at once
   }
   team_sync(team);
   if (n_mine > 0) prefetch(read_header(0), 0);

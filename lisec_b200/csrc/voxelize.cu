@@ -368,7 +368,8 @@ constexpr int kPlanVox = kVfeChunkRows / 2 + 4;  // row offsets of a chunk: <= k
 __device__ __forceinline__ void plan_chunk_tiles(long long c, int lane, int* rs, const int* __restrict__ chunk_first,
                                                  const int* __restrict__ row_start,
                                                  const long long* __restrict__ totals, int* __restrict__ tile_first,
-                                                 int* __restrict__ tile_row0, int* __restrict__ chunk_ntiles) {
+                                                 int* __restrict__ tile_row0, int* __restrict__ chunk_ntiles,
+                                                 int* __restrict__ tile_hdr) {
   // (everything read here was written by scan_down under programmatic dependent launch: ld.global.cg, never through L1
   // — a plain load here returned lines of the PREVIOUS call's tables: tools/check_tables.py)
   const long long n_chunks = __ldcg(totals + TOT_CHUNKS);
@@ -391,6 +392,8 @@ __device__ __forceinline__ void plan_chunk_tiles(long long c, int lane, int* rs,
     if (lane == 0) {
       tf[j] = v0 + b;
       tr[j] = base;
+      // the tile as one 16-byte record (first voxel, end voxel, first row, end row) for the VFE kernel's walkers
+      reinterpret_cast<int4*>(tile_hdr)[c * kChunkSlots + j] = make_int4(v0 + b, v0 + b + fit, base, rs[b + fit]);
     }
     b += fit;  // fit >= 1: one voxel always fits
     ++j;
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(256) fill_pass_kernel(const int* __restrict__ 
                                                         const int* __restrict__ row_start,
                                                         const long long* __restrict__ totals,
                                                         int* __restrict__ tile_first, int* __restrict__ tile_row0,
-                                                        int* __restrict__ chunk_ntiles) {
+                                                        int* __restrict__ chunk_ntiles, int* __restrict__ tile_hdr) {
   __shared__ int s_rs[8][kPlanVox];
   pdl_launch_dependents();
   pdl_wait();
@@ -419,7 +422,7 @@ __global__ void __launch_bounds__(256) fill_pass_kernel(const int* __restrict__ 
   if (blockIdx.x >= fill_blocks) {  // the tile plan's blocks: 8 chunks each
     const int wib = threadIdx.x >> 5;
     plan_chunk_tiles((long long)(blockIdx.x - fill_blocks) * 8 + wib, lane_id(), s_rs[wib], chunk_first, row_start, totals,
-                     tile_first, tile_row0, chunk_ntiles);
+                     tile_first, tile_row0, chunk_ntiles, tile_hdr);
     return;
   }
   const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -587,7 +590,7 @@ cudaError_t launch_fill_and_order(const void* pts, int pts_dtype, long long n_to
   cudaError_t err = launch_pdl(fill_pass_kernel, fill_blocks + plan_blocks, 256, 0, st, (const int*)w.cell_of_point, n_total,
                                (const int*)w.cell_voxel, (const int*)w.voxel_start, w.count, w.list_unsorted,
                                w.entry_voxel, fill_blocks, (const int*)w.chunk_first, (const int*)w.row_start,
-                               (const long long*)w.totals, w.tile_first, w.tile_row0, w.chunk_ntiles);
+                               (const long long*)w.totals, w.tile_first, w.tile_row0, w.chunk_ntiles, w.tile_hdr);
   // entries <= points; threads beyond the device-side totals exit
   if (err == cudaSuccess) {
     const unsigned blocks = (unsigned)((n_total + 255) / 256);
