@@ -254,8 +254,17 @@ def run_native(args):
     points_bytes = SWEEPS_PER_GPU * POINTS_PER_SWEEP * 12
     grid_bytes = grid.numel() * grid.element_size()
 
+    # The timed loop hands the front end the same 14 device buffers again and again, so it asks for CUDA-graph replay
+    # (Frontend.forward(graph=True): the second call with a buffer captures the step's six kernels, later calls replay
+    # them); step_eager() launches the kernels one by one — the pass that reads the fused kernel's own CUDA events.
     def step(i):
+        fe.forward(dev_batches[i % N_BATCHES], offsets, out=grid, graph=True)
+
+    def step_eager(i):
         fe.forward(dev_batches[i % N_BATCHES], offsets, out=grid)
+
+    for i in range(2 * N_BATCHES):  # every buffer seen twice: all graphs exist before anything is timed
+        step(i)
 
     # end to end: host (pinned) points in, per-sweep voxel counts out. The library copies on its own stream into
     # alternating staging buffers, so the H2D copy of step i+1 overlaps the kernels of step i; the totals of step i
@@ -298,7 +307,7 @@ def run_native(args):
     # steps (reading the events synchronises, so this pass is not the timed one): the AVERAGE over all of them
     k_ms = []
     for i in range(args.steps):
-        step(i)
+        step_eager(i)
         k_ms.append(fe.last_fused_kernel_ms)
     ms_kernel = float(np.mean(k_ms))
 
@@ -710,7 +719,10 @@ def run_native(args):
             "config": {"workload": WORKLOAD, "sweeps_per_gpu": SWEEPS_PER_GPU, "points_per_sweep": POINTS_PER_SWEEP,
                        "parallelism": "sweeps sharded over %d GPU(s), no data-path collective" % world,
                        "l2": "1.31 GB grid written per step (10x L2); inputs rotate over %d distinct batches "
-                             "(%d MB > L2)" % (N_BATCHES, N_BATCHES * points_bytes // 2**20)},
+                             "(%d MB > L2)" % (N_BATCHES, N_BATCHES * points_bytes // 2**20),
+                       "launch": "the timed loop replays one CUDA graph per input buffer (Frontend.forward(graph=True): the "
+                                 "step's 6 kernels, captured on a buffer's second use); e2e, the kernel-timing pass and "
+                                 "every other leg launch eagerly"},
             "points_per_s": value * POINTS_PER_SWEEP,
             "voxels_per_step": int(n_vox), "points_in_range_per_step": int(n_in),
             "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": points_bytes,

@@ -92,9 +92,11 @@ class Frontend:
             raise N.LisecError(st, msg)
         self._keep = None  # device tensors the last voxelize() refers to
         self._n_sweeps = 0
+        self._graphs = {}  # forward(graph=True): (points ptr, dtype, offsets, grid ptr) -> [calls seen, CUDAGraph, tensors]
 
     # ---- lifetime ----------------------------------------------------------------------------------------
     def close(self) -> None:
+        self._graphs = {}
         if getattr(self, "_h", None) and self._h:
             self._lib.lisec_destroy(self._h)
             self._h = C.c_void_p()
@@ -263,13 +265,35 @@ class Frontend:
         return out
 
     def forward(self, points: ArrayLike, sweep_offsets: Optional[Sequence[int]] = None,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """points already on the device -> dense grid [n_sweeps,nz,nx,ny,c3]; no host round trip."""
+                out: Optional[torch.Tensor] = None, graph: bool = False) -> torch.Tensor:
+        """points already on the device -> dense grid [n_sweeps,nz,nx,ny,c3]; no host round trip.
+
+        graph=True: for callers that hand in the SAME device buffers again and again (a staging buffer, a ring of them):
+        the second call with one (points buffer, offsets, grid buffer) captures the step's six kernels into a CUDA graph,
+        later calls replay it — the same kernels on the same buffers, with the GPU's launch work done once (a step of 8 x
+        100 k points: 0.338 -> 0.327 ms, tools/graph_probe.py). The kernels keep no host-side state between calls (every
+        counter is put back by the kernels themselves), which is what makes the replay legal
+        (tests/test_gpu_call_state.py). The buffers' CONTENTS may change between calls, their addresses and the offsets may not."""
         pts = self._device_points(points)
         off = _offsets([0, pts.shape[0]] if sweep_offsets is None else sweep_offsets)
         n = len(off) - 1
         if out is None:
             out = self.new_grid(n)
+        if graph:
+            key = (pts.data_ptr(), pts.dtype, off.tobytes(), out.data_ptr())
+            entry = self._graphs.setdefault(key, [0, None, (pts, out)])
+            entry[0] += 1
+            if entry[1] is None and entry[0] == 2:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.device(self.device), torch.cuda.graph(g):
+                    self.forward(pts, off, out=out)
+                entry[1] = g
+            if entry[1] is not None:
+                with torch.cuda.device(self.device):
+                    entry[1].replay()
+                self._keep = pts
+                self._n_sweeps = n
+                return out
         with torch.cuda.device(self.device):
             self._check(
                 self._lib.lisec_frontend_forward(self._h, _ptr(pts), self._dtype_code(pts.dtype),
