@@ -285,7 +285,8 @@ class Frontend:
             entry[0] += 1
             if entry[1] is None and entry[0] == 2:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.device(self.device), torch.cuda.graph(g):
+                # (thread-local capture mode: other threads of the process — an NCCL watchdog — may call CUDA meanwhile)
+                with torch.cuda.device(self.device), torch.cuda.graph(g, capture_error_mode="thread_local"):
                     self.forward(pts, off, out=out)
                 entry[1] = g
             if entry[1] is not None:
